@@ -1,0 +1,161 @@
+/*
+ * b200sep.h -- C ABI of the B200-native stem-separation hot path (libb200sep.so, sm_100a only).
+ *
+ * The reference (nomadkaraoke/python-audio-separator v0.44.1) is pure Python; its hot path calls into
+ * third-party wheels (ATen FFT/conv, onnxruntime).  This header is the FFI a maintainer would bind in place
+ * of those calls (ctypes stub: INTEGRATION.md).  Each entry point cites the reference interface it replaces
+ * (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; sizes are element counts;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls are asynchronous;
+ *   - return value: 0 = ok, negative = error (b200sep_last_error() gives the text, thread-local);
+ *   - no exceptions, no torch types, no ownership transfer except b200sep_*_create / _destroy handles;
+ *   - there is no CPU fallback: without a CUDA device every compute entry point returns B200SEP_ERR_CUDA.
+ */
+#ifndef B200SEP_H
+#define B200SEP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SEP_OK 0
+#define B200SEP_ERR_ARG (-1)     /* bad argument / unsupported shape */
+#define B200SEP_ERR_CUDA (-2)    /* CUDA runtime error (launch, alloc, no device) */
+#define B200SEP_ERR_STATE (-3)   /* handle used before it was fully initialised */
+
+#define B200SEP_ABI_VERSION 1
+
+/* spectrogram memory layouts */
+#define B200SEP_LAYOUT_CFT 0 /* (B, 2C, dim_f, frames): the reference's STFT.__call__ layout (uvr_lib_v5/stft.py:44-56) */
+#define B200SEP_LAYOUT_CTF 1 /* (B, 2C, frames, dim_f): what ConvTDFNet computes on after transpose(-1,-2) (uvr_lib_v5/mdxnet.py:101) */
+
+int b200sep_abi_version(void);
+const char* b200sep_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches evidence) */
+uint64_t b200sep_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * STFT plan: twiddle / window tables for one (n_fft, hop) pair.  n_fft must factor into {2,3,5}.
+ * Replaces STFT.__init__ (uvr_lib_v5/stft.py:11-18).
+ */
+typedef struct b200sep_stft_plan b200sep_stft_plan;
+int b200sep_stft_plan_create(b200sep_stft_plan** plan, int n_fft, int hop);
+void b200sep_stft_plan_destroy(b200sep_stft_plan* plan);
+
+/*
+ * Forward STFT of `batch` stereo chunks.  Replaces STFT.__call__ (uvr_lib_v5/stft.py:20-56): periodic Hann,
+ * center=True with reflect padding of n_fft/2, one-sided, un-normalised, planes [L_re, L_im, R_re, R_im],
+ * frequency axis cropped to dim_f; bins [0, zero_bins) are written as 0 (fuses `spek[:, :, :3, :] *= 0`,
+ * architectures/mdx_separator.py:425).
+ *
+ * Chunk b, channel c, sample n is read from  wave[b*batch_stride + c*chan_stride + n]  when valid_len <= 0 or
+ * b*batch_stride + n < valid_len, and is 0 otherwise (fuses the right zero-padding of the short last chunk,
+ * mdx_separator.py:363-366).  Two addressings are used:
+ *   - a contiguous (B,2,T) tensor:            batch_stride = 2T,   chan_stride = T, valid_len = 0 (unlimited);
+ *   - chunks cut out of a padded (2,L) mixture: batch_stride = step, chan_stride = L, valid_len = L - offset of `wave`.
+ * `chunk_len` = T must be a multiple of hop and > n_fft/2; frames = T/hop + 1.
+ * spec: layout CFT or CTF, float32, batch*4*dim_f*frames elements.
+ */
+int b200sep_stft_forward(const b200sep_stft_plan* plan, const float* wave, int64_t batch_stride, int64_t chan_stride,
+                         int64_t valid_len, int batch, int chunk_len, int dim_f, int zero_bins, int layout,
+                         float* spec, void* stream);
+
+/*
+ * Inverse STFT.  Replaces STFT.inverse (uvr_lib_v5/stft.py:99-126): bins dim_f..n_fft/2 zero-filled, complex
+ * irfft per frame, Hann window, overlap-add at hop, division by the overlap-added squared window, n_fft/2
+ * trimmed from both ends.  spec (B,4,dim_f,frames) [CFT] or (B,4,frames,dim_f) [CTF] -> wave (B,2,hop*(frames-1)).
+ * `work` must hold b200sep_stft_inverse_work_floats(...) floats.
+ */
+int64_t b200sep_stft_inverse_work_floats(const b200sep_stft_plan* plan, int batch, int frames, int dim_f, int layout);
+int b200sep_stft_inverse(const b200sep_stft_plan* plan, const float* spec, int batch, int frames, int dim_f, int layout,
+                         float* wave, float* work, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Windowed overlap-add of the per-chunk outputs.  Replaces the accumulation loop + divide + trim of
+ * MDXSeparator.demix (architectures/mdx_separator.py:339-340, :348-401):
+ *
+ *   result[:, s_i : e_i] += y_i[:, :e_i-s_i] * hanning(e_i - s_i);  divider[...] += hanning(e_i - s_i)
+ *   out = (result / divider)[:, trim : trim + n_out] * out_scale
+ *
+ * with s_i = i*step, e_i = min(s_i + chunk_len, total_len), written as a deterministic gather (each output
+ * sample sums its <= ceil(chunk/step) covering chunks in chunk order).  use_window=0 reproduces overlap==0
+ * (divider += 1).  chunks: (n_chunks, 2, chunk_len) float32; out: (2, n_out) float32.
+ * If mix != NULL (2, n_out), also writes secondary = mix - compensate * out  (mdx_separator.py:182),
+ * both as (n_out, 2) interleaved when interleave != 0 (the `.T` of mdx_separator.py:163) else (2, n_out).
+ */
+int b200sep_demix_overlap_add(const float* chunks, int n_chunks, int chunk_len, int64_t step, int64_t total_len,
+                              int64_t trim, int64_t n_out, int use_window, float out_scale, const float* mix,
+                              float compensate, int interleave, float* primary, float* secondary, void* stream);
+
+/* max |x| over n floats -> *result (device float).  (np.abs(mix).max(), mdx_separator.py:155; spec_utils.py:110) */
+int b200sep_absmax(const float* x, int64_t n, float* result, void* stream);
+/* y = x * s where s = max_peak/absmax if absmax > max_peak; min_peak/absmax if min_peak>=0 and absmax < min_peak;
+ * else 1 (spec_utils.normalize, uvr_lib_v5/spec_utils.py:99-115).  absmax is a device scalar. */
+int b200sep_normalize(const float* x, int64_t n, const float* absmax, float max_peak, float min_peak, float* y, void* stream);
+/* (x*32767) truncated toward zero to int16 (common_separator.py:331); x is (n,) float32 */
+int b200sep_to_pcm16(const float* x, int64_t n, int16_t* y, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * ConvTDFNet (the graph inside UVR-MDX-NET-*.onnx; topology: uvr_lib_v5/mdxnet.py:30-120, modules.py:1-74).
+ * Replaces `self.model_run(spek)` = ort.InferenceSession.run (architectures/mdx_separator.py:122-123, :443).
+ *
+ * The host passes the raw parameters in the reference module's state_dict order (see
+ * b200sep_mdxnet_param_count / the Python loader); BatchNorm folding, weight re-layout and the bf16 hi/lo
+ * split for the tensor-core path happen once at create time on the device.
+ */
+typedef struct b200sep_mdxnet b200sep_mdxnet;
+typedef struct {
+  int32_t dim_c;      /* 4 */
+  int32_t dim_f;      /* 3072 */
+  int32_t dim_t;      /* 256 */
+  int32_t num_blocks; /* 11 */
+  int32_t l;          /* 3 convs per TFC */
+  int32_t g;          /* 48 growth */
+  int32_t k;          /* 3 */
+  int32_t bn;         /* 8 TDF bottleneck factor */
+  int32_t max_batch;  /* chunks per forward the workspace is sized for */
+  int32_t precision;  /* 0 = fp32 SIMT everywhere; 1 = bf16x3 split tcgen05 where profitable */
+} b200sep_mdxnet_config;
+
+/* number of float parameters expected in `params_host` for this config */
+int64_t b200sep_mdxnet_param_count(const b200sep_mdxnet_config* cfg);
+int b200sep_mdxnet_create(b200sep_mdxnet** net, const b200sep_mdxnet_config* cfg, const float* params_host, int64_t n_params);
+void b200sep_mdxnet_destroy(b200sep_mdxnet* net);
+/* bytes of device memory held by the handle (weights + activation workspace) */
+int64_t b200sep_mdxnet_device_bytes(const b200sep_mdxnet* net);
+/*
+ * Forward: spec_in (B,4,dim_t,dim_f) [CTF] or (B,4,dim_f,dim_t) [CFT] float32 -> spec_out, same shape/layout.
+ * batch <= max_batch.
+ */
+int b200sep_mdxnet_forward(b200sep_mdxnet* net, const float* spec_in, float* spec_out, int batch, int layout, void* stream);
+
+/*
+ * Optional device-side timing of the forward, by kernel category (measurement only; bench.py's roofline).
+ * enable!=0 clears the records and makes every subsequent forward record a CUDA-event pair around each launch on
+ * the caller's stream; _read synchronises on those events and returns, per category, the summed device time,
+ * launch count and the ALGORITHMIC flops (2*MAC, unpadded) and bytes (inputs + outputs + weights, fp32) of the
+ * launches recorded.  Returns the number of categories (names via _profile_name).
+ */
+int b200sep_mdxnet_profile_enable(b200sep_mdxnet* net, int enable);
+int b200sep_mdxnet_profile_read(b200sep_mdxnet* net, int max_categories, float* ms, int64_t* launches, double* flops, double* bytes);
+const char* b200sep_mdxnet_profile_name(int category);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Whole-chunk operator: STFT -> zero bins -> net (optionally denoise: 0.5*f(x) - 0.5*f(-x)) -> iSTFT.
+ * Replaces MDXSeparator.run_model (architectures/mdx_separator.py:414-450) for `batch` chunks whose samples
+ * are read straight out of the padded mixture (see b200sep_stft_forward addressing).
+ * net == NULL reproduces is_match_mix=True (mdx_separator.py:429-432).  wave_out: (batch, 2, chunk_len).
+ */
+int64_t b200sep_mdx_run_model_work_floats(const b200sep_stft_plan* plan, int batch, int chunk_len, int dim_f);
+int b200sep_mdx_run_model(const b200sep_stft_plan* plan, b200sep_mdxnet* net, const float* wave, int64_t batch_stride,
+                          int64_t chan_stride, int64_t valid_len, int batch, int chunk_len, int dim_f, int denoise,
+                          float* wave_out, float* work, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SEP_H */

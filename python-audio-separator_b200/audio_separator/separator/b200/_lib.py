@@ -1,0 +1,73 @@
+"""ctypes binding of the C-ABI library (include/b200sep.h).  This is the stub a reference maintainer would add.
+
+There is NO fallback: if libb200sep.so is missing or fails to load, importing this module raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PKG_ROOT = os.path.abspath(os.path.join(_HERE, "..", "..", ".."))  # python-audio-separator_b200/
+LIB_PATH = os.environ.get("B200SEP_LIB", os.path.join(_PKG_ROOT, "libb200sep.so"))
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"libb200sep.so not found at {LIB_PATH}: build it with `python python-audio-separator_b200/build.py` "
+        "(the B200 engine has no CPU / PyTorch fallback)"
+    )
+lib = C.CDLL(LIB_PATH)
+
+LAYOUT_CFT = 0
+LAYOUT_CTF = 1
+
+i32, i64, f32, vp = C.c_int, C.c_int64, C.c_float, C.c_void_p
+
+
+class MdxNetConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("dim_c", "dim_f", "dim_t", "num_blocks", "l", "g", "k", "bn", "max_batch", "precision")]
+
+
+_SIGS = {
+    "b200sep_abi_version": (i32, []),
+    "b200sep_last_error": (C.c_char_p, []),
+    "b200sep_launch_count": (C.c_uint64, []),
+    "b200sep_stft_plan_create": (i32, [C.POINTER(vp), i32, i32]),
+    "b200sep_stft_plan_destroy": (None, [vp]),
+    "b200sep_stft_forward": (i32, [vp, vp, i64, i64, i64, i32, i32, i32, i32, i32, vp, vp]),
+    "b200sep_stft_inverse_work_floats": (i64, [vp, i32, i32, i32, i32]),
+    "b200sep_stft_inverse": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp]),
+    "b200sep_demix_overlap_add": (i32, [vp, i32, i32, i64, i64, i64, i64, i32, f32, vp, f32, i32, vp, vp, vp]),
+    "b200sep_absmax": (i32, [vp, i64, vp, vp]),
+    "b200sep_normalize": (i32, [vp, i64, vp, f32, f32, vp, vp]),
+    "b200sep_to_pcm16": (i32, [vp, i64, vp, vp]),
+    "b200sep_mdxnet_param_count": (i64, [C.POINTER(MdxNetConfig)]),
+    "b200sep_mdxnet_create": (i32, [C.POINTER(vp), C.POINTER(MdxNetConfig), vp, i64]),
+    "b200sep_mdxnet_destroy": (None, [vp]),
+    "b200sep_mdxnet_device_bytes": (i64, [vp]),
+    "b200sep_mdxnet_forward": (i32, [vp, vp, vp, i32, i32, vp]),
+    "b200sep_mdxnet_profile_enable": (i32, [vp, i32]),
+    "b200sep_mdxnet_profile_read": (i32, [vp, i32, vp, vp, vp, vp]),
+    "b200sep_mdxnet_profile_name": (C.c_char_p, [i32]),
+    "b200sep_mdx_run_model_work_floats": (i64, [vp, i32, i32, i32]),
+    "b200sep_mdx_run_model": (i32, [vp, vp, vp, i64, i64, i64, i32, i32, i32, i32, vp, vp, vp]),
+}
+EXPORTED = tuple(_SIGS)
+for _name, (_res, _args) in _SIGS.items():
+    _fn = getattr(lib, _name)  # AttributeError here = the library does not export a declared symbol
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+if lib.b200sep_abi_version() != 1:
+    raise ImportError("libb200sep.so ABI version mismatch")
+
+
+class B200SepError(RuntimeError):
+    pass
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise B200SepError(f"{what} failed (rc={rc}): {lib.b200sep_last_error().decode(errors='replace')}")
+
+
+def launch_count() -> int:
+    return int(lib.b200sep_launch_count())

@@ -1,0 +1,246 @@
+"""Python handles over the C-ABI engine (libb200sep.so).  PyTorch is used only for device memory and streams.
+
+MdxEngine is the device-resident replacement of the reference's per-chunk loop
+(architectures/mdx_separator.py:293-450): the padded mixture, every chunk's spectrogram, the network
+activations, the iSTFT frames and the overlap-add accumulators all stay in HBM; the host sees one upload of the
+mix and one download of the stems.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import LAYOUT_CFT, LAYOUT_CTF, check, lib
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("the B200 engine needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def _ptr(t: torch.Tensor) -> int:
+    assert t.is_cuda and t.is_contiguous(), "engine buffers must be contiguous CUDA tensors"
+    return t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class StftPlan:
+    """b200sep_stft_plan handle (replaces STFT.__init__, uvr_lib_v5/stft.py:11-18)."""
+
+    def __init__(self, n_fft: int, hop: int):
+        _require_cuda()
+        self.n_fft, self.hop = int(n_fft), int(hop)
+        h = C.c_void_p()
+        check(lib.b200sep_stft_plan_create(C.byref(h), self.n_fft, self.hop), "stft_plan_create")
+        self.handle = h
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            lib.b200sep_stft_plan_destroy(h)
+            self.handle = None
+
+    def forward(self, wave: torch.Tensor, dim_f: int, zero_bins: int = 0, layout: int = LAYOUT_CFT) -> torch.Tensor:
+        """wave (B,2,T) float32 cuda -> (B,4,dim_f,frames) [CFT] or (B,4,frames,dim_f) [CTF]."""
+        assert wave.dim() == 3 and wave.shape[1] == 2 and wave.dtype == torch.float32
+        wave = wave.contiguous()
+        B, _, T = wave.shape
+        frames = T // self.hop + 1
+        shape = (B, 4, dim_f, frames) if layout == LAYOUT_CFT else (B, 4, frames, dim_f)
+        spec = torch.empty(shape, dtype=torch.float32, device=wave.device)
+        check(lib.b200sep_stft_forward(self.handle, _ptr(wave), 2 * T, T, 0, B, T, dim_f, zero_bins, layout, _ptr(spec), _stream()), "stft_forward")
+        return spec
+
+    def inverse(self, spec: torch.Tensor, layout: int = LAYOUT_CFT) -> torch.Tensor:
+        """spec (B,4,dim_f,frames) [CFT] / (B,4,frames,dim_f) [CTF] -> wave (B,2,hop*(frames-1))."""
+        assert spec.dim() == 4 and spec.shape[1] == 4 and spec.dtype == torch.float32
+        spec = spec.contiguous()
+        B = spec.shape[0]
+        dim_f, frames = (spec.shape[2], spec.shape[3]) if layout == LAYOUT_CFT else (spec.shape[3], spec.shape[2])
+        wave = torch.empty((B, 2, self.hop * (frames - 1)), dtype=torch.float32, device=spec.device)
+        nwork = lib.b200sep_stft_inverse_work_floats(self.handle, B, frames, dim_f, layout)
+        work = torch.empty(nwork, dtype=torch.float32, device=spec.device)
+        check(lib.b200sep_stft_inverse(self.handle, _ptr(spec), B, frames, dim_f, layout, _ptr(wave), _ptr(work), _stream()), "stft_inverse")
+        return wave
+
+
+class MdxNet:
+    """b200sep_mdxnet handle: ConvTDFNet weights + activation arena on the device."""
+
+    def __init__(self, params_flat: np.ndarray, dim_c, dim_f, dim_t, num_blocks, l, g, k, bn, max_batch=1, precision=0):
+        _require_cuda()
+        self.cfg = _lib.MdxNetConfig(dim_c, dim_f, dim_t, num_blocks, l, g, k, bn, max_batch, precision)
+        params_flat = np.ascontiguousarray(params_flat, dtype=np.float32)
+        expect = lib.b200sep_mdxnet_param_count(C.byref(self.cfg))
+        if expect != params_flat.size:
+            raise ValueError(f"ConvTDFNet config expects {expect} parameters, blob has {params_flat.size}")
+        h = C.c_void_p()
+        check(lib.b200sep_mdxnet_create(C.byref(h), C.byref(self.cfg), params_flat.ctypes.data_as(C.c_void_p), params_flat.size), "mdxnet_create")
+        self.handle = h
+        self.max_batch = max_batch
+        self.dim_c, self.dim_f, self.dim_t = dim_c, dim_f, dim_t
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            lib.b200sep_mdxnet_destroy(h)
+            self.handle = None
+
+    @property
+    def device_bytes(self) -> int:
+        return int(lib.b200sep_mdxnet_device_bytes(self.handle))
+
+    def profile(self, enable: bool):
+        check(lib.b200sep_mdxnet_profile_enable(self.handle, int(enable)), "mdxnet_profile_enable")
+
+    def profile_read(self) -> dict:
+        """{category: {"ms", "launches", "flops", "bytes"}} summed over the forwards since profile(True)."""
+        n = 8
+        ms, ln, fl, by = (C.c_float * n)(), (C.c_int64 * n)(), (C.c_double * n)(), (C.c_double * n)()
+        k = lib.b200sep_mdxnet_profile_read(self.handle, n, ms, ln, fl, by)
+        if k < 0:
+            check(k, "mdxnet_profile_read")
+        return {lib.b200sep_mdxnet_profile_name(i).decode(): {"ms": float(ms[i]), "launches": int(ln[i]), "flops": float(fl[i]), "bytes": float(by[i])} for i in range(k)}
+
+    def forward(self, spec: torch.Tensor, layout: int = LAYOUT_CFT) -> torch.Tensor:
+        """spec (B,4,dim_f,dim_t) [CFT, the ONNX graph's input layout] or (B,4,dim_t,dim_f) [CTF] -> same shape."""
+        spec = spec.contiguous()
+        want = (self.dim_c, self.dim_f, self.dim_t) if layout == LAYOUT_CFT else (self.dim_c, self.dim_t, self.dim_f)
+        if tuple(spec.shape[1:]) != want or spec.dtype != torch.float32:
+            raise ValueError(f"ConvTDFNet input must be float32 (B,{want}), got {tuple(spec.shape)} {spec.dtype}")
+        out = torch.empty_like(spec)
+        B = spec.shape[0]
+        for b0 in range(0, B, self.max_batch):
+            nb = min(self.max_batch, B - b0)
+            check(lib.b200sep_mdxnet_forward(self.handle, _ptr(spec[b0 : b0 + nb]), _ptr(out[b0 : b0 + nb]), nb, layout, _stream()), "mdxnet_forward")
+        return out
+
+
+class MdxEngine:
+    """Device-resident MDX separation: chunk grid, run_model batches, windowed overlap-add, stem arithmetic."""
+
+    def __init__(self, net: MdxNet | None, n_fft, hop_length, dim_f, segment_size, overlap, compensate=1.0, enable_denoise=False, batch_size=None):
+        _require_cuda()
+        self.net = net
+        self.n_fft, self.hop, self.dim_f = int(n_fft), int(hop_length), int(dim_f)
+        self.segment_size = int(segment_size)
+        self.overlap = float(overlap)
+        self.compensate = float(compensate)
+        self.enable_denoise = bool(enable_denoise)
+        self.trim = self.n_fft // 2  # mdx_separator.py:217
+        self.chunk_size = self.hop * (self.segment_size - 1)  # :220
+        self.gen_size = self.chunk_size - 2 * self.trim  # :223
+        self.plan = StftPlan(self.n_fft, self.hop)
+        self.batch = int(batch_size or (net.max_batch if net is not None else 8))
+        if net is not None:
+            self.batch = min(self.batch, net.max_batch)
+        self._work = None
+        self.device = torch.device("cuda", torch.cuda.current_device())
+
+    # ---- chunk grid (mdx_separator.py:307-348)
+    def grid(self, n_samples: int, is_match_mix=False):
+        overlap = 0.02 if is_match_mix else self.overlap
+        gen = self.chunk_size - 2 * self.trim
+        pad = gen + self.trim - (n_samples % gen)
+        L = self.trim + n_samples + pad
+        step = int((1 - overlap) * self.chunk_size)
+        n_chunks = (L + step - 1) // step
+        return L, step, n_chunks, overlap
+
+    def _workspace(self, batch):
+        need = lib.b200sep_mdx_run_model_work_floats(self.plan.handle, batch, self.chunk_size, self.dim_f)
+        if self._work is None or self._work.numel() < need:
+            self._work = torch.empty(need, dtype=torch.float32, device=self.device)
+        return self._work
+
+    def run_model(self, mix: torch.Tensor, is_match_mix=False) -> torch.Tensor:
+        """MDXSeparator.run_model (mdx_separator.py:414-450) on a contiguous (B,2,chunk) CUDA tensor."""
+        mix = mix.contiguous()
+        B, _, T = mix.shape
+        assert T == self.chunk_size, (T, self.chunk_size)
+        out = torch.empty_like(mix)
+        net = None if is_match_mix else self.net.handle
+        for b0 in range(0, B, self.batch):
+            nb = min(self.batch, B - b0)
+            work = self._workspace(nb)
+            check(
+                lib.b200sep_mdx_run_model(self.plan.handle, net, _ptr(mix[b0 : b0 + nb]), 2 * T, T, 0, nb, T, self.dim_f, int(self.enable_denoise), _ptr(out[b0 : b0 + nb]), _ptr(work), _stream()),
+                "mdx_run_model",
+            )
+        return out
+
+    def demix_device(self, mix_dev: torch.Tensor, is_match_mix=False, out_scale=1.0, with_secondary=False, interleave=False):
+        """MDXSeparator.demix (mdx_separator.py:293-412) with everything resident in HBM.
+
+        mix_dev: (2,N) float32 CUDA (already peak-normalised by the caller).  Returns primary (2,N) [or (N,2) when
+        interleave] and, with_secondary, secondary = mix - compensate*primary (mdx_separator.py:182).
+        """
+        assert mix_dev.is_cuda and mix_dev.dtype == torch.float32 and mix_dev.shape[0] == 2
+        mix_dev = mix_dev.contiguous()
+        N = mix_dev.shape[1]
+        L, step, n_chunks, overlap = self.grid(N, is_match_mix)
+        T = self.chunk_size
+        mixture = torch.zeros((2, L), dtype=torch.float32, device=self.device)  # [0]*trim + mix + [0]*pad, :329
+        mixture[:, self.trim : self.trim + N] = mix_dev
+        chunks = torch.empty((n_chunks, 2, T), dtype=torch.float32, device=self.device)
+        net = None if is_match_mix else self.net.handle
+        esz = 4
+        for b0 in range(0, n_chunks, self.batch):
+            nb = min(self.batch, n_chunks - b0)
+            work = self._workspace(nb)
+            check(
+                lib.b200sep_mdx_run_model(
+                    self.plan.handle, net, mixture.data_ptr() + b0 * step * esz, step, L, L - b0 * step, nb, T, self.dim_f, int(self.enable_denoise), _ptr(chunks[b0 : b0 + nb]), _ptr(work), _stream()
+                ),
+                "mdx_run_model",
+            )
+        shape = (N, 2) if interleave else (2, N)
+        primary = torch.empty(shape, dtype=torch.float32, device=self.device)
+        secondary = torch.empty(shape, dtype=torch.float32, device=self.device) if with_secondary else None
+        check(
+            lib.b200sep_demix_overlap_add(
+                _ptr(chunks), n_chunks, T, step, L, self.trim, N, int(overlap != 0), float(out_scale), _ptr(mix_dev) if with_secondary else None, self.compensate, int(interleave), _ptr(primary), _ptr(secondary) if with_secondary else None, _stream()
+            ),
+            "demix_overlap_add",
+        )
+        return (primary, secondary) if with_secondary else primary
+
+    # ---- array-level body of MDXSeparator.separate (mdx_separator.py:152-182)
+    def separate_device(self, mix_dev: torch.Tensor, normalization_threshold=0.9, amplification_threshold=0.0):
+        """mix_dev (2,N) float32 CUDA as loaded -> (primary (N,2), secondary (N,2)) CUDA float32."""
+        n = mix_dev.numel()
+        peak = torch.empty(1, dtype=torch.float32, device=self.device)
+        check(lib.b200sep_absmax(_ptr(mix_dev), n, _ptr(peak), _stream()), "absmax")  # :155
+        mixn = torch.empty_like(mix_dev)
+        min_peak = -1.0 if amplification_threshold is None else float(amplification_threshold)
+        check(lib.b200sep_normalize(_ptr(mix_dev), n, _ptr(peak), float(normalization_threshold), min_peak, _ptr(mixn), _stream()), "normalize")  # :156
+        # `source = demix(mix) * peak` (:159): out_scale is a host float in the C ABI; read the peak back (4 bytes)
+        peak_h = float(peak.item())
+        return self.demix_device(mixn, out_scale=peak_h, with_secondary=True, interleave=True)
+
+    def to_pcm16(self, stem: torch.Tensor, normalization_threshold=0.9, amplification_threshold=0.0):
+        """write_audio_pydub's sample path on the device (common_separator.py:310-339): returns int16 (N*2,) or None."""
+        stem = stem.contiguous()
+        n = stem.numel()
+        peak = torch.empty(1, dtype=torch.float32, device=self.device)
+        check(lib.b200sep_absmax(_ptr(stem), n, _ptr(peak), _stream()), "absmax")
+        norm = torch.empty_like(stem)
+        min_peak = -1.0 if amplification_threshold is None else float(amplification_threshold)
+        check(lib.b200sep_normalize(_ptr(stem), n, _ptr(peak), float(normalization_threshold), min_peak, _ptr(norm), _stream()), "normalize")
+        pk = float(peak.item())
+        s = 1.0
+        if pk > normalization_threshold:
+            s = normalization_threshold / pk
+        elif min_peak >= 0 and pk < min_peak:
+            s = min_peak / pk
+        if pk * s < 1e-6:
+            return None
+        out = torch.empty(n, dtype=torch.int16, device=self.device)
+        check(lib.b200sep_to_pcm16(_ptr(norm), n, _ptr(out), _stream()), "to_pcm16")
+        return out
