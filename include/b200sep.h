@@ -57,7 +57,7 @@ void b200sep_stft_plan_destroy(b200sep_stft_plan* plan);
  * mdx_separator.py:363-366).  Two addressings are used:
  *   - a contiguous (B,2,T) tensor:            batch_stride = 2T,   chan_stride = T, valid_len = 0 (unlimited);
  *   - chunks cut out of a padded (2,L) mixture: batch_stride = step, chan_stride = L, valid_len = L - offset of `wave`.
- * `chunk_len` = T must be a multiple of hop and > n_fft/2; frames = T/hop + 1.
+ * `chunk_len` = T must be > n_fft/2 (reflect padding); frames = T/hop + 1 (integer division, like torch.stft).
  * spec: layout CFT or CTF, float32, batch*4*dim_f*frames elements.
  */
 int b200sep_stft_forward(const b200sep_stft_plan* plan, const float* wave, int64_t batch_stride, int64_t chan_stride,
@@ -154,6 +154,17 @@ int64_t b200sep_mdx_run_model_work_floats(const b200sep_stft_plan* plan, int bat
 int b200sep_mdx_run_model(const b200sep_stft_plan* plan, b200sep_mdxnet* net, const float* wave, int64_t batch_stride,
                           int64_t chan_stride, int64_t valid_len, int batch, int chunk_len, int dim_f, int denoise,
                           float* wave_out, float* work, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Self-tests of the tensor-core ("bf16x3 pair") operators in isolation: fp32 device tensors in, the operator runs
+ * exactly as inside the network (split into bf16 hi/lo planes -> tcgen05 kernel -> join), fp32 out.  Synchronous.
+ *   gemm   : out[M][N] = act((a[M][K] @ w[N][K]^T) * scale[c] + shift[c]) (+ res),  c = (row / rows_per_channel) % channels
+ *   conv3x3: out(B,Cout,T,F) = act(conv2d(x(B,Cin,T,F), w(Cout,Cin,3,3), padding=1) * scale[co] + shift[co]);  w is a HOST pointer
+ */
+int b200sep_selftest_umma_gemm(const float* a, const float* w, const float* res, float* out, int M, int N, int K, int rows_per_channel,
+                               int channels, const float* scale, const float* shift, int relu, void* stream);
+int b200sep_selftest_umma_conv3x3(const float* x, const float* w_host, float* out, int B, int Cin, int Cout, int T, int F, const float* scale,
+                                  const float* shift, int relu, void* stream);
 
 #ifdef __cplusplus
 }

@@ -24,15 +24,24 @@ class STFT:
     def __call__(self, input_tensor):
         x = self._on_device(input_tensor)
         lead, (c, t) = x.shape[:-2], x.shape[-2:]
-        if c != 2:
-            raise ValueError(f"STFT expects stereo input (..., 2, T); got {c} channels")
-        spec = self._plan.forward(x.reshape(-1, 2, t), self.dim_f, zero_bins=0, layout=LAYOUT_CFT)
-        return spec.reshape(*lead, 4, self.dim_f, spec.shape[-1])
+        rows = x.reshape(-1, t)
+        n = rows.shape[0]
+        if n % 2:  # the kernel transforms channel PAIRS as one complex FFT; pad an odd row count with silence
+            rows = torch.cat([rows, torch.zeros_like(rows[:1])], 0)
+        spec = self._plan.forward(rows.reshape(-1, 2, t), self.dim_f, zero_bins=0, layout=LAYOUT_CFT)
+        frames = spec.shape[-1]
+        spec = spec.reshape(-1, 2, self.dim_f, frames)[:n]  # (rows, {re,im}, F, frames)
+        return spec.reshape(*lead, c * 2, self.dim_f, frames)
 
     def inverse(self, input_tensor):
         s = self._on_device(input_tensor)
-        lead, (c, f, t) = s.shape[:-3], s.shape[-3:]
-        if c != 4:
-            raise ValueError(f"STFT.inverse expects (..., 4, dim_f, frames); got {c} planes")
-        wave = self._plan.inverse(s.reshape(-1, 4, f, t), layout=LAYOUT_CFT)
-        return wave.reshape(*lead, 2, wave.shape[-1])
+        lead, (c2, f, t) = s.shape[:-3], s.shape[-3:]
+        if c2 % 2:
+            raise ValueError(f"STFT.inverse expects (..., 2*C, dim_f, frames); got {c2} planes")
+        rows = s.reshape(-1, 2, f, t)
+        n = rows.shape[0]
+        if n % 2:
+            rows = torch.cat([rows, torch.zeros_like(rows[:1])], 0)
+        wave = self._plan.inverse(rows.reshape(-1, 4, f, t), layout=LAYOUT_CFT)
+        wave = wave.reshape(-1, wave.shape[-1])[:n]
+        return wave.reshape(*lead, 2, -1) if c2 == 4 else wave.reshape(*lead, c2 // 2, -1)

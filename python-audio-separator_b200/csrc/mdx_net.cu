@@ -11,6 +11,7 @@
 
 #include "common.cuh"
 #include "simt_ops.cuh"
+#include "umma_ops.cuh"
 
 namespace b200sep {
 
@@ -19,12 +20,21 @@ struct ConvW {       // one convolution (+ folded BatchNorm) on the device
   float* scale = nullptr;  // [N]
   float* shift = nullptr;  // [N]
   int cin = 0, n = 0, n_pad = 0, kh = 1, kw = 1, stride = 1;
+  // tensor-core path (precision 1): weights split into bf16 hi/lo planes, pre-blocked for umma_conv_run
+  bool umma = false;
+  void* wb_hi = nullptr;
+  void* wb_lo = nullptr;
+  int kc = 0, n_tile = 0;
 };
 struct LinW {        // TDF linear (+ folded BatchNorm over the channel axis)
   float* w = nullptr;  // [N][K]
   float* scale = nullptr;
   float* shift = nullptr;
   int n = 0, k = 0, channels = 0;
+  bool umma = false;
+  void* w_hi = nullptr;  // bf16 [N][K]
+  void* w_lo = nullptr;
+  UmmaGemmPlan plan;
 };
 struct BlockW {
   std::vector<ConvW> tfc;
@@ -44,7 +54,12 @@ struct b200sep_mdxnet {
   std::vector<ConvW> ds, us;
   std::vector<float*> bufA, bufB;  // per scale (0..n_scales), each max_batch * C_i * T_i * F_i floats
   float* tdf_tmp = nullptr;        // max over scales of max_batch * C_i * T_i * (F_i / bn)
+  int64_t tdf_tmp_elems = 0;
   float* io_tmp = nullptr;         // CFT<->CTF staging, max_batch * 4 * T * F
+  std::vector<int64_t> buf_elems;  // elements of bufA[i] / bufB[i] (= offset of the lo plane in pair mode)
+  std::vector<UmmaConvPlan> planA, planB;  // per scale: TMA maps over bufA[i] / bufB[i] as conv inputs
+  std::vector<char> plan_ok;
+  bool pair = false;               // precision 1: activations are bf16 hi/lo pairs
   std::vector<void*> allocs;
   int64_t device_bytes = 0;
   // optional per-category device timing (bench.py roofline): CUDA events recorded around every launch
@@ -98,6 +113,53 @@ static void fold_bn(int c, const float* bias, const float* gamma, const float* b
   }
 }
 
+static inline uint16_t f2bf(float f) {  // round-to-nearest-even float -> bf16 bits
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+static inline float bf2f(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+static int upload_u16(b200sep_mdxnet* net, void** dst, const std::vector<uint16_t>& src) {
+  int rc = dev_alloc(net, dst, (int64_t)src.size() * 2);
+  if (rc) return rc;
+  B2_CUDA(cudaMemcpy(*dst, src.data(), src.size() * 2, cudaMemcpyHostToDevice));
+  return B200SEP_OK;
+}
+
+// tcgen05 B operand for a stride-1 conv: [Cout/n_tile][tap][Cin/kc][kc/16] blocks of [n_tile][16] in 8x8 core matrices
+static int make_conv_umma(b200sep_mdxnet* net, ConvW& cw, const float* w /*(Cout,Cin,k,k)*/) {
+  const int taps = cw.kh * cw.kw;
+  umma_conv_choose(cw.cin, cw.n, &cw.kc, &cw.n_tile);
+  const int n_tiles = cw.n / cw.n_tile, n_chunks = cw.cin / cw.kc, ksteps = cw.kc / 16;
+  std::vector<uint16_t> hi((size_t)cw.n * cw.cin * taps), lo(hi.size());
+  size_t pos = 0;
+  for (int nt = 0; nt < n_tiles; ++nt)
+    for (int tap = 0; tap < taps; ++tap)
+      for (int ch = 0; ch < n_chunks; ++ch)
+        for (int j = 0; j < ksteps; ++j) {
+          for (int n = 0; n < cw.n_tile; ++n)
+            for (int kk = 0; kk < 16; ++kk) {
+              const int co = nt * cw.n_tile + n, ci = ch * cw.kc + j * 16 + kk;
+              const float v = w[((size_t)co * cw.cin + ci) * taps + tap];
+              const size_t o = pos + (size_t)((n / 8) * 2 + kk / 8) * 64 + (n % 8) * 8 + (kk % 8);
+              hi[o] = f2bf(v);
+              lo[o] = f2bf(v - bf2f(hi[o]));
+            }
+          pos += (size_t)cw.n_tile * 16;
+        }
+  int rc = upload_u16(net, &cw.wb_hi, hi);
+  if (!rc) rc = upload_u16(net, &cw.wb_lo, lo);
+  cw.umma = rc == 0;
+  return rc;
+}
+
 // Conv2d weight (Cout, Cin, kh, kw) -> [Cin][kh*kw][CoutPad]
 static int make_conv(b200sep_mdxnet* net, ParamReader& rd, ConvW& cw, int cin, int cout, int k, int stride, bool has_bn) {
   const int taps = k * k;
@@ -118,6 +180,7 @@ static int make_conv(b200sep_mdxnet* net, ParamReader& rd, ConvW& cw, int cin, i
   int rc = upload(net, &cw.w, wr);
   if (!rc) rc = upload(net, &cw.scale, sc);
   if (!rc) rc = upload(net, &cw.shift, sh);
+  if (!rc && net->pair && stride == 1 && k == 3 && umma_conv_supported(cin, cout, 8, k, k)) rc = make_conv_umma(net, cw, w);
   return rc;
 }
 
@@ -152,6 +215,16 @@ static int make_lin(b200sep_mdxnet* net, ParamReader& rd, LinW& lw, int n, int k
   int rc = upload(net, &lw.w, wv);
   if (!rc) rc = upload(net, &lw.scale, sc);
   if (!rc) rc = upload(net, &lw.shift, sh);
+  if (!rc && net->pair && umma_gemm_supported(1, n, k)) {
+    std::vector<uint16_t> hi((size_t)n * k), lo(hi.size());
+    for (size_t i = 0; i < hi.size(); ++i) {
+      hi[i] = f2bf(w[i]);
+      lo[i] = f2bf(w[i] - bf2f(hi[i]));
+    }
+    rc = upload_u16(net, &lw.w_hi, hi);
+    if (!rc) rc = upload_u16(net, &lw.w_lo, lo);
+    lw.umma = rc == 0;  // the TMA plan is bound once the activation arena exists
+  }
   return rc;
 }
 
@@ -189,42 +262,86 @@ struct ProfScope {  // records an event pair around the launches issued during i
   }
 };
 
-static int run_conv(b200sep_mdxnet* net, int cat, const ConvW& cw, const float* x, float* y, const float* mul, int B, int H, int W, int relu, int epilogue, cudaStream_t st) {
+static int run_conv(b200sep_mdxnet* net, int cat, const ConvW& cw, const float* x, float* y, const float* mul, int B, int H, int W, int relu, int epilogue, cudaStream_t st,
+                    const void* x_lo = nullptr, void* y_lo = nullptr, const void* mul_lo = nullptr) {
   const double pix = (double)B * (H / cw.stride) * (W / cw.stride);
   const double out_elems = pix * cw.n;
   ProfScope ps(net, st, cat, 2.0 * pix * cw.n * cw.cin * cw.kh * cw.kw,
                4.0 * ((double)B * cw.cin * H * W + out_elems * (mul ? 2 : 1) + (double)cw.cin * cw.kh * cw.kw * cw.n));
   ConvParams p;
   p.x = x; p.w = cw.w; p.scale = cw.scale; p.shift = cw.shift; p.mul = mul; p.y = y;
+  p.x_lo = x_lo; p.mul_lo = mul_lo; p.y_lo = y_lo;
   p.B = B; p.Cin = cw.cin; p.H = H; p.W = W; p.Cout = cw.n; p.CoutPad = cw.n_pad;
   p.Ho = H / cw.stride; p.Wo = W / cw.stride; p.relu = relu; p.epilogue = epilogue;
   return conv2d_simt(p, cw.kh, cw.kw, cw.stride, st);
 }
 
+// lo plane of a per-scale activation buffer in pair mode (nullptr in fp32 mode)
+static inline void* lo_of(const b200sep_mdxnet* net, const float* buf, int scale) {
+  return net->pair ? (void*)((uint16_t*)buf + net->buf_elems[scale]) : nullptr;
+}
+
 // TFC (l x conv3x3+BN+ReLU) then x + TDF(x) (modules.py:20-23, :63-74).  in: bufA, result left in bufB.
-static int run_block(b200sep_mdxnet* net, const BlockW& bw, float* A, float* Bf, int B, int c, int T, int F, cudaStream_t st) {
+static int run_block(b200sep_mdxnet* net, BlockW& bw, int scale, int B, int c, int T, int F, cudaStream_t st) {
+  float* A = net->bufA[scale];
+  float* Bf = net->bufB[scale];
   float* src = A;
   float* dst = Bf;
+  int rc;
   for (size_t i = 0; i < bw.tfc.size(); ++i) {
-    int rc = run_conv(net, CAT_CONV3X3, bw.tfc[i], src, dst, nullptr, B, T, F, 1, EPI_NORMAL, st);
+    const ConvW& cw = bw.tfc[i];
+    if (net->pair && cw.umma && net->plan_ok[scale]) {
+      const UmmaConvPlan& pl = (src == A) ? net->planA[scale] : net->planB[scale];
+      const double pix = (double)B * T * F;
+      ProfScope ps(net, st, CAT_CONV3X3, 2.0 * pix * cw.n * cw.cin * 9, 4.0 * (pix * cw.cin + pix * cw.n + 9.0 * cw.cin * cw.n));
+      rc = umma_conv_run(pl, cw.wb_hi, cw.wb_lo, B, cw.n, cw.n_tile, cw.kh, cw.scale, cw.shift, 1, dst, lo_of(net, dst, scale), st);
+    } else {
+      rc = run_conv(net, CAT_CONV3X3, cw, src, dst, nullptr, B, T, F, 1, EPI_NORMAL, st, lo_of(net, src, scale), lo_of(net, dst, scale));
+    }
     if (rc) return rc;
     float* t = src; src = dst; dst = t;
   }
-  // after an odd number of convs the result is in Bf; after an even number it is back in A
-  float* x = src;
-  GemmParams g;
-  g.A = x; g.Bw = bw.tdf1.w; g.scale = bw.tdf1.scale; g.shift = bw.tdf1.shift; g.res = nullptr; g.C = net->tdf_tmp;
-  g.M = B * c * T; g.N = bw.tdf1.n; g.K = F; g.rows_per_channel = T; g.channels = c; g.relu = 1;
-  int rc;
-  {
-    ProfScope ps(net, st, CAT_TDF, 2.0 * g.M * g.N * g.K, 4.0 * ((double)g.M * g.K + (double)g.M * g.N + (double)g.N * g.K));
+  float* x = src;  // after an odd number of convs the result is in Bf; after an even number it is back in A
+  const int M = B * c * T;
+  void* tmp_lo = net->pair ? (void*)((uint16_t*)net->tdf_tmp + net->tdf_tmp_elems) : nullptr;
+  // t1 = relu(bn(x @ W1^T))
+  if (net->pair && bw.tdf1.umma) {
+    ProfScope ps(net, st, CAT_TDF, 2.0 * M * bw.tdf1.n * (double)F, 4.0 * ((double)M * F + (double)M * bw.tdf1.n + (double)bw.tdf1.n * F));
+    rc = umma_gemm_run(x == Bf ? bw.tdf1.plan : bw.tdf1.plan, bw.tdf1.scale, bw.tdf1.shift, T, c, 1, net->tdf_tmp, tmp_lo, nullptr, nullptr, M, st);
+  } else {
+    GemmParams g;
+    g.A = x; g.A_lo = lo_of(net, x, scale); g.Bw = bw.tdf1.w; g.scale = bw.tdf1.scale; g.shift = bw.tdf1.shift; g.res = nullptr;
+    g.C = net->tdf_tmp; g.C_lo = tmp_lo;
+    g.M = M; g.N = bw.tdf1.n; g.K = F; g.rows_per_channel = T; g.channels = c; g.relu = 1;
+    ProfScope ps(net, st, CAT_TDF, 2.0 * g.M * g.N * (double)g.K, 4.0 * ((double)g.M * g.K + (double)g.M * g.N + (double)g.N * g.K));
     rc = gemm_tn_simt(g, st);
   }
   if (rc) return rc;
-  g.A = net->tdf_tmp; g.Bw = bw.tdf2.w; g.scale = bw.tdf2.scale; g.shift = bw.tdf2.shift; g.res = x; g.C = Bf;
-  g.N = F; g.K = bw.tdf2.k;
-  ProfScope ps(net, st, CAT_TDF, 2.0 * g.M * g.N * g.K, 4.0 * ((double)g.M * g.K + 2.0 * (double)g.M * g.N + (double)g.N * g.K));
-  return gemm_tn_simt(g, st);  // Bf = x + relu(bn(lin2(.)))  (x == Bf when l is odd: in-place residual)
+  // Bf = x + relu(bn(t1 @ W2^T))   (x == Bf when l is odd: in-place residual, each element read then written by one thread)
+  if (net->pair && bw.tdf2.umma) {
+    ProfScope ps(net, st, CAT_TDF, 2.0 * M * (double)F * bw.tdf2.k, 4.0 * ((double)M * bw.tdf2.k + 2.0 * M * F + (double)F * bw.tdf2.k));
+    rc = umma_gemm_run(bw.tdf2.plan, bw.tdf2.scale, bw.tdf2.shift, T, c, 1, Bf, lo_of(net, Bf, scale), x, lo_of(net, x, scale), M, st);
+  } else {
+    GemmParams g;
+    g.A = net->tdf_tmp; g.A_lo = tmp_lo; g.Bw = bw.tdf2.w; g.scale = bw.tdf2.scale; g.shift = bw.tdf2.shift;
+    g.res = x; g.res_lo = lo_of(net, x, scale); g.C = Bf; g.C_lo = lo_of(net, Bf, scale);
+    g.M = M; g.N = F; g.K = bw.tdf2.k; g.rows_per_channel = T; g.channels = c; g.relu = 1;
+    ProfScope ps(net, st, CAT_TDF, 2.0 * g.M * g.N * (double)g.K, 4.0 * ((double)g.M * g.K + 2.0 * (double)g.M * g.N + (double)g.N * g.K));
+    rc = gemm_tn_simt(g, st);
+  }
+  return rc;
+}
+
+// bind the TMA plans of one block's TDF linears: A operands are the block's output buffer and the shared tdf_tmp
+static int bind_block_plans(b200sep_mdxnet* net, BlockW& bw, int scale, int c, int T, int F) {
+  if (!net->pair) return B200SEP_OK;
+  const int M = net->cfg.max_batch * c * T;
+  float* x = (bw.tfc.size() & 1) ? net->bufB[scale] : net->bufA[scale];
+  int rc = B200SEP_OK;
+  if (bw.tdf1.umma) rc = umma_gemm_plan_create(&bw.tdf1.plan, x, lo_of(net, x, scale), bw.tdf1.w_hi, bw.tdf1.w_lo, M, bw.tdf1.n, F);
+  if (!rc && bw.tdf2.umma)
+    rc = umma_gemm_plan_create(&bw.tdf2.plan, net->tdf_tmp, (uint16_t*)net->tdf_tmp + net->tdf_tmp_elems, bw.tdf2.w_hi, bw.tdf2.w_lo, M, F, bw.tdf2.k);
+  return rc;
 }
 
 }  // namespace b200sep
@@ -268,6 +385,7 @@ extern "C" int b200sep_mdxnet_create(b200sep_mdxnet** out, const b200sep_mdxnet_
   b200sep_mdxnet* net = new b200sep_mdxnet();
   net->cfg = *cfg;
   net->n_scales = n;
+  net->pair = cfg->precision != 0;
   ParamReader rd{params_host, n_params};
   int rc = make_conv(net, rd, net->first, cfg->dim_c, cfg->g, 1, 1, true);
   int f = cfg->dim_f, c = cfg->g;
@@ -291,15 +409,37 @@ extern "C" int b200sep_mdxnet_create(b200sep_mdxnet** out, const b200sep_mdxnet_
   // activation arena
   net->bufA.assign(n + 1, nullptr);
   net->bufB.assign(n + 1, nullptr);
+  net->buf_elems.assign(n + 1, 0);
+  net->planA.resize(n + 1);
+  net->planB.resize(n + 1);
+  net->plan_ok.assign(n + 1, 0);
   int64_t tmp_max = 0;
   for (int i = 0; i <= n && !rc; ++i) {
     const int64_t ci = (int64_t)cfg->g * (i + 1), ti = cfg->dim_t >> i, fi = cfg->dim_f >> i;
-    const int64_t bytes = (int64_t)cfg->max_batch * ci * ti * fi * sizeof(float);
+    net->buf_elems[i] = (int64_t)cfg->max_batch * ci * ti * fi;
+    const int64_t bytes = net->buf_elems[i] * sizeof(float);
     rc = dev_alloc(net, (void**)&net->bufA[i], bytes);
     if (!rc) rc = dev_alloc(net, (void**)&net->bufB[i], bytes);
     tmp_max = std::max<int64_t>(tmp_max, (int64_t)cfg->max_batch * ci * ti * (fi / cfg->bn));
+    if (!rc && net->pair && umma_conv_supported((int)ci, (int)ci, (int)fi, 3, 3)) {
+      int kc, nt;
+      umma_conv_choose((int)ci, (int)ci, &kc, &nt);
+      rc = umma_conv_plan_create(&net->planA[i], net->bufA[i], lo_of(net, net->bufA[i], i), cfg->max_batch, (int)ci, (int)ti, (int)fi, kc);
+      if (!rc) rc = umma_conv_plan_create(&net->planB[i], net->bufB[i], lo_of(net, net->bufB[i], i), cfg->max_batch, (int)ci, (int)ti, (int)fi, kc);
+      net->plan_ok[i] = rc == 0;
+    }
   }
+  net->tdf_tmp_elems = tmp_max;
   if (!rc) rc = dev_alloc(net, (void**)&net->tdf_tmp, tmp_max * sizeof(float));
+  for (int i = 0; i <= n && !rc; ++i) {
+    const int ci = cfg->g * (i + 1), ti = cfg->dim_t >> i, fi = cfg->dim_f >> i;
+    if (i < n) {
+      rc = bind_block_plans(net, net->enc[i], i, ci, ti, fi);
+      if (!rc) rc = bind_block_plans(net, net->dec[n - 1 - i], i, ci, ti, fi);
+    } else {
+      rc = bind_block_plans(net, net->bottleneck, i, ci, ti, fi);
+    }
+  }
   if (!rc) rc = dev_alloc(net, (void**)&net->io_tmp, (int64_t)cfg->max_batch * cfg->dim_c * cfg->dim_t * cfg->dim_f * sizeof(float));
   if (rc) {
     b200sep_mdxnet_destroy(net);
@@ -335,27 +475,29 @@ extern "C" int b200sep_mdxnet_forward(b200sep_mdxnet* net, const float* spec_in,
     if (rc) return rc;
     in = net->io_tmp;
   }
-  rc = run_conv(net, CAT_POINTWISE, net->first, in, net->bufA[0], nullptr, B, T, F, 1, EPI_NORMAL, st);
+  rc = run_conv(net, CAT_POINTWISE, net->first, in, net->bufA[0], nullptr, B, T, F, 1, EPI_NORMAL, st, nullptr, lo_of(net, net->bufA[0], 0));
   if (rc) return rc;
   for (int i = 0; i < n; ++i) {  // encoder (mdxnet.py:103-107)
-    rc = run_block(net, net->enc[i], net->bufA[i], net->bufB[i], B, c, T, F, st);
+    rc = run_block(net, net->enc[i], i, B, c, T, F, st);
     if (rc) return rc;
-    rc = run_conv(net, CAT_DOWN, net->ds[i], net->bufB[i], net->bufA[i + 1], nullptr, B, T, F, 1, EPI_NORMAL, st);
+    rc = run_conv(net, CAT_DOWN, net->ds[i], net->bufB[i], net->bufA[i + 1], nullptr, B, T, F, 1, EPI_NORMAL, st, lo_of(net, net->bufB[i], i),
+                  lo_of(net, net->bufA[i + 1], i + 1));
     if (rc) return rc;
     T /= 2; F /= 2; c += cfg.g;
   }
-  rc = run_block(net, net->bottleneck, net->bufA[n], net->bufB[n], B, c, T, F, st);  // mdxnet.py:109
+  rc = run_block(net, net->bottleneck, n, B, c, T, F, st);  // mdxnet.py:109
   if (rc) return rc;
   for (int i = 0; i < n; ++i) {  // decoder (mdxnet.py:111-114): convT+BN+ReLU, multiply by the skip, TFC_TDF
     const int s = n - 1 - i;
-    rc = run_conv(net, CAT_UP, net->us[i], net->bufB[s + 1], net->bufA[s], net->bufB[s], B, T, F, 1, EPI_CONVT2X2, st);
+    rc = run_conv(net, CAT_UP, net->us[i], net->bufB[s + 1], net->bufA[s], net->bufB[s], B, T, F, 1, EPI_CONVT2X2, st, lo_of(net, net->bufB[s + 1], s + 1),
+                  lo_of(net, net->bufA[s], s), lo_of(net, net->bufB[s], s));
     if (rc) return rc;
     T *= 2; F *= 2; c -= cfg.g;
-    rc = run_block(net, net->dec[i], net->bufA[s], net->bufB[s], B, c, T, F, st);
+    rc = run_block(net, net->dec[i], s, B, c, T, F, st);
     if (rc) return rc;
   }
   float* out = (layout == B200SEP_LAYOUT_CFT) ? net->io_tmp : spec_out;
-  rc = run_conv(net, CAT_POINTWISE, net->final, net->bufB[0], out, nullptr, B, T, F, 0, EPI_NORMAL, st);
+  rc = run_conv(net, CAT_POINTWISE, net->final, net->bufB[0], out, nullptr, B, T, F, 0, EPI_NORMAL, st, lo_of(net, net->bufB[0], 0), nullptr);
   if (rc) return rc;
   if (layout == B200SEP_LAYOUT_CFT) {
     ProfScope ps(net, st, CAT_TRANSPOSE, 0.0, 8.0 * B * cfg.dim_c * T * F);

@@ -1,7 +1,19 @@
 // FP32 SIMT operators (see simt_ops.cuh).  Register-tiled implicit-GEMM convolution and a TN SGEMM.
 #include "simt_ops.cuh"
 
+#include <cuda_bf16.h>
+
 namespace b200sep {
+
+using bf16 = __nv_bfloat16;
+__device__ __forceinline__ float pair_load(const void* hi, const void* lo, int64_t i) {
+  return __bfloat162float(static_cast<const bf16*>(hi)[i]) + __bfloat162float(static_cast<const bf16*>(lo)[i]);
+}
+__device__ __forceinline__ void pair_store(void* hi, void* lo, int64_t i, float v) {
+  const bf16 h = __float2bfloat16_rn(v);
+  static_cast<bf16*>(hi)[i] = h;
+  static_cast<bf16*>(lo)[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // conv2d: block tile = 128 (w) x 2 (h) output pixels x 48 output channels, 256 threads,
@@ -40,7 +52,8 @@ __global__ void __launch_bounds__(CONV_NT) conv2d_simt_kernel(ConvParams p) {
 #pragma unroll
     for (int j = 0; j < 12; ++j) acc[i][j] = 0.f;
 
-  const float* xb = p.x + (int64_t)b * p.Cin * p.H * p.W;
+  const int64_t xoff = (int64_t)b * p.Cin * p.H * p.W;
+  const float* xb = p.x + xoff;
   for (int ci0 = 0; ci0 < p.Cin; ci0 += CI) {
     for (int idx = tid; idx < CI * G::ROWS * G::COLS; idx += CONV_NT) {
       const int c = idx % G::COLS;
@@ -48,7 +61,10 @@ __global__ void __launch_bounds__(CONV_NT) conv2d_simt_kernel(ConvParams p) {
       const int ci = idx / (G::COLS * G::ROWS);
       const int hi = h0 * S - G::PAD + r, wi = w0 * S - G::PAD + c;
       float v = 0.f;
-      if (ci0 + ci < p.Cin && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W) v = __ldg(&xb[((int64_t)(ci0 + ci) * p.H + hi) * p.W + wi]);
+      if (ci0 + ci < p.Cin && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W) {
+        const int64_t xi = ((int64_t)(ci0 + ci) * p.H + hi) * p.W + wi;
+        v = p.x_lo ? pair_load(p.x, p.x_lo, xoff + xi) : __ldg(&xb[xi]);
+      }
       in_s[(ci * G::ROWS + r) * G::COLS_PAD + G::OFF + c] = v;
     }
     for (int idx = tid; idx < CI * G::TAPS * (TCO / 4); idx += CONV_NT) {
@@ -99,7 +115,16 @@ __global__ void __launch_bounds__(CONV_NT) conv2d_simt_kernel(ConvParams p) {
         v[i] = fmaf(acc[i][j], sc, sh);
         if (p.relu) v[i] = fmaxf(v[i], 0.f);
       }
-      if (wbase + 3 < p.Wo && (p.Wo & 3) == 0) {
+      if (p.y_lo || p.mul_lo) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (wbase + i >= p.Wo) continue;
+          float r = v[i];
+          if (p.mul) r *= p.mul_lo ? pair_load(p.mul, p.mul_lo, o + i) : __ldg(&p.mul[o + i]);
+          if (p.y_lo) pair_store(p.y, p.y_lo, o + i, r);
+          else p.y[o + i] = r;
+        }
+      } else if (wbase + 3 < p.Wo && (p.Wo & 3) == 0) {
         if (p.mul) {
           const float4 m = __ldg(reinterpret_cast<const float4*>(&p.mul[o]));
           v[0] *= m.x; v[1] *= m.y; v[2] *= m.z; v[3] *= m.w;
@@ -122,8 +147,9 @@ __global__ void __launch_bounds__(CONV_NT) conv2d_simt_kernel(ConvParams p) {
         float v = fmaf(acc[i][j], sc, sh);
         if (p.relu) v = fmaxf(v, 0.f);
         const int64_t o = orow + 2 * (wbase + i) + dx;
-        if (p.mul) v *= __ldg(&p.mul[o]);
-        p.y[o] = v;
+        if (p.mul) v *= p.mul_lo ? pair_load(p.mul, p.mul_lo, o) : __ldg(&p.mul[o]);
+        if (p.y_lo) pair_store(p.y, p.y_lo, o, v);
+        else p.y[o] = v;
       }
     }
   }
@@ -164,7 +190,7 @@ __global__ void __launch_bounds__(GEMM_NT) gemm_tn_simt_kernel(GemmParams p) {
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const bool vec = (p.K & 3) == 0;  // float4 global loads need 16-byte aligned rows
+  const bool vec = (p.K & 3) == 0 && p.A_lo == nullptr;  // float4 global loads need 16-byte aligned fp32 rows
   float acc[8][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -185,7 +211,10 @@ __global__ void __launch_bounds__(GEMM_NT) gemm_tn_simt_kernel(GemmParams p) {
         float av[4] = {0.f, 0.f, 0.f, 0.f}, bv[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          if (m0 + row < p.M && k + e < p.K) av[e] = __ldg(&p.A[(int64_t)(m0 + row) * p.K + k + e]);
+          if (m0 + row < p.M && k + e < p.K) {
+            const int64_t ai = (int64_t)(m0 + row) * p.K + k + e;
+            av[e] = p.A_lo ? pair_load(p.A, p.A_lo, ai) : __ldg(&p.A[ai]);
+          }
           if (n0 + row < p.N && k + e < p.K) bv[e] = __ldg(&p.Bw[(int64_t)(n0 + row) * p.K + k + e]);
         }
         a = make_float4(av[0], av[1], av[2], av[3]);
@@ -223,8 +252,9 @@ __global__ void __launch_bounds__(GEMM_NT) gemm_tn_simt_kernel(GemmParams p) {
       float v = fmaf(acc[i][j], sc, sh);
       if (p.relu) v = fmaxf(v, 0.f);
       const int64_t o = (int64_t)r * p.N + n;
-      if (p.res) v += p.res[o];
-      p.C[o] = v;
+      if (p.res) v += p.res_lo ? pair_load(p.res, p.res_lo, o) : p.res[o];
+      if (p.C_lo) pair_store(p.C, p.C_lo, o, v);
+      else p.C[o] = v;
     }
   }
 }

@@ -19,6 +19,11 @@ struct ConvParams {
   const float* shift;  // [CoutTotal] folded BatchNorm shift + conv bias
   const float* mul;    // optional elementwise multiplier with the OUTPUT's shape (skip connection), or nullptr
   float* y;
+  // "pair" tensors (two bf16 planes hi+lo per fp32 value, see umma_ops.cu): when the *_lo pointer is non-null the
+  // corresponding main pointer is the bf16 hi plane and the value is float(hi)+float(lo)
+  const void* x_lo = nullptr;
+  const void* mul_lo = nullptr;
+  void* y_lo = nullptr;
   int B, Cin, H, W;    // input dims
   int Cout;            // GEMM-N: number of output channels of the implicit GEMM (4*C for EPI_CONVT2X2)
   int CoutPad;
@@ -39,6 +44,9 @@ struct GemmParams {
   const float* shift;
   const float* res;  // [M][N] or nullptr
   float* C;          // [M][N]
+  const void* A_lo = nullptr;    // pair variants as in ConvParams
+  const void* res_lo = nullptr;
+  void* C_lo = nullptr;
   int M, N, K;
   int rows_per_channel, channels;
   int relu;

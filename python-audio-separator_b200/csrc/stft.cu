@@ -391,7 +391,7 @@ extern "C" int b200sep_stft_forward(const b200sep_stft_plan* plan, const float* 
                                     int64_t valid_len, int batch, int chunk_len, int dim_f, int zero_bins, int layout, float* spec,
                                     void* stream) {
   B2_CHECK_ARG(plan && wave && spec, "stft_forward: NULL argument");
-  B2_CHECK_ARG(batch >= 0 && chunk_len > 0 && chunk_len % plan->hop == 0, "stft_forward: chunk_len=%d must be a positive multiple of hop=%d", chunk_len, plan->hop);
+  B2_CHECK_ARG(batch >= 0 && chunk_len > 0, "stft_forward: chunk_len=%d must be positive", chunk_len);
   B2_CHECK_ARG(chunk_len > plan->n_fft / 2, "stft_forward: reflect padding needs chunk_len=%d > n_fft/2=%d", chunk_len, plan->n_fft / 2);
   B2_CHECK_ARG(dim_f >= 1 && dim_f <= plan->n_fft / 2 + 1, "stft_forward: dim_f=%d out of range", dim_f);
   B2_CHECK_ARG(layout == B200SEP_LAYOUT_CFT || layout == B200SEP_LAYOUT_CTF, "stft_forward: bad layout %d", layout);

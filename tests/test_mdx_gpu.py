@@ -16,6 +16,7 @@ import mdx_oracle as O
 pytestmark = pytest.mark.gpu
 
 SMALL = dict(n_fft=1536, hop_length=256, dim_f=768, dim_t=32, segment_size=32, g=8)
+MID = dict(n_fft=1024, hop_length=256, dim_f=512, dim_t=32, segment_size=32, g=16, num_blocks=7)  # channel counts the tcgen05 conv accepts
 
 
 @pytest.fixture(scope="module")
@@ -81,18 +82,23 @@ def test_stft_vs_reference_golden(eng, golden_dir):
 
 
 def test_stft_class_mirror(eng):
-    """Same call pattern as tests/unit/test_stft.py of the reference (shapes (B,4,dim_f,N//hop+1), inverse (1,2,7936))."""
+    """Same call pattern as the reference's tests/unit/test_stft.py:43-138: mono (1,16000) input -> (..., dim_f, N//hop+1)."""
     import logging
 
     from audio_separator.separator.uvr_lib_v5.stft import STFT
 
     st = STFT(logging.getLogger("t"), 2048, 512, 1025, "cuda")
-    x = torch.randn(1, 2, 7936, device="cuda")
+    x1 = torch.rand(1, 16000, device="cuda")
+    s1 = st(x1)
+    assert tuple(s1.shape[-2:]) == (1025, 16000 // 512 + 1) and s1.shape[0] == 2
+    ref = O.stft_forward(x1.cpu().numpy()[None], 2048, 512, 1025)[0]
+    assert maxabs(s1.cpu().numpy(), ref) <= 2e-6 * 2048
+    x = torch.randn(3, 2, 7680, device="cuda")
     s = st(x)
-    assert tuple(s.shape) == (1, 4, 1025, 7936 // 512 + 1)
+    assert tuple(s.shape) == (3, 4, 1025, 16)
     y = st.inverse(s)
-    assert tuple(y.shape) == (1, 2, 7936)
-    assert (y - x).abs().max().item() < 1e-4  # COLA round trip
+    assert tuple(y.shape) == (3, 2, 7680)
+    assert (y - x).abs().max().item() < 1e-4  # COLA round trip with the full one-sided spectrum
     with pytest.raises(RuntimeError):
         st(x.cpu())
 
@@ -114,6 +120,21 @@ def test_network_small_vs_oracle_and_golden(eng, golden_dir, precision):
     ref3 = O.convtdfnet_forward(w, cfg, x3)
     got3 = net.forward(dev(x3.transpose(0, 1, 3, 2)), eng.LAYOUT_CTF).cpu().numpy().transpose(0, 1, 3, 2)
     assert maxabs(got3, ref3) <= rel * np.abs(ref3).max()
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_network_mid_vs_oracle(eng, precision):
+    """A 7-block net with 16..64 channels: every TFC conv and most TDF linears take the tensor-core path at precision 1."""
+    cfg = O.MDXConfig(**MID)
+    w = O.make_convtdfnet_weights(cfg, seed=21)
+    net = make_net(eng, cfg, w, max_batch=3, precision=precision)
+    rng = np.random.default_rng(2)
+    x = (rng.standard_normal((3, 4, cfg.dim_f, cfg.dim_t)) * 3).astype(np.float32)
+    ref = O.convtdfnet_forward(w, cfg, x, dtype="float64")
+    got = net.forward(dev(x)).cpu().numpy()
+    assert maxabs(got, ref) <= (1e-5 if precision == 0 else 1e-4) * np.abs(ref).max()
+    got1 = net.forward(dev(x[:1])).cpu().numpy()  # batch smaller than max_batch uses a prefix of the arena
+    assert maxabs(got1, ref[:1]) <= (1e-5 if precision == 0 else 1e-4) * np.abs(ref).max()
 
 
 @pytest.mark.parametrize("precision", [0, 1])
@@ -196,22 +217,36 @@ def test_demix_edge_grids_vs_golden(eng, golden_dir, n):
     assert maxabs(out.cpu().numpy(), edge[f"n{n}"]) <= 2e-5
 
 
-def test_full_size_properties(eng):
-    """BASELINE sizes (5-minute grid is too slow for the CPU oracle): size-independent properties.
-    (1) linearity of STFT->iSTFT->OLA with the pass-through spectrum: demix_match_mix(a*x) == a*demix_match_mix(x);
-    (2) reconstruction: with bins 0-2 zeroed, match-mix demix of a signal without content below 3 bins returns it;
-    (3) sample count and chunk grid equal the reference's (68 chunks for 5 min)."""
+def test_full_size_grid_against_oracle(eng):
+    """BASELINE-size chunk grid (n_fft 6144, chunk 261120): one minute of audio through STFT -> iSTFT -> Hann
+    overlap-add with the pass-through spectrum (the reference's always-run is_match_mix pass, mdx_separator.py:175),
+    compared sample-for-sample with the oracle; plus linearity and the 5-minute grid sizes."""
     cfg = O.MDXConfig()
     e = eng.MdxEngine(None, cfg.n_fft, cfg.hop_length, cfg.dim_f, cfg.segment_size, cfg.overlap, cfg.compensate)
-    N = 44100 * 60
     assert e.grid(13_230_000)[2] == 68 and e.grid(13_230_000, True)[2] == 52
-    t = np.arange(N) / 44100.0
-    x = np.stack([0.4 * np.sin(2 * np.pi * 440 * t) + 0.2 * np.sin(2 * np.pi * 3000 * t), 0.3 * np.sin(2 * np.pi * 1234.5 * t)]).astype(np.float32)
-    y = e.demix_device(dev(x), is_match_mix=True).cpu().numpy()
-    assert y.shape == x.shape
-    assert np.abs(y - x)[:, 4096:-4096].max() < 2e-4  # dim_f crop drops only the Nyquist bin; 0-2 bins carry no energy here
-    y2 = e.demix_device(dev(0.5 * x), is_match_mix=True).cpu().numpy()
-    assert np.abs(y2 - 0.5 * y).max() < 1e-6
+    N = 44100 * 60 + 123
+    x = O.normalize(O.synth_music(N, seed=77), 0.9, 0.0)
+    for match in (True,):
+        ref = O.demix(x, cfg, None, is_match_mix=match)
+        got = e.demix_device(dev(x), is_match_mix=match).cpu().numpy()
+        assert got.shape == ref.shape == (2, N)
+        assert maxabs(got, ref) <= 2e-5
+    # normal overlap (0.25) grid with the pass-through spectrum, driven through the C ABI
+    from audio_separator.separator.b200._lib import check, lib
+
+    L, step, n_chunks, _ = e.grid(N)
+    T = cfg.chunk_size
+    mixture = torch.zeros((2, L), device="cuda")
+    mixture[:, cfg.trim : cfg.trim + N] = dev(x)
+    chunks = torch.empty((n_chunks, 2, T), device="cuda")
+    work = torch.empty(lib.b200sep_mdx_run_model_work_floats(e.plan.handle, n_chunks, T, cfg.dim_f), device="cuda")
+    check(lib.b200sep_mdx_run_model(e.plan.handle, None, mixture.data_ptr(), step, L, L, n_chunks, T, cfg.dim_f, 0, chunks.data_ptr(), work.data_ptr(), None))
+    out = torch.empty((2, N), device="cuda")
+    check(lib.b200sep_demix_overlap_add(chunks.data_ptr(), n_chunks, T, step, L, cfg.trim, N, 1, 1.0, None, 0.0, 0, out.data_ptr(), None, None))
+    ref = O.demix(x, cfg, lambda s: s)
+    assert maxabs(out.cpu().numpy(), ref) <= 2e-5
+    got_half = e.demix_device(dev(0.5 * x), is_match_mix=True).cpu().numpy()
+    assert np.abs(got_half - 0.5 * got).max() < 1e-6  # linearity
 
 
 def test_mdx_separator_plugin_end_to_end(eng, tmp_path):
