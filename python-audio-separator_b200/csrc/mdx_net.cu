@@ -24,7 +24,7 @@ struct ConvW {       // one convolution (+ folded BatchNorm) on the device
   bool umma = false;
   void* wb_hi = nullptr;
   void* wb_lo = nullptr;
-  int kc = 0, n_tile = 0;
+  int kc = 0, n_tile = 0;  // n_tile = output channels per CTA (n_c)
 };
 struct LinW {        // TDF linear (+ folded BatchNorm over the channel axis)
   float* w = nullptr;  // [N][K]
@@ -133,27 +133,11 @@ static int upload_u16(b200sep_mdxnet* net, void** dst, const std::vector<uint16_
   return B200SEP_OK;
 }
 
-// tcgen05 B operand for a stride-1 conv: [Cout/n_tile][tap][Cin/kc][kc/16] blocks of [n_tile][16] in 8x8 core matrices
-static int make_conv_umma(b200sep_mdxnet* net, ConvW& cw, const float* w /*(Cout,Cin,k,k)*/) {
-  const int taps = cw.kh * cw.kw;
+// tcgen05 B operand of a 3x3 conv (see umma_conv_block_weights)
+static int make_conv_umma(b200sep_mdxnet* net, ConvW& cw, const float* w /*(Cout,Cin,3,3)*/) {
   umma_conv_choose(cw.cin, cw.n, &cw.kc, &cw.n_tile);
-  const int n_tiles = cw.n / cw.n_tile, n_chunks = cw.cin / cw.kc, ksteps = cw.kc / 16;
-  std::vector<uint16_t> hi((size_t)cw.n * cw.cin * taps), lo(hi.size());
-  size_t pos = 0;
-  for (int nt = 0; nt < n_tiles; ++nt)
-    for (int tap = 0; tap < taps; ++tap)
-      for (int ch = 0; ch < n_chunks; ++ch)
-        for (int j = 0; j < ksteps; ++j) {
-          for (int n = 0; n < cw.n_tile; ++n)
-            for (int kk = 0; kk < 16; ++kk) {
-              const int co = nt * cw.n_tile + n, ci = ch * cw.kc + j * 16 + kk;
-              const float v = w[((size_t)co * cw.cin + ci) * taps + tap];
-              const size_t o = pos + (size_t)((n / 8) * 2 + kk / 8) * 64 + (n % 8) * 8 + (kk % 8);
-              hi[o] = f2bf(v);
-              lo[o] = f2bf(v - bf2f(hi[o]));
-            }
-          pos += (size_t)cw.n_tile * 16;
-        }
+  std::vector<uint16_t> hi, lo;
+  umma_conv_block_weights(w, cw.n, cw.cin, cw.kc, cw.n_tile, hi, lo);
   int rc = upload_u16(net, &cw.wb_hi, hi);
   if (!rc) rc = upload_u16(net, &cw.wb_lo, lo);
   cw.umma = rc == 0;
@@ -181,6 +165,14 @@ static int make_conv(b200sep_mdxnet* net, ParamReader& rd, ConvW& cw, int cin, i
   if (!rc) rc = upload(net, &cw.scale, sc);
   if (!rc) rc = upload(net, &cw.shift, sh);
   if (!rc && net->pair && stride == 1 && k == 3 && umma_conv_supported(cin, cout, 8, k, k)) rc = make_conv_umma(net, cw, w);
+  if (!rc && net->pair && stride == 2 && k == 2 && umma_updown_supported(cin, cout, 8, 0)) {
+    umma_updown_choose(cin, cout, 0, &cw.kc, &cw.n_tile);
+    std::vector<uint16_t> hi, lo;
+    umma_down_block_weights(w, cout, cin, cw.kc, cw.n_tile, hi, lo);
+    rc = upload_u16(net, &cw.wb_hi, hi);
+    if (!rc) rc = upload_u16(net, &cw.wb_lo, lo);
+    cw.umma = rc == 0;
+  }
   return rc;
 }
 
@@ -202,6 +194,14 @@ static int make_convt(b200sep_mdxnet* net, ParamReader& rd, ConvW& cw, int cin, 
   int rc = upload(net, &cw.w, wr);
   if (!rc) rc = upload(net, &cw.scale, sc);
   if (!rc) rc = upload(net, &cw.shift, sh);
+  if (!rc && net->pair && umma_updown_supported(cin, cout, 8, 1)) {
+    umma_updown_choose(cin, cout, 1, &cw.kc, &cw.n_tile);
+    std::vector<uint16_t> hi, lo;
+    umma_up_block_weights(w, cin, cout, cw.kc, cw.n_tile, hi, lo);
+    rc = upload_u16(net, &cw.wb_hi, hi);
+    if (!rc) rc = upload_u16(net, &cw.wb_lo, lo);
+    cw.umma = rc == 0;
+  }
   return rc;
 }
 
@@ -475,13 +475,27 @@ extern "C" int b200sep_mdxnet_forward(b200sep_mdxnet* net, const float* spec_in,
     if (rc) return rc;
     in = net->io_tmp;
   }
-  rc = run_conv(net, CAT_POINTWISE, net->first, in, net->bufA[0], nullptr, B, T, F, 1, EPI_NORMAL, st, nullptr, lo_of(net, net->bufA[0], 0));
+  if (net->pair && pointwise_pair_supported(cfg.dim_c, cfg.g, (int64_t)T * F, 1)) {
+    const double pix = (double)B * T * F;
+    ProfScope ps(net, st, CAT_POINTWISE, 2.0 * pix * cfg.dim_c * cfg.g, 4.0 * pix * (cfg.dim_c + cfg.g));
+    rc = pointwise_first_pair(in, net->first.w, net->first.n_pad, net->first.scale, net->first.shift, 1, net->bufA[0], lo_of(net, net->bufA[0], 0), B, cfg.dim_c,
+                              cfg.g, (int64_t)T * F, st);
+  } else {
+    rc = run_conv(net, CAT_POINTWISE, net->first, in, net->bufA[0], nullptr, B, T, F, 1, EPI_NORMAL, st, nullptr, lo_of(net, net->bufA[0], 0));
+  }
   if (rc) return rc;
   for (int i = 0; i < n; ++i) {  // encoder (mdxnet.py:103-107)
     rc = run_block(net, net->enc[i], i, B, c, T, F, st);
     if (rc) return rc;
-    rc = run_conv(net, CAT_DOWN, net->ds[i], net->bufB[i], net->bufA[i + 1], nullptr, B, T, F, 1, EPI_NORMAL, st, lo_of(net, net->bufB[i], i),
-                  lo_of(net, net->bufA[i + 1], i + 1));
+    if (net->pair && net->ds[i].umma && net->plan_ok[i]) {
+      const ConvW& cw = net->ds[i];
+      const double pix = (double)B * (T / 2) * (F / 2);
+      ProfScope ps(net, st, CAT_DOWN, 2.0 * pix * cw.n * cw.cin * 4, 4.0 * ((double)B * cw.cin * T * F + pix * cw.n + 4.0 * cw.cin * cw.n));
+      rc = umma_down_run(net->planB[i], cw.wb_hi, cw.wb_lo, B, cw.n, cw.n_tile, cw.scale, cw.shift, 1, net->bufA[i + 1], lo_of(net, net->bufA[i + 1], i + 1), st);
+    } else {
+      rc = run_conv(net, CAT_DOWN, net->ds[i], net->bufB[i], net->bufA[i + 1], nullptr, B, T, F, 1, EPI_NORMAL, st, lo_of(net, net->bufB[i], i),
+                    lo_of(net, net->bufA[i + 1], i + 1));
+    }
     if (rc) return rc;
     T /= 2; F /= 2; c += cfg.g;
   }
@@ -489,15 +503,31 @@ extern "C" int b200sep_mdxnet_forward(b200sep_mdxnet* net, const float* spec_in,
   if (rc) return rc;
   for (int i = 0; i < n; ++i) {  // decoder (mdxnet.py:111-114): convT+BN+ReLU, multiply by the skip, TFC_TDF
     const int s = n - 1 - i;
-    rc = run_conv(net, CAT_UP, net->us[i], net->bufB[s + 1], net->bufA[s], net->bufB[s], B, T, F, 1, EPI_CONVT2X2, st, lo_of(net, net->bufB[s + 1], s + 1),
-                  lo_of(net, net->bufA[s], s), lo_of(net, net->bufB[s], s));
+    if (net->pair && net->us[i].umma && net->plan_ok[s + 1]) {
+      const ConvW& cw = net->us[i];
+      const int cr = cw.n / 4;
+      const double pix = (double)B * T * F;
+      ProfScope ps(net, st, CAT_UP, 2.0 * pix * cw.n * cw.cin, 4.0 * (pix * cw.cin + 2.0 * pix * cw.n + (double)cw.cin * cw.n));
+      rc = umma_up_run(net->planB[s + 1], cw.wb_hi, cw.wb_lo, B, cr, cw.n_tile, cw.scale, cw.shift, 1, net->bufB[s], lo_of(net, net->bufB[s], s), net->bufA[s],
+                       lo_of(net, net->bufA[s], s), st);
+    } else {
+      rc = run_conv(net, CAT_UP, net->us[i], net->bufB[s + 1], net->bufA[s], net->bufB[s], B, T, F, 1, EPI_CONVT2X2, st, lo_of(net, net->bufB[s + 1], s + 1),
+                    lo_of(net, net->bufA[s], s), lo_of(net, net->bufB[s], s));
+    }
     if (rc) return rc;
     T *= 2; F *= 2; c -= cfg.g;
     rc = run_block(net, net->dec[i], s, B, c, T, F, st);
     if (rc) return rc;
   }
   float* out = (layout == B200SEP_LAYOUT_CFT) ? net->io_tmp : spec_out;
-  rc = run_conv(net, CAT_POINTWISE, net->final, net->bufB[0], out, nullptr, B, T, F, 0, EPI_NORMAL, st, lo_of(net, net->bufB[0], 0), nullptr);
+  if (net->pair && pointwise_pair_supported(cfg.g, cfg.dim_c, (int64_t)T * F, 0)) {
+    const double pix = (double)B * T * F;
+    ProfScope ps(net, st, CAT_POINTWISE, 2.0 * pix * cfg.dim_c * cfg.g, 4.0 * pix * (cfg.dim_c + cfg.g));
+    rc = pointwise_last_pair(net->bufB[0], lo_of(net, net->bufB[0], 0), net->final.w, net->final.n_pad, net->final.scale, net->final.shift, 0, out, B, cfg.g,
+                             cfg.dim_c, (int64_t)T * F, st);
+  } else {
+    rc = run_conv(net, CAT_POINTWISE, net->final, net->bufB[0], out, nullptr, B, T, F, 0, EPI_NORMAL, st, lo_of(net, net->bufB[0], 0), nullptr);
+  }
   if (rc) return rc;
   if (layout == B200SEP_LAYOUT_CFT) {
     ProfScope ps(net, st, CAT_TRANSPOSE, 0.0, 8.0 * B * cfg.dim_c * T * F);

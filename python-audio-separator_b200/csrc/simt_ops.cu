@@ -269,6 +269,106 @@ int gemm_tn_simt(const GemmParams& p, cudaStream_t stream) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Bandwidth-bound 1x1 convolutions at the network's ends in pair mode (8 pixels per thread, 16-byte plane accesses).
+// first: fp32 (B,Cin<=8,P) -> pair (B,Cout,P) with BN+ReLU;  last: pair (B,Cin,P) -> fp32 (B,Cout<=8,P), bias only.
+__global__ void __launch_bounds__(256) pointwise_first_kernel(const float* __restrict__ x, const float* __restrict__ w, int w_stride,
+                                                             const float* __restrict__ scale, const float* __restrict__ shift, int relu, bf16* __restrict__ y_hi,
+                                                             bf16* __restrict__ y_lo, int Cin, int Cout, int64_t P) {
+  const int b = blockIdx.y;
+  const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (p0 >= P) return;
+  float xv[8][8];
+  for (int ci = 0; ci < Cin; ++ci) {
+    const float4* s = reinterpret_cast<const float4*>(x + ((int64_t)b * Cin + ci) * P + p0);
+    const float4 a = __ldg(s), c = __ldg(s + 1);
+    xv[ci][0] = a.x; xv[ci][1] = a.y; xv[ci][2] = a.z; xv[ci][3] = a.w; xv[ci][4] = c.x; xv[ci][5] = c.y; xv[ci][6] = c.z; xv[ci][7] = c.w;
+  }
+  for (int co = 0; co < Cout; ++co) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int ci = 0; ci < Cin; ++ci) {
+      const float wv = __ldg(&w[ci * w_stride + co]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(xv[ci][i], wv, acc[i]);
+    }
+    const float sc = __ldg(&scale[co]), sh = __ldg(&shift[co]);
+    __align__(16) bf16 h[8];
+    __align__(16) bf16 l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v = fmaf(acc[i], sc, sh);
+      if (relu) v = fmaxf(v, 0.f);
+      h[i] = __float2bfloat16_rn(v);
+      l[i] = __float2bfloat16_rn(v - __bfloat162float(h[i]));
+    }
+    const int64_t o = ((int64_t)b * Cout + co) * P + p0;
+    *reinterpret_cast<uint4*>(y_hi + o) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(y_lo + o) = *reinterpret_cast<const uint4*>(l);
+  }
+}
+
+__global__ void __launch_bounds__(256) pointwise_last_kernel(const bf16* __restrict__ x_hi, const bf16* __restrict__ x_lo, const float* __restrict__ w, int w_stride,
+                                                            const float* __restrict__ scale, const float* __restrict__ shift, int relu, float* __restrict__ y, int Cin,
+                                                            int Cout, int64_t P) {
+  const int b = blockIdx.y;
+  const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (p0 >= P) return;
+  float acc[8][8];
+#pragma unroll
+  for (int co = 0; co < 8; ++co)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[co][i] = 0.f;
+  for (int ci = 0; ci < Cin; ++ci) {
+    const int64_t o = ((int64_t)b * Cin + ci) * P + p0;
+    const uint4 hv = __ldg(reinterpret_cast<const uint4*>(x_hi + o)), lv = __ldg(reinterpret_cast<const uint4*>(x_lo + o));
+    const bf16* h = reinterpret_cast<const bf16*>(&hv);
+    const bf16* l = reinterpret_cast<const bf16*>(&lv);
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __bfloat162float(h[i]) + __bfloat162float(l[i]);
+#pragma unroll
+    for (int co = 0; co < 8; ++co) {
+      if (co < Cout) {
+        const float wv = __ldg(&w[ci * w_stride + co]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[co][i] = fmaf(v[i], wv, acc[co][i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int co = 0; co < 8; ++co) {
+    if (co < Cout) {
+      const float sc = __ldg(&scale[co]), sh = __ldg(&shift[co]);
+      float r[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        r[i] = fmaf(acc[co][i], sc, sh);
+        if (relu) r[i] = fmaxf(r[i], 0.f);
+      }
+      float4* d = reinterpret_cast<float4*>(y + ((int64_t)b * Cout + co) * P + p0);
+      d[0] = make_float4(r[0], r[1], r[2], r[3]);
+      d[1] = make_float4(r[4], r[5], r[6], r[7]);
+    }
+  }
+}
+
+bool pointwise_pair_supported(int Cin, int Cout, int64_t P, int first) { return P % 8 == 0 && (first ? Cin <= 8 : Cout <= 8); }
+
+int pointwise_first_pair(const float* x, const float* w, int w_stride, const float* scale, const float* shift, int relu, void* y_hi, void* y_lo, int B, int Cin,
+                         int Cout, int64_t P, cudaStream_t st) {
+  dim3 grid(cdiv(P / 8, 256), B);
+  pointwise_first_kernel<<<grid, 256, 0, st>>>(x, w, w_stride, scale, shift, relu, (bf16*)y_hi, (bf16*)y_lo, Cin, Cout, P);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+int pointwise_last_pair(const void* x_hi, const void* x_lo, const float* w, int w_stride, const float* scale, const float* shift, int relu, float* y, int B, int Cin,
+                        int Cout, int64_t P, cudaStream_t st) {
+  dim3 grid(cdiv(P / 8, 256), B);
+  pointwise_last_kernel<<<grid, 256, 0, st>>>((const bf16*)x_hi, (const bf16*)x_lo, w, w_stride, scale, shift, relu, y, Cin, Cout, P);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 __global__ void transpose_hw_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W) {
   __shared__ float tile[32][33];
   const int64_t plane = (int64_t)blockIdx.z * H * W;

@@ -53,6 +53,13 @@ struct GemmParams {
 };
 int gemm_tn_simt(const GemmParams& p, cudaStream_t stream);
 
+// 1x1 convolutions at the ends of a network in pair mode (see simt_ops.cu)
+bool pointwise_pair_supported(int Cin, int Cout, int64_t P, int first);
+int pointwise_first_pair(const float* x, const float* w, int w_stride, const float* scale, const float* shift, int relu, void* y_hi, void* y_lo, int B, int Cin,
+                         int Cout, int64_t P, cudaStream_t st);
+int pointwise_last_pair(const void* x_hi, const void* x_lo, const float* w, int w_stride, const float* scale, const float* shift, int relu, float* y, int B, int Cin,
+                        int Cout, int64_t P, cudaStream_t st);
+
 // (B, C, H, W) <-> (B, C, W, H) transpose of the two innermost axes (layout CFT <-> CTF at the C ABI)
 int transpose_hw(const float* x, float* y, int planes, int H, int W, cudaStream_t stream);
 

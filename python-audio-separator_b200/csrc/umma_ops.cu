@@ -9,9 +9,14 @@
 //
 // One kernel, two addressing modes:
 //   GEMM : D[M][N] = A[M][K] * W[N][K]^T     (TDF linears; A, W K-major, TMA SWIZZLE_128B tiles of 64 k)
-//   CONV : implicit GEMM for stride-1 KHxKW convolution on (B,C,T,F) pairs; the A tile of one tap is a TMA box
-//          [kc channels][128 pixels along F] shifted by (dy,dx) with out-of-bounds zero fill = the padding;
-//          the box lands MN-major (pixels contiguous) which tcgen05 consumes directly (a_major = MN).
+//   CONV : implicit GEMM for the 3x3 stride-1 convolution on (B,C,T,F) pairs.  The A tile of one filter ROW dy is a
+//          TMA box [kc channels][128 pixels along F] at row t+dy-1 (out-of-bounds rows zero-filled = the padding); it
+//          lands MN-major (pixels contiguous), which tcgen05 consumes directly (a_major = MN).  TMA cannot shift a box
+//          by one bf16 along the innermost axis (box starts must be 16-byte aligned -- measured: illegal instruction),
+//          so the horizontal taps are moved to the OUTPUT side: B holds the three dx filter columns side by side
+//          (N = 3*n_c accumulator columns, P_dx[m] = W[dy][dx] . x[f0+m]) and the epilogue forms
+//          out[f0+j] = P_0[j-1] + P_1[j] + P_2[j+1] with warp shuffles (+ a small smem exchange at warp edges).
+//          Tiles advance by 120 pixels so that every output has both neighbours inside the same 128-row tile.
 // Warp roles per CTA (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer, warps 2-5 = epilogue.
 #include <cuda_bf16.h>
 #include <string.h>
@@ -27,14 +32,16 @@ namespace b200sep {
 using bf16 = __nv_bfloat16;
 constexpr int kUmmaThreads = 192;
 constexpr int kTileM = 128;
+constexpr int kConvStride = 120;  // output pixels per conv tile (multiple of 8: TMA box starts must be 16-byte aligned)
 
 struct UmmaParams {
-  int mode;  // 0 GEMM, 1 CONV
+  int mode;  // 0 GEMM, 1 CONV3x3, 2 UP (ConvTranspose2d k2 s2), 3 DOWN (Conv2d k2 s2)
+  int f_stride, t_mul, t_off;  // implicit-GEMM addressing: tile f0 = blockIdx.x*f_stride, input row = t*t_mul + r + t_off
   int n_tile, n_total, tmem_cols;
   int num_iters, ksteps, stages;
   uint32_t a_bytes, b_bytes, stage_bytes;
   // CONV
-  int kw, pad, n_chunks, kc, T, F, Cin, Cout, n_tiles;
+  int n_chunks, kc, T, F, Cin, Cout, n_tiles, n_c;  // n_c = output channels per CTA; n_tile = 3*n_c accumulator columns
   const bf16* wb_hi;
   const bf16* wb_lo;
   // GEMM
@@ -45,7 +52,7 @@ struct UmmaParams {
   int relu;
   bf16* out_hi;
   bf16* out_lo;
-  const bf16* res_hi;
+  const bf16* res_hi;  // GEMM: residual added after the activation.  UP: skip tensor multiplied after the activation.
   const bf16* res_lo;
 };
 
@@ -64,6 +71,7 @@ __global__ void __launch_bounds__(kUmmaThreads) umma_pair_kernel(const __grid_co
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full_bar = empty_bar + p.stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* edge = reinterpret_cast<float*>(tmem_slot + 4);  // CONV: [2][4 warps][n_c] boundary rows exchanged between epilogue warps
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -73,12 +81,12 @@ __global__ void __launch_bounds__(kUmmaThreads) umma_pair_kernel(const __grid_co
     n_idx = blockIdx.x;
     m0 = blockIdx.y * kTileM;
   } else {
-    f0 = blockIdx.x * kTileM;
+    f0 = blockIdx.x * p.f_stride;
     t = blockIdx.y;
     n_idx = blockIdx.z % p.n_tiles;
     b = blockIdx.z / p.n_tiles;
   }
-  const int n0 = n_idx * p.n_tile;
+  const int n0 = n_idx * (p.mode == 0 ? p.n_tile : p.n_c);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -106,7 +114,7 @@ __global__ void __launch_bounds__(kUmmaThreads) umma_pair_kernel(const __grid_co
       int s = 0;
       uint32_t phase = 0;
       for (int i = 0; i < p.num_iters; ++i) {
-        ptx::mbar_wait(&empty_bar[s], phase ^ 1);
+        ptx::mbar_wait(&empty_bar[s], phase ^ 1, 100 + i);
         uint8_t* st = smem + (size_t)s * p.stage_bytes;
         uint8_t* a_hi = st;
         uint8_t* a_lo = st + p.a_bytes;
@@ -120,9 +128,8 @@ __global__ void __launch_bounds__(kUmmaThreads) umma_pair_kernel(const __grid_co
           ptx::tma_load_2d(b_hi, &tmB_hi, &full_bar[s], k0, n0);
           ptx::tma_load_2d(b_lo, &tmB_lo, &full_bar[s], k0, n0);
         } else {
-          const int tap = i / p.n_chunks, chunk = i - tap * p.n_chunks;
-          const int dy = tap / p.kw, dx = tap - dy * p.kw;
-          const int cf = f0 + dx - p.pad, ct = t + dy - p.pad, cc = b * p.Cin + chunk * p.kc;
+          const int r = i / p.n_chunks, chunk = i - r * p.n_chunks;
+          const int cf = f0, ct = t * p.t_mul + r + p.t_off, cc = b * p.Cin + chunk * p.kc;
           const uint32_t box = (uint32_t)p.kc * 128u;
           ptx::tma_load_3d(a_hi, &tmA_hi, &full_bar[s], cf, ct, cc);
           ptx::tma_load_3d(a_hi + box, &tmA_hi, &full_bar[s], cf + 64, ct, cc);
@@ -141,11 +148,11 @@ __global__ void __launch_bounds__(kUmmaThreads) umma_pair_kernel(const __grid_co
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      const uint32_t idesc = ptx::instr_desc_bf16(kTileM, p.n_tile, p.mode == 1 ? 1 : 0, 0);
+      const uint32_t idesc = ptx::instr_desc_bf16(kTileM, p.n_tile, p.mode != 0 ? 1 : 0, 0);
       int s = 0;
       uint32_t phase = 0;
       for (int i = 0; i < p.num_iters; ++i) {
-        ptx::mbar_wait(&full_bar[s], phase);
+        ptx::mbar_wait(&full_bar[s], phase, 200 + i);
         ptx::tc_fence_after();
         const uint32_t st = ptx::smem_u32(smem + (size_t)s * p.stage_bytes);
         const uint32_t a_hi = st, a_lo = st + p.a_bytes, b_hi = st + 2 * p.a_bytes, b_lo = b_hi + p.b_bytes;
@@ -180,7 +187,7 @@ __global__ void __launch_bounds__(kUmmaThreads) umma_pair_kernel(const __grid_co
     // ===== epilogue: TMEM -> registers -> BN/ReLU(/+res) -> split -> global =====
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const int m = q * 32 + lane;
-    ptx::mbar_wait(tmem_full_bar, 0);
+    ptx::mbar_wait(tmem_full_bar, 0, 300);
     ptx::tc_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     if (p.mode == 0) {
@@ -227,20 +234,117 @@ __global__ void __launch_bounds__(kUmmaThreads) umma_pair_kernel(const __grid_co
           dl[1] = reinterpret_cast<const uint4*>(ol)[1];
         }
       }
-    } else {
+    } else if (p.mode == 2) {
+      // ConvTranspose2d k2 s2: column (dy*2+dx)*n_c + co of lane m is the output pixel (2t+dy, 2(f0+m)+dx) of channel co;
+      // then BN + ReLU, times the skip tensor (uvr_lib_v5/mdxnet.py:111-112).  The two dx values are stored as one 4-byte pair.
+      const int nc = p.n_c;
       const int f = f0 + m;
       const bool row_ok = f < p.F;
-      const size_t plane = (size_t)p.T * p.F;
-      const size_t base = ((size_t)b * p.Cout) * plane + (size_t)t * p.F + f;
-      for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
-        uint32_t v[16];
-        ptx::tmem_ld16(trow + (uint32_t)c0, v);
+      const int T2 = 2 * p.T, F2 = 2 * p.F;
+      const size_t plane = (size_t)T2 * F2;
+      for (int dy = 0; dy < 2; ++dy) {
+        const size_t base = ((size_t)b * p.Cout) * plane + (size_t)(2 * t + dy) * F2 + 2 * f;
+        for (int c0 = 0; c0 < nc; c0 += 16) {
+          uint32_t v0[16], v1[16];
+          ptx::tmem_ld16(trow + (uint32_t)((dy * 2 + 0) * nc + c0), v0);
+          ptx::tmem_ld16(trow + (uint32_t)((dy * 2 + 1) * nc + c0), v1);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int co = n0 + c0 + j;
+            if (row_ok && co < p.Cout) {
+              const float sc = __ldg(&p.scale[co]), sh = __ldg(&p.shift[co]);
+              float x0 = fmaf(__uint_as_float(v0[j]), sc, sh), x1 = fmaf(__uint_as_float(v1[j]), sc, sh);
+              if (p.relu) {
+                x0 = fmaxf(x0, 0.f);
+                x1 = fmaxf(x1, 0.f);
+              }
+              const size_t o = base + (size_t)co * plane;
+              if (p.res_hi) {
+                const __nv_bfloat162 sh2 = *reinterpret_cast<const __nv_bfloat162*>(p.res_hi + o);
+                const __nv_bfloat162 sl2 = *reinterpret_cast<const __nv_bfloat162*>(p.res_lo + o);
+                x0 *= __bfloat162float(sh2.x) + __bfloat162float(sl2.x);
+                x1 *= __bfloat162float(sh2.y) + __bfloat162float(sl2.y);
+              }
+              __nv_bfloat162 oh, ol;
+              split_store2(x0, oh.x, ol.x);
+              split_store2(x1, oh.y, ol.y);
+              *reinterpret_cast<__nv_bfloat162*>(p.out_hi + o) = oh;  // 32 lanes -> 128 contiguous bytes
+              *reinterpret_cast<__nv_bfloat162*>(p.out_lo + o) = ol;
+            }
+          }
+        }
+      }
+    } else if (p.mode == 3) {
+      // Conv2d k2 s2: P_dx[m] (column dx*n_c + co) is the partial sum over (ci, dy) at INPUT pixel f0+m;
+      // out[(f0+m)/2] = P_0[m] + P_1[m+1] for even m (odd rows of P_0 / even rows of P_1 are computed but unused).
+      const int nc = p.n_c;
+      const int fo = (f0 + m) >> 1, Fo = p.F >> 1, To = p.T >> 1;
+      const bool row_ok = ((m & 1) == 0) && fo < Fo;
+      const size_t plane = (size_t)To * Fo;
+      const size_t base = ((size_t)b * p.Cout) * plane + (size_t)t * Fo + fo;
+      for (int c0 = 0; c0 < nc; c0 += 16) {
+        uint32_t v0[16], v1[16];
+        ptx::tmem_ld16(trow + (uint32_t)c0, v0);
+        ptx::tmem_ld16(trow + (uint32_t)(nc + c0), v1);
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
+          const float nb = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[j]), 1);  // P_1 of row m+1 (same warp: m even)
           const int co = n0 + c0 + j;
           if (row_ok && co < p.Cout) {
-            float x = fmaf(__uint_as_float(v[j]), __ldg(&p.scale[co]), __ldg(&p.shift[co]));
+            float x = fmaf(__uint_as_float(v0[j]) + nb, __ldg(&p.scale[co]), __ldg(&p.shift[co]));
+            if (p.relu) x = fmaxf(x, 0.f);
+            bf16 h, l;
+            split_store2(x, h, l);
+            const size_t o = base + (size_t)co * plane;
+            p.out_hi[o] = h;
+            p.out_lo[o] = l;
+          }
+        }
+      }
+    } else {
+      // P_dx[m][co] sits in column dx*n_c + co of TMEM lane m.  out[f0+j] = P_0[j-1] + P_1[j] + P_2[j+1].
+      const int nc = p.n_c;
+      float* edge0 = edge + q * nc;             // this warp's row 32q+31 of P_0 (needed by lane 0 of warp q+1)
+      float* edge2 = edge + (4 + q) * nc;       // this warp's row 32q    of P_2 (needed by lane 31 of warp q-1)
+      for (int c0 = 0; c0 < nc; c0 += 16) {
+        uint32_t v0[16], v2[16];
+        ptx::tmem_ld16(trow + (uint32_t)c0, v0);
+        ptx::tmem_ld16(trow + (uint32_t)(2 * nc + c0), v2);
+        ptx::tmem_ld_wait();
+        if (lane == 31) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) edge0[c0 + j] = __uint_as_float(v0[j]);
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) edge2[c0 + j] = __uint_as_float(v2[j]);
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+      const float* left = edge + (q - 1) * nc;        // valid for q > 0
+      const float* right = edge + (4 + q + 1) * nc;   // valid for q < 3
+      const int f = f0 + m;
+      const int j_lo = (f0 == 0) ? 0 : 1;
+      const bool row_ok = (m >= j_lo) && (m < kConvStride + 1) && (f < p.F);
+      const size_t plane = (size_t)p.T * p.F;
+      const size_t base = ((size_t)b * p.Cout) * plane + (size_t)t * p.F + f;
+      for (int c0 = 0; c0 < nc; c0 += 16) {
+        uint32_t v0[16], v1[16], v2[16];
+        ptx::tmem_ld16(trow + (uint32_t)c0, v0);
+        ptx::tmem_ld16(trow + (uint32_t)(nc + c0), v1);
+        ptx::tmem_ld16(trow + (uint32_t)(2 * nc + c0), v2);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float a = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[j]), 1);    // P_0 of row m-1
+          float c = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[j]), 1);  // P_2 of row m+1
+          if (lane == 0) a = (q > 0) ? left[c0 + j] : 0.f;   // m == 0: x[f0-1] is either padding (f0 == 0) or not an output row
+          if (lane == 31) c = (q < 3) ? right[c0 + j] : 0.f;  // m == 127 is never an output row
+          const int co = n0 + c0 + j;
+          if (row_ok && co < p.Cout) {
+            float x = fmaf(a + __uint_as_float(v1[j]) + c, __ldg(&p.scale[co]), __ldg(&p.shift[co]));
             if (p.relu) x = fmaxf(x, 0.f);
             bf16 h, l;
             split_store2(x, h, l);
@@ -310,13 +414,14 @@ static int pow2_cols(int n) {
 static int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo, UmmaParams& p, dim3 grid,
                   cudaStream_t st) {
   p.stage_bytes = ((2 * p.a_bytes + 2 * p.b_bytes + 1023) / 1024) * 1024;
-  const int budget = 100 * 1024;  // two CTAs per SM so one tile's epilogue overlaps the other's main loop
+  const int budget = 108 * 1024;  // two CTAs per SM so one tile's epilogue overlaps the other's main loop
   int stages = (int)(budget / p.stage_bytes);
   if (stages < 2) stages = 2;
   if (stages > 6) stages = 6;
   if (stages > p.num_iters) stages = p.num_iters;
   p.stages = stages;
-  const size_t smem = (size_t)stages * p.stage_bytes + 1024 /*alignment slack*/ + (2 * stages + 1) * sizeof(uint64_t) + 16;
+  const size_t smem = (size_t)stages * p.stage_bytes + 1024 /*alignment slack*/ + (2 * stages + 1) * sizeof(uint64_t) + 16 +
+                      (p.mode != 0 ? (size_t)8 * p.n_c * sizeof(float) : 0);
   B2_CHECK_ARG(smem <= 227 * 1024, "umma: tile needs %zu bytes of shared memory", smem);
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
@@ -364,20 +469,23 @@ int umma_gemm_run(const UmmaGemmPlan& pl, const float* scale, const float* shift
 }
 
 bool umma_conv_supported(int Cin, int Cout, int F, int kh, int kw) {
-  return Cin % 16 == 0 && Cout % 16 == 0 && F % 8 == 0 && kh == kw && (kh == 3 || kh == 1);
+  return Cin % 16 == 0 && Cout % 16 == 0 && F % 8 == 0 && kh == 3 && kw == 3;
 }
 
-int umma_conv_choose(int Cin, int Cout, int* kc, int* n_tile) {
+// kc = input channels per pipeline stage, n_c = output channels per CTA (3*n_c accumulator columns <= 256)
+int umma_conv_choose(int Cin, int Cout, int* kc, int* n_c) {
   int k = 64;
   while (k > 16 && Cin % k != 0) k -= 16;
   if (Cin % 48 == 0) k = 48;
   *kc = k;
-  int nt = Cout;
-  if (nt > 256) {
-    for (nt = 256; nt >= 16; nt -= 16)
-      if (Cout % nt == 0) break;
-  }
-  *n_tile = nt;
+  int nc = 16;
+  const int cand[5] = {48, 80, 64, 32, 16};
+  for (int i = 0; i < 5; ++i)
+    if (Cout % cand[i] == 0) {
+      nc = cand[i];
+      break;
+    }
+  *n_c = nc;
   return 0;
 }
 
@@ -391,21 +499,157 @@ int umma_conv_plan_create(UmmaConvPlan* pl, const void* x_hi, const void* x_lo, 
   return rc;
 }
 
-int umma_conv_run(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_lo, int B, int Cout, int n_tile, int ksize, const float* scale,
+int umma_conv_run(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_lo, int B, int Cout, int n_c, int ksize, const float* scale,
                   const float* shift, int relu, void* out_hi, void* out_lo, cudaStream_t st) {
+  B2_CHECK_ARG(ksize == 3, "umma_conv: only 3x3 kernels");
   UmmaParams p{};
-  p.mode = 1;
-  p.n_tile = n_tile; p.n_total = Cout; p.tmem_cols = pow2_cols(n_tile);
-  p.kw = ksize; p.pad = (ksize - 1) / 2; p.kc = pl.kc; p.n_chunks = pl.Cin / pl.kc;
-  p.num_iters = ksize * ksize * p.n_chunks; p.ksteps = pl.kc / 16;
-  p.a_bytes = (uint32_t)pl.kc * 256; p.b_bytes = (uint32_t)p.ksteps * n_tile * 32;
-  p.T = pl.T; p.F = pl.F; p.Cin = pl.Cin; p.Cout = Cout; p.n_tiles = Cout / n_tile;
+  p.mode = 1; p.f_stride = kConvStride; p.t_mul = 1; p.t_off = -1;
+  p.n_c = n_c; p.n_tile = 3 * n_c; p.n_total = Cout; p.tmem_cols = pow2_cols(3 * n_c);
+  p.kc = pl.kc; p.n_chunks = pl.Cin / pl.kc;
+  p.num_iters = 3 * p.n_chunks; p.ksteps = pl.kc / 16;
+  p.a_bytes = (uint32_t)pl.kc * 256; p.b_bytes = (uint32_t)p.ksteps * p.n_tile * 32;
+  p.T = pl.T; p.F = pl.F; p.Cin = pl.Cin; p.Cout = Cout; p.n_tiles = Cout / n_c;
   p.wb_hi = (const bf16*)wb_hi; p.wb_lo = (const bf16*)wb_lo;
   p.scale = scale; p.shift = shift; p.relu = relu;
   p.out_hi = (bf16*)out_hi; p.out_lo = (bf16*)out_lo;
-  dim3 grid(cdiv(pl.F, kTileM), pl.T, B * p.n_tiles);
+  dim3 grid(pl.F <= 1 ? 1 : cdiv(pl.F - 1, kConvStride), pl.T, B * p.n_tiles);
   B2_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "umma_conv: grid too large");
   return launch(pl.a_hi, pl.a_lo, pl.a_hi, pl.a_lo, p, grid, st);
+}
+
+static int pick_nc(int Cout, int mult, int limit) {  // largest n_c | Cout with mult*n_c <= limit and mult*n_c % 16 == 0
+  for (int nc = Cout; nc >= 4; --nc)
+    if (Cout % nc == 0 && mult * nc <= limit && (mult * nc) % 16 == 0 && nc % 16 == 0) return nc;
+  return 0;
+}
+bool umma_updown_supported(int Cin, int Cout, int F_in, int up) {
+  return Cin % 16 == 0 && F_in % 8 == 0 && pick_nc(Cout, up ? 4 : 2, 256) > 0 && (up || F_in % 2 == 0);
+}
+int umma_updown_choose(int Cin, int Cout, int up, int* kc, int* n_c) {
+  int k = 64;
+  while (k > 16 && Cin % k != 0) k -= 16;
+  if (Cin % 48 == 0) k = 48;
+  *kc = k;
+  *n_c = pick_nc(Cout, up ? 4 : 2, up ? 192 : 256);
+  if (*n_c == 0) *n_c = pick_nc(Cout, up ? 4 : 2, 256);
+  return 0;
+}
+
+// x: pair (B, Cin, T, F) -> ConvTranspose2d(k2,s2)+BN+ReLU (* skip) -> pair (B, Cout, 2T, 2F)
+int umma_up_run(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_lo, int B, int Cout, int n_c, const float* scale, const float* shift, int relu,
+                const void* skip_hi, const void* skip_lo, void* out_hi, void* out_lo, cudaStream_t st) {
+  UmmaParams p{};
+  p.mode = 2; p.f_stride = kTileM; p.t_mul = 1; p.t_off = 0;
+  p.n_c = n_c; p.n_tile = 4 * n_c; p.n_total = Cout; p.tmem_cols = pow2_cols(4 * n_c);
+  p.kc = pl.kc; p.n_chunks = pl.Cin / pl.kc; p.num_iters = p.n_chunks; p.ksteps = pl.kc / 16;
+  p.a_bytes = (uint32_t)pl.kc * 256; p.b_bytes = (uint32_t)p.ksteps * p.n_tile * 32;
+  p.T = pl.T; p.F = pl.F; p.Cin = pl.Cin; p.Cout = Cout; p.n_tiles = Cout / n_c;
+  p.wb_hi = (const bf16*)wb_hi; p.wb_lo = (const bf16*)wb_lo;
+  p.scale = scale; p.shift = shift; p.relu = relu;
+  p.out_hi = (bf16*)out_hi; p.out_lo = (bf16*)out_lo; p.res_hi = (const bf16*)skip_hi; p.res_lo = (const bf16*)skip_lo;
+  dim3 grid(cdiv(pl.F, kTileM), pl.T, B * p.n_tiles);
+  B2_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "umma_up: grid too large");
+  return launch(pl.a_hi, pl.a_lo, pl.a_hi, pl.a_lo, p, grid, st);
+}
+
+// x: pair (B, Cin, T, F) -> Conv2d(k2,s2)+BN+ReLU -> pair (B, Cout, T/2, F/2)
+int umma_down_run(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_lo, int B, int Cout, int n_c, const float* scale, const float* shift, int relu,
+                  void* out_hi, void* out_lo, cudaStream_t st) {
+  UmmaParams p{};
+  p.mode = 3; p.f_stride = kTileM; p.t_mul = 2; p.t_off = 0;
+  p.n_c = n_c; p.n_tile = 2 * n_c; p.n_total = Cout; p.tmem_cols = pow2_cols(2 * n_c);
+  p.kc = pl.kc; p.n_chunks = pl.Cin / pl.kc; p.num_iters = 2 * p.n_chunks; p.ksteps = pl.kc / 16;
+  p.a_bytes = (uint32_t)pl.kc * 256; p.b_bytes = (uint32_t)p.ksteps * p.n_tile * 32;
+  p.T = pl.T; p.F = pl.F; p.Cin = pl.Cin; p.Cout = Cout; p.n_tiles = Cout / n_c;
+  p.wb_hi = (const bf16*)wb_hi; p.wb_lo = (const bf16*)wb_lo;
+  p.scale = scale; p.shift = shift; p.relu = relu;
+  p.out_hi = (bf16*)out_hi; p.out_lo = (bf16*)out_lo;
+  dim3 grid(cdiv(pl.F, kTileM), pl.T / 2, B * p.n_tiles);
+  B2_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "umma_down: grid too large");
+  return launch(pl.a_hi, pl.a_lo, pl.a_hi, pl.a_lo, p, grid, st);
+}
+
+// Generic blocking: value(row, r, ci) for B rows [rows], row taps [n_r], -> [Cout/n_c][r][Cin/kc][kc/16][rows x 16 core-matrix tiled]
+template <class F>
+static void block_weights(int n_tiles, int n_r, int Cin, int kc, int rows, F value, std::vector<uint16_t>& hi, std::vector<uint16_t>& lo) {
+  auto f2bf = [](float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+  };
+  auto bf2f = [](uint16_t h) {
+    uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+  };
+  const int n_chunks = Cin / kc, ksteps = kc / 16;
+  hi.assign((size_t)n_tiles * n_r * Cin * rows, 0);
+  lo.assign(hi.size(), 0);
+  size_t pos = 0;
+  for (int nt = 0; nt < n_tiles; ++nt)
+    for (int r = 0; r < n_r; ++r)
+      for (int ch = 0; ch < n_chunks; ++ch)
+        for (int j = 0; j < ksteps; ++j) {
+          for (int row = 0; row < rows; ++row)
+            for (int kk = 0; kk < 16; ++kk) {
+              const float v = value(nt, row, r, ch * kc + j * 16 + kk);
+              const size_t o = pos + (size_t)((row / 8) * 2 + kk / 8) * 64 + (row % 8) * 8 + (kk % 8);
+              hi[o] = f2bf(v);
+              lo[o] = f2bf(v - bf2f(hi[o]));
+            }
+          pos += (size_t)rows * 16;
+        }
+}
+// ConvTranspose2d weight (Cin, Cout, 2, 2): B rows = (q = dy*2+dx, co_local)
+void umma_up_block_weights(const float* w, int Cin, int Cout, int kc, int n_c, std::vector<uint16_t>& hi, std::vector<uint16_t>& lo) {
+  block_weights(Cout / n_c, 1, Cin, kc, 4 * n_c, [&](int nt, int row, int, int ci) {
+    const int q = row / n_c, co = nt * n_c + row % n_c;
+    return w[((size_t)ci * Cout + co) * 4 + q];
+  }, hi, lo);
+}
+// Conv2d weight (Cout, Cin, 2, 2) stride 2: row taps r = dy, B rows = (dx, co_local)
+void umma_down_block_weights(const float* w, int Cout, int Cin, int kc, int n_c, std::vector<uint16_t>& hi, std::vector<uint16_t>& lo) {
+  block_weights(Cout / n_c, 2, Cin, kc, 2 * n_c, [&](int nt, int row, int dy, int ci) {
+    const int dx = row / n_c, co = nt * n_c + row % n_c;
+    return w[(((size_t)co * Cin + ci) * 2 + dy) * 2 + dx];
+  }, hi, lo);
+}
+
+// Host-side blocking of a (Cout, Cin, 3, 3) fp32 filter into the B operand stream of umma_conv_run:
+// [Cout/n_c][dy][Cin/kc][kc/16] blocks of [3*n_c rows = (dx, co)][16 k] stored as 8x8 core matrices (K-major, no swizzle).
+void umma_conv_block_weights(const float* w, int Cout, int Cin, int kc, int n_c, std::vector<uint16_t>& hi, std::vector<uint16_t>& lo) {
+  auto f2bf = [](float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+  };
+  auto bf2f = [](uint16_t h) {
+    uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+  };
+  const int n_tiles = Cout / n_c, n_chunks = Cin / kc, ksteps = kc / 16, rows = 3 * n_c;
+  hi.assign((size_t)Cout * Cin * 9, 0);
+  lo.assign(hi.size(), 0);
+  size_t pos = 0;
+  for (int nt = 0; nt < n_tiles; ++nt)
+    for (int dy = 0; dy < 3; ++dy)
+      for (int ch = 0; ch < n_chunks; ++ch)
+        for (int j = 0; j < ksteps; ++j) {
+          for (int r = 0; r < rows; ++r)
+            for (int kk = 0; kk < 16; ++kk) {
+              const int dx = r / n_c, co = nt * n_c + r % n_c, ci = ch * kc + j * 16 + kk;
+              const float v = w[(((size_t)co * Cin + ci) * 3 + dy) * 3 + dx];
+              const size_t o = pos + (size_t)((r / 8) * 2 + kk / 8) * 64 + (r % 8) * 8 + (kk % 8);
+              hi[o] = f2bf(v);
+              lo[o] = f2bf(v - bf2f(hi[o]));
+            }
+          pos += (size_t)rows * 16;
+        }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -437,19 +681,6 @@ int join_pair(const void* hi, const void* lo, float* y, int64_t n, cudaStream_t 
 // isolation against a plain fp32 reference): fp32 in -> split -> tcgen05 op -> join -> fp32 out.
 using namespace b200sep;
 
-static inline uint16_t st_f2bf(float f) {
-  uint32_t u;
-  memcpy(&u, &f, 4);
-  u += 0x7fffu + ((u >> 16) & 1u);
-  return (uint16_t)(u >> 16);
-}
-static inline float st_bf2f(uint16_t h) {
-  uint32_t u = (uint32_t)h << 16;
-  float f;
-  memcpy(&f, &u, 4);
-  return f;
-}
-
 extern "C" int b200sep_selftest_umma_gemm(const float* a, const float* w, const float* res, float* out, int M, int N, int K, int rows_per_channel,
                                           int channels, const float* scale, const float* shift, int relu, void* stream) {
   B2_CHECK_ARG(a && w && out && scale && shift, "selftest_umma_gemm: NULL argument");
@@ -479,24 +710,10 @@ extern "C" int b200sep_selftest_umma_conv3x3(const float* x, const float* w_host
   B2_CHECK_ARG(x && w_host && out && scale && shift, "selftest_umma_conv3x3: NULL argument");
   B2_CHECK_ARG(umma_conv_supported(Cin, Cout, F, 3, 3), "selftest_umma_conv3x3: Cin=%d Cout=%d F=%d not supported by the tensor-core path", Cin, Cout, F);
   cudaStream_t st = (cudaStream_t)stream;
-  int kc, n_tile;
-  umma_conv_choose(Cin, Cout, &kc, &n_tile);
-  const int taps = 9, n_tiles = Cout / n_tile, n_chunks = Cin / kc, ksteps = kc / 16;
-  std::vector<uint16_t> hi((size_t)Cout * Cin * taps), lo(hi.size());
-  size_t pos = 0;
-  for (int nt = 0; nt < n_tiles; ++nt)
-    for (int tap = 0; tap < taps; ++tap)
-      for (int ch = 0; ch < n_chunks; ++ch)
-        for (int j = 0; j < ksteps; ++j) {
-          for (int n = 0; n < n_tile; ++n)
-            for (int kk = 0; kk < 16; ++kk) {
-              const float v = w_host[((size_t)(nt * n_tile + n) * Cin + ch * kc + j * 16 + kk) * taps + tap];
-              const size_t o = pos + (size_t)((n / 8) * 2 + kk / 8) * 64 + (n % 8) * 8 + (kk % 8);
-              hi[o] = st_f2bf(v);
-              lo[o] = st_f2bf(v - st_bf2f(hi[o]));
-            }
-          pos += (size_t)n_tile * 16;
-        }
+  int kc, n_c;
+  umma_conv_choose(Cin, Cout, &kc, &n_c);
+  std::vector<uint16_t> hi, lo;
+  umma_conv_block_weights(w_host, Cout, Cin, kc, n_c, hi, lo);
   uint16_t *x_p = nullptr, *o_p = nullptr, *w_p = nullptr;
   const int64_t nx = (int64_t)B * Cin * T * F, no = (int64_t)B * Cout * T * F, nw = (int64_t)hi.size();
   B2_CUDA(cudaMalloc(&x_p, nx * 4));
@@ -507,9 +724,42 @@ extern "C" int b200sep_selftest_umma_conv3x3(const float* x, const float* w_host
   int rc = split_pair(x, x_p, x_p + nx, nx, st);
   UmmaConvPlan pl;
   if (!rc) rc = umma_conv_plan_create(&pl, x_p, x_p + nx, B, Cin, T, F, kc);
-  if (!rc) rc = umma_conv_run(pl, w_p, w_p + nw, B, Cout, n_tile, 3, scale, shift, relu, o_p, o_p + no, st);
+  if (!rc) rc = umma_conv_run(pl, w_p, w_p + nw, B, Cout, n_c, 3, scale, shift, relu, o_p, o_p + no, st);
   if (!rc) rc = join_pair(o_p, o_p + no, out, no, st);
   cudaStreamSynchronize(st);
   cudaFree(x_p); cudaFree(o_p); cudaFree(w_p);
+  return rc;
+}
+
+extern "C" int b200sep_selftest_umma_updown(const float* x, const float* w_host, const float* skip, float* out, int B, int Cin, int Cout, int T, int F,
+                                            const float* scale, const float* shift, int relu, int up, void* stream) {
+  B2_CHECK_ARG(x && w_host && out && scale && shift, "selftest_umma_updown: NULL argument");
+  B2_CHECK_ARG(umma_updown_supported(Cin, Cout, F, up), "selftest_umma_updown: Cin=%d Cout=%d F=%d not supported by the tensor-core path", Cin, Cout, F);
+  cudaStream_t st = (cudaStream_t)stream;
+  int kc, n_c;
+  umma_updown_choose(Cin, Cout, up, &kc, &n_c);
+  std::vector<uint16_t> hi, lo;
+  if (up) umma_up_block_weights(w_host, Cin, Cout, kc, n_c, hi, lo);
+  else umma_down_block_weights(w_host, Cout, Cin, kc, n_c, hi, lo);
+  uint16_t *x_p = nullptr, *o_p = nullptr, *w_p = nullptr, *s_p = nullptr;
+  const int64_t nx = (int64_t)B * Cin * T * F, no = up ? (int64_t)B * Cout * 4 * T * F : (int64_t)B * Cout * (T / 2) * (F / 2), nw = (int64_t)hi.size();
+  B2_CUDA(cudaMalloc(&x_p, nx * 4));
+  B2_CUDA(cudaMalloc(&o_p, no * 4));
+  B2_CUDA(cudaMalloc(&w_p, nw * 4));
+  if (skip) B2_CUDA(cudaMalloc(&s_p, no * 4));
+  B2_CUDA(cudaMemcpy(w_p, hi.data(), nw * 2, cudaMemcpyHostToDevice));
+  B2_CUDA(cudaMemcpy(w_p + nw, lo.data(), nw * 2, cudaMemcpyHostToDevice));
+  int rc = split_pair(x, x_p, x_p + nx, nx, st);
+  if (!rc && skip) rc = split_pair(skip, s_p, s_p + no, no, st);
+  UmmaConvPlan pl;
+  if (!rc) rc = umma_conv_plan_create(&pl, x_p, x_p + nx, B, Cin, T, F, kc);
+  if (!rc) {
+    if (up) rc = umma_up_run(pl, w_p, w_p + nw, B, Cout, n_c, scale, shift, relu, s_p, s_p ? s_p + no : nullptr, o_p, o_p + no, st);
+    else rc = umma_down_run(pl, w_p, w_p + nw, B, Cout, n_c, scale, shift, relu, o_p, o_p + no, st);
+  }
+  if (!rc) rc = join_pair(o_p, o_p + no, out, no, st);
+  cudaStreamSynchronize(st);
+  cudaFree(x_p); cudaFree(o_p); cudaFree(w_p);
+  if (s_p) cudaFree(s_p);
   return rc;
 }

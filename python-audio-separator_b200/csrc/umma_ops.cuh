@@ -1,6 +1,9 @@
 // Host interface of the tcgen05 "pair" operators (umma_ops.cu).
 #pragma once
 #include <cuda.h>
+#include <stdint.h>
+
+#include <vector>
 
 #include "common.cuh"
 
@@ -23,12 +26,23 @@ int umma_gemm_run(const UmmaGemmPlan& pl, const float* scale, const float* shift
                   void* out_lo, const void* res_hi, const void* res_lo, int M_active, cudaStream_t st);
 
 bool umma_conv_supported(int Cin, int Cout, int F, int kh, int kw);
-int umma_conv_choose(int Cin, int Cout, int* kc, int* n_tile);
+int umma_conv_choose(int Cin, int Cout, int* kc, int* n_c);
+void umma_conv_block_weights(const float* w, int Cout, int Cin, int kc, int n_c, std::vector<uint16_t>& hi, std::vector<uint16_t>& lo);
 // x: pair (Bmax, Cin, T, F)
 int umma_conv_plan_create(UmmaConvPlan* pl, const void* x_hi, const void* x_lo, int Bmax, int Cin, int T, int F, int kc);
-// weights pre-blocked by the host: [Cout/n_tile][taps*Cin/kc][kc/16][n_tile x 16 in 8x8 core matrices] (hi plane, lo plane)
-int umma_conv_run(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_lo, int B, int Cout, int n_tile, int ksize, const float* scale,
+// weights pre-blocked by umma_conv_block_weights (hi plane, lo plane)
+int umma_conv_run(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_lo, int B, int Cout, int n_c, int ksize, const float* scale,
                   const float* shift, int relu, void* out_hi, void* out_lo, cudaStream_t st);
+
+// ConvTranspose2d / Conv2d with 2x2 kernels and stride 2 (the U-Net's up / down sampling) on the same pipeline
+bool umma_updown_supported(int Cin, int Cout, int F_in, int up);
+int umma_updown_choose(int Cin, int Cout, int up, int* kc, int* n_c);
+void umma_up_block_weights(const float* w /*(Cin,Cout,2,2)*/, int Cin, int Cout, int kc, int n_c, std::vector<uint16_t>& hi, std::vector<uint16_t>& lo);
+void umma_down_block_weights(const float* w /*(Cout,Cin,2,2)*/, int Cout, int Cin, int kc, int n_c, std::vector<uint16_t>& hi, std::vector<uint16_t>& lo);
+int umma_up_run(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_lo, int B, int Cout, int n_c, const float* scale, const float* shift, int relu,
+                const void* skip_hi, const void* skip_lo, void* out_hi, void* out_lo, cudaStream_t st);
+int umma_down_run(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_lo, int B, int Cout, int n_c, const float* scale, const float* shift, int relu,
+                  void* out_hi, void* out_lo, cudaStream_t st);
 
 int split_pair(const float* x, void* hi, void* lo, int64_t n, cudaStream_t st);
 int join_pair(const void* hi, const void* lo, float* y, int64_t n, cudaStream_t st);

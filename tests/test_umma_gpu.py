@@ -57,3 +57,27 @@ def test_umma_conv3x3_vs_torch(lib, B, Cin, Cout, T, Fq):
     ref = torch.relu(F.conv2d(x.double(), w.cuda().double(), padding=1) * scale.double()[None, :, None, None] + shift.double()[None, :, None, None])
     assert torch.isfinite(out).all()
     assert rel_err(out, ref) <= 5e-5
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("B,Cin,Cout,T,Fq,up,skip", [(1, 32, 16, 4, 128, 1, True), (2, 96, 48, 8, 256, 1, True), (1, 288, 240, 8, 96, 1, False), (1, 96, 48, 6, 1536, 1, True),
+                                                     (1, 16, 32, 4, 128, 0, False), (2, 48, 96, 8, 256, 0, False), (1, 240, 288, 16, 192, 0, False), (1, 48, 96, 6, 3072, 0, False)])
+def test_umma_updown_vs_torch(lib, B, Cin, Cout, T, Fq, up, skip):
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + Cin + Cout + T + Fq + up)
+    x = torch.randn(B, Cin, T, Fq, device="cuda", generator=g)
+    wshape = (Cin, Cout, 2, 2) if up else (Cout, Cin, 2, 2)
+    w = (torch.randn(*wshape, device="cuda", generator=g) / (2 * Cin**0.5)).cpu().contiguous()
+    scale = torch.rand(Cout, device="cuda", generator=g) + 0.5
+    shift = torch.randn(Cout, device="cuda", generator=g) * 0.1
+    oshape = (B, Cout, 2 * T, 2 * Fq) if up else (B, Cout, T // 2, Fq // 2)
+    sk = torch.randn(*oshape, device="cuda", generator=g) if skip else None
+    out = torch.full(oshape, float("nan"), device="cuda")
+    rc = lib.lib.b200sep_selftest_umma_updown(x.data_ptr(), w.data_ptr(), sk.data_ptr() if skip else None, out.data_ptr(), B, Cin, Cout, T, Fq, scale.data_ptr(), shift.data_ptr(), 1, up, None)
+    lib.check(rc, "selftest_umma_updown")
+    wd = w.cuda().double()
+    y = F.conv_transpose2d(x.double(), wd, stride=2) if up else F.conv2d(x.double(), wd, stride=2)
+    ref = torch.relu(y * scale.double()[None, :, None, None] + shift.double()[None, :, None, None])
+    if skip:
+        ref = ref * sk.double()
+    assert torch.isfinite(out).all()
+    assert rel_err(out, ref) <= 5e-5
