@@ -249,6 +249,20 @@ __global__ void __launch_bounds__(kUmmaThreads) umma_pair_kernel(const __grid_co
           ptx::tmem_ld16(trow + (uint32_t)((dy * 2 + 0) * nc + c0), v0);
           ptx::tmem_ld16(trow + (uint32_t)((dy * 2 + 1) * nc + c0), v1);
           ptx::tmem_ld_wait();
+          // all skip loads of this 16-channel group are issued before any store (read-only path: the compiler cannot
+          // otherwise move them above the preceding stores, which serialised the epilogue on memory latency)
+          uint32_t sk_h[16], sk_l[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int co = n0 + c0 + j;
+            sk_h[j] = 0x3f803f80u;  // bf16 (1.0, 1.0)
+            sk_l[j] = 0u;
+            if (p.res_hi && row_ok && co < p.Cout) {
+              const size_t o = base + (size_t)co * plane;
+              sk_h[j] = __ldg(reinterpret_cast<const unsigned int*>(p.res_hi + o));
+              sk_l[j] = __ldg(reinterpret_cast<const unsigned int*>(p.res_lo + o));
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int co = n0 + c0 + j;
@@ -259,13 +273,10 @@ __global__ void __launch_bounds__(kUmmaThreads) umma_pair_kernel(const __grid_co
                 x0 = fmaxf(x0, 0.f);
                 x1 = fmaxf(x1, 0.f);
               }
+              // bf16 -> fp32 is a 16-bit shift: low half = element 0 (dx = 0), high half = element 1 (dx = 1)
+              x0 *= __uint_as_float(sk_h[j] << 16) + __uint_as_float(sk_l[j] << 16);
+              x1 *= __uint_as_float(sk_h[j] & 0xffff0000u) + __uint_as_float(sk_l[j] & 0xffff0000u);
               const size_t o = base + (size_t)co * plane;
-              if (p.res_hi) {
-                const __nv_bfloat162 sh2 = *reinterpret_cast<const __nv_bfloat162*>(p.res_hi + o);
-                const __nv_bfloat162 sl2 = *reinterpret_cast<const __nv_bfloat162*>(p.res_lo + o);
-                x0 *= __bfloat162float(sh2.x) + __bfloat162float(sl2.x);
-                x1 *= __bfloat162float(sh2.y) + __bfloat162float(sl2.y);
-              }
               __nv_bfloat162 oh, ol;
               split_store2(x0, oh.x, ol.x);
               split_store2(x1, oh.y, ol.y);
