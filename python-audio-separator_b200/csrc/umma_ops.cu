@@ -39,6 +39,7 @@ struct UmmaParams {
   int f_stride, t_mul, t_off;  // implicit-GEMM addressing: tile f0 = blockIdx.x*f_stride, input row = t*t_mul + r + t_off
   int n_tile, n_total, tmem_cols;
   int num_iters, ksteps, stages;
+  int num_tiles, n_ftiles, t_tiles;  // persistent tile walk (n_tiles below = tiles along N / output channels)
   uint32_t a_bytes, b_bytes, stage_bytes;
   // CONV
   int n_chunks, kc, T, F, Cin, Cout, n_tiles, n_c;  // n_c = output channels per CTA; n_tile = 3*n_c accumulator columns
@@ -61,39 +62,54 @@ __device__ __forceinline__ void split_store2(float v, bf16& hi, bf16& lo) {
   lo = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
-__global__ void __launch_bounds__(kUmmaThreads) umma_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                                                                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                                                                 const UmmaParams p) {
+struct TileCoord {
+  int m0, n_idx, f0, t, b;
+};
+// Tile order keeps concurrently running CTAs on neighbouring tiles (same A rows / same weights stay hot in L2).
+__device__ __forceinline__ TileCoord decode_tile(const UmmaParams& p, int tile) {
+  TileCoord c{0, 0, 0, 0, 0};
+  if (p.mode == 0) {
+    c.n_idx = tile % p.n_tiles;
+    c.m0 = (tile / p.n_tiles) * kTileM;
+  } else {
+    const int fx = tile % p.n_ftiles;
+    int r = tile / p.n_ftiles;
+    c.t = r % p.t_tiles;
+    r /= p.t_tiles;
+    c.n_idx = r % p.n_tiles;
+    c.b = r / p.n_tiles;
+    c.f0 = fx * p.f_stride;
+  }
+  return c;
+}
+
+// Persistent kernel: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ...  Three pipelines run
+// concurrently: TMA producer -> smem ring (full/empty mbarriers, continuous across tiles), MMA issuer -> one of two TMEM
+// accumulators (tmem_full/tmem_empty), epilogue warps draining the other accumulator.
+__global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                                                                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                                                                    const UmmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment for SWIZZLE_128B tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
-  uint64_t* tmem_full_bar = empty_bar + p.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  float* edge = reinterpret_cast<float*>(tmem_slot + 4);  // CONV: [2][4 warps][n_c] boundary rows exchanged between epilogue warps
+  uint64_t* tmem_full_bar = empty_bar + p.stages;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* edge_base = reinterpret_cast<float*>(tmem_slot + 4);  // CONV3x3: [2 acc][2][4 warps][n_c] rows exchanged between epilogue warps
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  // tile coordinates
-  int m0 = 0, n_idx = 0, f0 = 0, t = 0, b = 0;
-  if (p.mode == 0) {
-    n_idx = blockIdx.x;
-    m0 = blockIdx.y * kTileM;
-  } else {
-    f0 = blockIdx.x * p.f_stride;
-    t = blockIdx.y;
-    n_idx = blockIdx.z % p.n_tiles;
-    b = blockIdx.z / p.n_tiles;
-  }
-  const int n0 = n_idx * (p.mode == 0 ? p.n_tile : p.n_c);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
-    ptx::mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full_bar[a], 1);
+      ptx::mbar_init(&tmem_empty_bar[a], 4);  // one arrive per epilogue warp
+    }
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tmA_hi);
     ptx::prefetch_tensormap(&tmA_lo);
@@ -107,41 +123,46 @@ __global__ void __launch_bounds__(kUmmaThreads) umma_pair_kernel(const __grid_co
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc_stride = (uint32_t)p.tmem_cols / 2;
 
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
       int s = 0;
       uint32_t phase = 0;
-      for (int i = 0; i < p.num_iters; ++i) {
-        ptx::mbar_wait(&empty_bar[s], phase ^ 1, 100 + i);
-        uint8_t* st = smem + (size_t)s * p.stage_bytes;
-        uint8_t* a_hi = st;
-        uint8_t* a_lo = st + p.a_bytes;
-        uint8_t* b_hi = st + 2 * p.a_bytes;
-        uint8_t* b_lo = b_hi + p.b_bytes;
-        ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * p.a_bytes + 2 * p.b_bytes);
-        if (p.mode == 0) {
-          const int k0 = i * 64;
-          ptx::tma_load_2d(a_hi, &tmA_hi, &full_bar[s], k0, m0);
-          ptx::tma_load_2d(a_lo, &tmA_lo, &full_bar[s], k0, m0);
-          ptx::tma_load_2d(b_hi, &tmB_hi, &full_bar[s], k0, n0);
-          ptx::tma_load_2d(b_lo, &tmB_lo, &full_bar[s], k0, n0);
-        } else {
-          const int r = i / p.n_chunks, chunk = i - r * p.n_chunks;
-          const int cf = f0, ct = t * p.t_mul + r + p.t_off, cc = b * p.Cin + chunk * p.kc;
-          const uint32_t box = (uint32_t)p.kc * 128u;
-          ptx::tma_load_3d(a_hi, &tmA_hi, &full_bar[s], cf, ct, cc);
-          ptx::tma_load_3d(a_hi + box, &tmA_hi, &full_bar[s], cf + 64, ct, cc);
-          ptx::tma_load_3d(a_lo, &tmA_lo, &full_bar[s], cf, ct, cc);
-          ptx::tma_load_3d(a_lo + box, &tmA_lo, &full_bar[s], cf + 64, ct, cc);
-          const size_t woff = ((size_t)n_idx * p.num_iters + i) * (size_t)(p.b_bytes / 2);
-          ptx::bulk_load_1d(b_hi, p.wb_hi + woff, p.b_bytes, &full_bar[s]);
-          ptx::bulk_load_1d(b_lo, p.wb_lo + woff, p.b_bytes, &full_bar[s]);
-        }
-        if (++s == p.stages) {
-          s = 0;
-          phase ^= 1;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile);
+        const int n0 = tc.n_idx * p.n_tile;
+        for (int i = 0; i < p.num_iters; ++i) {
+          ptx::mbar_wait(&empty_bar[s], phase ^ 1, 100 + i);
+          uint8_t* st = smem + (size_t)s * p.stage_bytes;
+          uint8_t* a_hi = st;
+          uint8_t* a_lo = st + p.a_bytes;
+          uint8_t* b_hi = st + 2 * p.a_bytes;
+          uint8_t* b_lo = b_hi + p.b_bytes;
+          ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * p.a_bytes + 2 * p.b_bytes);
+          if (p.mode == 0) {
+            const int k0 = i * 64;
+            ptx::tma_load_2d(a_hi, &tmA_hi, &full_bar[s], k0, tc.m0);
+            ptx::tma_load_2d(a_lo, &tmA_lo, &full_bar[s], k0, tc.m0);
+            ptx::tma_load_2d(b_hi, &tmB_hi, &full_bar[s], k0, n0);
+            ptx::tma_load_2d(b_lo, &tmB_lo, &full_bar[s], k0, n0);
+          } else {
+            const int r = i / p.n_chunks, chunk = i - r * p.n_chunks;
+            const int cf = tc.f0, ct = tc.t * p.t_mul + r + p.t_off, cc = tc.b * p.Cin + chunk * p.kc;
+            const uint32_t box = (uint32_t)p.kc * 128u;
+            ptx::tma_load_3d(a_hi, &tmA_hi, &full_bar[s], cf, ct, cc);
+            ptx::tma_load_3d(a_hi + box, &tmA_hi, &full_bar[s], cf + 64, ct, cc);
+            ptx::tma_load_3d(a_lo, &tmA_lo, &full_bar[s], cf, ct, cc);
+            ptx::tma_load_3d(a_lo + box, &tmA_lo, &full_bar[s], cf + 64, ct, cc);
+            const size_t woff = ((size_t)tc.n_idx * p.num_iters + i) * (size_t)(p.b_bytes / 2);
+            ptx::bulk_load_1d(b_hi, p.wb_hi + woff, p.b_bytes, &full_bar[s]);
+            ptx::bulk_load_1d(b_lo, p.wb_lo + woff, p.b_bytes, &full_bar[s]);
+          }
+          if (++s == p.stages) {
+            s = 0;
+            phase ^= 1;
+          }
         }
       }
     }
@@ -149,222 +170,243 @@ __global__ void __launch_bounds__(kUmmaThreads) umma_pair_kernel(const __grid_co
     if (lane == 0) {
       // ===== MMA issuer =====
       const uint32_t idesc = ptx::instr_desc_bf16(kTileM, p.n_tile, p.mode != 0 ? 1 : 0, 0);
-      int s = 0;
-      uint32_t phase = 0;
-      for (int i = 0; i < p.num_iters; ++i) {
-        ptx::mbar_wait(&full_bar[s], phase, 200 + i);
+      int s = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, 400 + acc);  // epilogue has drained this accumulator
         ptx::tc_fence_after();
-        const uint32_t st = ptx::smem_u32(smem + (size_t)s * p.stage_bytes);
-        const uint32_t a_hi = st, a_lo = st + p.a_bytes, b_hi = st + 2 * p.a_bytes, b_lo = b_hi + p.b_bytes;
-        for (int j = 0; j < p.ksteps; ++j) {
-          uint64_t dah, dal, dbh, dbl;
-          if (p.mode == 0) {
-            dah = ptx::smem_desc(a_hi + j * 32, 16, 1024, ptx::kLayoutSW128);
-            dal = ptx::smem_desc(a_lo + j * 32, 16, 1024, ptx::kLayoutSW128);
-            dbh = ptx::smem_desc(b_hi + j * 32, 16, 1024, ptx::kLayoutSW128);
-            dbl = ptx::smem_desc(b_lo + j * 32, 16, 1024, ptx::kLayoutSW128);
-          } else {
-            const uint32_t lbo = (uint32_t)p.kc * 128u;  // next 64 pixels (second TMA box)
-            dah = ptx::smem_desc(a_hi + j * 2048, lbo, 1024, ptx::kLayoutSW128);
-            dal = ptx::smem_desc(a_lo + j * 2048, lbo, 1024, ptx::kLayoutSW128);
-            const uint32_t bstep = (uint32_t)p.n_tile * 32u;  // one [n_tile][16] block of 8x8 core matrices
-            dbh = ptx::smem_desc(b_hi + j * bstep, 128, 256, ptx::kLayoutNone);
-            dbl = ptx::smem_desc(b_lo + j * bstep, 128, 256, ptx::kLayoutNone);
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_stride;
+        for (int i = 0; i < p.num_iters; ++i) {
+          ptx::mbar_wait(&full_bar[s], phase, 200 + i);
+          ptx::tc_fence_after();
+          const uint32_t st = ptx::smem_u32(smem + (size_t)s * p.stage_bytes);
+          const uint32_t a_hi = st, a_lo = st + p.a_bytes, b_hi = st + 2 * p.a_bytes, b_lo = b_hi + p.b_bytes;
+          for (int j = 0; j < p.ksteps; ++j) {
+            uint64_t dah, dal, dbh, dbl;
+            if (p.mode == 0) {
+              dah = ptx::smem_desc(a_hi + j * 32, 16, 1024, ptx::kLayoutSW128);
+              dal = ptx::smem_desc(a_lo + j * 32, 16, 1024, ptx::kLayoutSW128);
+              dbh = ptx::smem_desc(b_hi + j * 32, 16, 1024, ptx::kLayoutSW128);
+              dbl = ptx::smem_desc(b_lo + j * 32, 16, 1024, ptx::kLayoutSW128);
+            } else {
+              const uint32_t lbo = (uint32_t)p.kc * 128u;  // next 64 pixels (second TMA box)
+              dah = ptx::smem_desc(a_hi + j * 2048, lbo, 1024, ptx::kLayoutSW128);
+              dal = ptx::smem_desc(a_lo + j * 2048, lbo, 1024, ptx::kLayoutSW128);
+              const uint32_t bstep = (uint32_t)p.n_tile * 32u;  // one [n_tile][16] block of 8x8 core matrices
+              dbh = ptx::smem_desc(b_hi + j * bstep, 128, 256, ptx::kLayoutNone);
+              dbl = ptx::smem_desc(b_lo + j * bstep, 128, 256, ptx::kLayoutNone);
+            }
+            ptx::umma_bf16(d_tmem, dah, dbh, idesc, (i | j) != 0 ? 1u : 0u);
+            ptx::umma_bf16(d_tmem, dah, dbl, idesc, 1u);
+            ptx::umma_bf16(d_tmem, dal, dbh, idesc, 1u);
           }
-          ptx::umma_bf16(tmem_base, dah, dbh, idesc, (i | j) != 0 ? 1u : 0u);
-          ptx::umma_bf16(tmem_base, dah, dbl, idesc, 1u);
-          ptx::umma_bf16(tmem_base, dal, dbh, idesc, 1u);
+          ptx::umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+          if (++s == p.stages) {
+            s = 0;
+            phase ^= 1;
+          }
         }
-        ptx::umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
-        if (i == p.num_iters - 1) ptx::umma_commit(tmem_full_bar);
-        if (++s == p.stages) {
-          s = 0;
-          phase ^= 1;
-        }
+        ptx::umma_commit(&tmem_full_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
       }
     }
   } else {
     // ===== epilogue: TMEM -> registers -> BN/ReLU(/+res) -> split -> global =====
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const int m = q * 32 + lane;
-    ptx::mbar_wait(tmem_full_bar, 0, 300);
-    ptx::tc_fence_after();
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    if (p.mode == 0) {
-      const int r = m0 + m;
-      float sc = 1.f, sh = 0.f;
-      if (r < p.M) {
-        const int c = (r / p.rows_per_channel) % p.channels;
-        sc = __ldg(&p.scale[c]);
-        sh = __ldg(&p.shift[c]);
-      }
-      for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
-        uint32_t v[16];
-        ptx::tmem_ld16(trow + (uint32_t)c0, v);
-        ptx::tmem_ld_wait();
-        const int n = n0 + c0;
-        if (r < p.M && n < p.n_total) {
-          const size_t o = (size_t)r * p.n_total + n;
-          float x[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            x[j] = fmaf(__uint_as_float(v[j]), sc, sh);
-            if (p.relu) x[j] = fmaxf(x[j], 0.f);
-          }
-          if (p.res_hi) {
-            uint4 rh[2], rl[2];
-            rh[0] = __ldg(reinterpret_cast<const uint4*>(p.res_hi + o));
-            rh[1] = __ldg(reinterpret_cast<const uint4*>(p.res_hi + o) + 1);
-            rl[0] = __ldg(reinterpret_cast<const uint4*>(p.res_lo + o));
-            rl[1] = __ldg(reinterpret_cast<const uint4*>(p.res_lo + o) + 1);
-            const bf16* h = reinterpret_cast<const bf16*>(rh);
-            const bf16* l = reinterpret_cast<const bf16*>(rl);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) x[j] += __bfloat162float(h[j]) + __bfloat162float(l[j]);
-          }
-          __align__(16) bf16 oh[16];
-          __align__(16) bf16 ol[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) split_store2(x[j], oh[j], ol[j]);
-          uint4* dh = reinterpret_cast<uint4*>(p.out_hi + o);
-          uint4* dl = reinterpret_cast<uint4*>(p.out_lo + o);
-          dh[0] = reinterpret_cast<const uint4*>(oh)[0];
-          dh[1] = reinterpret_cast<const uint4*>(oh)[1];
-          dl[0] = reinterpret_cast<const uint4*>(ol)[0];
-          dl[1] = reinterpret_cast<const uint4*>(ol)[1];
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      const int m0 = tc.m0, f0 = tc.f0, t = tc.t, b = tc.b;
+      const int n0 = tc.n_idx * (p.mode == 0 ? p.n_tile : p.n_c);
+      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase, 300 + acc);
+      ptx::tc_fence_after();
+      const uint32_t trow = tmem_base + (uint32_t)acc * acc_stride + ((uint32_t)(q * 32) << 16);
+      float* edge = edge_base + acc * 8 * p.n_c;
+      if (p.mode == 0) {
+        const int r = m0 + m;
+        float sc = 1.f, sh = 0.f;
+        if (r < p.M) {
+          const int c = (r / p.rows_per_channel) % p.channels;
+          sc = __ldg(&p.scale[c]);
+          sh = __ldg(&p.shift[c]);
         }
-      }
-    } else if (p.mode == 2) {
-      // ConvTranspose2d k2 s2: column (dy*2+dx)*n_c + co of lane m is the output pixel (2t+dy, 2(f0+m)+dx) of channel co;
-      // then BN + ReLU, times the skip tensor (uvr_lib_v5/mdxnet.py:111-112).  The two dx values are stored as one 4-byte pair.
-      const int nc = p.n_c;
-      const int f = f0 + m;
-      const bool row_ok = f < p.F;
-      const int T2 = 2 * p.T, F2 = 2 * p.F;
-      const size_t plane = (size_t)T2 * F2;
-      for (int dy = 0; dy < 2; ++dy) {
-        const size_t base = ((size_t)b * p.Cout) * plane + (size_t)(2 * t + dy) * F2 + 2 * f;
+        for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+          uint32_t v[16];
+          ptx::tmem_ld16(trow + (uint32_t)c0, v);
+          ptx::tmem_ld_wait();
+          const int n = n0 + c0;
+          if (r < p.M && n < p.n_total) {
+            const size_t o = (size_t)r * p.n_total + n;
+            float x[16];
+  #pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              x[j] = fmaf(__uint_as_float(v[j]), sc, sh);
+              if (p.relu) x[j] = fmaxf(x[j], 0.f);
+            }
+            if (p.res_hi) {
+              uint4 rh[2], rl[2];
+              rh[0] = __ldg(reinterpret_cast<const uint4*>(p.res_hi + o));
+              rh[1] = __ldg(reinterpret_cast<const uint4*>(p.res_hi + o) + 1);
+              rl[0] = __ldg(reinterpret_cast<const uint4*>(p.res_lo + o));
+              rl[1] = __ldg(reinterpret_cast<const uint4*>(p.res_lo + o) + 1);
+              const bf16* h = reinterpret_cast<const bf16*>(rh);
+              const bf16* l = reinterpret_cast<const bf16*>(rl);
+  #pragma unroll
+              for (int j = 0; j < 16; ++j) x[j] += __bfloat162float(h[j]) + __bfloat162float(l[j]);
+            }
+            __align__(16) bf16 oh[16];
+            __align__(16) bf16 ol[16];
+  #pragma unroll
+            for (int j = 0; j < 16; ++j) split_store2(x[j], oh[j], ol[j]);
+            uint4* dh = reinterpret_cast<uint4*>(p.out_hi + o);
+            uint4* dl = reinterpret_cast<uint4*>(p.out_lo + o);
+            dh[0] = reinterpret_cast<const uint4*>(oh)[0];
+            dh[1] = reinterpret_cast<const uint4*>(oh)[1];
+            dl[0] = reinterpret_cast<const uint4*>(ol)[0];
+            dl[1] = reinterpret_cast<const uint4*>(ol)[1];
+          }
+        }
+      } else if (p.mode == 2) {
+        // ConvTranspose2d k2 s2: column (dy*2+dx)*n_c + co of lane m is the output pixel (2t+dy, 2(f0+m)+dx) of channel co;
+        // then BN + ReLU, times the skip tensor (uvr_lib_v5/mdxnet.py:111-112).  The two dx values are stored as one 4-byte pair.
+        const int nc = p.n_c;
+        const int f = f0 + m;
+        const bool row_ok = f < p.F;
+        const int T2 = 2 * p.T, F2 = 2 * p.F;
+        const size_t plane = (size_t)T2 * F2;
+        for (int dy = 0; dy < 2; ++dy) {
+          const size_t base = ((size_t)b * p.Cout) * plane + (size_t)(2 * t + dy) * F2 + 2 * f;
+          for (int c0 = 0; c0 < nc; c0 += 16) {
+            uint32_t v0[16], v1[16];
+            ptx::tmem_ld16(trow + (uint32_t)((dy * 2 + 0) * nc + c0), v0);
+            ptx::tmem_ld16(trow + (uint32_t)((dy * 2 + 1) * nc + c0), v1);
+            ptx::tmem_ld_wait();
+            // all skip loads of this 16-channel group are issued before any store (read-only path: the compiler cannot
+            // otherwise move them above the preceding stores, which serialised the epilogue on memory latency)
+            uint32_t sk_h[16], sk_l[16];
+  #pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int co = n0 + c0 + j;
+              sk_h[j] = 0x3f803f80u;  // bf16 (1.0, 1.0)
+              sk_l[j] = 0u;
+              if (p.res_hi && row_ok && co < p.Cout) {
+                const size_t o = base + (size_t)co * plane;
+                sk_h[j] = __ldg(reinterpret_cast<const unsigned int*>(p.res_hi + o));
+                sk_l[j] = __ldg(reinterpret_cast<const unsigned int*>(p.res_lo + o));
+              }
+            }
+  #pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int co = n0 + c0 + j;
+              if (row_ok && co < p.Cout) {
+                const float sc = __ldg(&p.scale[co]), sh = __ldg(&p.shift[co]);
+                float x0 = fmaf(__uint_as_float(v0[j]), sc, sh), x1 = fmaf(__uint_as_float(v1[j]), sc, sh);
+                if (p.relu) {
+                  x0 = fmaxf(x0, 0.f);
+                  x1 = fmaxf(x1, 0.f);
+                }
+                // bf16 -> fp32 is a 16-bit shift: low half = element 0 (dx = 0), high half = element 1 (dx = 1)
+                x0 *= __uint_as_float(sk_h[j] << 16) + __uint_as_float(sk_l[j] << 16);
+                x1 *= __uint_as_float(sk_h[j] & 0xffff0000u) + __uint_as_float(sk_l[j] & 0xffff0000u);
+                const size_t o = base + (size_t)co * plane;
+                __nv_bfloat162 oh, ol;
+                split_store2(x0, oh.x, ol.x);
+                split_store2(x1, oh.y, ol.y);
+                *reinterpret_cast<__nv_bfloat162*>(p.out_hi + o) = oh;  // 32 lanes -> 128 contiguous bytes
+                *reinterpret_cast<__nv_bfloat162*>(p.out_lo + o) = ol;
+              }
+            }
+          }
+        }
+      } else if (p.mode == 3) {
+        // Conv2d k2 s2: P_dx[m] (column dx*n_c + co) is the partial sum over (ci, dy) at INPUT pixel f0+m;
+        // out[(f0+m)/2] = P_0[m] + P_1[m+1] for even m (odd rows of P_0 / even rows of P_1 are computed but unused).
+        const int nc = p.n_c;
+        const int fo = (f0 + m) >> 1, Fo = p.F >> 1, To = p.T >> 1;
+        const bool row_ok = ((m & 1) == 0) && fo < Fo;
+        const size_t plane = (size_t)To * Fo;
+        const size_t base = ((size_t)b * p.Cout) * plane + (size_t)t * Fo + fo;
         for (int c0 = 0; c0 < nc; c0 += 16) {
           uint32_t v0[16], v1[16];
-          ptx::tmem_ld16(trow + (uint32_t)((dy * 2 + 0) * nc + c0), v0);
-          ptx::tmem_ld16(trow + (uint32_t)((dy * 2 + 1) * nc + c0), v1);
+          ptx::tmem_ld16(trow + (uint32_t)c0, v0);
+          ptx::tmem_ld16(trow + (uint32_t)(nc + c0), v1);
           ptx::tmem_ld_wait();
-          // all skip loads of this 16-channel group are issued before any store (read-only path: the compiler cannot
-          // otherwise move them above the preceding stores, which serialised the epilogue on memory latency)
-          uint32_t sk_h[16], sk_l[16];
-#pragma unroll
+  #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int co = n0 + c0 + j;
-            sk_h[j] = 0x3f803f80u;  // bf16 (1.0, 1.0)
-            sk_l[j] = 0u;
-            if (p.res_hi && row_ok && co < p.Cout) {
-              const size_t o = base + (size_t)co * plane;
-              sk_h[j] = __ldg(reinterpret_cast<const unsigned int*>(p.res_hi + o));
-              sk_l[j] = __ldg(reinterpret_cast<const unsigned int*>(p.res_lo + o));
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
+            const float nb = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[j]), 1);  // P_1 of row m+1 (same warp: m even)
             const int co = n0 + c0 + j;
             if (row_ok && co < p.Cout) {
-              const float sc = __ldg(&p.scale[co]), sh = __ldg(&p.shift[co]);
-              float x0 = fmaf(__uint_as_float(v0[j]), sc, sh), x1 = fmaf(__uint_as_float(v1[j]), sc, sh);
-              if (p.relu) {
-                x0 = fmaxf(x0, 0.f);
-                x1 = fmaxf(x1, 0.f);
-              }
-              // bf16 -> fp32 is a 16-bit shift: low half = element 0 (dx = 0), high half = element 1 (dx = 1)
-              x0 *= __uint_as_float(sk_h[j] << 16) + __uint_as_float(sk_l[j] << 16);
-              x1 *= __uint_as_float(sk_h[j] & 0xffff0000u) + __uint_as_float(sk_l[j] & 0xffff0000u);
+              float x = fmaf(__uint_as_float(v0[j]) + nb, __ldg(&p.scale[co]), __ldg(&p.shift[co]));
+              if (p.relu) x = fmaxf(x, 0.f);
+              bf16 h, l;
+              split_store2(x, h, l);
               const size_t o = base + (size_t)co * plane;
-              __nv_bfloat162 oh, ol;
-              split_store2(x0, oh.x, ol.x);
-              split_store2(x1, oh.y, ol.y);
-              *reinterpret_cast<__nv_bfloat162*>(p.out_hi + o) = oh;  // 32 lanes -> 128 contiguous bytes
-              *reinterpret_cast<__nv_bfloat162*>(p.out_lo + o) = ol;
+              p.out_hi[o] = h;
+              p.out_lo[o] = l;
+            }
+          }
+        }
+      } else {
+        // P_dx[m][co] sits in column dx*n_c + co of TMEM lane m.  out[f0+j] = P_0[j-1] + P_1[j] + P_2[j+1].
+        const int nc = p.n_c;
+        float* edge0 = edge + q * nc;             // this warp's row 32q+31 of P_0 (needed by lane 0 of warp q+1)
+        float* edge2 = edge + (4 + q) * nc;       // this warp's row 32q    of P_2 (needed by lane 31 of warp q-1)
+        for (int c0 = 0; c0 < nc; c0 += 16) {
+          uint32_t v0[16], v2[16];
+          ptx::tmem_ld16(trow + (uint32_t)c0, v0);
+          ptx::tmem_ld16(trow + (uint32_t)(2 * nc + c0), v2);
+          ptx::tmem_ld_wait();
+          if (lane == 31) {
+  #pragma unroll
+            for (int j = 0; j < 16; ++j) edge0[c0 + j] = __uint_as_float(v0[j]);
+          }
+          if (lane == 0) {
+  #pragma unroll
+            for (int j = 0; j < 16; ++j) edge2[c0 + j] = __uint_as_float(v2[j]);
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+        const float* left = edge + (q - 1) * nc;        // valid for q > 0
+        const float* right = edge + (4 + q + 1) * nc;   // valid for q < 3
+        const int f = f0 + m;
+        const int j_lo = (f0 == 0) ? 0 : 1;
+        const bool row_ok = (m >= j_lo) && (m < kConvStride + 1) && (f < p.F);
+        const size_t plane = (size_t)p.T * p.F;
+        const size_t base = ((size_t)b * p.Cout) * plane + (size_t)t * p.F + f;
+        for (int c0 = 0; c0 < nc; c0 += 16) {
+          uint32_t v0[16], v1[16], v2[16];
+          ptx::tmem_ld16(trow + (uint32_t)c0, v0);
+          ptx::tmem_ld16(trow + (uint32_t)(nc + c0), v1);
+          ptx::tmem_ld16(trow + (uint32_t)(2 * nc + c0), v2);
+          ptx::tmem_ld_wait();
+  #pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float a = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[j]), 1);    // P_0 of row m-1
+            float c = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[j]), 1);  // P_2 of row m+1
+            if (lane == 0) a = (q > 0) ? left[c0 + j] : 0.f;   // m == 0: x[f0-1] is either padding (f0 == 0) or not an output row
+            if (lane == 31) c = (q < 3) ? right[c0 + j] : 0.f;  // m == 127 is never an output row
+            const int co = n0 + c0 + j;
+            if (row_ok && co < p.Cout) {
+              float x = fmaf(a + __uint_as_float(v1[j]) + c, __ldg(&p.scale[co]), __ldg(&p.shift[co]));
+              if (p.relu) x = fmaxf(x, 0.f);
+              bf16 h, l;
+              split_store2(x, h, l);
+              const size_t o = base + (size_t)co * plane;
+              p.out_hi[o] = h;  // 32 lanes -> 32 consecutive pixels: one 64-byte segment per plane
+              p.out_lo[o] = l;
             }
           }
         }
       }
-    } else if (p.mode == 3) {
-      // Conv2d k2 s2: P_dx[m] (column dx*n_c + co) is the partial sum over (ci, dy) at INPUT pixel f0+m;
-      // out[(f0+m)/2] = P_0[m] + P_1[m+1] for even m (odd rows of P_0 / even rows of P_1 are computed but unused).
-      const int nc = p.n_c;
-      const int fo = (f0 + m) >> 1, Fo = p.F >> 1, To = p.T >> 1;
-      const bool row_ok = ((m & 1) == 0) && fo < Fo;
-      const size_t plane = (size_t)To * Fo;
-      const size_t base = ((size_t)b * p.Cout) * plane + (size_t)t * Fo + fo;
-      for (int c0 = 0; c0 < nc; c0 += 16) {
-        uint32_t v0[16], v1[16];
-        ptx::tmem_ld16(trow + (uint32_t)c0, v0);
-        ptx::tmem_ld16(trow + (uint32_t)(nc + c0), v1);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float nb = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[j]), 1);  // P_1 of row m+1 (same warp: m even)
-          const int co = n0 + c0 + j;
-          if (row_ok && co < p.Cout) {
-            float x = fmaf(__uint_as_float(v0[j]) + nb, __ldg(&p.scale[co]), __ldg(&p.shift[co]));
-            if (p.relu) x = fmaxf(x, 0.f);
-            bf16 h, l;
-            split_store2(x, h, l);
-            const size_t o = base + (size_t)co * plane;
-            p.out_hi[o] = h;
-            p.out_lo[o] = l;
-          }
-        }
-      }
-    } else {
-      // P_dx[m][co] sits in column dx*n_c + co of TMEM lane m.  out[f0+j] = P_0[j-1] + P_1[j] + P_2[j+1].
-      const int nc = p.n_c;
-      float* edge0 = edge + q * nc;             // this warp's row 32q+31 of P_0 (needed by lane 0 of warp q+1)
-      float* edge2 = edge + (4 + q) * nc;       // this warp's row 32q    of P_2 (needed by lane 31 of warp q-1)
-      for (int c0 = 0; c0 < nc; c0 += 16) {
-        uint32_t v0[16], v2[16];
-        ptx::tmem_ld16(trow + (uint32_t)c0, v0);
-        ptx::tmem_ld16(trow + (uint32_t)(2 * nc + c0), v2);
-        ptx::tmem_ld_wait();
-        if (lane == 31) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) edge0[c0 + j] = __uint_as_float(v0[j]);
-        }
-        if (lane == 0) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) edge2[c0 + j] = __uint_as_float(v2[j]);
-        }
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
-      const float* left = edge + (q - 1) * nc;        // valid for q > 0
-      const float* right = edge + (4 + q + 1) * nc;   // valid for q < 3
-      const int f = f0 + m;
-      const int j_lo = (f0 == 0) ? 0 : 1;
-      const bool row_ok = (m >= j_lo) && (m < kConvStride + 1) && (f < p.F);
-      const size_t plane = (size_t)p.T * p.F;
-      const size_t base = ((size_t)b * p.Cout) * plane + (size_t)t * p.F + f;
-      for (int c0 = 0; c0 < nc; c0 += 16) {
-        uint32_t v0[16], v1[16], v2[16];
-        ptx::tmem_ld16(trow + (uint32_t)c0, v0);
-        ptx::tmem_ld16(trow + (uint32_t)(nc + c0), v1);
-        ptx::tmem_ld16(trow + (uint32_t)(2 * nc + c0), v2);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float a = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[j]), 1);    // P_0 of row m-1
-          float c = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[j]), 1);  // P_2 of row m+1
-          if (lane == 0) a = (q > 0) ? left[c0 + j] : 0.f;   // m == 0: x[f0-1] is either padding (f0 == 0) or not an output row
-          if (lane == 31) c = (q < 3) ? right[c0 + j] : 0.f;  // m == 127 is never an output row
-          const int co = n0 + c0 + j;
-          if (row_ok && co < p.Cout) {
-            float x = fmaf(a + __uint_as_float(v1[j]) + c, __ldg(&p.scale[co]), __ldg(&p.shift[co]));
-            if (p.relu) x = fmaxf(x, 0.f);
-            bf16 h, l;
-            split_store2(x, h, l);
-            const size_t o = base + (size_t)co * plane;
-            p.out_hi[o] = h;  // 32 lanes -> 32 consecutive pixels: one 64-byte segment per plane
-            p.out_lo[o] = l;
-          }
-        }
-      }
+      // this warp is done reading the accumulator: hand it back to the MMA issuer
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   }
   ptx::tc_fence_before();
@@ -422,23 +464,39 @@ static int pow2_cols(int n) {
   return c;
 }
 
-static int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo, UmmaParams& p, dim3 grid,
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kNumSMs;
+  }
+  return n;
+}
+
+// `tiles` is the logical tile grid: GEMM (n tiles, m tiles, 1); conv modes (f tiles, output rows, batch * channel tiles).
+static int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo, UmmaParams& p, dim3 tiles,
                   cudaStream_t st) {
   p.stage_bytes = ((2 * p.a_bytes + 2 * p.b_bytes + 1023) / 1024) * 1024;
-  const int budget = 108 * 1024;  // two CTAs per SM so one tile's epilogue overlaps the other's main loop
+  p.tmem_cols = 2 * pow2_cols(p.n_tile);  // two accumulators: the epilogue of tile i overlaps the MMAs of tile i+1
+  B2_CHECK_ARG(p.tmem_cols <= 512, "umma: n_tile=%d needs more than 512 TMEM columns", p.n_tile);
+  if (p.mode == 0) p.n_tiles = (int)tiles.x;
+  p.n_ftiles = (int)tiles.x;
+  p.t_tiles = (int)tiles.y;
+  p.num_tiles = (int)(tiles.x * tiles.y * tiles.z);
+  const size_t fixed = 1024 /*alignment slack*/ + 64 * sizeof(uint64_t) + 64 + (p.mode != 0 ? (size_t)16 * p.n_c * sizeof(float) : 0);
+  const size_t budget = 220 * 1024 - fixed;  // one persistent CTA per SM
   int stages = (int)(budget / p.stage_bytes);
-  if (stages < 2) stages = 2;
-  if (stages > 6) stages = 6;
-  if (stages > p.num_iters) stages = p.num_iters;
+  if (stages > 8) stages = 8;
+  B2_CHECK_ARG(stages >= 2, "umma: a pipeline stage of %u bytes does not fit twice in shared memory", p.stage_bytes);
   p.stages = stages;
-  const size_t smem = (size_t)stages * p.stage_bytes + 1024 /*alignment slack*/ + (2 * stages + 1) * sizeof(uint64_t) + 16 +
-                      (p.mode != 0 ? (size_t)8 * p.n_c * sizeof(float) : 0);
-  B2_CHECK_ARG(smem <= 227 * 1024, "umma: tile needs %zu bytes of shared memory", smem);
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
+  const size_t smem = (size_t)stages * p.stage_bytes + fixed;
+  static bool attr_set = false;
+  if (!attr_set) {
     B2_CUDA(cudaFuncSetAttribute(umma_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_smem = 227 * 1024;
+    attr_set = true;
   }
+  const int grid = std::min(p.num_tiles, num_sms());
   umma_pair_kernel<<<grid, kUmmaThreads, smem, st>>>(a_hi, a_lo, b_hi, b_lo, p);
   B2_LAUNCHED();
   return B200SEP_OK;
@@ -469,7 +527,7 @@ int umma_gemm_run(const UmmaGemmPlan& pl, const float* scale, const float* shift
                   void* out_lo, const void* res_hi, const void* res_lo, int M_active, cudaStream_t st) {
   UmmaParams p{};
   p.mode = 0;
-  p.n_tile = pl.n_tile; p.n_total = pl.N; p.tmem_cols = pow2_cols(pl.n_tile);
+  p.n_tile = pl.n_tile; p.n_total = pl.N;
   p.num_iters = (pl.K + 63) / 64; p.ksteps = 4;
   p.a_bytes = 128 * 128; p.b_bytes = (uint32_t)pl.n_tile * 128;
   p.M = M_active; p.K = pl.K; p.rows_per_channel = rows_per_channel; p.channels = channels;
@@ -515,7 +573,7 @@ int umma_conv_run(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_lo, 
   B2_CHECK_ARG(ksize == 3, "umma_conv: only 3x3 kernels");
   UmmaParams p{};
   p.mode = 1; p.f_stride = kConvStride; p.t_mul = 1; p.t_off = -1;
-  p.n_c = n_c; p.n_tile = 3 * n_c; p.n_total = Cout; p.tmem_cols = pow2_cols(3 * n_c);
+  p.n_c = n_c; p.n_tile = 3 * n_c; p.n_total = Cout;
   p.kc = pl.kc; p.n_chunks = pl.Cin / pl.kc;
   p.num_iters = 3 * p.n_chunks; p.ksteps = pl.kc / 16;
   p.a_bytes = (uint32_t)pl.kc * 256; p.b_bytes = (uint32_t)p.ksteps * p.n_tile * 32;
@@ -524,7 +582,6 @@ int umma_conv_run(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_lo, 
   p.scale = scale; p.shift = shift; p.relu = relu;
   p.out_hi = (bf16*)out_hi; p.out_lo = (bf16*)out_lo;
   dim3 grid(pl.F <= 1 ? 1 : cdiv(pl.F - 1, kConvStride), pl.T, B * p.n_tiles);
-  B2_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "umma_conv: grid too large");
   return launch(pl.a_hi, pl.a_lo, pl.a_hi, pl.a_lo, p, grid, st);
 }
 
@@ -551,7 +608,7 @@ int umma_up_run(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_lo, in
                 const void* skip_hi, const void* skip_lo, void* out_hi, void* out_lo, cudaStream_t st) {
   UmmaParams p{};
   p.mode = 2; p.f_stride = kTileM; p.t_mul = 1; p.t_off = 0;
-  p.n_c = n_c; p.n_tile = 4 * n_c; p.n_total = Cout; p.tmem_cols = pow2_cols(4 * n_c);
+  p.n_c = n_c; p.n_tile = 4 * n_c; p.n_total = Cout;
   p.kc = pl.kc; p.n_chunks = pl.Cin / pl.kc; p.num_iters = p.n_chunks; p.ksteps = pl.kc / 16;
   p.a_bytes = (uint32_t)pl.kc * 256; p.b_bytes = (uint32_t)p.ksteps * p.n_tile * 32;
   p.T = pl.T; p.F = pl.F; p.Cin = pl.Cin; p.Cout = Cout; p.n_tiles = Cout / n_c;
@@ -559,7 +616,6 @@ int umma_up_run(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_lo, in
   p.scale = scale; p.shift = shift; p.relu = relu;
   p.out_hi = (bf16*)out_hi; p.out_lo = (bf16*)out_lo; p.res_hi = (const bf16*)skip_hi; p.res_lo = (const bf16*)skip_lo;
   dim3 grid(cdiv(pl.F, kTileM), pl.T, B * p.n_tiles);
-  B2_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "umma_up: grid too large");
   return launch(pl.a_hi, pl.a_lo, pl.a_hi, pl.a_lo, p, grid, st);
 }
 
@@ -568,7 +624,7 @@ int umma_down_run(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_lo, 
                   void* out_hi, void* out_lo, cudaStream_t st) {
   UmmaParams p{};
   p.mode = 3; p.f_stride = kTileM; p.t_mul = 2; p.t_off = 0;
-  p.n_c = n_c; p.n_tile = 2 * n_c; p.n_total = Cout; p.tmem_cols = pow2_cols(2 * n_c);
+  p.n_c = n_c; p.n_tile = 2 * n_c; p.n_total = Cout;
   p.kc = pl.kc; p.n_chunks = pl.Cin / pl.kc; p.num_iters = 2 * p.n_chunks; p.ksteps = pl.kc / 16;
   p.a_bytes = (uint32_t)pl.kc * 256; p.b_bytes = (uint32_t)p.ksteps * p.n_tile * 32;
   p.T = pl.T; p.F = pl.F; p.Cin = pl.Cin; p.Cout = Cout; p.n_tiles = Cout / n_c;
@@ -576,7 +632,6 @@ int umma_down_run(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_lo, 
   p.scale = scale; p.shift = shift; p.relu = relu;
   p.out_hi = (bf16*)out_hi; p.out_lo = (bf16*)out_lo;
   dim3 grid(cdiv(pl.F, kTileM), pl.T / 2, B * p.n_tiles);
-  B2_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "umma_down: grid too large");
   return launch(pl.a_hi, pl.a_lo, pl.a_hi, pl.a_lo, p, grid, st);
 }
 
