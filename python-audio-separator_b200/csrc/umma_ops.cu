@@ -30,7 +30,8 @@
 namespace b200sep {
 
 using bf16 = __nv_bfloat16;
-constexpr int kUmmaThreads = 192;
+constexpr int kUmmaThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int kMaxChannels = 512;   // per-channel scale/shift staged in shared memory (conv modes)
 constexpr int kTileM = 128;
 constexpr int kConvStride = 120;  // output pixels per conv tile (multiple of 8: TMA box starts must be 16-byte aligned)
 
@@ -97,7 +98,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
   uint64_t* tmem_full_bar = empty_bar + p.stages;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  float* edge_base = reinterpret_cast<float*>(tmem_slot + 4);  // CONV3x3: [2 acc][2][4 warps][n_c] rows exchanged between epilogue warps
+  float* sc_s = reinterpret_cast<float*>(tmem_slot + 4);  // conv modes: folded BatchNorm scale / shift per output channel
+  float* sh_s = sc_s + kMaxChannels;
+  float* edge_base = sh_s + kMaxChannels;  // CONV3x3: [2 acc][2][4 quadrants][n_c] rows exchanged between epilogue warps
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -108,7 +111,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
-      ptx::mbar_init(&tmem_empty_bar[a], 4);  // one arrive per epilogue warp
+      ptx::mbar_init(&tmem_empty_bar[a], 8);  // one arrive per epilogue warp
     }
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tmA_hi);
@@ -119,6 +122,12 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
     }
   }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (p.mode != 0) {
+    for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
+      sc_s[i] = __ldg(&p.scale[i]);
+      sh_s[i] = __ldg(&p.shift[i]);
+    }
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -212,19 +221,24 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
       }
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> BN/ReLU(/+res) -> split -> global =====
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    // ===== epilogue: TMEM -> registers -> BN/ReLU(/+res, *skip) -> split into bf16 hi/lo -> global =====
+    // Eight warps: warp w may only touch TMEM lanes 32*(w%4)..+31, so two warps share each lane quadrant and split
+    // the accumulator columns between them (two warps per scheduler also hide the ALU latency of the conversion chain).
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int m = q * 32 + lane;
+    const int ncol = (p.mode == 0) ? p.n_tile : p.n_c;  // columns of ONE logical output group
+    const int nchunks = ncol / 16;
+    const int ch_begin = half ? (nchunks + 1) / 2 : 0, ch_end = half ? nchunks : (nchunks + 1) / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile);
       const int m0 = tc.m0, f0 = tc.f0, t = tc.t, b = tc.b;
-      const int n0 = tc.n_idx * (p.mode == 0 ? p.n_tile : p.n_c);
+      const int n0 = tc.n_idx * ncol;
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase, 300 + acc);
       ptx::tc_fence_after();
       const uint32_t trow = tmem_base + (uint32_t)acc * acc_stride + ((uint32_t)(q * 32) << 16);
-      float* edge = edge_base + acc * 8 * p.n_c;
       if (p.mode == 0) {
         const int r = m0 + m;
         float sc = 1.f, sh = 0.f;
@@ -233,7 +247,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
           sc = __ldg(&p.scale[c]);
           sh = __ldg(&p.shift[c]);
         }
-        for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+        for (int ch = ch_begin; ch < ch_end; ++ch) {
+          const int c0 = ch * 16;
           uint32_t v[16];
           ptx::tmem_ld16(trow + (uint32_t)c0, v);
           ptx::tmem_ld_wait();
@@ -241,7 +256,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
           if (r < p.M && n < p.n_total) {
             const size_t o = (size_t)r * p.n_total + n;
             float x[16];
-  #pragma unroll
+#pragma unroll
             for (int j = 0; j < 16; ++j) {
               x[j] = fmaf(__uint_as_float(v[j]), sc, sh);
               if (p.relu) x[j] = fmaxf(x[j], 0.f);
@@ -254,12 +269,12 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
               rl[1] = __ldg(reinterpret_cast<const uint4*>(p.res_lo + o) + 1);
               const bf16* h = reinterpret_cast<const bf16*>(rh);
               const bf16* l = reinterpret_cast<const bf16*>(rl);
-  #pragma unroll
+#pragma unroll
               for (int j = 0; j < 16; ++j) x[j] += __bfloat162float(h[j]) + __bfloat162float(l[j]);
             }
             __align__(16) bf16 oh[16];
             __align__(16) bf16 ol[16];
-  #pragma unroll
+#pragma unroll
             for (int j = 0; j < 16; ++j) split_store2(x[j], oh[j], ol[j]);
             uint4* dh = reinterpret_cast<uint4*>(p.out_hi + o);
             uint4* dl = reinterpret_cast<uint4*>(p.out_lo + o);
@@ -278,31 +293,31 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
         const int T2 = 2 * p.T, F2 = 2 * p.F;
         const size_t plane = (size_t)T2 * F2;
         for (int dy = 0; dy < 2; ++dy) {
-          const size_t base = ((size_t)b * p.Cout) * plane + (size_t)(2 * t + dy) * F2 + 2 * f;
-          for (int c0 = 0; c0 < nc; c0 += 16) {
+          const size_t base = ((size_t)b * p.Cout + n0) * plane + (size_t)(2 * t + dy) * F2 + 2 * f;
+          for (int ch = ch_begin; ch < ch_end; ++ch) {
+            const int c0 = ch * 16;
             uint32_t v0[16], v1[16];
             ptx::tmem_ld16(trow + (uint32_t)((dy * 2 + 0) * nc + c0), v0);
             ptx::tmem_ld16(trow + (uint32_t)((dy * 2 + 1) * nc + c0), v1);
             ptx::tmem_ld_wait();
-            // all skip loads of this 16-channel group are issued before any store (read-only path: the compiler cannot
-            // otherwise move them above the preceding stores, which serialised the epilogue on memory latency)
-            uint32_t sk_h[16], sk_l[16];
-  #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int co = n0 + c0 + j;
-              sk_h[j] = 0x3f803f80u;  // bf16 (1.0, 1.0)
-              sk_l[j] = 0u;
-              if (p.res_hi && row_ok && co < p.Cout) {
-                const size_t o = base + (size_t)co * plane;
-                sk_h[j] = __ldg(reinterpret_cast<const unsigned int*>(p.res_hi + o));
-                sk_l[j] = __ldg(reinterpret_cast<const unsigned int*>(p.res_lo + o));
+            if (row_ok) {
+              const size_t o0 = base + (size_t)c0 * plane;
+              // all skip loads of this 16-channel group are issued before any store (read-only path)
+              uint32_t sk_h[16], sk_l[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                sk_h[j] = 0x3f803f80u;  // bf16 (1.0, 1.0)
+                sk_l[j] = 0u;
+                if (p.res_hi) {
+                  sk_h[j] = __ldg(reinterpret_cast<const unsigned int*>(p.res_hi + o0 + (size_t)j * plane));
+                  sk_l[j] = __ldg(reinterpret_cast<const unsigned int*>(p.res_lo + o0 + (size_t)j * plane));
+                }
               }
-            }
-  #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int co = n0 + c0 + j;
-              if (row_ok && co < p.Cout) {
-                const float sc = __ldg(&p.scale[co]), sh = __ldg(&p.shift[co]);
+              bf16* ph = p.out_hi + o0;
+              bf16* pl = p.out_lo + o0;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float sc = sc_s[n0 + c0 + j], sh = sh_s[n0 + c0 + j];
                 float x0 = fmaf(__uint_as_float(v0[j]), sc, sh), x1 = fmaf(__uint_as_float(v1[j]), sc, sh);
                 if (p.relu) {
                   x0 = fmaxf(x0, 0.f);
@@ -311,12 +326,13 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
                 // bf16 -> fp32 is a 16-bit shift: low half = element 0 (dx = 0), high half = element 1 (dx = 1)
                 x0 *= __uint_as_float(sk_h[j] << 16) + __uint_as_float(sk_l[j] << 16);
                 x1 *= __uint_as_float(sk_h[j] & 0xffff0000u) + __uint_as_float(sk_l[j] & 0xffff0000u);
-                const size_t o = base + (size_t)co * plane;
                 __nv_bfloat162 oh, ol;
                 split_store2(x0, oh.x, ol.x);
                 split_store2(x1, oh.y, ol.y);
-                *reinterpret_cast<__nv_bfloat162*>(p.out_hi + o) = oh;  // 32 lanes -> 128 contiguous bytes
-                *reinterpret_cast<__nv_bfloat162*>(p.out_lo + o) = ol;
+                *reinterpret_cast<__nv_bfloat162*>(ph) = oh;  // 32 lanes -> 128 contiguous bytes
+                *reinterpret_cast<__nv_bfloat162*>(pl) = ol;
+                ph += plane;
+                pl += plane;
               }
             }
           }
@@ -328,76 +344,85 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
         const int fo = (f0 + m) >> 1, Fo = p.F >> 1, To = p.T >> 1;
         const bool row_ok = ((m & 1) == 0) && fo < Fo;
         const size_t plane = (size_t)To * Fo;
-        const size_t base = ((size_t)b * p.Cout) * plane + (size_t)t * Fo + fo;
-        for (int c0 = 0; c0 < nc; c0 += 16) {
+        const size_t base = ((size_t)b * p.Cout + n0) * plane + (size_t)t * Fo + fo;
+        for (int ch = ch_begin; ch < ch_end; ++ch) {
+          const int c0 = ch * 16;
           uint32_t v0[16], v1[16];
           ptx::tmem_ld16(trow + (uint32_t)c0, v0);
           ptx::tmem_ld16(trow + (uint32_t)(nc + c0), v1);
           ptx::tmem_ld_wait();
-  #pragma unroll
+          bf16* ph = p.out_hi + base + (size_t)c0 * plane;
+          bf16* pl = p.out_lo + base + (size_t)c0 * plane;
+#pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float nb = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[j]), 1);  // P_1 of row m+1 (same warp: m even)
-            const int co = n0 + c0 + j;
-            if (row_ok && co < p.Cout) {
-              float x = fmaf(__uint_as_float(v0[j]) + nb, __ldg(&p.scale[co]), __ldg(&p.shift[co]));
+            if (row_ok) {
+              float x = fmaf(__uint_as_float(v0[j]) + nb, sc_s[n0 + c0 + j], sh_s[n0 + c0 + j]);
               if (p.relu) x = fmaxf(x, 0.f);
               bf16 h, l;
               split_store2(x, h, l);
-              const size_t o = base + (size_t)co * plane;
-              p.out_hi[o] = h;
-              p.out_lo[o] = l;
+              *ph = h;
+              *pl = l;
             }
+            ph += plane;
+            pl += plane;
           }
         }
       } else {
-        // P_dx[m][co] sits in column dx*n_c + co of TMEM lane m.  out[f0+j] = P_0[j-1] + P_1[j] + P_2[j+1].
+        // 3x3: P_dx[m][co] sits in column dx*n_c + co of TMEM lane m.  out[f0+j] = P_0[j-1] + P_1[j] + P_2[j+1].
         const int nc = p.n_c;
-        float* edge0 = edge + q * nc;             // this warp's row 32q+31 of P_0 (needed by lane 0 of warp q+1)
-        float* edge2 = edge + (4 + q) * nc;       // this warp's row 32q    of P_2 (needed by lane 31 of warp q-1)
-        for (int c0 = 0; c0 < nc; c0 += 16) {
+        float* edge = edge_base + acc * 8 * nc;
+        float* edge0 = edge + q * nc;        // this warp's row 32q+31 of P_0 (needed by lane 0 of quadrant q+1)
+        float* edge2 = edge + (4 + q) * nc;  // this warp's row 32q    of P_2 (needed by lane 31 of quadrant q-1)
+        for (int ch = ch_begin; ch < ch_end; ++ch) {
+          const int c0 = ch * 16;
           uint32_t v0[16], v2[16];
           ptx::tmem_ld16(trow + (uint32_t)c0, v0);
           ptx::tmem_ld16(trow + (uint32_t)(2 * nc + c0), v2);
           ptx::tmem_ld_wait();
           if (lane == 31) {
-  #pragma unroll
+#pragma unroll
             for (int j = 0; j < 16; ++j) edge0[c0 + j] = __uint_as_float(v0[j]);
           }
           if (lane == 0) {
-  #pragma unroll
+#pragma unroll
             for (int j = 0; j < 16; ++j) edge2[c0 + j] = __uint_as_float(v2[j]);
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
-        const float* left = edge + (q - 1) * nc;        // valid for q > 0
-        const float* right = edge + (4 + q + 1) * nc;   // valid for q < 3
+        // the four warps that own this column half exchange their boundary rows (named barrier 1 or 2, 128 threads)
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+        const float* left = edge + (q - 1) * nc;       // valid for q > 0
+        const float* right = edge + (4 + q + 1) * nc;  // valid for q < 3
         const int f = f0 + m;
         const int j_lo = (f0 == 0) ? 0 : 1;
         const bool row_ok = (m >= j_lo) && (m < kConvStride + 1) && (f < p.F);
         const size_t plane = (size_t)p.T * p.F;
-        const size_t base = ((size_t)b * p.Cout) * plane + (size_t)t * p.F + f;
-        for (int c0 = 0; c0 < nc; c0 += 16) {
+        const size_t base = ((size_t)b * p.Cout + n0) * plane + (size_t)t * p.F + f;
+        for (int ch = ch_begin; ch < ch_end; ++ch) {
+          const int c0 = ch * 16;
           uint32_t v0[16], v1[16], v2[16];
           ptx::tmem_ld16(trow + (uint32_t)c0, v0);
           ptx::tmem_ld16(trow + (uint32_t)(nc + c0), v1);
           ptx::tmem_ld16(trow + (uint32_t)(2 * nc + c0), v2);
           ptx::tmem_ld_wait();
-  #pragma unroll
+          bf16* ph = p.out_hi + base + (size_t)c0 * plane;
+          bf16* pl = p.out_lo + base + (size_t)c0 * plane;
+#pragma unroll
           for (int j = 0; j < 16; ++j) {
             float a = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[j]), 1);    // P_0 of row m-1
             float c = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[j]), 1);  // P_2 of row m+1
-            if (lane == 0) a = (q > 0) ? left[c0 + j] : 0.f;   // m == 0: x[f0-1] is either padding (f0 == 0) or not an output row
+            if (lane == 0) a = (q > 0) ? left[c0 + j] : 0.f;    // m == 0: x[f0-1] is either padding (f0 == 0) or not an output row
             if (lane == 31) c = (q < 3) ? right[c0 + j] : 0.f;  // m == 127 is never an output row
-            const int co = n0 + c0 + j;
-            if (row_ok && co < p.Cout) {
-              float x = fmaf(a + __uint_as_float(v1[j]) + c, __ldg(&p.scale[co]), __ldg(&p.shift[co]));
+            if (row_ok) {
+              float x = fmaf(a + __uint_as_float(v1[j]) + c, sc_s[n0 + c0 + j], sh_s[n0 + c0 + j]);
               if (p.relu) x = fmaxf(x, 0.f);
               bf16 h, l;
               split_store2(x, h, l);
-              const size_t o = base + (size_t)co * plane;
-              p.out_hi[o] = h;  // 32 lanes -> 32 consecutive pixels: one 64-byte segment per plane
-              p.out_lo[o] = l;
+              *ph = h;  // 32 lanes -> 32 consecutive pixels: one 64-byte segment per plane
+              *pl = l;
             }
+            ph += plane;
+            pl += plane;
           }
         }
       }
@@ -484,7 +509,8 @@ static int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtens
   p.n_ftiles = (int)tiles.x;
   p.t_tiles = (int)tiles.y;
   p.num_tiles = (int)(tiles.x * tiles.y * tiles.z);
-  const size_t fixed = 1024 /*alignment slack*/ + 64 * sizeof(uint64_t) + 64 + (p.mode != 0 ? (size_t)16 * p.n_c * sizeof(float) : 0);
+  const size_t fixed = 1024 /*alignment slack*/ + 64 * sizeof(uint64_t) + 64 + 2 * kMaxChannels * sizeof(float) + (p.mode != 0 ? (size_t)16 * p.n_c * sizeof(float) : 0);
+  B2_CHECK_ARG(p.mode == 0 || p.Cout <= kMaxChannels, "umma: more than %d output channels", kMaxChannels);
   const size_t budget = 220 * 1024 - fixed;  // one persistent CTA per SM
   int stages = (int)(budget / p.stage_bytes);
   if (stages > 8) stages = 8;
