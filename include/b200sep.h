@@ -91,6 +91,17 @@ int b200sep_demix_overlap_add(const float* chunks, int n_chunks, int chunk_len, 
                               int64_t trim, int64_t n_out, int use_window, float out_scale, const float* mix,
                               float compensate, int interleave, float* primary, float* secondary, void* stream);
 
+/*
+ * Same, for ONE rank of a time-sharded run (chunk ranges split across GPUs): `chunks` holds the n_local_chunks chunks
+ * [first_chunk, first_chunk + n_local_chunks) of the global n_chunks grid (own chunks plus the halo received from the
+ * left neighbour) and only outputs q in [q_begin, q_end) are written; primary / secondary / mix are still indexed
+ * with the global q and n_out.  Returns B200SEP_ERR_ARG if a covering chunk is missing from the buffer.
+ */
+int b200sep_demix_overlap_add_range(const float* chunks, int first_chunk, int n_local_chunks, int n_chunks, int chunk_len, int64_t step,
+                                    int64_t total_len, int64_t trim, int64_t n_out, int64_t q_begin, int64_t q_end, int use_window,
+                                    float out_scale, const float* mix, float compensate, int interleave, float* primary,
+                                    float* secondary, void* stream);
+
 /* max |x| over n floats -> *result (device float).  (np.abs(mix).max(), mdx_separator.py:155; spec_utils.py:110) */
 int b200sep_absmax(const float* x, int64_t n, float* result, void* stream);
 /* y = x * s where s = max_peak/absmax if absmax > max_peak; min_peak/absmax if min_peak>=0 and absmax < min_peak;

@@ -36,6 +36,7 @@ _SIGS = {
     "b200sep_stft_inverse_work_floats": (i64, [vp, i32, i32, i32, i32]),
     "b200sep_stft_inverse": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp]),
     "b200sep_demix_overlap_add": (i32, [vp, i32, i32, i64, i64, i64, i64, i32, f32, vp, f32, i32, vp, vp, vp]),
+    "b200sep_demix_overlap_add_range": (i32, [vp, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i32, f32, vp, f32, i32, vp, vp, vp]),
     "b200sep_absmax": (i32, [vp, i64, vp, vp]),
     "b200sep_normalize": (i32, [vp, i64, vp, f32, f32, vp, vp]),
     "b200sep_to_pcm16": (i32, [vp, i64, vp, vp]),

@@ -42,7 +42,7 @@ class StftPlan:
 
     def __del__(self):
         h = getattr(self, "handle", None)
-        if h:
+        if h and lib is not None:  # `lib` may already be torn down at interpreter exit
             lib.b200sep_stft_plan_destroy(h)
             self.handle = None
 
@@ -88,7 +88,7 @@ class MdxNet:
 
     def __del__(self):
         h = getattr(self, "handle", None)
-        if h:
+        if h and lib is not None:
             lib.b200sep_mdxnet_destroy(h)
             self.handle = None
 

@@ -263,10 +263,11 @@ __global__ void istft_ola_kernel(const float* __restrict__ fr, const float* __re
 }
 
 // demix accumulate/divide/trim as a gather over covering chunks (mdx_separator.py:348-401)
-__global__ void demix_ola_kernel(const float* __restrict__ chunks, int n_chunks, int chunk_len, int64_t step, int64_t total_len,
-                                 int64_t trim, int64_t n_out, int use_window, float out_scale, const float* __restrict__ mix,
-                                 float compensate, int interleave, float* __restrict__ primary, float* __restrict__ secondary) {
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_out; q += (int64_t)gridDim.x * blockDim.x) {
+__global__ void demix_ola_kernel(const float* __restrict__ chunks, int first_chunk, int n_chunks, int chunk_len, int64_t step, int64_t total_len,
+                                 int64_t trim, int64_t n_out, int64_t q_begin, int64_t q_end, int use_window, float out_scale,
+                                 const float* __restrict__ mix, float compensate, int interleave, float* __restrict__ primary,
+                                 float* __restrict__ secondary) {
+  for (int64_t q = q_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < q_end; q += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p = q + trim;
     int64_t i_hi = p / step;
     if (i_hi > n_chunks - 1) i_hi = n_chunks - 1;
@@ -286,7 +287,7 @@ __global__ void demix_ola_kernel(const float* __restrict__ chunks, int n_chunks,
         // np.hanning(M)[n] = 0.5 - 0.5*cos(2*pi*n/(M-1)); np.hanning(1) = [1.]
         w = (actual > 1) ? (float)(0.5 - 0.5 * cospi(2.0 * (double)n / (double)(actual - 1))) : 1.f;
       }
-      const float* y = chunks + (int64_t)i * 2 * chunk_len;
+      const float* y = chunks + (int64_t)(i - first_chunk) * 2 * chunk_len;  // chunks[0] is global chunk `first_chunk`
       res[0] += __ldg(&y[n]) * w;
       res[1] += __ldg(&y[chunk_len + n]) * w;
       div += w;
@@ -430,6 +431,29 @@ extern "C" int b200sep_stft_inverse(const b200sep_stft_plan* plan, const float* 
   return B200SEP_OK;
 }
 
+extern "C" int b200sep_demix_overlap_add_range(const float* chunks, int first_chunk, int n_local_chunks, int n_chunks, int chunk_len, int64_t step,
+                                               int64_t total_len, int64_t trim, int64_t n_out, int64_t q_begin, int64_t q_end, int use_window,
+                                               float out_scale, const float* mix, float compensate, int interleave, float* primary,
+                                               float* secondary, void* stream) {
+  B2_CHECK_ARG(chunks && primary, "demix_overlap_add_range: NULL argument");
+  B2_CHECK_ARG(mix == nullptr || secondary != nullptr, "demix_overlap_add_range: mix given without a secondary buffer");
+  B2_CHECK_ARG(n_chunks >= 1 && chunk_len >= 1 && step >= 1 && total_len >= 1 && trim >= 0 && n_out >= 0, "demix_overlap_add_range: bad sizes");
+  B2_CHECK_ARG(trim + n_out <= total_len && 0 <= q_begin && q_begin <= q_end && q_end <= n_out, "demix_overlap_add_range: bad output range");
+  if (q_end == q_begin) return B200SEP_OK;
+  // every chunk that covers [q_begin, q_end) must be present in the local buffer
+  const int64_t p0 = q_begin + trim, p1 = q_end - 1 + trim;
+  int64_t need_lo = (p0 - chunk_len + 1 <= 0) ? 0 : (p0 - chunk_len + step) / step;
+  int64_t need_hi = std::min<int64_t>(p1 / step, n_chunks - 1);
+  B2_CHECK_ARG(need_lo >= first_chunk && need_hi < (int64_t)first_chunk + n_local_chunks,
+               "demix_overlap_add_range: outputs [%lld,%lld) need chunks [%lld,%lld] but the buffer holds [%d,%d)", (long long)q_begin, (long long)q_end,
+               (long long)need_lo, (long long)need_hi, first_chunk, first_chunk + n_local_chunks);
+  const int blocks = (int)std::min<int64_t>(cdiv(q_end - q_begin, 256), kNumSMs * 16);
+  demix_ola_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(chunks, first_chunk, n_chunks, chunk_len, step, total_len, trim, n_out, q_begin, q_end, use_window,
+                                                             out_scale, mix, compensate, interleave, primary, secondary);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
 extern "C" int b200sep_demix_overlap_add(const float* chunks, int n_chunks, int chunk_len, int64_t step, int64_t total_len, int64_t trim,
                                          int64_t n_out, int use_window, float out_scale, const float* mix, float compensate,
                                          int interleave, float* primary, float* secondary, void* stream) {
@@ -439,7 +463,7 @@ extern "C" int b200sep_demix_overlap_add(const float* chunks, int n_chunks, int 
   B2_CHECK_ARG(trim + n_out <= total_len, "demix_overlap_add: trim+n_out exceeds total_len");
   if (n_out == 0) return B200SEP_OK;
   const int blocks = (int)std::min<int64_t>(cdiv(n_out, 256), kNumSMs * 16);
-  demix_ola_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(chunks, n_chunks, chunk_len, step, total_len, trim, n_out, use_window, out_scale,
+  demix_ola_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(chunks, 0, n_chunks, chunk_len, step, total_len, trim, n_out, 0, n_out, use_window, out_scale,
                                                              mix, compensate, interleave, primary, secondary);
   B2_LAUNCHED();
   return B200SEP_OK;

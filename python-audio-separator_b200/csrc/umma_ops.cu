@@ -19,6 +19,7 @@
 //          Tiles advance by 120 pixels so that every output has both neighbours inside the same 128-row tile.
 // Warp roles per CTA (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer, warps 2-5 = epilogue.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -40,6 +41,7 @@ struct UmmaParams {
   int f_stride, t_mul, t_off;  // implicit-GEMM addressing: tile f0 = blockIdx.x*f_stride, input row = t*t_mul + r + t_off
   int n_tile, n_total, tmem_cols;
   int num_iters, ksteps, stages;
+  int dbg;  // development switches from env B200SEP_DBG (0 in production): see launch()
   int num_tiles, n_ftiles, t_tiles;  // persistent tile walk (n_tiles below = tiles along N / output channels)
   uint32_t a_bytes, b_bytes, stage_bytes;
   // CONV
@@ -149,24 +151,32 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
           uint8_t* a_lo = st + p.a_bytes;
           uint8_t* b_hi = st + 2 * p.a_bytes;
           uint8_t* b_lo = b_hi + p.b_bytes;
-          ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * p.a_bytes + 2 * p.b_bytes);
+          ptx::mbar_arrive_expect_tx(&full_bar[s], ((p.dbg & 8) ? 0 : 2 * p.a_bytes) + ((p.dbg & 16) ? 0 : 2 * p.b_bytes));
           if (p.mode == 0) {
             const int k0 = i * 64;
-            ptx::tma_load_2d(a_hi, &tmA_hi, &full_bar[s], k0, tc.m0);
-            ptx::tma_load_2d(a_lo, &tmA_lo, &full_bar[s], k0, tc.m0);
-            ptx::tma_load_2d(b_hi, &tmB_hi, &full_bar[s], k0, n0);
-            ptx::tma_load_2d(b_lo, &tmB_lo, &full_bar[s], k0, n0);
+            if (!(p.dbg & 8)) {
+              ptx::tma_load_2d(a_hi, &tmA_hi, &full_bar[s], k0, tc.m0);
+              ptx::tma_load_2d(a_lo, &tmA_lo, &full_bar[s], k0, tc.m0);
+            }
+            if (!(p.dbg & 16)) {
+              ptx::tma_load_2d(b_hi, &tmB_hi, &full_bar[s], k0, n0);
+              ptx::tma_load_2d(b_lo, &tmB_lo, &full_bar[s], k0, n0);
+            }
           } else {
             const int r = i / p.n_chunks, chunk = i - r * p.n_chunks;
             const int cf = tc.f0, ct = tc.t * p.t_mul + r + p.t_off, cc = tc.b * p.Cin + chunk * p.kc;
             const uint32_t box = (uint32_t)p.kc * 128u;
-            ptx::tma_load_3d(a_hi, &tmA_hi, &full_bar[s], cf, ct, cc);
-            ptx::tma_load_3d(a_hi + box, &tmA_hi, &full_bar[s], cf + 64, ct, cc);
-            ptx::tma_load_3d(a_lo, &tmA_lo, &full_bar[s], cf, ct, cc);
-            ptx::tma_load_3d(a_lo + box, &tmA_lo, &full_bar[s], cf + 64, ct, cc);
+            if (!(p.dbg & 8)) {
+              ptx::tma_load_3d(a_hi, &tmA_hi, &full_bar[s], cf, ct, cc);
+              ptx::tma_load_3d(a_hi + box, &tmA_hi, &full_bar[s], cf + 64, ct, cc);
+              ptx::tma_load_3d(a_lo, &tmA_lo, &full_bar[s], cf, ct, cc);
+              ptx::tma_load_3d(a_lo + box, &tmA_lo, &full_bar[s], cf + 64, ct, cc);
+            }
             const size_t woff = ((size_t)tc.n_idx * p.num_iters + i) * (size_t)(p.b_bytes / 2);
-            ptx::bulk_load_1d(b_hi, p.wb_hi + woff, p.b_bytes, &full_bar[s]);
-            ptx::bulk_load_1d(b_lo, p.wb_lo + woff, p.b_bytes, &full_bar[s]);
+            if (!(p.dbg & 16)) {
+              ptx::bulk_load_1d(b_hi, p.wb_hi + woff, p.b_bytes, &full_bar[s]);
+              ptx::bulk_load_1d(b_lo, p.wb_lo + woff, p.b_bytes, &full_bar[s]);
+            }
           }
           if (++s == p.stages) {
             s = 0;
@@ -190,7 +200,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
           ptx::tc_fence_after();
           const uint32_t st = ptx::smem_u32(smem + (size_t)s * p.stage_bytes);
           const uint32_t a_hi = st, a_lo = st + p.a_bytes, b_hi = st + 2 * p.a_bytes, b_lo = b_hi + p.b_bytes;
-          for (int j = 0; j < p.ksteps; ++j) {
+          for (int j = 0; j < ((p.dbg & 4) ? 0 : p.ksteps); ++j) {
             uint64_t dah, dal, dbh, dbl;
             if (p.mode == 0) {
               dah = ptx::smem_desc(a_hi + j * 32, 16, 1024, ptx::kLayoutSW128);
@@ -230,16 +240,35 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
     const int ncol = (p.mode == 0) ? p.n_tile : p.n_c;  // columns of ONE logical output group
     const int nchunks = ncol / 16;
     const int ch_begin = half ? (nchunks + 1) / 2 : 0, ch_end = half ? nchunks : (nchunks + 1) / 2;
+    const bool st_on = !(p.dbg & 2);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile);
       const int m0 = tc.m0, f0 = tc.f0, t = tc.t, b = tc.b;
       const int n0 = tc.n_idx * ncol;
+      // GEMM: the residual does not depend on the accumulator -> fetch it while the MMAs of this tile are still running
+      uint4 rh[4][2], rl[4][2];
+      if (p.mode == 0 && p.res_hi && !(p.dbg & 1)) {
+        const int r = m0 + m;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int n = n0 + (ch_begin + k) * 16;
+          if (ch_begin + k < ch_end && r < p.M && n < p.n_total) {
+            const size_t o = (size_t)r * p.n_total + n;
+            rh[k][0] = __ldg(reinterpret_cast<const uint4*>(p.res_hi + o));
+            rh[k][1] = __ldg(reinterpret_cast<const uint4*>(p.res_hi + o) + 1);
+            rl[k][0] = __ldg(reinterpret_cast<const uint4*>(p.res_lo + o));
+            rl[k][1] = __ldg(reinterpret_cast<const uint4*>(p.res_lo + o) + 1);
+          }
+        }
+      }
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase, 300 + acc);
       ptx::tc_fence_after();
       const uint32_t trow = tmem_base + (uint32_t)acc * acc_stride + ((uint32_t)(q * 32) << 16);
-      if (p.mode == 0) {
+      if (p.dbg & 32) {
+        // development: handshake only
+      } else if (p.mode == 0) {
         const int r = m0 + m;
         float sc = 1.f, sh = 0.f;
         if (r < p.M) {
@@ -247,7 +276,10 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
           sc = __ldg(&p.scale[c]);
           sh = __ldg(&p.shift[c]);
         }
-        for (int ch = ch_begin; ch < ch_end; ++ch) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int ch = ch_begin + k;
+          if (ch >= ch_end) break;
           const int c0 = ch * 16;
           uint32_t v[16];
           ptx::tmem_ld16(trow + (uint32_t)c0, v);
@@ -261,14 +293,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
               x[j] = fmaf(__uint_as_float(v[j]), sc, sh);
               if (p.relu) x[j] = fmaxf(x[j], 0.f);
             }
-            if (p.res_hi) {
-              uint4 rh[2], rl[2];
-              rh[0] = __ldg(reinterpret_cast<const uint4*>(p.res_hi + o));
-              rh[1] = __ldg(reinterpret_cast<const uint4*>(p.res_hi + o) + 1);
-              rl[0] = __ldg(reinterpret_cast<const uint4*>(p.res_lo + o));
-              rl[1] = __ldg(reinterpret_cast<const uint4*>(p.res_lo + o) + 1);
-              const bf16* h = reinterpret_cast<const bf16*>(rh);
-              const bf16* l = reinterpret_cast<const bf16*>(rl);
+            if (p.res_hi && !(p.dbg & 1)) {
+              const bf16* h = reinterpret_cast<const bf16*>(rh[k]);
+              const bf16* l = reinterpret_cast<const bf16*>(rl[k]);
 #pragma unroll
               for (int j = 0; j < 16; ++j) x[j] += __bfloat162float(h[j]) + __bfloat162float(l[j]);
             }
@@ -278,10 +305,12 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
             for (int j = 0; j < 16; ++j) split_store2(x[j], oh[j], ol[j]);
             uint4* dh = reinterpret_cast<uint4*>(p.out_hi + o);
             uint4* dl = reinterpret_cast<uint4*>(p.out_lo + o);
-            dh[0] = reinterpret_cast<const uint4*>(oh)[0];
-            dh[1] = reinterpret_cast<const uint4*>(oh)[1];
-            dl[0] = reinterpret_cast<const uint4*>(ol)[0];
-            dl[1] = reinterpret_cast<const uint4*>(ol)[1];
+            if (st_on || x[0] == 1.2345e30f) {
+              dh[0] = reinterpret_cast<const uint4*>(oh)[0];
+              dh[1] = reinterpret_cast<const uint4*>(oh)[1];
+              dl[0] = reinterpret_cast<const uint4*>(ol)[0];
+              dl[1] = reinterpret_cast<const uint4*>(ol)[1];
+            }
           }
         }
       } else if (p.mode == 2) {
@@ -308,16 +337,24 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
               for (int j = 0; j < 16; ++j) {
                 sk_h[j] = 0x3f803f80u;  // bf16 (1.0, 1.0)
                 sk_l[j] = 0u;
-                if (p.res_hi) {
+                if (p.res_hi && !(p.dbg & 1)) {
                   sk_h[j] = __ldg(reinterpret_cast<const unsigned int*>(p.res_hi + o0 + (size_t)j * plane));
                   sk_l[j] = __ldg(reinterpret_cast<const unsigned int*>(p.res_lo + o0 + (size_t)j * plane));
                 }
+              }
+              float scv[16], shv[16];
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 s4 = *reinterpret_cast<const float4*>(&sc_s[n0 + c0 + 4 * j4]);
+                const float4 h4 = *reinterpret_cast<const float4*>(&sh_s[n0 + c0 + 4 * j4]);
+                scv[4 * j4] = s4.x; scv[4 * j4 + 1] = s4.y; scv[4 * j4 + 2] = s4.z; scv[4 * j4 + 3] = s4.w;
+                shv[4 * j4] = h4.x; shv[4 * j4 + 1] = h4.y; shv[4 * j4 + 2] = h4.z; shv[4 * j4 + 3] = h4.w;
               }
               bf16* ph = p.out_hi + o0;
               bf16* pl = p.out_lo + o0;
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                const float sc = sc_s[n0 + c0 + j], sh = sh_s[n0 + c0 + j];
+                const float sc = scv[j], sh = shv[j];
                 float x0 = fmaf(__uint_as_float(v0[j]), sc, sh), x1 = fmaf(__uint_as_float(v1[j]), sc, sh);
                 if (p.relu) {
                   x0 = fmaxf(x0, 0.f);
@@ -329,8 +366,10 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
                 __nv_bfloat162 oh, ol;
                 split_store2(x0, oh.x, ol.x);
                 split_store2(x1, oh.y, ol.y);
-                *reinterpret_cast<__nv_bfloat162*>(ph) = oh;  // 32 lanes -> 128 contiguous bytes
-                *reinterpret_cast<__nv_bfloat162*>(pl) = ol;
+                if (st_on || x0 == 1.2345e30f) {
+                  *reinterpret_cast<__nv_bfloat162*>(ph) = oh;  // 32 lanes -> 128 contiguous bytes
+                  *reinterpret_cast<__nv_bfloat162*>(pl) = ol;
+                }
                 ph += plane;
                 pl += plane;
               }
@@ -351,21 +390,31 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
           ptx::tmem_ld16(trow + (uint32_t)c0, v0);
           ptx::tmem_ld16(trow + (uint32_t)(nc + c0), v1);
           ptx::tmem_ld_wait();
-          bf16* ph = p.out_hi + base + (size_t)c0 * plane;
-          bf16* pl = p.out_lo + base + (size_t)c0 * plane;
+          float x[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float nb = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[j]), 1);  // P_1 of row m+1 (same warp: m even)
-            if (row_ok) {
-              float x = fmaf(__uint_as_float(v0[j]) + nb, sc_s[n0 + c0 + j], sh_s[n0 + c0 + j]);
-              if (p.relu) x = fmaxf(x, 0.f);
+          for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v0[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(v1[j]), 1);  // + P_1 of row m+1
+          float sc[16], sh[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 s4 = *reinterpret_cast<const float4*>(&sc_s[n0 + c0 + 4 * j4]);
+            const float4 h4 = *reinterpret_cast<const float4*>(&sh_s[n0 + c0 + 4 * j4]);
+            sc[4 * j4] = s4.x; sc[4 * j4 + 1] = s4.y; sc[4 * j4 + 2] = s4.z; sc[4 * j4 + 3] = s4.w;
+            sh[4 * j4] = h4.x; sh[4 * j4 + 1] = h4.y; sh[4 * j4 + 2] = h4.z; sh[4 * j4 + 3] = h4.w;
+          }
+          if (row_ok) {
+            bf16* ph = p.out_hi + base + (size_t)c0 * plane;
+            bf16* pl = p.out_lo + base + (size_t)c0 * plane;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float y = fmaf(x[j], sc[j], sh[j]);
+              if (p.relu) y = fmaxf(y, 0.f);
               bf16 h, l;
-              split_store2(x, h, l);
-              *ph = h;
-              *pl = l;
+              split_store2(y, h, l);
+              if (st_on || y == 1.2345e30f) {
+                ph[(size_t)j * plane] = h;
+                pl[(size_t)j * plane] = l;
+              }
             }
-            ph += plane;
-            pl += plane;
           }
         }
       } else {
@@ -405,24 +454,46 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
           ptx::tmem_ld16(trow + (uint32_t)(nc + c0), v1);
           ptx::tmem_ld16(trow + (uint32_t)(2 * nc + c0), v2);
           ptx::tmem_ld_wait();
-          bf16* ph = p.out_hi + base + (size_t)c0 * plane;
-          bf16* pl = p.out_lo + base + (size_t)c0 * plane;
+          float x[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            float a = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[j]), 1);    // P_0 of row m-1
-            float c = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[j]), 1);  // P_2 of row m+1
-            if (lane == 0) a = (q > 0) ? left[c0 + j] : 0.f;    // m == 0: x[f0-1] is either padding (f0 == 0) or not an output row
-            if (lane == 31) c = (q < 3) ? right[c0 + j] : 0.f;  // m == 127 is never an output row
-            if (row_ok) {
-              float x = fmaf(a + __uint_as_float(v1[j]) + c, sc_s[n0 + c0 + j], sh_s[n0 + c0 + j]);
-              if (p.relu) x = fmaxf(x, 0.f);
+            const float a = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[j]), 1);    // P_0 of row m-1
+            const float c = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[j]), 1);  // P_2 of row m+1
+            x[j] = __uint_as_float(v1[j]) + ((lane == 0) ? 0.f : a) + ((lane == 31) ? 0.f : c);
+          }
+          // rows at a warp edge take their neighbour from the exchange buffer (one divergent region per 16 columns);
+          // m == 0 with f0 == 0 is the left zero padding, m == 0 otherwise and m == 127 are never output rows
+          if (lane == 0 && q > 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] += left[c0 + j];
+          }
+          if (lane == 31 && q < 3) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] += right[c0 + j];
+          }
+          // per-channel affine: read all 32 coefficients before the first global store (vector LDS, no per-column stall)
+          float sc[16], sh[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 s4 = *reinterpret_cast<const float4*>(&sc_s[n0 + c0 + 4 * j4]);
+            const float4 h4 = *reinterpret_cast<const float4*>(&sh_s[n0 + c0 + 4 * j4]);
+            sc[4 * j4] = s4.x; sc[4 * j4 + 1] = s4.y; sc[4 * j4 + 2] = s4.z; sc[4 * j4 + 3] = s4.w;
+            sh[4 * j4] = h4.x; sh[4 * j4 + 1] = h4.y; sh[4 * j4 + 2] = h4.z; sh[4 * j4 + 3] = h4.w;
+          }
+          if (row_ok) {
+            bf16* ph = p.out_hi + base + (size_t)c0 * plane;
+            bf16* pl = p.out_lo + base + (size_t)c0 * plane;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float y = fmaf(x[j], sc[j], sh[j]);
+              if (p.relu) y = fmaxf(y, 0.f);
               bf16 h, l;
-              split_store2(x, h, l);
-              *ph = h;  // 32 lanes -> 32 consecutive pixels: one 64-byte segment per plane
-              *pl = l;
+              split_store2(y, h, l);
+              if (st_on || y == 1.2345e30f) {
+                ph[(size_t)j * plane] = h;  // 32 lanes -> 32 consecutive pixels: one 64-byte segment per plane
+                pl[(size_t)j * plane] = l;
+              }
             }
-            ph += plane;
-            pl += plane;
           }
         }
       }
@@ -502,6 +573,10 @@ static int num_sms() {
 // `tiles` is the logical tile grid: GEMM (n tiles, m tiles, 1); conv modes (f tiles, output rows, batch * channel tiles).
 static int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo, UmmaParams& p, dim3 tiles,
                   cudaStream_t st) {
+  {
+    const char* e = getenv("B200SEP_DBG");  // development only: selectively disable parts of the kernel (results become wrong)
+    p.dbg = e ? atoi(e) : 0;
+  }
   p.stage_bytes = ((2 * p.a_bytes + 2 * p.b_bytes + 1023) / 1024) * 1024;
   p.tmem_cols = 2 * pow2_cols(p.n_tile);  // two accumulators: the epilogue of tile i overlaps the MMAs of tile i+1
   B2_CHECK_ARG(p.tmem_cols <= 512, "umma: n_tile=%d needs more than 512 TMEM columns", p.n_tile);
@@ -559,6 +634,7 @@ int umma_gemm_run(const UmmaGemmPlan& pl, const float* scale, const float* shift
   p.M = M_active; p.K = pl.K; p.rows_per_channel = rows_per_channel; p.channels = channels;
   p.scale = scale; p.shift = shift; p.relu = relu;
   p.out_hi = (bf16*)out_hi; p.out_lo = (bf16*)out_lo; p.res_hi = (const bf16*)res_hi; p.res_lo = (const bf16*)res_lo;
+  B2_CHECK_ARG(pl.n_tile <= 128, "umma_gemm: n_tile=%d exceeds the epilogue's 8 column groups", pl.n_tile);
   dim3 grid(pl.N / pl.n_tile, cdiv(M_active, kTileM));
   return launch(pl.a_hi, pl.a_lo, pl.b_hi, pl.b_lo, p, grid, st);
 }
