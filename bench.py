@@ -26,6 +26,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "python-audio-separator_b200"))
 
 SR = 44100
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE conv3x3 launch at U-Net scale 0, batch 4 (profiles/r01_conv3x3_s0_ncu_full.txt)
+NCU_CONV_S0_DRAM_BYTES_PER_LAUNCH = 605.2e6 + 566.1e6
 METRIC = "real-time factor (audio-sec/wall-sec) @44.1kHz stereo"
 
 
@@ -222,23 +224,31 @@ def main():
         dist.all_reduce(lt)
         launches = int(lt[0])
 
-    # ---- roofline of the dominant kernel category, timed live with CUDA events around each launch on the engine's stream
+    # ---- roofline of the dominant kernel (launch shape), timed live with CUDA events around each launch on the engine's stream
     net.profile(True)
     step_device()
     torch.cuda.synchronize()
     prof = net.profile_read()
     net.profile(False)
     peaks = load_peaks()
-    top = max(prof.items(), key=lambda kv: kv[1]["ms"])
-    tname, tv = top
+    net_ms = sum(v["ms"] for v in prof.values())
+    tname, tv = max(prof.items(), key=lambda kv: kv[1]["ms"])
     tf = tv["flops"] / (tv["ms"] * 1e-3) / 1e12 if tv["ms"] > 0 else 0.0
+    # DRAM bytes of that launch shape from the committed `ncu --set full` capture (profiles/README.md); only valid for the default config
+    traffic = None
+    if tname == "conv3x3_scale0" and args.batch == 4:
+        traffic = NCU_CONV_S0_DRAM_BYTES_PER_LAUNCH
     roofline = {
-        "kernel": tname, "bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"],
-        "traffic": None, "peak_source": peaks["source"], "launches": tv["launches"], "avg_launch_ms": tv["ms"] / max(1, tv["launches"]),
-        "algorithmic_flops_per_launch": tv["flops"] / max(1, tv["launches"]),
+        "kernel": f"umma_pair_kernel[{tname}]" if args.precision else f"conv2d_simt_kernel[{tname}]", "bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"],
+        "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"], "traffic": traffic, "peak_source": peaks["source"],
+        "arithmetic": "bf16x3 split (3 tcgen05 MMAs per algorithmic MAC): attainable = peak/3" if args.precision else "fp32 FMA (no tensor cores)",
+        "frac_of_attainable": (3.0 if args.precision else 1.0) * tf / peaks["bf16_tflops"],
+        "launches": tv["launches"], "avg_launch_ms": tv["ms"] / max(1, tv["launches"]),
+        "algorithmic_flops_per_launch": tv["flops"] / max(1, tv["launches"]), "algorithmic_bytes_per_launch": tv["bytes"] / max(1, tv["launches"]),
         "hbm_view": {"achieved_gbs": tv["bytes"] / (tv["ms"] * 1e-3) / 1e9 if tv["ms"] > 0 else 0.0, "peak_gbs": peaks["hbm_gbs"]},
-        "share_of_net_time": tv["ms"] / max(1e-9, sum(v["ms"] for v in prof.values())),
-        "by_category_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
+        "share_of_net_time": tv["ms"] / max(1e-9, net_ms), "net_ms_per_step": net_ms,
+        "by_category_ms": {k: round(v["ms"], 3) for k, v in prof.items() if v["launches"]},
+        "by_category_tflops": {k: round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1) for k, v in prof.items() if v["ms"] > 0 and v["flops"] > 0},
     }
 
     if rank != 0:
