@@ -93,8 +93,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
                                                                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                                                                     const UmmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // 1024-byte alignment for SWIZZLE_128B tiles
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment for SWIZZLE_128B tiles.  The offset is applied to the __shared__ array itself (not through an integer
+  // round trip) so every derived pointer keeps the shared address space: LDS/STS instead of generic LD/ST in the epilogue.
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full_bar = empty_bar + p.stages;  // [2]
@@ -238,9 +239,10 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
     const int half = (warp - 2) >> 2;
     const int m = q * 32 + lane;
     const int ncol = (p.mode == 0) ? p.n_tile : p.n_c;  // columns of ONE logical output group
-    const int nchunks = ncol / 16;
+    // GEMM: 16-column groups; conv modes: 8-column groups (n_c = 48 splits 24/24 between the two warps of a quadrant)
+    const int cw = (p.mode == 0) ? 16 : 8;
+    const int nchunks = ncol / cw;
     const int ch_begin = half ? (nchunks + 1) / 2 : 0, ch_end = half ? nchunks : (nchunks + 1) / 2;
-    const bool st_on = !(p.dbg & 2);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -305,17 +307,16 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
             for (int j = 0; j < 16; ++j) split_store2(x[j], oh[j], ol[j]);
             uint4* dh = reinterpret_cast<uint4*>(p.out_hi + o);
             uint4* dl = reinterpret_cast<uint4*>(p.out_lo + o);
-            if (st_on || x[0] == 1.2345e30f) {
-              dh[0] = reinterpret_cast<const uint4*>(oh)[0];
-              dh[1] = reinterpret_cast<const uint4*>(oh)[1];
-              dl[0] = reinterpret_cast<const uint4*>(ol)[0];
-              dl[1] = reinterpret_cast<const uint4*>(ol)[1];
-            }
+            dh[0] = reinterpret_cast<const uint4*>(oh)[0];
+            dh[1] = reinterpret_cast<const uint4*>(oh)[1];
+            dl[0] = reinterpret_cast<const uint4*>(ol)[0];
+            dl[1] = reinterpret_cast<const uint4*>(ol)[1];
           }
         }
       } else if (p.mode == 2) {
         // ConvTranspose2d k2 s2: column (dy*2+dx)*n_c + co of lane m is the output pixel (2t+dy, 2(f0+m)+dx) of channel co;
         // then BN + ReLU, times the skip tensor (uvr_lib_v5/mdxnet.py:111-112).  The two dx values are stored as one 4-byte pair.
+        constexpr int CW = 8;
         const int nc = p.n_c;
         const int f = f0 + m;
         const bool row_ok = f < p.F;
@@ -324,17 +325,17 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
         for (int dy = 0; dy < 2; ++dy) {
           const size_t base = ((size_t)b * p.Cout + n0) * plane + (size_t)(2 * t + dy) * F2 + 2 * f;
           for (int ch = ch_begin; ch < ch_end; ++ch) {
-            const int c0 = ch * 16;
-            uint32_t v0[16], v1[16];
-            ptx::tmem_ld16(trow + (uint32_t)((dy * 2 + 0) * nc + c0), v0);
-            ptx::tmem_ld16(trow + (uint32_t)((dy * 2 + 1) * nc + c0), v1);
+            const int c0 = ch * CW;
+            uint32_t v0[CW], v1[CW];
+            ptx::tmem_ld8(trow + (uint32_t)((dy * 2 + 0) * nc + c0), v0);
+            ptx::tmem_ld8(trow + (uint32_t)((dy * 2 + 1) * nc + c0), v1);
             ptx::tmem_ld_wait();
             if (row_ok) {
               const size_t o0 = base + (size_t)c0 * plane;
-              // all skip loads of this 16-channel group are issued before any store (read-only path)
-              uint32_t sk_h[16], sk_l[16];
+              // all skip loads of this group are issued before any store (read-only path)
+              uint32_t sk_h[CW], sk_l[CW];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
+              for (int j = 0; j < CW; ++j) {
                 sk_h[j] = 0x3f803f80u;  // bf16 (1.0, 1.0)
                 sk_l[j] = 0u;
                 if (p.res_hi && !(p.dbg & 1)) {
@@ -342,9 +343,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
                   sk_l[j] = __ldg(reinterpret_cast<const unsigned int*>(p.res_lo + o0 + (size_t)j * plane));
                 }
               }
-              float scv[16], shv[16];
+              float scv[CW], shv[CW];
 #pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
+              for (int j4 = 0; j4 < CW / 4; ++j4) {
                 const float4 s4 = *reinterpret_cast<const float4*>(&sc_s[n0 + c0 + 4 * j4]);
                 const float4 h4 = *reinterpret_cast<const float4*>(&sh_s[n0 + c0 + 4 * j4]);
                 scv[4 * j4] = s4.x; scv[4 * j4 + 1] = s4.y; scv[4 * j4 + 2] = s4.z; scv[4 * j4 + 3] = s4.w;
@@ -353,9 +354,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
               bf16* ph = p.out_hi + o0;
               bf16* pl = p.out_lo + o0;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float sc = scv[j], sh = shv[j];
-                float x0 = fmaf(__uint_as_float(v0[j]), sc, sh), x1 = fmaf(__uint_as_float(v1[j]), sc, sh);
+              for (int j = 0; j < CW; ++j) {
+                float x0 = fmaf(__uint_as_float(v0[j]), scv[j], shv[j]), x1 = fmaf(__uint_as_float(v1[j]), scv[j], shv[j]);
                 if (p.relu) {
                   x0 = fmaxf(x0, 0.f);
                   x1 = fmaxf(x1, 0.f);
@@ -366,10 +366,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
                 __nv_bfloat162 oh, ol;
                 split_store2(x0, oh.x, ol.x);
                 split_store2(x1, oh.y, ol.y);
-                if (st_on || x0 == 1.2345e30f) {
-                  *reinterpret_cast<__nv_bfloat162*>(ph) = oh;  // 32 lanes -> 128 contiguous bytes
-                  *reinterpret_cast<__nv_bfloat162*>(pl) = ol;
-                }
+                *reinterpret_cast<__nv_bfloat162*>(ph) = oh;  // 32 lanes -> 128 contiguous bytes
+                *reinterpret_cast<__nv_bfloat162*>(pl) = ol;
                 ph += plane;
                 pl += plane;
               }
@@ -379,23 +377,24 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
       } else if (p.mode == 3) {
         // Conv2d k2 s2: P_dx[m] (column dx*n_c + co) is the partial sum over (ci, dy) at INPUT pixel f0+m;
         // out[(f0+m)/2] = P_0[m] + P_1[m+1] for even m (odd rows of P_0 / even rows of P_1 are computed but unused).
+        constexpr int CW = 8;
         const int nc = p.n_c;
         const int fo = (f0 + m) >> 1, Fo = p.F >> 1, To = p.T >> 1;
         const bool row_ok = ((m & 1) == 0) && fo < Fo;
         const size_t plane = (size_t)To * Fo;
         const size_t base = ((size_t)b * p.Cout + n0) * plane + (size_t)t * Fo + fo;
         for (int ch = ch_begin; ch < ch_end; ++ch) {
-          const int c0 = ch * 16;
-          uint32_t v0[16], v1[16];
-          ptx::tmem_ld16(trow + (uint32_t)c0, v0);
-          ptx::tmem_ld16(trow + (uint32_t)(nc + c0), v1);
+          const int c0 = ch * CW;
+          uint32_t v0[CW], v1[CW];
+          ptx::tmem_ld8(trow + (uint32_t)c0, v0);
+          ptx::tmem_ld8(trow + (uint32_t)(nc + c0), v1);
           ptx::tmem_ld_wait();
-          float x[16];
+          float x[CW];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v0[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(v1[j]), 1);  // + P_1 of row m+1
-          float sc[16], sh[16];
+          for (int j = 0; j < CW; ++j) x[j] = __uint_as_float(v0[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(v1[j]), 1);  // + P_1 of row m+1
+          float sc[CW], sh[CW];
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
+          for (int j4 = 0; j4 < CW / 4; ++j4) {
             const float4 s4 = *reinterpret_cast<const float4*>(&sc_s[n0 + c0 + 4 * j4]);
             const float4 h4 = *reinterpret_cast<const float4*>(&sh_s[n0 + c0 + 4 * j4]);
             sc[4 * j4] = s4.x; sc[4 * j4 + 1] = s4.y; sc[4 * j4 + 2] = s4.z; sc[4 * j4 + 3] = s4.w;
@@ -405,37 +404,38 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
             bf16* ph = p.out_hi + base + (size_t)c0 * plane;
             bf16* pl = p.out_lo + base + (size_t)c0 * plane;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < CW; ++j) {
               float y = fmaf(x[j], sc[j], sh[j]);
               if (p.relu) y = fmaxf(y, 0.f);
               bf16 h, l;
               split_store2(y, h, l);
-              if (st_on || y == 1.2345e30f) {
-                ph[(size_t)j * plane] = h;
-                pl[(size_t)j * plane] = l;
-              }
+              *ph = h;
+              *pl = l;
+              ph += plane;
+              pl += plane;
             }
           }
         }
       } else {
         // 3x3: P_dx[m][co] sits in column dx*n_c + co of TMEM lane m.  out[f0+j] = P_0[j-1] + P_1[j] + P_2[j+1].
+        constexpr int CW = 8;
         const int nc = p.n_c;
         float* edge = edge_base + acc * 8 * nc;
         float* edge0 = edge + q * nc;        // this warp's row 32q+31 of P_0 (needed by lane 0 of quadrant q+1)
         float* edge2 = edge + (4 + q) * nc;  // this warp's row 32q    of P_2 (needed by lane 31 of quadrant q-1)
         for (int ch = ch_begin; ch < ch_end; ++ch) {
-          const int c0 = ch * 16;
-          uint32_t v0[16], v2[16];
-          ptx::tmem_ld16(trow + (uint32_t)c0, v0);
-          ptx::tmem_ld16(trow + (uint32_t)(2 * nc + c0), v2);
+          const int c0 = ch * CW;
+          uint32_t v0[CW], v2[CW];
+          ptx::tmem_ld8(trow + (uint32_t)c0, v0);
+          ptx::tmem_ld8(trow + (uint32_t)(2 * nc + c0), v2);
           ptx::tmem_ld_wait();
           if (lane == 31) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) edge0[c0 + j] = __uint_as_float(v0[j]);
+            for (int j = 0; j < CW; ++j) edge0[c0 + j] = __uint_as_float(v0[j]);
           }
           if (lane == 0) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) edge2[c0 + j] = __uint_as_float(v2[j]);
+            for (int j = 0; j < CW; ++j) edge2[c0 + j] = __uint_as_float(v2[j]);
           }
         }
         // the four warps that own this column half exchange their boundary rows (named barrier 1 or 2, 128 threads)
@@ -448,33 +448,33 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
         const size_t plane = (size_t)p.T * p.F;
         const size_t base = ((size_t)b * p.Cout + n0) * plane + (size_t)t * p.F + f;
         for (int ch = ch_begin; ch < ch_end; ++ch) {
-          const int c0 = ch * 16;
-          uint32_t v0[16], v1[16], v2[16];
-          ptx::tmem_ld16(trow + (uint32_t)c0, v0);
-          ptx::tmem_ld16(trow + (uint32_t)(nc + c0), v1);
-          ptx::tmem_ld16(trow + (uint32_t)(2 * nc + c0), v2);
+          const int c0 = ch * CW;
+          uint32_t v0[CW], v1[CW], v2[CW];
+          ptx::tmem_ld8(trow + (uint32_t)c0, v0);
+          ptx::tmem_ld8(trow + (uint32_t)(nc + c0), v1);
+          ptx::tmem_ld8(trow + (uint32_t)(2 * nc + c0), v2);
           ptx::tmem_ld_wait();
-          float x[16];
+          float x[CW];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < CW; ++j) {
             const float a = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[j]), 1);    // P_0 of row m-1
             const float c = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[j]), 1);  // P_2 of row m+1
             x[j] = __uint_as_float(v1[j]) + ((lane == 0) ? 0.f : a) + ((lane == 31) ? 0.f : c);
           }
-          // rows at a warp edge take their neighbour from the exchange buffer (one divergent region per 16 columns);
+          // rows at a warp edge take their neighbour from the exchange buffer (one divergent region per group);
           // m == 0 with f0 == 0 is the left zero padding, m == 0 otherwise and m == 127 are never output rows
           if (lane == 0 && q > 0) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) x[j] += left[c0 + j];
+            for (int j = 0; j < CW; ++j) x[j] += left[c0 + j];
           }
           if (lane == 31 && q < 3) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) x[j] += right[c0 + j];
+            for (int j = 0; j < CW; ++j) x[j] += right[c0 + j];
           }
-          // per-channel affine: read all 32 coefficients before the first global store (vector LDS, no per-column stall)
-          float sc[16], sh[16];
+          // per-channel affine: read the coefficients before the first global store (vector LDS, no per-column stall)
+          float sc[CW], sh[CW];
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
+          for (int j4 = 0; j4 < CW / 4; ++j4) {
             const float4 s4 = *reinterpret_cast<const float4*>(&sc_s[n0 + c0 + 4 * j4]);
             const float4 h4 = *reinterpret_cast<const float4*>(&sh_s[n0 + c0 + 4 * j4]);
             sc[4 * j4] = s4.x; sc[4 * j4 + 1] = s4.y; sc[4 * j4 + 2] = s4.z; sc[4 * j4 + 3] = s4.w;
@@ -484,15 +484,15 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
             bf16* ph = p.out_hi + base + (size_t)c0 * plane;
             bf16* pl = p.out_lo + base + (size_t)c0 * plane;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < CW; ++j) {
               float y = fmaf(x[j], sc[j], sh[j]);
               if (p.relu) y = fmaxf(y, 0.f);
               bf16 h, l;
               split_store2(y, h, l);
-              if (st_on || y == 1.2345e30f) {
-                ph[(size_t)j * plane] = h;  // 32 lanes -> 32 consecutive pixels: one 64-byte segment per plane
-                pl[(size_t)j * plane] = l;
-              }
+              *ph = h;  // 32 lanes -> 32 consecutive pixels: one 64-byte segment per plane
+              *pl = l;
+              ph += plane;
+              pl += plane;
             }
           }
         }
