@@ -167,6 +167,40 @@ int b200sep_mdx_run_model(const b200sep_stft_plan* plan, b200sep_mdxnet* net, co
                           float* wave_out, float* work, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * TFC_TDF_net (MDX23C; uvr_lib_v5/tfc_tdf_v3.py:151-267).  Replaces `self.model_run(batch)` of the non-Roformer MDXC branch
+ * (architectures/mdxc_separator.py:390) between its two STFTs.  Only norm = InstanceNorm (affine), act = gelu, scale = [2, 2]
+ * (the MDX23C-8KFFT-InstVoc_HQ configuration).  Parameters in the reference module's state_dict order.
+ */
+typedef struct b200sep_tfcnet b200sep_tfcnet;
+typedef struct {
+  int32_t dim_f;          /* audio.dim_f (4096) */
+  int32_t dim_t;          /* frames per chunk (inference.dim_t, 256) */
+  int32_t num_subbands;   /* model.num_subbands (4) */
+  int32_t audio_channels; /* audio.num_channels (2) */
+  int32_t num_scales;     /* 5 */
+  int32_t l;              /* num_blocks_per_scale (2) */
+  int32_t c;              /* model.num_channels (128) */
+  int32_t g;              /* growth (128) */
+  int32_t bn;             /* bottleneck_factor (4) */
+  int32_t num_targets;    /* 1 if training.target_instrument else len(training.instruments) */
+  int32_t max_batch;
+} b200sep_tfcnet_config;
+int64_t b200sep_tfcnet_param_count(const b200sep_tfcnet_config* cfg);
+int b200sep_tfcnet_create(b200sep_tfcnet** net, const b200sep_tfcnet_config* cfg, const float* params_host, int64_t n_params);
+void b200sep_tfcnet_destroy(b200sep_tfcnet* net);
+int64_t b200sep_tfcnet_device_bytes(const b200sep_tfcnet* net);
+/* spec_in (B, 4, dim_t, dim_f) float32 [layout CTF] -> spec_out (B * num_targets, 4, dim_t, dim_f) [CTF] */
+int b200sep_tfcnet_forward(b200sep_tfcnet* net, const float* spec_in, float* spec_out, int batch, void* stream);
+
+/*
+ * Rectangular overlap-add of the MDXC branch (architectures/mdxc_separator.py:395-402): chunks (n_chunks, channels, chunk_len)
+ * placed every `hop` samples are summed, the slice [front, front + n_out) is taken and divided by `divisor` (= overlap).
+ * out: (channels, n_out).
+ */
+int b200sep_rect_overlap_add(const float* chunks, int n_chunks, int channels, int chunk_len, int64_t hop, int64_t front, int64_t n_out,
+                             float divisor, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Self-tests of the tensor-core ("bf16x3 pair") operators in isolation: fp32 device tensors in, the operator runs
  * exactly as inside the network (split into bf16 hi/lo planes -> tcgen05 kernel -> join), fp32 out.  Synchronous.
  *   gemm   : out[M][N] = act((a[M][K] @ w[N][K]^T) * scale[c] + shift[c]) (+ res),  c = (row / rows_per_channel) % channels

@@ -55,7 +55,12 @@ def install():
         def __init__(self, *a, **k):
             pass
 
-    for name in ("librosa", "soundfile", "audioread", "onnx", "onnxruntime", "onnx2torch", "julius", "ml_collections", "samplerate", "resampy"):
+    if "ml_collections" not in sys.modules:
+        class _ConfigDict(dict):
+            __getattr__ = dict.__getitem__
+
+        _stub("ml_collections", ConfigDict=_ConfigDict)
+    for name in ("librosa", "soundfile", "audioread", "onnx", "onnxruntime", "onnx2torch", "julius", "samplerate", "resampy"):
         if name not in sys.modules:
             try:
                 importlib.import_module(name)

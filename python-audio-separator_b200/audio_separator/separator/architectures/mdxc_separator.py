@@ -1,0 +1,88 @@
+"""B200 MDXC architecture plugin (non-Roformer TFC_TDF_net models, e.g. MDX23C-8KFFT-InstVoc_HQ).
+
+Plugin contract of the reference's MDXCSeparator (audio_separator/separator/architectures/mdxc_separator.py:19-228):
+ctor `(common_config, arch_config)` with arch keys segment_size / override_model_segment_size / batch_size / overlap /
+pitch_shift, `separate(path, custom_output_names)`, `demix(mix) -> {instrument: (2, N)}`.  The chunk loop runs on the GPU
+through libb200sep.so (MdxcEngine).  Roformer checkpoints and pitch shifting are not part of this path.
+"""
+import os
+
+import numpy as np
+import torch
+
+from ..b200.engine import MdxcEngine, TfcNet
+from ..common_separator import CommonSeparator, normalize
+
+
+class MDXCSeparator(CommonSeparator):
+    def __init__(self, common_config, arch_config):
+        super().__init__(config=common_config)
+        self.model_data_cfgdict = self.model_data  # the model's YAML as a dict (mdxc_separator.py:60)
+        self.segment_size = arch_config.get("segment_size", 256)
+        self.override_model_segment_size = arch_config.get("override_model_segment_size", False)
+        self.overlap = arch_config.get("overlap", 8)
+        self.batch_size = arch_config.get("batch_size", 1)
+        self.pitch_shift = arch_config.get("pitch_shift", 0)
+        if self.is_roformer_model:
+            raise NotImplementedError("Roformer checkpoints are outside the accelerated MDXC path (SURVEY.md section 8f)")
+        if self.pitch_shift:
+            raise NotImplementedError("pitch_shift is not part of the accelerated path")
+        if not torch.cuda.is_available():
+            raise RuntimeError("MDXCSeparator (B200 build) needs a CUDA device: there is no CPU path in this package")
+        self.torch_device = torch.device("cuda", torch.cuda.current_device())
+        self.is_primary_stem_main_target = False
+        self.load_model()
+
+    def load_model(self):
+        """Replaces TFC_TDF_net(config).load_state_dict(torch.load(ckpt)) (mdxc_separator.py:76-116)."""
+        cfg = self.model_data_cfgdict
+        audio, model, training = cfg["audio"], cfg["model"], cfg["training"]
+        if model.get("norm") != "InstanceNorm" or model.get("act", "gelu") != "gelu" or list(model.get("scale", [2, 2])) != [2, 2]:
+            raise ValueError("the B200 TFC_TDF_net supports norm=InstanceNorm, act=gelu, scale=[2,2] (the MDX23C configuration)")
+        path = self.model_path
+        if path.lower().endswith(".npz"):
+            with np.load(path) as z:
+                state = {k: z[k] for k in z.files}
+        else:
+            sd = torch.load(path, map_location="cpu", weights_only=True)
+            state = {k: v.float().numpy() for k, v in (sd.get("state_dict", sd)).items()}
+        dim_t = self.segment_size if self.override_model_segment_size else cfg["inference"]["dim_t"]  # :355-360
+        targets = 1 if training.get("target_instrument") else len(training["instruments"])
+        self.net = TfcNet(state, audio["dim_f"], dim_t, model["num_subbands"], audio.get("num_channels", 2), model["num_scales"], model["num_blocks_per_scale"],
+                          model["num_channels"], model["growth"], model["bottleneck_factor"], targets, max_batch=max(1, int(self.batch_size)))
+        self.engine = MdxcEngine(self.net, audio["n_fft"], audio["hop_length"], audio["dim_f"], dim_t, self.overlap)
+        self.model_run = self.engine.model_run
+
+    def demix(self, mix):
+        """(2, N) ndarray -> {instrument: (2, N) ndarray} (mdxc_separator.py:406-434) or the single target's array."""
+        out = self.engine.demix_device(torch.as_tensor(np.ascontiguousarray(mix, dtype=np.float32)).to(self.torch_device)).cpu().numpy()
+        training = self.model_data_cfgdict["training"]
+        if self.net.num_targets > 1:
+            return {k: v for k, v in zip(training["instruments"], out)}
+        return out[0]
+
+    def separate(self, audio_file_path, custom_output_names=None):
+        self.audio_file_path = audio_file_path
+        self.audio_file_base = os.path.splitext(os.path.basename(audio_file_path))[0]
+        mix = self.prepare_mix(self.audio_file_path)
+        mix = normalize(wave=np.array(mix, dtype=np.float32), max_peak=self.normalization_threshold, min_peak=self.amplification_threshold)  # :149
+        source = self.demix(mix)
+        output_files = []
+        if isinstance(source, dict):  # multi-stem models: one file per instrument (:186-214)
+            for stem_name, stem_source in source.items():
+                if self.output_single_stem and self.output_single_stem.lower() != stem_name.lower():
+                    continue
+                path = self.get_stem_output_path(stem_name, custom_output_names)
+                stem = normalize(wave=stem_source, max_peak=self.normalization_threshold, min_peak=self.amplification_threshold).T
+                self.final_process(path, stem, stem_name)
+                output_files.append(path)
+            return output_files
+        self.primary_source = normalize(wave=source, max_peak=self.normalization_threshold, min_peak=self.amplification_threshold).T  # :160-182
+        self.secondary_source = mix.T - source.T
+        for name, src in ((self.secondary_stem_name, self.secondary_source), (self.primary_stem_name, self.primary_source)):
+            if self.output_single_stem and self.output_single_stem.lower() != name.lower():
+                continue
+            path = self.get_stem_output_path(name, custom_output_names)
+            self.final_process(path, src, name)
+            output_files.append(path)
+        return output_files

@@ -26,6 +26,10 @@ class MdxNetConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("dim_c", "dim_f", "dim_t", "num_blocks", "l", "g", "k", "bn", "max_batch", "precision")]
 
 
+class TfcNetConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("dim_f", "dim_t", "num_subbands", "audio_channels", "num_scales", "l", "c", "g", "bn", "num_targets", "max_batch")]
+
+
 _SIGS = {
     "b200sep_abi_version": (i32, []),
     "b200sep_last_error": (C.c_char_p, []),
@@ -48,6 +52,12 @@ _SIGS = {
     "b200sep_mdxnet_profile_enable": (i32, [vp, i32]),
     "b200sep_mdxnet_profile_read": (i32, [vp, i32, vp, vp, vp, vp]),
     "b200sep_mdxnet_profile_name": (C.c_char_p, [i32]),
+    "b200sep_tfcnet_param_count": (i64, [C.POINTER(TfcNetConfig)]),
+    "b200sep_tfcnet_create": (i32, [C.POINTER(vp), C.POINTER(TfcNetConfig), vp, i64]),
+    "b200sep_tfcnet_destroy": (None, [vp]),
+    "b200sep_tfcnet_device_bytes": (i64, [vp]),
+    "b200sep_tfcnet_forward": (i32, [vp, vp, vp, i32, vp]),
+    "b200sep_rect_overlap_add": (i32, [vp, i32, i32, i32, i64, i64, i64, f32, vp, vp]),
     "b200sep_selftest_umma_gemm": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, vp]),
     "b200sep_selftest_umma_conv3x3": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, vp]),
     "b200sep_selftest_umma_updown": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp]),

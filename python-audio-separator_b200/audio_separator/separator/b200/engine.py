@@ -244,3 +244,148 @@ class MdxEngine:
         out = torch.empty(n, dtype=torch.int16, device=self.device)
         check(lib.b200sep_to_pcm16(_ptr(norm), n, _ptr(out), _stream()), "to_pcm16")
         return out
+
+
+# =========================================================================================================
+# MDXC (MDX23C / TFC_TDF_net) -- architectures/mdxc_separator.py non-Roformer branch
+def tfcnet_param_names(dim_f, num_subbands, audio_channels, num_scales, l, c, g, bn, num_targets):
+    """Ordered (name, shape) of TFC_TDF_net's state_dict (uvr_lib_v5/tfc_tdf_v3.py:110-214)."""
+    out = []
+    dim_c = num_subbands * audio_channels * 2
+    f = dim_f // num_subbands
+
+    def norm(prefix, ch):
+        out.append((f"{prefix}.weight", (ch,)))
+        out.append((f"{prefix}.bias", (ch,)))
+
+    def block(prefix, in_c, ch, ff):
+        for i in range(l):
+            b = f"{prefix}.blocks.{i}"
+            norm(f"{b}.tfc1.0", in_c)
+            out.append((f"{b}.tfc1.2.weight", (ch, in_c, 3, 3)))
+            norm(f"{b}.tdf.0", ch)
+            out.append((f"{b}.tdf.2.weight", (ff // bn, ff)))
+            norm(f"{b}.tdf.3", ch)
+            out.append((f"{b}.tdf.5.weight", (ff, ff // bn)))
+            norm(f"{b}.tfc2.0", ch)
+            out.append((f"{b}.tfc2.2.weight", (ch, ch, 3, 3)))
+            out.append((f"{b}.shortcut.weight", (ch, in_c, 1, 1)))
+            in_c = ch
+
+    out.append(("first_conv.weight", (c, dim_c, 1, 1)))
+    ch = c
+    for i in range(num_scales):
+        block(f"encoder_blocks.{i}.tfc_tdf", ch, ch, f)
+        norm(f"encoder_blocks.{i}.downscale.conv.0", ch)
+        out.append((f"encoder_blocks.{i}.downscale.conv.2.weight", (ch + g, ch, 2, 2)))
+        f //= 2
+        ch += g
+    block("bottleneck_block", ch, ch, f)
+    for i in range(num_scales):
+        norm(f"decoder_blocks.{i}.upscale.conv.0", ch)
+        out.append((f"decoder_blocks.{i}.upscale.conv.2.weight", (ch, ch - g, 2, 2)))
+        f *= 2
+        ch -= g
+        block(f"decoder_blocks.{i}.tfc_tdf", 2 * ch, ch, f)
+    out.append(("final_conv.0.weight", (ch, ch + dim_c, 1, 1)))
+    out.append(("final_conv.2.weight", (num_targets * dim_c, ch, 1, 1)))
+    return out
+
+
+class TfcNet:
+    """b200sep_tfcnet handle (TFC_TDF_net weights + arena).  `state`: name -> array in the reference's state_dict naming."""
+
+    def __init__(self, state: dict, dim_f, dim_t, num_subbands=4, audio_channels=2, num_scales=5, l=2, c=128, g=128, bn=4, num_targets=2, max_batch=1):
+        _require_cuda()
+        names = tfcnet_param_names(dim_f, num_subbands, audio_channels, num_scales, l, c, g, bn, num_targets)
+        parts = []
+        for name, shape in names:
+            a = np.asarray(state[name], dtype=np.float32)
+            if tuple(a.shape) != tuple(shape):
+                raise ValueError(f"parameter {name}: expected shape {shape}, got {a.shape}")
+            parts.append(a.reshape(-1))
+        flat = np.ascontiguousarray(np.concatenate(parts))
+        self.cfg = _lib.TfcNetConfig(dim_f, dim_t, num_subbands, audio_channels, num_scales, l, c, g, bn, num_targets, max_batch)
+        expect = lib.b200sep_tfcnet_param_count(C.byref(self.cfg))
+        if expect != flat.size:
+            raise ValueError(f"TFC_TDF_net config expects {expect} parameters, state has {flat.size}")
+        h = C.c_void_p()
+        check(lib.b200sep_tfcnet_create(C.byref(h), C.byref(self.cfg), flat.ctypes.data_as(C.c_void_p), flat.size), "tfcnet_create")
+        self.handle = h
+        self.max_batch, self.dim_f, self.dim_t, self.num_targets = max_batch, dim_f, dim_t, num_targets
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h and lib is not None:
+            lib.b200sep_tfcnet_destroy(h)
+            self.handle = None
+
+    @property
+    def device_bytes(self) -> int:
+        return int(lib.b200sep_tfcnet_device_bytes(self.handle))
+
+    def forward_spec(self, spec: torch.Tensor) -> torch.Tensor:
+        """spec (B,4,dim_t,dim_f) float32 CUDA [layout CTF] -> (B, S, 4, dim_t, dim_f)."""
+        spec = spec.contiguous()
+        assert tuple(spec.shape[1:]) == (4, self.dim_t, self.dim_f) and spec.dtype == torch.float32, spec.shape
+        B = spec.shape[0]
+        out = torch.empty((B, self.num_targets, 4, self.dim_t, self.dim_f), dtype=torch.float32, device=spec.device)
+        for b0 in range(0, B, self.max_batch):
+            nb = min(self.max_batch, B - b0)
+            check(lib.b200sep_tfcnet_forward(self.handle, _ptr(spec[b0 : b0 + nb]), _ptr(out[b0 : b0 + nb]), nb, _stream()), "tfcnet_forward")
+        return out
+
+
+class MdxcEngine:
+    """Device-resident MDXCSeparator.demix, non-Roformer branch (mdxc_separator.py:345-404): unfold -> batches ->
+    STFT -> TFC_TDF_net -> iSTFT -> rectangular overlap-add / overlap."""
+
+    def __init__(self, net: TfcNet, n_fft, hop_length, dim_f, dim_t, overlap):
+        _require_cuda()
+        self.net, self.n_fft, self.hop, self.dim_f, self.dim_t, self.overlap = net, int(n_fft), int(hop_length), int(dim_f), int(dim_t), int(overlap)
+        self.chunk_size = self.hop * (self.dim_t - 1)  # :361
+        self.hop_size = self.chunk_size // self.overlap  # :364
+        self.plan = StftPlan(self.n_fft, self.hop)
+        self.batch = net.max_batch
+        self.device = torch.device("cuda", torch.cuda.current_device())
+
+    def grid(self, n_samples):
+        chunk, hop = self.chunk_size, self.hop_size
+        pad = hop - (n_samples - chunk) % hop  # :367
+        front = chunk - hop
+        Lp = front + n_samples + pad + front
+        return Lp, front, pad, (Lp - chunk) // hop + 1
+
+    def model_run(self, wave: torch.Tensor) -> torch.Tensor:
+        """TFC_TDF_net.forward (tfc_tdf_v3.py:230-267): (B,2,chunk) CUDA -> (B,S,2,chunk)."""
+        B, _, T = wave.shape
+        S = self.net.num_targets
+        out = torch.empty((B, S, 2, T), dtype=torch.float32, device=wave.device)
+        for b0 in range(0, B, self.batch):
+            nb = min(self.batch, B - b0)
+            spec = self.plan.forward(wave[b0 : b0 + nb], self.dim_f, 0, LAYOUT_CTF)
+            y = self.net.forward_spec(spec)  # (nb, S, 4, frames, dim_f)
+            w = self.plan.inverse(y.reshape(nb * S, 4, y.shape[-2], y.shape[-1]), LAYOUT_CTF)
+            out[b0 : b0 + nb] = w.reshape(nb, S, 2, T)
+        return out
+
+    def demix_device(self, mix_dev: torch.Tensor) -> torch.Tensor:
+        """mix (2,N) float32 CUDA -> (S, 2, N)."""
+        mix_dev = mix_dev.contiguous()
+        N = mix_dev.shape[1]
+        Lp, front, pad, n_chunks = self.grid(N)
+        T, hop, S = self.chunk_size, self.hop_size, self.net.num_targets
+        padded = torch.zeros((2, Lp), dtype=torch.float32, device=self.device)  # :371
+        padded[:, front : front + N] = mix_dev
+        chunks = torch.empty((n_chunks, S * 2, T), dtype=torch.float32, device=self.device)
+        for b0 in range(0, n_chunks, self.batch):
+            nb = min(self.batch, n_chunks - b0)
+            spec = torch.empty((nb, 4, self.dim_t, self.dim_f), dtype=torch.float32, device=self.device)
+            # chunks are read straight out of the padded mixture (mix.unfold(1, chunk, hop), :374)
+            check(lib.b200sep_stft_forward(self.plan.handle, padded.data_ptr() + b0 * hop * 4, hop, Lp, Lp - b0 * hop, nb, T, self.dim_f, 0, LAYOUT_CTF, _ptr(spec), _stream()), "stft_forward")
+            y = self.net.forward_spec(spec)
+            w = self.plan.inverse(y.reshape(nb * S, 4, self.dim_t, self.dim_f), LAYOUT_CTF)  # (nb*S, 2, T)
+            chunks[b0 : b0 + nb] = w.reshape(nb, S * 2, T)
+        out = torch.empty((S * 2, N), dtype=torch.float32, device=self.device)
+        check(lib.b200sep_rect_overlap_add(_ptr(chunks), n_chunks, S * 2, T, hop, front, N, float(self.overlap), _ptr(out), _stream()), "rect_overlap_add")  # :395-402
+        return out.reshape(S, 2, N)

@@ -49,7 +49,7 @@ class Separator:
             raise NotImplementedError("ensembles / file-level chunking are outside the B200 hot-path scope")
         self.arch_specific_params = {
             "MDX": {"hop_length": 1024, "segment_size": 256, "overlap": 0.25, "batch_size": 1, "enable_denoise": False, **(mdx_params or {})},
-            "VR": dict(vr_params or {}), "Demucs": dict(demucs_params or {}), "MDXC": dict(mdxc_params or {}),
+            "VR": dict(vr_params or {}), "Demucs": dict(demucs_params or {}), "MDXC": {"segment_size": 256, "override_model_segment_size": False, "batch_size": 1, "overlap": 8, "pitch_shift": 0, **(mdxc_params or {})},
         }
         self.torch_device = self.torch_device_cpu = torch.device("cpu")
         self.torch_device_mps = None
@@ -71,6 +71,12 @@ class Separator:
         if os.path.exists(side):
             with open(side, encoding="utf-8") as f:
                 return json.load(f)
+        for ext in (".yaml", ".yml"):  # MDXC / Demucs models carry a YAML config next to the checkpoint (separator.py:758-777)
+            if os.path.exists(os.path.splitext(model_path)[0] + ext):
+                import yaml
+
+                with open(os.path.splitext(model_path)[0] + ext, encoding="utf-8") as f:
+                    return yaml.safe_load(f)
         name = os.path.basename(model_path)
         if name in KNOWN_MODEL_DATA:
             return dict(KNOWN_MODEL_DATA[name])
@@ -84,7 +90,7 @@ class Separator:
         if not os.path.isfile(model_path):
             raise FileNotFoundError(f"{model_path} not found (this build does not download models)")
         model_data = self.load_model_data(model_path)
-        model_type = model_data.get("b200_arch") or ("MDX" if model_path.lower().endswith((".onnx", ".npz")) else None)
+        model_type = model_data.get("b200_arch") or ("MDXC" if "audio" in model_data and "model" in model_data else ("MDX" if model_path.lower().endswith((".onnx", ".npz")) else None))
         classes = {"MDX": "mdx_separator.MDXSeparator", "VR": "vr_separator.VRSeparator", "Demucs": "demucs_separator.DemucsSeparator", "MDXC": "mdxc_separator.MDXCSeparator"}
         if model_type not in classes:
             raise ValueError(f"Model type not supported (yet): {model_type}")

@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(GEMM_NT) gemm_tn_simt_kernel(GemmParams p) {
     const int r = m0 + ty * 8 + i;
     if (r >= p.M) continue;
     const int c = (r / p.rows_per_channel) % p.channels;
-    const float sc = __ldg(&p.scale[c]), sh = __ldg(&p.shift[c]);
+    const float sc = p.scale ? __ldg(&p.scale[c]) : 1.f, sh = p.shift ? __ldg(&p.shift[c]) : 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int n = n0 + tx * 8 + j;

@@ -302,6 +302,22 @@ __global__ void demix_ola_kernel(const float* __restrict__ chunks, int first_chu
   }
 }
 
+// MDX23C accumulation (mdxc_separator.py:395-402): rectangular overlap-add of full-length chunks placed every `hop`,
+// slice [front, front + n_out), divide by the constant `overlap`.  chunks: (n_chunks, C, chunk); out: (C, n_out).
+__global__ void rect_ola_kernel(const float* __restrict__ chunks, int n_chunks, int C, int chunk_len, int64_t hop, int64_t front, int64_t n_out,
+                                float divisor, float* __restrict__ out) {
+  const int c = blockIdx.y;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_out; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = q + front;
+    int64_t i_hi = p / hop;
+    if (i_hi > n_chunks - 1) i_hi = n_chunks - 1;
+    int64_t i_lo = (p - chunk_len + 1 <= 0) ? 0 : (p - chunk_len + hop) / hop;
+    float acc = 0.f;
+    for (int64_t i = i_lo; i <= i_hi; ++i) acc += __ldg(&chunks[((int64_t)i * C + c) * chunk_len + (p - i * hop)]);
+    out[(int64_t)c * n_out + q] = acc / divisor;
+  }
+}
+
 __global__ void absmax_kernel(const float* __restrict__ x, int64_t n, unsigned int* result_bits) {
   float m = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
@@ -465,6 +481,18 @@ extern "C" int b200sep_demix_overlap_add(const float* chunks, int n_chunks, int 
   const int blocks = (int)std::min<int64_t>(cdiv(n_out, 256), kNumSMs * 16);
   demix_ola_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(chunks, 0, n_chunks, chunk_len, step, total_len, trim, n_out, 0, n_out, use_window, out_scale,
                                                              mix, compensate, interleave, primary, secondary);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
+extern "C" int b200sep_rect_overlap_add(const float* chunks, int n_chunks, int channels, int chunk_len, int64_t hop, int64_t front, int64_t n_out,
+                                        float divisor, float* out, void* stream) {
+  B2_CHECK_ARG(chunks && out && n_chunks >= 1 && channels >= 1 && chunk_len >= 1 && hop >= 1 && front >= 0 && n_out >= 0 && divisor != 0.f,
+               "rect_overlap_add: bad argument");
+  B2_CHECK_ARG(front + n_out <= (int64_t)(n_chunks - 1) * hop + chunk_len, "rect_overlap_add: output range exceeds the chunk grid");
+  if (n_out == 0) return B200SEP_OK;
+  dim3 grid((unsigned)std::min<int64_t>(cdiv(n_out, 256), kNumSMs * 8), channels);
+  rect_ola_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(chunks, n_chunks, channels, chunk_len, hop, front, n_out, divisor, out);
   B2_LAUNCHED();
   return B200SEP_OK;
 }

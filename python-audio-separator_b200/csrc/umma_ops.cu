@@ -37,7 +37,7 @@ constexpr int kTileM = 128;
 constexpr int kConvStride = 120;  // output pixels per conv tile (multiple of 8: TMA box starts must be 16-byte aligned)
 
 struct UmmaParams {
-  int mode;  // 0 GEMM, 1 CONV3x3, 2 UP (ConvTranspose2d k2 s2), 3 DOWN (Conv2d k2 s2)
+  int mode;  // 0 GEMM, 1 CONV3x3, 2 UP (ConvTranspose2d k2 s2), 3 DOWN (Conv2d k2 s2), 4 PW (Conv2d 1x1)
   int f_stride, t_mul, t_off;  // implicit-GEMM addressing: tile f0 = blockIdx.x*f_stride, input row = t*t_mul + r + t_off
   int n_tile, n_total, tmem_cols;
   int num_iters, ksteps, stages;
@@ -53,12 +53,22 @@ struct UmmaParams {
   // epilogue
   const float* scale;
   const float* shift;
-  int relu;
+  int act;  // 0 none, 1 ReLU, 2 GELU (erf)
   bf16* out_hi;
   bf16* out_lo;
-  const bf16* res_hi;  // GEMM: residual added after the activation.  UP: skip tensor multiplied after the activation.
+  float* out_f32;      // PW only: write plain fp32 instead of a pair
+  const bf16* res_hi;  // GEMM / CONV3x3 / PW: residual (output-shaped, own channel count) ADDED after the activation.  UP: skip tensor MULTIPLIED.
   const bf16* res_lo;
+  const bf16* mul_hi;  // CONV3x3 / PW: output-shaped tensor multiplied last
+  const bf16* mul_lo;
+  int out_c_total, out_c_off;  // conv modes: the output occupies channels [out_c_off, out_c_off + Cout) of a (B, out_c_total, T', F') tensor
 };
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == 1) return fmaxf(x, 0.f);
+  if (act == 2) return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));  // nn.GELU() default (exact erf form)
+  return x;
+}
 
 __device__ __forceinline__ void split_store2(float v, bf16& hi, bf16& lo) {
   hi = __float2bfloat16_rn(v);
@@ -127,8 +137,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
   if (warp == 1) ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   if (p.mode != 0) {
     for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
-      sc_s[i] = __ldg(&p.scale[i]);
-      sh_s[i] = __ldg(&p.shift[i]);
+      sc_s[i] = p.scale ? __ldg(&p.scale[i]) : 1.f;
+      sh_s[i] = p.shift ? __ldg(&p.shift[i]) : 0.f;
     }
   }
   ptx::tc_fence_before();
@@ -275,8 +285,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
         float sc = 1.f, sh = 0.f;
         if (r < p.M) {
           const int c = (r / p.rows_per_channel) % p.channels;
-          sc = __ldg(&p.scale[c]);
-          sh = __ldg(&p.shift[c]);
+          sc = p.scale ? __ldg(&p.scale[c]) : 1.f;
+          sh = p.shift ? __ldg(&p.shift[c]) : 0.f;
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -292,8 +302,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
             float x[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              x[j] = fmaf(__uint_as_float(v[j]), sc, sh);
-              if (p.relu) x[j] = fmaxf(x[j], 0.f);
+              x[j] = apply_act(fmaf(__uint_as_float(v[j]), sc, sh), p.act);
             }
             if (p.res_hi && !(p.dbg & 1)) {
               const bf16* h = reinterpret_cast<const bf16*>(rh[k]);
@@ -323,7 +332,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
         const int T2 = 2 * p.T, F2 = 2 * p.F;
         const size_t plane = (size_t)T2 * F2;
         for (int dy = 0; dy < 2; ++dy) {
-          const size_t base = ((size_t)b * p.Cout + n0) * plane + (size_t)(2 * t + dy) * F2 + 2 * f;
+          const size_t base = ((size_t)b * p.out_c_total + p.out_c_off + n0) * plane + (size_t)(2 * t + dy) * F2 + 2 * f;
+          const size_t sbase = ((size_t)b * p.Cout + n0) * plane + (size_t)(2 * t + dy) * F2 + 2 * f;  // skip tensor: own channel count
           for (int ch = ch_begin; ch < ch_end; ++ch) {
             const int c0 = ch * CW;
             uint32_t v0[CW], v1[CW];
@@ -331,7 +341,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
             ptx::tmem_ld8(trow + (uint32_t)((dy * 2 + 1) * nc + c0), v1);
             ptx::tmem_ld_wait();
             if (row_ok) {
-              const size_t o0 = base + (size_t)c0 * plane;
+              const size_t o0 = base + (size_t)c0 * plane, s0 = sbase + (size_t)c0 * plane;
               // all skip loads of this group are issued before any store (read-only path)
               uint32_t sk_h[CW], sk_l[CW];
 #pragma unroll
@@ -339,8 +349,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
                 sk_h[j] = 0x3f803f80u;  // bf16 (1.0, 1.0)
                 sk_l[j] = 0u;
                 if (p.res_hi && !(p.dbg & 1)) {
-                  sk_h[j] = __ldg(reinterpret_cast<const unsigned int*>(p.res_hi + o0 + (size_t)j * plane));
-                  sk_l[j] = __ldg(reinterpret_cast<const unsigned int*>(p.res_lo + o0 + (size_t)j * plane));
+                  sk_h[j] = __ldg(reinterpret_cast<const unsigned int*>(p.res_hi + s0 + (size_t)j * plane));
+                  sk_l[j] = __ldg(reinterpret_cast<const unsigned int*>(p.res_lo + s0 + (size_t)j * plane));
                 }
               }
               float scv[CW], shv[CW];
@@ -356,10 +366,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
 #pragma unroll
               for (int j = 0; j < CW; ++j) {
                 float x0 = fmaf(__uint_as_float(v0[j]), scv[j], shv[j]), x1 = fmaf(__uint_as_float(v1[j]), scv[j], shv[j]);
-                if (p.relu) {
-                  x0 = fmaxf(x0, 0.f);
-                  x1 = fmaxf(x1, 0.f);
-                }
+                x0 = apply_act(x0, p.act);
+                x1 = apply_act(x1, p.act);
                 // bf16 -> fp32 is a 16-bit shift: low half = element 0 (dx = 0), high half = element 1 (dx = 1)
                 x0 *= __uint_as_float(sk_h[j] << 16) + __uint_as_float(sk_l[j] << 16);
                 x1 *= __uint_as_float(sk_h[j] & 0xffff0000u) + __uint_as_float(sk_l[j] & 0xffff0000u);
@@ -382,7 +390,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
         const int fo = (f0 + m) >> 1, Fo = p.F >> 1, To = p.T >> 1;
         const bool row_ok = ((m & 1) == 0) && fo < Fo;
         const size_t plane = (size_t)To * Fo;
-        const size_t base = ((size_t)b * p.Cout + n0) * plane + (size_t)t * Fo + fo;
+        const size_t base = ((size_t)b * p.out_c_total + p.out_c_off + n0) * plane + (size_t)t * Fo + fo;
         for (int ch = ch_begin; ch < ch_end; ++ch) {
           const int c0 = ch * CW;
           uint32_t v0[CW], v1[CW];
@@ -405,14 +413,59 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
             bf16* pl = p.out_lo + base + (size_t)c0 * plane;
 #pragma unroll
             for (int j = 0; j < CW; ++j) {
-              float y = fmaf(x[j], sc[j], sh[j]);
-              if (p.relu) y = fmaxf(y, 0.f);
+              const float y = apply_act(fmaf(x[j], sc[j], sh[j]), p.act);
               bf16 h, l;
               split_store2(y, h, l);
               *ph = h;
               *pl = l;
               ph += plane;
               pl += plane;
+            }
+          }
+        }
+      } else if (p.mode == 4) {
+        // 1x1 convolution: column co of lane m is output pixel f0+m of channel n0+co.
+        constexpr int CW = 8;
+        const int f = f0 + m;
+        const bool row_ok = f < p.F;
+        const size_t plane = (size_t)p.T * p.F;
+        const size_t base = ((size_t)b * p.out_c_total + p.out_c_off + n0) * plane + (size_t)t * p.F + f;
+        const size_t rbase = ((size_t)b * p.Cout + n0) * plane + (size_t)t * p.F + f;
+        for (int ch = ch_begin; ch < ch_end; ++ch) {
+          const int c0 = ch * CW;
+          uint32_t v[CW];
+          ptx::tmem_ld8(trow + (uint32_t)c0, v);
+          ptx::tmem_ld_wait();
+          float sc[CW], sh[CW];
+#pragma unroll
+          for (int j4 = 0; j4 < CW / 4; ++j4) {
+            const float4 s4 = *reinterpret_cast<const float4*>(&sc_s[n0 + c0 + 4 * j4]);
+            const float4 h4 = *reinterpret_cast<const float4*>(&sh_s[n0 + c0 + 4 * j4]);
+            sc[4 * j4] = s4.x; sc[4 * j4 + 1] = s4.y; sc[4 * j4 + 2] = s4.z; sc[4 * j4 + 3] = s4.w;
+            sh[4 * j4] = h4.x; sh[4 * j4 + 1] = h4.y; sh[4 * j4 + 2] = h4.z; sh[4 * j4 + 3] = h4.w;
+          }
+          if (row_ok) {
+            float rv[CW], mv[CW];
+#pragma unroll
+            for (int j = 0; j < CW; ++j) {
+              rv[j] = 0.f;
+              mv[j] = 1.f;
+              const size_t ro = rbase + (size_t)(c0 + j) * plane;
+              if (p.res_hi) rv[j] = __bfloat162float(p.res_hi[ro]) + __bfloat162float(p.res_lo[ro]);
+              if (p.mul_hi) mv[j] = __bfloat162float(p.mul_hi[ro]) + __bfloat162float(p.mul_lo[ro]);
+            }
+#pragma unroll
+            for (int j = 0; j < CW; ++j) {
+              const float y = (apply_act(fmaf(__uint_as_float(v[j]), sc[j], sh[j]), p.act) + rv[j]) * mv[j];
+              const size_t o = base + (size_t)(c0 + j) * plane;
+              if (p.out_f32) {
+                p.out_f32[o] = y;
+              } else {
+                bf16 h, l;
+                split_store2(y, h, l);
+                p.out_hi[o] = h;
+                p.out_lo[o] = l;
+              }
             }
           }
         }
@@ -446,7 +499,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
         const int j_lo = (f0 == 0) ? 0 : 1;
         const bool row_ok = (m >= j_lo) && (m < kConvStride + 1) && (f < p.F);
         const size_t plane = (size_t)p.T * p.F;
-        const size_t base = ((size_t)b * p.Cout + n0) * plane + (size_t)t * p.F + f;
+        const size_t base = ((size_t)b * p.out_c_total + p.out_c_off + n0) * plane + (size_t)t * p.F + f;
+        const size_t rbase = ((size_t)b * p.Cout + n0) * plane + (size_t)t * p.F + f;  // residual / multiplier: (B, Cout, T, F)
         for (int ch = ch_begin; ch < ch_end; ++ch) {
           const int c0 = ch * CW;
           uint32_t v0[CW], v1[CW], v2[CW];
@@ -481,12 +535,21 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
             sh[4 * j4] = h4.x; sh[4 * j4 + 1] = h4.y; sh[4 * j4 + 2] = h4.z; sh[4 * j4 + 3] = h4.w;
           }
           if (row_ok) {
+            // optional residual / multiplier: every load of the group is issued before the first store
+            float rv[CW], mv[CW];
+#pragma unroll
+            for (int j = 0; j < CW; ++j) {
+              rv[j] = 0.f;
+              mv[j] = 1.f;
+              const size_t ro = rbase + (size_t)(c0 + j) * plane;
+              if (p.res_hi) rv[j] = __bfloat162float(p.res_hi[ro]) + __bfloat162float(p.res_lo[ro]);
+              if (p.mul_hi) mv[j] = __bfloat162float(p.mul_hi[ro]) + __bfloat162float(p.mul_lo[ro]);
+            }
             bf16* ph = p.out_hi + base + (size_t)c0 * plane;
             bf16* pl = p.out_lo + base + (size_t)c0 * plane;
 #pragma unroll
             for (int j = 0; j < CW; ++j) {
-              float y = fmaf(x[j], sc[j], sh[j]);
-              if (p.relu) y = fmaxf(y, 0.f);
+              const float y = (apply_act(fmaf(x[j], sc[j], sh[j]), p.act) + rv[j]) * mv[j];
               bf16 h, l;
               split_store2(y, h, l);
               *ph = h;  // 32 lanes -> 32 consecutive pixels: one 64-byte segment per plane
@@ -624,15 +687,32 @@ int umma_gemm_plan_create(UmmaGemmPlan* pl, const void* a_hi, const void* a_lo, 
   return rc;
 }
 
+static void fill_epilogue(UmmaParams& p, const UmmaEpilogue& e, int Cout) {
+  p.scale = e.scale; p.shift = e.shift; p.act = e.act;
+  p.out_hi = (bf16*)e.out_hi; p.out_lo = (bf16*)e.out_lo; p.out_f32 = e.out_f32;
+  p.res_hi = (const bf16*)e.res_hi; p.res_lo = (const bf16*)e.res_lo;
+  p.mul_hi = (const bf16*)e.mul_hi; p.mul_lo = (const bf16*)e.mul_lo;
+  p.out_c_total = e.out_c_total > 0 ? e.out_c_total : Cout;
+  p.out_c_off = e.out_c_off;
+}
+
 int umma_gemm_run(const UmmaGemmPlan& pl, const float* scale, const float* shift, int rows_per_channel, int channels, int relu, void* out_hi,
                   void* out_lo, const void* res_hi, const void* res_lo, int M_active, cudaStream_t st) {
+  UmmaEpilogue e;
+  e.scale = scale; e.shift = shift; e.act = relu ? 1 : 0; e.out_hi = out_hi; e.out_lo = out_lo; e.res_hi = res_hi; e.res_lo = res_lo;
+  return umma_gemm_run_ex(pl, rows_per_channel, channels, M_active, e, st);
+}
+
+int umma_gemm_run_ex(const UmmaGemmPlan& pl, int rows_per_channel, int channels, int M_active, const UmmaEpilogue& e, cudaStream_t st) {
+  const float* scale = e.scale; const float* shift = e.shift; const int relu = e.act;
+  void* out_hi = e.out_hi; void* out_lo = e.out_lo; const void* res_hi = e.res_hi; const void* res_lo = e.res_lo;
   UmmaParams p{};
   p.mode = 0;
   p.n_tile = pl.n_tile; p.n_total = pl.N;
   p.num_iters = (pl.K + 63) / 64; p.ksteps = 4;
   p.a_bytes = 128 * 128; p.b_bytes = (uint32_t)pl.n_tile * 128;
   p.M = M_active; p.K = pl.K; p.rows_per_channel = rows_per_channel; p.channels = channels;
-  p.scale = scale; p.shift = shift; p.relu = relu;
+  p.scale = scale; p.shift = shift; p.act = relu;
   p.out_hi = (bf16*)out_hi; p.out_lo = (bf16*)out_lo; p.res_hi = (const bf16*)res_hi; p.res_lo = (const bf16*)res_lo;
   B2_CHECK_ARG(pl.n_tile <= 128, "umma_gemm: n_tile=%d exceeds the epilogue's 8 column groups", pl.n_tile);
   dim3 grid(pl.N / pl.n_tile, cdiv(M_active, kTileM));
@@ -673,6 +753,12 @@ int umma_conv_plan_create(UmmaConvPlan* pl, const void* x_hi, const void* x_lo, 
 int umma_conv_run(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_lo, int B, int Cout, int n_c, int ksize, const float* scale,
                   const float* shift, int relu, void* out_hi, void* out_lo, cudaStream_t st) {
   B2_CHECK_ARG(ksize == 3, "umma_conv: only 3x3 kernels");
+  UmmaEpilogue e;
+  e.scale = scale; e.shift = shift; e.act = relu ? 1 : 0; e.out_hi = out_hi; e.out_lo = out_lo;
+  return umma_conv_run_ex(pl, wb_hi, wb_lo, B, Cout, n_c, e, st);
+}
+
+int umma_conv_run_ex(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_lo, int B, int Cout, int n_c, const UmmaEpilogue& e, cudaStream_t st) {
   UmmaParams p{};
   p.mode = 1; p.f_stride = kConvStride; p.t_mul = 1; p.t_off = -1;
   p.n_c = n_c; p.n_tile = 3 * n_c; p.n_total = Cout;
@@ -681,8 +767,7 @@ int umma_conv_run(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_lo, 
   p.a_bytes = (uint32_t)pl.kc * 256; p.b_bytes = (uint32_t)p.ksteps * p.n_tile * 32;
   p.T = pl.T; p.F = pl.F; p.Cin = pl.Cin; p.Cout = Cout; p.n_tiles = Cout / n_c;
   p.wb_hi = (const bf16*)wb_hi; p.wb_lo = (const bf16*)wb_lo;
-  p.scale = scale; p.shift = shift; p.relu = relu;
-  p.out_hi = (bf16*)out_hi; p.out_lo = (bf16*)out_lo;
+  fill_epilogue(p, e, Cout);
   dim3 grid(pl.F <= 1 ? 1 : cdiv(pl.F - 1, kConvStride), pl.T, B * p.n_tiles);
   return launch(pl.a_hi, pl.a_lo, pl.a_hi, pl.a_lo, p, grid, st);
 }
@@ -708,6 +793,12 @@ int umma_updown_choose(int Cin, int Cout, int up, int* kc, int* n_c) {
 // x: pair (B, Cin, T, F) -> ConvTranspose2d(k2,s2)+BN+ReLU (* skip) -> pair (B, Cout, 2T, 2F)
 int umma_up_run(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_lo, int B, int Cout, int n_c, const float* scale, const float* shift, int relu,
                 const void* skip_hi, const void* skip_lo, void* out_hi, void* out_lo, cudaStream_t st) {
+  UmmaEpilogue e;
+  e.scale = scale; e.shift = shift; e.act = relu ? 1 : 0; e.out_hi = out_hi; e.out_lo = out_lo; e.res_hi = skip_hi; e.res_lo = skip_lo;
+  return umma_up_run_ex(pl, wb_hi, wb_lo, B, Cout, n_c, e, st);
+}
+
+int umma_up_run_ex(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_lo, int B, int Cout, int n_c, const UmmaEpilogue& e, cudaStream_t st) {
   UmmaParams p{};
   p.mode = 2; p.f_stride = kTileM; p.t_mul = 1; p.t_off = 0;
   p.n_c = n_c; p.n_tile = 4 * n_c; p.n_total = Cout;
@@ -715,8 +806,7 @@ int umma_up_run(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_lo, in
   p.a_bytes = (uint32_t)pl.kc * 256; p.b_bytes = (uint32_t)p.ksteps * p.n_tile * 32;
   p.T = pl.T; p.F = pl.F; p.Cin = pl.Cin; p.Cout = Cout; p.n_tiles = Cout / n_c;
   p.wb_hi = (const bf16*)wb_hi; p.wb_lo = (const bf16*)wb_lo;
-  p.scale = scale; p.shift = shift; p.relu = relu;
-  p.out_hi = (bf16*)out_hi; p.out_lo = (bf16*)out_lo; p.res_hi = (const bf16*)skip_hi; p.res_lo = (const bf16*)skip_lo;
+  fill_epilogue(p, e, Cout);
   dim3 grid(cdiv(pl.F, kTileM), pl.T, B * p.n_tiles);
   return launch(pl.a_hi, pl.a_lo, pl.a_hi, pl.a_lo, p, grid, st);
 }
@@ -724,6 +814,12 @@ int umma_up_run(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_lo, in
 // x: pair (B, Cin, T, F) -> Conv2d(k2,s2)+BN+ReLU -> pair (B, Cout, T/2, F/2)
 int umma_down_run(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_lo, int B, int Cout, int n_c, const float* scale, const float* shift, int relu,
                   void* out_hi, void* out_lo, cudaStream_t st) {
+  UmmaEpilogue e;
+  e.scale = scale; e.shift = shift; e.act = relu ? 1 : 0; e.out_hi = out_hi; e.out_lo = out_lo;
+  return umma_down_run_ex(pl, wb_hi, wb_lo, B, Cout, n_c, e, st);
+}
+
+int umma_down_run_ex(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_lo, int B, int Cout, int n_c, const UmmaEpilogue& e, cudaStream_t st) {
   UmmaParams p{};
   p.mode = 3; p.f_stride = kTileM; p.t_mul = 2; p.t_off = 0;
   p.n_c = n_c; p.n_tile = 2 * n_c; p.n_total = Cout;
@@ -731,8 +827,7 @@ int umma_down_run(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_lo, 
   p.a_bytes = (uint32_t)pl.kc * 256; p.b_bytes = (uint32_t)p.ksteps * p.n_tile * 32;
   p.T = pl.T; p.F = pl.F; p.Cin = pl.Cin; p.Cout = Cout; p.n_tiles = Cout / n_c;
   p.wb_hi = (const bf16*)wb_hi; p.wb_lo = (const bf16*)wb_lo;
-  p.scale = scale; p.shift = shift; p.relu = relu;
-  p.out_hi = (bf16*)out_hi; p.out_lo = (bf16*)out_lo;
+  fill_epilogue(p, e, Cout);
   dim3 grid(cdiv(pl.F, kTileM), pl.T / 2, B * p.n_tiles);
   return launch(pl.a_hi, pl.a_lo, pl.a_hi, pl.a_lo, p, grid, st);
 }
@@ -783,6 +878,33 @@ void umma_down_block_weights(const float* w, int Cout, int Cin, int kc, int n_c,
     const int dx = row / n_c, co = nt * n_c + row % n_c;
     return w[(((size_t)co * Cin + ci) * 2 + dy) * 2 + dx];
   }, hi, lo);
+}
+
+// Conv2d weight (Cout, Cin, 1, 1): one tap, B rows = co_local
+void umma_pw_block_weights(const float* w, int Cout, int Cin, int kc, int n_c, std::vector<uint16_t>& hi, std::vector<uint16_t>& lo) {
+  block_weights(Cout / n_c, 1, Cin, kc, n_c, [&](int nt, int row, int, int ci) { return w[(size_t)(nt * n_c + row) * Cin + ci]; }, hi, lo);
+}
+bool umma_pw_supported(int Cin, int Cout, int F) { return Cin % 16 == 0 && Cout % 16 == 0 && F % 8 == 0; }
+int umma_pw_choose(int Cin, int Cout, int* kc, int* n_c) {
+  int k = 64;
+  while (k > 16 && Cin % k != 0) k -= 16;
+  if (Cin % 48 == 0) k = 48;
+  *kc = k;
+  *n_c = pick_nc(Cout, 1, 256);
+  return 0;
+}
+// x: pair (B, Cin, T, F) -> Conv2d 1x1 (+affine, act, +res, *mul) -> pair or fp32 (B, Cout, T, F)
+int umma_pw_run_ex(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_lo, int B, int Cout, int n_c, const UmmaEpilogue& e, cudaStream_t st) {
+  UmmaParams p{};
+  p.mode = 4; p.f_stride = kTileM; p.t_mul = 1; p.t_off = 0;
+  p.n_c = n_c; p.n_tile = n_c; p.n_total = Cout;
+  p.kc = pl.kc; p.n_chunks = pl.Cin / pl.kc; p.num_iters = p.n_chunks; p.ksteps = pl.kc / 16;
+  p.a_bytes = (uint32_t)pl.kc * 256; p.b_bytes = (uint32_t)p.ksteps * p.n_tile * 32;
+  p.T = pl.T; p.F = pl.F; p.Cin = pl.Cin; p.Cout = Cout; p.n_tiles = Cout / n_c;
+  p.wb_hi = (const bf16*)wb_hi; p.wb_lo = (const bf16*)wb_lo;
+  fill_epilogue(p, e, Cout);
+  dim3 grid(cdiv(pl.F, kTileM), pl.T, B * p.n_tiles);
+  return launch(pl.a_hi, pl.a_lo, pl.a_hi, pl.a_lo, p, grid, st);
 }
 
 // Host-side blocking of a (Cout, Cin, 3, 3) fp32 filter into the B operand stream of umma_conv_run:

@@ -131,3 +131,18 @@ def _silent(tmp_path):
         wf.setnchannels(2); wf.setsampwidth(2); wf.setframerate(44100)
         wf.writeframes(np.zeros(200, "<i2").tobytes())
     return p
+
+
+def test_tfcnet_param_count_matches_reference_state_dict(lib_built):
+    import mdxc_oracle as X
+    from audio_separator.separator.b200 import _lib, engine
+
+    for kw in (dict(), dict(n_fft=1024, hop_length=256, dim_f=512, dim_t=16, num_scales=2, num_channels_model=16, growth=16, bottleneck_factor=4)):
+        cfg = X.MDXCConfig(**kw)
+        shapes = X.param_shapes(cfg)
+        mine = engine.tfcnet_param_names(cfg.dim_f, cfg.num_subbands, 2, cfg.num_scales, cfg.num_blocks_per_scale, cfg.num_channels_model, cfg.growth, cfg.bottleneck_factor, cfg.num_targets)
+        assert mine == shapes
+        c = _lib.TfcNetConfig(cfg.dim_f, cfg.dim_t, cfg.num_subbands, 2, cfg.num_scales, cfg.num_blocks_per_scale, cfg.num_channels_model, cfg.growth, cfg.bottleneck_factor, cfg.num_targets, 1)
+        assert _lib.lib.b200sep_tfcnet_param_count(ctypes.byref(c)) == sum(int(np.prod(s)) for _, s in shapes)
+    # MDX23C-8KFFT-InstVoc_HQ: 112 M parameters = 448 MB fp32
+    assert 111e6 < sum(int(np.prod(s)) for _, s in X.param_shapes(X.MDXCConfig())) < 113e6
