@@ -32,7 +32,7 @@ namespace b200sep {
 
 using bf16 = __nv_bfloat16;
 constexpr int kUmmaThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
-constexpr int kMaxChannels = 512;   // per-channel scale/shift staged in shared memory (conv modes)
+constexpr int kMaxChannels = 1024;  // per-channel scale/shift staged in shared memory (conv modes)
 constexpr int kTileM = 128;
 constexpr int kConvStride = 120;  // output pixels per conv tile (multiple of 8: TMA box starts must be 16-byte aligned)
 
