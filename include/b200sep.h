@@ -201,6 +201,53 @@ int b200sep_rect_overlap_add(const float* chunks, int n_chunks, int channels, in
                              float divisor, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Generalised STFT framing (HTDemucs._spec / _ispec, uvr_lib_v5/demucs/htdemucs.py:383-413 + spec.py:11-38): see stft.cu.
+ */
+int b200sep_stft_forward_ex(const b200sep_stft_plan* plan, const float* wave, int64_t batch_stride, int64_t chan_stride, int64_t valid_len,
+                            int batch, int chunk_len, int frames, int frame_offset, float scale, int dim_f, int zero_bins, int layout,
+                            float* spec, void* stream);
+int b200sep_stft_inverse_ex(const b200sep_stft_plan* plan, const float* spec, int batch, int frames, int dim_f, int layout, int out_len,
+                            int ola_offset, int env_extra, float scale, float* wave, float* work, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * fp32 operators of the HTDemucs path (uvr_lib_v5/demucs/{htdemucs,hdemucs,demucs,transformer,apply}.py).  Each replaces the
+ * ATen call named in its comment; tensors are contiguous float32 device arrays.
+ *
+ * conv2d_f32: nn.Conv1d / nn.Conv2d (hdemucs.py:107,113; demucs.py:147,150) and, with up_axis != 0, nn.ConvTranspose1d/2d
+ *   (hdemucs.py:285) expressed as a 2-tap convolution over the coarse index q with up*Cout GEMM columns (column r*Cout+co ->
+ *   output index q*up + r - trim, kept inside [0, out_len)).  x (B,Cin,H,W); w_blocked [Cin][KH*KW][ceil48(CoutCols)];
+ *   y = act(conv + bias (+ add if add_before_act)) (+ add otherwise).  act: 0 none, 1 ReLU, 2 GELU(erf), 3 LeakyReLU(0.01).
+ *   Supported (KH,KW,SH,SW,DW): (1,1,1,1,1) (3,3,1,1,1) (1,3,1,1,1) (1,3,1,1,2) (8,1,4,1,1) (1,8,1,4,1) (2,1,1,1,1) (1,2,1,1,1).
+ */
+int b200sep_conv2d_f32(const float* x, const float* w_blocked, const float* bias, const float* add, float* y, int B, int Cin, int H, int W, int Cout,
+                       int Ho, int Wo, int KH, int KW, int SH, int SW, int PH, int PW, int DW, int act, int add_before_act, int up_axis, int up,
+                       int trim, int out_len, void* stream);
+/* nn.GroupNorm(1, C), affine, optional activation (demucs.py:141,144).  Channel-first x (B, C, Fr, L): one sample per (b, fr) row
+ * (Fr = 1: (B, C, L); Fr > 1: DConv on every frequency row without the permute of hdemucs.py:141-146); channel_last: x (B, L, C)
+ * tokens (MyGroupNorm, transformer.py:184-193). */
+int b200sep_groupnorm1_f32(const float* x, const float* gamma, const float* beta, float* y, int B, int C, int Fr, int64_t L, int act, int channel_last,
+                           void* stream);
+/* y = x.permute(p0,p1,p2,p3).contiguous() for a 4-D tensor (the einops rearranges around the transformer, transformer.py:532-555) */
+int b200sep_permute4_f32(const float* x, float* y, int d0, int d1, int d2, int d3, int p0, int p1, int p2, int p3, void* stream);
+/* F.glu(dim=1) on (B, 2C, L); with res/scale: y = res + scale[c] * glu  (LayerScale residual of DConv, demucs.py:92-93,166-168) */
+int b200sep_glu_f32(const float* a, const float* res, const float* scale, float* y, int B, int C, int64_t L, void* stream);
+/* nn.LayerNorm(C) on (rows, C) (transformer.py:481-482 and the layers' norm1/2/3) */
+int b200sep_layernorm_f32(const float* x, const float* gamma, const float* beta, float* y, int64_t rows, int C, void* stream);
+/* batched TN GEMM: C[z] = epi(alpha * A[z] (M,K; lda) @ Bw[z] (N,K; ldb)^T): + bias_n[n] + bias_m[m], act, then res + res_scale[n]*v
+ * (nn.Linear / in_proj / out_proj / attention scores and values of nn.MultiheadAttention; LayerScale gamma_1/2, transformer.py:268-269) */
+int b200sep_gemm_f32(const float* A, const float* Bw, float* C, int M, int N, int K, int lda, int ldb, int ldc, int batch, int64_t strideA,
+                     int64_t strideB, int64_t strideC, float alpha, const float* bias_n, const float* bias_m, int act, const float* res,
+                     const float* res_scale, void* stream);
+int b200sep_softmax_rows_f32(float* x, int64_t rows, int n, void* stream);
+/* op 0: out = alpha*a + beta*b (b NULL: + beta);  op 1: out = a*b */
+int b200sep_ew_f32(const float* a, const float* b, float* out, int64_t n, float alpha, float beta, int op, void* stream);
+/* out2[0] = mean, out2[1] = unbiased std over n elements (htdemucs.py:501-510) */
+int b200sep_meanstd_f32(const float* x, int64_t n, float* out2, void* stream);
+/* apply_model's split branch (demucs/apply.py:215-250): triangle-weighted overlap-add of segments (n_segs, channels, seg_len) at
+ * stride `stride`, normalised by the summed weights -> out (channels, length) */
+int b200sep_triangle_overlap_add(const float* segs, int n_segs, int channels, int seg_len, int64_t stride, int64_t length, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Self-tests of the tensor-core ("bf16x3 pair") operators in isolation: fp32 device tensors in, the operator runs
  * exactly as inside the network (split into bf16 hi/lo planes -> tcgen05 kernel -> join), fp32 out.  Synchronous.
  *   gemm   : out[M][N] = act((a[M][K] @ w[N][K]^T) * scale[c] + shift[c]) (+ res),  c = (row / rows_per_channel) % channels

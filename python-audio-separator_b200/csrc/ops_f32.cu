@@ -1,0 +1,385 @@
+// fp32 operators for the HTDemucs path (hdemucs.py / demucs.py / transformer.py of the reference): GroupNorm(1,C),
+// GLU (+LayerScale residual), LayerNorm, batched TN GEMM with bias / activation / scaled residual, row softmax,
+// small element-wise helpers, whole-tensor mean/std, and the triangle-window segment overlap-add of apply_model.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace b200sep {
+
+__device__ __forceinline__ float f32_act(float v, int act) {
+  if (act == 1) return fmaxf(v, 0.f);
+  if (act == 2) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+  return v;
+}
+
+__device__ __forceinline__ float2 block_sum2(float a, float b, float* red) {
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) {
+    red[w] = a;
+    red[32 + w] = b;
+  }
+  __syncthreads();
+  float ta = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f, tb = (threadIdx.x < nw) ? red[32 + threadIdx.x] : 0.f;
+  if (w == 0) {
+    for (int o = 16; o > 0; o >>= 1) {
+      ta += __shfl_xor_sync(0xffffffffu, ta, o);
+      tb += __shfl_xor_sync(0xffffffffu, tb, o);
+    }
+    if (l == 0) {
+      red[0] = ta;
+      red[32] = tb;
+    }
+  }
+  __syncthreads();
+  return make_float2(red[0], red[32]);
+}
+
+// GroupNorm(num_groups=1, C) over one sample of C*L elements (two passes: mean, then centred variance), affine per channel,
+// optional activation.  grid = samples = B*Fr.  (hdemucs.py:79-80 norm_fn, demucs.py:139-141; eps 1e-5, biased variance.)
+// Layouts: channel-first (B, C, Fr, L) where sample (b, fr) owns elements x[((b*C + c)*Fr + fr)*L + l]  (Fr = 1: plain (B, C, L);
+// Fr > 1: DConv applied per frequency row of a (B, C, Fr, T) tensor without the permute of hdemucs.py:141-146), or
+// channel-last (samples, L, C) (MyGroupNorm on (B, T, C) tokens, transformer.py:184-193).
+__global__ void __launch_bounds__(512) groupnorm1_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        float* __restrict__ y, int C, int Fr, int64_t L, int act, int channel_last) {
+  __shared__ float red[64];
+  const int64_t n = (int64_t)C * L;
+  const int b = blockIdx.x / Fr, fr = blockIdx.x % Fr;
+  auto idx = [&](int64_t i) -> int64_t {
+    if (channel_last || Fr == 1) return (int64_t)blockIdx.x * n + i;
+    const int64_t c = i / L, l = i - c * L;
+    return (((int64_t)b * C + c) * Fr + fr) * L + l;
+  };
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += x[idx(i)];
+  const float mean = block_sum2(s, 0.f, red).x / (float)n;
+  float q = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const float d = x[idx(i)] - mean;
+    q = fmaf(d, d, q);
+  }
+  const float rstd = rsqrtf(block_sum2(q, 0.f, red).x / (float)n + 1e-5f);
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = channel_last ? (int)(i % C) : (int)(i / L);
+    const int64_t o = idx(i);
+    y[o] = f32_act((x[o] - mean) * rstd * __ldg(&gamma[c]) + __ldg(&beta[c]), act);
+  }
+}
+
+// out[perm(i)] = in[i] for a 4-D tensor: out dims = in dims permuted by (p0,p1,p2,p3) ("b c fr t -> b t fr c" etc., transformer.py:532,555)
+__global__ void permute4_kernel(const float* __restrict__ x, float* __restrict__ y, int d0, int d1, int d2, int d3, int p0, int p1, int p2, int p3, int64_t n) {
+  const int din[4] = {d0, d1, d2, d3};
+  const int perm[4] = {p0, p1, p2, p3};
+  const int64_t sin_[4] = {(int64_t)d1 * d2 * d3, (int64_t)d2 * d3, d3, 1};
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = o, src = 0;
+    for (int k = 3; k >= 0; --k) {
+      const int dk = din[perm[k]];
+      src += (r % dk) * sin_[perm[k]];
+      r /= dk;
+    }
+    y[o] = x[src];
+  }
+}
+
+// y[b][c][l] = (res ? res + scale[c] * g : g),  g = a[b][c][l] * sigmoid(a[b][C + c][l])   (F.glu(dim=1); LayerScale, demucs.py:92-93)
+__global__ void glu_kernel(const float* __restrict__ a, const float* __restrict__ res, const float* __restrict__ scale, float* __restrict__ y, int C, int64_t L,
+                           int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t l = i % L;
+    const int64_t bc = i / L;
+    const int c = (int)(bc % C);
+    const int64_t b = bc / C;
+    const float u = a[((b * 2 * C) + c) * L + l], v = a[((b * 2 * C) + C + c) * L + l];
+    float g = u / (1.f + expf(-v));
+    if (res) g = res[i] + __ldg(&scale[c]) * g;
+    y[i] = g;
+  }
+}
+
+// LayerNorm over the last dimension C of (rows, C); one warp per row.  eps 1e-5.
+__global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y, int64_t rows,
+                                 int C) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + row * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += xr[c];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float d = xr[c] - mean;
+    q = fmaf(d, d, q);
+  }
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / C + 1e-5f);
+  float* yr = y + row * C;
+  for (int c = lane; c < C; c += 32) yr[c] = (xr[c] - mean) * rstd * __ldg(&gamma[c]) + __ldg(&beta[c]);
+}
+
+// Batched SGEMM TN: C[z][m][n] = epi( sum_k A[z][m][k] * Bw[z][n][k] ), 128x128x16 tiles, 8x8 per thread.
+// epi: v = acc * alpha + (bias_n ? bias[n] : 0) + (bias_m ? bias_row[m] : 0); v = act(v); if res: v = res + (rs ? rs[n] : 1) * v
+struct GemmF32 {
+  const float* A;
+  const float* Bw;
+  float* C;
+  const float* bias_n;
+  const float* bias_m;
+  const float* res;
+  const float* res_scale;
+  int M, N, K, lda, ldb, ldc;
+  int64_t sA, sB, sC;  // batch strides (elements)
+  float alpha;
+  int act;
+};
+constexpr int FBM = 128, FBN = 128, FBK = 16;
+__global__ void __launch_bounds__(256) gemm_f32_kernel(GemmF32 p) {
+  __shared__ __align__(16) float As[FBK][FBM + 4];
+  __shared__ __align__(16) float Bs[FBK][FBN + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * FBM, n0 = blockIdx.x * FBN;
+  const float* A = p.A + (int64_t)blockIdx.z * p.sA;
+  const float* Bw = p.Bw + (int64_t)blockIdx.z * p.sB;
+  float* C = p.C + (int64_t)blockIdx.z * p.sC;
+  const float* res = p.res ? p.res + (int64_t)blockIdx.z * p.sC : nullptr;
+  const bool vec = ((p.lda | p.ldb) & 3) == 0 && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Bw)) & 15) == 0;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < p.K; k0 += FBK) {
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int idx = tid + it * 256;
+      const int row = idx >> 2, kq = idx & 3, k = k0 + kq * 4;
+      float av[4] = {0.f, 0.f, 0.f, 0.f}, bv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (vec && k + 3 < p.K) {
+        if (m0 + row < p.M) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(&A[(int64_t)(m0 + row) * p.lda + k]));
+          av[0] = t.x; av[1] = t.y; av[2] = t.z; av[3] = t.w;
+        }
+        if (n0 + row < p.N) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(&Bw[(int64_t)(n0 + row) * p.ldb + k]));
+          bv[0] = t.x; bv[1] = t.y; bv[2] = t.z; bv[3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (m0 + row < p.M && k + e < p.K) av[e] = __ldg(&A[(int64_t)(m0 + row) * p.lda + k + e]);
+          if (n0 + row < p.N && k + e < p.K) bv[e] = __ldg(&Bw[(int64_t)(n0 + row) * p.ldb + k + e]);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        As[kq * 4 + e][row] = av[e];
+        Bs[kq * 4 + e][row] = bv[e];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < FBK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 8]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[k][tx * 8 + 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + ty * 8 + i;
+    if (m >= p.M) continue;
+    const float bm = p.bias_m ? __ldg(&p.bias_m[m]) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + tx * 8 + j;
+      if (n >= p.N) continue;
+      float v = fmaf(acc[i][j], p.alpha, bm + (p.bias_n ? __ldg(&p.bias_n[n]) : 0.f));
+      v = f32_act(v, p.act);
+      const int64_t o = (int64_t)m * p.ldc + n;
+      if (res) v = res[o] + (p.res_scale ? __ldg(&p.res_scale[n]) : 1.f) * v;
+      C[o] = v;
+    }
+  }
+}
+
+// in-place softmax over the last dimension of (rows, n); one CTA per row
+__global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ x, int n) {
+  __shared__ float red[64];
+  float* r = x + (int64_t)blockIdx.x * n;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, r[i]);
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0];
+  for (int w = 1; w < (blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+  __syncthreads();
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float e = expf(r[i] - m);
+    r[i] = e;
+    s += e;
+  }
+  const float tot = block_sum2(s, 0.f, red).x;
+  const float inv = 1.f / tot;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) r[i] *= inv;
+}
+
+// out = alpha * a + beta * b (b may be null) ; op 1: out = a * b
+__global__ void ew_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int64_t n, float alpha, float beta, int op) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v;
+    if (op == 1) v = a[i] * b[i];
+    else v = alpha * a[i] + (b ? beta * b[i] : beta);
+    out[i] = v;
+  }
+}
+
+// sum and sum of squares (double accumulation) -> out[0] = mean, out[1] = unbiased std  (x.mean(), x.std() of htdemucs.py:501-510)
+__global__ void __launch_bounds__(1024) meanstd_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+  __shared__ double rs[32], rq[32];
+  double s = 0.0, q = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = x[i];
+    s += v;
+    q += v * v;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    rs[threadIdx.x >> 5] = s;
+    rq[threadIdx.x >> 5] = q;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double S = 0.0, Q = 0.0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) {
+      S += rs[w];
+      Q += rq[w];
+    }
+    const double mean = S / (double)n;
+    const double var = (Q - S * mean) / (double)(n - 1);
+    out[0] = (float)mean;
+    out[1] = (float)sqrt(var > 0.0 ? var : 0.0);
+  }
+}
+
+// apply_model's split branch (demucs/apply.py:215-250) as a gather: out[c][q] = sum_i w[q - o_i] * seg_i[c][q - o_i] / sum_i w[q - o_i],
+// segments i start at o_i = i * stride, have `seg_len` samples except the last (clipped at `length`); triangle weight of `seg_len`.
+__global__ void tri_ola_kernel(const float* __restrict__ segs, int n_segs, int channels, int seg_len, int64_t stride, int64_t length, float* __restrict__ out) {
+  const int c = blockIdx.y;
+  const float wmax = (float)(seg_len - seg_len / 2 > seg_len / 2 ? seg_len - seg_len / 2 : seg_len / 2);
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < length; q += (int64_t)gridDim.x * blockDim.x) {
+    int64_t i_hi = q / stride;
+    if (i_hi > n_segs - 1) i_hi = n_segs - 1;
+    int64_t i_lo = (q - seg_len + 1 <= 0) ? 0 : (q - seg_len + stride) / stride;
+    float acc = 0.f, sw = 0.f;
+    for (int64_t i = i_lo; i <= i_hi; ++i) {
+      const int64_t n = q - i * stride;  // position inside segment i (its valid part is always long enough: clipped only at `length`)
+      const float w = ((n < seg_len / 2) ? (float)(n + 1) : (float)(seg_len - n)) / wmax;  // cat(arange(1, s/2+1), arange(s - s/2, 0, -1)) / max
+      acc += w * __ldg(&segs[((int64_t)i * channels + c) * seg_len + n]);
+      sw += w;
+    }
+    out[(int64_t)c * length + q] = acc / sw;
+  }
+}
+
+}  // namespace b200sep
+
+using namespace b200sep;
+
+extern "C" int b200sep_groupnorm1_f32(const float* x, const float* gamma, const float* beta, float* y, int B, int C, int Fr, int64_t L, int act, int channel_last,
+                                      void* stream) {
+  B2_CHECK_ARG(x && gamma && beta && y && B >= 1 && C >= 1 && Fr >= 1 && L >= 1, "groupnorm1_f32: bad argument");
+  B2_CHECK_ARG(!(channel_last && Fr != 1), "groupnorm1_f32: channel_last layout has no frequency rows");
+  groupnorm1_kernel<<<B * Fr, 512, 0, (cudaStream_t)stream>>>(x, gamma, beta, y, C, Fr, L, act, channel_last);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
+extern "C" int b200sep_permute4_f32(const float* x, float* y, int d0, int d1, int d2, int d3, int p0, int p1, int p2, int p3, void* stream) {
+  B2_CHECK_ARG(x && y && d0 >= 1 && d1 >= 1 && d2 >= 1 && d3 >= 1, "permute4_f32: bad argument");
+  const int seen = (1 << p0) | (1 << p1) | (1 << p2) | (1 << p3);
+  B2_CHECK_ARG(p0 >= 0 && p0 < 4 && p1 >= 0 && p1 < 4 && p2 >= 0 && p2 < 4 && p3 >= 0 && p3 < 4 && seen == 15, "permute4_f32: not a permutation");
+  const int64_t n = (int64_t)d0 * d1 * d2 * d3;
+  permute4_kernel<<<(int)std::min<int64_t>(cdiv(n, 256), kNumSMs * 16), 256, 0, (cudaStream_t)stream>>>(x, y, d0, d1, d2, d3, p0, p1, p2, p3, n);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
+extern "C" int b200sep_glu_f32(const float* a, const float* res, const float* scale, float* y, int B, int C, int64_t L, void* stream) {
+  B2_CHECK_ARG(a && y && (res == nullptr || scale != nullptr), "glu_f32: bad argument");
+  const int64_t n = (int64_t)B * C * L;
+  if (n == 0) return B200SEP_OK;
+  glu_kernel<<<(int)std::min<int64_t>(cdiv(n, 256), kNumSMs * 16), 256, 0, (cudaStream_t)stream>>>(a, res, scale, y, C, L, n);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
+extern "C" int b200sep_layernorm_f32(const float* x, const float* gamma, const float* beta, float* y, int64_t rows, int C, void* stream) {
+  B2_CHECK_ARG(x && gamma && beta && y && rows >= 0 && C >= 1, "layernorm_f32: bad argument");
+  if (rows == 0) return B200SEP_OK;
+  layernorm_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, y, rows, C);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
+extern "C" int b200sep_gemm_f32(const float* A, const float* Bw, float* C, int M, int N, int K, int lda, int ldb, int ldc, int batch, int64_t strideA,
+                                int64_t strideB, int64_t strideC, float alpha, const float* bias_n, const float* bias_m, int act, const float* res,
+                                const float* res_scale, void* stream) {
+  B2_CHECK_ARG(A && Bw && C && M >= 1 && N >= 1 && K >= 1 && batch >= 1 && batch <= 65535, "gemm_f32: bad argument");
+  GemmF32 p{A, Bw, C, bias_n, bias_m, res, res_scale, M, N, K, lda, ldb, ldc, strideA, strideB, strideC, alpha, act};
+  dim3 grid(cdiv(N, FBN), cdiv(M, FBM), batch);
+  B2_CHECK_ARG(grid.y <= 65535, "gemm_f32: M too large");
+  gemm_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
+extern "C" int b200sep_softmax_rows_f32(float* x, int64_t rows, int n, void* stream) {
+  B2_CHECK_ARG(x && rows >= 0 && n >= 1 && rows <= 0x7fffffff, "softmax_rows_f32: bad argument");
+  if (rows == 0) return B200SEP_OK;
+  softmax_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, n);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
+extern "C" int b200sep_ew_f32(const float* a, const float* b, float* out, int64_t n, float alpha, float beta, int op, void* stream) {
+  B2_CHECK_ARG(a && out && n >= 0 && (op != 1 || b), "ew_f32: bad argument");
+  if (n == 0) return B200SEP_OK;
+  ew_kernel<<<(int)std::min<int64_t>(cdiv(n, 256), kNumSMs * 16), 256, 0, (cudaStream_t)stream>>>(a, b, out, n, alpha, beta, op);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
+extern "C" int b200sep_meanstd_f32(const float* x, int64_t n, float* out2, void* stream) {
+  B2_CHECK_ARG(x && out2 && n >= 2, "meanstd_f32: need at least 2 elements");
+  meanstd_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, n, out2);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
+extern "C" int b200sep_triangle_overlap_add(const float* segs, int n_segs, int channels, int seg_len, int64_t stride, int64_t length, float* out, void* stream) {
+  B2_CHECK_ARG(segs && out && n_segs >= 1 && channels >= 1 && seg_len >= 2 && stride >= 1 && length >= 1, "triangle_overlap_add: bad argument");
+  dim3 grid((unsigned)std::min<int64_t>(cdiv(length, 256), kNumSMs * 8), channels);
+  tri_ola_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(segs, n_segs, channels, seg_len, stride, length, out);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}

@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(kFftThreads) stft_forward_kernel(FftStages st,
                                                                    const float* __restrict__ window, const float* __restrict__ wave,
                                                                    int64_t batch_stride, int64_t chan_stride, int64_t valid_len,
                                                                    int hop, int chunk_len, int frames, int dim_f, int zero_bins,
-                                                                   int layout, float* __restrict__ spec) {
+                                                                   int layout, float* __restrict__ spec, int frame_offset, float scale) {
   extern __shared__ float2 smem[];
   const int N = st.n;
   float2* buf0 = smem;
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kFftThreads) stft_forward_kernel(FftStages st,
   const int t = blockIdx.x, b = blockIdx.y;
   const int64_t base = (int64_t)b * batch_stride;
   for (int n = threadIdx.x; n < N; n += blockDim.x) {
-    int s = t * hop + n - N / 2;
+    int s = t * hop + n - frame_offset;
     if (s < 0) s = -s;                                // reflect (torch.stft center=True, pad_mode="reflect")
     if (s >= chunk_len) s = 2 * (chunk_len - 1) - s;
     float xl = 0.f, xr = 0.f;
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(kFftThreads) stft_forward_kernel(FftStages st,
       xl = __ldg(&wave[base + s]);
       xr = __ldg(&wave[base + chan_stride + s]);
     }
-    const float w = __ldg(&window[n]);
+    const float w = __ldg(&window[n]) * scale;
     buf0[n] = make_float2(xl * w, xr * w);
   }
   __syncthreads();
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kFftThreads) stft_forward_kernel(FftStages st,
 // inverse per-frame transform: grid (frames, batch); writes windowed time frames (B,2,frames,N)
 __global__ void __launch_bounds__(kFftThreads) istft_frames_kernel(FftStages st, const float2* __restrict__ tw,
                                                                    const float* __restrict__ window, const float* __restrict__ spec,
-                                                                   int frames, int dim_f, int layout, float* __restrict__ fr) {
+                                                                   int frames, int dim_f, int layout, float* __restrict__ fr, float scale) {
   extern __shared__ float2 smem[];
   const int N = st.n;
   float2* buf0 = smem;
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(kFftThreads) istft_frames_kernel(FftStages st,
   }
   __syncthreads();
   const float2* y = fft_smem<+1>(buf0, buf1, st, tw);
-  const float inv_n = 1.0f / (float)N;
+  const float inv_n = scale / (float)N;
   float* o_l = fr + (((int64_t)b * 2 + 0) * frames + t) * N;
   float* o_r = fr + (((int64_t)b * 2 + 1) * frames + t) * N;
   for (int n = threadIdx.x; n < N; n += blockDim.x) {
@@ -241,21 +241,25 @@ __global__ void __launch_bounds__(kFftThreads) istft_frames_kernel(FftStages st,
 }
 
 // overlap-add of the windowed frames / window envelope, trimmed by N/2: (B,2,frames,N) -> (B,2,hop*(frames-1))
+// frame t sits at OLA position t*hop; output sample n is OLA position n + ola_offset.  The squared-window envelope also counts
+// `env_extra` virtual all-zero frames before frame 0 and after the last one (HTDemucs._ispec pads two such frames, htdemucs.py:405-413).
 __global__ void istft_ola_kernel(const float* __restrict__ fr, const float* __restrict__ window, int N, int hop, int frames,
-                                 int out_len, float* __restrict__ wave) {
+                                 int out_len, float* __restrict__ wave, int ola_offset, int env_extra) {
   const int bc = blockIdx.y;
   const float* f = fr + (int64_t)bc * frames * N;
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < out_len; n += gridDim.x * blockDim.x) {
-    const int m = n + N / 2;
-    int t_hi = m / hop;
-    if (t_hi > frames - 1) t_hi = frames - 1;
-    int t_lo = (m - N + hop) / hop;  // ceil((m-N+1)/hop) for m-N+1 > 0
-    if (m - N + 1 <= 0) t_lo = 0;
+    const int m = n + ola_offset;
+    // floor/ceil with negative numerators: shift by a multiple of hop
+    const int sh = (env_extra + 1) * hop;
+    int t_hi = (m + sh) / hop - (env_extra + 1);
+    int t_lo = (m - N + 1 + sh + hop - 1) / hop - (env_extra + 1);  // smallest t with t*hop + N > m
+    if (t_hi > frames - 1 + env_extra) t_hi = frames - 1 + env_extra;
+    if (t_lo < -env_extra) t_lo = -env_extra;
     float acc = 0.f, env = 0.f;
     for (int t = t_lo; t <= t_hi; ++t) {
       const int i = m - t * hop;
       const float w = __ldg(&window[i]);
-      acc += __ldg(&f[(int64_t)t * N + i]);
+      if (t >= 0 && t < frames) acc += __ldg(&f[(int64_t)t * N + i]);
       env += w * w;
     }
     wave[(int64_t)bc * out_len + n] = acc / env;
@@ -417,7 +421,28 @@ extern "C" int b200sep_stft_forward(const b200sep_stft_plan* plan, const float* 
   dim3 grid(frames, batch);
   stft_forward_kernel<<<grid, kFftThreads, fft_smem_bytes(plan->n_fft), (cudaStream_t)stream>>>(
       plan->st, plan->twiddle, plan->window, wave, batch_stride, chan_stride, valid_len, plan->hop, chunk_len, frames, dim_f, zero_bins,
-      layout, spec);
+      layout, spec, plan->n_fft / 2, 1.0f);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
+// Generalised framing: frame t covers samples [t*hop - frame_offset, +n_fft) of the chunk (reflected at its ends), `frames` is given
+// explicitly and every bin is multiplied by `scale`.  HTDemucs._spec (demucs/htdemucs.py:383-403, spec.py:11-22: normalized=True,
+// reflect pad 3*hop/2, frames 2..2+le kept, last bin dropped) is frame_offset = 3*hop/2, frames = ceil(T/hop), scale = n_fft^-1/2, dim_f = n_fft/2.
+extern "C" int b200sep_stft_forward_ex(const b200sep_stft_plan* plan, const float* wave, int64_t batch_stride, int64_t chan_stride, int64_t valid_len,
+                                       int batch, int chunk_len, int frames, int frame_offset, float scale, int dim_f, int zero_bins, int layout,
+                                       float* spec, void* stream) {
+  B2_CHECK_ARG(plan && wave && spec, "stft_forward_ex: NULL argument");
+  B2_CHECK_ARG(batch >= 0 && chunk_len > 0 && frames >= 1, "stft_forward_ex: bad sizes");
+  B2_CHECK_ARG(frame_offset >= 0 && frame_offset < chunk_len && (frames - 1) * plan->hop - frame_offset + plan->n_fft - 1 <= 2 * (chunk_len - 1),
+               "stft_forward_ex: frames reach beyond a single reflection of the chunk");
+  B2_CHECK_ARG(dim_f >= 1 && dim_f <= plan->n_fft / 2 + 1, "stft_forward_ex: dim_f=%d out of range", dim_f);
+  B2_CHECK_ARG(layout == B200SEP_LAYOUT_CFT || layout == B200SEP_LAYOUT_CTF, "stft_forward_ex: bad layout %d", layout);
+  if (batch == 0) return B200SEP_OK;
+  dim3 grid(frames, batch);
+  stft_forward_kernel<<<grid, kFftThreads, fft_smem_bytes(plan->n_fft), (cudaStream_t)stream>>>(
+      plan->st, plan->twiddle, plan->window, wave, batch_stride, chan_stride, valid_len, plan->hop, chunk_len, frames, dim_f, zero_bins, layout, spec,
+      frame_offset, scale);
   B2_LAUNCHED();
   return B200SEP_OK;
 }
@@ -438,11 +463,31 @@ extern "C" int b200sep_stft_inverse(const b200sep_stft_plan* plan, const float* 
   if (batch == 0) return B200SEP_OK;
   dim3 grid(frames, batch);
   istft_frames_kernel<<<grid, kFftThreads, fft_smem_bytes(plan->n_fft), (cudaStream_t)stream>>>(plan->st, plan->twiddle, plan->window, spec,
-                                                                                               frames, dim_f, layout, work);
+                                                                                               frames, dim_f, layout, work, 1.0f);
   B2_LAUNCHED();
   const int out_len = plan->hop * (frames - 1);
   dim3 g2(cdiv(out_len, 256), batch * 2);
-  istft_ola_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(work, plan->window, plan->n_fft, plan->hop, frames, out_len, wave);
+  istft_ola_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(work, plan->window, plan->n_fft, plan->hop, frames, out_len, wave, plan->n_fft / 2, 0);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
+// Generalised inverse: out_len samples, sample n = overlap-add position n + ola_offset, `env_extra` virtual zero frames on each side in
+// the window envelope, spectrum multiplied by `scale` first.  HTDemucs._ispec + ispectro (htdemucs.py:405-413, spec.py:25-38) is
+// ola_offset = 3*hop/2, env_extra = 2, scale = sqrt(n_fft), out_len = segment length, dim_f = n_fft/2 (Nyquist bin zero).
+extern "C" int b200sep_stft_inverse_ex(const b200sep_stft_plan* plan, const float* spec, int batch, int frames, int dim_f, int layout, int out_len,
+                                       int ola_offset, int env_extra, float scale, float* wave, float* work, void* stream) {
+  B2_CHECK_ARG(plan && spec && wave && work, "stft_inverse_ex: NULL argument");
+  B2_CHECK_ARG(frames >= 1 && out_len >= 1 && ola_offset >= 0 && env_extra >= 0, "stft_inverse_ex: bad sizes");
+  B2_CHECK_ARG(dim_f >= 1 && dim_f <= plan->n_fft / 2 + 1, "stft_inverse_ex: dim_f=%d out of range", dim_f);
+  B2_CHECK_ARG(layout == B200SEP_LAYOUT_CFT || layout == B200SEP_LAYOUT_CTF, "stft_inverse_ex: bad layout %d", layout);
+  if (batch == 0) return B200SEP_OK;
+  dim3 grid(frames, batch);
+  istft_frames_kernel<<<grid, kFftThreads, fft_smem_bytes(plan->n_fft), (cudaStream_t)stream>>>(plan->st, plan->twiddle, plan->window, spec, frames, dim_f,
+                                                                                               layout, work, scale);
+  B2_LAUNCHED();
+  dim3 g2(cdiv(out_len, 256), batch * 2);
+  istft_ola_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(work, plan->window, plan->n_fft, plan->hop, frames, out_len, wave, ola_offset, env_extra);
   B2_LAUNCHED();
   return B200SEP_OK;
 }
