@@ -239,13 +239,17 @@ int b200sep_gemm_f32(const float* A, const float* Bw, float* C, int M, int N, in
                      int64_t strideB, int64_t strideC, float alpha, const float* bias_n, const float* bias_m, int act, const float* res,
                      const float* res_scale, void* stream);
 int b200sep_softmax_rows_f32(float* x, int64_t rows, int n, void* stream);
-/* op 0: out = alpha*a + beta*b (b NULL: + beta);  op 1: out = a*b */
+/* op 0: out = alpha*a + beta*b (b NULL: + beta);  op 1: out = a*b;  with b = device {mean, std} (meanstd_f32):
+ * op 2: out = (a - mean) / (1e-5 + std);  op 3: out = a*std + mean  (htdemucs.py:501-510, :588-589, :611-612) */
 int b200sep_ew_f32(const float* a, const float* b, float* out, int64_t n, float alpha, float beta, int op, void* stream);
 /* out2[0] = mean, out2[1] = unbiased std over n elements (htdemucs.py:501-510) */
 int b200sep_meanstd_f32(const float* x, int64_t n, float* out2, void* stream);
-/* apply_model's split branch (demucs/apply.py:215-250): triangle-weighted overlap-add of segments (n_segs, channels, seg_len) at
- * stride `stride`, normalised by the summed weights -> out (channels, length) */
-int b200sep_triangle_overlap_add(const float* segs, int n_segs, int channels, int seg_len, int64_t stride, int64_t length, float* out, void* stream);
+/* apply_model's split branch (demucs/apply.py:215-250): triangle-weighted overlap-add of segments (n_segs, channels, seg_len;
+ * each already centre-trimmed to its valid length, stored from sample 0) at stride `stride` over a signal of `length` samples,
+ * normalised by the summed weights.  out (channels, n_out): out[c][n] (+)= scale * chan_scale[c] * signal[c][q0 + n]
+ * -- q0/scale/accumulate fold in the shift average (apply.py:197-214), chan_scale (nullable) the bag weights (apply.py:169-195). */
+int b200sep_triangle_overlap_add(const float* segs, int n_segs, int channels, int seg_len, int64_t stride, int64_t length, int64_t q0, int64_t n_out,
+                                 float scale, const float* chan_scale, int accumulate, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Self-tests of the tensor-core ("bf16x3 pair") operators in isolation: fp32 device tensors in, the operator runs

@@ -69,7 +69,7 @@ _SIGS = {
     "b200sep_softmax_rows_f32": (i32, [vp, i64, i32, vp]),
     "b200sep_ew_f32": (i32, [vp, vp, vp, i64, f32, f32, i32, vp]),
     "b200sep_meanstd_f32": (i32, [vp, i64, vp, vp]),
-    "b200sep_triangle_overlap_add": (i32, [vp, i32, i32, i32, i64, i64, vp, vp]),
+    "b200sep_triangle_overlap_add": (i32, [vp, i32, i32, i32, i64, i64, i64, i64, f32, vp, i32, vp, vp]),
     "b200sep_selftest_umma_gemm": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, vp]),
     "b200sep_selftest_umma_conv3x3": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, vp]),
     "b200sep_selftest_umma_updown": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp]),

@@ -1,0 +1,531 @@
+"""HTDemucs (Demucs v4) on the fp32 operator kernels of libb200sep.so.
+
+HTDemucsNet.forward replaces HTDemucs.forward (uvr_lib_v5/demucs/htdemucs.py:483-620) for the structure of the released htdemucs
+checkpoints (depth 4, no GroupNorm in the encoder/decoder layers, DConv in both, complex-as-channels, sin embeddings, norm_first +
+layer-scale + norm_out cross-transformer).  DemucsEngine replaces apply_model (demucs/apply.py:124-260) and
+DemucsSeparator.demix_demucs (architectures/demucs_separator.py:162-195).
+
+This file is the graph builder only: it owns device buffers (torch tensors = device memory, nothing else) and the ORDER of the
+operator launches; every arithmetic step is a kernel behind the C ABI (include/b200sep.h).  No CPU / ATen compute fallback.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from fractions import Fraction
+
+import numpy as np
+import torch
+
+from ._lib import LAYOUT_CFT, check, lib
+from .engine import StftPlan, _ptr, _require_cuda, _stream
+
+ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+
+
+@dataclass
+class HTDemucsConfig:
+    """Constructor arguments of HTDemucs that shape the graph (htdemucs.py:36-98); defaults = the released htdemucs models."""
+
+    sources: tuple = ("drums", "bass", "other", "vocals")
+    audio_channels: int = 2
+    channels: int = 48
+    growth: int = 2
+    nfft: int = 4096
+    depth: int = 4
+    kernel_size: int = 8
+    stride: int = 4
+    context: int = 1
+    dconv_depth: int = 2
+    dconv_comp: int = 8
+    bottom_channels: int = 512
+    t_layers: int = 5
+    t_heads: int = 8
+    t_hidden_scale: float = 4.0
+    freq_emb: float = 0.2
+    emb_scale: float = 10.0
+    samplerate: int = 44100
+    segment: Fraction = Fraction(39, 5)
+    max_period: float = 10000.0
+
+    @property
+    def hop(self):
+        return self.nfft // 4
+
+    @property
+    def seg_len(self):  # int(self.segment * self.samplerate), htdemucs.py:486
+        return int(Fraction(self.segment) * self.samplerate)
+
+    def validate(self):
+        if self.audio_channels != 2:
+            raise ValueError("the B200 HTDemucs path handles stereo models only")
+        if self.kernel_size != 8 or self.stride != 4 or self.context != 1:
+            raise ValueError("the B200 HTDemucs path needs kernel_size 8, stride 4, context 1 (the released htdemucs geometry)")
+        if self.dconv_depth != 2:
+            raise ValueError("the B200 HTDemucs path needs dconv_depth 2 (dilations 1 and 2)")
+        if self.nfft // 2 != self.stride**self.depth * (self.nfft // 2 // self.stride**self.depth):
+            raise ValueError("nfft/2 must be divisible by stride**depth")
+
+
+# --------------------------------------------------------------------------------------------------------- host-side weight prep
+def _ceil48(n):
+    return -(-n // 48) * 48
+
+
+def block_conv_weight(w: np.ndarray) -> np.ndarray:
+    """(Cout, Cin, KH, KW) -> [Cin][KH*KW][ceil48(Cout)], the layout b200sep_conv2d_f32 streams through shared memory."""
+    co, ci, kh, kw = w.shape
+    out = np.zeros((ci, kh * kw, _ceil48(co)), np.float32)
+    out[:, :, :co] = w.transpose(1, 2, 3, 0).reshape(ci, kh * kw, co)
+    return out
+
+
+def block_convtr_weight(w: np.ndarray, stride: int) -> np.ndarray:
+    """ConvTranspose weight (Cin, Cout, K) with K = 2*stride -> the 2-tap convolution over the coarse index q whose GEMM column
+    r*Cout + co produces output sample q*stride + r:   y[q*s + r] = x[q-1] . W[:, :, r + s] + x[q] . W[:, :, r]."""
+    ci, co, k = w.shape
+    assert k == 2 * stride
+    out = np.zeros((ci, 2, _ceil48(stride * co)), np.float32)
+    for r in range(stride):
+        out[:, 0, r * co : (r + 1) * co] = w[:, :, r + stride]
+        out[:, 1, r * co : (r + 1) * co] = w[:, :, r]
+    return out
+
+
+def sin_embedding_1d(length: int, dim: int, max_period: float) -> np.ndarray:
+    """create_sin_embedding (transformer.py:19-26) as (length, dim): [cos(phase) | sin(phase)]."""
+    half = dim // 2
+    pos = np.arange(length, dtype=np.float32)[:, None]
+    expo = np.arange(half, dtype=np.float32)[None, :] / np.float32(half - 1)
+    phase = pos / np.power(np.float32(max_period), expo, dtype=np.float32)
+    return np.concatenate([np.cos(phase), np.sin(phase)], axis=1).astype(np.float32)
+
+
+def sin_embedding_2d_tokens(dim: int, height: int, width: int, max_period: float) -> np.ndarray:
+    """create_2d_sin_embedding (transformer.py:29-49) already rearranged "c fr t -> (t fr) c": (width*height, dim).
+    First half of the channels encodes the width (time) position, second half the height (frequency) position, sin/cos interleaved."""
+    half = dim // 2
+    div = np.exp(np.arange(0, half, 2, dtype=np.float32) * np.float32(-(math.log(max_period) / half))).astype(np.float32)
+    pw = np.arange(width, dtype=np.float32)[:, None] * div[None, :]   # (width, half/2)
+    ph = np.arange(height, dtype=np.float32)[:, None] * div[None, :]  # (height, half/2)
+    pe = np.zeros((width, height, dim), np.float32)
+    pe[:, :, 0:half:2] = np.sin(pw)[:, None, :]
+    pe[:, :, 1:half:2] = np.cos(pw)[:, None, :]
+    pe[:, :, half::2] = np.sin(ph)[None, :, :]
+    pe[:, :, half + 1 :: 2] = np.cos(ph)[None, :, :]
+    return pe.reshape(width * height, dim)
+
+
+# --------------------------------------------------------------------------------------------------------- operator wrappers
+def _new(shape, like=None, device=None):
+    return torch.empty(shape, dtype=torch.float32, device=like.device if like is not None else device)
+
+
+def conv2d(x, wb, bias, cout, k, s=(1, 1), p=(0, 0), dw=1, act=ACT_NONE, add=None, add_before_act=False, out_hw=None):
+    """x (B,Cin,H,W) -> (B,cout,Ho,Wo);  out_hw overrides the implied output size (right/bottom zero padding is implicit)."""
+    B, cin, H, W = x.shape
+    if out_hw is None:
+        Ho = (H + 2 * p[0] - k[0]) // s[0] + 1
+        Wo = (W + 2 * p[1] - dw * (k[1] - 1) - 1) // s[1] + 1
+    else:
+        Ho, Wo = out_hw
+    y = _new((B, cout, Ho, Wo), x)
+    check(lib.b200sep_conv2d_f32(_ptr(x), _ptr(wb), _ptr(bias) if bias is not None else None, _ptr(add) if add is not None else None, _ptr(y), B, cin, H, W, cout,
+                                 Ho, Wo, k[0], k[1], s[0], s[1], p[0], p[1], dw, act, int(add_before_act), 0, 1, 0, 0, _stream()), "conv2d_f32")
+    return y
+
+
+def conv_transpose(x, wb, bias, cout, axis, stride, trim, out_len, act=ACT_NONE):
+    """nn.ConvTranspose1d/2d with kernel 2*stride along `axis` (1 = H, 2 = W), output cropped to [trim, trim + out_len)."""
+    B, cin, H, W = x.shape
+    if axis == 1:
+        y = _new((B, cout, out_len, W), x)
+        k, p, hw = (2, 1), (1, 0), (H + 1, W)
+    else:
+        y = _new((B, cout, H, out_len), x)
+        k, p, hw = (1, 2), (0, 1), (H, W + 1)
+    check(lib.b200sep_conv2d_f32(_ptr(x), _ptr(wb), _ptr(bias), None, _ptr(y), B, cin, H, W, stride * cout, hw[0], hw[1], k[0], k[1], 1, 1, p[0], p[1], 1, act, 0,
+                                 axis, stride, trim, out_len, _stream()), "conv2d_f32(transposed)")
+    return y
+
+
+def groupnorm1(x, gamma, beta, act=ACT_NONE, channel_last=False):
+    """in place; x (B,C,Fr,L) channel-first (one sample per (b, fr)) or (B,L,C) channel_last."""
+    if channel_last:
+        B, L, Cc = x.shape
+        Fr = 1
+    else:
+        B, Cc, Fr, L = x.shape
+    check(lib.b200sep_groupnorm1_f32(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(x), B, Cc, Fr, L, act, int(channel_last), _stream()), "groupnorm1_f32")
+    return x
+
+
+def glu(a, res=None, scale=None):
+    B, c2, H, W = a.shape
+    y = _new((B, c2 // 2, H, W), a)
+    check(lib.b200sep_glu_f32(_ptr(a), _ptr(res) if res is not None else None, _ptr(scale) if scale is not None else None, _ptr(y), B, c2 // 2, H * W, _stream()), "glu_f32")
+    return y
+
+
+def layernorm(x, gamma, beta):
+    y = torch.empty_like(x)
+    check(lib.b200sep_layernorm_f32(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), x.numel() // x.shape[-1], x.shape[-1], _stream()), "layernorm_f32")
+    return y
+
+
+def ew(a, b, out, alpha=1.0, beta=1.0, op=0):
+    check(lib.b200sep_ew_f32(_ptr(a), _ptr(b) if b is not None else None, _ptr(out), a.numel(), alpha, beta, op, _stream()), "ew_f32")
+    return out
+
+
+def linear(x2d, w, bias, act=ACT_NONE, res=None, res_scale=None):
+    """(M,K) @ w(N,K)^T + bias -> (M,N); optional res + res_scale[n] * (.)"""
+    M, K = x2d.shape
+    N = w.shape[0]
+    y = _new((M, N), x2d)
+    check(lib.b200sep_gemm_f32(_ptr(x2d), _ptr(w), _ptr(y), M, N, K, K, K, N, 1, 0, 0, 0, 1.0, _ptr(bias) if bias is not None else None, None, act,
+                               _ptr(res) if res is not None else None, _ptr(res_scale) if res_scale is not None else None, _stream()), "gemm_f32")
+    return y
+
+
+def _gemm_raw(a_ptr, b_ptr, c_ptr, M, N, K, lda, ldb, ldc, batch, sA, sB, sC, alpha=1.0, bias_n=None, bias_m=None):
+    check(lib.b200sep_gemm_f32(a_ptr, b_ptr, c_ptr, M, N, K, lda, ldb, ldc, batch, sA, sB, sC, alpha, bias_n, bias_m, 0, None, None, _stream()), "gemm_f32")
+
+
+# --------------------------------------------------------------------------------------------------------- the network
+class HTDemucsNet:
+    """Device-resident HTDemucs weights (re-blocked for the conv kernel) + the launch sequence of one forward."""
+
+    def __init__(self, cfg: HTDemucsConfig, state: dict, device="cuda:0"):
+        _require_cuda()
+        cfg.validate()
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.S = len(cfg.sources)
+        self.stft = StftPlan(cfg.nfft, cfg.hop)
+        self.W = {}
+        st = {k: np.asarray(v, dtype=np.float32) for k, v in state.items()}
+        self._check_structure(st)
+        for name, a in st.items():
+            if name.endswith("conv_tr.weight"):
+                a = block_convtr_weight(a.reshape(a.shape[0], a.shape[1], cfg.kernel_size), cfg.stride)
+            elif name.endswith(".weight") and a.ndim >= 3 and "crosstransformer" not in name:
+                if name.startswith(("encoder.", "decoder.")) and a.ndim == 4:
+                    a = block_conv_weight(a)  # (co, ci, K, 1) freq conv / (co, ci, 3, 3) rewrite / (co, ci, 1, 1)
+                else:  # Conv1d (co, ci, k) -> kernel (1, k)
+                    a = block_conv_weight(a.reshape(a.shape[0], a.shape[1], 1, a.shape[2]))
+            self.W[name] = torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+        # ScaledEmbedding.forward * freq_emb weight (hdemucs.py:62-64, htdemucs.py:539-541): added after encoder 0, shape (C, Fr)
+        emb = st["freq_emb.embedding.weight"] * np.float32(cfg.emb_scale)  # (Fr, C)
+        self.freq_emb_t = torch.from_numpy(np.ascontiguousarray((np.float32(cfg.freq_emb) * emb).T)).to(self.device)
+        self._pe_cache = {}
+        self._emb_cache = {}
+
+    def _check_structure(self, st):
+        cfg = self.cfg
+        need = ["encoder.0.conv.weight", "tencoder.0.conv.weight", "decoder.0.conv_tr.weight", "tdecoder.0.conv_tr.weight", "freq_emb.embedding.weight",
+                "encoder.0.dconv.layers.1.6.scale", "crosstransformer.norm_in.weight", "crosstransformer.layers.0.norm_out.weight",
+                "crosstransformer.layers.0.gamma_1.scale"]
+        for n in need:
+            if n not in st:
+                raise ValueError(f"state dict lacks {n}: not an htdemucs-v4 checkpoint of the supported structure")
+        for n in st:
+            if ".norm1.weight" in n and n.startswith(("encoder", "decoder", "tencoder", "tdecoder")):
+                raise ValueError("encoder/decoder GroupNorm layers (norm_starts < depth) are not supported")
+        if f"encoder.{cfg.depth - 1}.conv.weight" not in st or f"encoder.{cfg.depth}.conv.weight" in st:
+            raise ValueError(f"state dict does not have depth {cfg.depth}")
+        if st["encoder.0.conv.weight"].shape[0] != cfg.channels:
+            raise ValueError("config.channels does not match the checkpoint")
+
+    # ---- sub-graphs --------------------------------------------------------------------------------------------
+    def _dconv(self, x, prefix):
+        """DConv.forward (demucs.py:166-168) on x (B,C,Fr,T): conv1d k3 dilated -> GroupNorm(1)+GELU -> 1x1 -> GroupNorm(1) -> GLU, LayerScale residual."""
+        W = self.W
+        C_ = x.shape[1]
+        for d in range(self.cfg.dconv_depth):
+            p = f"{prefix}.dconv.layers.{d}"
+            dil = 2**d
+            hid = W[f"{p}.0.bias"].numel()
+            h = conv2d(x, W[f"{p}.0.weight"], W[f"{p}.0.bias"], hid, (1, 3), p=(0, dil), dw=dil)
+            groupnorm1(h, W[f"{p}.1.weight"], W[f"{p}.1.bias"], ACT_GELU)
+            h = conv2d(h, W[f"{p}.3.weight"], W[f"{p}.3.bias"], 2 * C_, (1, 1))
+            groupnorm1(h, W[f"{p}.4.weight"], W[f"{p}.4.bias"])
+            x = glu(h, res=x, scale=W[f"{p}.6.scale"])
+        return x
+
+    def _enc(self, x, prefix, freq):
+        """HEncLayer.forward (hdemucs.py:119-153), norm = Identity, empty = False."""
+        W, cfg = self.W, self.cfg
+        co = W[f"{prefix}.conv.bias"].numel()
+        if freq:
+            y = conv2d(x, W[f"{prefix}.conv.weight"], W[f"{prefix}.conv.bias"], co, (cfg.kernel_size, 1), s=(cfg.stride, 1), p=(cfg.kernel_size // 4, 0), act=ACT_GELU)
+        else:
+            le = x.shape[-1]
+            y = conv2d(x, W[f"{prefix}.conv.weight"], W[f"{prefix}.conv.bias"], co, (1, cfg.kernel_size), s=(1, cfg.stride), p=(0, cfg.kernel_size // 4), act=ACT_GELU,
+                       out_hw=(1, -(-le // cfg.stride)))  # F.pad to a multiple of the stride == implicit zero columns on the right
+        y = self._dconv(y, prefix)
+        z = conv2d(y, W[f"{prefix}.rewrite.weight"], W[f"{prefix}.rewrite.bias"], 2 * co, (1, 1))
+        return glu(z)
+
+    def _dec(self, x, skip, length, prefix, freq, last):
+        """HDecLayer.forward (hdemucs.py:299-330), norm = Identity, empty = False."""
+        W, cfg = self.W, self.cfg
+        ci = x.shape[1]
+        x = ew(x, skip, _new(x.shape, x))
+        if freq:
+            y = glu(conv2d(x, W[f"{prefix}.rewrite.weight"], W[f"{prefix}.rewrite.bias"], 2 * ci, (3, 3), p=(1, 1)))
+        else:
+            y = glu(conv2d(x, W[f"{prefix}.rewrite.weight"], W[f"{prefix}.rewrite.bias"], 2 * ci, (1, 3), p=(0, 1)))
+        y = self._dconv(y, prefix)
+        co = W[f"{prefix}.conv_tr.bias"].numel()
+        act = ACT_NONE if last else ACT_GELU
+        if freq:
+            return conv_transpose(y, W[f"{prefix}.conv_tr.weight"], W[f"{prefix}.conv_tr.bias"], co, 1, cfg.stride, cfg.kernel_size // 4, y.shape[2] * cfg.stride, act)
+        return conv_transpose(y, W[f"{prefix}.conv_tr.weight"], W[f"{prefix}.conv_tr.bias"], co, 2, cfg.stride, cfg.kernel_size // 4, length, act)
+
+    def _mha(self, q_in, kv_in, p, res, res_scale):
+        """nn.MultiheadAttention(batch_first) + the layer-scaled residual: res + gamma * out_proj(softmax(QK^T/sqrt(hd)) V).  q_in (B,Lq,D), kv_in (B,Lk,D)."""
+        W = self.W
+        B, Lq, D = q_in.shape
+        Lk = kv_in.shape[1]
+        H = self.cfg.t_heads
+        hd = D // H
+        Wi, bi = W[f"{p}.in_proj_weight"], W[f"{p}.in_proj_bias"]
+        q = linear(q_in.view(B * Lq, D), Wi[:D], bi[:D])
+        k = linear(kv_in.view(B * Lk, D), Wi[D : 2 * D], bi[D : 2 * D])
+        # V^T per batch: (D, Lk) = Wv (D,D) @ kv^T, bias per row
+        vt = _new((B, D, Lk), q_in)
+        wv, bv = Wi[2 * D :], bi[2 * D :]
+        _gemm_raw(_ptr(wv), _ptr(kv_in), _ptr(vt), D, Lk, D, D, D, Lk, B, 0, Lk * D, D * Lk, bias_m=_ptr(bv))
+        o = _new((B, Lq, D), q_in)
+        sc = _new((H, Lq, Lk), q_in)
+        fs = 4  # bytes per float
+        for b in range(B):
+            _gemm_raw(q.data_ptr() + b * Lq * D * fs, k.data_ptr() + b * Lk * D * fs, _ptr(sc), Lq, Lk, hd, D, D, Lk, H, hd, hd, Lq * Lk, alpha=1.0 / math.sqrt(hd))
+            check(lib.b200sep_softmax_rows_f32(_ptr(sc), H * Lq, Lk, _stream()), "softmax_rows_f32")
+            _gemm_raw(_ptr(sc), vt.data_ptr() + b * D * Lk * fs, o.data_ptr() + b * Lq * D * fs, Lq, hd, Lk, Lk, Lk, D, H, Lq * Lk, hd * Lk, hd)
+        y = linear(o.view(B * Lq, D), W[f"{p}.out_proj.weight"], W[f"{p}.out_proj.bias"], res=res.view(B * Lq, D), res_scale=res_scale)
+        return y.view(B, Lq, D)
+
+    def _ffn(self, x_norm, x, p):
+        W = self.W
+        B, L, D = x.shape
+        h = linear(x_norm.view(B * L, D), W[f"{p}.linear1.weight"], W[f"{p}.linear1.bias"], act=ACT_GELU)
+        return linear(h, W[f"{p}.linear2.weight"], W[f"{p}.linear2.bias"], res=x.view(B * L, D), res_scale=W[f"{p}.gamma_2.scale"]).view(B, L, D)
+
+    def _self_layer(self, x, p):  # MyTransformerEncoderLayer.forward, norm_first (transformer.py:268-274)
+        W = self.W
+        n1 = layernorm(x, W[f"{p}.norm1.weight"], W[f"{p}.norm1.bias"])
+        x = self._mha(n1, n1, f"{p}.self_attn", x, W[f"{p}.gamma_1.scale"])
+        x = self._ffn(layernorm(x, W[f"{p}.norm2.weight"], W[f"{p}.norm2.bias"]), x, p)
+        return groupnorm1(x, W[f"{p}.norm_out.weight"], W[f"{p}.norm_out.bias"], channel_last=True)
+
+    def _cross_layer(self, q, k, p):  # CrossTransformerEncoderLayer.forward, norm_first (transformer.py:385-390)
+        W = self.W
+        x = self._mha(layernorm(q, W[f"{p}.norm1.weight"], W[f"{p}.norm1.bias"]), layernorm(k, W[f"{p}.norm2.weight"], W[f"{p}.norm2.bias"]), f"{p}.cross_attn", q,
+                      W[f"{p}.gamma_1.scale"])
+        x = self._ffn(layernorm(x, W[f"{p}.norm3.weight"], W[f"{p}.norm3.bias"]), x, p)
+        return groupnorm1(x, W[f"{p}.norm_out.weight"], W[f"{p}.norm_out.bias"], channel_last=True)
+
+    def _pos(self, kind, *dims):
+        key = (kind,) + dims
+        if key not in self._pe_cache:
+            a = sin_embedding_2d_tokens(*dims, self.cfg.max_period) if kind == "2d" else sin_embedding_1d(*dims, self.cfg.max_period)
+            self._pe_cache[key] = torch.from_numpy(a).to(self.device)
+        return self._pe_cache[key]
+
+    def _transformer(self, x, xt):
+        """channel up-samplers + CrossTransformerEncoder.forward + channel down-samplers (htdemucs.py:546-560, transformer.py:529-560)."""
+        W, cfg = self.W, self.cfg
+        B, c0, Fr, T1 = x.shape
+        if cfg.bottom_channels:
+            D = cfg.bottom_channels
+            x = conv2d(x.view(B, c0, 1, Fr * T1), W["channel_upsampler.weight"], W["channel_upsampler.bias"], D, (1, 1)).view(B, D, Fr, T1)
+            xt = conv2d(xt, W["channel_upsampler_t.weight"], W["channel_upsampler_t.bias"], D, (1, 1))
+        D = x.shape[1]
+        T2 = xt.shape[-1]
+        xs = _new((B, T1, Fr, D), x)  # "b c fr t1 -> b (t1 fr) c"
+        check(lib.b200sep_permute4_f32(_ptr(x), _ptr(xs), B, D, Fr, T1, 0, 3, 2, 1, _stream()), "permute4_f32")
+        xs = layernorm(xs.view(B, T1 * Fr, D), W["crosstransformer.norm_in.weight"], W["crosstransformer.norm_in.bias"])
+        pe2 = self._pos("2d", D, Fr, T1)
+        for b in range(B):
+            ew(xs[b], pe2, xs[b])
+        xts = _new((B, T2, 1, D), x)  # "b c t2 -> b t2 c"
+        check(lib.b200sep_permute4_f32(_ptr(xt), _ptr(xts), B, D, 1, T2, 0, 3, 2, 1, _stream()), "permute4_f32")
+        xts = layernorm(xts.view(B, T2, D), W["crosstransformer.norm_in_t.weight"], W["crosstransformer.norm_in_t.bias"])
+        pe1 = self._pos("1d", T2, D)
+        for b in range(B):
+            ew(xts[b], pe1, xts[b])
+        for li in range(cfg.t_layers):
+            pf, pt = f"crosstransformer.layers.{li}", f"crosstransformer.layers_t.{li}"
+            if li % 2 == 0:
+                xs = self._self_layer(xs, pf)
+                xts = self._self_layer(xts, pt)
+            else:
+                old = xs
+                xs = self._cross_layer(xs, xts, pf)
+                xts = self._cross_layer(xts, old, pt)
+        x = _new((B, D, Fr, T1), xs)
+        check(lib.b200sep_permute4_f32(_ptr(xs), _ptr(x), B, T1, Fr, D, 0, 3, 2, 1, _stream()), "permute4_f32")
+        xt = _new((B, D, 1, T2), xs)
+        check(lib.b200sep_permute4_f32(_ptr(xts), _ptr(xt), B, T2, 1, D, 0, 3, 2, 1, _stream()), "permute4_f32")
+        if cfg.bottom_channels:
+            x = conv2d(x.view(B, D, 1, Fr * T1), W["channel_downsampler.weight"], W["channel_downsampler.bias"], c0, (1, 1)).view(B, c0, Fr, T1)
+            xt = conv2d(xt, W["channel_downsampler_t.weight"], W["channel_downsampler_t.bias"], c0, (1, 1))
+        return x, xt
+
+    # ---- forward ---------------------------------------------------------------------------------------------------
+    def forward(self, mix: torch.Tensor) -> torch.Tensor:
+        """mix (B, 2, L <= seg_len) float32 cuda -> (B, S, 2, L).  (eval mode, use_train_segment: shorter inputs are zero-padded
+        to the training segment and the output is cut back, htdemucs.py:486-493, :614-618.)"""
+        cfg, S = self.cfg, self.S
+        assert mix.dim() == 3 and mix.shape[1] == 2 and mix.dtype == torch.float32 and mix.is_cuda
+        B, _, L0 = mix.shape
+        T_len = cfg.seg_len
+        if L0 > T_len:
+            raise ValueError(f"segment of {L0} samples exceeds the training segment {T_len}")
+        if L0 < T_len:
+            mp = torch.zeros((B, 2, T_len), dtype=torch.float32, device=mix.device)
+            mp[..., :L0].copy_(mix)
+        else:
+            mp = mix.contiguous()
+        hl, nfft = cfg.hop, cfg.nfft
+        le = -(-T_len // hl)
+        Fq = nfft // 2
+        # _spec + _magnitude (htdemucs.py:383-403, :415-424): normalized STFT, frames 2..2+le of the 3*hop/2-reflect-padded signal, bins 0..nfft/2-1
+        spec = _new((B, 4, Fq, le), mp)
+        check(lib.b200sep_stft_forward_ex(self.stft.handle, _ptr(mp), 2 * T_len, T_len, 0, B, T_len, le, hl // 2 * 3, 1.0 / math.sqrt(nfft), Fq, 0, LAYOUT_CFT,
+                                          _ptr(spec), _stream()), "stft_forward_ex")
+        stats = _new((B, 4), mp)  # per sample: mean, std of the spectrogram; mean, std of the waveform
+        x = _new(spec.shape, mp)
+        xt = _new((B, 2, 1, T_len), mp)
+        fs = 4
+        for b in range(B):
+            check(lib.b200sep_meanstd_f32(_ptr(spec[b]), spec[b].numel(), stats.data_ptr() + (4 * b) * fs, _stream()), "meanstd_f32")
+            check(lib.b200sep_meanstd_f32(_ptr(mp[b]), mp[b].numel(), stats.data_ptr() + (4 * b + 2) * fs, _stream()), "meanstd_f32")
+            check(lib.b200sep_ew_f32(_ptr(spec[b]), stats.data_ptr() + (4 * b) * fs, _ptr(x[b]), spec[b].numel(), 1.0, 0.0, 2, _stream()), "ew_f32")
+            check(lib.b200sep_ew_f32(_ptr(mp[b]), stats.data_ptr() + (4 * b + 2) * fs, _ptr(xt[b]), mp[b].numel(), 1.0, 0.0, 2, _stream()), "ew_f32")
+        saved, saved_t, lengths_t = [], [], []
+        for i in range(cfg.depth):  # htdemucs.py:520-544 (every time encoder runs: no "empty" layers at depth 4)
+            lengths_t.append(xt.shape[-1])
+            xt = self._enc(xt, f"tencoder.{i}", False)
+            saved_t.append(xt)
+            x = self._enc(x, f"encoder.{i}", True)
+            if i == 0:
+                Bc, Cc, Fr, Tt = x.shape
+                emb = self._freq_emb_full(Fr, Tt, Cc)
+                for b in range(B):
+                    ew(x[b], emb, x[b])
+            saved.append(x)
+        if cfg.t_layers:
+            x, xt = self._transformer(x, xt)
+        for j in range(cfg.depth):  # :562-580
+            last = j == cfg.depth - 1
+            x = self._dec(x, saved.pop(-1), 0, f"decoder.{j}", True, last)
+            xt = self._dec(xt, saved_t.pop(-1), lengths_t.pop(-1), f"tdecoder.{j}", False, last)
+        # x (B, S*4, Fq, le) * std + mean -> _mask (cac) -> _ispec (:405-413): iSTFT with the Nyquist bin and two frames per side zero
+        out = _new((B, S, 2, T_len), mp)
+        nwork = lib.b200sep_stft_inverse_work_floats(self.stft.handle, S, le, Fq, LAYOUT_CFT)
+        work = _new((nwork,), mp)
+        xi = _new((S, 2, T_len), mp)
+        for b in range(B):
+            check(lib.b200sep_ew_f32(_ptr(x[b]), stats.data_ptr() + (4 * b) * fs, _ptr(x[b]), x[b].numel(), 1.0, 0.0, 3, _stream()), "ew_f32")
+            check(lib.b200sep_stft_inverse_ex(self.stft.handle, _ptr(x[b]), S, le, Fq, LAYOUT_CFT, T_len, hl // 2 * 3, 2, math.sqrt(nfft), _ptr(xi), _ptr(work), _stream()),
+                  "stft_inverse_ex")
+            check(lib.b200sep_ew_f32(_ptr(xt[b]), stats.data_ptr() + (4 * b + 2) * fs, _ptr(out[b]), xt[b].numel(), 1.0, 0.0, 3, _stream()), "ew_f32")
+            ew(out[b], xi, out[b])
+        return out[..., :L0] if L0 < T_len else out
+
+    def _freq_emb_full(self, Fr, Tt, Cc):
+        """freq_emb * emb broadcast over time, (C, Fr, T) -- materialised once per shape so the add is a plain element-wise kernel."""
+        key = (Fr, Tt, Cc)
+        if key not in self._emb_cache:
+            self._emb_cache[key] = self.freq_emb_t[:, :, None].expand(Cc, Fr, Tt).contiguous()
+        return self._emb_cache[key]
+
+    __call__ = forward
+
+
+# --------------------------------------------------------------------------------------------------------- apply_model / demix
+class DemucsEngine:
+    """apply_model(shifts, split=True, overlap) over a bag of HTDemucs models + DemucsSeparator.demix_demucs, device resident."""
+
+    def __init__(self, nets, bag_weights=None, overlap=0.25, batch_size=4):
+        _require_cuda()
+        self.nets = list(nets)
+        cfg = self.nets[0].cfg
+        self.cfg = cfg
+        S = len(cfg.sources)
+        if bag_weights is None:
+            bag_weights = [[1.0] * S for _ in self.nets]  # BagOfModels default (apply.py:52-57)
+        assert len(bag_weights) == len(self.nets) and all(len(w) == S for w in bag_weights)
+        self.bag_weights = [list(map(float, w)) for w in bag_weights]
+        self.overlap = float(overlap)
+        self.batch_size = int(batch_size)
+        self.device = self.nets[0].device
+
+    def _apply_split(self, net, tensor, offset, length, out, q0, n_out, scale, chan_scale, accumulate):
+        """apply_model's split branch on TensorChunk(tensor, offset, length) (apply.py:215-250); the weighted result's samples
+        [q0, q0 + n_out) are scaled and written / accumulated into out (S*2, n_out)."""
+        cfg = self.cfg
+        seg = cfg.seg_len
+        S = len(cfg.sources)
+        stride = int((1 - self.overlap) * seg)
+        total = tensor.shape[-1]
+        offs = list(range(0, length, stride))
+        ext = torch.zeros((2, total + 2 * seg), dtype=torch.float32, device=tensor.device)  # TensorChunk.padded zero-fills outside the tensor (apply.py:97-113)
+        ext[:, seg : seg + total].copy_(tensor)
+        segs = torch.zeros((len(offs), S * 2, seg), dtype=torch.float32, device=tensor.device)
+        for i0 in range(0, len(offs), self.batch_size):
+            group = offs[i0 : i0 + self.batch_size]
+            batch = _new((len(group), 2, seg), tensor)
+            clens = []
+            for j, off in enumerate(group):
+                clen = min(length - off, seg)
+                start = offset + off - (seg - clen) // 2
+                batch[j].copy_(ext[:, seg + start : seg + start + seg])
+                clens.append(clen)
+            y = net.forward(batch)  # (n, S, 2, seg)
+            for j, clen in enumerate(clens):  # center_trim to the chunk's valid length (apply.py:258), stored from sample 0
+                d = (seg - clen) // 2
+                segs[i0 + j, :, :clen].copy_(y[j].reshape(S * 2, seg)[:, d : d + clen])
+        check(lib.b200sep_triangle_overlap_add(_ptr(segs), len(offs), S * 2, seg, stride, length, q0, n_out, scale, _ptr(chan_scale) if chan_scale is not None else None,
+                                               int(accumulate), _ptr(out), _stream()), "triangle_overlap_add")
+
+    def apply_model(self, mix: torch.Tensor, shift_offsets, net_index=0, out=None, chan_scale=None, accumulate=False):
+        """mix (2, N) cuda -> (S*2, N).  shift_offsets: the `random.randint(0, max_shift)` draws of apply.py:207 (empty = shifts 0)."""
+        net = self.nets[net_index]
+        S = len(self.cfg.sources)
+        N = mix.shape[-1]
+        if out is None:
+            out = _new((S * 2, N), mix)
+        if not shift_offsets:
+            self._apply_split(net, mix, 0, N, out, 0, N, 1.0, chan_scale, accumulate)
+            return out
+        ms = int(0.5 * self.cfg.samplerate)
+        pm = torch.zeros((2, N + 2 * ms), dtype=torch.float32, device=mix.device)
+        pm[:, ms : ms + N].copy_(mix)
+        for i, o in enumerate(shift_offsets):
+            self._apply_split(net, pm, o, N + ms - o, out, ms - o, N, 1.0 / len(shift_offsets), chan_scale, accumulate or i > 0)
+        return out
+
+    def demix(self, mix: np.ndarray, shift_offsets) -> np.ndarray:
+        """DemucsSeparator.demix_demucs (demucs_separator.py:162-195): mix (2, N) host -> sources (S, 2, N) host, sources 0/1 swapped.
+        shift_offsets: one list of shift draws per model of the bag."""
+        S = len(self.cfg.sources)
+        mix_d = torch.from_numpy(np.ascontiguousarray(mix, dtype=np.float32)).to(self.device)
+        N = mix_d.shape[1]
+        ref = ew(mix_d[0], mix_d[1], _new((N,), mix_d), 0.5, 0.5)
+        stats = _new((2,), mix_d)
+        check(lib.b200sep_meanstd_f32(_ptr(ref), N, _ptr(stats), _stream()), "meanstd_f32")
+        mean, std = (float(v) for v in stats.cpu())
+        mn = ew(mix_d, None, _new(mix_d.shape, mix_d), 1.0 / std, -mean / std)
+        tot = np.sum(np.asarray(self.bag_weights, np.float64), axis=0)
+        out = _new((S * 2, N), mix_d)
+        for mi in range(len(self.nets)):
+            cs = torch.tensor(np.repeat(np.asarray(self.bag_weights[mi]) / tot, 2).astype(np.float32), device=self.device)
+            self.apply_model(mn, list(shift_offsets[mi]), mi, out, cs, accumulate=mi > 0)
+        ew(out, None, out, std, mean)
+        src = out.view(S, 2, N).cpu().numpy()
+        src[[0, 1]] = src[[1, 0]]
+        return src

@@ -240,11 +240,19 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ x
   for (int i = threadIdx.x; i < n; i += blockDim.x) r[i] *= inv;
 }
 
-// out = alpha * a + beta * b (b may be null) ; op 1: out = a * b
+// op 0: out = alpha * a + beta * b (b may be null: + beta);  op 1: out = a * b;
+// op 2: out = (a - b[0]) / (1e-5 + b[1]);  op 3: out = a * b[1] + b[0]   (b = device {mean, std}; htdemucs.py:501-510, :588-589, :611-612)
 __global__ void ew_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int64_t n, float alpha, float beta, int op) {
+  float m = 0.f, sd = 0.f;
+  if (op >= 2) {
+    m = __ldg(&b[0]);
+    sd = __ldg(&b[1]);
+  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float v;
     if (op == 1) v = a[i] * b[i];
+    else if (op == 2) v = (a[i] - m) / (1e-5f + sd);
+    else if (op == 3) v = a[i] * sd + m;
     else v = alpha * a[i] + (b ? beta * b[i] : beta);
     out[i] = v;
   }
@@ -283,10 +291,15 @@ __global__ void __launch_bounds__(1024) meanstd_kernel(const float* __restrict__
 
 // apply_model's split branch (demucs/apply.py:215-250) as a gather: out[c][q] = sum_i w[q - o_i] * seg_i[c][q - o_i] / sum_i w[q - o_i],
 // segments i start at o_i = i * stride, have `seg_len` samples except the last (clipped at `length`); triangle weight of `seg_len`.
-__global__ void tri_ola_kernel(const float* __restrict__ segs, int n_segs, int channels, int seg_len, int64_t stride, int64_t length, float* __restrict__ out) {
+// Output sample n of channel c is position q = q0 + n of the overlap-added signal, times scale * chan_scale[c]; `accumulate` adds to out
+// (the shift-trick average, apply.py:197-214, and the per-source bag weights, apply.py:169-195, folded into the same pass).
+__global__ void tri_ola_kernel(const float* __restrict__ segs, int n_segs, int channels, int seg_len, int64_t stride, int64_t length, int64_t q0, int64_t n_out,
+                               float scale, const float* __restrict__ chan_scale, int accumulate, float* __restrict__ out) {
   const int c = blockIdx.y;
   const float wmax = (float)(seg_len - seg_len / 2 > seg_len / 2 ? seg_len - seg_len / 2 : seg_len / 2);
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < length; q += (int64_t)gridDim.x * blockDim.x) {
+  const float sc = scale * (chan_scale ? __ldg(&chan_scale[c]) : 1.f);
+  for (int64_t n_o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n_o < n_out; n_o += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t q = q0 + n_o;
     int64_t i_hi = q / stride;
     if (i_hi > n_segs - 1) i_hi = n_segs - 1;
     int64_t i_lo = (q - seg_len + 1 <= 0) ? 0 : (q - seg_len + stride) / stride;
@@ -297,7 +310,9 @@ __global__ void tri_ola_kernel(const float* __restrict__ segs, int n_segs, int c
       acc += w * __ldg(&segs[((int64_t)i * channels + c) * seg_len + n]);
       sw += w;
     }
-    out[(int64_t)c * length + q] = acc / sw;
+    const int64_t o = (int64_t)c * n_out + n_o;
+    const float v = sc * (acc / sw);
+    out[o] = accumulate ? out[o] + v : v;
   }
 }
 
@@ -362,7 +377,7 @@ extern "C" int b200sep_softmax_rows_f32(float* x, int64_t rows, int n, void* str
 }
 
 extern "C" int b200sep_ew_f32(const float* a, const float* b, float* out, int64_t n, float alpha, float beta, int op, void* stream) {
-  B2_CHECK_ARG(a && out && n >= 0 && (op != 1 || b), "ew_f32: bad argument");
+  B2_CHECK_ARG(a && out && n >= 0 && op >= 0 && op <= 3 && (op == 0 || b), "ew_f32: bad argument");
   if (n == 0) return B200SEP_OK;
   ew_kernel<<<(int)std::min<int64_t>(cdiv(n, 256), kNumSMs * 16), 256, 0, (cudaStream_t)stream>>>(a, b, out, n, alpha, beta, op);
   B2_LAUNCHED();
@@ -376,10 +391,14 @@ extern "C" int b200sep_meanstd_f32(const float* x, int64_t n, float* out2, void*
   return B200SEP_OK;
 }
 
-extern "C" int b200sep_triangle_overlap_add(const float* segs, int n_segs, int channels, int seg_len, int64_t stride, int64_t length, float* out, void* stream) {
+extern "C" int b200sep_triangle_overlap_add(const float* segs, int n_segs, int channels, int seg_len, int64_t stride, int64_t length, int64_t q0, int64_t n_out,
+                                            float scale, const float* chan_scale, int accumulate, float* out, void* stream) {
   B2_CHECK_ARG(segs && out && n_segs >= 1 && channels >= 1 && seg_len >= 2 && stride >= 1 && length >= 1, "triangle_overlap_add: bad argument");
-  dim3 grid((unsigned)std::min<int64_t>(cdiv(length, 256), kNumSMs * 8), channels);
-  tri_ola_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(segs, n_segs, channels, seg_len, stride, length, out);
+  B2_CHECK_ARG(q0 >= 0 && n_out >= 1 && q0 + n_out <= length, "triangle_overlap_add: output range [%lld, %lld) outside the signal of %lld samples",
+               (long long)q0, (long long)(q0 + n_out), (long long)length);
+  B2_CHECK_ARG((int64_t)(n_segs - 1) * stride < length, "triangle_overlap_add: more segments than the signal holds");
+  dim3 grid((unsigned)std::min<int64_t>(cdiv(n_out, 256), kNumSMs * 8), channels);
+  tri_ola_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(segs, n_segs, channels, seg_len, stride, length, q0, n_out, scale, chan_scale, accumulate, out);
   B2_LAUNCHED();
   return B200SEP_OK;
 }
