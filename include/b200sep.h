@@ -224,9 +224,11 @@ int b200sep_conv2d_f32(const float* x, const float* w_blocked, const float* bias
                        int trim, int out_len, void* stream);
 /* nn.GroupNorm(1, C), affine, optional activation (demucs.py:141,144).  Channel-first x (B, C, Fr, L): one sample per (b, fr) row
  * (Fr = 1: (B, C, L); Fr > 1: DConv on every frequency row without the permute of hdemucs.py:141-146); channel_last: x (B, L, C)
- * tokens (MyGroupNorm, transformer.py:184-193). */
+ * tokens (MyGroupNorm, transformer.py:184-193).
+ * work: b200sep_groupnorm1_work_floats(...) floats of 16-byte aligned device scratch (per-CTA partial sums; keeps the call re-entrant). */
+int64_t b200sep_groupnorm1_work_floats(int B, int C, int Fr, int64_t L);
 int b200sep_groupnorm1_f32(const float* x, const float* gamma, const float* beta, float* y, int B, int C, int Fr, int64_t L, int act, int channel_last,
-                           void* stream);
+                           float* work, void* stream);
 /* y = x.permute(p0,p1,p2,p3).contiguous() for a 4-D tensor (the einops rearranges around the transformer, transformer.py:532-555) */
 int b200sep_permute4_f32(const float* x, float* y, int d0, int d1, int d2, int d3, int p0, int p1, int p2, int p3, void* stream);
 /* F.glu(dim=1) on (B, 2C, L); with res/scale: y = res + scale[c] * glu  (LayerScale residual of DConv, demucs.py:92-93,166-168) */

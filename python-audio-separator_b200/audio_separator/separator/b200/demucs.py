@@ -156,7 +156,8 @@ def groupnorm1(x, gamma, beta, act=ACT_NONE, channel_last=False):
         Fr = 1
     else:
         B, Cc, Fr, L = x.shape
-    check(lib.b200sep_groupnorm1_f32(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(x), B, Cc, Fr, L, act, int(channel_last), _stream()), "groupnorm1_f32")
+    work = _new((lib.b200sep_groupnorm1_work_floats(B, Cc, Fr, L),), x)
+    check(lib.b200sep_groupnorm1_f32(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(x), B, Cc, Fr, L, act, int(channel_last), _ptr(work), _stream()), "groupnorm1_f32")
     return x
 
 

@@ -40,35 +40,89 @@ __device__ __forceinline__ float2 block_sum2(float a, float b, float* red) {
   return make_float2(red[0], red[32]);
 }
 
-// GroupNorm(num_groups=1, C) over one sample of C*L elements (two passes: mean, then centred variance), affine per channel,
-// optional activation.  grid = samples = B*Fr.  (hdemucs.py:79-80 norm_fn, demucs.py:139-141; eps 1e-5, biased variance.)
-// Layouts: channel-first (B, C, Fr, L) where sample (b, fr) owns elements x[((b*C + c)*Fr + fr)*L + l]  (Fr = 1: plain (B, C, L);
-// Fr > 1: DConv applied per frequency row of a (B, C, Fr, T) tensor without the permute of hdemucs.py:141-146), or
-// channel-last (samples, L, C) (MyGroupNorm on (B, T, C) tokens, transformer.py:184-193).
-__global__ void __launch_bounds__(512) groupnorm1_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                        float* __restrict__ y, int C, int Fr, int64_t L, int act, int channel_last) {
-  __shared__ float red[64];
-  const int64_t n = (int64_t)C * L;
-  const int b = blockIdx.x / Fr, fr = blockIdx.x % Fr;
-  auto idx = [&](int64_t i) -> int64_t {
-    if (channel_last || Fr == 1) return (int64_t)blockIdx.x * n + i;
-    const int64_t c = i / L, l = i - c * L;
-    return (((int64_t)b * C + c) * Fr + fr) * L + l;
-  };
-  float s = 0.f;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += x[idx(i)];
-  const float mean = block_sum2(s, 0.f, red).x / (float)n;
-  float q = 0.f;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const float d = x[idx(i)] - mean;
+// GroupNorm(num_groups=1, C) over one sample of n = C*L elements, affine per channel, optional activation (hdemucs.py:79-80 norm_fn,
+// demucs.py:139-141; eps 1e-5, biased variance).  Two kernels so that a single huge sample (the time branch: 96 x 85995) still fills
+// the GPU: (1) `nblk` CTAs per sample reduce shifted sums  sum(x - x0), sum((x - x0)^2)  (x0 = the sample's first element, which
+// removes the E[x^2] - mean^2 cancellation) into double partials; (2) every CTA re-reduces the partials of its sample in a fixed
+// order (deterministic) and normalises its slice.
+// Layouts: channel-first (B, C, Fr, L) where sample (b, fr) owns x[((b*C + c)*Fr + fr)*L + l]  (Fr = 1: plain (B, C, L); Fr > 1: DConv
+// applied per frequency row of a (B, C, Fr, T) tensor without the permute of hdemucs.py:141-146), or channel-last (samples, L, C)
+// (MyGroupNorm on (B, T, C) tokens, transformer.py:184-193).
+struct GnGeom {
+  int C, Fr, channel_last;
+  uint32_t L, n, chunk;
+};
+__device__ __forceinline__ int64_t gn_index(const GnGeom& g, int sample, uint32_t i) {
+  if (g.channel_last || g.Fr == 1) return (int64_t)sample * g.n + i;
+  const uint32_t c = i / g.L, l = i - c * g.L;
+  const int b = sample / g.Fr, fr = sample - b * g.Fr;
+  return (((int64_t)b * g.C + c) * g.Fr + fr) * g.L + l;
+}
+
+__global__ void __launch_bounds__(256) gn_partial_kernel(const float* __restrict__ x, GnGeom g, double2* __restrict__ part) {
+  __shared__ double rs[8], rq[8];
+  const int sample = blockIdx.y;
+  const float x0 = __ldg(&x[gn_index(g, sample, 0)]);
+  const uint32_t lo = blockIdx.x * g.chunk, hi = min(g.n, lo + g.chunk);
+  float s = 0.f, q = 0.f;
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += 256) {
+    const float d = __ldg(&x[gn_index(g, sample, i)]) - x0;
+    s += d;
     q = fmaf(d, d, q);
   }
-  const float rstd = rsqrtf(block_sum2(q, 0.f, red).x / (float)n + 1e-5f);
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const int c = channel_last ? (int)(i % C) : (int)(i / L);
-    const int64_t o = idx(i);
+  double ds = s, dq = q;
+  for (int o = 16; o > 0; o >>= 1) {
+    ds += __shfl_xor_sync(0xffffffffu, ds, o);
+    dq += __shfl_xor_sync(0xffffffffu, dq, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    rs[threadIdx.x >> 5] = ds;
+    rq[threadIdx.x >> 5] = dq;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double S = 0.0, Q = 0.0;
+    for (int w = 0; w < 8; ++w) {
+      S += rs[w];
+      Q += rq[w];
+    }
+    double2* ps = part + (int64_t)sample * (gridDim.x + 1);
+    ps[blockIdx.x] = make_double2(S, Q);
+    if (blockIdx.x == 0) ps[gridDim.x] = make_double2((double)x0, 0.0);  // the apply pass may run in place: it must not re-read x0 from x
+  }
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      float* __restrict__ y, GnGeom g, const double2* __restrict__ part, int act) {
+  __shared__ float stat[2];
+  const int sample = blockIdx.y;
+  if (threadIdx.x == 0) {
+    double S = 0.0, Q = 0.0;
+    const double2* ps = part + (int64_t)sample * (gridDim.x + 1);
+    for (unsigned k = 0; k < gridDim.x; ++k) {
+      S += ps[k].x;
+      Q += ps[k].y;
+    }
+    const double md = S / (double)g.n;  // mean of (x - x0)
+    double var = Q / (double)g.n - md * md;
+    if (var < 0.0) var = 0.0;
+    stat[0] = (float)(ps[gridDim.x].x + md);
+    stat[1] = (float)(1.0 / sqrt(var + 1e-5));
+  }
+  __syncthreads();
+  const float mean = stat[0], rstd = stat[1];
+  const uint32_t lo = blockIdx.x * g.chunk, hi = min(g.n, lo + g.chunk);
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += 256) {
+    const int c = g.channel_last ? (int)(i % (uint32_t)g.C) : (int)(i / g.L);
+    const int64_t o = gn_index(g, sample, i);
     y[o] = f32_act((x[o] - mean) * rstd * __ldg(&gamma[c]) + __ldg(&beta[c]), act);
   }
+}
+
+static int gn_blocks_per_sample(int samples, int64_t n) {
+  int64_t nblk = std::max<int64_t>(1, (4 * kNumSMs + samples - 1) / samples);
+  nblk = std::min<int64_t>(nblk, std::max<int64_t>(1, n / 2048));
+  return (int)std::min<int64_t>(nblk, 1024);
 }
 
 // out[perm(i)] = in[i] for a 4-D tensor: out dims = in dims permuted by (p0,p1,p2,p3) ("b c fr t -> b t fr c" etc., transformer.py:532,555)
@@ -320,11 +374,27 @@ __global__ void tri_ola_kernel(const float* __restrict__ segs, int n_segs, int c
 
 using namespace b200sep;
 
+extern "C" int64_t b200sep_groupnorm1_work_floats(int B, int C, int Fr, int64_t L) {
+  if (B < 1 || C < 1 || Fr < 1 || L < 1) return 0;
+  return (int64_t)B * Fr * (gn_blocks_per_sample(B * Fr, (int64_t)C * L) + 1) * 4;  // one double2 per CTA + the shift x0
+}
+
 extern "C" int b200sep_groupnorm1_f32(const float* x, const float* gamma, const float* beta, float* y, int B, int C, int Fr, int64_t L, int act, int channel_last,
-                                      void* stream) {
-  B2_CHECK_ARG(x && gamma && beta && y && B >= 1 && C >= 1 && Fr >= 1 && L >= 1, "groupnorm1_f32: bad argument");
+                                      float* work, void* stream) {
+  B2_CHECK_ARG(x && gamma && beta && y && work && B >= 1 && C >= 1 && Fr >= 1 && L >= 1, "groupnorm1_f32: bad argument");
   B2_CHECK_ARG(!(channel_last && Fr != 1), "groupnorm1_f32: channel_last layout has no frequency rows");
-  groupnorm1_kernel<<<B * Fr, 512, 0, (cudaStream_t)stream>>>(x, gamma, beta, y, C, Fr, L, act, channel_last);
+  B2_CHECK_ARG((int64_t)C * L < (1ll << 31) && (int64_t)B * Fr <= 65535, "groupnorm1_f32: sample of %lld elements / %lld samples too large", (long long)C * L,
+               (long long)B * Fr);
+  B2_CHECK_ARG((reinterpret_cast<uintptr_t>(work) & 15) == 0, "groupnorm1_f32: work must be 16-byte aligned");
+  const int samples = B * Fr;
+  const int nblk = gn_blocks_per_sample(samples, (int64_t)C * L);
+  GnGeom g;
+  g.C = C; g.Fr = Fr; g.channel_last = channel_last; g.L = (uint32_t)L; g.n = (uint32_t)((int64_t)C * L);
+  g.chunk = (uint32_t)cdiv((int64_t)g.n, nblk);
+  dim3 grid(nblk, samples);
+  gn_partial_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, g, reinterpret_cast<double2*>(work));
+  B2_LAUNCHED();
+  gn_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, y, g, reinterpret_cast<const double2*>(work), act);
   B2_LAUNCHED();
   return B200SEP_OK;
 }
