@@ -31,6 +31,7 @@ class HTConfig:
     kernel_size: int = 8
     stride: int = 4
     context: int = 1
+    dconv_mode: int = 3  # bit 0: DConv in the encoders, bit 1: in the decoders (hdemucs.py:83-84, :268-269)
     dconv_depth: int = 2
     dconv_comp: int = 8
     bottom_channels: int = 512
@@ -53,7 +54,7 @@ class HTConfig:
 
     def kwargs(self):  # what the reference constructor receives
         return dict(sources=list(self.sources), audio_channels=self.audio_channels, channels=self.channels, growth=self.growth, nfft=self.nfft, depth=self.depth,
-                    kernel_size=self.kernel_size, stride=self.stride, context=self.context, dconv_mode=3, dconv_depth=self.dconv_depth, dconv_comp=self.dconv_comp,
+                    kernel_size=self.kernel_size, stride=self.stride, context=self.context, dconv_mode=self.dconv_mode, dconv_depth=self.dconv_depth, dconv_comp=self.dconv_comp,
                     bottom_channels=self.bottom_channels, t_layers=self.t_layers, t_heads=self.t_heads, t_hidden_scale=self.t_hidden_scale, freq_emb=self.freq_emb,
                     emb_scale=self.emb_scale, samplerate=self.samplerate, segment=self.segment)
 
@@ -83,17 +84,21 @@ def param_shapes(cfg: HTConfig):
     K = cfg.kernel_size
     for i, ci, co in enc:
         out.extend([(f"encoder.{i}.conv.weight", (co, ci, K, 1)), (f"encoder.{i}.conv.bias", (co,)), (f"encoder.{i}.rewrite.weight", (2 * co, co, 1, 1)), (f"encoder.{i}.rewrite.bias", (2 * co,))])
-        dconv(f"encoder.{i}", co)
+        if cfg.dconv_mode & 1:
+            dconv(f"encoder.{i}", co)
     k3 = 1 + 2 * cfg.context
     for j, (ci, co) in enumerate(dec):
         out.extend([(f"decoder.{j}.conv_tr.weight", (ci, co, K, 1)), (f"decoder.{j}.conv_tr.bias", (co,)), (f"decoder.{j}.rewrite.weight", (2 * ci, ci, k3, k3)), (f"decoder.{j}.rewrite.bias", (2 * ci,))])
-        dconv(f"decoder.{j}", ci)
+        if cfg.dconv_mode & 2:
+            dconv(f"decoder.{j}", ci)
     for i, ci, co in tenc:
         out.extend([(f"tencoder.{i}.conv.weight", (co, ci, K)), (f"tencoder.{i}.conv.bias", (co,)), (f"tencoder.{i}.rewrite.weight", (2 * co, co, 1)), (f"tencoder.{i}.rewrite.bias", (2 * co,))])
-        dconv(f"tencoder.{i}", co)
+        if cfg.dconv_mode & 1:
+            dconv(f"tencoder.{i}", co)
     for j, (ci, co) in enumerate(tdec):
         out.extend([(f"tdecoder.{j}.conv_tr.weight", (ci, co, K)), (f"tdecoder.{j}.conv_tr.bias", (co,)), (f"tdecoder.{j}.rewrite.weight", (2 * ci, ci, k3)), (f"tdecoder.{j}.rewrite.bias", (2 * ci,))])
-        dconv(f"tdecoder.{j}", ci)
+        if cfg.dconv_mode & 2:
+            dconv(f"tdecoder.{j}", ci)
     out.append(("freq_emb.embedding.weight", (cfg.nfft // 2 // cfg.stride, cfg.channels)))
     tc = cfg.channels * cfg.growth ** (cfg.depth - 1)
     dim = tc
@@ -180,6 +185,8 @@ def forward(weights, cfg: HTConfig, mix: np.ndarray, dtype="float32") -> np.ndar
     B = mixp.shape[0]
 
     def dconv(y, prefix):  # demucs.py:166-168
+        if f"{prefix}.dconv.layers.0.0.weight" not in W:  # dconv_mode without this side
+            return y
         for d in range(cfg.dconv_depth):
             p = f"{prefix}.dconv.layers.{d}"
             dil = 2**d

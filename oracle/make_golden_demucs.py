@@ -45,6 +45,14 @@ def main():
         ys_ref = model(torch.from_numpy(short)).numpy()
     check("htdemucs forward (short, padded)", ys_ref, D.forward(w, cfg, short), 2e-5 * max(1.0, np.abs(ys_ref).max()))
 
+    # constructor defaults that differ from the pinned structure: DConv in the encoders only (dconv_mode=1), no channel up-samplers
+    cfg1 = D.HTConfig(**dict(SMALL, dconv_mode=1, bottom_channels=0, t_layers=2))
+    w1 = D.make_weights(cfg1, seed=6)
+    model1 = ref_model(cfg1, w1)
+    with torch.no_grad():
+        y1_ref = model1(torch.from_numpy(seg)).numpy()
+    check("htdemucs forward (dconv_mode=1, bottom_channels=0)", y1_ref, D.forward(w1, cfg1, seg), 2e-5 * max(1.0, np.abs(y1_ref).max()))
+
     # apply_model with shifts=2, split=True: record the reference's random offsets
     apply = ref_shim.ref_module("audio_separator.separator.uvr_lib_v5.demucs.apply")
     N = int(2.3 * L)
@@ -84,7 +92,7 @@ def main():
     check("demix_demucs", src_ref, src_orc, 5e-5 * max(1.0, np.abs(src_ref).max()))
     np.savez_compressed(
         os.path.join(GOLD, "demucs_small.npz"), weights_seed=5, mix_seed=31, seg_len=L, n_apply=N, shift_offsets=np.array(offs),
-        forward_ref=y_ref.astype(np.float32), forward_short_ref=ys_ref.astype(np.float32), apply_ref=a_ref.astype(np.float32), demix_ref=src_ref.astype(np.float32),
+        forward_ref=y_ref.astype(np.float32), forward_short_ref=ys_ref.astype(np.float32), forward_dm1_ref=y1_ref.astype(np.float32), apply_ref=a_ref.astype(np.float32), demix_ref=src_ref.astype(np.float32),
     )
     print("wrote tests/golden/demucs_small.npz; oracle pinned: OK")
 

@@ -225,8 +225,9 @@ class HTDemucsNet:
     def _check_structure(self, st):
         cfg = self.cfg
         need = ["encoder.0.conv.weight", "tencoder.0.conv.weight", "decoder.0.conv_tr.weight", "tdecoder.0.conv_tr.weight", "freq_emb.embedding.weight",
-                "encoder.0.dconv.layers.1.6.scale", "crosstransformer.norm_in.weight", "crosstransformer.layers.0.norm_out.weight",
-                "crosstransformer.layers.0.gamma_1.scale"]
+                "encoder.0.rewrite.weight", "decoder.0.rewrite.weight"]
+        if cfg.t_layers:
+            need += ["crosstransformer.norm_in.weight", "crosstransformer.layers.0.norm_out.weight", "crosstransformer.layers.0.gamma_1.scale"]
         for n in need:
             if n not in st:
                 raise ValueError(f"state dict lacks {n}: not an htdemucs-v4 checkpoint of the supported structure")
@@ -237,12 +238,21 @@ class HTDemucsNet:
             raise ValueError(f"state dict does not have depth {cfg.depth}")
         if st["encoder.0.conv.weight"].shape[0] != cfg.channels:
             raise ValueError("config.channels does not match the checkpoint")
+        if any(".dconv.layers.0.3.weight" in n for n in st) and f"encoder.0.dconv.layers.{cfg.dconv_depth - 1}.0.weight" not in st and \
+                f"decoder.0.dconv.layers.{cfg.dconv_depth - 1}.0.weight" not in st:
+            raise ValueError("config.dconv_depth does not match the checkpoint")
+        if any(".dconv.layers.0.0.weight" in n and st[n].shape[-1] != 3 for n in st) or any(".lstm." in n or ".attn." in n for n in st):
+            raise ValueError("DConv with LSTM / attention or a kernel other than 3 is not supported")
+        if bool(cfg.bottom_channels) != ("channel_upsampler.weight" in st):
+            raise ValueError("config.bottom_channels does not match the checkpoint")
 
     # ---- sub-graphs --------------------------------------------------------------------------------------------
     def _dconv(self, x, prefix):
         """DConv.forward (demucs.py:166-168) on x (B,C,Fr,T): conv1d k3 dilated -> GroupNorm(1)+GELU -> 1x1 -> GroupNorm(1) -> GLU, LayerScale residual."""
         W = self.W
         C_ = x.shape[1]
+        if f"{prefix}.dconv.layers.0.0.weight" not in W:  # dconv_mode without DConv on this side (hdemucs.py:83-84, :268-269)
+            return x
         for d in range(self.cfg.dconv_depth):
             p = f"{prefix}.dconv.layers.{d}"
             dil = 2**d

@@ -286,3 +286,66 @@ def test_full_size_segment_vs_oracle(dm):
     assert got.shape == ref.shape == (1, 4, 2, ocfg.seg_len)
     err = np.abs(got - ref).max()
     assert err <= 1e-4 * max(1.0, np.abs(ref).max()), (err, np.abs(ref).max())
+
+
+def _write_package(path, ocfg, w, half=False):
+    """A `.th` package as demucs/states.py serialises it, with the class pickled by reference to a module that is NOT importable
+    when the package is read back (the product must not need the reference's classes)."""
+    import sys
+    import types
+
+    mod = types.ModuleType("demucs_fake_pkg.htdemucs")
+    parent = types.ModuleType("demucs_fake_pkg")
+    HT = type("HTDemucs", (), {"__module__": "demucs_fake_pkg.htdemucs"})
+    mod.HTDemucs = HT
+    sys.modules["demucs_fake_pkg"], sys.modules["demucs_fake_pkg.htdemucs"] = parent, mod
+    try:
+        state = {k: (torch.from_numpy(v).half() if half else torch.from_numpy(v)) for k, v in w.items()}
+        torch.save({"klass": HT, "args": (), "kwargs": ocfg.kwargs(), "state": state}, path)
+    finally:
+        del sys.modules["demucs_fake_pkg"], sys.modules["demucs_fake_pkg.htdemucs"]
+
+
+def test_demucs_separator_plugin_end_to_end(dm, tmp_path):
+    """Separator(...).load_model(bag.yaml); separate(wav) -> four WAVs named as the reference names them; PCM within 3 LSB of the oracle."""
+    import random
+    import wave
+
+    from audio_separator.separator import Separator
+
+    ocfg = D.HTConfig(**SMALL)
+    w_a, w_b = D.make_weights(ocfg, seed=21), D.make_weights(ocfg, seed=22)
+    _write_package(str(tmp_path / "aaaa1111.th"), ocfg, w_a)
+    _write_package(str(tmp_path / "bbbb2222-0123abcd.th"), ocfg, w_b)
+    (tmp_path / "tiny_ft.yaml").write_text("models: ['aaaa1111', 'bbbb2222']\nweights: [[1, 0, 1, 1], [0, 1, 1, 0]]\n")
+    mix = M.synth_music(30000, seed=3)
+    pcm = (mix.T * 32767).astype("<i2")
+    with wave.open(str(tmp_path / "song.wav"), "wb") as wf:
+        wf.setnchannels(2); wf.setsampwidth(2); wf.setframerate(44100); wf.writeframes(pcm.tobytes())
+    sep = Separator(model_file_dir=str(tmp_path), output_dir=str(tmp_path / "out"), demucs_params={"shifts": 1, "batch_size": 2})
+    sep.load_model("tiny_ft.yaml")
+    random.seed(1234)
+    files = sep.separate(str(tmp_path / "song.wav"))
+    assert files == ["song_(Bass)_tiny_ft.wav", "song_(Drums)_tiny_ft.wav", "song_(Other)_tiny_ft.wav", "song_(Vocals)_tiny_ft.wav"]
+    random.seed(1234)
+    offs = [[random.randint(0, 22050)], [random.randint(0, 22050)]]
+    loaded = pcm.astype(np.float32).T / 32768.0
+    fns = [lambda c: D.forward(w_a, ocfg, c), lambda c: D.forward(w_b, ocfg, c)]
+    ref = D.demix_demucs(fns, [[1, 0, 1, 1], [0, 1, 1, 0]], ocfg, loaded, offs, 0.25)
+    for k, fname in enumerate(files):
+        with wave.open(str(tmp_path / "out" / fname)) as wf:
+            assert wf.getnframes() == 30000 and wf.getnchannels() == 2
+            got = np.frombuffer(wf.readframes(30000), dtype="<i2").astype(np.int32)
+        want = M.to_pcm16(ref[k].T.copy(), 0.9, 0.0).astype(np.int32)  # final_process receives (N, 2)
+        assert np.abs(got - want).max() <= 3  # <= 1e-4 * 32767 LSB
+
+
+def test_dconv_mode_1_without_bottom_channels_vs_reference_golden(dm, small):
+    """The constructor defaults dconv_mode=1 / bottom_channels=0 (DConv in the encoders only, transformer at the encoder width)."""
+    z, ocfg, w, net, mix = small
+    kw = dict(SMALL, bottom_channels=0, t_layers=2)
+    ocfg1 = D.HTConfig(**dict(kw, dconv_mode=1))
+    w1 = D.make_weights(ocfg1, seed=6)
+    net1 = dm.HTDemucsNet(dm.HTDemucsConfig(**kw), w1)
+    y = net1.forward(dev(mix[None, :, : ocfg1.seg_len])).cpu().numpy()
+    assert np.abs(y - z["forward_dm1_ref"]).max() <= 1e-4
