@@ -205,7 +205,7 @@ int b200sep_rect_overlap_add(const float* chunks, int n_chunks, int channels, in
  */
 int b200sep_stft_forward_ex(const b200sep_stft_plan* plan, const float* wave, int64_t batch_stride, int64_t chan_stride, int64_t valid_len,
                             int batch, int chunk_len, int frames, int frame_offset, float scale, int dim_f, int zero_bins, int layout,
-                            float* spec, void* stream);
+                            int pad_mode /* 0 reflect (torch.stft), 1 zeros (librosa.stft pad_mode="constant") */, float* spec, void* stream);
 int b200sep_stft_inverse_ex(const b200sep_stft_plan* plan, const float* spec, int batch, int frames, int dim_f, int layout, int out_len,
                             int ola_offset, int env_extra, float scale, float* wave, float* work, void* stream);
 
@@ -216,12 +216,13 @@ int b200sep_stft_inverse_ex(const b200sep_stft_plan* plan, const float* spec, in
  * conv2d_f32: nn.Conv1d / nn.Conv2d (hdemucs.py:107,113; demucs.py:147,150) and, with up_axis != 0, nn.ConvTranspose1d/2d
  *   (hdemucs.py:285) expressed as a 2-tap convolution over the coarse index q with up*Cout GEMM columns (column r*Cout+co ->
  *   output index q*up + r - trim, kept inside [0, out_len)).  x (B,Cin,H,W); w_blocked [Cin][KH*KW][ceil48(CoutCols)];
- *   y = act(conv + bias (+ add if add_before_act)) (+ add otherwise).  act: 0 none, 1 ReLU, 2 GELU(erf), 3 LeakyReLU(0.01).
- *   Supported (KH,KW,SH,SW,DW): (1,1,1,1,1) (3,3,1,1,1) (1,3,1,1,1) (1,3,1,1,2) (8,1,4,1,1) (1,8,1,4,1) (2,1,1,1,1) (1,2,1,1,1).
+ *   y = act(conv + bias (+ add if add_before_act)) (+ add otherwise).  act: 0 none, 1 ReLU, 2 GELU(erf), 3 LeakyReLU(0.01), 4 sigmoid.
+ *   out_c_total != 0: y has out_c_total channels and this call fills [out_c_off, out_c_off + Cout) (a fused torch.cat; plain convs only).
+ *   Supported (KH,KW,SH,SW,DW): (1,1,1,1,1) (3,3,1,1,1) (3,3,2,2,1) (1,3,1,1,1) (1,3,1,1,2) (8,1,4,1,1) (1,8,1,4,1) (2,1,1,1,1) (1,2,1,1,1).
  */
 int b200sep_conv2d_f32(const float* x, const float* w_blocked, const float* bias, const float* add, float* y, int B, int Cin, int H, int W, int Cout,
                        int Ho, int Wo, int KH, int KW, int SH, int SW, int PH, int PW, int DW, int act, int add_before_act, int up_axis, int up,
-                       int trim, int out_len, void* stream);
+                       int trim, int out_len, int out_c_total, int out_c_off, void* stream);
 /* nn.GroupNorm(1, C), affine, optional activation (demucs.py:141,144).  Channel-first x (B, C, Fr, L): one sample per (b, fr) row
  * (Fr = 1: (B, C, L); Fr > 1: DConv on every frequency row without the permute of hdemucs.py:141-146); channel_last: x (B, L, C)
  * tokens (MyGroupNorm, transformer.py:184-193).
@@ -252,6 +253,32 @@ int b200sep_meanstd_f32(const float* x, int64_t n, float* out2, void* stream);
  * -- q0/scale/accumulate fold in the shift average (apply.py:197-214), chan_scale (nullable) the bag weights (apply.py:169-195). */
 int b200sep_triangle_overlap_add(const float* segs, int n_segs, int channels, int seg_len, int64_t stride, int64_t length, int64_t q0, int64_t n_out,
                                  float scale, const float* chan_scale, int accumulate, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Operators of the VR path (uvr_lib_v5/vr_network/{nets,layers}.py, architectures/vr_separator.py, uvr_lib_v5/spec_utils.py).
+ * Spectrograms are 4 float planes (L re, L im, R re, R im) of (bins, frames), the CFT layout of the STFT entry points.
+ */
+/* depthwise 3x3, dilation = padding = d: the first conv of SeperableConv2DBNActiv (layers.py:60-70); w (C, 9) */
+int b200sep_dwconv3x3_f32(const float* x, const float* w, float* y, int B, int C, int H, int W, int dilation, void* stream);
+/* F.interpolate(scale_factor=2, mode="bilinear", align_corners=True) (Decoder, layers.py:175) into channels [dst_c_off, +C) of (B, dst_c_total, 2H, 2W) */
+int b200sep_upsample2x_bilinear_f32(const float* x, float* y, int B, int C, int H, int W, int dst_c_total, int dst_c_off, void* stream);
+/* nn.AdaptiveAvgPool2d((1, None)) (ASPPModule.conv1, layers.py:232): (BC, H, W) -> (BC, W) */
+int b200sep_mean_h_f32(const float* x, float* y, int BC, int H, int W, void* stream);
+/* dst[i0*ds0 + i1*ds1 + i2*ds2 + i3*ds3] = src[i0*ss0 + ...] over a (d0,d1,d2,d3) index box: torch.cat / crop_center / broadcast / patch slicing */
+int b200sep_copy4_f32(const float* src, float* dst, int d0, int d1, int d2, int d3, int64_t ss0, int64_t ss1, int64_t ss2, int64_t ss3, int64_t ds0,
+                      int64_t ds1, int64_t ds2, int64_t ds3, void* stream);
+/* x[plane][bin][t] *= gain[bin]: pre-filter of combine_spectrograms (spec_utils.py:266-277), fft_lp_filter / fft_hp_filter (:410-429) */
+int b200sep_bin_gain_f32(float* x, const float* gain, int planes, int bins, int frames, void* stream);
+/* |X| written at column pad_l of a zero-filled (2, bins, frames_out) buffer (spec_utils.preprocess + np.pad, vr_separator.py:345-349) */
+int b200sep_vr_magnitude_pad(const float* spec, float* mag, int bins, int frames, int frames_out, int pad_l, void* stream);
+/* adjust_aggr + the masked spectrograms (spec_utils.py:472-492, vr_separator.py:329-343): m = mask^e; y = m*X; v = (1-m)*X; non-finite -> 0.
+ * mask (2, bins, mask_stride); e = exp_low_* below split_bin, exp_high_* from it on, per channel. */
+int b200sep_vr_apply_mask(const float* mask, int mask_stride, const float* spec, int bins, int frames, int split_bin, float exp_low_left, float exp_high_left,
+                          float exp_low_right, float exp_high_right, float* y_spec, float* v_spec, void* stream);
+/* scipy.signal.resample_poly's upfirdn (== librosa.resample(res_type="polyphase"), vr_separator.py:280):
+ * y[c][k] = sum_i x[c][i] * taps[(k + n_pre_remove)*down - i*up];  taps = the zero-padded FIR scaled by `up` */
+int b200sep_resample_poly_f32(const float* x, const float* taps, int n_taps, int up, int down, int64_t n_pre_remove, int channels, int64_t n_in,
+                              int64_t n_out, float* y, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Self-tests of the tensor-core ("bf16x3 pair") operators in isolation: fp32 device tensors in, the operator runs

@@ -58,9 +58,9 @@ _SIGS = {
     "b200sep_tfcnet_device_bytes": (i64, [vp]),
     "b200sep_tfcnet_forward": (i32, [vp, vp, vp, i32, vp]),
     "b200sep_rect_overlap_add": (i32, [vp, i32, i32, i32, i64, i64, i64, f32, vp, vp]),
-    "b200sep_stft_forward_ex": (i32, [vp, vp, i64, i64, i64, i32, i32, i32, i32, f32, i32, i32, i32, vp, vp]),
+    "b200sep_stft_forward_ex": (i32, [vp, vp, i64, i64, i64, i32, i32, i32, i32, f32, i32, i32, i32, i32, vp, vp]),
     "b200sep_stft_inverse_ex": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp, vp, vp]),
-    "b200sep_conv2d_f32": (i32, [vp, vp, vp, vp, vp] + [i32] * 20 + [vp]),
+    "b200sep_conv2d_f32": (i32, [vp, vp, vp, vp, vp] + [i32] * 22 + [vp]),
     "b200sep_groupnorm1_work_floats": (i64, [i32, i32, i32, i64]),
     "b200sep_groupnorm1_f32": (i32, [vp, vp, vp, vp, i32, i32, i32, i64, i32, i32, vp, vp]),
     "b200sep_permute4_f32": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
@@ -71,6 +71,14 @@ _SIGS = {
     "b200sep_ew_f32": (i32, [vp, vp, vp, i64, f32, f32, i32, vp]),
     "b200sep_meanstd_f32": (i32, [vp, i64, vp, vp]),
     "b200sep_triangle_overlap_add": (i32, [vp, i32, i32, i32, i64, i64, i64, i64, f32, vp, i32, vp, vp]),
+    "b200sep_dwconv3x3_f32": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "b200sep_upsample2x_bilinear_f32": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "b200sep_mean_h_f32": (i32, [vp, vp, i32, i32, i32, vp]),
+    "b200sep_copy4_f32": (i32, [vp, vp, i32, i32, i32, i32] + [i64] * 8 + [vp]),
+    "b200sep_bin_gain_f32": (i32, [vp, vp, i32, i32, i32, vp]),
+    "b200sep_vr_magnitude_pad": (i32, [vp, vp, i32, i32, i32, i32, vp]),
+    "b200sep_vr_apply_mask": (i32, [vp, i32, vp, i32, i32, i32, f32, f32, f32, f32, vp, vp, vp]),
+    "b200sep_resample_poly_f32": (i32, [vp, vp, i32, i32, i32, i64, i32, i64, i64, vp, vp]),
     "b200sep_selftest_umma_gemm": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, vp]),
     "b200sep_selftest_umma_conv3x3": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, vp]),
     "b200sep_selftest_umma_updown": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp]),

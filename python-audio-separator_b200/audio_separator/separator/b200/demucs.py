@@ -121,17 +121,22 @@ def _new(shape, like=None, device=None):
     return torch.empty(shape, dtype=torch.float32, device=like.device if like is not None else device)
 
 
-def conv2d(x, wb, bias, cout, k, s=(1, 1), p=(0, 0), dw=1, act=ACT_NONE, add=None, add_before_act=False, out_hw=None):
-    """x (B,Cin,H,W) -> (B,cout,Ho,Wo);  out_hw overrides the implied output size (right/bottom zero padding is implicit)."""
+def conv2d(x, wb, bias, cout, k, s=(1, 1), p=(0, 0), dw=1, act=ACT_NONE, add=None, add_before_act=False, out_hw=None, out=None, out_c_off=0):
+    """x (B,Cin,H,W) -> (B,cout,Ho,Wo);  out_hw overrides the implied output size (right/bottom zero padding is implicit);
+    out/out_c_off: write into channels [out_c_off, out_c_off + cout) of an existing (B, C_total, Ho, Wo) tensor (a fused torch.cat)."""
     B, cin, H, W = x.shape
     if out_hw is None:
         Ho = (H + 2 * p[0] - k[0]) // s[0] + 1
         Wo = (W + 2 * p[1] - dw * (k[1] - 1) - 1) // s[1] + 1
     else:
         Ho, Wo = out_hw
-    y = _new((B, cout, Ho, Wo), x)
+    if out is None:
+        y, ct = _new((B, cout, Ho, Wo), x), 0
+    else:
+        assert out.shape[0] == B and tuple(out.shape[2:]) == (Ho, Wo), (out.shape, (B, cout, Ho, Wo))
+        y, ct = out, out.shape[1]
     check(lib.b200sep_conv2d_f32(_ptr(x), _ptr(wb), _ptr(bias) if bias is not None else None, _ptr(add) if add is not None else None, _ptr(y), B, cin, H, W, cout,
-                                 Ho, Wo, k[0], k[1], s[0], s[1], p[0], p[1], dw, act, int(add_before_act), 0, 1, 0, 0, _stream()), "conv2d_f32")
+                                 Ho, Wo, k[0], k[1], s[0], s[1], p[0], p[1], dw, act, int(add_before_act), 0, 1, 0, 0, ct, out_c_off, _stream()), "conv2d_f32")
     return y
 
 
@@ -145,7 +150,7 @@ def conv_transpose(x, wb, bias, cout, axis, stride, trim, out_len, act=ACT_NONE)
         y = _new((B, cout, H, out_len), x)
         k, p, hw = (1, 2), (0, 1), (H, W + 1)
     check(lib.b200sep_conv2d_f32(_ptr(x), _ptr(wb), _ptr(bias), None, _ptr(y), B, cin, H, W, stride * cout, hw[0], hw[1], k[0], k[1], 1, 1, p[0], p[1], 1, act, 0,
-                                 axis, stride, trim, out_len, _stream()), "conv2d_f32(transposed)")
+                                 axis, stride, trim, out_len, 0, 0, _stream()), "conv2d_f32(transposed)")
     return y
 
 
@@ -406,7 +411,7 @@ class HTDemucsNet:
         # _spec + _magnitude (htdemucs.py:383-403, :415-424): normalized STFT, frames 2..2+le of the 3*hop/2-reflect-padded signal, bins 0..nfft/2-1
         spec = _new((B, 4, Fq, le), mp)
         check(lib.b200sep_stft_forward_ex(self.stft.handle, _ptr(mp), 2 * T_len, T_len, 0, B, T_len, le, hl // 2 * 3, 1.0 / math.sqrt(nfft), Fq, 0, LAYOUT_CFT,
-                                          _ptr(spec), _stream()), "stft_forward_ex")
+                                          0, _ptr(spec), _stream()), "stft_forward_ex")
         stats = _new((B, 4), mp)  # per sample: mean, std of the spectrogram; mean, std of the waveform
         x = _new(spec.shape, mp)
         xt = _new((B, 2, 1, T_len), mp)

@@ -1,0 +1,420 @@
+"""VR architecture (CascadedASPPNet, "VR arch" v4 / v5.0 models) on the operator kernels of libb200sep.so.
+
+VRNet.predict_mask replaces CascadedASPPNet.predict_mask (uvr_lib_v5/vr_network/nets.py:96-175, layers.py:8-294); VREngine replaces
+VRSeparator.loading_mix / inference_vr / spec_to_wav (architectures/vr_separator.py:255-375) with the multi-band STFT, the polyphase
+band resampling, the patch loop, the mask post-processing and the band synthesis all on the GPU.
+This file is the graph builder: device buffers + launch order.  All arithmetic is behind the C ABI (include/b200sep.h).
+
+Not covered (raises): VR 5.1 models (nets_new.CascadedNet), enable_tta / enable_post_process / high_end_process, `reverse` model
+parameters, analysis bands resampled with anything but res_type "polyphase".  The band UP-sampling of the synthesis side uses the
+same Kaiser polyphase design (the reference calls libsamplerate "sinc_fastest" there; see DESIGN.md: parity unpinned for that step).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from ._lib import LAYOUT_CFT, check, lib
+from .demucs import ACT_NONE, ACT_RELU, _new, block_conv_weight, conv2d, ew
+from .engine import StftPlan, _ptr, _require_cuda, _stream
+
+ACT_LEAKY, ACT_SIGMOID = 3, 4
+NON_ACCOM_STEMS = ("Vocals", "Other", "Bass", "Drums", "Guitar", "Piano", "Synthesizer", "Strings", "Woodwinds", "Brass", "Wind Inst")  # common_separator.py:55
+NN_ARCH_SIZES = (31191, 33966, 56817, 123821, 123812, 129605, 218409, 537238, 537227)  # vr_separator.py:166
+VR_51_SIZES = (56817, 218409)
+
+
+def copy_view(src: torch.Tensor, dst: torch.Tensor):
+    """dst[...] = src[...] for two (possibly strided / broadcast) 4-D views of float32 CUDA storage: one strided-copy kernel."""
+    assert src.dim() == 4 and tuple(src.shape) == tuple(dst.shape), (src.shape, dst.shape)
+    d = src.shape
+    check(lib.b200sep_copy4_f32(src.data_ptr(), dst.data_ptr(), d[0], d[1], d[2], d[3], *src.stride(), *dst.stride(), _stream()), "copy4_f32")
+
+
+def resample_poly_design(up: int, down: int):
+    """The FIR scipy.signal.resample_poly designs (window=("kaiser", 5.0)) and the alignment of its output:
+    -> (taps float32 zero-padded in front and scaled by `up`, n_pre_remove)."""
+    g = math.gcd(up, down)
+    up, down = up // g, down // g
+    max_rate = max(up, down)
+    f_c = 1.0 / max_rate
+    half_len = 10 * max_rate
+    n = 2 * half_len + 1
+    m = np.arange(n, dtype=np.float64) - half_len
+    h = f_c * np.sinc(f_c * m) * np.kaiser(n, 5.0)  # firwin: windowed ideal low-pass, unit gain at DC
+    h = h / h.sum() * up
+    n_pre_pad = down - half_len % down
+    n_pre_remove = (half_len + n_pre_pad) // down
+    return np.concatenate([np.zeros(n_pre_pad), h]).astype(np.float32), n_pre_remove, up, down
+
+
+def lp_gain(n_bins, start, stop):
+    """fft_lp_filter as a per-bin gain (spec_utils.py:410-418)."""
+    g = np.ones(n_bins, np.float64)
+    v = 1.0
+    for b in range(start, stop):
+        v -= 1 / (stop - start)
+        g[b] = v
+    g[stop:] = 0
+    return g
+
+
+def hp_gain(n_bins, start, stop):
+    """fft_hp_filter as a per-bin gain (spec_utils.py:421-429)."""
+    g = np.ones(n_bins, np.float64)
+    v = 1.0
+    for b in range(start, stop, -1):
+        v -= 1 / (start - stop)
+        g[b] = v
+    g[0 : stop + 1] = 0
+    return g
+
+
+def capacity(nn_architecture: int):
+    """determine_model_capacity (nets.py:67-93)."""
+    if nn_architecture in (31191, 33966, 129605):
+        return 16, 8, 16, 32
+    if nn_architecture in (123821, 123812):
+        return 32, 16, 32, 64
+    if nn_architecture in (537238, 537227):
+        return 64, 32, 64, 128
+    raise NotImplementedError(f"nn_architecture {nn_architecture}: only CascadedASPPNet sizes are covered (VR 5.1 CascadedNet is not)")
+
+
+class VRNet:
+    """CascadedASPPNet in eval mode: BatchNorm folded into the preceding (bias-free) convolution, Dropout = identity."""
+
+    def __init__(self, nn_architecture: int, n_fft_bins: int, state: dict, device="cuda:0"):
+        _require_cuda()
+        self.arch = int(nn_architecture)
+        self.c1, self.cb, self.c2, self.c3 = capacity(self.arch)
+        self.n_enc = 5 if self.arch == 129605 else 4
+        self.n_extra = 1 if self.arch == 129605 else (2 if self.arch in (537238, 537227, 33966) else 0)
+        self.max_bin, self.output_bin, self.offset = n_fft_bins // 2, n_fft_bins // 2 + 1, 128
+        self.device = torch.device(device)
+        st = {k: np.asarray(v) for k, v in state.items()}
+        self.W = {}
+        for name in st:
+            if not name.endswith(".conv.0.weight"):
+                continue
+            p = name[: -len(".conv.0.weight")]
+            if p + ".conv.2.running_var" in st:  # SeperableConv2DBNActiv: depthwise (C,1,3,3), pointwise (nout,C,1,1), BatchNorm at index 2
+                self._put(p + ".dw", st[name].reshape(st[name].shape[0], 9).astype(np.float32))
+                self._fold(p, st[p + ".conv.1.weight"], st, p + ".conv.2")
+            elif p + ".conv.1.running_var" in st:  # Conv2DBNActiv
+                self._fold(p, st[name], st, p + ".conv.1")
+        for nm in ("out",):
+            self._put(nm + ".w", block_conv_weight(st[nm + ".weight"].astype(np.float32)))
+        need = ["stg1_low_band_net.enc1.conv1.w", "stg3_full_band_net.dec1.conv.w", "stg2_bridge.w", "out.w", "stg1_low_band_net.aspp.conv3.dw"]
+        for n in need:
+            if n not in self.W:
+                raise ValueError(f"state dict lacks {n.rsplit('.', 1)[0]}: not a CascadedASPPNet checkpoint")
+        if self.W["stg1_low_band_net.enc1.conv1.b"].numel() != self.c1:
+            raise ValueError("checkpoint width does not match the capacity of its nn_architecture size")
+
+    def _put(self, name, a):
+        self.W[name] = torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+
+    def _fold(self, p, w, st, bn):
+        inv = st[bn + ".weight"].astype(np.float64) / np.sqrt(st[bn + ".running_var"].astype(np.float64) + 1e-5)
+        wf = (w.astype(np.float64) * inv[:, None, None, None]).astype(np.float32)
+        self._put(p + ".w", block_conv_weight(wf))
+        self._put(p + ".b", (st[bn + ".bias"].astype(np.float64) - st[bn + ".running_mean"].astype(np.float64) * inv).astype(np.float32))
+        self.W[p + ".k"] = int(w.shape[-1])
+
+    # ---- sub-graphs
+    def _cba(self, x, p, stride=1, act=ACT_RELU, out=None, out_c_off=0):
+        k = self.W[p + ".k"]
+        cout = self.W[p + ".b"].numel()
+        return conv2d(x, self.W[p + ".w"], self.W[p + ".b"], cout, (k, k), s=(stride, stride), p=(k // 2, k // 2), act=act, out=out, out_c_off=out_c_off)
+
+    def _sep(self, x, p, dil, out, out_c_off):
+        B, C, H, W = x.shape
+        y = _new(x.shape, x)
+        check(lib.b200sep_dwconv3x3_f32(_ptr(x), _ptr(self.W[p + ".dw"]), _ptr(y), B, C, H, W, dil, _stream()), "dwconv3x3_f32")
+        return self._cba(y, p, out=out, out_c_off=out_c_off)
+
+    def _aspp(self, x, p):
+        B, C, H, W = x.shape
+        n_feat = 5 + self.n_extra
+        cat = _new((B, C * n_feat, H, W), x)
+        pooled = _new((B, C, 1, W), x)
+        check(lib.b200sep_mean_h_f32(_ptr(x), _ptr(pooled), B * C, H, W, _stream()), "mean_h_f32")
+        f1 = self._cba(pooled, p + ".conv1.1")  # (B,C,1,W); bilinear resize of a height-1 map (align_corners) = broadcast over H
+        copy_view(f1.expand(B, C, H, W), cat[:, :C])
+        self._cba(x, p + ".conv2", out=cat, out_c_off=C)
+        for i, dil in ((3, 4), (4, 8), (5, 16)):
+            self._sep(x, f"{p}.conv{i}", dil, cat, C * (i - 1))
+        for i in range(self.n_extra):  # conv6 / conv7 are one shared module in the reference: the same weights under both names
+            self._sep(x, f"{p}.conv{6 + i}", 16, cat, C * (5 + i))
+        return self._cba(cat, p + ".bottleneck.0")
+
+    def _dec(self, x, skip, p):
+        B, C, H, W = x.shape
+        Cs, Hs, Ws = skip.shape[1:]
+        if Hs != 2 * H or Ws < 2 * W:
+            raise ValueError(f"decoder skip {tuple(skip.shape)} does not fit the up-sampled {(B, C, 2 * H, 2 * W)} (the reference fails here too)")
+        cat = _new((B, C + Cs, 2 * H, 2 * W), x)
+        check(lib.b200sep_upsample2x_bilinear_f32(_ptr(x), _ptr(cat), B, C, H, W, C + Cs, 0, _stream()), "upsample2x_bilinear_f32")
+        d = (Ws - 2 * W) // 2  # crop_center: time axis (spec_utils.py:50-71)
+        copy_view(skip[:, :, :, d : d + 2 * W], cat[:, C:])
+        return self._cba(cat, p + ".conv")
+
+    def _base(self, x, p):
+        skips = []
+        for i in range(1, self.n_enc + 1):
+            s = self._cba(x, f"{p}.enc{i}.conv1", act=ACT_LEAKY)
+            x = self._cba(s, f"{p}.enc{i}.conv2", stride=2, act=ACT_LEAKY)
+            skips.append(s)
+        x = self._aspp(x, f"{p}.aspp")
+        for i in range(self.n_enc, 0, -1):
+            x = self._dec(x, skips[i - 1], f"{p}.dec{i}")
+        return x
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x (B, 2, >= max_bin, W) magnitudes -> mask (B, 2, output_bin, W) (CascadedASPPNet.forward, eval)."""
+        assert x.dim() == 4 and x.shape[1] == 2 and x.dtype == torch.float32 and x.is_cuda
+        B, _, _, Wd = x.shape
+        mb, c1, c2 = self.max_bin, self.c1, self.c2
+        bw = mb // 2
+        h2 = _new((B, 2 + c1 + c2, mb, Wd), x)  # cat([x, aux1, aux2], 1); its first 2 + c1 channels are stage 2's input
+        copy_view(x[:, :, :mb], h2[:, :2])
+        lo, hi = _new((B, 2, bw, Wd), x), _new((B, 2, mb - bw, Wd), x)
+        copy_view(x[:, :, :bw], lo)
+        copy_view(x[:, :, bw:mb], hi)
+        copy_view(self._base(lo, "stg1_low_band_net"), h2[:, 2 : 2 + c1, :bw])
+        copy_view(self._base(hi, "stg1_high_band_net"), h2[:, 2 : 2 + c1, bw:])
+        h1 = _new((B, 2 + c1, mb, Wd), x)
+        copy_view(h2[:, : 2 + c1], h1)
+        self_aux2 = self._base(self._cba(h1, "stg2_bridge"), "stg2_full_band_net")
+        copy_view(self_aux2, h2[:, 2 + c1 :])
+        h = self._base(self._cba(h2, "stg3_bridge"), "stg3_full_band_net")
+        m = conv2d(h, self.W["out.w"], None, 2, (1, 1), act=ACT_SIGMOID)
+        mask = _new((B, 2, self.output_bin, Wd), x)
+        copy_view(m, mask[:, :, :mb])
+        copy_view(m[:, :, mb - 1 : mb].expand(B, 2, self.output_bin - mb, Wd), mask[:, :, mb:])  # F.pad(mode="replicate") on the bin axis
+        return mask
+
+    def predict_mask(self, x: torch.Tensor) -> torch.Tensor:
+        m = self.forward(x)
+        if self.offset > 0:
+            B, _, nb, Wd = m.shape
+            out = _new((B, 2, nb, Wd - 2 * self.offset), m)
+            copy_view(m[:, :, :, self.offset : Wd - self.offset], out)
+            return out
+        return m
+
+
+class VREngine:
+    """The VRSeparator hot path between reading the file and final_process, device resident."""
+
+    def __init__(self, net: VRNet, param: dict, window_size=512, aggression=5, primary_stem="Instrumental", batch_size=1):
+        self.net, self.p = net, param
+        self.window_size, self.batch_size = int(window_size), max(1, int(batch_size))
+        self.aggression, self.primary_stem = int(aggression), primary_stem
+        self.device = net.device
+        p = param
+        if p.get("reverse"):
+            raise NotImplementedError("model parameters with reverse=true are not covered")
+        self.n_bands = len(p["band"])
+        if net.output_bin != p["bins"] + 1:
+            raise ValueError("network bin count does not match the model parameters")
+        self.plans = {d: StftPlan(bp["n_fft"], bp["hl"]) for d, bp in p["band"].items()}
+        self._taps = {}
+        # pre-filter of combine_spectrograms (spec_utils.py:266-277) as a per-bin gain
+        g = np.ones(p["bins"] + 1, np.float64)
+        if p["pre_filter_start"] > 0:
+            if self.n_bands == 1:
+                g = lp_gain(p["bins"] + 1, p["pre_filter_start"], p["pre_filter_stop"])
+            else:
+                gp = 1.0
+                for b in range(p["pre_filter_start"] + 1, p["pre_filter_stop"]):
+                    gp = math.pow(10, -(b - p["pre_filter_start"]) * (3.5 - gp) / 20.0)
+                    g[b] = gp
+        self.pre_gain = torch.from_numpy(g.astype(np.float32)).to(self.device)
+        # synthesis-side band filters of cmb_spectrogram_to_wave (spec_utils.py:341-395)
+        self.syn_gain = {}
+        for d in range(1, self.n_bands + 1):
+            bp = p["band"][d]
+            nb = bp["n_fft"] // 2 + 1
+            g = np.ones(nb, np.float64)
+            if d == self.n_bands:
+                if bp.get("hpf_start", -1) > 0:
+                    g = hp_gain(nb, bp["hpf_start"], bp["hpf_stop"] - 1)
+            elif d == 1:
+                g = lp_gain(nb, bp["lpf_start"], bp["lpf_stop"])
+            else:
+                g = hp_gain(nb, bp["hpf_start"], bp["hpf_stop"] - 1) * lp_gain(nb, bp["lpf_start"], bp["lpf_stop"])
+            self.syn_gain[d] = torch.from_numpy(g.astype(np.float32)).to(self.device)
+
+    # ---- resampling
+    def _resample(self, x: torch.Tensor, orig_sr: int, target_sr: int) -> torch.Tensor:
+        if orig_sr == target_sr:
+            return x
+        g = math.gcd(int(orig_sr), int(target_sr))
+        up, down = int(target_sr) // g, int(orig_sr) // g
+        if (up, down) not in self._taps:
+            taps, pre, _, _ = resample_poly_design(up, down)
+            self._taps[(up, down)] = (torch.from_numpy(taps).to(self.device), pre)
+        taps, pre = self._taps[(up, down)]
+        C, n_in = x.shape
+        n_out = -(-n_in * up // down)
+        y = _new((C, n_out), x)
+        check(lib.b200sep_resample_poly_f32(_ptr(x), _ptr(taps), taps.numel(), up, down, pre, C, n_in, n_out, _ptr(y), _stream()), "resample_poly_f32")
+        return y
+
+    # ---- analysis
+    def _wave_to_spec(self, wave: torch.Tensor, d: int) -> torch.Tensor:
+        """wave_to_spectrogram (spec_utils.py:282-312): (2, n) -> planes (4, n_fft/2+1, 1 + n//hop)."""
+        p, bp = self.p, self.p["band"][d]
+        if p.get("mid_side"):
+            w2 = _new(wave.shape, wave)
+            ew(wave[0], wave[1], w2[0], 0.5, 0.5)
+            ew(wave[0], wave[1], w2[1], 1.0, -1.0)
+            wave = w2
+        elif p.get("mid_side_b2"):
+            w2 = _new(wave.shape, wave)
+            ew(wave[1], wave[0], w2[0], 1.0, 0.5)
+            ew(wave[0], wave[1], w2[1], 1.0, -0.5)
+            wave = w2
+        n = wave.shape[1]
+        n_fft, hop = bp["n_fft"], bp["hl"]
+        frames = 1 + n // hop
+        spec = _new((4, n_fft // 2 + 1, frames), wave)
+        check(lib.b200sep_stft_forward_ex(self.plans[d].handle, _ptr(wave), 2 * n, n, 0, 1, n, frames, n_fft // 2, 1.0, n_fft // 2 + 1, 0, LAYOUT_CFT, 1, _ptr(spec),
+                                          _stream()), "stft_forward_ex")
+        return spec
+
+    def loading_mix(self, wave: torch.Tensor) -> torch.Tensor:
+        """VRSeparator.loading_mix + combine_spectrograms: (2, N) at the top band's rate -> planes (4, bins + 1, frames)."""
+        p, n = self.p, self.n_bands
+        if p["band"][n]["sr"] != p["sr"]:
+            raise NotImplementedError("the top band must be read at the model sample rate")
+        waves, specs = {}, {}
+        for d in range(n, 0, -1):
+            bp = p["band"][d]
+            if d == n:
+                waves[d] = wave.contiguous()
+            else:
+                up_sr = p["band"][d + 1]["sr"]
+                if bp["sr"] != up_sr and bp.get("res_type") != "polyphase":
+                    raise NotImplementedError(f"band {d} is resampled with res_type={bp.get('res_type')}: only polyphase is covered")
+                waves[d] = self._resample(waves[d + 1], up_sr, bp["sr"])
+            specs[d] = self._wave_to_spec(waves[d], d)
+        l = min(s.shape[2] for s in specs.values())
+        out = torch.zeros((4, p["bins"] + 1, l), dtype=torch.float32, device=self.device)
+        off = 0
+        for d in range(1, n + 1):
+            bp = p["band"][d]
+            h = bp["crop_stop"] - bp["crop_start"]
+            copy_view(specs[d][None, :, bp["crop_start"] : bp["crop_stop"], :l], out[None, :, off : off + h])
+            off += h
+        if off > p["bins"]:
+            raise ValueError("Too much bins")
+        if p["pre_filter_start"] > 0:
+            check(lib.b200sep_bin_gain_f32(_ptr(out), _ptr(self.pre_gain), 4, p["bins"] + 1, l, _stream()), "bin_gain_f32")
+        return out
+
+    # ---- inference
+    def _exponents(self):
+        """adjust_aggr (spec_utils.py:472-492): exponent below / above the split bin, per channel."""
+        aggr = float(int(self.aggression) / 100) * 2
+        if aggr == 0:
+            return 1.0, 1.0, 1.0, 1.0
+        if self.primary_stem in NON_ACCOM_STEMS:
+            aggr = 1 - aggr
+        a = [aggr, aggr]
+        corr = self.p.get("aggr_correction")
+        if corr is not None:
+            a[0] += corr["left"]
+            a[1] += corr["right"]
+        return 1 + a[0] / 3, 1 + a[0], 1 + a[1] / 3, 1 + a[1]
+
+    def inference(self, spec: torch.Tensor):
+        """VRSeparator.inference_vr (vr_separator.py:295-366): planes (4, bins+1, frames) -> (y planes, v planes)."""
+        nb, n_frame = spec.shape[1], spec.shape[2]
+        off = self.net.offset
+        roi = self.window_size - 2 * off
+        if roi == 0:
+            roi = self.window_size
+        pad_l, pad_r = off, roi - (n_frame % roi) + off  # make_padding (spec_utils.py:85-96)
+        n_pad = pad_l + n_frame + pad_r
+        mag = torch.zeros((2, nb, n_pad), dtype=torch.float32, device=self.device)
+        check(lib.b200sep_vr_magnitude_pad(_ptr(spec), _ptr(mag), nb, n_frame, n_pad, pad_l, _stream()), "vr_magnitude_pad")
+        mx = _new((1,), mag)
+        check(lib.b200sep_absmax(_ptr(mag), mag.numel(), _ptr(mx), _stream()), "absmax")
+        peak = float(mx.cpu())
+        ew(mag, None, mag, 1.0 / peak if peak > 0 else float("nan"), 0.0)  # X_mag_pad /= X_mag_pad.max()
+        patches = (n_pad - 2 * off) // roi
+        if patches <= 0 or self.window_size - 2 * off <= 0:
+            raise ValueError("Window size error: h1_shape[3] must be greater than h2_shape[3]")
+        mask = _new((2, nb, patches * roi), mag)
+        m4 = mask.view(2, nb, patches, roi)
+        for i in range(0, patches, self.batch_size):
+            b = min(self.batch_size, patches - i)
+            batch = _new((b, 2, nb, self.window_size), mag)
+            src = torch.as_strided(mag, (b, 2, nb, self.window_size), (roi, nb * n_pad, n_pad, 1), storage_offset=i * roi)
+            copy_view(src, batch)
+            pred = self.net.predict_mask(batch)  # (b, 2, nb, roi)
+            copy_view(pred, m4[:, :, i : i + b].permute(2, 0, 1, 3))
+        y, v = _new(spec.shape, spec), _new(spec.shape, spec)
+        e = self._exponents()
+        check(lib.b200sep_vr_apply_mask(_ptr(mask), patches * roi, _ptr(spec), nb, n_frame, self.p["band"][1]["crop_stop"], e[0], e[1], e[2], e[3], _ptr(y), _ptr(v),
+                                        _stream()), "vr_apply_mask")
+        return y, v
+
+    # ---- synthesis
+    def _spec_to_wave(self, s: torch.Tensor, d: int) -> torch.Tensor:
+        """spectrogram_to_wave (spec_utils.py:315-338): planes (4, n_fft/2+1, frames) -> (2, hop*(frames-1))."""
+        bp, p = self.p["band"][d], self.p
+        frames, nb = s.shape[2], s.shape[1]
+        out_len = bp["hl"] * (frames - 1)
+        wave = _new((2, out_len), s)
+        work = _new((lib.b200sep_stft_inverse_work_floats(self.plans[d].handle, 1, frames, nb, LAYOUT_CFT),), s)
+        check(lib.b200sep_stft_inverse_ex(self.plans[d].handle, _ptr(s), 1, frames, nb, LAYOUT_CFT, out_len, bp["n_fft"] // 2, 0, 1.0, _ptr(wave), _ptr(work), _stream()),
+              "stft_inverse_ex")
+        if p.get("mid_side"):
+            w2 = _new(wave.shape, wave)
+            ew(wave[0], wave[1], w2[0], 1.0, 0.5)
+            ew(wave[0], wave[1], w2[1], 1.0, -0.5)
+            return w2
+        if p.get("mid_side_b2"):
+            w2 = _new(wave.shape, wave)
+            ew(wave[1], wave[0], w2[0], 1 / 1.25, 0.4)
+            ew(wave[0], wave[1], w2[1], 1 / 1.25, -0.4)
+            return w2
+        return wave
+
+    def spec_to_wav(self, spec_m: torch.Tensor) -> torch.Tensor:
+        """cmb_spectrogram_to_wave (spec_utils.py:341-395): planes (4, bins+1, frames) -> (2, hop_top*(frames-1))."""
+        p, n = self.p, self.n_bands
+        frames = spec_m.shape[2]
+        off = 0
+        wave = None
+        for d in range(1, n + 1):
+            bp = p["band"][d]
+            nb = bp["n_fft"] // 2 + 1
+            s = torch.zeros((4, nb, frames), dtype=torch.float32, device=self.device)
+            h = bp["crop_stop"] - bp["crop_start"]
+            copy_view(spec_m[None, :, off : off + h], s[None, :, bp["crop_start"] : bp["crop_stop"]])
+            off += h
+            filtered = (d == n and bp.get("hpf_start", -1) > 0) or d < n
+            if filtered:
+                check(lib.b200sep_bin_gain_f32(_ptr(s), _ptr(self.syn_gain[d]), 4, nb, frames, _stream()), "bin_gain_f32")
+            w_d = self._spec_to_wave(s, d)
+            if d == n:
+                wave = w_d if n == 1 else ew(wave, w_d, wave)
+            else:
+                if d > 1:
+                    w_d = ew(wave, w_d, w_d)
+                wave = self._resample(w_d, bp["sr"], p["band"][d + 1]["sr"])
+        return wave
+
+    def separate(self, wave: np.ndarray):
+        """(2, N) host -> primary (2, M), secondary (2, M) host float32, M = hop_top * (frames - 1)."""
+        wd = torch.from_numpy(np.ascontiguousarray(wave, dtype=np.float32)).to(self.device)
+        spec = self.loading_mix(wd)
+        y, v = self.inference(spec)
+        return self.spec_to_wav(y).cpu().numpy(), self.spec_to_wav(v).cpu().numpy()

@@ -49,7 +49,7 @@ class Separator:
             raise NotImplementedError("ensembles / file-level chunking are outside the B200 hot-path scope")
         self.arch_specific_params = {
             "MDX": {"hop_length": 1024, "segment_size": 256, "overlap": 0.25, "batch_size": 1, "enable_denoise": False, **(mdx_params or {})},
-            "VR": dict(vr_params or {}), "Demucs": {"segment_size": "Default", "shifts": 2, "overlap": 0.25, "segments_enabled": True, **(demucs_params or {})}, "MDXC": {"segment_size": 256, "override_model_segment_size": False, "batch_size": 1, "overlap": 8, "pitch_shift": 0, **(mdxc_params or {})},
+            "VR": {"batch_size": 1, "window_size": 512, "aggression": 5, "enable_tta": False, "enable_post_process": False, "post_process_threshold": 0.2, "high_end_process": False, **(vr_params or {})}, "Demucs": {"segment_size": "Default", "shifts": 2, "overlap": 0.25, "segments_enabled": True, **(demucs_params or {})}, "MDXC": {"segment_size": 256, "override_model_segment_size": False, "batch_size": 1, "overlap": 8, "pitch_shift": 0, **(mdxc_params or {})},
         }
         self.torch_device = self.torch_device_cpu = torch.device("cpu")
         self.torch_device_mps = None
@@ -92,7 +92,7 @@ class Separator:
         if not os.path.isfile(model_path):
             raise FileNotFoundError(f"{model_path} not found (this build does not download models)")
         model_data = self.load_model_data(model_path)
-        model_type = model_data.get("b200_arch") or ("MDXC" if "audio" in model_data and "model" in model_data else (
+        model_type = model_data.get("b200_arch") or ("VR" if "vr_model_param" in model_data else None) or ("MDXC" if "audio" in model_data and "model" in model_data else (
             "Demucs" if "models" in model_data and model_path.lower().endswith((".yaml", ".yml")) else ("MDX" if model_path.lower().endswith((".onnx", ".npz")) else None)))
         classes = {"MDX": "mdx_separator.MDXSeparator", "VR": "vr_separator.VRSeparator", "Demucs": "demucs_separator.DemucsSeparator", "MDXC": "mdxc_separator.MDXCSeparator"}
         if model_type not in classes:

@@ -17,17 +17,19 @@ struct ConvGenParams {
   float* y;
   int B, Cin, H, W, Cout, CoutPad, Ho, Wo;
   int PH, PW;         // zero padding (top / left); bottom / right are implied by Ho, Wo
-  int act;            // 0 none, 1 ReLU, 2 GELU(erf), 3 LeakyReLU(0.01) -- applied after bias (+ add when add_before_act)
+  int act;            // 0 none, 1 ReLU, 2 GELU(erf), 3 LeakyReLU(0.01), 4 sigmoid -- applied after bias (+ add when add_before_act)
   int add_before_act;
   // transposed-convolution scatter: GEMM column co' = r * CoutReal + co; output index along the strided axis = q * up + r - trim,
   // kept when 0 <= index < out_len.  up_axis: 0 = none, 1 = H, 2 = W.
   int up_axis, up, trim, out_len, CoutReal;
+  int OutCT, OutCOff;  // the output tensor has OutCT channels and this convolution fills [OutCOff, OutCOff + Cout) (torch.cat fused away)
 };
 
 __device__ __forceinline__ float gen_act(float v, int act) {
   if (act == 1) return fmaxf(v, 0.f);
   if (act == 2) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
   if (act == 3) return v > 0.f ? v : 0.01f * v;
+  if (act == 4) return 1.f / (1.f + expf(-v));
   return v;
 }
 
@@ -117,22 +119,23 @@ __global__ void __launch_bounds__(GNT) conv_gen_kernel(ConvGenParams p) {
     for (int i = 0; i < 4; ++i) {
       const int wq = wbase + i;
       if (wq >= p.Wo) continue;
-      int64_t o;
+      int64_t o, o_add;
       if (p.up_axis == 0) {
-        o = (((int64_t)b * p.Cout + co) * p.Ho + h) * p.Wo + wq;
+        o = (((int64_t)b * p.OutCT + p.OutCOff + co) * p.Ho + h) * p.Wo + wq;
+        o_add = (((int64_t)b * p.Cout + co) * p.Ho + h) * p.Wo + wq;
       } else if (p.up_axis == 1) {  // scatter along H
         const int ho = h * p.up + r_up - p.trim;
         if (ho < 0 || ho >= p.out_len) continue;
-        o = (((int64_t)b * p.CoutReal + c_real) * p.out_len + ho) * p.Wo + wq;
+        o = o_add = (((int64_t)b * p.CoutReal + c_real) * p.out_len + ho) * p.Wo + wq;
       } else {  // scatter along W
         const int wo = wq * p.up + r_up - p.trim;
         if (wo < 0 || wo >= p.out_len) continue;
-        o = (((int64_t)b * p.CoutReal + c_real) * p.Ho + h) * p.out_len + wo;
+        o = o_add = (((int64_t)b * p.CoutReal + c_real) * p.Ho + h) * p.out_len + wo;
       }
       float v = acc[i][j] + bias;
-      if (p.add && p.add_before_act) v += __ldg(&p.add[o]);
+      if (p.add && p.add_before_act) v += __ldg(&p.add[o_add]);
       v = gen_act(v, p.act);
-      if (p.add && !p.add_before_act) v += __ldg(&p.add[o]);
+      if (p.add && !p.add_before_act) v += __ldg(&p.add[o_add]);
       p.y[o] = v;
     }
   }
@@ -160,12 +163,15 @@ using namespace b200sep;
 
 extern "C" int b200sep_conv2d_f32(const float* x, const float* w_blocked, const float* bias, const float* add, float* y, int B, int Cin, int H, int W, int Cout,
                                   int Ho, int Wo, int KH, int KW, int SH, int SW, int PH, int PW, int DW, int act, int add_before_act, int up_axis, int up,
-                                  int trim, int out_len, void* stream) {
+                                  int trim, int out_len, int out_c_total, int out_c_off, void* stream) {
   B2_CHECK_ARG(x && w_blocked && y && B >= 1 && Cin >= 1 && Cout >= 1 && Ho >= 1 && Wo >= 1, "conv2d_f32: bad argument");
+  B2_CHECK_ARG(out_c_total == 0 || (up_axis == 0 && out_c_off >= 0 && out_c_off + Cout <= out_c_total), "conv2d_f32: bad output channel slice [%d, %d) of %d",
+               out_c_off, out_c_off + Cout, out_c_total);
   ConvGenParams p;
   p.x = x; p.w = w_blocked; p.bias = bias; p.add = add; p.y = y;
   p.B = B; p.Cin = Cin; p.H = H; p.W = W; p.Cout = Cout; p.CoutPad = cdiv(Cout, GTCO) * GTCO; p.Ho = Ho; p.Wo = Wo;
   p.PH = PH; p.PW = PW; p.act = act; p.add_before_act = add_before_act;
+  p.OutCT = out_c_total ? out_c_total : Cout; p.OutCOff = out_c_total ? out_c_off : 0;
   p.up_axis = up_axis; p.up = up; p.trim = trim; p.out_len = out_len; p.CoutReal = up_axis ? Cout / up : Cout;
   B2_CHECK_ARG(up_axis == 0 || (up >= 1 && Cout % up == 0), "conv2d_f32: transposed mode needs Cout divisible by the up factor");
   cudaStream_t st = (cudaStream_t)stream;
@@ -173,6 +179,7 @@ extern "C" int b200sep_conv2d_f32(const float* x, const float* w_blocked, const 
   if (KH == kh && KW == kw && SH == sh && SW == sw && DW == dw) return launch_gen<kh, kw, sh, sw, dw>(p, st);
   B2_CONV_CASE(1, 1, 1, 1, 1)
   B2_CONV_CASE(3, 3, 1, 1, 1)
+  B2_CONV_CASE(3, 3, 2, 2, 1)
   B2_CONV_CASE(1, 3, 1, 1, 1)
   B2_CONV_CASE(1, 3, 1, 1, 2)
   B2_CONV_CASE(8, 1, 4, 1, 1)

@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(kFftThreads) stft_forward_kernel(FftStages st,
                                                                    const float* __restrict__ window, const float* __restrict__ wave,
                                                                    int64_t batch_stride, int64_t chan_stride, int64_t valid_len,
                                                                    int hop, int chunk_len, int frames, int dim_f, int zero_bins,
-                                                                   int layout, float* __restrict__ spec, int frame_offset, float scale) {
+                                                                   int layout, float* __restrict__ spec, int frame_offset, float scale, int zero_pad) {
   extern __shared__ float2 smem[];
   const int N = st.n;
   float2* buf0 = smem;
@@ -160,10 +160,11 @@ __global__ void __launch_bounds__(kFftThreads) stft_forward_kernel(FftStages st,
   const int64_t base = (int64_t)b * batch_stride;
   for (int n = threadIdx.x; n < N; n += blockDim.x) {
     int s = t * hop + n - frame_offset;
+    const bool outside = s < 0 || s >= chunk_len;
     if (s < 0) s = -s;                                // reflect (torch.stft center=True, pad_mode="reflect")
     if (s >= chunk_len) s = 2 * (chunk_len - 1) - s;
     float xl = 0.f, xr = 0.f;
-    if (valid_len <= 0 || base + s < valid_len) {
+    if (!(zero_pad && outside) && (valid_len <= 0 || base + s < valid_len)) {  // zero_pad: librosa.stft's pad_mode="constant"
       xl = __ldg(&wave[base + s]);
       xr = __ldg(&wave[base + chan_stride + s]);
     }
@@ -421,7 +422,7 @@ extern "C" int b200sep_stft_forward(const b200sep_stft_plan* plan, const float* 
   dim3 grid(frames, batch);
   stft_forward_kernel<<<grid, kFftThreads, fft_smem_bytes(plan->n_fft), (cudaStream_t)stream>>>(
       plan->st, plan->twiddle, plan->window, wave, batch_stride, chan_stride, valid_len, plan->hop, chunk_len, frames, dim_f, zero_bins,
-      layout, spec, plan->n_fft / 2, 1.0f);
+      layout, spec, plan->n_fft / 2, 1.0f, 0);
   B2_LAUNCHED();
   return B200SEP_OK;
 }
@@ -431,18 +432,20 @@ extern "C" int b200sep_stft_forward(const b200sep_stft_plan* plan, const float* 
 // reflect pad 3*hop/2, frames 2..2+le kept, last bin dropped) is frame_offset = 3*hop/2, frames = ceil(T/hop), scale = n_fft^-1/2, dim_f = n_fft/2.
 extern "C" int b200sep_stft_forward_ex(const b200sep_stft_plan* plan, const float* wave, int64_t batch_stride, int64_t chan_stride, int64_t valid_len,
                                        int batch, int chunk_len, int frames, int frame_offset, float scale, int dim_f, int zero_bins, int layout,
-                                       float* spec, void* stream) {
+                                       int pad_mode, float* spec, void* stream) {
   B2_CHECK_ARG(plan && wave && spec, "stft_forward_ex: NULL argument");
-  B2_CHECK_ARG(batch >= 0 && chunk_len > 0 && frames >= 1, "stft_forward_ex: bad sizes");
-  B2_CHECK_ARG(frame_offset >= 0 && frame_offset < chunk_len && (frames - 1) * plan->hop - frame_offset + plan->n_fft - 1 <= 2 * (chunk_len - 1),
+  B2_CHECK_ARG(batch >= 0 && chunk_len > 0 && frames >= 1 && (pad_mode == 0 || pad_mode == 1), "stft_forward_ex: bad sizes");
+  B2_CHECK_ARG(pad_mode == 1 || (frame_offset >= 0 && frame_offset < chunk_len && (frames - 1) * plan->hop - frame_offset + plan->n_fft - 1 <= 2 * (chunk_len - 1)),
                "stft_forward_ex: frames reach beyond a single reflection of the chunk");
+  B2_CHECK_ARG(pad_mode == 0 || (frame_offset >= 0 && frame_offset <= plan->n_fft && (int64_t)(frames - 1) * plan->hop - frame_offset < chunk_len + plan->n_fft),
+               "stft_forward_ex: zero-padded frames lie entirely outside the signal");
   B2_CHECK_ARG(dim_f >= 1 && dim_f <= plan->n_fft / 2 + 1, "stft_forward_ex: dim_f=%d out of range", dim_f);
   B2_CHECK_ARG(layout == B200SEP_LAYOUT_CFT || layout == B200SEP_LAYOUT_CTF, "stft_forward_ex: bad layout %d", layout);
   if (batch == 0) return B200SEP_OK;
   dim3 grid(frames, batch);
   stft_forward_kernel<<<grid, kFftThreads, fft_smem_bytes(plan->n_fft), (cudaStream_t)stream>>>(
       plan->st, plan->twiddle, plan->window, wave, batch_stride, chan_stride, valid_len, plan->hop, chunk_len, frames, dim_f, zero_bins, layout, spec,
-      frame_offset, scale);
+      frame_offset, scale, pad_mode);
   B2_LAUNCHED();
   return B200SEP_OK;
 }

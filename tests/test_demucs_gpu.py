@@ -175,7 +175,7 @@ def test_spec_ispec_vs_torch(dm, small):
     ref = torch.view_as_real(zz).permute(0, 1, 4, 2, 3).reshape(1, 4, nfft // 2, le)
     spec = torch.empty((1, 4, nfft // 2, le), device="cuda")
     xd = x.cuda().contiguous()
-    check(lib.b200sep_stft_forward_ex(net.stft.handle, xd.data_ptr(), 2 * T_len, T_len, 0, 1, T_len, le, pad, 1.0 / math.sqrt(nfft), nfft // 2, 0, LAYOUT_CFT, spec.data_ptr(), 0))
+    check(lib.b200sep_stft_forward_ex(net.stft.handle, xd.data_ptr(), 2 * T_len, T_len, 0, 1, T_len, le, pad, 1.0 / math.sqrt(nfft), nfft // 2, 0, LAYOUT_CFT, 0, spec.data_ptr(), 0))
     torch.cuda.synchronize()
     assert (spec.cpu() - ref).abs().max() <= 2e-5 * max(1.0, ref.abs().max())
     # inverse of an arbitrary (non-consistent) spectrogram

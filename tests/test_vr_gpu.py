@@ -1,0 +1,198 @@
+"""GPU parity of the VR path: the operator kernels against ATen / scipy on the CPU, VRNet.predict_mask and the whole
+VRSeparator hot path against golden vectors produced by the UNMODIFIED reference (oracle/make_golden_vr.py), and one full-size
+patch (HP2 capacity, 673 x 512) against the oracle.  Audio tolerance 1e-4 max-abs; masks are compared absolutely (range 0..1)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import mdx_oracle as M
+import vr_oracle as V
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(x):
+    return torch.as_tensor(np.ascontiguousarray(x)).cuda()
+
+
+def planes(spec):
+    """complex (2, bins, frames) -> float planes (4, bins, frames): L re, L im, R re, R im"""
+    return np.stack([spec[0].real, spec[0].imag, spec[1].real, spec[1].imag]).astype(np.float32)
+
+
+def cplx(p):
+    p = np.asarray(p)
+    return np.stack([p[0] + 1j * p[1], p[2] + 1j * p[3]])
+
+
+@pytest.fixture(scope="module")
+def vr(lib_built):
+    assert torch.cuda.is_available()
+    from audio_separator.separator.b200 import vr
+
+    return vr
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "vr_small.npz"))
+
+
+def test_vr_operator_kernels(vr):
+    from audio_separator.separator.b200._lib import check, lib
+    from audio_separator.separator.b200.demucs import block_conv_weight, conv2d
+
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn((2, 6, 21, 40), generator=g)
+    w = torch.randn((6, 1, 3, 3), generator=g)
+    xd, wd = x.cuda(), w.cuda()  # keep the device tensors alive across the raw-pointer calls
+    for dil in (1, 4, 16):
+        y = torch.empty_like(x).cuda()
+        check(lib.b200sep_dwconv3x3_f32(xd.data_ptr(), wd.data_ptr(), y.data_ptr(), 2, 6, 21, 40, dil, 0))
+        torch.cuda.synchronize()
+        assert (y.cpu() - F.conv2d(x, w, padding=dil, dilation=dil, groups=6)).abs().max() <= 1e-5
+    up = torch.zeros((2, 9, 42, 80)).cuda()
+    check(lib.b200sep_upsample2x_bilinear_f32(xd.data_ptr(), up.data_ptr(), 2, 6, 21, 40, 9, 2, 0))
+    torch.cuda.synchronize()
+    ref = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+    assert (up.cpu()[:, 2:8] - ref).abs().max() <= 1e-5 and not up.cpu()[:, :2].any() and not up.cpu()[:, 8:].any()
+    pooled = torch.empty((2, 6, 1, 40)).cuda()
+    check(lib.b200sep_mean_h_f32(xd.data_ptr(), pooled.data_ptr(), 12, 21, 40, 0))
+    torch.cuda.synchronize()
+    assert (pooled.cpu() - F.adaptive_avg_pool2d(x, (1, None))).abs().max() <= 1e-6
+    # strided copy: crop + channel slice + broadcast
+    dst = torch.zeros((2, 10, 21, 30)).cuda()
+    vr.copy_view(xd[:, :, :, 5:35], dst[:, 3:9])
+    vr.copy_view(xd[:, :1, :1, 5:35].expand(2, 1, 21, 30), dst[:, 9:])
+    torch.cuda.synchronize()
+    assert torch.equal(dst.cpu()[:, 3:9], x[:, :, :, 5:35]) and torch.equal(dst.cpu()[:, 9], x[:, 0, :1, 5:35].expand(2, 21, 30)) and not dst.cpu()[:, :3].any()
+    # 3x3 stride-2 convolution with sigmoid into a channel slice
+    wc = torch.randn((5, 6, 3, 3), generator=g) * 0.2
+    b = torch.randn(5, generator=g)
+    out = torch.zeros((2, 8, 11, 20)).cuda()
+    conv2d(xd, dev(block_conv_weight(wc.numpy())), b.cuda(), 5, (3, 3), s=(2, 2), p=(1, 1), act=vr.ACT_SIGMOID, out=out, out_c_off=3)
+    ref = torch.sigmoid(F.conv2d(x, wc, b, stride=2, padding=1))
+    assert (out.cpu()[:, 3:] - ref).abs().max() <= 1e-5 and not out.cpu()[:, :3].any()
+
+
+def test_resample_poly_vs_scipy(vr):
+    import scipy.signal
+
+    from audio_separator.separator.b200._lib import check, lib
+
+    x = np.random.default_rng(3).standard_normal((2, 30011)).astype(np.float32)
+    for up, down in ((1, 3), (1, 2), (2, 1), (3, 1)):
+        taps, pre, _, _ = vr.resample_poly_design(up, down)
+        n_out = -(-x.shape[1] * up // down)
+        y = torch.empty((2, n_out), device="cuda")
+        td, xd = dev(taps), dev(x)
+        check(lib.b200sep_resample_poly_f32(xd.data_ptr(), td.data_ptr(), len(taps), up, down, pre, 2, x.shape[1], n_out, y.data_ptr(), 0))
+        torch.cuda.synchronize()
+        ref = scipy.signal.resample_poly(x, up, down, axis=-1)
+        assert ref.shape == (2, n_out) and np.abs(y.cpu().numpy() - ref).max() <= 2e-6
+
+
+@pytest.mark.parametrize("arch,bins,width", [(31191, 128, 272), (129605, 128, 288)])
+def test_predict_mask_vs_reference_golden(vr, gold, arch, bins, width):
+    w = V.make_weights(arch, seed=arch % 97)
+    net = vr.VRNet(arch, bins * 2, w)
+    m = net.predict_mask(dev(gold[f"mask_in_{arch}"])).cpu().numpy()
+    ref = gold[f"mask_ref_{arch}"]
+    assert m.shape == ref.shape
+    assert np.abs(m - ref).max() <= 2e-5, np.abs(m - ref).max()
+
+
+def test_seven_layer_aspp_and_hp_capacity_vs_oracle(vr):
+    rng = np.random.default_rng(5)
+    for arch in (33966, 123821):
+        w = V.make_weights(arch, seed=arch % 97)
+        cfg = V.VRConfig(param=V.single_band_param(n_fft=128, hl=32, bins=64), nn_architecture=arch, window_size=272)
+        x = np.abs(rng.standard_normal((3, 2, 65, 272))).astype(np.float32)
+        ref = V.predict_mask(w, cfg, x)
+        got = vr.VRNet(arch, 128, w).predict_mask(dev(x)).cpu().numpy()
+        assert np.abs(got - ref).max() <= 2e-5
+
+
+def _engine_1band(vr, **kw):
+    arch = 31191
+    w = V.make_weights(arch, seed=arch % 97)
+    p = V.single_band_param(n_fft=256, hl=64, bins=128)
+    return vr.VREngine(vr.VRNet(arch, 256, w), p, window_size=272, **kw), w, p
+
+
+def test_single_band_path_vs_reference_golden(vr, gold):
+    eng, w, p = _engine_1band(vr, aggression=5, primary_stem="Instrumental", batch_size=3)
+    wave = M.synth_music(int(gold["n_samples"]), seed=int(gold["wave_seed"]))
+    X = eng.loading_mix(dev(wave)).cpu().numpy()
+    assert np.abs(cplx(X) - gold["X_1band"]).max() <= 1e-4
+    prim, sec = eng.separate(wave)
+    assert prim.shape == gold["prim_1band"].shape  # hop * (frames - 1) samples: not the input length
+    assert np.abs(prim - gold["prim_1band"]).max() <= 1e-4 and np.abs(sec - gold["sec_1band"]).max() <= 1e-4
+    # vocal primary stem with aggression 10: exponents flip to 1 - aggr
+    eng_v, _, _ = _engine_1band(vr, aggression=10, primary_stem="Vocals", batch_size=2)
+    y, v = eng_v.inference(dev(planes(gold["X_1band"])))
+    assert np.abs(cplx(y.cpu().numpy()) - gold["y_vocals"]).max() <= 2e-4 * np.abs(gold["y_vocals"]).max()
+
+
+def test_four_band_path_vs_reference_golden_and_oracle(vr, gold):
+    p4 = V.four_band_v2_param()
+    w4 = V.make_weights(33966, seed=5)
+    eng = vr.VREngine(vr.VRNet(33966, 1344, w4), p4, window_size=272, batch_size=2)
+    wave = M.synth_music(int(gold["n_samples4"]), seed=int(gold["wave4_seed"]))
+    X = eng.loading_mix(dev(wave)).cpu().numpy()
+    ref = gold["X_4band"]
+    assert X.shape[1:] == ref.shape[1:] and np.abs(cplx(X) - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
+    y, v = eng.inference(dev(planes(ref)))
+    prim = eng.spec_to_wav(y).cpu().numpy()
+    # reference glue + the Kaiser polyphase stand-in for the libsamplerate up-sampling (parity unpinned for that step)
+    assert prim.shape == gold["prim_4band_standin"].shape == (2, 480 * (ref.shape[2] - 1))
+    assert np.abs(prim - gold["prim_4band_standin"]).max() <= 1e-4
+
+
+def test_full_size_patch_vs_oracle(vr):
+    """HP2 capacity (537238: 64/128-channel stages, seven-branch ASPP) on one 4band_v2 patch (2, 673, 512)."""
+    arch = 537238
+    w = V.make_weights(arch, seed=9)
+    cfg = V.VRConfig(param=V.four_band_v2_param(), nn_architecture=arch)
+    x = np.abs(np.random.default_rng(10).standard_normal((1, 2, 673, 512))).astype(np.float32)
+    x /= x.max()
+    ref = V.predict_mask(w, cfg, x)
+    got = vr.VRNet(arch, 1344, w).predict_mask(dev(x)).cpu().numpy()
+    assert got.shape == ref.shape == (1, 2, 673, 256)
+    assert np.abs(got - ref).max() <= 1e-4, np.abs(got - ref).max()
+
+
+def test_vr_separator_plugin_end_to_end(vr, tmp_path):
+    import wave as wavmod
+
+    from audio_separator.separator import Separator
+
+    arch = 31191
+    w = V.make_weights(arch, seed=3)
+    np.savez(tmp_path / "tiny-vr.npz", **w)
+    (tmp_path / "tiny-vr.json").write_text('{"vr_model_param": "tiny_1band", "primary_stem": "Instrumental", "b200_nn_architecture": 31191}')
+    import json
+
+    p = V.single_band_param(n_fft=256, hl=64, bins=128)
+    (tmp_path / "tiny_1band.json").write_text(json.dumps({k: v for k, v in p.items() if not isinstance(v, bool)}))
+    mix = M.synth_music(30000, seed=8)
+    pcm = (mix.T * 32767).astype("<i2")
+    with wavmod.open(str(tmp_path / "song.wav"), "wb") as wf:
+        wf.setnchannels(2); wf.setsampwidth(2); wf.setframerate(44100); wf.writeframes(pcm.tobytes())
+    sep = Separator(model_file_dir=str(tmp_path), output_dir=str(tmp_path / "out"), vr_params={"window_size": 272, "batch_size": 4, "aggression": 5})
+    sep.load_model("tiny-vr.npz")
+    files = sep.separate(str(tmp_path / "song.wav"))
+    assert files == ["song_(Instrumental)_tiny-vr.wav", "song_(Vocals)_tiny-vr.wav"]
+    loaded = pcm.astype(np.float32).T / 32768.0
+    cfg = V.VRConfig(param=p, nn_architecture=arch, window_size=272, aggression=5, primary_stem="Instrumental")
+    prim, sec = V.separate_arrays(loaded, cfg, lambda b: V.predict_mask(w, cfg, b), batch_size=4)
+    for fname, ref in zip(files, (prim, sec)):
+        with wavmod.open(str(tmp_path / "out" / fname)) as wf:
+            n = wf.getnframes()
+            assert n == ref.shape[1] and wf.getnchannels() == 2
+            got = np.frombuffer(wf.readframes(n), dtype="<i2").astype(np.int32)
+        want = M.to_pcm16(ref.T.copy(), 0.9, 0.0).astype(np.int32)
+        assert np.abs(got - want).max() <= 3
