@@ -4,6 +4,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "tc_f32.cuh"
 
 namespace b200sep {
 
@@ -430,6 +431,8 @@ extern "C" int b200sep_gemm_f32(const float* A, const float* Bw, float* C, int M
                                 int64_t strideB, int64_t strideC, float alpha, const float* bias_n, const float* bias_m, int act, const float* res,
                                 const float* res_scale, void* stream) {
   B2_CHECK_ARG(A && Bw && C && M >= 1 && N >= 1 && K >= 1 && batch >= 1 && batch <= 65535, "gemm_f32: bad argument");
+  if (tc_enabled() && tc_gemm_usable(M, N, K, batch))
+    return tc_gemm_f32(A, Bw, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, alpha, bias_n, bias_m, act, res, res_scale, (cudaStream_t)stream);
   GemmF32 p{A, Bw, C, bias_n, bias_m, res, res_scale, M, N, K, lda, ldb, ldc, strideA, strideB, strideC, alpha, act};
   dim3 grid(cdiv(N, FBN), cdiv(M, FBM), batch);
   B2_CHECK_ARG(grid.y <= 65535, "gemm_f32: M too large");

@@ -1,0 +1,413 @@
+// fp32-in / fp32-out GEMM and implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05, sm_100a).
+//
+// The operands stay plain fp32 tensors in HBM (any strides, batched).  Producer warps read them, split every value on the fly into a
+// bf16 "hi" and a bf16 "lo" part (x ~= hi + lo, 16 mantissa bits) and write both into shared memory in the canonical K-major
+// SWIZZLE_128B layout; one elected thread then issues, per 64-wide k-block, the three products  Ah*Bh + Ah*Bl + Al*Bh  as
+// tcgen05.mma.kind::f16 instructions accumulating in fp32 in TMEM (relative error ~1e-5 per contraction); eight
+// epilogue warps drain the accumulator (tcgen05.ld), apply bias / activation / residual and store fp32.
+//
+//   warp 0        : MMA issuer (lane 0) + TMEM allocation
+//   warps 1..8    : producers: global fp32 -> registers -> split -> swizzled st.shared -> fence.proxy.async -> mbarrier arrive
+//   warps 9..16   : epilogue; warp w owns TMEM lanes 32*(w%4).., the two warps of a lane quadrant split the columns
+//
+// Persistent CTAs (one per SM) walk the (batch, m-tile, n-tile) list; the shared-memory ring (full/empty mbarriers) and the two TMEM
+// accumulators (tmem_full/tmem_empty) run continuously across tiles, so the epilogue of tile i overlaps the main loop of tile i+1.
+//
+// Used by b200sep_gemm_f32 (nn.Linear / attention of the HTDemucs cross-transformer) and b200sep_conv2d_f32 (Demucs encoders /
+// DConv / rewrite convolutions, the VR CascadedASPPNet convolutions) when the shape is large enough; the SIMT kernels in ops_f32.cu /
+// conv_gen.cu remain for tiny or oddly aligned shapes and for the transposed (scatter) convolution.
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "tc_f32.cuh"
+#include "umma.cuh"
+
+namespace b200sep {
+
+namespace {
+
+constexpr int kTM = 128, kTK = 64;
+constexpr int kProducerWarps = 8, kEpilogueWarps = 8;
+constexpr int kThreads = 32 * (1 + kProducerWarps + kEpilogueWarps);  // 544
+constexpr int kProdThreads = 32 * kProducerWarps;
+
+struct TcParams {
+  // A operand (M rows): mode 0 GEMM  a[z*a_sz + m*a_rs + k]  (k contiguous);  mode 1 convolution gather (see below)
+  const float* a;
+  int64_t a_sz, a_rs;
+  // B operand (N rows):  b[z*b_sz + n*b_rs + k*b_ks]   (b_ks == 1: K-major source; b_rs == 1: N-major source, e.g. blocked conv weights)
+  const float* b;
+  int64_t b_sz, b_rs, b_ks;
+  int M, N, K, batch;
+  int n_tile, stages, tmem_cols;
+  int m_tiles, n_tiles, num_tiles, num_iters;
+  uint32_t a_bytes, b_bytes, stage_bytes;
+  int a_vec, b_vec;  // 16-byte aligned K-major sources: float4 loads
+  // convolution geometry (mode 1): x (batch, Cin, H, W), output pixels M = Ho*Wo, K = Cin*KH*KW ordered (ci, kh, kw)
+  int mode, Cin, H, W, Wo, KH, KW, SH, SW, PH, PW, DW;
+  // epilogue: v = acc*alpha + bias_n[n] + bias_m[m]; (+ add before act); act; (+ add after act | res + res_scale[n]*v);
+  // out[z*o_sz + m*o_sm + n*o_sn];  res / add indexed  res[z*r_sz + m*r_sm + n*r_sn]
+  float* out;
+  int64_t o_sz, o_sm, o_sn;
+  const float* res;
+  int64_t r_sz, r_sm, r_sn;
+  const float* res_scale;
+  const float* bias_n;
+  const float* bias_m;
+  float alpha;
+  int act, add_before_act;
+};
+
+__device__ __forceinline__ float tc_act(float v, int act) {
+  if (act == 1) return fmaxf(v, 0.f);
+  if (act == 2) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+  if (act == 3) return v > 0.f ? v : 0.01f * v;
+  if (act == 4) return 1.f / (1.f + expf(-v));
+  return v;
+}
+
+// x -> (hi, lo) bf16 pair for two values, packed little-endian: element 0 in the low half
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+  const float r0 = x0 - __bfloat162float(h.x), r1 = x1 - __bfloat162float(h.y);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// 8 consecutive k of one row -> one 16-byte chunk in each plane, at the SWIZZLE_128B position of (row, chunk)
+__device__ __forceinline__ void store_chunk(uint8_t* plane_hi, uint8_t* plane_lo, int row, int chunk, const float* v) {
+  uint4 h, l;
+  split2(v[0], v[1], h.x, l.x);
+  split2(v[2], v[3], h.y, l.y);
+  split2(v[4], v[5], h.z, l.z);
+  split2(v[6], v[7], h.w, l.w);
+  const uint32_t off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+  *reinterpret_cast<uint4*>(plane_hi + off) = h;
+  *reinterpret_cast<uint4*>(plane_lo + off) = l;
+}
+
+// K-major source: rows x 64 k, element (r, k) at src[r*rs + k].  pt = producer thread index (0..255).
+__device__ __forceinline__ void fill_kmajor(uint8_t* hi, uint8_t* lo, const float* __restrict__ src, int64_t rs, int rows_tile, int row0, int rows_total, int k0,
+                                            int K, int vec, int pt) {
+  for (int id = pt; id < rows_tile * 8; id += kProdThreads) {
+    const int r = id >> 3, c = id & 7;
+    const int k = k0 + c * 8;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (row0 + r < rows_total && k < K) {
+      const float* p = src + (int64_t)(row0 + r) * rs + k;
+      if (vec && k + 7 < K) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (k + e < K) v[e] = __ldg(p + e);
+      }
+    }
+    store_chunk(hi, lo, r, c, v);
+  }
+}
+
+// row-major ("N-major") source: element (r, k) at src[r + k*ks]; lanes walk consecutive rows so the loads coalesce
+__device__ __forceinline__ void fill_nmajor(uint8_t* hi, uint8_t* lo, const float* __restrict__ src, int64_t ks, int rows_tile, int row0, int rows_total, int k0, int K,
+                                            int pt) {
+  const int sh = (rows_tile == 256) ? 8 : 7;  // tiles are 128 or 256 rows
+  for (int id = pt; id < rows_tile * 8; id += kProdThreads) {
+    const int r = id & (rows_tile - 1), c = id >> sh;
+    const int k = k0 + c * 8;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (row0 + r < rows_total) {
+      const float* p = src + (row0 + r) + (int64_t)k * ks;
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (k + e < K) v[e] = __ldg(p + (int64_t)e * ks);
+    }
+    store_chunk(hi, lo, r, c, v);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) tc_f32_kernel(const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full_bar = empty_bar + p.stages;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(&full_bar[s], kProducerWarps);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full_bar[a], 1);
+      ptx::mbar_init(&tmem_empty_bar[a], kEpilogueWarps);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc_stride = (uint32_t)p.tmem_cols / 2;
+  const int tiles_per_z = p.m_tiles * p.n_tiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = ptx::instr_desc_bf16(kTM, p.n_tile, 0, 0);
+      int s = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, 400 + acc);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_stride;
+        for (int i = 0; i < p.num_iters; ++i) {
+          ptx::mbar_wait(&full_bar[s], phase, 200 + i);
+          ptx::tc_fence_after();
+          const uint32_t st = ptx::smem_u32(smem + (size_t)s * p.stage_bytes);
+          const uint32_t a_hi = st, a_lo = st + p.a_bytes, b_hi = st + 2 * p.a_bytes, b_lo = b_hi + p.b_bytes;
+#pragma unroll
+          for (int j = 0; j < kTK / 16; ++j) {
+            const uint64_t dah = ptx::smem_desc(a_hi + j * 32, 16, 1024, ptx::kLayoutSW128);
+            const uint64_t dal = ptx::smem_desc(a_lo + j * 32, 16, 1024, ptx::kLayoutSW128);
+            const uint64_t dbh = ptx::smem_desc(b_hi + j * 32, 16, 1024, ptx::kLayoutSW128);
+            const uint64_t dbl = ptx::smem_desc(b_lo + j * 32, 16, 1024, ptx::kLayoutSW128);
+            ptx::umma_bf16(d_tmem, dah, dbh, idesc, (i | j) != 0 ? 1u : 0u);
+            ptx::umma_bf16(d_tmem, dah, dbl, idesc, 1u);
+            ptx::umma_bf16(d_tmem, dal, dbh, idesc, 1u);
+          }
+          ptx::umma_commit(&empty_bar[s]);
+          if (++s == p.stages) {
+            s = 0;
+            phase ^= 1;
+          }
+        }
+        ptx::umma_commit(&tmem_full_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp <= kProducerWarps) {
+    // ===== producers =====
+    const int pt = threadIdx.x - 32;
+    int s = 0;
+    uint32_t phase = 0;
+    const int taps = p.KH * p.KW;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int z = tile / tiles_per_z, rem = tile - z * tiles_per_z;
+      const int m0 = (rem / p.n_tiles) * kTM, n0 = (rem % p.n_tiles) * p.n_tile;
+      const float* bz = p.b + (int64_t)z * p.b_sz;
+      // convolution: this thread always fills tile row (pt & 127) -> decode its output pixel once per tile
+      const int arow = pt & (kTM - 1);
+      int hi0 = 0, wi0 = 0;
+      bool arow_ok = false;
+      const float* xz = p.a + (int64_t)z * p.a_sz;
+      if (p.mode == 1) {
+        const int m = m0 + arow;
+        arow_ok = m < p.M;
+        const int ho = m / p.Wo, wo = m - ho * p.Wo;
+        hi0 = ho * p.SH - p.PH;
+        wi0 = wo * p.SW - p.PW;
+      }
+      for (int i = 0; i < p.num_iters; ++i) {
+        ptx::mbar_wait(&empty_bar[s], phase ^ 1, 100 + i);
+        uint8_t* st = smem + (size_t)s * p.stage_bytes;
+        uint8_t* a_hi = st;
+        uint8_t* a_lo = st + p.a_bytes;
+        uint8_t* b_hi = st + 2 * p.a_bytes;
+        uint8_t* b_lo = b_hi + p.b_bytes;
+        const int k0 = i * kTK;
+        if (p.mode == 0) {
+          fill_kmajor(a_hi, a_lo, xz, p.a_rs, kTM, m0, p.M, k0, p.K, p.a_vec, pt);
+        } else {
+          // implicit-GEMM gather: k = (ci, kh, kw); two threads per pixel row take alternate 8-wide chunks
+          for (int c = pt >> 7; c < 8; c += kProdThreads / kTM) {
+            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            int k = k0 + c * 8;
+            if (arow_ok && k < p.K) {
+              int ci = k / taps;
+              int tap = k - ci * taps;
+              int kh = tap / p.KW, kw = tap - kh * p.KW;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                if (k + e < p.K) {
+                  const int hi = hi0 + kh, wi = wi0 + kw * p.DW;
+                  if (hi >= 0 && hi < p.H && wi >= 0 && wi < p.W) v[e] = __ldg(&xz[((int64_t)ci * p.H + hi) * p.W + wi]);
+                }
+                if (++kw == p.KW) {
+                  kw = 0;
+                  if (++kh == p.KH) {
+                    kh = 0;
+                    ++ci;
+                  }
+                }
+              }
+            }
+            store_chunk(a_hi, a_lo, arow, c, v);
+          }
+        }
+        if (p.b_ks == 1) fill_kmajor(b_hi, b_lo, bz, p.b_rs, p.n_tile, n0, p.N, k0, p.K, p.b_vec, pt);
+        else fill_nmajor(b_hi, b_lo, bz, p.b_ks, p.n_tile, n0, p.N, k0, p.K, pt);
+        ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core's async proxy
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&full_bar[s]);
+        if (++s == p.stages) {
+          s = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===== epilogue =====
+    const int q = warp & 3;
+    const int half = (warp - 1 - kProducerWarps) >> 2;
+    const int mrow = q * 32 + lane;
+    const int nchunks = p.n_tile / 16;
+    const int ch_begin = half ? nchunks / 2 : 0, ch_end = half ? nchunks : nchunks / 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int z = tile / tiles_per_z, rem = tile - z * tiles_per_z;
+      const int m = (rem / p.n_tiles) * kTM + mrow, n0 = (rem % p.n_tiles) * p.n_tile;
+      const bool row_ok = m < p.M;
+      const float bm = (row_ok && p.bias_m) ? __ldg(&p.bias_m[m]) : 0.f;
+      float* orow = p.out + (int64_t)z * p.o_sz + (int64_t)m * p.o_sm;
+      const float* rrow = p.res ? p.res + (int64_t)z * p.r_sz + (int64_t)m * p.r_sm : nullptr;
+      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase, 300 + acc);
+      ptx::tc_fence_after();
+      const uint32_t trow = tmem_base + (uint32_t)acc * acc_stride + ((uint32_t)(q * 32) << 16);
+      for (int ch = ch_begin; ch < ch_end; ++ch) {
+        const int c0 = ch * 16;
+        if (n0 + c0 >= p.N) break;  // warp-uniform
+        uint32_t v[16];
+        ptx::tmem_ld16(trow + (uint32_t)c0, v);
+        ptx::tmem_ld_wait();
+        if (!row_ok) continue;
+        float x[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int n = n0 + c0 + j;
+          float y = fmaf(__uint_as_float(v[j]), p.alpha, bm);
+          if (n < p.N) {
+            if (p.bias_n) y += __ldg(&p.bias_n[n]);
+            if (rrow && p.add_before_act) y += __ldg(&rrow[(int64_t)n * p.r_sn]);
+            y = tc_act(y, p.act);
+            if (rrow && !p.add_before_act) y = __ldg(&rrow[(int64_t)n * p.r_sn]) + (p.res_scale ? __ldg(&p.res_scale[n]) : 1.f) * y;
+          }
+          x[j] = y;
+        }
+        const int n = n0 + c0;
+        if (p.o_sn == 1 && n + 15 < p.N && ((reinterpret_cast<uintptr_t>(orow + n) & 15) == 0)) {
+          float4* d = reinterpret_cast<float4*>(orow + n);
+          d[0] = make_float4(x[0], x[1], x[2], x[3]);
+          d[1] = make_float4(x[4], x[5], x[6], x[7]);
+          d[2] = make_float4(x[8], x[9], x[10], x[11]);
+          d[3] = make_float4(x[12], x[13], x[14], x[15]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n + j < p.N) orow[(int64_t)(n + j) * p.o_sn] = x[j];
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+int tc_launch(TcParams& p, cudaStream_t st) {
+  p.n_tile = (p.N > 128) ? 256 : 128;
+  p.stages = (p.n_tile == 256) ? 2 : 3;
+  p.tmem_cols = 2 * p.n_tile;
+  p.a_bytes = kTM * 128;
+  p.b_bytes = (uint32_t)p.n_tile * 128;
+  p.stage_bytes = 2 * p.a_bytes + 2 * p.b_bytes;
+  p.m_tiles = cdiv(p.M, kTM);
+  p.n_tiles = cdiv(p.N, p.n_tile);
+  const int64_t nt = (int64_t)p.batch * p.m_tiles * p.n_tiles;
+  B2_CHECK_ARG(nt < (1ll << 31), "tc_f32: too many tiles");
+  p.num_tiles = (int)nt;
+  p.num_iters = cdiv(p.K, kTK);
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2_CUDA(cudaFuncSetAttribute(tc_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  const int grid = std::min(p.num_tiles, kNumSMs);
+  tc_f32_kernel<<<grid, kThreads, smem, st>>>(p);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+bool tc_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("B200SEP_TC");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+bool tc_gemm_usable(int M, int N, int K, int batch) {
+  // tiny problems do not fill a 128 x 128 x 64 tile pipeline; the SIMT kernel is faster there
+  return K >= 32 && N >= 32 && (int64_t)M * N * batch >= 128 * 128;
+}
+
+int tc_gemm_f32(const float* A, const float* Bw, float* C, int M, int N, int K, int lda, int ldb, int ldc, int batch, int64_t sA, int64_t sB, int64_t sC, float alpha,
+                const float* bias_n, const float* bias_m, int act, const float* res, const float* res_scale, cudaStream_t st) {
+  TcParams p{};
+  p.mode = 0;
+  p.a = A; p.a_sz = sA; p.a_rs = lda;
+  p.b = Bw; p.b_sz = sB; p.b_rs = ldb; p.b_ks = 1;
+  p.M = M; p.N = N; p.K = K; p.batch = batch;
+  p.a_vec = (lda % 4 == 0) && (sA % 4 == 0) && aligned16(A);
+  p.b_vec = (ldb % 4 == 0) && (sB % 4 == 0) && aligned16(Bw);
+  p.KH = p.KW = 1;
+  p.out = C; p.o_sz = sC; p.o_sm = ldc; p.o_sn = 1;
+  p.res = res; p.r_sz = sC; p.r_sm = ldc; p.r_sn = 1;
+  p.res_scale = res_scale; p.bias_n = bias_n; p.bias_m = bias_m; p.alpha = alpha; p.act = act; p.add_before_act = 0;
+  return tc_launch(p, st);
+}
+
+bool tc_conv_usable(int Cin, int Cout, int KH, int KW, int Ho, int Wo, int B) {
+  return Cin * KH * KW >= 32 && Cout >= 16 && (int64_t)Ho * Wo * B >= 2048;
+}
+
+int tc_conv2d_f32(const float* x, const float* w_blocked, const float* bias, const float* add, float* y, int B, int Cin, int H, int W, int Cout, int CoutPad, int Ho,
+                  int Wo, int KH, int KW, int SH, int SW, int PH, int PW, int DW, int act, int add_before_act, int out_c_total, int out_c_off, cudaStream_t st) {
+  TcParams p{};
+  p.mode = 1;
+  p.a = x; p.a_sz = (int64_t)Cin * H * W; p.a_rs = 0;
+  p.b = w_blocked; p.b_sz = 0; p.b_rs = 1; p.b_ks = CoutPad;  // [Cin][KH*KW][CoutPad]: k = (ci, tap) rows, output channel contiguous
+  p.M = Ho * Wo; p.N = Cout; p.K = Cin * KH * KW; p.batch = B;
+  p.Cin = Cin; p.H = H; p.W = W; p.Wo = Wo; p.KH = KH; p.KW = KW; p.SH = SH; p.SW = SW; p.PH = PH; p.PW = PW; p.DW = DW;
+  const int64_t P = (int64_t)Ho * Wo;
+  const int ct = out_c_total ? out_c_total : Cout;
+  p.out = y + (int64_t)(out_c_total ? out_c_off : 0) * P; p.o_sz = ct * P; p.o_sm = 1; p.o_sn = P;
+  p.res = add; p.r_sz = (int64_t)Cout * P; p.r_sm = 1; p.r_sn = P;
+  p.res_scale = nullptr; p.bias_n = bias; p.bias_m = nullptr; p.alpha = 1.f; p.act = act; p.add_before_act = add_before_act;
+  return tc_launch(p, st);
+}
+
+}  // namespace b200sep
