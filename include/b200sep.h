@@ -222,7 +222,7 @@ int b200sep_stft_inverse_ex(const b200sep_stft_plan* plan, const float* spec, in
  */
 int b200sep_conv2d_f32(const float* x, const float* w_blocked, const float* bias, const float* add, float* y, int B, int Cin, int H, int W, int Cout,
                        int Ho, int Wo, int KH, int KW, int SH, int SW, int PH, int PW, int DW, int act, int add_before_act, int up_axis, int up,
-                       int trim, int out_len, int out_c_total, int out_c_off, void* stream);
+                       int trim, int out_len, int out_c_total, int out_c_off, const void* w_packed, void* stream);
 /* nn.GroupNorm(1, C), affine, optional activation (demucs.py:141,144).  Channel-first x (B, C, Fr, L): one sample per (b, fr) row
  * (Fr = 1: (B, C, L); Fr > 1: DConv on every frequency row without the permute of hdemucs.py:141-146); channel_last: x (B, L, C)
  * tokens (MyGroupNorm, transformer.py:184-193).
@@ -240,7 +240,13 @@ int b200sep_layernorm_f32(const float* x, const float* gamma, const float* beta,
  * (nn.Linear / in_proj / out_proj / attention scores and values of nn.MultiheadAttention; LayerScale gamma_1/2, transformer.py:268-269) */
 int b200sep_gemm_f32(const float* A, const float* Bw, float* C, int M, int N, int K, int lda, int ldb, int ldc, int batch, int64_t strideA,
                      int64_t strideB, int64_t strideC, float alpha, const float* bias_n, const float* bias_m, int act, const float* res,
-                     const float* res_scale, void* stream);
+                     const float* res_scale, const void* w_packed, void* stream);
+/* Large conv2d_f32 / gemm_f32 calls run on the tensor cores (csrc/tc_f32.cu: fp32 operands split in-kernel into bf16 hi + lo, three
+ * tcgen05 products, fp32 accumulation).  For STATIC B operands (weights) the split can be done once: w_packed (nullable) is the image
+ * tc_pack_*_weights writes into a buffer of b200sep_tc_packed_floats(N, K) floats, K = the GEMM K (linear) or ceil8(Cin)*KH*KW (conv). */
+int64_t b200sep_tc_packed_floats(int N, int K);
+int b200sep_tc_pack_linear_weights(const float* W, int N, int K, int ldw, float* packed, void* stream);
+int b200sep_tc_pack_conv_weights(const float* w_blocked, int Cin, int taps, int Cout, float* packed, void* stream);
 int b200sep_softmax_rows_f32(float* x, int64_t rows, int n, void* stream);
 /* op 0: out = alpha*a + beta*b (b NULL: + beta);  op 1: out = a*b;  with b = device {mean, std} (meanstd_f32):
  * op 2: out = (a - mean) / (1e-5 + std);  op 3: out = a*std + mean  (htdemucs.py:501-510, :588-589, :611-612) */

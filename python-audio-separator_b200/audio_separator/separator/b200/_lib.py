@@ -60,13 +60,16 @@ _SIGS = {
     "b200sep_rect_overlap_add": (i32, [vp, i32, i32, i32, i64, i64, i64, f32, vp, vp]),
     "b200sep_stft_forward_ex": (i32, [vp, vp, i64, i64, i64, i32, i32, i32, i32, f32, i32, i32, i32, i32, vp, vp]),
     "b200sep_stft_inverse_ex": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp, vp, vp]),
-    "b200sep_conv2d_f32": (i32, [vp, vp, vp, vp, vp] + [i32] * 22 + [vp]),
+    "b200sep_conv2d_f32": (i32, [vp, vp, vp, vp, vp] + [i32] * 22 + [vp, vp]),
+    "b200sep_tc_packed_floats": (i64, [i32, i32]),
+    "b200sep_tc_pack_linear_weights": (i32, [vp, i32, i32, i32, vp, vp]),
+    "b200sep_tc_pack_conv_weights": (i32, [vp, i32, i32, i32, vp, vp]),
     "b200sep_groupnorm1_work_floats": (i64, [i32, i32, i32, i64]),
     "b200sep_groupnorm1_f32": (i32, [vp, vp, vp, vp, i32, i32, i32, i64, i32, i32, vp, vp]),
     "b200sep_permute4_f32": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     "b200sep_glu_f32": (i32, [vp, vp, vp, vp, i32, i32, i64, vp]),
     "b200sep_layernorm_f32": (i32, [vp, vp, vp, vp, i64, i32, vp]),
-    "b200sep_gemm_f32": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i64, i64, i64, f32, vp, vp, i32, vp, vp, vp]),
+    "b200sep_gemm_f32": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i64, i64, i64, f32, vp, vp, i32, vp, vp, vp, vp]),
     "b200sep_softmax_rows_f32": (i32, [vp, i64, i32, vp]),
     "b200sep_ew_f32": (i32, [vp, vp, vp, i64, f32, f32, i32, vp]),
     "b200sep_meanstd_f32": (i32, [vp, i64, vp, vp]),

@@ -121,6 +121,26 @@ def _new(shape, like=None, device=None):
     return torch.empty(shape, dtype=torch.float32, device=like.device if like is not None else device)
 
 
+def _packed_conv(wb, cin, taps, cout):
+    """The tensor-core image of a blocked convolution weight (bf16 hi/lo planes in the kernel's shared-memory layout), built once per tensor."""
+    pk = getattr(wb, "_b200_packed", None)
+    if pk is None and cin * taps >= 32 and cout >= 16:
+        cin8 = -(-cin // 8) * 8
+        pk = _new((lib.b200sep_tc_packed_floats(cout, cin8 * taps),), wb)
+        check(lib.b200sep_tc_pack_conv_weights(_ptr(wb), cin, taps, cout, _ptr(pk), _stream()), "tc_pack_conv_weights")
+        wb._b200_packed = pk
+    return pk
+
+
+def _packed_linear(w):
+    pk = getattr(w, "_b200_packed", None)
+    if pk is None and w.shape[0] >= 32 and w.shape[1] >= 32:
+        pk = _new((lib.b200sep_tc_packed_floats(w.shape[0], w.shape[1]),), w)
+        check(lib.b200sep_tc_pack_linear_weights(_ptr(w), w.shape[0], w.shape[1], w.shape[1], _ptr(pk), _stream()), "tc_pack_linear_weights")
+        w._b200_packed = pk
+    return pk
+
+
 def conv2d(x, wb, bias, cout, k, s=(1, 1), p=(0, 0), dw=1, act=ACT_NONE, add=None, add_before_act=False, out_hw=None, out=None, out_c_off=0):
     """x (B,Cin,H,W) -> (B,cout,Ho,Wo);  out_hw overrides the implied output size (right/bottom zero padding is implicit);
     out/out_c_off: write into channels [out_c_off, out_c_off + cout) of an existing (B, C_total, Ho, Wo) tensor (a fused torch.cat)."""
@@ -135,8 +155,10 @@ def conv2d(x, wb, bias, cout, k, s=(1, 1), p=(0, 0), dw=1, act=ACT_NONE, add=Non
     else:
         assert out.shape[0] == B and tuple(out.shape[2:]) == (Ho, Wo), (out.shape, (B, cout, Ho, Wo))
         y, ct = out, out.shape[1]
+    pk = _packed_conv(wb, cin, k[0] * k[1], cout)
     check(lib.b200sep_conv2d_f32(_ptr(x), _ptr(wb), _ptr(bias) if bias is not None else None, _ptr(add) if add is not None else None, _ptr(y), B, cin, H, W, cout,
-                                 Ho, Wo, k[0], k[1], s[0], s[1], p[0], p[1], dw, act, int(add_before_act), 0, 1, 0, 0, ct, out_c_off, _stream()), "conv2d_f32")
+                                 Ho, Wo, k[0], k[1], s[0], s[1], p[0], p[1], dw, act, int(add_before_act), 0, 1, 0, 0, ct, out_c_off,
+                                 _ptr(pk) if pk is not None else None, _stream()), "conv2d_f32")
     return y
 
 
@@ -150,7 +172,7 @@ def conv_transpose(x, wb, bias, cout, axis, stride, trim, out_len, act=ACT_NONE)
         y = _new((B, cout, H, out_len), x)
         k, p, hw = (1, 2), (0, 1), (H, W + 1)
     check(lib.b200sep_conv2d_f32(_ptr(x), _ptr(wb), _ptr(bias), None, _ptr(y), B, cin, H, W, stride * cout, hw[0], hw[1], k[0], k[1], 1, 1, p[0], p[1], 1, act, 0,
-                                 axis, stride, trim, out_len, 0, 0, _stream()), "conv2d_f32(transposed)")
+                                 axis, stride, trim, out_len, 0, 0, None, _stream()), "conv2d_f32(transposed)")
     return y
 
 
@@ -189,13 +211,15 @@ def linear(x2d, w, bias, act=ACT_NONE, res=None, res_scale=None):
     M, K = x2d.shape
     N = w.shape[0]
     y = _new((M, N), x2d)
+    pk = _packed_linear(w)
     check(lib.b200sep_gemm_f32(_ptr(x2d), _ptr(w), _ptr(y), M, N, K, K, K, N, 1, 0, 0, 0, 1.0, _ptr(bias) if bias is not None else None, None, act,
-                               _ptr(res) if res is not None else None, _ptr(res_scale) if res_scale is not None else None, _stream()), "gemm_f32")
+                               _ptr(res) if res is not None else None, _ptr(res_scale) if res_scale is not None else None, _ptr(pk) if pk is not None else None,
+                               _stream()), "gemm_f32")
     return y
 
 
 def _gemm_raw(a_ptr, b_ptr, c_ptr, M, N, K, lda, ldb, ldc, batch, sA, sB, sC, alpha=1.0, bias_n=None, bias_m=None):
-    check(lib.b200sep_gemm_f32(a_ptr, b_ptr, c_ptr, M, N, K, lda, ldb, ldc, batch, sA, sB, sC, alpha, bias_n, bias_m, 0, None, None, _stream()), "gemm_f32")
+    check(lib.b200sep_gemm_f32(a_ptr, b_ptr, c_ptr, M, N, K, lda, ldb, ldc, batch, sA, sB, sC, alpha, bias_n, bias_m, 0, None, None, None, _stream()), "gemm_f32")
 
 
 # --------------------------------------------------------------------------------------------------------- the network
@@ -220,6 +244,12 @@ class HTDemucsNet:
                     a = block_conv_weight(a)  # (co, ci, K, 1) freq conv / (co, ci, 3, 3) rewrite / (co, ci, 1, 1)
                 else:  # Conv1d (co, ci, k) -> kernel (1, k)
                     a = block_conv_weight(a.reshape(a.shape[0], a.shape[1], 1, a.shape[2]))
+            if name.endswith("in_proj_weight") or name.endswith("in_proj_bias"):  # nn.MultiheadAttention packs q, k, v: keep three persistent tensors
+                D = a.shape[0] // 3
+                kind = "weight" if name.endswith("weight") else "bias"
+                for j, nm in enumerate("qkv"):
+                    self.W[name.replace(f"in_proj_{kind}", f"{nm}_{kind}")] = torch.from_numpy(np.ascontiguousarray(a[j * D : (j + 1) * D])).to(self.device)
+                continue
             self.W[name] = torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
         # ScaledEmbedding.forward * freq_emb weight (hdemucs.py:62-64, htdemucs.py:539-541): added after encoder 0, shape (C, Fr)
         emb = st["freq_emb.embedding.weight"] * np.float32(cfg.emb_scale)  # (Fr, C)
@@ -306,12 +336,11 @@ class HTDemucsNet:
         Lk = kv_in.shape[1]
         H = self.cfg.t_heads
         hd = D // H
-        Wi, bi = W[f"{p}.in_proj_weight"], W[f"{p}.in_proj_bias"]
-        q = linear(q_in.view(B * Lq, D), Wi[:D], bi[:D])
-        k = linear(kv_in.view(B * Lk, D), Wi[D : 2 * D], bi[D : 2 * D])
+        q = linear(q_in.view(B * Lq, D), W[f"{p}.q_weight"], W[f"{p}.q_bias"])
+        k = linear(kv_in.view(B * Lk, D), W[f"{p}.k_weight"], W[f"{p}.k_bias"])
         # V^T per batch: (D, Lk) = Wv (D,D) @ kv^T, bias per row
         vt = _new((B, D, Lk), q_in)
-        wv, bv = Wi[2 * D :], bi[2 * D :]
+        wv, bv = W[f"{p}.v_weight"], W[f"{p}.v_bias"]
         _gemm_raw(_ptr(wv), _ptr(kv_in), _ptr(vt), D, Lk, D, D, D, Lk, B, 0, Lk * D, D * Lk, bias_m=_ptr(bv))
         o = _new((B, Lq, D), q_in)
         sc = _new((H, Lq, Lk), q_in)

@@ -164,7 +164,7 @@ using namespace b200sep;
 
 extern "C" int b200sep_conv2d_f32(const float* x, const float* w_blocked, const float* bias, const float* add, float* y, int B, int Cin, int H, int W, int Cout,
                                   int Ho, int Wo, int KH, int KW, int SH, int SW, int PH, int PW, int DW, int act, int add_before_act, int up_axis, int up,
-                                  int trim, int out_len, int out_c_total, int out_c_off, void* stream) {
+                                  int trim, int out_len, int out_c_total, int out_c_off, const void* w_packed, void* stream) {
   B2_CHECK_ARG(x && w_blocked && y && B >= 1 && Cin >= 1 && Cout >= 1 && Ho >= 1 && Wo >= 1, "conv2d_f32: bad argument");
   B2_CHECK_ARG(out_c_total == 0 || (up_axis == 0 && out_c_off >= 0 && out_c_off + Cout <= out_c_total), "conv2d_f32: bad output channel slice [%d, %d) of %d",
                out_c_off, out_c_off + Cout, out_c_total);
@@ -177,7 +177,8 @@ extern "C" int b200sep_conv2d_f32(const float* x, const float* w_blocked, const 
   B2_CHECK_ARG(up_axis == 0 || (up >= 1 && Cout % up == 0), "conv2d_f32: transposed mode needs Cout divisible by the up factor");
   cudaStream_t st = (cudaStream_t)stream;
   if (up_axis == 0 && tc_enabled() && tc_conv_usable(Cin, Cout, KH, KW, Ho, Wo, B))
-    return tc_conv2d_f32(x, w_blocked, bias, add, y, B, Cin, H, W, Cout, p.CoutPad, Ho, Wo, KH, KW, SH, SW, PH, PW, DW, act, add_before_act, out_c_total, out_c_off, st);
+    return tc_conv2d_f32(x, w_blocked, bias, add, y, B, Cin, H, W, Cout, p.CoutPad, Ho, Wo, KH, KW, SH, SW, PH, PW, DW, act, add_before_act, out_c_total, out_c_off, w_packed,
+                         st);
 #define B2_CONV_CASE(kh, kw, sh, sw, dw) \
   if (KH == kh && KW == kw && SH == sh && SW == sw && DW == dw) return launch_gen<kh, kw, sh, sw, dw>(p, st);
   B2_CONV_CASE(1, 1, 1, 1, 1)

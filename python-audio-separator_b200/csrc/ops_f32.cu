@@ -429,10 +429,11 @@ extern "C" int b200sep_layernorm_f32(const float* x, const float* gamma, const f
 
 extern "C" int b200sep_gemm_f32(const float* A, const float* Bw, float* C, int M, int N, int K, int lda, int ldb, int ldc, int batch, int64_t strideA,
                                 int64_t strideB, int64_t strideC, float alpha, const float* bias_n, const float* bias_m, int act, const float* res,
-                                const float* res_scale, void* stream) {
+                                const float* res_scale, const void* w_packed, void* stream) {
   B2_CHECK_ARG(A && Bw && C && M >= 1 && N >= 1 && K >= 1 && batch >= 1 && batch <= 65535, "gemm_f32: bad argument");
   if (tc_enabled() && tc_gemm_usable(M, N, K, batch))
-    return tc_gemm_f32(A, Bw, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, alpha, bias_n, bias_m, act, res, res_scale, (cudaStream_t)stream);
+    return tc_gemm_f32(A, Bw, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, alpha, bias_n, bias_m, act, res, res_scale,
+                       (batch == 1 || strideB == 0) ? w_packed : nullptr, (cudaStream_t)stream);
   GemmF32 p{A, Bw, C, bias_n, bias_m, res, res_scale, M, N, K, lda, ldb, ldc, strideA, strideB, strideC, alpha, act};
   dim3 grid(cdiv(N, FBN), cdiv(M, FBM), batch);
   B2_CHECK_ARG(grid.y <= 65535, "gemm_f32: M too large");
@@ -474,4 +475,18 @@ extern "C" int b200sep_triangle_overlap_add(const float* segs, int n_segs, int c
   tri_ola_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(segs, n_segs, channels, seg_len, stride, length, q0, n_out, scale, chan_scale, accumulate, out);
   B2_LAUNCHED();
   return B200SEP_OK;
+}
+
+extern "C" int64_t b200sep_tc_packed_floats(int N, int K) { return (N >= 1 && K >= 1) ? tc_packed_bytes(N, K) / 4 : 0; }
+
+extern "C" int b200sep_tc_pack_linear_weights(const float* W, int N, int K, int ldw, float* packed, void* stream) {
+  B2_CHECK_ARG(W && packed && N >= 1 && K >= 1 && ldw >= K, "tc_pack_linear_weights: bad argument");
+  B2_CHECK_ARG((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "tc_pack_linear_weights: packed must be 16-byte aligned");
+  return tc_pack_linear(W, N, K, ldw, packed, (cudaStream_t)stream);
+}
+
+extern "C" int b200sep_tc_pack_conv_weights(const float* w_blocked, int Cin, int taps, int Cout, float* packed, void* stream) {
+  B2_CHECK_ARG(w_blocked && packed && Cin >= 1 && taps >= 1 && Cout >= 1, "tc_pack_conv_weights: bad argument");
+  B2_CHECK_ARG((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "tc_pack_conv_weights: packed must be 16-byte aligned");
+  return tc_pack_conv(w_blocked, Cin, taps, Cout, cdiv(Cout, 48) * 48, packed, (cudaStream_t)stream);
 }

@@ -47,7 +47,7 @@ struct TcParams {
   uint32_t a_bytes, b_bytes, stage_bytes;
   int a_vec, b_vec;  // 16-byte aligned K-major sources: float4 loads
   // convolution geometry (mode 1): x (batch, Cin, H, W), output pixels M = Ho*Wo, K = Cin*KH*KW ordered (ci, kh, kw)
-  int mode, Cin, H, W, Wo, KH, KW, SH, SW, PH, PW, DW;
+  int mode, Cin, Cin8, H, W, Wo, KH, KW, SH, SW, PH, PW, DW;
   // epilogue: v = acc*alpha + bias_n[n] + bias_m[m]; (+ add before act); act; (+ add after act | res + res_scale[n]*v);
   // out[z*o_sz + m*o_sm + n*o_sn];  res / add indexed  res[z*r_sz + m*r_sm + n*r_sn]
   float* out;
@@ -59,6 +59,9 @@ struct TcParams {
   const float* bias_m;
   float alpha;
   int act, add_before_act;
+  // B operand pre-split into the kernel's shared-memory image (tc_pack_*): per (n-tile, k-block) one [hi plane | lo plane] block that a
+  // single cp.async.bulk drops into the stage -- static weights cost the producer warps nothing
+  const uint8_t* b_packed;
 };
 
 __device__ __forceinline__ float tc_act(float v, int act) {
@@ -90,25 +93,40 @@ __device__ __forceinline__ void store_chunk(uint8_t* plane_hi, uint8_t* plane_lo
   *reinterpret_cast<uint4*>(plane_lo + off) = l;
 }
 
+// The fills below handle their 16-byte chunks ("items") in groups of kG: all global loads of a group are issued before the first
+// conversion / shared store, so every producer thread keeps kG*8 loads in flight (the loop is latency-, not issue-bound).
+constexpr int kG = 4;
+
 // K-major source: rows x 64 k, element (r, k) at src[r*rs + k].  pt = producer thread index (0..255).
 __device__ __forceinline__ void fill_kmajor(uint8_t* hi, uint8_t* lo, const float* __restrict__ src, int64_t rs, int rows_tile, int row0, int rows_total, int k0,
                                             int K, int vec, int pt) {
-  for (int id = pt; id < rows_tile * 8; id += kProdThreads) {
-    const int r = id >> 3, c = id & 7;
-    const int k = k0 + c * 8;
-    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (row0 + r < rows_total && k < K) {
-      const float* p = src + (int64_t)(row0 + r) * rs + k;
-      if (vec && k + 7 < K) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-      } else {
+  const int items = rows_tile * 8;
+  for (int base = pt; base < items; base += kG * kProdThreads) {
+    float v[kG][8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
-          if (k + e < K) v[e] = __ldg(p + e);
+    for (int g = 0; g < kG; ++g) {
+      const int id = base + g * kProdThreads;
+      const int r = id >> 3, c = id & 7;
+      const int k = k0 + c * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[g][e] = 0.f;
+      if (id < items && row0 + r < rows_total && k < K) {
+        const float* p = src + (int64_t)(row0 + r) * rs + k;
+        if (vec && k + 7 < K) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+          v[g][0] = a.x; v[g][1] = a.y; v[g][2] = a.z; v[g][3] = a.w; v[g][4] = b.x; v[g][5] = b.y; v[g][6] = b.z; v[g][7] = b.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (k + e < K) v[g][e] = __ldg(p + e);
+        }
       }
     }
-    store_chunk(hi, lo, r, c, v);
+#pragma unroll
+    for (int g = 0; g < kG; ++g) {
+      const int id = base + g * kProdThreads;
+      if (id < items) store_chunk(hi, lo, id >> 3, id & 7, v[g]);
+    }
   }
 }
 
@@ -116,17 +134,58 @@ __device__ __forceinline__ void fill_kmajor(uint8_t* hi, uint8_t* lo, const floa
 __device__ __forceinline__ void fill_nmajor(uint8_t* hi, uint8_t* lo, const float* __restrict__ src, int64_t ks, int rows_tile, int row0, int rows_total, int k0, int K,
                                             int pt) {
   const int sh = (rows_tile == 256) ? 8 : 7;  // tiles are 128 or 256 rows
-  for (int id = pt; id < rows_tile * 8; id += kProdThreads) {
-    const int r = id & (rows_tile - 1), c = id >> sh;
-    const int k = k0 + c * 8;
-    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (row0 + r < rows_total) {
-      const float* p = src + (row0 + r) + (int64_t)k * ks;
+  const int items = rows_tile * 8;
+  for (int base = pt; base < items; base += kG * kProdThreads) {
+    float v[kG][8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e)
-        if (k + e < K) v[e] = __ldg(p + (int64_t)e * ks);
+    for (int g = 0; g < kG; ++g) {
+      const int id = base + g * kProdThreads;
+      const int r = id & (rows_tile - 1), c = id >> sh;
+      const int k = k0 + c * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[g][e] = 0.f;
+      if (id < items && row0 + r < rows_total) {
+        const float* p = src + (row0 + r) + (int64_t)k * ks;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (k + e < K) v[g][e] = __ldg(p + (int64_t)e * ks);
+      }
     }
-    store_chunk(hi, lo, r, c, v);
+#pragma unroll
+    for (int g = 0; g < kG; ++g) {
+      const int id = base + g * kProdThreads;
+      if (id < items) store_chunk(hi, lo, id & (rows_tile - 1), id >> sh, v[g]);
+    }
+  }
+}
+
+// convolution weights blocked [Cin][taps][CoutPad] (output channel contiguous) read in the kernel's (tap, ci) K order
+__device__ __forceinline__ void fill_conv_weights(uint8_t* hi, uint8_t* lo, const float* __restrict__ w, int64_t cout_pad, int rows_tile, int n0, int N, int k0, int Cin,
+                                                  int Cin8, int taps, int pt) {
+  const int sh = (rows_tile == 256) ? 8 : 7;
+  const int items = rows_tile * 8;
+  for (int base = pt; base < items; base += kG * kProdThreads) {
+    float v[kG][8];
+#pragma unroll
+    for (int g = 0; g < kG; ++g) {
+      const int id = base + g * kProdThreads;
+      const int r = id & (rows_tile - 1), c = id >> sh;
+      const int kg = k0 + c * 8;
+      const int tap = kg / Cin8, ci0 = kg - tap * Cin8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[g][e] = 0.f;
+      if (id < items && n0 + r < N && tap < taps) {
+        const float* p = w + ((int64_t)ci0 * taps + tap) * cout_pad + n0 + r;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (ci0 + e < Cin) v[g][e] = __ldg(p + (int64_t)e * taps * cout_pad);
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < kG; ++g) {
+      const int id = base + g * kProdThreads;
+      if (id < items) store_chunk(hi, lo, id & (rows_tile - 1), id >> sh, v[g]);
+    }
   }
 }
 
@@ -142,7 +201,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f32_kernel(const TcParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      ptx::mbar_init(&full_bar[s], kProducerWarps);
+      ptx::mbar_init(&full_bar[s], kProducerWarps + (p.b_packed ? 1 : 0));
       ptx::mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -201,6 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f32_kernel(const TcParams p) {
     int s = 0;
     uint32_t phase = 0;
     const int taps = p.KH * p.KW;
+    const int64_t plane = (int64_t)p.H * p.W;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int z = tile / tiles_per_z, rem = tile - z * tiles_per_z;
       const int m0 = (rem / p.n_tiles) * kTM, n0 = (rem % p.n_tiles) * p.n_tile;
@@ -228,33 +288,43 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f32_kernel(const TcParams p) {
         if (p.mode == 0) {
           fill_kmajor(a_hi, a_lo, xz, p.a_rs, kTM, m0, p.M, k0, p.K, p.a_vec, pt);
         } else {
-          // implicit-GEMM gather: k = (ci, kh, kw); two threads per pixel row take alternate 8-wide chunks
-          for (int c = pt >> 7; c < 8; c += kProdThreads / kTM) {
-            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            int k = k0 + c * 8;
-            if (arow_ok && k < p.K) {
-              int ci = k / taps;
-              int tap = k - ci * taps;
-              int kh = tap / p.KW, kw = tap - kh * p.KW;
+          // implicit-GEMM gather.  K is ordered (tap, ci) with ci padded to a multiple of 8, so one 16-byte chunk = 8 consecutive input
+          // channels of ONE tap: a single bounds test and 8 loads at a constant stride.  Two threads per pixel row, 4 chunks each.
+          float v[4][8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                if (k + e < p.K) {
-                  const int hi = hi0 + kh, wi = wi0 + kw * p.DW;
-                  if (hi >= 0 && hi < p.H && wi >= 0 && wi < p.W) v[e] = __ldg(&xz[((int64_t)ci * p.H + hi) * p.W + wi]);
+          for (int g = 0; g < 4; ++g) {
+            const int c = (pt >> 7) + 2 * g;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[g][e] = 0.f;
+            const int kg = k0 + c * 8;
+            const int tap = kg / p.Cin8, ci0 = kg - tap * p.Cin8;
+            const int kh = tap / p.KW, kw = tap - kh * p.KW;
+            const int hi = hi0 + kh, wi = wi0 + kw * p.DW;
+            if (arow_ok && tap < taps && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W) {
+              const float* px = xz + ((int64_t)ci0 * p.H + hi) * p.W + wi;
+              if (ci0 + 8 <= p.Cin) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  v[g][e] = __ldg(px);
+                  px += plane;
                 }
-                if (++kw == p.KW) {
-                  kw = 0;
-                  if (++kh == p.KH) {
-                    kh = 0;
-                    ++ci;
-                  }
-                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  if (ci0 + e < p.Cin) v[g][e] = __ldg(px + (int64_t)e * plane);
               }
             }
-            store_chunk(a_hi, a_lo, arow, c, v);
           }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) store_chunk(a_hi, a_lo, arow, (pt >> 7) + 2 * g, v[g]);
         }
-        if (p.b_ks == 1) fill_kmajor(b_hi, b_lo, bz, p.b_rs, p.n_tile, n0, p.N, k0, p.K, p.b_vec, pt);
+        if (p.b_packed) {
+          if (pt == 0) {
+            ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * p.b_bytes);
+            ptx::bulk_load_1d(b_hi, p.b_packed + ((size_t)(n0 / p.n_tile) * p.num_iters + i) * (size_t)(2 * p.b_bytes), 2 * p.b_bytes, &full_bar[s]);
+          }
+        } else if (p.mode == 1) fill_conv_weights(b_hi, b_lo, bz, p.b_ks, p.n_tile, n0, p.N, k0, p.Cin, p.Cin8, taps, pt);
+        else if (p.b_ks == 1) fill_kmajor(b_hi, b_lo, bz, p.b_rs, p.n_tile, n0, p.N, k0, p.K, p.b_vec, pt);
         else fill_nmajor(b_hi, b_lo, bz, p.b_ks, p.n_tile, n0, p.N, k0, p.K, pt);
         ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core's async proxy
         __syncwarp();
@@ -332,8 +402,37 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f32_kernel(const TcParams p) {
   }
 }
 
+static int pick_n_tile(int N) { return (N > 128) ? 256 : 128; }
+
+// one thread per 16-byte chunk of the packed image: (n-tile, k-block, row, chunk)
+__global__ void tc_pack_kernel(const float* __restrict__ src, int conv, int64_t rs, int64_t ks, int N, int K, int Cin, int Cin8, int taps, int n_tile, int num_iters,
+                               uint8_t* __restrict__ packed, int64_t total) {
+  for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(id & 7);
+    const int r = (int)((id >> 3) % n_tile);
+    const int64_t blk = (id >> 3) / n_tile;  // tn * num_iters + i
+    const int i = (int)(blk % num_iters), tn = (int)(blk / num_iters);
+    const int n = tn * n_tile + r, kg = i * kTK + c * 8;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (n < N) {
+      if (conv) {  // src = blocked conv weights [Cin][taps][cout_pad = ks]; kernel K order (tap, ci padded to 8)
+        const int tap = kg / Cin8, ci0 = kg - tap * Cin8;
+        if (tap < taps)
+          for (int e = 0; e < 8; ++e)
+            if (ci0 + e < Cin) v[e] = src[((int64_t)(ci0 + e) * taps + tap) * ks + n];
+      } else {
+        for (int e = 0; e < 8; ++e)
+          if (kg + e < K) v[e] = src[(int64_t)n * rs + kg + e];
+      }
+    }
+    const size_t plane = (size_t)n_tile * 128;
+    uint8_t* base = packed + (size_t)blk * 2 * plane;
+    store_chunk(base, base + plane, r, c, v);
+  }
+}
+
 int tc_launch(TcParams& p, cudaStream_t st) {
-  p.n_tile = (p.N > 128) ? 256 : 128;
+  p.n_tile = pick_n_tile(p.N);
   p.stages = (p.n_tile == 256) ? 2 : 3;
   p.tmem_cols = 2 * p.n_tile;
   p.a_bytes = kTM * 128;
@@ -369,21 +468,45 @@ bool tc_enabled() {
   return on;
 }
 
+int64_t tc_packed_bytes(int N, int K) {
+  const int nt = pick_n_tile(N);
+  return (int64_t)cdiv(N, nt) * cdiv(K, kTK) * 2 * nt * 128;
+}
+
+int tc_pack_linear(const float* W, int N, int K, int ldw, void* packed, cudaStream_t st) {
+  const int nt = pick_n_tile(N), iters = cdiv(K, kTK);
+  const int64_t total = (int64_t)cdiv(N, nt) * iters * nt * 8;
+  tc_pack_kernel<<<(int)std::min<int64_t>(cdiv(total, 256), kNumSMs * 16), 256, 0, st>>>(W, 0, ldw, 1, N, K, 0, 8, 1, nt, iters, (uint8_t*)packed, total);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
+int tc_pack_conv(const float* w_blocked, int Cin, int taps, int Cout, int CoutPad, void* packed, cudaStream_t st) {
+  const int cin8 = (Cin + 7) / 8 * 8, K = cin8 * taps;
+  const int nt = pick_n_tile(Cout), iters = cdiv(K, kTK);
+  const int64_t total = (int64_t)cdiv(Cout, nt) * iters * nt * 8;
+  tc_pack_kernel<<<(int)std::min<int64_t>(cdiv(total, 256), kNumSMs * 16), 256, 0, st>>>(w_blocked, 1, 0, CoutPad, Cout, K, Cin, cin8, taps, nt, iters, (uint8_t*)packed,
+                                                                                          total);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
 bool tc_gemm_usable(int M, int N, int K, int batch) {
   // tiny problems do not fill a 128 x 128 x 64 tile pipeline; the SIMT kernel is faster there
   return K >= 32 && N >= 32 && (int64_t)M * N * batch >= 128 * 128;
 }
 
 int tc_gemm_f32(const float* A, const float* Bw, float* C, int M, int N, int K, int lda, int ldb, int ldc, int batch, int64_t sA, int64_t sB, int64_t sC, float alpha,
-                const float* bias_n, const float* bias_m, int act, const float* res, const float* res_scale, cudaStream_t st) {
+                const float* bias_n, const float* bias_m, int act, const float* res, const float* res_scale, const void* w_packed, cudaStream_t st) {
   TcParams p{};
   p.mode = 0;
+  p.b_packed = (const uint8_t*)w_packed;
   p.a = A; p.a_sz = sA; p.a_rs = lda;
   p.b = Bw; p.b_sz = sB; p.b_rs = ldb; p.b_ks = 1;
   p.M = M; p.N = N; p.K = K; p.batch = batch;
   p.a_vec = (lda % 4 == 0) && (sA % 4 == 0) && aligned16(A);
   p.b_vec = (ldb % 4 == 0) && (sB % 4 == 0) && aligned16(Bw);
-  p.KH = p.KW = 1;
+  p.KH = p.KW = 1; p.Cin8 = 8;
   p.out = C; p.o_sz = sC; p.o_sm = ldc; p.o_sn = 1;
   p.res = res; p.r_sz = sC; p.r_sm = ldc; p.r_sn = 1;
   p.res_scale = res_scale; p.bias_n = bias_n; p.bias_m = bias_m; p.alpha = alpha; p.act = act; p.add_before_act = 0;
@@ -391,16 +514,19 @@ int tc_gemm_f32(const float* A, const float* Bw, float* C, int M, int N, int K, 
 }
 
 bool tc_conv_usable(int Cin, int Cout, int KH, int KW, int Ho, int Wo, int B) {
-  return Cin * KH * KW >= 32 && Cout >= 16 && (int64_t)Ho * Wo * B >= 2048;
+  return Cin * KH * KW >= 32 && Cout >= 16 && (int64_t)Ho * Wo * B >= 512;
 }
 
 int tc_conv2d_f32(const float* x, const float* w_blocked, const float* bias, const float* add, float* y, int B, int Cin, int H, int W, int Cout, int CoutPad, int Ho,
-                  int Wo, int KH, int KW, int SH, int SW, int PH, int PW, int DW, int act, int add_before_act, int out_c_total, int out_c_off, cudaStream_t st) {
+                  int Wo, int KH, int KW, int SH, int SW, int PH, int PW, int DW, int act, int add_before_act, int out_c_total, int out_c_off, const void* w_packed,
+                  cudaStream_t st) {
   TcParams p{};
   p.mode = 1;
+  p.b_packed = (const uint8_t*)w_packed;
   p.a = x; p.a_sz = (int64_t)Cin * H * W; p.a_rs = 0;
   p.b = w_blocked; p.b_sz = 0; p.b_rs = 1; p.b_ks = CoutPad;  // [Cin][KH*KW][CoutPad]: k = (ci, tap) rows, output channel contiguous
-  p.M = Ho * Wo; p.N = Cout; p.K = Cin * KH * KW; p.batch = B;
+  p.Cin8 = (Cin + 7) / 8 * 8;
+  p.M = Ho * Wo; p.N = Cout; p.K = p.Cin8 * KH * KW; p.batch = B;  // K in the kernel's (tap, ci padded to 8) order
   p.Cin = Cin; p.H = H; p.W = W; p.Wo = Wo; p.KH = KH; p.KW = KW; p.SH = SH; p.SW = SW; p.PH = PH; p.PW = PW; p.DW = DW;
   const int64_t P = (int64_t)Ho * Wo;
   const int ct = out_c_total ? out_c_total : Cout;
