@@ -31,7 +31,8 @@
 namespace b200sep {
 
 using bf16 = __nv_bfloat16;
-constexpr int kUmmaThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int kEpiParts = 2;  // epilogue warps per TMEM lane quadrant: the epilogue is latency-bound (0.48 eligible warps per scheduler with 2), so more warps = more overlap
+constexpr int kUmmaThreads = 64 + 128 * kEpiParts;  // warp 0 TMA, warp 1 MMA, then 4 * kEpiParts epilogue warps
 constexpr int kMaxChannels = 1024;  // per-channel scale/shift staged in shared memory (conv modes)
 constexpr int kTileM = 128;
 constexpr int kConvStride = 120;  // output pixels per conv tile (multiple of 8: TMA box starts must be 16-byte aligned)
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
-      ptx::mbar_init(&tmem_empty_bar[a], 8);  // one arrive per epilogue warp
+      ptx::mbar_init(&tmem_empty_bar[a], 4 * kEpiParts);  // one arrive per epilogue warp
     }
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tmA_hi);
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
     // GEMM: 16-column groups; conv modes: 8-column groups (n_c = 48 splits 24/24 between the two warps of a quadrant)
     const int cw = (p.mode == 0) ? 16 : 8;
     const int nchunks = ncol / cw;
-    const int ch_begin = half ? (nchunks + 1) / 2 : 0, ch_end = half ? nchunks : (nchunks + 1) / 2;
+    const int ch_begin = half * nchunks / kEpiParts, ch_end = (half + 1) * nchunks / kEpiParts;  // `half` = which of the kEpiParts column parts
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
