@@ -216,7 +216,7 @@ int b200sep_stft_inverse_ex(const b200sep_stft_plan* plan, const float* spec, in
  * conv2d_f32: nn.Conv1d / nn.Conv2d (hdemucs.py:107,113; demucs.py:147,150) and, with up_axis != 0, nn.ConvTranspose1d/2d
  *   (hdemucs.py:285) expressed as a 2-tap convolution over the coarse index q with up*Cout GEMM columns (column r*Cout+co ->
  *   output index q*up + r - trim, kept inside [0, out_len)).  x (B,Cin,H,W); w_blocked [Cin][KH*KW][ceil48(CoutCols)];
- *   y = act(conv + bias (+ add if add_before_act)) (+ add otherwise).  act: 0 none, 1 ReLU, 2 GELU(erf), 3 LeakyReLU(0.01), 4 sigmoid.
+ *   y = act(conv + bias (+ add if add_before_act)) (+ add otherwise).  act: 0 none, 1 ReLU, 2 GELU(erf), 3 LeakyReLU(0.01), 4 sigmoid, 5 tanh (also gemm_f32).
  *   out_c_total != 0: y has out_c_total channels and this call fills [out_c_off, out_c_off + Cout) (a fused torch.cat; plain convs only).
  *   Supported (KH,KW,SH,SW,DW): (1,1,1,1,1) (3,3,1,1,1) (3,3,2,2,1) (1,3,1,1,1) (1,3,1,1,2) (8,1,4,1,1) (1,8,1,4,1) (2,1,1,1,1) (1,2,1,1,1).
  */
@@ -247,7 +247,8 @@ int b200sep_gemm_f32(const float* A, const float* Bw, float* C, int M, int N, in
 int64_t b200sep_tc_packed_floats(int N, int K);
 int b200sep_tc_pack_linear_weights(const float* W, int N, int K, int ldw, float* packed, void* stream);
 int b200sep_tc_pack_conv_weights(const float* w_blocked, int Cin, int taps, int Cout, float* packed, void* stream);
-int b200sep_softmax_rows_f32(float* x, int64_t rows, int n, void* stream);
+/* in-place softmax over the first n columns of each row (row stride ld >= n; padding columns are left untouched) */
+int b200sep_softmax_rows_f32(float* x, int64_t rows, int n, int64_t ld, void* stream);
 /* op 0: out = alpha*a + beta*b (b NULL: + beta);  op 1: out = a*b;  with b = device {mean, std} (meanstd_f32):
  * op 2: out = (a - mean) / (1e-5 + std);  op 3: out = a*std + mean  (htdemucs.py:501-510, :588-589, :611-612) */
 int b200sep_ew_f32(const float* a, const float* b, float* out, int64_t n, float alpha, float beta, int op, void* stream);
@@ -285,6 +286,27 @@ int b200sep_vr_apply_mask(const float* mask, int mask_stride, const float* spec,
  * y[c][k] = sum_i x[c][i] * taps[(k + n_pre_remove)*down - i*up];  taps = the zero-padded FIR scaled by `up` */
 int b200sep_resample_poly_f32(const float* x, const float* taps, int n_taps, int up, int down, int64_t n_pre_remove, int channels, int64_t n_in,
                               int64_t n_out, float* y, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Operators of the BS-Roformer path (uvr_lib_v5/roformer/bs_roformer.py, attend.py; mdxc_separator.py:272-343).
+ */
+/* RMSNorm (bs_roformer.py:30-37): y = F.normalize(x, dim=-1) * sqrt(C) * gamma on `rows` rows of C columns (row strides ld_in / ld_out:
+ * a band of the band-split input is a column slice) */
+int b200sep_rmsnorm_f32(const float* x, const float* gamma, float* y, int64_t rows, int C, int64_t ld_in, int64_t ld_out, void* stream);
+/* "b n (qkv h d) -> qkv b h n d" + rotary_embed.rotate_queries_or_keys on q and k (bs_roformer.py:67-72; rotary-embedding-torch defaults):
+ * qkv (B, n, 3*H*dh) -> q, k (B, H, n, dh), v_t (B, H, dh, ldv) = V transposed, columns n..ldv-1 zero (ldv: K-major operand of P@V, padded for alignment) */
+int b200sep_rope_split_heads_f32(const float* qkv, const float* freqs, float* q, float* k, float* v_t, int B, int n, int H, int dh, int ldv, void* stream);
+/* out * sigmoid(gates) + "b h n d -> b n (h d)" (bs_roformer.py:76-81): o (B, H, n, dh), gates (B*n, H) -> y (B*n, H*dh) */
+int b200sep_gate_merge_heads_f32(const float* o, const float* gates, float* y, int B, int n, int H, int dh, void* stream);
+/* nn.GLU(dim=-1) of MaskEstimator (bs_roformer.py:175): a (rows, 2C; ld_in) -> y (rows, C; ld_out) */
+int b200sep_glu_rows_f32(const float* a, float* y, int64_t rows, int C, int64_t ld_in, int64_t ld_out, void* stream);
+/* stft_repr * mask as complex numbers and the re-ordering to iSTFT planes (bs_roformer.py:472-484):
+ * stft_tf (B, T, F, 4) and mask (B, n_stems, T, F, 4) with feature order (f, s, c) -> planes (B*n_stems, 4, F, T) [L re, L im, R re, R im] */
+int b200sep_roformer_mask_apply(const float* stft_tf, const float* mask, float* planes, int B, int n_stems, int T, int F, void* stream);
+/* Roformer branch of MDXCSeparator.demix (mdxc_separator.py:310-343): out[c][q] = sum_i window[q - starts[i]] * chunks[i][c][q - starts[i]] /
+ * max(sum_i window[q - starts[i]], 1e-10); chunks (n_chunks, channels, len), starts device int64[n_chunks] */
+int b200sep_overlap_add_starts(const float* chunks, const int64_t* starts, const float* window, int n_chunks, int channels, int len, int64_t n_out, float* out,
+                               void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Self-tests of the tensor-core ("bf16x3 pair") operators in isolation: fp32 device tensors in, the operator runs

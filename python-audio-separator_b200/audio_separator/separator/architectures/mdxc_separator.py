@@ -3,7 +3,8 @@
 Plugin contract of the reference's MDXCSeparator (audio_separator/separator/architectures/mdxc_separator.py:19-228):
 ctor `(common_config, arch_config)` with arch keys segment_size / override_model_segment_size / batch_size / overlap /
 pitch_shift, `separate(path, custom_output_names)`, `demix(mix) -> {instrument: (2, N)}`.  The chunk loop runs on the GPU
-through libb200sep.so (MdxcEngine).  Roformer checkpoints and pitch shifting are not part of this path.
+through libb200sep.so (MdxcEngine for TFC_TDF_net checkpoints, RoformerEngine for BS-Roformer checkpoints -- the Roformer branch of
+demix, mdxc_separator.py:272-343).  Mel-Band Roformer checkpoints and pitch shifting are not part of this path.
 """
 import os
 
@@ -11,6 +12,7 @@ import numpy as np
 import torch
 
 from ..b200.engine import MdxcEngine, TfcNet
+from ..b200.roformer import BSRoformerConfig, BSRoformerNet, RoformerEngine
 from ..common_separator import CommonSeparator, normalize
 
 
@@ -23,20 +25,22 @@ class MDXCSeparator(CommonSeparator):
         self.overlap = arch_config.get("overlap", 8)
         self.batch_size = arch_config.get("batch_size", 1)
         self.pitch_shift = arch_config.get("pitch_shift", 0)
-        if self.is_roformer_model:
-            raise NotImplementedError("Roformer checkpoints are outside the accelerated MDXC path (SURVEY.md section 8f)")
+        self.process_all_stems = arch_config.get("process_all_stems", True)
+        self.is_roformer = bool(self.is_roformer_model)
         if self.pitch_shift:
             raise NotImplementedError("pitch_shift is not part of the accelerated path")
         if not torch.cuda.is_available():
             raise RuntimeError("MDXCSeparator (B200 build) needs a CUDA device: there is no CPU path in this package")
         self.torch_device = torch.device("cuda", torch.cuda.current_device())
-        self.is_primary_stem_main_target = False
+        self.is_primary_stem_main_target = bool(self.model_data_cfgdict["training"].get("target_instrument")) if self.is_roformer else False  # :69
         self.load_model()
 
     def load_model(self):
         """Replaces TFC_TDF_net(config).load_state_dict(torch.load(ckpt)) (mdxc_separator.py:76-116)."""
         cfg = self.model_data_cfgdict
         audio, model, training = cfg["audio"], cfg["model"], cfg["training"]
+        if self.is_roformer:
+            return self._load_roformer(cfg)
         if model.get("norm") != "InstanceNorm" or model.get("act", "gelu") != "gelu" or list(model.get("scale", [2, 2])) != [2, 2]:
             raise ValueError("the B200 TFC_TDF_net supports norm=InstanceNorm, act=gelu, scale=[2,2] (the MDX23C configuration)")
         path = self.model_path
@@ -53,8 +57,40 @@ class MDXCSeparator(CommonSeparator):
         self.engine = MdxcEngine(self.net, audio["n_fft"], audio["hop_length"], audio["dim_f"], dim_t, self.overlap)
         self.model_run = self.engine.model_run
 
+    def _load_roformer(self, cfg):
+        """RoformerLoader.load_model (roformer/roformer_loader.py:82-195): BSRoformer(**model section) + load_state_dict."""
+        model, training = cfg["model"], cfg["training"]
+        if "num_bands" in model or "freqs_per_bands" not in model:
+            raise NotImplementedError("Mel-Band Roformer checkpoints are outside the accelerated path (only BS-Roformer: `freqs_per_bands` in the model section)")
+        rcfg = BSRoformerConfig.from_model_section(model)
+        path = self.model_path
+        if path.lower().endswith(".npz"):
+            with np.load(path) as z:
+                state = {k: z[k] for k in z.files}
+        else:
+            sd = torch.load(path, map_location="cpu", weights_only=True)
+            state = {k: v.float().numpy() for k, v in (sd.get("state_dict", sd)).items()}
+        self.net = BSRoformerNet(rcfg, state, device=self.torch_device)
+        dim_t = self.segment_size if self.override_model_segment_size else cfg["inference"]["dim_t"]  # :281-286
+        self.engine = RoformerEngine(self.net, dim_t, self.overlap, cfg["audio"].get("sample_rate", 44100), len(training["instruments"]), max(1, int(self.batch_size)))
+        self.model_run = self.net.forward
+
+    def _demix_roformer(self, mix):
+        """Roformer branch of demix + the stem dictionary (mdxc_separator.py:272-343, :406-468)."""
+        training = self.model_data_cfgdict["training"]
+        orig = np.ascontiguousarray(mix, dtype=np.float32)
+        out = self.engine.demix_device(torch.as_tensor(orig).to(self.torch_device)).cpu().numpy()
+        if self.net.cfg.num_stems > 1:
+            return {k: v for k, v in zip(training["instruments"], out)}
+        primary = out[0]
+        if self.is_primary_stem_main_target:  # single-target models also return the residual as the secondary stem
+            return {self.primary_stem_name: primary, self.secondary_stem_name: orig - primary}
+        return primary
+
     def demix(self, mix):
         """(2, N) ndarray -> {instrument: (2, N) ndarray} (mdxc_separator.py:406-434) or the single target's array."""
+        if self.is_roformer:
+            return self._demix_roformer(mix)
         out = self.engine.demix_device(torch.as_tensor(np.ascontiguousarray(mix, dtype=np.float32)).to(self.torch_device)).cpu().numpy()
         training = self.model_data_cfgdict["training"]
         if self.net.num_targets > 1:
@@ -68,13 +104,24 @@ class MDXCSeparator(CommonSeparator):
         mix = normalize(wave=np.array(mix, dtype=np.float32), max_peak=self.normalization_threshold, min_peak=self.amplification_threshold)  # :149
         source = self.demix(mix)
         output_files = []
-        if isinstance(source, dict):  # multi-stem models: one file per instrument (:186-214)
-            for stem_name, stem_source in source.items():
-                if self.output_single_stem and self.output_single_stem.lower() != stem_name.lower():
+        if isinstance(source, dict):  # (:156-214)
+            training = self.model_data_cfgdict["training"]
+            stem_list = [training["target_instrument"]] if training.get("target_instrument") else list(training["instruments"])
+            norm = lambda w: normalize(wave=w, max_peak=self.normalization_threshold, min_peak=self.amplification_threshold).T  # noqa: E731
+            if self.process_all_stems and len(stem_list) > 2:  # every stem of a multi-stem model, in the model's order
+                for stem_name in stem_list:
+                    if self.output_single_stem and self.output_single_stem.lower() != stem_name.lower():
+                        continue
+                    path = self.get_stem_output_path(stem_name, custom_output_names)
+                    self.final_process(path, norm(source[stem_name]), stem_name)
+                    output_files.append(path)
+                return output_files
+            self.primary_source, self.secondary_source = norm(source[self.primary_stem_name]), norm(source[self.secondary_stem_name])
+            for name, src in ((self.secondary_stem_name, self.secondary_source), (self.primary_stem_name, self.primary_source)):  # secondary file first
+                if self.output_single_stem and self.output_single_stem.lower() != name.lower():
                     continue
-                path = self.get_stem_output_path(stem_name, custom_output_names)
-                stem = normalize(wave=stem_source, max_peak=self.normalization_threshold, min_peak=self.amplification_threshold).T
-                self.final_process(path, stem, stem_name)
+                path = self.get_stem_output_path(name, custom_output_names)
+                self.final_process(path, src, name)
                 output_files.append(path)
             return output_files
         self.primary_source = normalize(wave=source, max_peak=self.normalization_threshold, min_peak=self.amplification_threshold).T  # :160-182

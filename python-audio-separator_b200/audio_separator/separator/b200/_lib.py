@@ -70,7 +70,7 @@ _SIGS = {
     "b200sep_glu_f32": (i32, [vp, vp, vp, vp, i32, i32, i64, vp]),
     "b200sep_layernorm_f32": (i32, [vp, vp, vp, vp, i64, i32, vp]),
     "b200sep_gemm_f32": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i64, i64, i64, f32, vp, vp, i32, vp, vp, vp, vp]),
-    "b200sep_softmax_rows_f32": (i32, [vp, i64, i32, vp]),
+    "b200sep_softmax_rows_f32": (i32, [vp, i64, i32, i64, vp]),
     "b200sep_ew_f32": (i32, [vp, vp, vp, i64, f32, f32, i32, vp]),
     "b200sep_meanstd_f32": (i32, [vp, i64, vp, vp]),
     "b200sep_triangle_overlap_add": (i32, [vp, i32, i32, i32, i64, i64, i64, i64, f32, vp, i32, vp, vp]),
@@ -82,6 +82,12 @@ _SIGS = {
     "b200sep_vr_magnitude_pad": (i32, [vp, vp, i32, i32, i32, i32, vp]),
     "b200sep_vr_apply_mask": (i32, [vp, i32, vp, i32, i32, i32, f32, f32, f32, f32, vp, vp, vp]),
     "b200sep_resample_poly_f32": (i32, [vp, vp, i32, i32, i32, i64, i32, i64, i64, vp, vp]),
+    "b200sep_rmsnorm_f32": (i32, [vp, vp, vp, i64, i32, i64, i64, vp]),
+    "b200sep_rope_split_heads_f32": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "b200sep_gate_merge_heads_f32": (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
+    "b200sep_glu_rows_f32": (i32, [vp, vp, i64, i32, i64, i64, vp]),
+    "b200sep_roformer_mask_apply": (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
+    "b200sep_overlap_add_starts": (i32, [vp, vp, vp, i32, i32, i32, i64, vp, vp]),
     "b200sep_selftest_umma_gemm": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, vp]),
     "b200sep_selftest_umma_conv3x3": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, vp]),
     "b200sep_selftest_umma_updown": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp]),

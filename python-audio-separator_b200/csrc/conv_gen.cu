@@ -31,6 +31,7 @@ __device__ __forceinline__ float gen_act(float v, int act) {
   if (act == 2) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
   if (act == 3) return v > 0.f ? v : 0.01f * v;
   if (act == 4) return 1.f / (1.f + expf(-v));
+  if (act == 5) return tanhf(v);
   return v;
 }
 

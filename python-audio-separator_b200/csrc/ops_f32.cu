@@ -11,6 +11,9 @@ namespace b200sep {
 __device__ __forceinline__ float f32_act(float v, int act) {
   if (act == 1) return fmaxf(v, 0.f);
   if (act == 2) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+  if (act == 3) return v > 0.f ? v : 0.01f * v;
+  if (act == 4) return 1.f / (1.f + expf(-v));
+  if (act == 5) return tanhf(v);
   return v;
 }
 
@@ -273,9 +276,9 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmF32 p) {
 }
 
 // in-place softmax over the last dimension of (rows, n); one CTA per row
-__global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ x, int n) {
+__global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ x, int n, int64_t ld) {
   __shared__ float red[64];
-  float* r = x + (int64_t)blockIdx.x * n;
+  float* r = x + (int64_t)blockIdx.x * ld;
   float m = -INFINITY;
   for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, r[i]);
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -442,10 +445,10 @@ extern "C" int b200sep_gemm_f32(const float* A, const float* Bw, float* C, int M
   return B200SEP_OK;
 }
 
-extern "C" int b200sep_softmax_rows_f32(float* x, int64_t rows, int n, void* stream) {
-  B2_CHECK_ARG(x && rows >= 0 && n >= 1 && rows <= 0x7fffffff, "softmax_rows_f32: bad argument");
+extern "C" int b200sep_softmax_rows_f32(float* x, int64_t rows, int n, int64_t ld, void* stream) {
+  B2_CHECK_ARG(x && rows >= 0 && n >= 1 && rows <= 0x7fffffff && ld >= n, "softmax_rows_f32: bad argument");
   if (rows == 0) return B200SEP_OK;
-  softmax_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, n);
+  softmax_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, n, ld);
   B2_LAUNCHED();
   return B200SEP_OK;
 }

@@ -1,0 +1,175 @@
+// Operators of the BS-Roformer path (uvr_lib_v5/roformer/bs_roformer.py, attend.py; the Roformer branch of mdxc_separator.py) that are
+// not GEMMs: RMSNorm on (strided) rows, rotary embedding fused with the head split, sigmoid gating fused with the head merge, GLU over
+// the last dimension into a column slice, the complex mask product that also re-orders to iSTFT planes, and the Hamming overlap-add
+// with a weight counter at arbitrary chunk starts.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace b200sep {
+
+// RMSNorm (bs_roformer.py:30-37): y = x / max(||x||_2, 1e-12) * sqrt(C) * gamma; one warp per row; rows may be column slices (ld_in / ld_out)
+__global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, float* __restrict__ y, int64_t rows, int C, int64_t ld_in, int64_t ld_out) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + row * ld_in;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float v = xr[c];
+    s = fmaf(v, v, s);
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float inv = sqrtf((float)C) / fmaxf(sqrtf(s), 1e-12f);
+  float* yr = y + row * ld_out;
+  for (int c = lane; c < C; c += 32) yr[c] = xr[c] * inv * __ldg(&gamma[c]);
+}
+
+// qkv (B, n, 3, H, dh) = the to_qkv output -> q, k (B, H, n, dh) with the rotary embedding applied (positions 0..n-1, interleaved pairs,
+// rotary-embedding-torch defaults) and v TRANSPOSED (B, H, dh, ldv) so the P@V GEMM reads it K-major; columns n..ldv-1 of v are zeroed.
+__global__ void rope_split_kernel(const float* __restrict__ qkv, const float* __restrict__ freqs, float* __restrict__ q, float* __restrict__ k, float* __restrict__ vt,
+                                  int n, int H, int dh, int ldv, int64_t total) {
+  const int half = dh >> 1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int p = (int)(i % half);
+    const int h = (int)((i / half) % H);
+    const int pos = (int)((i / ((int64_t)half * H)) % ldv);
+    const int64_t b = i / ((int64_t)half * H * ldv);
+    const int64_t o_v = (((b * H + h) * dh) + 2 * p) * ldv + pos;
+    if (pos >= n) {  // padding columns of V^T
+      vt[o_v] = 0.f;
+      vt[o_v + ldv] = 0.f;
+      continue;
+    }
+    const float* src = qkv + ((b * n + pos) * 3) * (int64_t)H * dh + (int64_t)h * dh + 2 * p;
+    const float ang = (float)pos * __ldg(&freqs[p]);
+    float sn, cs;
+    sincosf(ang, &sn, &cs);
+    const int64_t o = ((b * H + h) * n + pos) * (int64_t)dh + 2 * p;
+    const float q0 = src[0], q1 = src[1];
+    q[o] = q0 * cs - q1 * sn;      // t*cos + rotate_half(t)*sin, rotate_half = (-x2, x1)
+    q[o + 1] = q1 * cs + q0 * sn;
+    const float k0 = src[(int64_t)H * dh], k1 = src[(int64_t)H * dh + 1];
+    k[o] = k0 * cs - k1 * sn;
+    k[o + 1] = k1 * cs + k0 * sn;
+    vt[o_v] = src[2 * (int64_t)H * dh];
+    vt[o_v + ldv] = src[2 * (int64_t)H * dh + 1];
+  }
+}
+
+// out (B, H, n, dh) * sigmoid(gates (B*n, H)) -> merged (B*n, H*dh)   (bs_roformer.py:78-81)
+__global__ void gate_merge_kernel(const float* __restrict__ o, const float* __restrict__ gates, float* __restrict__ y, int n, int H, int dh, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int d = (int)(i % dh);
+    const int h = (int)((i / dh) % H);
+    const int64_t bn = i / ((int64_t)dh * H);  // b*n + pos
+    const int64_t b = bn / n, pos = bn - b * n;
+    const float g = 1.f / (1.f + expf(-__ldg(&gates[bn * H + h])));
+    y[i] = o[((b * H + h) * n + pos) * (int64_t)dh + d] * g;
+  }
+}
+
+// nn.GLU(dim=-1) on rows (rows, 2C; ld_in) -> (rows, C) written at y with row stride ld_out (a column slice of the mask tensor)
+__global__ void glu_rows_kernel(const float* __restrict__ a, float* __restrict__ y, int C, int64_t ld_in, int64_t ld_out, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t r = i / C;
+    const float u = a[r * ld_in + c], v = a[r * ld_in + C + c];
+    y[r * ld_out + c] = u / (1.f + expf(-v));
+  }
+}
+
+// stft (b, T, F, 4) [feature order (f, s, c)] x mask (b, n, T, F, 4) complex product per (f, s) -> iSTFT planes (b*n, 4, F, T)
+// (bs_roformer.py:472-484: view_as_complex, multiply, "b n (f s) t -> (b n s) f t")
+__global__ void mask_apply_kernel(const float* __restrict__ st, const float* __restrict__ mask, float* __restrict__ out, int n_stems, int T, int F, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    // i indexes the OUTPUT (bn, s, f, t) so the stores coalesce along t
+    const int t = (int)(i % T);
+    const int f = (int)((i / T) % F);
+    const int s = (int)((i / ((int64_t)T * F)) % 2);
+    const int64_t bn = i / ((int64_t)T * F * 2);
+    const int64_t b = bn / n_stems;
+    const float* sp = st + ((b * T + t) * (int64_t)F + f) * 4 + 2 * s;
+    const float* mp = mask + ((bn * T + t) * (int64_t)F + f) * 4 + 2 * s;
+    const float xr = sp[0], xi = sp[1], mr = mp[0], mi = mp[1];
+    const int64_t plane = (int64_t)F * T;
+    float* op = out + (bn * 4 + 2 * s) * plane + (int64_t)f * T + t;
+    op[0] = xr * mr - xi * mi;
+    op[plane] = xr * mi + xi * mr;
+  }
+}
+
+// Roformer branch of MDXCSeparator.demix (mdxc_separator.py:310-343): result += x * window; counter += window; result / clamp(counter, 1e-10)
+// as a gather over the chunks covering each output sample.  chunks (n_chunks, channels, len); chunk i is placed at starts[i].
+__global__ void ola_starts_kernel(const float* __restrict__ chunks, const int64_t* __restrict__ starts, const float* __restrict__ window, int n_chunks, int channels,
+                                  int len, int64_t n_out, float* __restrict__ out) {
+  const int c = blockIdx.y;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_out; q += (int64_t)gridDim.x * blockDim.x) {
+    float acc = 0.f, cnt = 0.f;
+    for (int i = 0; i < n_chunks; ++i) {
+      const int64_t r = q - __ldg(&starts[i]);
+      if (r >= 0 && r < len) {
+        const float w = __ldg(&window[r]);
+        acc = fmaf(__ldg(&chunks[((int64_t)i * channels + c) * len + r]), w, acc);
+        cnt += w;
+      }
+    }
+    out[(int64_t)c * n_out + q] = acc / fmaxf(cnt, 1e-10f);
+  }
+}
+
+static inline int rf_grid(int64_t n) { return (int)std::min<int64_t>(cdiv(n, 256), kNumSMs * 16); }
+
+}  // namespace b200sep
+
+using namespace b200sep;
+
+extern "C" int b200sep_rmsnorm_f32(const float* x, const float* gamma, float* y, int64_t rows, int C, int64_t ld_in, int64_t ld_out, void* stream) {
+  B2_CHECK_ARG(x && gamma && y && rows >= 0 && C >= 1 && ld_in >= C && ld_out >= C, "rmsnorm_f32: bad argument");
+  if (rows == 0) return B200SEP_OK;
+  rmsnorm_kernel<<<(unsigned)cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, gamma, y, rows, C, ld_in, ld_out);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
+extern "C" int b200sep_rope_split_heads_f32(const float* qkv, const float* freqs, float* q, float* k, float* v_t, int B, int n, int H, int dh, int ldv, void* stream) {
+  B2_CHECK_ARG(qkv && freqs && q && k && v_t && B >= 1 && n >= 1 && H >= 1 && dh >= 2 && dh % 2 == 0 && ldv >= n, "rope_split_heads_f32: bad argument");
+  const int64_t total = (int64_t)B * ldv * H * (dh / 2);
+  rope_split_kernel<<<rf_grid(total), 256, 0, (cudaStream_t)stream>>>(qkv, freqs, q, k, v_t, n, H, dh, ldv, total);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
+extern "C" int b200sep_gate_merge_heads_f32(const float* o, const float* gates, float* y, int B, int n, int H, int dh, void* stream) {
+  B2_CHECK_ARG(o && gates && y && B >= 1 && n >= 1 && H >= 1 && dh >= 1, "gate_merge_heads_f32: bad argument");
+  const int64_t total = (int64_t)B * n * H * dh;
+  gate_merge_kernel<<<rf_grid(total), 256, 0, (cudaStream_t)stream>>>(o, gates, y, n, H, dh, total);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
+extern "C" int b200sep_glu_rows_f32(const float* a, float* y, int64_t rows, int C, int64_t ld_in, int64_t ld_out, void* stream) {
+  B2_CHECK_ARG(a && y && rows >= 0 && C >= 1 && ld_in >= 2 * C && ld_out >= C, "glu_rows_f32: bad argument");
+  const int64_t total = rows * C;
+  if (total == 0) return B200SEP_OK;
+  glu_rows_kernel<<<rf_grid(total), 256, 0, (cudaStream_t)stream>>>(a, y, C, ld_in, ld_out, total);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
+extern "C" int b200sep_roformer_mask_apply(const float* stft_tf, const float* mask, float* planes, int B, int n_stems, int T, int F, void* stream) {
+  B2_CHECK_ARG(stft_tf && mask && planes && B >= 1 && n_stems >= 1 && T >= 1 && F >= 1, "roformer_mask_apply: bad argument");
+  const int64_t total = (int64_t)B * n_stems * 2 * F * T;
+  mask_apply_kernel<<<rf_grid(total), 256, 0, (cudaStream_t)stream>>>(stft_tf, mask, planes, n_stems, T, F, total);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
+extern "C" int b200sep_overlap_add_starts(const float* chunks, const int64_t* starts, const float* window, int n_chunks, int channels, int len, int64_t n_out, float* out,
+                                          void* stream) {
+  B2_CHECK_ARG(chunks && starts && window && out && n_chunks >= 1 && channels >= 1 && len >= 1 && n_out >= 1, "overlap_add_starts: bad argument");
+  dim3 grid((unsigned)std::min<int64_t>(cdiv(n_out, 256), kNumSMs * 8), channels);
+  ola_starts_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(chunks, starts, window, n_chunks, channels, len, n_out, out);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}

@@ -121,7 +121,7 @@ def test_groupnorm_glu_layernorm_softmax_permute(dm):
 
     s = (torch.randn((33, 300), generator=g) * 5).cuda()
     ref = torch.softmax(s.cpu(), -1)
-    check(lib.b200sep_softmax_rows_f32(s.data_ptr(), 33, 300, 0))
+    check(lib.b200sep_softmax_rows_f32(s.data_ptr(), 33, 300, 300, 0))
     torch.cuda.synchronize()
     assert (s.cpu() - ref).abs().max() <= 1e-6
     p = torch.randn((2, 3, 4, 5), generator=g).cuda()

@@ -1,0 +1,44 @@
+"""CPU checks of the BS-Roformer side: the oracle against the reference-generated golden and the chunk grid / window of the Roformer branch."""
+import os
+
+import numpy as np
+
+import mdx_oracle as M
+import roformer_oracle as R
+
+SMALL = dict(dim=32, depth=2, time_transformer_depth=1, freq_transformer_depth=2, freqs_per_bands=(2, 2, 4, 4, 8, 12, 16, 17), dim_head=8, heads=4, stft_n_fft=128,
+             stft_hop_length=32, stft_win_length=128, dim_t=65, overlap=8)
+
+
+def test_oracle_matches_reference_golden(golden_dir):
+    z = np.load(os.path.join(golden_dir, "roformer_small.npz"))
+    cfg = R.BSRoformerConfig(**SMALL)
+    w = R.make_weights(cfg, seed=3)
+    mix = M.synth_music(int(z["n_samples"]), seed=int(z["mix_seed"]))
+    y = R.forward(w, cfg, mix[None, :, : cfg.chunk_size])
+    assert y.shape == z["forward_ref"].shape and np.abs(y - z["forward_ref"]).max() <= 2e-5
+    d = R.demix(mix, cfg, lambda c: R.forward(w, cfg, c), n_instruments=2)
+    assert d.shape == (2, 2, mix.shape[1]) and np.abs(d[0] - z["demix_ref"]).max() <= 2e-5
+    assert np.array_equal(d[0], d[1])  # a single-target model broadcasts its output into every row of the result tensor (mdxc_separator.py:313)
+    cfg_o = R.BSRoformerConfig(**dict(SMALL, overlap=0.03))
+    d_o = R.demix(mix, cfg_o, lambda c: R.forward(w, cfg, c), n_instruments=2)
+    assert np.abs(d_o[0] - z["demix_overlap_ref"]).max() <= 2e-5
+
+
+def test_chunk_grid_and_rotary_restatement():
+    cfg = R.BSRoformerConfig(**SMALL)
+    assert cfg.chunk_size == 32 * 64 and cfg.step == cfg.chunk_size  # overlap 8 s * 44100 > chunk: step clamps to the chunk size (no overlap)
+    assert R.BSRoformerConfig(**dict(SMALL, overlap=0.03)).step == 1323
+    assert sum(R.DEFAULT_FREQS_PER_BANDS) == 1025 and len(R.DEFAULT_FREQS_PER_BANDS) == 62
+    import torch
+
+    fr = torch.from_numpy(R.rotary_freqs(8))
+    assert np.allclose(fr.numpy(), 1.0 / 10000 ** (np.arange(0, 8, 2) / 8))
+    t = torch.randn(2, 3, 5, 8)
+    r = R.apply_rotary(t, fr)
+    assert torch.allclose(r[..., 0, :], t[..., 0, :])  # position 0 is not rotated
+    assert torch.allclose((r**2).sum(-1), (t**2).sum(-1), atol=1e-5)  # rotations preserve the norm of every pair
+    # relative-position property: <rot(q, m), rot(k, n)> depends on m - n only
+    q, k = torch.randn(8), torch.randn(8)
+    Q, K = R.apply_rotary(q.repeat(6, 1), fr), R.apply_rotary(k.repeat(6, 1), fr)
+    assert torch.allclose(Q[1] @ K[0], Q[4] @ K[3], atol=1e-5) and torch.allclose(Q[2] @ K[5], Q[0] @ K[3], atol=1e-5)
