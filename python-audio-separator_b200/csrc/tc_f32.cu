@@ -286,6 +286,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f32_kernel(const TcParams p) {
         uint8_t* b_hi = st + 2 * p.a_bytes;
         uint8_t* b_lo = b_hi + p.b_bytes;
         const int k0 = i * kTK;
+        if (p.b_packed && pt == 0) {  // static weights: one bulk copy of the pre-split image, in flight while the A tile is converted
+          ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * p.b_bytes);
+          ptx::bulk_load_1d(b_hi, p.b_packed + ((size_t)(n0 / p.n_tile) * p.num_iters + i) * (size_t)(2 * p.b_bytes), 2 * p.b_bytes, &full_bar[s]);
+        }
         if (p.mode == 0) {
           fill_kmajor(a_hi, a_lo, xz, p.a_rs, kTM, m0, p.M, k0, p.K, p.a_vec, pt);
         } else {
@@ -320,10 +324,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f32_kernel(const TcParams p) {
           for (int g = 0; g < 4; ++g) store_chunk(a_hi, a_lo, arow, (pt >> 7) + 2 * g, v[g]);
         }
         if (p.b_packed) {
-          if (pt == 0) {
-            ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * p.b_bytes);
-            ptx::bulk_load_1d(b_hi, p.b_packed + ((size_t)(n0 / p.n_tile) * p.num_iters + i) * (size_t)(2 * p.b_bytes), 2 * p.b_bytes, &full_bar[s]);
-          }
+          // issued above, right after the stage became free
         } else if (p.mode == 1) fill_conv_weights(b_hi, b_lo, bz, p.b_ks, p.n_tile, n0, p.N, k0, p.Cin, p.Cin8, taps, pt);
         else if (p.b_ks == 1) fill_kmajor(b_hi, b_lo, bz, p.b_rs, p.n_tile, n0, p.N, k0, p.K, p.b_vec, pt);
         else fill_nmajor(b_hi, b_lo, bz, p.b_ks, p.n_tile, n0, p.N, k0, p.K, pt);
