@@ -275,10 +275,42 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmF32 p) {
   }
 }
 
-// in-place softmax over the last dimension of (rows, n); one CTA per row
+// in-place softmax over the first n columns of rows with stride ld; one CTA per row.  Rows of up to 2048 columns are held in registers
+// (one global read + one write per element instead of three reads + two writes): the attention score matrices are HBM-bound.
+constexpr int kSmReg = 8;
 __global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ x, int n, int64_t ld) {
   __shared__ float red[64];
   float* r = x + (int64_t)blockIdx.x * ld;
+  if (n <= 256 * kSmReg) {
+    float v[kSmReg];
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kSmReg; ++j) {
+      const int i = threadIdx.x + j * 256;
+      v[j] = (i < n) ? r[i] : -INFINITY;
+      m = fmaxf(m, v[j]);
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < kSmReg; ++j) {
+      v[j] = expf(v[j] - m);  // exp(-inf) = 0 for the padding slots
+      s += v[j];
+    }
+    const float inv = 1.f / block_sum2(s, 0.f, red).x;
+#pragma unroll
+    for (int j = 0; j < kSmReg; ++j) {
+      const int i = threadIdx.x + j * 256;
+      if (i < n) r[i] = v[j] * inv;
+    }
+    return;
+  }
   float m = -INFINITY;
   for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, r[i]);
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -296,6 +328,40 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ x
   const float tot = block_sum2(s, 0.f, red).x;
   const float inv = 1.f / tot;
   for (int i = threadIdx.x; i < n; i += blockDim.x) r[i] *= inv;
+}
+
+// GEMM with a tiny N (the 8 attention gates of the Roformer, bs_roformer.py:78): one warp per row of A, the N weight rows stay in L1.
+// C[m][n] = act(alpha * A[m] . Bw[n] + bias_n[n] + bias_m[m]) (+ residual as in gemm_f32_kernel)
+constexpr int kSmallN = 16;
+__global__ void __launch_bounds__(256) gemm_small_n_kernel(GemmF32 p) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= p.M) return;
+  const int lane = threadIdx.x & 31;
+  const float* A = p.A + (int64_t)blockIdx.z * p.sA + row * p.lda;
+  const float* Bw = p.Bw + (int64_t)blockIdx.z * p.sB;
+  float acc[kSmallN];
+#pragma unroll
+  for (int j = 0; j < kSmallN; ++j) acc[j] = 0.f;
+  for (int k = lane; k < p.K; k += 32) {
+    const float a = A[k];
+#pragma unroll
+    for (int j = 0; j < kSmallN; ++j)
+      if (j < p.N) acc[j] = fmaf(a, __ldg(&Bw[(int64_t)j * p.ldb + k]), acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < kSmallN; ++j)
+    for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+  if (lane < p.N) {
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < kSmallN; ++j)
+      if (j == lane) v = acc[j];
+    v = fmaf(v, p.alpha, (p.bias_m ? __ldg(&p.bias_m[row]) : 0.f) + (p.bias_n ? __ldg(&p.bias_n[lane]) : 0.f));
+    v = f32_act(v, p.act);
+    const int64_t o = (int64_t)blockIdx.z * p.sC + row * p.ldc + lane;
+    if (p.res) v = p.res[o] + (p.res_scale ? __ldg(&p.res_scale[lane]) : 1.f) * v;
+    p.C[o] = v;
+  }
 }
 
 // op 0: out = alpha * a + beta * b (b may be null: + beta);  op 1: out = a * b;
@@ -438,6 +504,12 @@ extern "C" int b200sep_gemm_f32(const float* A, const float* Bw, float* C, int M
     return tc_gemm_f32(A, Bw, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, alpha, bias_n, bias_m, act, res, res_scale,
                        (batch == 1 || strideB == 0) ? w_packed : nullptr, (cudaStream_t)stream);
   GemmF32 p{A, Bw, C, bias_n, bias_m, res, res_scale, M, N, K, lda, ldb, ldc, strideA, strideB, strideC, alpha, act};
+  if (N <= kSmallN && M >= 1024) {
+    dim3 g(cdiv(M, 8), 1, batch);
+    gemm_small_n_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(p);
+    B2_LAUNCHED();
+    return B200SEP_OK;
+  }
   dim3 grid(cdiv(N, FBN), cdiv(M, FBM), batch);
   B2_CHECK_ARG(grid.y <= 65535, "gemm_f32: M too large");
   gemm_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);

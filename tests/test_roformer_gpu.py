@@ -98,6 +98,18 @@ def test_roformer_operator_kernels(rf):
         res[:, s : s + C] += ch[i] * win
         cnt[s : s + C] += win
     assert (out.cpu() - res / cnt.clamp(min=1e-10)).abs().max() <= 1e-5
+    # softmax on rows with a padded stride (register path, and the streaming path for very long rows)
+    for n, ld in ((801, 804), (62, 64), (3000, 3000)):
+        sc = torch.randn((19, ld), generator=g) * 6
+        sdv2 = sc.cuda()
+        check(lib.b200sep_softmax_rows_f32(sdv2.data_ptr(), 19, n, ld, 0))
+        got = sdv2.cpu()
+        assert (got[:, :n] - torch.softmax(sc[:, :n], -1)).abs().max() <= 1e-6 and torch.equal(got[:, n:], sc[:, n:])
+    # tiny-N GEMM (the attention gates): warp-per-row kernel
+    from audio_separator.separator.b200.demucs import linear
+
+    xg, wg, bg = torch.randn((2500, 96), generator=g), torch.randn((8, 96), generator=g) * 0.1, torch.randn(8, generator=g)
+    assert (linear(xg.cuda(), wg.cuda(), bg.cuda()).cpu() - F.linear(xg, wg, bg)).abs().max() <= 2e-5
     torch.cuda.synchronize()
 
 
