@@ -6,7 +6,7 @@ depth x [time transformer over (b f) sequences, frequency transformer over (b t)
 QK^T / softmax / PV GEMMs, sigmoid gates + head merge, output GEMM with residual, RMSNorm + GELU MLP with residual) -> final RMSNorm ->
 per-band mask MLPs (tanh, GLU) -> complex mask product -> iSTFT -> Hamming overlap-add with weight counter.
 All GEMMs run through b200sep_gemm_f32 (tensor cores for the large ones, static weights pre-split once).
-Covered: linear_transformer_depth = 0, stereo or mono, any num_stems / mask_estimator_depth / band layout; Mel-Band Roformer is not.
+Covered: linear_transformer_depth = 0, stereo, any num_stems / mask_estimator_depth / band layout; mono and Mel-Band Roformer are not.
 """
 from __future__ import annotations
 

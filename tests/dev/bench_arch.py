@@ -1,6 +1,6 @@
 """Real-time factor of the MDX23C / HTDemucs / VR paths on one B200 (measurement tool; bench.py stays the MDX north-star contract).
 
-    python tests/dev/bench_arch.py [--arch mdxc|demucs|vr|all] [--steps 2] [--warmup 1] [--no-cpu]
+    python tests/dev/bench_arch.py [--arch mdxc|roformer|demucs|vr|all] [--steps 2] [--warmup 1] [--no-cpu]
 
 One JSON line per architecture: value = audio-seconds / device-seconds with the mix resident in HBM (CUDA events),
 e2e = through the engine's host-buffer entry (upload + download inside the timed region), cpu_baseline = the oracle port on the host
@@ -58,6 +58,29 @@ def bench_mdxc(a):
         cpu = {"value": round(cfg.hop_size / SR / dt, 4), "unit": "x realtime", "cores": torch.get_num_threads(), "kind": "port", "sample": "one chunk forward (hop_size new audio-seconds per chunk at overlap 8)"}
     line("MDXC", f"MDX23C-8KFFT-InstVoc_HQ topology, {a.minutes}-min track, overlap {cfg.overlap}, dim_t {cfg.dim_t}", secs, dev_s, e2e_s, launches, a.steps, a.warmup, mix.nbytes, 2 * mix.nbytes, cpu,
          {"chunks": X.chunk_grid(mix.shape[1], cfg)[3], "batch": 2})
+
+
+def bench_roformer(a):
+    import roformer_oracle as R
+    from audio_separator.separator.b200 import roformer as rf
+    kw = dict(stft_hop_length=441)
+    ocfg = R.BSRoformerConfig(**kw)
+    w = R.make_weights(ocfg, seed=8)
+    eng = rf.RoformerEngine(rf.BSRoformerNet(rf.BSRoformerConfig(**kw), w), 801, 8, SR, n_instruments=2, batch_size=2)
+    secs = a.minutes * 60
+    mix = M.normalize(M.synth_music(int(secs * SR), seed=5), 0.9, 0.0)
+    md = torch.from_numpy(mix).cuda()
+    dev_s, launches = timed(lambda: eng.demix_device(md), a.steps, a.warmup)
+    pin = torch.from_numpy(mix).pin_memory()
+    e2e_s, _ = timed(lambda: eng.demix_device(pin.cuda(non_blocking=True)).cpu(), a.steps, 1)
+    cpu = None
+    if not a.no_cpu:
+        t0 = time.time()
+        R.forward(w, ocfg, mix[None, :, : ocfg.chunk_size])
+        dt = time.time() - t0
+        cpu = {"value": round((ocfg.chunk_size / SR) / dt, 4), "unit": "x realtime", "cores": torch.get_num_threads(), "kind": "port", "sample": f"one 8-s chunk forward ({dt:.2f} s); step = chunk (no overlap at the default overlap setting)"}
+    line("MDXC/BS-Roformer", f"model_bs_roformer_ep_317 geometry (dim 512, depth 12, 62 bands, n_fft 2048 / hop 441, dim_t 801), {a.minutes}-min track", secs, dev_s, e2e_s, launches, a.steps,
+         a.warmup, mix.nbytes, mix.nbytes, cpu, {"chunks_per_forward": 2})
 
 
 def bench_demucs(a):
@@ -122,6 +145,6 @@ if __name__ == "__main__":
     ap.add_argument("--minutes", type=float, default=1.0)
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
-    for name, fn in (("mdxc", bench_mdxc), ("demucs", bench_demucs), ("vr", bench_vr)):
+    for name, fn in (("mdxc", bench_mdxc), ("roformer", bench_roformer), ("demucs", bench_demucs), ("vr", bench_vr)):
         if a.arch in ("all", name):
             fn(a)
