@@ -363,18 +363,57 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f32_kernel(const TcParams p) {
         ptx::tmem_ld16(trow + (uint32_t)c0, v);
         ptx::tmem_ld_wait();
         if (!row_ok) continue;
+        // Everything that does not depend on the column is decided OUTSIDE the 16-column loops (the first version re-tested bias / residual /
+        // activation per column: ~25 instructions per output, 48 k warp-instructions per tile, which made K = 64 attention GEMMs epilogue-bound).
         float x[16];
+        const int nb0 = n0 + c0;
+        const bool full = nb0 + 15 < p.N;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int n = n0 + c0 + j;
-          float y = fmaf(__uint_as_float(v[j]), p.alpha, bm);
-          if (n < p.N) {
-            if (p.bias_n) y += __ldg(&p.bias_n[n]);
-            if (rrow && p.add_before_act) y += __ldg(&rrow[(int64_t)n * p.r_sn]);
-            y = tc_act(y, p.act);
-            if (rrow && !p.add_before_act) y = __ldg(&rrow[(int64_t)n * p.r_sn]) + (p.res_scale ? __ldg(&p.res_scale[n]) : 1.f) * y;
+        for (int j = 0; j < 16; ++j) x[j] = fmaf(__uint_as_float(v[j]), p.alpha, bm);
+        if (p.bias_n) {
+          if (full) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias_n + nb0) + j4);  // nb0 is a multiple of 16
+              x[4 * j4] += bv.x; x[4 * j4 + 1] += bv.y; x[4 * j4 + 2] += bv.z; x[4 * j4 + 3] += bv.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (nb0 + j < p.N) x[j] += __ldg(&p.bias_n[nb0 + j]);
           }
-          x[j] = y;
+        }
+        if (rrow && p.add_before_act) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (full || nb0 + j < p.N) x[j] += __ldg(&rrow[(int64_t)(nb0 + j) * p.r_sn]);
+        }
+        switch (p.act) {
+          case 1:
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = fmaxf(x[j], 0.f);
+            break;
+          case 0: break;
+          default:
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = tc_act(x[j], p.act);
+        }
+        if (rrow && !p.add_before_act) {
+          if (p.res_scale) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (full || nb0 + j < p.N) x[j] = __ldg(&rrow[(int64_t)(nb0 + j) * p.r_sn]) + __ldg(&p.res_scale[nb0 + j]) * x[j];
+          } else if (p.r_sn == 1 && full && ((reinterpret_cast<uintptr_t>(rrow + nb0) & 15) == 0)) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 rv = __ldg(reinterpret_cast<const float4*>(rrow + nb0) + j4);
+              x[4 * j4] += rv.x; x[4 * j4 + 1] += rv.y; x[4 * j4 + 2] += rv.z; x[4 * j4 + 3] += rv.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (full || nb0 + j < p.N) x[j] += __ldg(&rrow[(int64_t)(nb0 + j) * p.r_sn]);
+          }
         }
         const int n = n0 + c0;
         if (p.o_sn == 1 && n + 15 < p.N && ((reinterpret_cast<uintptr_t>(orow + n) & 15) == 0)) {
