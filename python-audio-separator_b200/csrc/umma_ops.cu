@@ -536,23 +536,36 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
             sh[4 * j4] = h4.x; sh[4 * j4 + 1] = h4.y; sh[4 * j4 + 2] = h4.z; sh[4 * j4 + 3] = h4.w;
           }
           if (row_ok) {
-            // optional residual / multiplier: every load of the group is issued before the first store
-            float rv[CW], mv[CW];
+            // The activation and the optional residual / multiplier are decided once per group, outside the column loops (no per-column
+            // tests, no dummy "+0" / "*1" arithmetic); every load of the group is still issued before the first store.
+            float y[CW];
+            if (p.act == 1) {
 #pragma unroll
-            for (int j = 0; j < CW; ++j) {
-              rv[j] = 0.f;
-              mv[j] = 1.f;
-              const size_t ro = rbase + (size_t)(c0 + j) * plane;
-              if (p.res_hi) rv[j] = __bfloat162float(p.res_hi[ro]) + __bfloat162float(p.res_lo[ro]);
-              if (p.mul_hi) mv[j] = __bfloat162float(p.mul_hi[ro]) + __bfloat162float(p.mul_lo[ro]);
+              for (int j = 0; j < CW; ++j) y[j] = fmaxf(fmaf(x[j], sc[j], sh[j]), 0.f);
+            } else {
+#pragma unroll
+              for (int j = 0; j < CW; ++j) y[j] = apply_act(fmaf(x[j], sc[j], sh[j]), p.act);
+            }
+            if (p.res_hi) {
+#pragma unroll
+              for (int j = 0; j < CW; ++j) {
+                const size_t ro = rbase + (size_t)(c0 + j) * plane;
+                y[j] += __bfloat162float(p.res_hi[ro]) + __bfloat162float(p.res_lo[ro]);
+              }
+            }
+            if (p.mul_hi) {
+#pragma unroll
+              for (int j = 0; j < CW; ++j) {
+                const size_t ro = rbase + (size_t)(c0 + j) * plane;
+                y[j] *= __bfloat162float(p.mul_hi[ro]) + __bfloat162float(p.mul_lo[ro]);
+              }
             }
             bf16* ph = p.out_hi + base + (size_t)c0 * plane;
             bf16* pl = p.out_lo + base + (size_t)c0 * plane;
 #pragma unroll
             for (int j = 0; j < CW; ++j) {
-              const float y = (apply_act(fmaf(x[j], sc[j], sh[j]), p.act) + rv[j]) * mv[j];
               bf16 h, l;
-              split_store2(y, h, l);
+              split_store2(y[j], h, l);
               *ph = h;  // 32 lanes -> 32 consecutive pixels: one 64-byte segment per plane
               *pl = l;
               ph += plane;

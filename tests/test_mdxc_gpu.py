@@ -91,10 +91,10 @@ def test_mdxc_plugin_end_to_end(setup, tmp_path):
     sep = Separator(model_file_dir=str(tmp_path), output_dir=str(tmp_path / "out"), mdxc_params={"overlap": cfg.overlap, "batch_size": 2})
     sep.load_model("tiny-mdx23c.npz")
     files = sep.separate(str(tmp_path / "song.wav"))
-    assert files == ["song_(Vocals)_tiny-mdx23c.wav", "song_(Instrumental)_tiny-mdx23c.wav"]
+    assert files == ["song_(Instrumental)_tiny-mdx23c.wav", "song_(Vocals)_tiny-mdx23c.wav"]  # two-stem dict: the secondary file first (mdxc_separator.py:186-214)
     loaded = M.normalize(pcm.astype(np.float32).T / 32768.0, 0.9, 0.0)
-    ref = X.demix(loaded, cfg, lambda x: X.net_forward(w, cfg, x))
-    for fname, stem in zip(files, ref):
+    ref = X.demix(loaded, cfg, lambda x: X.net_forward(w, cfg, x))  # rows in training.instruments order: Vocals, Instrumental
+    for fname, stem in zip(files, (ref[1], ref[0])):
         with wave.open(str(tmp_path / "out" / fname)) as wf:
             assert wf.getnframes() == 12000
             got = np.frombuffer(wf.readframes(12000), dtype="<i2").astype(np.int32)
