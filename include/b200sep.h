@@ -249,6 +249,9 @@ int b200sep_tc_pack_linear_weights(const float* W, int N, int K, int ldw, float*
 int b200sep_tc_pack_conv_weights(const float* w_blocked, int Cin, int taps, int Cout, float* packed, void* stream);
 /* in-place softmax over the first n columns of each row (row stride ld >= n; padding columns are left untouched) */
 int b200sep_softmax_rows_f32(float* x, int64_t rows, int n, int64_t ld, void* stream);
+/* batched C[z] = alpha * A[z] (M,K; lda) @ B[z] (K,N; ldb): the P @ V product of attention without a transposed copy of V */
+int b200sep_gemm_kn_f32(const float* A, const float* B_kn, float* C, int M, int N, int K, int lda, int ldb, int ldc, int batch, int64_t strideA, int64_t strideB,
+                        int64_t strideC, float alpha, void* stream);
 /* op 0: out = alpha*a + beta*b (b NULL: + beta);  op 1: out = a*b;  with b = device {mean, std} (meanstd_f32):
  * op 2: out = (a - mean) / (1e-5 + std);  op 3: out = a*std + mean  (htdemucs.py:501-510, :588-589, :611-612) */
 int b200sep_ew_f32(const float* a, const float* b, float* out, int64_t n, float alpha, float beta, int op, void* stream);
@@ -294,8 +297,8 @@ int b200sep_resample_poly_f32(const float* x, const float* taps, int n_taps, int
  * a band of the band-split input is a column slice) */
 int b200sep_rmsnorm_f32(const float* x, const float* gamma, float* y, int64_t rows, int C, int64_t ld_in, int64_t ld_out, void* stream);
 /* "b n (qkv h d) -> qkv b h n d" + rotary_embed.rotate_queries_or_keys on q and k (bs_roformer.py:67-72; rotary-embedding-torch defaults):
- * qkv (B, n, 3*H*dh) -> q, k (B, H, n, dh), v_t (B, H, dh, ldv) = V transposed, columns n..ldv-1 zero (ldv: K-major operand of P@V, padded for alignment) */
-int b200sep_rope_split_heads_f32(const float* qkv, const float* freqs, float* q, float* k, float* v_t, int B, int n, int H, int dh, int ldv, void* stream);
+ * qkv (B, n, 3*H*dh) -> q, k, v (B, H, n, dh) */
+int b200sep_rope_split_heads_f32(const float* qkv, const float* freqs, float* q, float* k, float* v, int B, int n, int H, int dh, void* stream);
 /* out * sigmoid(gates) + "b h n d -> b n (h d)" (bs_roformer.py:76-81): o (B, H, n, dh), gates (B*n, H) -> y (B*n, H*dh) */
 int b200sep_gate_merge_heads_f32(const float* o, const float* gates, float* y, int B, int n, int H, int dh, void* stream);
 /* nn.GLU(dim=-1) of MaskEstimator (bs_roformer.py:175): a (rows, 2C; ld_in) -> y (rows, C; ld_out) */

@@ -83,7 +83,8 @@ _SIGS = {
     "b200sep_vr_apply_mask": (i32, [vp, i32, vp, i32, i32, i32, f32, f32, f32, f32, vp, vp, vp]),
     "b200sep_resample_poly_f32": (i32, [vp, vp, i32, i32, i32, i64, i32, i64, i64, vp, vp]),
     "b200sep_rmsnorm_f32": (i32, [vp, vp, vp, i64, i32, i64, i64, vp]),
-    "b200sep_rope_split_heads_f32": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "b200sep_rope_split_heads_f32": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    "b200sep_gemm_kn_f32": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i64, i64, i64, f32, vp]),
     "b200sep_gate_merge_heads_f32": (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
     "b200sep_glu_rows_f32": (i32, [vp, vp, i64, i32, i64, i64, vp]),
     "b200sep_roformer_mask_apply": (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),

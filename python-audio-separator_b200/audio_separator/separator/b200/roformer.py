@@ -110,22 +110,20 @@ class BSRoformerNet:
         d, H, dh = cfg.dim, cfg.heads, cfg.dim_head
         inner = H * dh
         rows = Bq * n
-        ldv = -(-n // 4) * 4  # row stride of the score matrix and of V^T: 16-byte aligned K-major operands for the P@V GEMM
+        ldv = -(-n // 4) * 4  # row stride of the score matrix: a 16-byte aligned K-major A operand for the P@V GEMM
         for l in range(depth):
             a, f = f"{p}.layers.{l}.0", f"{p}.layers.{l}.1"
             xn = rmsnorm(x, W[f"{a}.norm.gamma"], rows, d)
             qkv = _new((rows, 3 * inner), x)
             gemm(_ptr(xn), W[f"{a}.to_qkv.weight"], _ptr(qkv), rows, d, 3 * inner)
-            q, k = _new((Bq, H, n, dh), x), _new((Bq, H, n, dh), x)
-            vt = _new((Bq, H, dh, ldv), x)
-            check(lib.b200sep_rope_split_heads_f32(_ptr(qkv), _ptr(W[f"{a}.rotary_embed.freqs"]), _ptr(q), _ptr(k), _ptr(vt), Bq, n, H, dh, ldv, _stream()), "rope_split_heads_f32")
+            q, k, v = _new((Bq, H, n, dh), x), _new((Bq, H, n, dh), x), _new((Bq, H, n, dh), x)
+            check(lib.b200sep_rope_split_heads_f32(_ptr(qkv), _ptr(W[f"{a}.rotary_embed.freqs"]), _ptr(q), _ptr(k), _ptr(v), Bq, n, H, dh, _stream()), "rope_split_heads_f32")
             sc = _new((Bq * H, n, ldv), x)  # padding columns n..ldv-1 are never read: the P@V GEMM runs K = n over rows of stride ldv
             check(lib.b200sep_gemm_f32(_ptr(q), _ptr(k), _ptr(sc), n, n, dh, dh, dh, ldv, Bq * H, n * dh, n * dh, n * ldv, dh**-0.5, None, None, 0, None, None, None, _stream()),
                   "gemm_f32(scores)")
             check(lib.b200sep_softmax_rows_f32(_ptr(sc), Bq * H * n, n, ldv, _stream()), "softmax_rows_f32")
             o = _new((Bq, H, n, dh), x)
-            check(lib.b200sep_gemm_f32(_ptr(sc), _ptr(vt), _ptr(o), n, dh, n, ldv, ldv, dh, Bq * H, n * ldv, dh * ldv, n * dh, 1.0, None, None, 0, None, None, None, _stream()),
-                  "gemm_f32(PV)")
+            check(lib.b200sep_gemm_kn_f32(_ptr(sc), _ptr(v), _ptr(o), n, dh, n, ldv, dh, dh, Bq * H, n * ldv, n * dh, n * dh, 1.0, _stream()), "gemm_kn_f32(PV)")
             gates = _new((rows, H), x)
             gemm(_ptr(xn), W[f"{a}.to_gates.weight"], _ptr(gates), rows, d, H, bias=W[f"{a}.to_gates.bias"])
             merged = _new((rows, inner), x)

@@ -196,6 +196,7 @@ struct GemmF32 {
   int64_t sA, sB, sC;  // batch strides (elements)
   float alpha;
   int act;
+  int b_kn;  // B given as (K, N) row-major instead of (N, K)
 };
 constexpr int FBM = 128, FBN = 128, FBK = 16;
 __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmF32 p) {
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmF32 p) {
   const float* Bw = p.Bw + (int64_t)blockIdx.z * p.sB;
   float* C = p.C + (int64_t)blockIdx.z * p.sC;
   const float* res = p.res ? p.res + (int64_t)blockIdx.z * p.sC : nullptr;
-  const bool vec = ((p.lda | p.ldb) & 3) == 0 && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Bw)) & 15) == 0;
+  const bool vec = !p.b_kn && ((p.lda | p.ldb) & 3) == 0 && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Bw)) & 15) == 0;
   float acc[8][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmF32 p) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           if (m0 + row < p.M && k + e < p.K) av[e] = __ldg(&A[(int64_t)(m0 + row) * p.lda + k + e]);
-          if (n0 + row < p.N && k + e < p.K) bv[e] = __ldg(&Bw[(int64_t)(n0 + row) * p.ldb + k + e]);
+          if (n0 + row < p.N && k + e < p.K) bv[e] = __ldg(p.b_kn ? &Bw[(int64_t)(k + e) * p.ldb + n0 + row] : &Bw[(int64_t)(n0 + row) * p.ldb + k + e]);
         }
       }
 #pragma unroll
@@ -330,31 +331,81 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ x
   for (int i = threadIdx.x; i < n; i += blockDim.x) r[i] *= inv;
 }
 
+// warp-per-row variant for rows of up to 32 * PER columns (attention rows: 62 and 801 in the BS-Roformer): the row lives in registers, no
+// block-level synchronisation, 8 rows per CTA.
+template <int PER>
+__global__ void __launch_bounds__(256) softmax_rows_warp_kernel(float* __restrict__ x, int64_t rows, int n, int64_t ld) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float* r = x + row * ld;
+  float v[PER];
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int i = lane + j * 32;
+    v[j] = (i < n) ? r[i] : -INFINITY;
+    m = fmaxf(m, v[j]);
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    v[j] = expf(v[j] - m);
+    s += v[j];
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float inv = 1.f / s;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int i = lane + j * 32;
+    if (i < n) r[i] = v[j] * inv;
+  }
+}
+
 // GEMM with a tiny N (the 8 attention gates of the Roformer, bs_roformer.py:78): one warp per row of A, the N weight rows stay in L1.
 // C[m][n] = act(alpha * A[m] . Bw[n] + bias_n[n] + bias_m[m]) (+ residual as in gemm_f32_kernel)
 constexpr int kSmallN = 16;
+template <int NN>
 __global__ void __launch_bounds__(256) gemm_small_n_kernel(GemmF32 p) {
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= p.M) return;
   const int lane = threadIdx.x & 31;
   const float* A = p.A + (int64_t)blockIdx.z * p.sA + row * p.lda;
   const float* Bw = p.Bw + (int64_t)blockIdx.z * p.sB;
-  float acc[kSmallN];
+  float acc[NN];
 #pragma unroll
-  for (int j = 0; j < kSmallN; ++j) acc[j] = 0.f;
-  for (int k = lane; k < p.K; k += 32) {
+  for (int j = 0; j < NN; ++j) acc[j] = 0.f;
+  const bool vec = ((p.lda | p.ldb) & 3) == 0 && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Bw)) & 15) == 0;
+  int k = 0;
+  if (vec) {
+    for (k = 4 * lane; k + 3 < p.K; k += 128) {
+      const float4 a = *reinterpret_cast<const float4*>(A + k);
+#pragma unroll
+      for (int j = 0; j < NN; ++j) {
+        if (j < p.N) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(Bw + (int64_t)j * p.ldb + k));
+          acc[j] = fmaf(a.x, w.x, fmaf(a.y, w.y, fmaf(a.z, w.z, fmaf(a.w, w.w, acc[j]))));
+        }
+      }
+    }
+    k = (p.K / 4) * 4 + lane;  // the K % 4 tail
+  } else {
+    k = lane;
+  }
+  for (; k < p.K; k += 32) {
     const float a = A[k];
 #pragma unroll
-    for (int j = 0; j < kSmallN; ++j)
+    for (int j = 0; j < NN; ++j)
       if (j < p.N) acc[j] = fmaf(a, __ldg(&Bw[(int64_t)j * p.ldb + k]), acc[j]);
   }
 #pragma unroll
-  for (int j = 0; j < kSmallN; ++j)
+  for (int j = 0; j < NN; ++j)
     for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
   if (lane < p.N) {
     float v = 0.f;
 #pragma unroll
-    for (int j = 0; j < kSmallN; ++j)
+    for (int j = 0; j < NN; ++j)
       if (j == lane) v = acc[j];
     v = fmaf(v, p.alpha, (p.bias_m ? __ldg(&p.bias_m[row]) : 0.f) + (p.bias_n ? __ldg(&p.bias_n[lane]) : 0.f));
     v = f32_act(v, p.act);
@@ -502,11 +553,12 @@ extern "C" int b200sep_gemm_f32(const float* A, const float* Bw, float* C, int M
   B2_CHECK_ARG(A && Bw && C && M >= 1 && N >= 1 && K >= 1 && batch >= 1 && batch <= 65535, "gemm_f32: bad argument");
   if (tc_enabled() && tc_gemm_usable(M, N, K, batch))
     return tc_gemm_f32(A, Bw, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, alpha, bias_n, bias_m, act, res, res_scale,
-                       (batch == 1 || strideB == 0) ? w_packed : nullptr, (cudaStream_t)stream);
-  GemmF32 p{A, Bw, C, bias_n, bias_m, res, res_scale, M, N, K, lda, ldb, ldc, strideA, strideB, strideC, alpha, act};
+                       (batch == 1 || strideB == 0) ? w_packed : nullptr, 0, (cudaStream_t)stream);
+  GemmF32 p{A, Bw, C, bias_n, bias_m, res, res_scale, M, N, K, lda, ldb, ldc, strideA, strideB, strideC, alpha, act, 0};
   if (N <= kSmallN && M >= 1024) {
     dim3 g(cdiv(M, 8), 1, batch);
-    gemm_small_n_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(p);
+    if (N <= 8) gemm_small_n_kernel<8><<<g, 256, 0, (cudaStream_t)stream>>>(p);
+    else gemm_small_n_kernel<kSmallN><<<g, 256, 0, (cudaStream_t)stream>>>(p);
     B2_LAUNCHED();
     return B200SEP_OK;
   }
@@ -520,7 +572,11 @@ extern "C" int b200sep_gemm_f32(const float* A, const float* Bw, float* C, int M
 extern "C" int b200sep_softmax_rows_f32(float* x, int64_t rows, int n, int64_t ld, void* stream) {
   B2_CHECK_ARG(x && rows >= 0 && n >= 1 && rows <= 0x7fffffff && ld >= n, "softmax_rows_f32: bad argument");
   if (rows == 0) return B200SEP_OK;
-  softmax_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, n, ld);
+  const unsigned wgrid = (unsigned)cdiv(rows, 8);
+  if (n <= 64) softmax_rows_warp_kernel<2><<<wgrid, 256, 0, (cudaStream_t)stream>>>(x, rows, n, ld);
+  else if (n <= 256) softmax_rows_warp_kernel<8><<<wgrid, 256, 0, (cudaStream_t)stream>>>(x, rows, n, ld);
+  else if (n <= 832) softmax_rows_warp_kernel<26><<<wgrid, 256, 0, (cudaStream_t)stream>>>(x, rows, n, ld);
+  else softmax_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, n, ld);
   B2_LAUNCHED();
   return B200SEP_OK;
 }
@@ -550,6 +606,20 @@ extern "C" int b200sep_triangle_overlap_add(const float* segs, int n_segs, int c
   tri_ola_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(segs, n_segs, channels, seg_len, stride, length, q0, n_out, scale, chan_scale, accumulate, out);
   B2_LAUNCHED();
   return B200SEP_OK;
+}
+
+extern "C" int b200sep_gemm_kn_f32(const float* A, const float* B_kn, float* C, int M, int N, int K, int lda, int ldb, int ldc, int batch, int64_t strideA, int64_t strideB,
+                                   int64_t strideC, float alpha, void* stream) {
+  B2_CHECK_ARG(A && B_kn && C && M >= 1 && N >= 1 && K >= 1 && batch >= 1 && lda >= K && ldb >= N && ldc >= N, "gemm_kn_f32: bad argument");
+  if (!(tc_enabled() && tc_gemm_usable(M, N, K, batch))) {  // small shapes: the SIMT kernel reads B transposed
+    B2_CHECK_ARG(batch <= 65535, "gemm_kn_f32: batch too large for the SIMT path");
+    GemmF32 p{A, B_kn, C, nullptr, nullptr, nullptr, nullptr, M, N, K, lda, ldb, ldc, strideA, strideB, strideC, alpha, 0, 1};
+    dim3 grid(cdiv(N, FBN), cdiv(M, FBM), batch);
+    gemm_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    B2_LAUNCHED();
+    return B200SEP_OK;
+  }
+  return tc_gemm_f32(A, B_kn, C, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, alpha, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 1, (cudaStream_t)stream);
 }
 
 extern "C" int64_t b200sep_tc_packed_floats(int N, int K) { return (N >= 1 && K >= 1) ? tc_packed_bytes(N, K) / 4 : 0; }

@@ -25,35 +25,26 @@ __global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restr
   for (int c = lane; c < C; c += 32) yr[c] = xr[c] * inv * __ldg(&gamma[c]);
 }
 
-// qkv (B, n, 3, H, dh) = the to_qkv output -> q, k (B, H, n, dh) with the rotary embedding applied (positions 0..n-1, interleaved pairs,
-// rotary-embedding-torch defaults) and v TRANSPOSED (B, H, dh, ldv) so the P@V GEMM reads it K-major; columns n..ldv-1 of v are zeroed.
-__global__ void rope_split_kernel(const float* __restrict__ qkv, const float* __restrict__ freqs, float* __restrict__ q, float* __restrict__ k, float* __restrict__ vt,
-                                  int n, int H, int dh, int ldv, int64_t total) {
+// qkv (B, n, 3, H, dh) = the to_qkv output -> q, k, v (B, H, n, dh); q and k with the rotary embedding applied (positions 0..n-1, interleaved
+// pairs, rotary-embedding-torch defaults).  One thread per (b, pos, h, pair): float2 loads and stores, all coalesced along d.
+__global__ void rope_split_kernel(const float* __restrict__ qkv, const float* __restrict__ freqs, float* __restrict__ q, float* __restrict__ k, float* __restrict__ v,
+                                  int n, int H, int dh, int64_t total) {
   const int half = dh >> 1;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int p = (int)(i % half);
     const int h = (int)((i / half) % H);
-    const int pos = (int)((i / ((int64_t)half * H)) % ldv);
-    const int64_t b = i / ((int64_t)half * H * ldv);
-    const int64_t o_v = (((b * H + h) * dh) + 2 * p) * ldv + pos;
-    if (pos >= n) {  // padding columns of V^T
-      vt[o_v] = 0.f;
-      vt[o_v + ldv] = 0.f;
-      continue;
-    }
+    const int pos = (int)((i / ((int64_t)half * H)) % n);
+    const int64_t b = i / ((int64_t)half * H * n);
     const float* src = qkv + ((b * n + pos) * 3) * (int64_t)H * dh + (int64_t)h * dh + 2 * p;
-    const float ang = (float)pos * __ldg(&freqs[p]);
     float sn, cs;
-    sincosf(ang, &sn, &cs);
+    sincosf((float)pos * __ldg(&freqs[p]), &sn, &cs);
     const int64_t o = ((b * H + h) * n + pos) * (int64_t)dh + 2 * p;
-    const float q0 = src[0], q1 = src[1];
-    q[o] = q0 * cs - q1 * sn;      // t*cos + rotate_half(t)*sin, rotate_half = (-x2, x1)
-    q[o + 1] = q1 * cs + q0 * sn;
-    const float k0 = src[(int64_t)H * dh], k1 = src[(int64_t)H * dh + 1];
-    k[o] = k0 * cs - k1 * sn;
-    k[o + 1] = k1 * cs + k0 * sn;
-    vt[o_v] = src[2 * (int64_t)H * dh];
-    vt[o_v + ldv] = src[2 * (int64_t)H * dh + 1];
+    const float2 qv = *reinterpret_cast<const float2*>(src);
+    const float2 kv = *reinterpret_cast<const float2*>(src + (int64_t)H * dh);
+    const float2 vv = *reinterpret_cast<const float2*>(src + 2 * (int64_t)H * dh);
+    *reinterpret_cast<float2*>(q + o) = make_float2(qv.x * cs - qv.y * sn, qv.y * cs + qv.x * sn);  // t*cos + rotate_half(t)*sin, rotate_half = (-x2, x1)
+    *reinterpret_cast<float2*>(k + o) = make_float2(kv.x * cs - kv.y * sn, kv.y * cs + kv.x * sn);
+    *reinterpret_cast<float2*>(v + o) = vv;
   }
 }
 
@@ -132,10 +123,12 @@ extern "C" int b200sep_rmsnorm_f32(const float* x, const float* gamma, float* y,
   return B200SEP_OK;
 }
 
-extern "C" int b200sep_rope_split_heads_f32(const float* qkv, const float* freqs, float* q, float* k, float* v_t, int B, int n, int H, int dh, int ldv, void* stream) {
-  B2_CHECK_ARG(qkv && freqs && q && k && v_t && B >= 1 && n >= 1 && H >= 1 && dh >= 2 && dh % 2 == 0 && ldv >= n, "rope_split_heads_f32: bad argument");
-  const int64_t total = (int64_t)B * ldv * H * (dh / 2);
-  rope_split_kernel<<<rf_grid(total), 256, 0, (cudaStream_t)stream>>>(qkv, freqs, q, k, v_t, n, H, dh, ldv, total);
+extern "C" int b200sep_rope_split_heads_f32(const float* qkv, const float* freqs, float* q, float* k, float* v, int B, int n, int H, int dh, void* stream) {
+  B2_CHECK_ARG(qkv && freqs && q && k && v && B >= 1 && n >= 1 && H >= 1 && dh >= 2 && dh % 2 == 0, "rope_split_heads_f32: bad argument");
+  B2_CHECK_ARG(((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 7) == 0,
+               "rope_split_heads_f32: buffers must be 8-byte aligned");
+  const int64_t total = (int64_t)B * n * H * (dh / 2);
+  rope_split_kernel<<<rf_grid(total), 256, 0, (cudaStream_t)stream>>>(qkv, freqs, q, k, v, n, H, dh, total);
   B2_LAUNCHED();
   return B200SEP_OK;
 }

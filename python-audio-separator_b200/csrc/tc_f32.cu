@@ -538,12 +538,18 @@ bool tc_gemm_usable(int M, int N, int K, int batch) {
 }
 
 int tc_gemm_f32(const float* A, const float* Bw, float* C, int M, int N, int K, int lda, int ldb, int ldc, int batch, int64_t sA, int64_t sB, int64_t sC, float alpha,
-                const float* bias_n, const float* bias_m, int act, const float* res, const float* res_scale, const void* w_packed, cudaStream_t st) {
+                const float* bias_n, const float* bias_m, int act, const float* res, const float* res_scale, const void* w_packed, int b_is_kn,
+                cudaStream_t st) {
   TcParams p{};
   p.mode = 0;
   p.b_packed = (const uint8_t*)w_packed;
   p.a = A; p.a_sz = sA; p.a_rs = lda;
-  p.b = Bw; p.b_sz = sB; p.b_rs = ldb; p.b_ks = 1;
+  p.b = Bw; p.b_sz = sB;
+  if (b_is_kn) {  // B given as (K, N) row-major (e.g. V in P @ V): the producers gather it n-major, no transposed copy needed
+    p.b_rs = 1; p.b_ks = ldb;
+  } else {
+    p.b_rs = ldb; p.b_ks = 1;
+  }
   p.M = M; p.N = N; p.K = K; p.batch = batch;
   p.a_vec = (lda % 4 == 0) && (sA % 4 == 0) && aligned16(A);
   p.b_vec = (ldb % 4 == 0) && (sB % 4 == 0) && aligned16(Bw);

@@ -53,16 +53,23 @@ def test_roformer_operator_kernels(rf):
     check(lib.b200sep_rmsnorm_f32(xd.data_ptr() + 20 * 4, gd.data_ptr(), y.data_ptr(), 37, 12, 50, 12, 0))
     ref = F.normalize(x[:, 20:32], dim=-1) * 12**0.5 * gam
     assert (y.cpu() - ref).abs().max() <= 1e-5
-    # rotary + head split, V transposed with padding
-    B, n, H, dh, ldv = 3, 13, 4, 8, 16
+    # rotary + head split
+    B, n, H, dh = 3, 13, 4, 8
     qkv = torch.randn((B, n, 3 * H * dh), generator=g)
     fr = torch.from_numpy(R.rotary_freqs(dh))
     qd, fd = qkv.cuda(), fr.cuda()
-    q, k, vt = torch.empty((B, H, n, dh), device="cuda"), torch.empty((B, H, n, dh), device="cuda"), torch.full((B, H, dh, ldv), 9.0, device="cuda")
-    check(lib.b200sep_rope_split_heads_f32(qd.data_ptr(), fd.data_ptr(), q.data_ptr(), k.data_ptr(), vt.data_ptr(), B, n, H, dh, ldv, 0))
+    q, k, v = (torch.empty((B, H, n, dh), device="cuda") for _ in range(3))
+    check(lib.b200sep_rope_split_heads_f32(qd.data_ptr(), fd.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), B, n, H, dh, 0))
     qr, kr, vr = qkv.view(B, n, 3, H, dh).permute(2, 0, 3, 1, 4)
     assert (q.cpu() - R.apply_rotary(qr, fr)).abs().max() <= 1e-5 and (k.cpu() - R.apply_rotary(kr, fr)).abs().max() <= 1e-5
-    assert torch.equal(vt.cpu()[..., :n], vr.transpose(-1, -2)) and not vt.cpu()[..., n:].any()
+    assert torch.equal(v.cpu(), vr.contiguous())
+    # P @ V with V given (K, N) row-major and P on a padded row stride
+    P, V = torch.rand((6, 70, 72), generator=g), torch.randn((6, 70, 64), generator=g)
+    Pd, Vd = P.cuda(), V.cuda()
+    O = torch.empty((6, 70, 64), device="cuda")
+    check(lib.b200sep_gemm_kn_f32(Pd.data_ptr(), Vd.data_ptr(), O.data_ptr(), 70, 64, 70, 72, 64, 64, 6, 70 * 72, 70 * 64, 70 * 64, 1.0, 0))
+    ref = torch.einsum("bik,bkd->bid", P[:, :, :70].double(), V.double())
+    assert (O.cpu().double() - ref).abs().max() <= 3e-5 * ref.abs().max()
     # gates + head merge
     o, gates = torch.randn((B, H, n, dh), generator=g), torch.randn((B * n, H), generator=g)
     od, gd2 = o.cuda(), gates.cuda()
@@ -99,7 +106,7 @@ def test_roformer_operator_kernels(rf):
         cnt[s : s + C] += win
     assert (out.cpu() - res / cnt.clamp(min=1e-10)).abs().max() <= 1e-5
     # softmax on rows with a padded stride (register path, and the streaming path for very long rows)
-    for n, ld in ((801, 804), (62, 64), (3000, 3000)):
+    for n, ld in ((801, 804), (62, 64), (200, 200), (1500, 1504), (3000, 3000)):
         sc = torch.randn((19, ld), generator=g) * 6
         sdv2 = sc.cuda()
         check(lib.b200sep_softmax_rows_f32(sdv2.data_ptr(), 19, n, ld, 0))
