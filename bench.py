@@ -26,8 +26,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "python-audio-separator_b200"))
 
 SR = 44100
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE conv3x3 launch at U-Net scale 0, batch 4 (profiles/r01_conv3x3_s0_ncu_full.txt)
-NCU_CONV_S0_DRAM_BYTES_PER_LAUNCH = 605.2e6 + 566.1e6
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE conv3x3 launch at U-Net scale 0, batch 4 (profiles/r01b_conv3x3_s0_ncu_full.txt)
+NCU_CONV_S0_DRAM_BYTES_PER_LAUNCH = 731.8e6 + 605.5e6
 METRIC = "real-time factor (audio-sec/wall-sec) @44.1kHz stereo"
 
 
