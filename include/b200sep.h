@@ -306,6 +306,12 @@ int b200sep_glu_rows_f32(const float* a, float* y, int64_t rows, int C, int64_t 
 /* stft_repr * mask as complex numbers and the re-ordering to iSTFT planes (bs_roformer.py:472-484):
  * stft_tf (B, T, F, 4) and mask (B, n_stems, T, F, 4) with feature order (f, s, c) -> planes (B*n_stems, 4, F, T) [L re, L im, R re, R im] */
 int b200sep_roformer_mask_apply(const float* stft_tf, const float* mask, float* planes, int B, int n_stems, int T, int F, void* stream);
+/* Mel-Band Roformer: stft_repr[batch_arange, freq_indices] (mel_band_roformer.py:300-303) on (re, im) pairs: dst[row][g] = src[row][idx[g]] */
+int b200sep_gather_pairs_f32(const float* src, const int* idx, float* dst, int64_t rows, int n_src_pairs, int n_gather, void* stream);
+/* masks.scatter_add_ / num_bands_per_freq (mel_band_roformer.py:306-318) as an output-side gather: out[row][fs] = mean of mask_gathered[row][pos] over
+ * pos in csr_positions[csr_offsets[fs] .. csr_offsets[fs+1])  (complex pairs) */
+int b200sep_mask_average_f32(const float* mask_gathered, const int* csr_offsets, const int* csr_positions, float* mask_out, int64_t rows, int n_gather, int n_out,
+                             void* stream);
 /* Roformer branch of MDXCSeparator.demix (mdxc_separator.py:310-343): out[c][q] = sum_i window[q - starts[i]] * chunks[i][c][q - starts[i]] /
  * max(sum_i window[q - starts[i]], 1e-10); chunks (n_chunks, channels, len), starts device int64[n_chunks] */
 int b200sep_overlap_add_starts(const float* chunks, const int64_t* starts, const float* window, int n_chunks, int channels, int len, int64_t n_out, float* out,

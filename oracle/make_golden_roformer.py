@@ -100,6 +100,37 @@ def main():
     d2_orc = R.demix(mix, cfg2, lambda c: R.forward(w2, cfg2, c), n_instruments=2)
     check("demix Roformer branch (2 stems)", np.stack([d2_ref["Vocals"], d2_ref["Instrumental"]]), d2_orc, 2e-5)
     out.update(mix_seed=51, n_samples=N, demix_ref=np.asarray(d_ref), demix_overlap_ref=np.asarray(d_ref_o), demix_2stem_ref=np.stack([d2_ref["Vocals"], d2_ref["Instrumental"]]))
+    # ---- Mel-Band Roformer (librosa.filters.mel is absent: the oracle's restatement of it is injected; only the SUPPORT of the filters matters)
+    sys.modules["librosa"].filters = types.SimpleNamespace(mel=lambda sr, n_fft, n_mels: R.mel_filter_bank(sr, n_fft, n_mels))
+    sys.modules["librosa.filters"] = sys.modules["librosa"].filters
+    mb = ref_shim.ref_module("audio_separator.separator.uvr_lib_v5.roformer.mel_band_roformer")
+    MSMALL = dict(dim=32, depth=2, time_transformer_depth=1, freq_transformer_depth=1, num_bands=12, dim_head=8, heads=4, mask_estimator_depth=2, stft_n_fft=128, stft_hop_length=32,
+                  stft_win_length=128, dim_t=65)
+    mcfg = R.MelBandRoformerConfig(**MSMALL)
+    mw = R.make_mel_weights(mcfg, seed=6)
+    mm = mb.MelBandRoformer(**mcfg.kwargs()).eval()
+    msd = mm.state_dict()
+    mnames = [n for n, _ in R.mel_param_shapes(mcfg)]
+    assert list(msd) == mnames, [(a, b) for a, b in zip(msd, mnames) if a != b][:5]
+    for (n, sh), v in zip(R.mel_param_shapes(mcfg), msd.values()):
+        assert tuple(v.shape) == tuple(sh), (n, v.shape, sh)
+    mm.load_state_dict({k: torch.from_numpy(v) for k, v in mw.items()})
+    fpb, fidx, nfpb, nbpf = R.mel_band_layout(mcfg)
+    assert torch.equal(mm.freq_indices, torch.from_numpy(fidx)) and torch.equal(mm.num_bands_per_freq, torch.from_numpy(nbpf))
+    with torch.no_grad():
+        my_ref = mm(torch.from_numpy(chunk)).numpy()
+    check("MelBandRoformer.forward (stereo, 1 stem, overlapping bands)", my_ref, R.forward_mel(mw, mcfg, chunk), 2e-5)
+    mcfg2 = R.MelBandRoformerConfig(**dict(MSMALL, num_stems=2, mask_estimator_depth=1, depth=1, freq_transformer_depth=2))
+    mw2 = R.make_mel_weights(mcfg2, seed=7)
+    mm2 = mb.MelBandRoformer(**mcfg2.kwargs()).eval()
+    mm2.load_state_dict({k: torch.from_numpy(v) for k, v in mw2.items()})
+    with torch.no_grad():
+        my2_ref = mm2(torch.from_numpy(chunk)).numpy()
+    check("MelBandRoformer.forward (2 stems, mask depth 1)", my2_ref, R.forward_mel(mw2, mcfg2, chunk), 2e-5)
+    md_ref = run_demix(mm, mcfg, ["Vocals", "Instrumental"], "Vocals", 8)
+    md_orc = R.demix(mix, mcfg, lambda c: R.forward_mel(mw, mcfg, c), n_instruments=2)
+    check("demix Roformer branch with a Mel-Band model", np.asarray(md_ref), md_orc[0], 2e-5)
+    out.update(mel_forward_ref=my_ref, mel_forward_2stem_ref=my2_ref, mel_demix_ref=np.asarray(md_ref))
     np.savez_compressed(os.path.join(GOLD, "roformer_small.npz"), **{k: (np.asarray(v, dtype=np.float32) if isinstance(v, np.ndarray) else v) for k, v in out.items()})
     print("wrote tests/golden/roformer_small.npz; oracle pinned: OK (rotary-embedding-torch restated, see header)")
 

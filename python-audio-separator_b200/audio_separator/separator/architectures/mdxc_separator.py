@@ -3,8 +3,8 @@
 Plugin contract of the reference's MDXCSeparator (audio_separator/separator/architectures/mdxc_separator.py:19-228):
 ctor `(common_config, arch_config)` with arch keys segment_size / override_model_segment_size / batch_size / overlap /
 pitch_shift, `separate(path, custom_output_names)`, `demix(mix) -> {instrument: (2, N)}`.  The chunk loop runs on the GPU
-through libb200sep.so (MdxcEngine for TFC_TDF_net checkpoints, RoformerEngine for BS-Roformer checkpoints -- the Roformer branch of
-demix, mdxc_separator.py:272-343).  Mel-Band Roformer checkpoints and pitch shifting are not part of this path.
+through libb200sep.so (MdxcEngine for TFC_TDF_net checkpoints, RoformerEngine for BS-Roformer and Mel-Band Roformer checkpoints -- the Roformer branch of
+demix, mdxc_separator.py:272-343).  Pitch shifting is not part of this path.
 """
 import os
 
@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from ..b200.engine import MdxcEngine, TfcNet
-from ..b200.roformer import BSRoformerConfig, BSRoformerNet, RoformerEngine
+from ..b200.roformer import BSRoformerConfig, BSRoformerNet, MelBandRoformerConfig, RoformerEngine
 from ..common_separator import CommonSeparator, normalize
 
 
@@ -60,9 +60,12 @@ class MDXCSeparator(CommonSeparator):
     def _load_roformer(self, cfg):
         """RoformerLoader.load_model (roformer/roformer_loader.py:82-195): BSRoformer(**model section) + load_state_dict."""
         model, training = cfg["model"], cfg["training"]
-        if "num_bands" in model or "freqs_per_bands" not in model:
-            raise NotImplementedError("Mel-Band Roformer checkpoints are outside the accelerated path (only BS-Roformer: `freqs_per_bands` in the model section)")
-        rcfg = BSRoformerConfig.from_model_section(model)
+        if "num_bands" in model:  # roformer_loader.py:_create_mel_band_roformer
+            rcfg = MelBandRoformerConfig.from_model_section(model)
+        elif "freqs_per_bands" in model:
+            rcfg = BSRoformerConfig.from_model_section(model)
+        else:
+            raise ValueError("Unknown Roformer model type in configuration (neither num_bands nor freqs_per_bands)")
         path = self.model_path
         if path.lower().endswith(".npz"):
             with np.load(path) as z:

@@ -6,7 +6,7 @@ depth x [time transformer over (b f) sequences, frequency transformer over (b t)
 QK^T / softmax / PV GEMMs, sigmoid gates + head merge, output GEMM with residual, RMSNorm + GELU MLP with residual) -> final RMSNorm ->
 per-band mask MLPs (tanh, GLU) -> complex mask product -> iSTFT -> Hamming overlap-add with weight counter.
 All GEMMs run through b200sep_gemm_f32 (tensor cores for the large ones, static weights pre-split once).
-Covered: linear_transformer_depth = 0, stereo, any num_stems / mask_estimator_depth / band layout; mono and Mel-Band Roformer are not.
+Covered: BS-Roformer (linear_transformer_depth = 0) and Mel-Band Roformer, stereo, any num_stems / mask_estimator_depth / band layout; mono is not.
 """
 from __future__ import annotations
 
@@ -70,6 +70,85 @@ class BSRoformerConfig:
         return tuple(2 * f * self.audio_channels for f in self.freqs_per_bands)
 
 
+@dataclass
+class MelBandRoformerConfig:
+    """MelBandRoformer constructor arguments that shape the graph (mel_band_roformer.py:124-160)."""
+
+    dim: int = 384
+    depth: int = 6
+    stereo: bool = True
+    num_stems: int = 1
+    time_transformer_depth: int = 1
+    freq_transformer_depth: int = 1
+    num_bands: int = 60
+    dim_head: int = 64
+    heads: int = 8
+    mask_estimator_depth: int = 1
+    sample_rate: int = 44100
+    stft_n_fft: int = 2048
+    stft_hop_length: int = 512
+    stft_win_length: int = 2048
+    stft_normalized: bool = False
+
+    @classmethod
+    def from_model_section(cls, m: dict) -> "MelBandRoformerConfig":
+        cfg = cls(**{k: m[k] for k in cls.__dataclass_fields__ if k in m})
+        if m.get("sage_attention", False) or m.get("match_input_audio_length", False):
+            raise NotImplementedError("sage_attention / match_input_audio_length are not covered")
+        if m.get("stft_window_fn") not in (None, "torch.hann_window"):
+            raise NotImplementedError("only the Hann STFT window is covered")
+        if cfg.stft_normalized or cfg.stft_win_length != cfg.stft_n_fft:
+            raise NotImplementedError("stft_normalized / win_length != n_fft are not covered")
+        return cfg
+
+    @property
+    def audio_channels(self):
+        return 2 if self.stereo else 1
+
+    @property
+    def freqs_per_bands(self):
+        return tuple(int(v) for v in mel_band_layout(self)[2])
+
+    @property
+    def band_dims(self):
+        return tuple(2 * f * self.audio_channels for f in self.freqs_per_bands)
+
+
+def _slaney_mel(f):
+    f = np.asarray(f, dtype=np.float64)
+    lin = f * 3.0 / 200.0
+    return np.where(f >= 1000.0, 15.0 + np.log(np.maximum(f, 1e-300) / 1000.0) / (np.log(6.4) / 27.0), lin)
+
+
+def _slaney_hz(m):
+    m = np.asarray(m, dtype=np.float64)
+    return np.where(m >= 15.0, 1000.0 * np.exp((np.log(6.4) / 27.0) * (m - 15.0)), m * 200.0 / 3.0)
+
+
+def mel_band_layout(cfg: "MelBandRoformerConfig"):
+    """Which STFT bins each band covers: the support of librosa.filters.mel(sr, n_fft, n_mels=num_bands) (Slaney scale, triangles between
+    consecutive mel points; bin 0 forced into the first band and the last bin into the last one), as MelBandRoformer.__init__ derives it
+    (mel_band_roformer.py:239-262).  -> (mask (bands, F), gather indices over the (f s) axis, freqs per band, bands per freq)"""
+    n_f = cfg.stft_n_fft // 2 + 1
+    fft_f = np.fft.rfftfreq(n=cfg.stft_n_fft, d=1.0 / cfg.sample_rate)
+    pts = _slaney_hz(np.linspace(_slaney_mel(0.0), _slaney_mel(cfg.sample_rate / 2.0), cfg.num_bands + 2))
+    widths = np.diff(pts)
+    ramps = np.subtract.outer(pts, fft_f)
+    tri = np.zeros((cfg.num_bands, n_f), dtype=np.float32)
+    for i in range(cfg.num_bands):
+        tri[i] = np.maximum(0, np.minimum(-ramps[i] / widths[i], ramps[i + 2] / widths[i + 1]))
+    tri *= (2.0 / (pts[2 : cfg.num_bands + 2] - pts[: cfg.num_bands]))[:, None]
+    tri[0, 0] = 1.0
+    tri[-1, -1] = 1.0
+    mask = tri > 0
+    if not mask.any(axis=0).all():
+        raise ValueError("all frequencies need to be covered by all bands for now")
+    idx = np.tile(np.arange(n_f), (cfg.num_bands, 1))[mask]
+    if cfg.stereo:
+        idx = (idx[:, None] * 2 + np.arange(2)[None, :]).reshape(-1)
+    return mask, idx.astype(np.int64), mask.sum(1), mask.sum(0)
+
+
 def gemm(a_ptr, w, c_ptr, M, lda, ldc, bias=None, act=ACT_NONE, res_ptr=None):
     """rows x K (row stride lda) @ w (N, K)^T + bias -> rows x N at row stride ldc (+ res with the same strides)."""
     N, K = w.shape
@@ -85,7 +164,10 @@ def rmsnorm(x, gamma, rows, C, ld_in=None, out=None):
 
 
 class BSRoformerNet:
-    def __init__(self, cfg: BSRoformerConfig, state: dict, device="cuda:0"):
+    """BS-Roformer (cfg: BSRoformerConfig) or Mel-Band Roformer (cfg: MelBandRoformerConfig): the graphs differ only in the band layout (disjoint
+    slices vs gathered, overlapping mel bands whose masks are averaged), the per-transformer output norm and the mask MLP depth."""
+
+    def __init__(self, cfg, state: dict, device="cuda:0"):
         _require_cuda()
         self.cfg = cfg
         self.device = torch.device(device)
@@ -96,13 +178,27 @@ class BSRoformerNet:
         for k, v in state.items():
             a = np.asarray(v, dtype=np.float32) if not isinstance(v, torch.Tensor) else v.detach().to(torch.float32).numpy()
             self.W[k] = torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
-        for n in ("final_norm.gamma", "band_split.to_features.0.1.weight", "layers.0.0.layers.0.0.to_qkv.weight", "mask_estimators.0.to_freqs.0.0.0.weight"):
+        for n in ("band_split.to_features.0.1.weight", "layers.0.0.layers.0.0.to_qkv.weight", "mask_estimators.0.to_freqs.0.0.0.weight"):
             if n not in self.W:
-                raise ValueError(f"state dict lacks {n}: not a BSRoformer checkpoint")
+                raise ValueError(f"state dict lacks {n}: not a Roformer checkpoint")
         if self.W["layers.0.0.layers.0.0.to_qkv.weight"].shape != (3 * cfg.heads * cfg.dim_head, cfg.dim):
             raise ValueError("dim / heads / dim_head do not match the checkpoint")
-        if f"band_split.to_features.{len(cfg.band_dims) - 1}.1.weight" not in self.W or f"band_split.to_features.{len(cfg.band_dims)}.1.weight" in self.W:
-            raise ValueError("freqs_per_bands does not match the checkpoint")
+        self.band_dims = cfg.band_dims
+        if f"band_split.to_features.{len(self.band_dims) - 1}.1.weight" not in self.W or f"band_split.to_features.{len(self.band_dims)}.1.weight" in self.W:
+            raise ValueError("the band layout does not match the checkpoint")
+        for bi, d_in in enumerate(self.band_dims):
+            if self.W[f"band_split.to_features.{bi}.1.weight"].shape[1] != d_in:
+                raise ValueError(f"band {bi}: the checkpoint expects {self.W[f'band_split.to_features.{bi}.1.weight'].shape[1]} inputs, the band layout gives {d_in}")
+        self.n_mask_linear = sum(1 for k in self.W if k.startswith("mask_estimators.0.to_freqs.0.0.") and k.endswith(".weight"))
+        self.mel = isinstance(cfg, MelBandRoformerConfig)
+        if self.mel:  # overlapping bands: gather indices for the band split, CSR lists for the mask average
+            _, idx, _, _ = mel_band_layout(cfg)
+            FS = (cfg.stft_n_fft // 2 + 1) * 2
+            order = np.argsort(idx, kind="stable")
+            counts = np.bincount(idx, minlength=FS)
+            self.gather_idx = torch.from_numpy(idx.astype(np.int32)).to(self.device)
+            self.csr_off = torch.from_numpy(np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)).to(self.device)
+            self.csr_pos = torch.from_numpy(order.astype(np.int32)).to(self.device)
 
     # ---- one Transformer (norm_output=False): x (Bq, n, d) in place
     def _transformer(self, x, Bq, n, p, depth):
@@ -136,6 +232,8 @@ class BSRoformerNet:
             gemm(_ptr(hn), W[f"{f}.net.1.weight"], _ptr(h), rows, d, hid, bias=W[f"{f}.net.1.bias"], act=ACT_GELU)
             x = _new((rows, d), x)
             gemm(_ptr(h), W[f"{f}.net.4.weight"], _ptr(x), rows, hid, d, bias=W[f"{f}.net.4.bias"], res_ptr=_ptr(x2))  # ff(x) + x
+        if f"{p}.norm.gamma" in W:  # Transformer(norm_output=True): the Mel-Band variant (mel_band_roformer.py:82-101)
+            x = rmsnorm(x, W[f"{p}.norm.gamma"], rows, d)
         return x
 
     def forward(self, raw_audio: torch.Tensor) -> torch.Tensor:
@@ -143,18 +241,23 @@ class BSRoformerNet:
         cfg, W = self.cfg, self.W
         assert raw_audio.dim() == 3 and raw_audio.shape[1] == 2 and raw_audio.dtype == torch.float32 and raw_audio.is_cuda
         b, _, L = raw_audio.shape
-        d, nb, S = cfg.dim, len(cfg.band_dims), cfg.num_stems
+        d, nb, S = cfg.dim, len(self.band_dims), cfg.num_stems
         Fq = cfg.stft_n_fft // 2 + 1
         spec = self.stft.forward(raw_audio, Fq, 0, LAYOUT_CFT)  # torch.stft(center=True, reflect, hann): planes (b, 4, F, T)
         T = spec.shape[3]
         feat = _new((b, T, Fq, 4), spec)  # "b s f t c -> b t (f s c)": feature index (f, s, c)
         check(lib.b200sep_permute4_f32(_ptr(spec), _ptr(feat), b, 4, Fq, T, 0, 3, 2, 1, _stream()), "permute4_f32")
         rows = b * T
-        nfeat = Fq * 4
+        src = feat
+        if self.mel:  # stft_repr[batch_arange, freq_indices]: every band gets its own copy of the (freq, channel) pairs it covers
+            G = self.gather_idx.numel()
+            src = _new((b, T, G, 2), spec)
+            check(lib.b200sep_gather_pairs_f32(_ptr(feat), _ptr(self.gather_idx), _ptr(src), rows, Fq * 2, G, _stream()), "gather_pairs_f32")
+        nfeat = src.shape[2] * src.shape[3] if self.mel else Fq * 4
         x = _new((b, T, nb, d), spec)
         off = 0
-        for bi, d_in in enumerate(cfg.band_dims):  # BandSplit (bs_roformer.py:134-150)
-            xn = rmsnorm(feat.data_ptr() + off * 4, W[f"band_split.to_features.{bi}.0.gamma"], rows, d_in, ld_in=nfeat, out=_new((rows, d_in), spec))
+        for bi, d_in in enumerate(self.band_dims):  # BandSplit (bs_roformer.py:134-150)
+            xn = rmsnorm(src.data_ptr() + off * 4, W[f"band_split.to_features.{bi}.0.gamma"], rows, d_in, ld_in=nfeat, out=_new((rows, d_in), spec))
             gemm(_ptr(xn), W[f"band_split.to_features.{bi}.1.weight"], x.data_ptr() + bi * d * 4, rows, d_in, nb * d, bias=W[f"band_split.to_features.{bi}.1.bias"])
             off += d_in
         for i in range(cfg.depth):
@@ -164,16 +267,16 @@ class BSRoformerNet:
             x = _new((b, T, nb, d), xt)  # "(b f) t d -> (b t) f d"
             check(lib.b200sep_permute4_f32(_ptr(xt), _ptr(x), b, nb, T, d, 0, 2, 1, 3, _stream()), "permute4_f32")
             x = self._transformer(x.view(b * T * nb, d), b * T, nb, f"layers.{i}.1", cfg.freq_transformer_depth).view(b, T, nb, d)
-        xf = rmsnorm(x, W["final_norm.gamma"], rows * nb, d)
+        xf = rmsnorm(x, W["final_norm.gamma"], rows * nb, d) if "final_norm.gamma" in W else x
         mask = _new((b, S, T, nfeat), spec)
         for si in range(S):  # MaskEstimator (bs_roformer.py:165-190)
             off = 0
-            for bi, d_in in enumerate(cfg.band_dims):
+            for bi, d_in in enumerate(self.band_dims):
                 h_ptr, lda, kdim = xf.data_ptr() + bi * d * 4, nb * d, d
-                for li in range(cfg.mask_estimator_depth):
+                for li in range(self.n_mask_linear):  # BS: mask_estimator_depth linears, Mel-Band: depth + 1 (their MLP helpers differ)
                     p = f"mask_estimators.{si}.to_freqs.{bi}.0.{2 * li}"
                     w = W[f"{p}.weight"]
-                    last = li == cfg.mask_estimator_depth - 1
+                    last = li == self.n_mask_linear - 1
                     y = _new((rows, w.shape[0]), spec)
                     gemm(h_ptr, w, _ptr(y), rows, lda, w.shape[0], bias=W[f"{p}.bias"], act=ACT_NONE if last else ACT_TANH)
                     hold = y  # keeps the buffer alive while its raw pointer is in use
@@ -182,6 +285,10 @@ class BSRoformerNet:
                     check(lib.b200sep_glu_rows_f32(hold.data_ptr() + bb * T * 2 * d_in * 4, mask.data_ptr() + (((bb * S + si) * T) * nfeat + off) * 4, T, d_in, 2 * d_in, nfeat,
                                                    _stream()), "glu_rows_f32")
                 off += d_in
+        if self.mel:  # masks_summed / num_bands_per_freq (mel_band_roformer.py:306-318)
+            full = _new((b, S, T, Fq * 4), spec)
+            check(lib.b200sep_mask_average_f32(_ptr(mask), _ptr(self.csr_off), _ptr(self.csr_pos), _ptr(full), b * S * T, nfeat // 2, Fq * 2, _stream()), "mask_average_f32")
+            mask = full
         planes = _new((b * S, 4, Fq, T), spec)
         check(lib.b200sep_roformer_mask_apply(_ptr(feat), _ptr(mask), _ptr(planes), b, S, T, Fq, _stream()), "roformer_mask_apply")
         wave = self.stft.inverse(planes, LAYOUT_CFT)  # torch.istft(center=True, hann): (b*S, 2, hop*(T-1))

@@ -109,6 +109,34 @@ __global__ void ola_starts_kernel(const float* __restrict__ chunks, const int64_
   }
 }
 
+// Mel-Band Roformer (mel_band_roformer.py:300-303): x[row][g] = src[row][idx[g]] for (re, im) pairs; row = (b, t)
+__global__ void gather_pairs_kernel(const float2* __restrict__ src, const int* __restrict__ idx, float2* __restrict__ dst, int n_src, int G, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    const int64_t row = i / G;
+    dst[i] = src[row * n_src + __ldg(&idx[g])];
+  }
+}
+
+// masks_summed / num_bands_per_freq (mel_band_roformer.py:306-318) as a gather on the output side: for every (row, fs) the complex masks of the
+// bands covering that frequency (CSR list of positions in the gathered axis) are summed and divided by their count.
+__global__ void mask_average_kernel(const float2* __restrict__ mg, const int* __restrict__ off, const int* __restrict__ pos, float2* __restrict__ out, int G, int FS,
+                                    int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int fs = (int)(i % FS);
+    const int64_t row = i / FS;
+    const int a = __ldg(&off[fs]), b = __ldg(&off[fs + 1]);
+    float2 acc = make_float2(0.f, 0.f);
+    for (int e = a; e < b; ++e) {
+      const float2 v = mg[row * G + __ldg(&pos[e])];
+      acc.x += v.x;
+      acc.y += v.y;
+    }
+    const float inv = 1.f / fmaxf((float)(b - a), 1e-8f);
+    out[i] = make_float2(acc.x * inv, acc.y * inv);
+  }
+}
+
 static inline int rf_grid(int64_t n) { return (int)std::min<int64_t>(cdiv(n, 256), kNumSMs * 16); }
 
 }  // namespace b200sep
@@ -163,6 +191,26 @@ extern "C" int b200sep_overlap_add_starts(const float* chunks, const int64_t* st
   B2_CHECK_ARG(chunks && starts && window && out && n_chunks >= 1 && channels >= 1 && len >= 1 && n_out >= 1, "overlap_add_starts: bad argument");
   dim3 grid((unsigned)std::min<int64_t>(cdiv(n_out, 256), kNumSMs * 8), channels);
   ola_starts_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(chunks, starts, window, n_chunks, channels, len, n_out, out);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
+extern "C" int b200sep_gather_pairs_f32(const float* src, const int* idx, float* dst, int64_t rows, int n_src_pairs, int n_gather, void* stream) {
+  B2_CHECK_ARG(src && idx && dst && rows >= 0 && n_src_pairs >= 1 && n_gather >= 1, "gather_pairs_f32: bad argument");
+  const int64_t total = rows * n_gather;
+  if (total == 0) return B200SEP_OK;
+  gather_pairs_kernel<<<rf_grid(total), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(src), idx, reinterpret_cast<float2*>(dst), n_src_pairs, n_gather, total);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
+extern "C" int b200sep_mask_average_f32(const float* mask_gathered, const int* csr_offsets, const int* csr_positions, float* mask_out, int64_t rows, int n_gather, int n_out,
+                                        void* stream) {
+  B2_CHECK_ARG(mask_gathered && csr_offsets && csr_positions && mask_out && rows >= 0 && n_gather >= 1 && n_out >= 1, "mask_average_f32: bad argument");
+  const int64_t total = rows * n_out;
+  if (total == 0) return B200SEP_OK;
+  mask_average_kernel<<<rf_grid(total), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(mask_gathered), csr_offsets, csr_positions,
+                                                                        reinterpret_cast<float2*>(mask_out), n_gather, n_out, total);
   B2_LAUNCHED();
   return B200SEP_OK;
 }

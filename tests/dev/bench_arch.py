@@ -83,6 +83,28 @@ def bench_roformer(a):
          a.warmup, mix.nbytes, mix.nbytes, cpu, {"chunks_per_forward": 2})
 
 
+def bench_melband(a):
+    import roformer_oracle as R
+    from audio_separator.separator.b200 import roformer as rf
+    ocfg = R.MelBandRoformerConfig()
+    w = R.make_mel_weights(ocfg, seed=14)
+    eng = rf.RoformerEngine(rf.BSRoformerNet(rf.MelBandRoformerConfig(stft_hop_length=441, mask_estimator_depth=2), w), 801, 8, SR, n_instruments=2, batch_size=2)
+    secs = a.minutes * 60
+    mix = M.normalize(M.synth_music(int(secs * SR), seed=6), 0.9, 0.0)
+    md = torch.from_numpy(mix).cuda()
+    dev_s, launches = timed(lambda: eng.demix_device(md), a.steps, a.warmup)
+    pin = torch.from_numpy(mix).pin_memory()
+    e2e_s, _ = timed(lambda: eng.demix_device(pin.cuda(non_blocking=True)).cpu(), a.steps, 1)
+    cpu = None
+    if not a.no_cpu:
+        t0 = time.time()
+        R.forward_mel(w, ocfg, mix[None, :, : ocfg.chunk_size])
+        dt = time.time() - t0
+        cpu = {"value": round((ocfg.chunk_size / SR) / dt, 4), "unit": "x realtime", "cores": torch.get_num_threads(), "kind": "port", "sample": f"one 8-s chunk forward ({dt:.2f} s)"}
+    line("MDXC/Mel-Band-Roformer", f"Mel-Band Roformer geometry (dim 384, depth 6, 60 mel bands, n_fft 2048 / hop 441, dim_t 801), {a.minutes}-min track", secs, dev_s, e2e_s, launches, a.steps,
+         a.warmup, mix.nbytes, mix.nbytes, cpu, {"chunks_per_forward": 2})
+
+
 def bench_demucs(a):
     import demucs_oracle as D
     from audio_separator.separator.b200 import demucs as dm
@@ -145,6 +167,6 @@ if __name__ == "__main__":
     ap.add_argument("--minutes", type=float, default=1.0)
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
-    for name, fn in (("mdxc", bench_mdxc), ("roformer", bench_roformer), ("demucs", bench_demucs), ("vr", bench_vr)):
+    for name, fn in (("mdxc", bench_mdxc), ("roformer", bench_roformer), ("melband", bench_melband), ("demucs", bench_demucs), ("vr", bench_vr)):
         if a.arch in ("all", name):
             fn(a)

@@ -42,3 +42,24 @@ def test_chunk_grid_and_rotary_restatement():
     q, k = torch.randn(8), torch.randn(8)
     Q, K = R.apply_rotary(q.repeat(6, 1), fr), R.apply_rotary(k.repeat(6, 1), fr)
     assert torch.allclose(Q[1] @ K[0], Q[4] @ K[3], atol=1e-5) and torch.allclose(Q[2] @ K[5], Q[0] @ K[3], atol=1e-5)
+
+
+def test_melband_oracle_and_band_layout(golden_dir, lib_built):
+    z = np.load(os.path.join(golden_dir, "roformer_small.npz"))
+    MS = dict(dim=32, depth=2, time_transformer_depth=1, freq_transformer_depth=1, num_bands=12, dim_head=8, heads=4, mask_estimator_depth=2, stft_n_fft=128, stft_hop_length=32,
+              stft_win_length=128, dim_t=65)
+    cfg = R.MelBandRoformerConfig(**MS)
+    w = R.make_mel_weights(cfg, seed=6)
+    mix = M.synth_music(int(z["n_samples"]), seed=int(z["mix_seed"]))
+    y = R.forward_mel(w, cfg, mix[None, :, : cfg.chunk_size])
+    assert np.abs(y - z["mel_forward_ref"]).max() <= 2e-5
+    # the product re-derives the band layout on its own (no oracle import on the product path): both must agree bin for bin
+    from audio_separator.separator.b200 import roformer as rf
+
+    for kw in (dict(), dict(num_bands=12, stft_n_fft=128, stft_hop_length=32, stft_win_length=128), dict(num_bands=64, sample_rate=48000, stft_n_fft=4096, stft_win_length=4096)):
+        a = R.mel_band_layout(R.MelBandRoformerConfig(**kw))
+        b = rf.mel_band_layout(rf.MelBandRoformerConfig(**kw))
+        assert all(np.array_equal(p, q) for p, q in zip(a, b))
+        mask, idx, nfpb, nbpf = b
+        assert mask[0, 0] and mask[-1, -1] and nbpf.min() >= 1 and nfpb.sum() * 2 == len(idx)
+        assert (np.diff(np.where(mask[5])[0]) == 1).all()  # a band covers a contiguous run of bins

@@ -194,3 +194,62 @@ def test_mdxc_plugin_roformer_end_to_end(rf, tmp_path):
             got = np.frombuffer(wf.readframes(30000), dtype="<i2").astype(np.int32)
         want = M.to_pcm16(ref.T.copy(), 0.9, 0.0).astype(np.int32)
         assert np.abs(got - want).max() <= 3
+
+
+# ------------------------------------------------------------------------------------------------ Mel-Band Roformer
+MSMALL = dict(dim=32, depth=2, time_transformer_depth=1, freq_transformer_depth=1, num_bands=12, dim_head=8, heads=4, mask_estimator_depth=2, stft_n_fft=128, stft_hop_length=32,
+              stft_win_length=128)
+
+
+def test_melband_gather_and_average_kernels(rf):
+    from audio_separator.separator.b200._lib import check, lib
+
+    g = torch.Generator().manual_seed(2)
+    cfg = rf.MelBandRoformerConfig(**MSMALL)
+    mask_b, idx, nfpb, nbpf = rf.mel_band_layout(cfg)
+    FS, G = 65 * 2, len(idx)
+    src = torch.randn((7, FS, 2), generator=g)
+    sd, idd = src.cuda(), torch.from_numpy(idx.astype(np.int32)).cuda()
+    dst = torch.empty((7, G, 2), device="cuda")
+    check(lib.b200sep_gather_pairs_f32(sd.data_ptr(), idd.data_ptr(), dst.data_ptr(), 7, FS, G, 0))
+    assert torch.equal(dst.cpu(), src[:, torch.from_numpy(idx)])
+    mg = torch.randn((7, G, 2), generator=g)
+    order = np.argsort(idx, kind="stable")
+    off = np.concatenate([[0], np.cumsum(np.bincount(idx, minlength=FS))]).astype(np.int32)
+    mgd, od, pd = mg.cuda(), torch.from_numpy(off).cuda(), torch.from_numpy(order.astype(np.int32)).cuda()
+    out = torch.empty((7, FS, 2), device="cuda")
+    check(lib.b200sep_mask_average_f32(mgd.data_ptr(), od.data_ptr(), pd.data_ptr(), out.data_ptr(), 7, G, FS, 0))
+    summed = torch.zeros((7, FS, 2)).index_add_(1, torch.from_numpy(idx), mg)
+    ref = summed / torch.from_numpy(np.repeat(nbpf, 2)).float()[None, :, None]
+    assert (out.cpu() - ref).abs().max() <= 1e-6
+    torch.cuda.synchronize()
+
+
+def test_melband_forward_and_demix_vs_reference_golden(rf, gold):
+    ocfg = R.MelBandRoformerConfig(**dict(MSMALL, dim_t=65))
+    w = R.make_mel_weights(ocfg, seed=6)
+    net = rf.BSRoformerNet(rf.MelBandRoformerConfig(**MSMALL), w)
+    mix = M.synth_music(int(gold["n_samples"]), seed=int(gold["mix_seed"]))
+    y = net.forward(dev(mix[None, :, : ocfg.chunk_size])).cpu().numpy()
+    assert y.shape == gold["mel_forward_ref"].shape and np.abs(y - gold["mel_forward_ref"]).max() <= 1e-4
+    kw2 = dict(MSMALL, num_stems=2, mask_estimator_depth=1, depth=1, freq_transformer_depth=2)
+    ocfg2 = R.MelBandRoformerConfig(**dict(kw2, dim_t=65))
+    net2 = rf.BSRoformerNet(rf.MelBandRoformerConfig(**kw2), R.make_mel_weights(ocfg2, seed=7))
+    y2 = net2.forward(dev(mix[None, :, : ocfg2.chunk_size])).cpu().numpy()
+    assert y2.shape == gold["mel_forward_2stem_ref"].shape and np.abs(y2 - gold["mel_forward_2stem_ref"]).max() <= 1e-4
+    out = rf.RoformerEngine(net, 65, 8, 44100, n_instruments=2, batch_size=2).demix_device(dev(mix)).cpu().numpy()
+    assert np.abs(out[0] - gold["mel_demix_ref"]).max() <= 1e-4
+
+
+def test_melband_full_size_chunk_vs_oracle(rf):
+    """A released Mel-Band geometry: dim 384, depth 6, 60 mel bands over 1025 bins (3958 gathered bin-channel pairs), hop 441, 801 frames."""
+    ocfg = R.MelBandRoformerConfig()
+    w = R.make_mel_weights(ocfg, seed=14)
+    net = rf.BSRoformerNet(rf.MelBandRoformerConfig(stft_hop_length=441, mask_estimator_depth=2), w)
+    mix = M.synth_music(ocfg.chunk_size, seed=15)[None]
+    mix = (mix / np.abs(mix).max() * 0.9).astype(np.float32)
+    ref = R.forward_mel(w, ocfg, mix)
+    got = net.forward(dev(mix)).cpu().numpy()
+    assert got.shape == ref.shape == (1, 2, ocfg.chunk_size)
+    err = np.abs(got - ref).max()
+    assert err <= 1e-4 * max(1.0, np.abs(ref).max()), (err, np.abs(ref).max())
