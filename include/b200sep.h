@@ -218,10 +218,12 @@ int b200sep_stft_inverse_ex(const b200sep_stft_plan* plan, const float* spec, in
  *   output index q*up + r - trim, kept inside [0, out_len)).  x (B,Cin,H,W); w_blocked [Cin][KH*KW][ceil48(CoutCols)];
  *   y = act(conv + bias (+ add if add_before_act)) (+ add otherwise).  act: 0 none, 1 ReLU, 2 GELU(erf), 3 LeakyReLU(0.01), 4 sigmoid, 5 tanh (also gemm_f32).
  *   out_c_total != 0: y has out_c_total channels and this call fills [out_c_off, out_c_off + Cout) (a fused torch.cat; plain convs only).
- *   Supported (KH,KW,SH,SW,DW): (1,1,1,1,1) (3,3,1,1,1) (3,3,2,2,1) (1,3,1,1,1) (1,3,1,1,2) (8,1,4,1,1) (1,8,1,4,1) (2,1,1,1,1) (1,2,1,1,1).
+ *   Tiled SIMT kernels for DH = 1 and (KH,KW,SH,SW,DW) in: (1,1,1,1,1) (3,3,1,1,1) (3,3,2,2,1) (1,3,1,1,1) (1,3,1,1,2) (8,1,4,1,1) (1,8,1,4,1) (2,1,1,1,1) (1,2,1,1,1);
+ *   any other geometry (e.g. the (4,2) / (8,4) / (12,6)-dilated ASPP convolutions of VR 5.1, layers_new.py:96-98) runs on the tensor cores when it is large
+ *   enough (Cin*KH*KW >= 32, Cout >= 16, >= 512 output pixels) and on a plain one-thread-per-output kernel otherwise.
  */
 int b200sep_conv2d_f32(const float* x, const float* w_blocked, const float* bias, const float* add, float* y, int B, int Cin, int H, int W, int Cout,
-                       int Ho, int Wo, int KH, int KW, int SH, int SW, int PH, int PW, int DW, int act, int add_before_act, int up_axis, int up,
+                       int Ho, int Wo, int KH, int KW, int SH, int SW, int PH, int PW, int DH, int DW, int act, int add_before_act, int up_axis, int up,
                        int trim, int out_len, int out_c_total, int out_c_off, const void* w_packed, void* stream);
 /* nn.GroupNorm(1, C), affine, optional activation (demucs.py:141,144).  Channel-first x (B, C, Fr, L): one sample per (b, fr) row
  * (Fr = 1: (B, C, L); Fr > 1: DConv on every frequency row without the permute of hdemucs.py:141-146); channel_last: x (B, L, C)
@@ -316,6 +318,11 @@ int b200sep_mask_average_f32(const float* mask_gathered, const int* csr_offsets,
  * max(sum_i window[q - starts[i]], 1e-10); chunks (n_chunks, channels, len), starts device int64[n_chunks] */
 int b200sep_overlap_add_starts(const float* chunks, const int64_t* starts, const float* window, int n_chunks, int channels, int len, int64_t n_out, float* out,
                                void* stream);
+
+/* nn.LSTM(bidirectional=True), one layer (LSTMModule of VR 5.1, layers_new.py:124-149): the recurrence only.  x_proj (2, T, N, 4*hid) = the input
+ * projections x_t @ W_ih^T + b_ih + b_hh of the forward / reverse direction (gate order i, f, g, o; computed with gemm_f32), w_hh (2, 4*hid, hid);
+ * out (T, N, 2*hid) = [forward h_t | reverse h_t].  hid <= 96. */
+int b200sep_lstm_bidir_f32(const float* x_proj, const float* w_hh, float* out, int T, int N, int hid, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Self-tests of the tensor-core ("bf16x3 pair") operators in isolation: fp32 device tensors in, the operator runs

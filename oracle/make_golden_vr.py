@@ -142,6 +142,49 @@ def main():
     prim4_orc = V.cmb_spectrogram_to_wave(y4o, p4)
     check("cmb_spectrogram_to_wave 4band (glue; up-sampler = stand-in on both sides)", prim4_ref, prim4_orc, 5e-5)
     out.update(wave4_seed=43, n_samples4=60000, X_4band=X4_ref.astype(np.complex64), prim_4band_standin=prim4_ref.astype(np.float32))
+    # ---- VR 5.1: CascadedNet (LSTM branch) + the is_v51_model glue (filter masks, convert_channels)
+    nets_new = ref_shim.ref_module("audio_separator.separator.uvr_lib_v5.vr_network.nets_new")
+    for bins, nout, nl in ((128, 8, 16), (64, 16, 32)):
+        w51 = V.make_weights_51(bins * 2, nout, nl, seed=3)
+        n51 = nets_new.CascadedNet(bins * 2, 56817, nout=nout, nout_lstm=nl).eval()
+        assert list(n51.state_dict()) == [n for n, _ in V.param_shapes_51(bins * 2, nout, nl)]
+        n51.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in w51.items()})
+        x51 = np.abs(rng.standard_normal((2, 2, bins + 1, 160))).astype(np.float32)
+        with torch.no_grad():
+            m51 = n51.predict_mask(torch.from_numpy(x51)).numpy()
+        check(f"CascadedNet.predict_mask (VR 5.1, bins {bins}, nout {nout})", m51, V.predict_mask_51(w51, bins * 2, x51), 5e-6)
+        if bins == 128:
+            out["mask51_in"], out["mask51_ref"] = x51, m51
+    p51 = V.single_band_param(n_fft=256, hl=64, bins=128, pre_filter_start=120, pre_filter_stop=127)
+    p51["band"][1]["convert_channels"] = "mid_side_c"
+    cfg51 = V.VRConfig(param=p51, window_size=160, aggression=5, primary_stem="Vocals", offset=64, is_51=True, nout=8, nout_lstm=16)
+    w51 = V.make_weights_51(256, 8, 16, seed=3)
+    n51 = nets_new.CascadedNet(256, 56817, nout=8, nout_lstm=16).eval()
+    n51.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in w51.items()})
+    sep51 = ref_separator(cfg51, n51, wave)
+    sep51.is_vr_51_model = True
+    X51 = sep51.loading_mix()
+    check("loading_mix VR 5.1 (convert_channels mid_side_c, lp filter mask)", X51, V.loading_mix(wave, cfg51), 1e-4)
+    y51, v51 = sep51.inference_vr(X51.copy(), "cpu", sep51.aggressiveness)
+    pred51 = lambda b: V.predict_mask_51(w51, 256, b)  # noqa: E731
+    y51o, v51o = V.inference_vr(X51.copy(), cfg51, pred51, batch_size=2)
+    check("inference_vr VR 5.1", y51, y51o, 1e-4)
+    prim51_ref, sec51_ref = sep51.spec_to_wav(y51), sep51.spec_to_wav(v51)
+    prim51, sec51 = V.separate_arrays(wave, cfg51, pred51, batch_size=2)
+    check("separate VR 5.1 primary", prim51_ref, prim51, 2e-5)
+    check("separate VR 5.1 secondary", sec51_ref, sec51, 2e-5)
+    out.update(X_51=X51.astype(np.complex64), prim_51=prim51_ref.astype(np.float32), sec_51=sec51_ref.astype(np.float32))
+    # multi-band 5.1 glue (hp / lp filter masks on the synthesis side); the up-sampler is the stand-in on both sides
+    p4 = V.four_band_v2_param()
+    p4["band"][4]["convert_channels"] = "stereo_n"
+    cfg451 = V.VRConfig(param=p4, window_size=160, offset=64, is_51=True)
+    sep451 = ref_separator(cfg451, None, wave4)
+    sep451.is_vr_51_model = True
+    X451 = sep451.loading_mix()
+    check("loading_mix 4band VR 5.1", X451, V.loading_mix(wave4, cfg451), 1e-4)
+    w451_ref = sep451.spec_to_wav(X451.copy())
+    check("cmb_spectrogram_to_wave 4band VR 5.1 (filter masks; stand-in up-sampler)", w451_ref, V.cmb_spectrogram_to_wave(X451.copy(), p4, is_51=True), 5e-5)
+    out.update(X_4band_51=X451.astype(np.complex64), wave_4band_51_standin=w451_ref.astype(np.float32))
     np.savez_compressed(os.path.join(GOLD, "vr_small.npz"), **out)
     print("wrote tests/golden/vr_small.npz; oracle pinned: OK (multi-band synthesis up-sampling: parity unpinned)")
 

@@ -50,7 +50,10 @@ class VRConfig:
     window_size: int = 512
     aggression: int = 5  # arch_config["aggression"]; value = aggression / 100 (vr_separator.py:67)
     primary_stem: str = "Instrumental"
-    offset: int = 128  # CascadedASPPNet.offset
+    offset: int = 128  # CascadedASPPNet.offset (CascadedNet of VR 5.1: 64)
+    is_51: bool = False  # VR 5.1 model (model_data has "nout" and "nout_lstm", vr_separator.py:38-41): CascadedNet + the is_v51_model glue
+    nout: int = 32
+    nout_lstm: int = 128
 
     @property
     def n_fft_bins(self):  # what VRSeparator passes as n_fft: param["bins"] * 2 (vr_separator.py:178)
@@ -275,8 +278,21 @@ def upsample(y: np.ndarray, orig_sr: int, target_sr: int) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------------------------------------- spec_utils / VRSeparator
-def wave_to_spectrogram(wave: np.ndarray, hop: int, n_fft: int, param: dict) -> np.ndarray:
-    """spec_utils.py:282-312 (is_v51_model=False)."""
+def convert_channels(spec, param, band):  # spec_utils.py:232-247
+    cc = param["band"][band].get("convert_channels")
+    if cc == "mid_side_c":
+        return np.stack([spec[0] + spec[1] * 0.25, spec[1] - spec[0] * 0.25])
+    if cc == "mid_side":
+        return np.stack([(spec[0] + spec[1]) / 2, spec[0] - spec[1]])
+    if cc == "stereo_n":
+        return np.stack([(spec[0] + spec[1] * 0.25) / 0.9375, (spec[1] + spec[0] * 0.25) / 0.9375])
+    return spec
+
+
+def wave_to_spectrogram(wave: np.ndarray, hop: int, n_fft: int, param: dict, is_51=False, band=None) -> np.ndarray:
+    """spec_utils.py:282-312."""
+    if is_51:
+        return convert_channels(np.stack([stft(wave[0], n_fft, hop), stft(wave[1], n_fft, hop)]), param, band)
     if param.get("reverse"):
         l, r = np.flip(wave[0]), np.flip(wave[1])
     elif param.get("mid_side"):
@@ -302,12 +318,12 @@ def loading_mix(wave: np.ndarray, cfg: VRConfig) -> np.ndarray:
             if bp["res_type"] != "polyphase" and bp["sr"] != p["band"][d + 1]["sr"]:
                 raise NotImplementedError(f"band {d} resamples with res_type={bp['res_type']}: only polyphase is restated")
             waves[d] = resample_polyphase(waves[d + 1], p["band"][d + 1]["sr"], bp["sr"])
-        specs[d] = wave_to_spectrogram(waves[d], bp["hl"], bp["n_fft"], p)
-    return combine_spectrograms(specs, p)
+        specs[d] = wave_to_spectrogram(waves[d], bp["hl"], bp["n_fft"], p, cfg.is_51, d)
+    return combine_spectrograms(specs, p, cfg.is_51)
 
 
-def combine_spectrograms(specs: dict, p: dict) -> np.ndarray:
-    """spec_utils.py:250-279 (is_v51_model=False)."""
+def combine_spectrograms(specs: dict, p: dict, is_51=False) -> np.ndarray:
+    """spec_utils.py:250-279."""
     n = len(p["band"])
     l = min(specs[i].shape[2] for i in specs)
     out = np.zeros((2, p["bins"] + 1, l), np.complex64)
@@ -320,7 +336,9 @@ def combine_spectrograms(specs: dict, p: dict) -> np.ndarray:
     if off > p["bins"]:
         raise ValueError("Too much bins")
     if p["pre_filter_start"] > 0:
-        if n == 1:
+        if is_51:
+            out = (out * lp_filter_mask(out.shape[1], p["pre_filter_start"], p["pre_filter_stop"])).astype(np.complex64)
+        elif n == 1:
             out = fft_lp_filter(out, p["pre_filter_start"], p["pre_filter_stop"])
         else:
             gp = 1.0
@@ -393,8 +411,17 @@ def inference_vr(X_spec: np.ndarray, cfg: VRConfig, predict, batch_size=1):
     return y, v
 
 
-def spectrogram_to_wave(spec, hop, param):  # spec_utils.py:315-338 (is_v51_model=False)
+def spectrogram_to_wave(spec, hop, param, is_51=False, band=None):  # spec_utils.py:315-338
     l, r = istft(spec[0], hop), istft(spec[1], hop)
+    if is_51:
+        cc = param["band"][band].get("convert_channels")
+        if cc == "mid_side_c":
+            return np.stack([l / 1.0625 - r / 4.25, r / 1.0625 + l / 4.25])
+        if cc == "mid_side":
+            return np.stack([l + r / 2, l - r / 2])
+        if cc == "stereo_n":
+            return np.stack([l - r * 0.25, r - l * 0.25])
+        return np.stack([l, r])
     if param.get("reverse"):
         return np.stack([np.flip(l), np.flip(r)])
     if param.get("mid_side"):
@@ -404,8 +431,14 @@ def spectrogram_to_wave(spec, hop, param):  # spec_utils.py:315-338 (is_v51_mode
     return np.stack([l, r])
 
 
-def cmb_spectrogram_to_wave(spec_m: np.ndarray, p: dict, up=upsample) -> np.ndarray:
-    """spec_utils.py:341-395 (no high-end bins, is_v51_model=False).  `up` is the band up-sampler (see the module docstring)."""
+def cmb_spectrogram_to_wave(spec_m: np.ndarray, p: dict, up=upsample, is_51=False) -> np.ndarray:
+    """spec_utils.py:341-395 (no high-end bins).  `up` is the band up-sampler (see the module docstring)."""
+    def hp(s_, a, b_):
+        return s_ * hp_filter_mask(s_.shape[1], a, b_) if is_51 else fft_hp_filter(s_, a, b_)
+
+    def lp(s_, a, b_):
+        return s_ * lp_filter_mask(s_.shape[1], a, b_) if is_51 else fft_lp_filter(s_, a, b_)
+
     n = len(p["band"])
     off = 0
     wave = None
@@ -417,18 +450,18 @@ def cmb_spectrogram_to_wave(spec_m: np.ndarray, p: dict, up=upsample) -> np.ndar
         off += h
         if d == n:
             if bp["hpf_start"] > 0:
-                s = fft_hp_filter(s, bp["hpf_start"], bp["hpf_stop"] - 1)
-            w_d = spectrogram_to_wave(s, bp["hl"], p)
+                s = hp(s, bp["hpf_start"], bp["hpf_stop"] - 1)
+            w_d = spectrogram_to_wave(s, bp["hl"], p, is_51, d)
             wave = w_d if n == 1 else np.add(wave, w_d)
         else:
             sr = p["band"][d + 1]["sr"]
             if d == 1:
-                s = fft_lp_filter(s, bp["lpf_start"], bp["lpf_stop"])
-                wave = up(spectrogram_to_wave(s, bp["hl"], p), bp["sr"], sr)
+                s = lp(s, bp["lpf_start"], bp["lpf_stop"])
+                wave = up(spectrogram_to_wave(s, bp["hl"], p, is_51, d), bp["sr"], sr)
             else:
-                s = fft_hp_filter(s, bp["hpf_start"], bp["hpf_stop"] - 1)
-                s = fft_lp_filter(s, bp["lpf_start"], bp["lpf_stop"])
-                wave = up(np.add(wave, spectrogram_to_wave(s, bp["hl"], p)), bp["sr"], sr)
+                s = hp(s, bp["hpf_start"], bp["hpf_stop"] - 1)
+                s = lp(s, bp["lpf_start"], bp["lpf_stop"])
+                wave = up(np.add(wave, spectrogram_to_wave(s, bp["hl"], p, is_51, d)), bp["sr"], sr)
     return wave
 
 
@@ -438,4 +471,183 @@ def separate_arrays(wave: np.ndarray, cfg: VRConfig, predict, batch_size=1, up=u
     y, v = inference_vr(X, cfg, predict, batch_size)
     y = np.nan_to_num(y, nan=0.0, posinf=0.0, neginf=0.0)
     v = np.nan_to_num(v, nan=0.0, posinf=0.0, neginf=0.0)
-    return cmb_spectrogram_to_wave(y, cfg.param, up).astype(np.float32), cmb_spectrogram_to_wave(v, cfg.param, up).astype(np.float32)
+    return cmb_spectrogram_to_wave(y, cfg.param, up, cfg.is_51).astype(np.float32), cmb_spectrogram_to_wave(v, cfg.param, up, cfg.is_51).astype(np.float32)
+
+
+# =========================================================================================================================
+# VR 5.1: CascadedNet with an LSTM branch (uvr_lib_v5/vr_network/nets_new.py:8-160, layers_new.py:8-149) and the is_v51_model variants of the
+# spectrogram glue (spec_utils.py: convert_channels :232-247, get_lp_filter_mask / get_hp_filter_mask :398-407, the `is_v51_model` branches of
+# combine_spectrograms :266-268, wave_to_spectrogram :301-310, spectrogram_to_wave :322-330, cmb_spectrogram_to_wave :357-384).
+def param_shapes_51(n_fft_bins: int, nout: int, nout_lstm: int, nn_arch_size: int = 56817):
+    out = []
+    max_bin = n_fft_bins // 2
+    nin_lstm = max_bin // 2
+    nout = 64 if nn_arch_size == 218409 else nout
+
+    def cba(p, nin, no, k):
+        out.append((f"{p}.conv.0.weight", (no, nin, k, k)))
+        for nm in ("weight", "bias", "running_mean", "running_var"):
+            out.append((f"{p}.conv.1.{nm}", (no,)))
+        out.append((f"{p}.conv.1.num_batches_tracked", ()))
+
+    def base(p, nin, no, n_lstm_in, n_lstm_out):
+        cba(f"{p}.enc1", nin, no, 3)
+        c = no
+        for i, m in zip((2, 3, 4, 5), (2, 4, 6, 8)):
+            cba(f"{p}.enc{i}.conv1", c, no * m, 3)
+            cba(f"{p}.enc{i}.conv2", no * m, no * m, 3)
+            c = no * m
+        cba(f"{p}.aspp.conv1.1", no * 8, no * 8, 1)
+        cba(f"{p}.aspp.conv2", no * 8, no * 8, 1)
+        for i in (3, 4, 5):
+            cba(f"{p}.aspp.conv{i}", no * 8, no * 8, 3)
+        cba(f"{p}.aspp.bottleneck", no * 40, no * 8, 1)
+        cba(f"{p}.dec4.conv1", no * 14, no * 6, 3)
+        cba(f"{p}.dec3.conv1", no * 10, no * 4, 3)
+        cba(f"{p}.dec2.conv1", no * 6, no * 2, 3)
+        cba(f"{p}.lstm_dec2.conv", no * 2, 1, 1)
+        hid = n_lstm_out // 2
+        for sfx in ("", "_reverse"):
+            out.extend([(f"{p}.lstm_dec2.lstm.weight_ih_l0{sfx}", (4 * hid, n_lstm_in)), (f"{p}.lstm_dec2.lstm.weight_hh_l0{sfx}", (4 * hid, hid)),
+                        (f"{p}.lstm_dec2.lstm.bias_ih_l0{sfx}", (4 * hid,)), (f"{p}.lstm_dec2.lstm.bias_hh_l0{sfx}", (4 * hid,))])
+        out.extend([(f"{p}.lstm_dec2.dense.0.weight", (n_lstm_in, n_lstm_out)), (f"{p}.lstm_dec2.dense.0.bias", (n_lstm_in,))])
+        for nm in ("weight", "bias", "running_mean", "running_var"):
+            out.append((f"{p}.lstm_dec2.dense.1.{nm}", (n_lstm_in,)))
+        out.append((f"{p}.lstm_dec2.dense.1.num_batches_tracked", ()))
+        cba(f"{p}.dec1.conv1", no * 3 + 1, no, 3)
+
+    base("stg1_low_band_net.0", 2, nout // 2, nin_lstm // 2, nout_lstm)
+    cba("stg1_low_band_net.1", nout // 2, nout // 4, 1)
+    base("stg1_high_band_net", 2, nout // 4, nin_lstm // 2, nout_lstm // 2)
+    base("stg2_low_band_net.0", nout // 4 + 2, nout, nin_lstm // 2, nout_lstm)
+    cba("stg2_low_band_net.1", nout, nout // 2, 1)
+    base("stg2_high_band_net", nout // 4 + 2, nout // 2, nin_lstm // 2, nout_lstm // 2)
+    base("stg3_full_band_net", 3 * nout // 4 + 2, nout, nin_lstm, nout_lstm)
+    out.append(("out.weight", (2, nout, 1, 1)))
+    out.append(("aux_out.weight", (2, 3 * nout // 4, 1, 1)))
+    return out
+
+
+def make_weights_51(n_fft_bins, nout, nout_lstm, seed=0, nn_arch_size=56817):
+    rng = np.random.default_rng(seed)
+    w = {}
+    for name, shape in param_shapes_51(n_fft_bins, nout, nout_lstm, nn_arch_size):
+        if name.endswith("num_batches_tracked"):
+            a = np.array(100, dtype=np.int64)
+        elif name.endswith("running_var"):
+            a = rng.uniform(0.5, 1.5, shape).astype(np.float32)
+        elif name.endswith("running_mean"):
+            a = rng.normal(0.0, 0.2, shape).astype(np.float32)
+        elif ".lstm." in name:
+            a = rng.uniform(-0.3, 0.3, shape).astype(np.float32)
+        elif len(shape) == 1 and name.endswith(".weight"):
+            a = rng.uniform(0.7, 1.3, shape).astype(np.float32)
+        elif len(shape) == 1:
+            a = rng.normal(0.0, 0.1, shape).astype(np.float32)
+        elif len(shape) == 2:
+            a = rng.normal(0.0, math.sqrt(1.0 / shape[1]), shape).astype(np.float32)
+        else:
+            a = rng.normal(0.0, math.sqrt(2.0 / (shape[1] * shape[2] * shape[3])), shape).astype(np.float32)
+        w[name] = a
+    return w
+
+
+def net_forward_51(weights, n_fft_bins: int, x: np.ndarray, dtype="float32") -> np.ndarray:
+    """CascadedNet.forward in eval mode (nets_new.py:104-137): x (B, 2, bins + 1, W) -> mask (B, 2, bins + 1, W)."""
+    import torch
+    import torch.nn.functional as F
+
+    td = torch.float64 if dtype == "float64" else torch.float32
+    W = {k: torch.from_numpy(np.asarray(v)).to(td) for k, v in weights.items() if not k.endswith("num_batches_tracked")}
+    x = torch.from_numpy(np.ascontiguousarray(x)).to(td)
+
+    def cba(y, p, stride=1, pad=None, dil=1, leaky=False):
+        k = W[f"{p}.conv.0.weight"].shape[-1]
+        if pad is None:
+            pad = 1 if k == 3 else 0
+        y = F.conv2d(y, W[f"{p}.conv.0.weight"], stride=stride, padding=pad, dilation=dil)
+        y = F.batch_norm(y, W[f"{p}.conv.1.running_mean"], W[f"{p}.conv.1.running_var"], W[f"{p}.conv.1.weight"], W[f"{p}.conv.1.bias"], False, 0.0, 1e-5)
+        return F.leaky_relu(y, 0.01) if leaky else F.relu(y)
+
+    def enc(y, p, stride):
+        return cba(cba(y, f"{p}.conv1", stride=stride, leaky=True), f"{p}.conv2", leaky=True)
+
+    def dec(y, skip, p):
+        y = F.interpolate(y, scale_factor=2, mode="bilinear", align_corners=True)
+        d = skip.shape[3] - y.shape[3]
+        assert d >= 0
+        if d:
+            skip = skip[:, :, :, d // 2 : d // 2 + y.shape[3]]
+        return cba(torch.cat([y, skip], 1), f"{p}.conv1")
+
+    def aspp(y, p):
+        h, w_ = y.shape[2:]
+        f1 = F.interpolate(cba(F.adaptive_avg_pool2d(y, (1, None)), f"{p}.conv1.1"), size=(h, w_), mode="bilinear", align_corners=True)
+        feats = [f1, cba(y, f"{p}.conv2")] + [cba(y, f"{p}.conv{i}", pad=dl, dil=dl) for i, dl in zip((3, 4, 5), ((4, 2), (8, 4), (12, 6)))]
+        return cba(torch.cat(feats, 1), f"{p}.bottleneck")
+
+    def lstm_dir(seq, p, sfx):  # seq (T, N, in) -> (T, N, hid); gate order i, f, g, o
+        Wi, Wh, bi, bh = W[f"{p}.weight_ih_l0{sfx}"], W[f"{p}.weight_hh_l0{sfx}"], W[f"{p}.bias_ih_l0{sfx}"], W[f"{p}.bias_hh_l0{sfx}"]
+        hid = Wh.shape[1]
+        h = torch.zeros(seq.shape[1], hid, dtype=td)
+        c = torch.zeros_like(h)
+        outs = []
+        for t in range(seq.shape[0]):
+            g = seq[t] @ Wi.t() + bi + h @ Wh.t() + bh
+            i_, f_, g_, o_ = g.chunk(4, dim=1)
+            c = torch.sigmoid(f_) * c + torch.sigmoid(i_) * torch.tanh(g_)
+            h = torch.sigmoid(o_) * torch.tanh(c)
+            outs.append(h)
+        return torch.stack(outs)
+
+    def lstm_module(y, p):  # layers_new.py:130-149
+        N, _, nbins, nframes = y.shape
+        h = cba(y, f"{p}.conv")[:, 0].permute(2, 0, 1)  # nframes, N, nbins
+        fw = lstm_dir(h, f"{p}.lstm", "")
+        bw = lstm_dir(h.flip(0), f"{p}.lstm", "_reverse").flip(0)
+        h = torch.cat([fw, bw], dim=-1).reshape(nframes * N, -1)
+        h = F.linear(h, W[f"{p}.dense.0.weight"], W[f"{p}.dense.0.bias"])
+        h = F.relu(F.batch_norm(h, W[f"{p}.dense.1.running_mean"], W[f"{p}.dense.1.running_var"], W[f"{p}.dense.1.weight"], W[f"{p}.dense.1.bias"], False, 0.0, 1e-5))
+        return h.reshape(nframes, N, 1, nbins).permute(1, 2, 3, 0)
+
+    def base(y, p):
+        e1 = cba(y, f"{p}.enc1")
+        e2 = enc(e1, f"{p}.enc2", 2)
+        e3 = enc(e2, f"{p}.enc3", 2)
+        e4 = enc(e3, f"{p}.enc4", 2)
+        e5 = enc(e4, f"{p}.enc5", 2)
+        h = aspp(e5, f"{p}.aspp")
+        h = dec(h, e4, f"{p}.dec4")
+        h = dec(h, e3, f"{p}.dec3")
+        h = dec(h, e2, f"{p}.dec2")
+        h = torch.cat([h, lstm_module(h, f"{p}.lstm_dec2")], 1)
+        return dec(h, e1, f"{p}.dec1")
+
+    with torch.no_grad():
+        max_bin, output_bin = n_fft_bins // 2, n_fft_bins // 2 + 1
+        x = x[:, :, :max_bin]
+        bw = x.shape[2] // 2
+        l1_in, h1_in = x[:, :, :bw], x[:, :, bw:]
+        l1 = cba(base(l1_in, "stg1_low_band_net.0"), "stg1_low_band_net.1")
+        h1 = base(h1_in, "stg1_high_band_net")
+        aux1 = torch.cat([l1, h1], 2)
+        l2 = cba(base(torch.cat([l1_in, l1], 1), "stg2_low_band_net.0"), "stg2_low_band_net.1")
+        h2 = base(torch.cat([h1_in, h1], 1), "stg2_high_band_net")
+        aux2 = torch.cat([l2, h2], 2)
+        f3 = base(torch.cat([x, aux1, aux2], 1), "stg3_full_band_net")
+        mask = torch.sigmoid(F.conv2d(f3, W["out.weight"]))
+        mask = F.pad(mask, (0, 0, 0, output_bin - mask.shape[2]), mode="replicate")
+    return mask.to(torch.float32).numpy()
+
+
+def predict_mask_51(weights, n_fft_bins, x, offset=64, dtype="float32"):
+    m = net_forward_51(weights, n_fft_bins, x, dtype)
+    return m[:, :, :, offset:-offset] if offset > 0 else m
+
+
+def lp_filter_mask(n_bins, bin_start, bin_stop):  # spec_utils.py:398-401
+    return np.concatenate([np.ones((bin_start - 1, 1)), np.linspace(1, 0, bin_stop - bin_start + 1)[:, None], np.zeros((n_bins - bin_stop, 1))], axis=0)
+
+
+def hp_filter_mask(n_bins, bin_start, bin_stop):  # spec_utils.py:404-407
+    return np.concatenate([np.zeros((bin_stop + 1, 1)), np.linspace(0, 1, 1 + bin_start - bin_stop)[:, None], np.ones((n_bins - bin_start - 2, 1))], axis=0)

@@ -1,4 +1,4 @@
-"""B200 VR architecture plugin (CascadedASPPNet models, e.g. the HP / HP2 / SP "VR arch" v4-v5.0 checkpoints).
+"""B200 VR architecture plugin (CascadedASPPNet models -- the HP / HP2 / SP "VR arch" v4-v5.0 checkpoints -- and VR 5.1 CascadedNet models).
 
 Plugin contract of the reference's VRSeparator (audio_separator/separator/architectures/vr_separator.py:26-253): ctor
 `(common_config, arch_config)` with arch keys batch_size / window_size / aggression / enable_tta / enable_post_process /
@@ -12,15 +12,18 @@ import numpy as np
 import torch
 
 from ..b200 import vr_params
-from ..b200.vr import NN_ARCH_SIZES, VR_51_SIZES, VREngine, VRNet
+from ..b200.vr import NN_ARCH_SIZES, VR_51_SIZES, VREngine, VRNet, VRNet51
 from ..common_separator import CommonSeparator
 
 
 class VRSeparator(CommonSeparator):
     def __init__(self, common_config, arch_config):
         super().__init__(config=common_config)
-        if "nout" in self.model_data and "nout_lstm" in self.model_data:
-            raise NotImplementedError("VR 5.1 models (CascadedNet with LSTM) are outside the accelerated VR path")
+        self.model_capacity = 32, 128
+        self.is_vr_51_model = False
+        if "nout" in self.model_data and "nout_lstm" in self.model_data:  # vr_separator.py:38-41
+            self.model_capacity = self.model_data["nout"], self.model_data["nout_lstm"]
+            self.is_vr_51_model = True
         self.model_params = vr_params.load(self.model_data["vr_model_param"], os.path.dirname(self.model_path))
         self.enable_tta = arch_config.get("enable_tta", False)
         self.enable_post_process = arch_config.get("enable_post_process", False)
@@ -46,15 +49,17 @@ class VRSeparator(CommonSeparator):
         model_size = math.ceil(os.stat(self.model_path).st_size / 1024)
         nn_arch_size = min(NN_ARCH_SIZES, key=lambda x: abs(x - model_size))
         arch = int(self.model_data.get("b200_nn_architecture", nn_arch_size))  # tests use reduced widths whose file size is off the table
-        if arch in VR_51_SIZES:
-            raise NotImplementedError("VR 5.1 models (CascadedNet with LSTM) are outside the accelerated VR path")
+        self.is_vr_51_model = self.is_vr_51_model or arch in VR_51_SIZES  # :175-179
         if self.model_path.lower().endswith(".npz"):
             with np.load(self.model_path) as z:
                 state = {k: z[k] for k in z.files}
         else:
             sd = torch.load(self.model_path, map_location="cpu", weights_only=True)
             state = {k: v.numpy() for k, v in sd.items()}
-        self.net = VRNet(arch, self.model_params["bins"] * 2, state, device=self.torch_device)
+        if self.is_vr_51_model:
+            self.net = VRNet51(self.model_params["bins"] * 2, self.model_capacity[0], self.model_capacity[1], state, nn_arch_size=arch, device=self.torch_device)
+        else:
+            self.net = VRNet(arch, self.model_params["bins"] * 2, state, device=self.torch_device)
         self.engine = VREngine(self.net, self.model_params, self.window_size, self.aggression_setting, self.primary_stem_name, self.batch_size)
 
     def separate(self, audio_file_path, custom_output_names=None):

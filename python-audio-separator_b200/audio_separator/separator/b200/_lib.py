@@ -60,7 +60,8 @@ _SIGS = {
     "b200sep_rect_overlap_add": (i32, [vp, i32, i32, i32, i64, i64, i64, f32, vp, vp]),
     "b200sep_stft_forward_ex": (i32, [vp, vp, i64, i64, i64, i32, i32, i32, i32, f32, i32, i32, i32, i32, vp, vp]),
     "b200sep_stft_inverse_ex": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp, vp, vp]),
-    "b200sep_conv2d_f32": (i32, [vp, vp, vp, vp, vp] + [i32] * 22 + [vp, vp]),
+    "b200sep_conv2d_f32": (i32, [vp, vp, vp, vp, vp] + [i32] * 23 + [vp, vp]),
+    "b200sep_lstm_bidir_f32": (i32, [vp, vp, vp, i32, i32, i32, vp]),
     "b200sep_tc_packed_floats": (i64, [i32, i32]),
     "b200sep_tc_pack_linear_weights": (i32, [vp, i32, i32, i32, vp, vp]),
     "b200sep_tc_pack_conv_weights": (i32, [vp, i32, i32, i32, vp, vp]),

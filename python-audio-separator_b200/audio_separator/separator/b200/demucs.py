@@ -141,12 +141,12 @@ def _packed_linear(w):
     return pk
 
 
-def conv2d(x, wb, bias, cout, k, s=(1, 1), p=(0, 0), dw=1, act=ACT_NONE, add=None, add_before_act=False, out_hw=None, out=None, out_c_off=0):
+def conv2d(x, wb, bias, cout, k, s=(1, 1), p=(0, 0), dw=1, act=ACT_NONE, add=None, add_before_act=False, out_hw=None, out=None, out_c_off=0, dh=1):
     """x (B,Cin,H,W) -> (B,cout,Ho,Wo);  out_hw overrides the implied output size (right/bottom zero padding is implicit);
     out/out_c_off: write into channels [out_c_off, out_c_off + cout) of an existing (B, C_total, Ho, Wo) tensor (a fused torch.cat)."""
     B, cin, H, W = x.shape
     if out_hw is None:
-        Ho = (H + 2 * p[0] - k[0]) // s[0] + 1
+        Ho = (H + 2 * p[0] - dh * (k[0] - 1) - 1) // s[0] + 1
         Wo = (W + 2 * p[1] - dw * (k[1] - 1) - 1) // s[1] + 1
     else:
         Ho, Wo = out_hw
@@ -157,7 +157,7 @@ def conv2d(x, wb, bias, cout, k, s=(1, 1), p=(0, 0), dw=1, act=ACT_NONE, add=Non
         y, ct = out, out.shape[1]
     pk = _packed_conv(wb, cin, k[0] * k[1], cout)
     check(lib.b200sep_conv2d_f32(_ptr(x), _ptr(wb), _ptr(bias) if bias is not None else None, _ptr(add) if add is not None else None, _ptr(y), B, cin, H, W, cout,
-                                 Ho, Wo, k[0], k[1], s[0], s[1], p[0], p[1], dw, act, int(add_before_act), 0, 1, 0, 0, ct, out_c_off,
+                                 Ho, Wo, k[0], k[1], s[0], s[1], p[0], p[1], dh, dw, act, int(add_before_act), 0, 1, 0, 0, ct, out_c_off,
                                  _ptr(pk) if pk is not None else None, _stream()), "conv2d_f32")
     return y
 
@@ -171,7 +171,7 @@ def conv_transpose(x, wb, bias, cout, axis, stride, trim, out_len, act=ACT_NONE)
     else:
         y = _new((B, cout, H, out_len), x)
         k, p, hw = (1, 2), (0, 1), (H, W + 1)
-    check(lib.b200sep_conv2d_f32(_ptr(x), _ptr(wb), _ptr(bias), None, _ptr(y), B, cin, H, W, stride * cout, hw[0], hw[1], k[0], k[1], 1, 1, p[0], p[1], 1, act, 0,
+    check(lib.b200sep_conv2d_f32(_ptr(x), _ptr(wb), _ptr(bias), None, _ptr(y), B, cin, H, W, stride * cout, hw[0], hw[1], k[0], k[1], 1, 1, p[0], p[1], 1, 1, act, 0,
                                  axis, stride, trim, out_len, 0, 0, None, _stream()), "conv2d_f32(transposed)")
     return y
 

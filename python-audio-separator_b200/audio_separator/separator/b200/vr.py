@@ -5,7 +5,7 @@ VRSeparator.loading_mix / inference_vr / spec_to_wav (architectures/vr_separator
 band resampling, the patch loop, the mask post-processing and the band synthesis all on the GPU.
 This file is the graph builder: device buffers + launch order.  All arithmetic is behind the C ABI (include/b200sep.h).
 
-Not covered (raises): VR 5.1 models (nets_new.CascadedNet), enable_tta / enable_post_process / high_end_process, `reverse` model
+VR 5.1 models (nets_new.CascadedNet, LSTM branch) run through VRNet51.  Not covered (raises): enable_tta / enable_post_process / high_end_process, `reverse` model
 parameters, analysis bands resampled with anything but res_type "polyphase".  The band UP-sampling of the synthesis side uses the
 same Kaiser polyphase design (the reference calls libsamplerate "sinc_fastest" there; see DESIGN.md: parity unpinned for that step).
 """
@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from ._lib import LAYOUT_CFT, check, lib
-from .demucs import ACT_NONE, ACT_RELU, _new, block_conv_weight, conv2d, ew
+from .demucs import ACT_NONE, ACT_RELU, _new, block_conv_weight, conv2d, ew, linear
 from .engine import StftPlan, _ptr, _require_cuda, _stream
 
 ACT_LEAKY, ACT_SIGMOID = 3, 4
@@ -72,6 +72,16 @@ def hp_gain(n_bins, start, stop):
     return g
 
 
+def lp_filter_mask(n_bins, start, stop):
+    """get_lp_filter_mask (spec_utils.py:398-401, the VR 5.1 filters): ones, a linear ramp 1 -> 0 over [start-1, stop], zeros."""
+    return np.concatenate([np.ones(start - 1), np.linspace(1, 0, stop - start + 1), np.zeros(n_bins - stop)])
+
+
+def hp_filter_mask(n_bins, start, stop):
+    """get_hp_filter_mask (spec_utils.py:404-407): zeros up to `stop`, a linear ramp 0 -> 1 up to `start`, ones."""
+    return np.concatenate([np.zeros(stop + 1), np.linspace(0, 1, 1 + start - stop), np.ones(n_bins - start - 2)])
+
+
 def capacity(nn_architecture: int):
     """determine_model_capacity (nets.py:67-93)."""
     if nn_architecture in (31191, 33966, 129605):
@@ -96,6 +106,17 @@ class VRNet:
         self.device = torch.device(device)
         st = {k: np.asarray(v) for k, v in state.items()}
         self.W = {}
+        self._fold_all(st)
+        for nm in ("out",):
+            self._put(nm + ".w", block_conv_weight(st[nm + ".weight"].astype(np.float32)))
+        need = ["stg1_low_band_net.enc1.conv1.w", "stg3_full_band_net.dec1.conv.w", "stg2_bridge.w", "out.w", "stg1_low_band_net.aspp.conv3.dw"]
+        for n in need:
+            if n not in self.W:
+                raise ValueError(f"state dict lacks {n.rsplit('.', 1)[0]}: not a CascadedASPPNet checkpoint")
+        if self.W["stg1_low_band_net.enc1.conv1.b"].numel() != self.c1:
+            raise ValueError("checkpoint width does not match the capacity of its nn_architecture size")
+
+    def _fold_all(self, st):
         for name in st:
             if not name.endswith(".conv.0.weight"):
                 continue
@@ -105,14 +126,6 @@ class VRNet:
                 self._fold(p, st[p + ".conv.1.weight"], st, p + ".conv.2")
             elif p + ".conv.1.running_var" in st:  # Conv2DBNActiv
                 self._fold(p, st[name], st, p + ".conv.1")
-        for nm in ("out",):
-            self._put(nm + ".w", block_conv_weight(st[nm + ".weight"].astype(np.float32)))
-        need = ["stg1_low_band_net.enc1.conv1.w", "stg3_full_band_net.dec1.conv.w", "stg2_bridge.w", "out.w", "stg1_low_band_net.aspp.conv3.dw"]
-        for n in need:
-            if n not in self.W:
-                raise ValueError(f"state dict lacks {n.rsplit('.', 1)[0]}: not a CascadedASPPNet checkpoint")
-        if self.W["stg1_low_band_net.enc1.conv1.b"].numel() != self.c1:
-            raise ValueError("checkpoint width does not match the capacity of its nn_architecture size")
 
     def _put(self, name, a):
         self.W[name] = torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
@@ -125,10 +138,11 @@ class VRNet:
         self.W[p + ".k"] = int(w.shape[-1])
 
     # ---- sub-graphs
-    def _cba(self, x, p, stride=1, act=ACT_RELU, out=None, out_c_off=0):
+    def _cba(self, x, p, stride=1, act=ACT_RELU, out=None, out_c_off=0, dil=(1, 1)):
         k = self.W[p + ".k"]
         cout = self.W[p + ".b"].numel()
-        return conv2d(x, self.W[p + ".w"], self.W[p + ".b"], cout, (k, k), s=(stride, stride), p=(k // 2, k // 2), act=act, out=out, out_c_off=out_c_off)
+        pad = (dil[0] * (k // 2), dil[1] * (k // 2))  # Conv2DBNActiv(..., pad=dilation, dilation=dilation) in the ASPP modules
+        return conv2d(x, self.W[p + ".w"], self.W[p + ".b"], cout, (k, k), s=(stride, stride), p=pad, dw=dil[1], dh=dil[0], act=act, out=out, out_c_off=out_c_off)
 
     def _sep(self, x, p, dil, out, out_c_off):
         B, C, H, W = x.shape
@@ -207,11 +221,136 @@ class VRNet:
         return m
 
 
+class VRNet51(VRNet):
+    """CascadedNet of VR 5.1 (vr_network/nets_new.py:52-160, layers_new.py): five band nets with stride-2 encoders, an ASPP of dilated 3x3 convolutions
+    (dilations (4,2), (8,4), (12,6)) and a bidirectional-LSTM branch over the time axis in front of the last decoder; eval mode (BatchNorm folded)."""
+
+    def __init__(self, n_fft_bins: int, nout: int, nout_lstm: int, state: dict, nn_arch_size: int = 56817, device="cuda:0"):
+        _require_cuda()
+        self.arch = int(nn_arch_size)
+        self.nout = 64 if self.arch == 218409 else int(nout)
+        self.max_bin, self.output_bin, self.offset = n_fft_bins // 2, n_fft_bins // 2 + 1, 64
+        self.device = torch.device(device)
+        st = {k: np.asarray(v) for k, v in state.items()}
+        self.W = {}
+        self._fold_all(st)
+        self._put("out.w", block_conv_weight(st["out.weight"].astype(np.float32)))
+        for name in st:  # LSTMModule: both directions' input projections (biases summed), recurrent weights, dense + BatchNorm1d folded
+            if not name.endswith(".lstm.weight_ih_l0"):
+                continue
+            p = name[: -len(".lstm.weight_ih_l0")]
+            for d, sfx in enumerate(("", "_reverse")):
+                self._put(f"{p}.wih{d}", st[f"{p}.lstm.weight_ih_l0{sfx}"].astype(np.float32))
+                self._put(f"{p}.bih{d}", (st[f"{p}.lstm.bias_ih_l0{sfx}"].astype(np.float64) + st[f"{p}.lstm.bias_hh_l0{sfx}"].astype(np.float64)).astype(np.float32))
+            self._put(f"{p}.whh", np.stack([st[f"{p}.lstm.weight_hh_l0"], st[f"{p}.lstm.weight_hh_l0_reverse"]]).astype(np.float32))
+            inv = st[f"{p}.dense.1.weight"].astype(np.float64) / np.sqrt(st[f"{p}.dense.1.running_var"].astype(np.float64) + 1e-5)
+            self._put(f"{p}.dense.w", (st[f"{p}.dense.0.weight"].astype(np.float64) * inv[:, None]).astype(np.float32))
+            self._put(f"{p}.dense.b", ((st[f"{p}.dense.0.bias"].astype(np.float64) - st[f"{p}.dense.1.running_mean"].astype(np.float64)) * inv
+                                       + st[f"{p}.dense.1.bias"].astype(np.float64)).astype(np.float32))
+        for n in ("stg1_low_band_net.0.enc1.w", "stg1_low_band_net.1.w", "stg3_full_band_net.lstm_dec2.whh", "stg3_full_band_net.dec1.conv1.w", "out.w"):
+            if n not in self.W:
+                raise ValueError(f"state dict lacks {n.rsplit('.', 1)[0]}: not a VR 5.1 CascadedNet checkpoint")
+        if self.W["stg3_full_band_net.enc1.b"].numel() != self.nout:
+            raise ValueError("model_data nout does not match the checkpoint")
+
+    def _enc(self, x, p, stride):
+        return self._cba(self._cba(x, f"{p}.conv1", stride=stride, act=ACT_LEAKY), f"{p}.conv2", act=ACT_LEAKY)
+
+    def _dec51(self, x, skip, p):
+        B, C, H, W = x.shape
+        Cs, Hs, Ws = skip.shape[1:]
+        if Hs != 2 * H or Ws < 2 * W:
+            raise ValueError(f"decoder skip {tuple(skip.shape)} does not fit the up-sampled {(B, C, 2 * H, 2 * W)} (the reference fails here too)")
+        cat = _new((B, C + Cs, 2 * H, 2 * W), x)
+        check(lib.b200sep_upsample2x_bilinear_f32(_ptr(x), _ptr(cat), B, C, H, W, C + Cs, 0, _stream()), "upsample2x_bilinear_f32")
+        d = (Ws - 2 * W) // 2
+        copy_view(skip[:, :, :, d : d + 2 * W], cat[:, C:])
+        return self._cba(cat, f"{p}.conv1")
+
+    def _aspp51(self, x, p):
+        B, C, H, W = x.shape
+        co = self.W[f"{p}.conv2.b"].numel()
+        cat = _new((B, co * 5, H, W), x)
+        pooled = _new((B, C, 1, W), x)
+        check(lib.b200sep_mean_h_f32(_ptr(x), _ptr(pooled), B * C, H, W, _stream()), "mean_h_f32")
+        f1 = self._cba(pooled, f"{p}.conv1.1")
+        copy_view(f1.expand(B, co, H, W), cat[:, :co])
+        self._cba(x, f"{p}.conv2", out=cat, out_c_off=co)
+        for i, dil in ((3, (4, 2)), (4, (8, 4)), (5, (12, 6))):
+            self._cba(x, f"{p}.conv{i}", out=cat, out_c_off=co * (i - 1), dil=dil)
+        return self._cba(cat, f"{p}.bottleneck")
+
+    def _lstm(self, x, p, out, out_c_off):
+        """LSTMModule.forward (layers_new.py:130-149): (N, C, nbins, nframes) -> one channel (N, 1, nbins, nframes) written into `out`."""
+        W = self.W
+        N, _, nb, nf = x.shape
+        hc = self._cba(x, f"{p}.conv")  # (N, 1, nbins, nframes)
+        seq = _new((nf, N, nb, 1), x)
+        copy_view(hc.permute(3, 0, 2, 1), seq)  # "N 1 bins frames -> frames N bins"
+        hid = W[f"{p}.whh"].shape[2]
+        xp = _new((2, nf * N, 4 * hid), x)
+        for d in range(2):
+            check(lib.b200sep_gemm_f32(_ptr(seq), _ptr(W[f"{p}.wih{d}"]), xp.data_ptr() + d * nf * N * 4 * hid * 4, nf * N, 4 * hid, nb, nb, nb, 4 * hid, 1, 0, 0, 0, 1.0,
+                                       _ptr(W[f"{p}.bih{d}"]), None, 0, None, None, None, _stream()), "gemm_f32(lstm input projection)")
+        hs = _new((nf * N, 2 * hid), x)
+        check(lib.b200sep_lstm_bidir_f32(_ptr(xp), _ptr(W[f"{p}.whh"]), _ptr(hs), nf, N, hid, _stream()), "lstm_bidir_f32")
+        dn = linear(hs, W[f"{p}.dense.w"], W[f"{p}.dense.b"], act=ACT_RELU)  # Linear + BatchNorm1d (folded) + ReLU: (frames*N, bins)
+        copy_view(dn.view(nf, N, nb, 1).permute(1, 3, 2, 0), out[:, out_c_off : out_c_off + 1])
+
+    def _base51(self, x, p):
+        e1 = self._cba(x, f"{p}.enc1")
+        e2 = self._enc(e1, f"{p}.enc2", 2)
+        e3 = self._enc(e2, f"{p}.enc3", 2)
+        e4 = self._enc(e3, f"{p}.enc4", 2)
+        e5 = self._enc(e4, f"{p}.enc5", 2)
+        h = self._aspp51(e5, f"{p}.aspp")
+        h = self._dec51(h, e4, f"{p}.dec4")
+        h = self._dec51(h, e3, f"{p}.dec3")
+        h = self._dec51(h, e2, f"{p}.dec2")
+        B, C, H, W = h.shape
+        hl = _new((B, C + 1, H, W), h)  # torch.cat([bottleneck, lstm_dec2(bottleneck)], dim=1)
+        copy_view(h, hl[:, :C])
+        self._lstm(h, f"{p}.lstm_dec2", hl, C)
+        return self._dec51(hl, e1, f"{p}.dec1")
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        assert x.dim() == 4 and x.shape[1] == 2 and x.dtype == torch.float32 and x.is_cuda
+        B, _, _, Wd = x.shape
+        mb = self.max_bin
+        bw = mb // 2
+        no = self.nout
+        xin = _new((B, 2, mb, Wd), x)
+        copy_view(x[:, :, :mb], xin)
+        lo, hi = _new((B, 2, bw, Wd), x), _new((B, 2, mb - bw, Wd), x)
+        copy_view(x[:, :, :bw], lo)
+        copy_view(x[:, :, bw:mb], hi)
+        l1 = self._cba(self._base51(lo, "stg1_low_band_net.0"), "stg1_low_band_net.1")  # (B, no/4, bw, W)
+        h1 = self._base51(hi, "stg1_high_band_net")
+        c4 = no // 4
+        l2_in, h2_in = _new((B, 2 + c4, bw, Wd), x), _new((B, 2 + c4, mb - bw, Wd), x)
+        copy_view(lo, l2_in[:, :2]); copy_view(l1, l2_in[:, 2:])
+        copy_view(hi, h2_in[:, :2]); copy_view(h1, h2_in[:, 2:])
+        l2 = self._cba(self._base51(l2_in, "stg2_low_band_net.0"), "stg2_low_band_net.1")  # (B, no/2, bw, W)
+        h2 = self._base51(h2_in, "stg2_high_band_net")
+        c2 = no // 2
+        f3_in = _new((B, 2 + c4 + c2, mb, Wd), x)  # cat([x, aux1, aux2], 1) with aux_i = cat([l_i, h_i], 2)
+        copy_view(xin, f3_in[:, :2])
+        copy_view(l1, f3_in[:, 2 : 2 + c4, :bw]); copy_view(h1, f3_in[:, 2 : 2 + c4, bw:])
+        copy_view(l2, f3_in[:, 2 + c4 :, :bw]); copy_view(h2, f3_in[:, 2 + c4 :, bw:])
+        f3 = self._base51(f3_in, "stg3_full_band_net")
+        m = conv2d(f3, self.W["out.w"], None, 2, (1, 1), act=ACT_SIGMOID)
+        mask = _new((B, 2, self.output_bin, Wd), x)
+        copy_view(m, mask[:, :, :mb])
+        copy_view(m[:, :, mb - 1 : mb].expand(B, 2, self.output_bin - mb, Wd), mask[:, :, mb:])
+        return mask
+
+
 class VREngine:
     """The VRSeparator hot path between reading the file and final_process, device resident."""
 
     def __init__(self, net: VRNet, param: dict, window_size=512, aggression=5, primary_stem="Instrumental", batch_size=1):
         self.net, self.p = net, param
+        self.is_51 = isinstance(net, VRNet51)  # is_v51_model: filter masks instead of the running-gain filters, per-band convert_channels
         self.window_size, self.batch_size = int(window_size), max(1, int(batch_size))
         self.aggression, self.primary_stem = int(aggression), primary_stem
         self.device = net.device
@@ -226,7 +365,9 @@ class VREngine:
         # pre-filter of combine_spectrograms (spec_utils.py:266-277) as a per-bin gain
         g = np.ones(p["bins"] + 1, np.float64)
         if p["pre_filter_start"] > 0:
-            if self.n_bands == 1:
+            if self.is_51:
+                g = lp_filter_mask(p["bins"] + 1, p["pre_filter_start"], p["pre_filter_stop"])
+            elif self.n_bands == 1:
                 g = lp_gain(p["bins"] + 1, p["pre_filter_start"], p["pre_filter_stop"])
             else:
                 gp = 1.0
@@ -240,13 +381,14 @@ class VREngine:
             bp = p["band"][d]
             nb = bp["n_fft"] // 2 + 1
             g = np.ones(nb, np.float64)
+            hp_f, lp_f = (hp_filter_mask, lp_filter_mask) if self.is_51 else (hp_gain, lp_gain)
             if d == self.n_bands:
                 if bp.get("hpf_start", -1) > 0:
-                    g = hp_gain(nb, bp["hpf_start"], bp["hpf_stop"] - 1)
+                    g = hp_f(nb, bp["hpf_start"], bp["hpf_stop"] - 1)
             elif d == 1:
-                g = lp_gain(nb, bp["lpf_start"], bp["lpf_stop"])
+                g = lp_f(nb, bp["lpf_start"], bp["lpf_stop"])
             else:
-                g = hp_gain(nb, bp["hpf_start"], bp["hpf_stop"] - 1) * lp_gain(nb, bp["lpf_start"], bp["lpf_stop"])
+                g = hp_f(nb, bp["hpf_start"], bp["hpf_stop"] - 1) * lp_f(nb, bp["lpf_start"], bp["lpf_stop"])
             self.syn_gain[d] = torch.from_numpy(g.astype(np.float32)).to(self.device)
 
     # ---- resampling
@@ -269,7 +411,9 @@ class VREngine:
     def _wave_to_spec(self, wave: torch.Tensor, d: int) -> torch.Tensor:
         """wave_to_spectrogram (spec_utils.py:282-312): (2, n) -> planes (4, n_fft/2+1, 1 + n//hop)."""
         p, bp = self.p, self.p["band"][d]
-        if p.get("mid_side"):
+        if self.is_51:
+            pass  # wave_to_spectrogram(is_v51_model=True): plain L/R transform, convert_channels afterwards
+        elif p.get("mid_side"):
             w2 = _new(wave.shape, wave)
             ew(wave[0], wave[1], w2[0], 0.5, 0.5)
             ew(wave[0], wave[1], w2[1], 1.0, -1.0)
@@ -285,6 +429,14 @@ class VREngine:
         spec = _new((4, n_fft // 2 + 1, frames), wave)
         check(lib.b200sep_stft_forward_ex(self.plans[d].handle, _ptr(wave), 2 * n, n, 0, 1, n, frames, n_fft // 2, 1.0, n_fft // 2 + 1, 0, LAYOUT_CFT, 1, _ptr(spec),
                                           _stream()), "stft_forward_ex")
+        cc = bp.get("convert_channels") if self.is_51 else None
+        if cc in ("mid_side_c", "mid_side", "stereo_n"):  # convert_channels (spec_utils.py:232-247): a real 2x2 mix of the L / R spectrograms
+            (a, b), (c, e) = {"mid_side_c": ((1.0, 0.25), (-0.25, 1.0)), "mid_side": ((0.5, 0.5), (1.0, -1.0)), "stereo_n": ((1 / 0.9375, 0.25 / 0.9375), (0.25 / 0.9375, 1 / 0.9375))}[cc]
+            mixed = _new(spec.shape, spec)
+            L, R = spec[0:2], spec[2:4]  # (re, im) planes of the two channels
+            ew(L, R, mixed[0:2], a, b)
+            ew(L, R, mixed[2:4], c, e)
+            spec = mixed
         return spec
 
     def loading_mix(self, wave: torch.Tensor) -> torch.Tensor:
@@ -375,6 +527,15 @@ class VREngine:
         work = _new((lib.b200sep_stft_inverse_work_floats(self.plans[d].handle, 1, frames, nb, LAYOUT_CFT),), s)
         check(lib.b200sep_stft_inverse_ex(self.plans[d].handle, _ptr(s), 1, frames, nb, LAYOUT_CFT, out_len, bp["n_fft"] // 2, 0, 1.0, _ptr(wave), _ptr(work), _stream()),
               "stft_inverse_ex")
+        if self.is_51:
+            cc = bp.get("convert_channels")
+            if cc in ("mid_side_c", "mid_side", "stereo_n"):  # spectrogram_to_wave(is_v51_model=True) (spec_utils.py:322-330)
+                (a, b), (c, e) = {"mid_side_c": ((1 / 1.0625, -1 / 4.25), (1 / 4.25, 1 / 1.0625)), "mid_side": ((1.0, 0.5), (1.0, -0.5)), "stereo_n": ((1.0, -0.25), (-0.25, 1.0))}[cc]
+                w2 = _new(wave.shape, wave)
+                ew(wave[0], wave[1], w2[0], a, b)
+                ew(wave[0], wave[1], w2[1], c, e)
+                return w2
+            return wave
         if p.get("mid_side"):
             w2 = _new(wave.shape, wave)
             ew(wave[0], wave[1], w2[0], 1.0, 0.5)

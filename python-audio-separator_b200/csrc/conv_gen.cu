@@ -3,6 +3,8 @@
 // Register-tiled implicit GEMM on CUDA cores (block = 128 w x 2 h x 48 output channels, thread = 4 w x 12 channels,
 // input channels staged 8 at a time through shared memory) -- the same scheme as conv2d_simt_kernel, generalised.
 // Exact fp32 semantics; the tensor-core ("pair") path covers the shapes in umma_ops.cu.
+#include <algorithm>
+
 #include "common.cuh"
 #include "tc_f32.cuh"
 
@@ -143,6 +145,33 @@ __global__ void __launch_bounds__(GNT) conv_gen_kernel(ConvGenParams p) {
   }
 }
 
+// Any geometry (arbitrary kernel, strides, dilations along H and W): one thread per output element.  Only reached for shapes the tiled
+// kernels do not cover AND that are too small for the tensor-core route (e.g. the dilated ASPP convolutions of VR 5.1 on a tiny feature map).
+__global__ void conv_direct_kernel(ConvGenParams p, int KH, int KW, int SH, int SW, int DH, int DW, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int wo = (int)(i % p.Wo);
+    const int ho = (int)((i / p.Wo) % p.Ho);
+    const int co = (int)((i / ((int64_t)p.Wo * p.Ho)) % p.Cout);
+    const int b = (int)(i / ((int64_t)p.Wo * p.Ho * p.Cout));
+    float acc = 0.f;
+    for (int ci = 0; ci < p.Cin; ++ci)
+      for (int kh = 0; kh < KH; ++kh) {
+        const int hi = ho * SH - p.PH + kh * DH;
+        if (hi < 0 || hi >= p.H) continue;
+        for (int kw = 0; kw < KW; ++kw) {
+          const int wi = wo * SW - p.PW + kw * DW;
+          if (wi < 0 || wi >= p.W) continue;
+          acc = fmaf(__ldg(&p.x[(((int64_t)b * p.Cin + ci) * p.H + hi) * p.W + wi]), __ldg(&p.w[((int64_t)ci * KH * KW + kh * KW + kw) * p.CoutPad + co]), acc);
+        }
+      }
+    float v = acc + (p.bias ? __ldg(&p.bias[co]) : 0.f);
+    if (p.add && p.add_before_act) v += __ldg(&p.add[i]);
+    v = gen_act(v, p.act);
+    if (p.add && !p.add_before_act) v += __ldg(&p.add[i]);
+    p.y[(((int64_t)b * p.OutCT + p.OutCOff + co) * p.Ho + ho) * p.Wo + wo] = v;
+  }
+}
+
 template <int KH, int KW, int SH, int SW, int DW>
 static int launch_gen(const ConvGenParams& p, cudaStream_t st) {
   using G = GenGeom<KH, KW, SH, SW, DW>;
@@ -164,7 +193,7 @@ static int launch_gen(const ConvGenParams& p, cudaStream_t st) {
 using namespace b200sep;
 
 extern "C" int b200sep_conv2d_f32(const float* x, const float* w_blocked, const float* bias, const float* add, float* y, int B, int Cin, int H, int W, int Cout,
-                                  int Ho, int Wo, int KH, int KW, int SH, int SW, int PH, int PW, int DW, int act, int add_before_act, int up_axis, int up,
+                                  int Ho, int Wo, int KH, int KW, int SH, int SW, int PH, int PW, int DH, int DW, int act, int add_before_act, int up_axis, int up,
                                   int trim, int out_len, int out_c_total, int out_c_off, const void* w_packed, void* stream) {
   B2_CHECK_ARG(x && w_blocked && y && B >= 1 && Cin >= 1 && Cout >= 1 && Ho >= 1 && Wo >= 1, "conv2d_f32: bad argument");
   B2_CHECK_ARG(out_c_total == 0 || (up_axis == 0 && out_c_off >= 0 && out_c_off + Cout <= out_c_total), "conv2d_f32: bad output channel slice [%d, %d) of %d",
@@ -178,10 +207,10 @@ extern "C" int b200sep_conv2d_f32(const float* x, const float* w_blocked, const 
   B2_CHECK_ARG(up_axis == 0 || (up >= 1 && Cout % up == 0), "conv2d_f32: transposed mode needs Cout divisible by the up factor");
   cudaStream_t st = (cudaStream_t)stream;
   if (up_axis == 0 && tc_enabled() && tc_conv_usable(Cin, Cout, KH, KW, Ho, Wo, B))
-    return tc_conv2d_f32(x, w_blocked, bias, add, y, B, Cin, H, W, Cout, p.CoutPad, Ho, Wo, KH, KW, SH, SW, PH, PW, DW, act, add_before_act, out_c_total, out_c_off, w_packed,
+    return tc_conv2d_f32(x, w_blocked, bias, add, y, B, Cin, H, W, Cout, p.CoutPad, Ho, Wo, KH, KW, SH, SW, PH, PW, DH, DW, act, add_before_act, out_c_total, out_c_off, w_packed,
                          st);
 #define B2_CONV_CASE(kh, kw, sh, sw, dw) \
-  if (KH == kh && KW == kw && SH == sh && SW == sw && DW == dw) return launch_gen<kh, kw, sh, sw, dw>(p, st);
+  if (DH == 1 && KH == kh && KW == kw && SH == sh && SW == sw && DW == dw) return launch_gen<kh, kw, sh, sw, dw>(p, st);
   B2_CONV_CASE(1, 1, 1, 1, 1)
   B2_CONV_CASE(3, 3, 1, 1, 1)
   B2_CONV_CASE(3, 3, 2, 2, 1)
@@ -192,6 +221,10 @@ extern "C" int b200sep_conv2d_f32(const float* x, const float* w_blocked, const 
   B2_CONV_CASE(2, 1, 1, 1, 1)
   B2_CONV_CASE(1, 2, 1, 1, 1)
 #undef B2_CONV_CASE
-  set_error("conv2d_f32: unsupported geometry kernel %dx%d stride %dx%d dilation_w %d", KH, KW, SH, SW, DW);
-  return B200SEP_ERR_ARG;
+  B2_CHECK_ARG(up_axis == 0 && KH >= 1 && KW >= 1 && SH >= 1 && SW >= 1 && DH >= 1 && DW >= 1, "conv2d_f32: unsupported geometry kernel %dx%d stride %dx%d dilation %dx%d%s", KH, KW,
+               SH, SW, DH, DW, up_axis ? " (transposed)" : "");
+  const int64_t total = (int64_t)B * Cout * Ho * Wo;
+  conv_direct_kernel<<<(int)std::min<int64_t>(cdiv(total, 256), kNumSMs * 16), 256, 0, st>>>(p, KH, KW, SH, SW, DH, DW, total);
+  B2_LAUNCHED();
+  return B200SEP_OK;
 }

@@ -47,7 +47,7 @@ struct TcParams {
   uint32_t a_bytes, b_bytes, stage_bytes;
   int a_vec, b_vec;  // 16-byte aligned K-major sources: float4 loads
   // convolution geometry (mode 1): x (batch, Cin, H, W), output pixels M = Ho*Wo, K = Cin*KH*KW ordered (ci, kh, kw)
-  int mode, Cin, Cin8, H, W, Wo, KH, KW, SH, SW, PH, PW, DW;
+  int mode, Cin, Cin8, H, W, Wo, KH, KW, SH, SW, PH, PW, DH, DW;
   // epilogue: v = acc*alpha + bias_n[n] + bias_m[m]; (+ add before act); act; (+ add after act | res + res_scale[n]*v);
   // out[z*o_sz + m*o_sm + n*o_sn];  res / add indexed  res[z*r_sz + m*r_sm + n*r_sn]
   float* out;
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f32_kernel(const TcParams p) {
             const int kg = k0 + c * 8;
             const int tap = kg / p.Cin8, ci0 = kg - tap * p.Cin8;
             const int kh = tap / p.KW, kw = tap - kh * p.KW;
-            const int hi = hi0 + kh, wi = wi0 + kw * p.DW;
+            const int hi = hi0 + kh * p.DH, wi = wi0 + kw * p.DW;
             if (arow_ok && tap < taps && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W) {
               const float* px = xz + ((int64_t)ci0 * p.H + hi) * p.W + wi;
               if (ci0 + 8 <= p.Cin) {
@@ -553,7 +553,7 @@ int tc_gemm_f32(const float* A, const float* Bw, float* C, int M, int N, int K, 
   p.M = M; p.N = N; p.K = K; p.batch = batch;
   p.a_vec = (lda % 4 == 0) && (sA % 4 == 0) && aligned16(A);
   p.b_vec = (ldb % 4 == 0) && (sB % 4 == 0) && aligned16(Bw);
-  p.KH = p.KW = 1; p.Cin8 = 8;
+  p.KH = p.KW = 1; p.Cin8 = 8; p.DH = p.DW = 1;
   p.out = C; p.o_sz = sC; p.o_sm = ldc; p.o_sn = 1;
   p.res = res; p.r_sz = sC; p.r_sm = ldc; p.r_sn = 1;
   p.res_scale = res_scale; p.bias_n = bias_n; p.bias_m = bias_m; p.alpha = alpha; p.act = act; p.add_before_act = 0;
@@ -565,7 +565,7 @@ bool tc_conv_usable(int Cin, int Cout, int KH, int KW, int Ho, int Wo, int B) {
 }
 
 int tc_conv2d_f32(const float* x, const float* w_blocked, const float* bias, const float* add, float* y, int B, int Cin, int H, int W, int Cout, int CoutPad, int Ho,
-                  int Wo, int KH, int KW, int SH, int SW, int PH, int PW, int DW, int act, int add_before_act, int out_c_total, int out_c_off, const void* w_packed,
+                  int Wo, int KH, int KW, int SH, int SW, int PH, int PW, int DH, int DW, int act, int add_before_act, int out_c_total, int out_c_off, const void* w_packed,
                   cudaStream_t st) {
   TcParams p{};
   p.mode = 1;
@@ -574,7 +574,7 @@ int tc_conv2d_f32(const float* x, const float* w_blocked, const float* bias, con
   p.b = w_blocked; p.b_sz = 0; p.b_rs = 1; p.b_ks = CoutPad;  // [Cin][KH*KW][CoutPad]: k = (ci, tap) rows, output channel contiguous
   p.Cin8 = (Cin + 7) / 8 * 8;
   p.M = Ho * Wo; p.N = Cout; p.K = p.Cin8 * KH * KW; p.batch = B;  // K in the kernel's (tap, ci padded to 8) order
-  p.Cin = Cin; p.H = H; p.W = W; p.Wo = Wo; p.KH = KH; p.KW = KW; p.SH = SH; p.SW = SW; p.PH = PH; p.PW = PW; p.DW = DW;
+  p.Cin = Cin; p.H = H; p.W = W; p.Wo = Wo; p.KH = KH; p.KW = KW; p.SH = SH; p.SW = SW; p.PH = PH; p.PW = PW; p.DH = DH; p.DW = DW;
   const int64_t P = (int64_t)Ho * Wo;
   const int ct = out_c_total ? out_c_total : Cout;
   p.out = y + (int64_t)(out_c_total ? out_c_off : 0) * P; p.o_sz = ct * P; p.o_sm = 1; p.o_sn = P;

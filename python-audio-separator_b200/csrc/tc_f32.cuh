@@ -12,7 +12,7 @@ int tc_gemm_f32(const float* A, const float* Bw, float* C, int M, int N, int K, 
                 cudaStream_t st);
 bool tc_conv_usable(int Cin, int Cout, int KH, int KW, int Ho, int Wo, int B);
 int tc_conv2d_f32(const float* x, const float* w_blocked, const float* bias, const float* add, float* y, int B, int Cin, int H, int W, int Cout, int CoutPad, int Ho,
-                  int Wo, int KH, int KW, int SH, int SW, int PH, int PW, int DW, int act, int add_before_act, int out_c_total, int out_c_off, const void* w_packed,
+                  int Wo, int KH, int KW, int SH, int SW, int PH, int PW, int DH, int DW, int act, int add_before_act, int out_c_total, int out_c_off, const void* w_packed,
                   cudaStream_t st);
 // static B operands (weights) pre-split into the kernel's shared-memory image; K = the kernel's K (convolution: ceil8(Cin) * taps)
 int64_t tc_packed_bytes(int N, int K);

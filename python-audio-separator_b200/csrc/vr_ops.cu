@@ -151,6 +151,41 @@ __global__ void resample_poly_kernel(const float* __restrict__ x, const float* _
   }
 }
 
+// One CTA per (batch element, direction): 4*hid threads, thread j owns gate row j of W_hh (kept in shared memory, transposed so the inner
+// product reads are conflict-free); h_{t-1} and the four gate pre-activations are exchanged through shared memory, two barriers per step.
+__global__ void lstm_bidir_kernel(const float* __restrict__ xp, const float* __restrict__ whh, float* __restrict__ out, int T, int N, int hid) {
+  extern __shared__ float lsm[];
+  float* wT = lsm;                     // [hid][4*hid]: wT[k][j] = W_hh[j][k]
+  float* hbuf = wT + 4 * hid * hid;    // [hid]
+  float* gates = hbuf + hid;           // [4*hid]
+  const int n = blockIdx.x, dir = blockIdx.y, j = threadIdx.x, G = 4 * hid;
+  const float* w = whh + (int64_t)dir * G * hid;
+  for (int i = j; i < G * hid; i += G) {
+    const int row = i / hid, k = i - row * hid;
+    wT[k * G + row] = w[i];
+  }
+  if (j < hid) hbuf[j] = 0.f;
+  float c = 0.f;
+  __syncthreads();
+  const float* xpd = xp + (int64_t)dir * T * N * G;
+  for (int s = 0; s < T; ++s) {
+    const int t = dir ? T - 1 - s : s;
+    float g = __ldg(&xpd[((int64_t)t * N + n) * G + j]);
+    for (int k = 0; k < hid; ++k) g = fmaf(wT[k * G + j], hbuf[k], g);
+    gates[j] = g;
+    __syncthreads();
+    if (j < hid) {
+      const float ig = 1.f / (1.f + expf(-gates[j])), fg = 1.f / (1.f + expf(-gates[hid + j]));
+      const float gg = tanhf(gates[2 * hid + j]), og = 1.f / (1.f + expf(-gates[3 * hid + j]));
+      c = fg * c + ig * gg;
+      const float h = og * tanhf(c);
+      hbuf[j] = h;
+      out[((int64_t)t * N + n) * (2 * hid) + dir * hid + j] = h;
+    }
+    __syncthreads();
+  }
+}
+
 static inline int ew_grid(int64_t n) { return (int)std::min<int64_t>(cdiv(n, 256), kNumSMs * 16); }
 
 }  // namespace b200sep
@@ -227,6 +262,19 @@ extern "C" int b200sep_resample_poly_f32(const float* x, const float* taps, int 
                "resample_poly_f32: bad argument");
   dim3 grid((unsigned)std::min<int64_t>(cdiv(n_out, 256), kNumSMs * 8), channels);
   resample_poly_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, taps, n_taps, up, down, n_pre_remove, n_in, n_out, y);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
+extern "C" int b200sep_lstm_bidir_f32(const float* x_proj, const float* w_hh, float* out, int T, int N, int hid, void* stream) {
+  B2_CHECK_ARG(x_proj && w_hh && out && T >= 1 && N >= 1 && hid >= 1 && hid <= 96, "lstm_bidir_f32: bad argument (hid must be <= 96)");
+  const int smem = (4 * hid * hid + 5 * hid) * (int)sizeof(float);
+  static int attr = 0;
+  if (smem > attr) {
+    B2_CUDA(cudaFuncSetAttribute(lstm_bidir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = smem;
+  }
+  lstm_bidir_kernel<<<dim3(N, 2), 4 * hid, smem, (cudaStream_t)stream>>>(x_proj, w_hh, out, T, N, hid);
   B2_LAUNCHED();
   return B200SEP_OK;
 }

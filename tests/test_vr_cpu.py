@@ -65,3 +65,19 @@ def test_resampler_design_and_filters_match_scipy_and_the_oracle(lib_built):
     assert p["bins"] == ref["bins"] and p["band"][3] == ref["band"][3] and p["reverse"] is False
     with pytest.raises(FileNotFoundError):
         vr_params.load("no_such_layout", "/nonexistent")
+
+
+def test_vr51_oracle_matches_reference_golden(golden_dir):
+    z = np.load(os.path.join(golden_dir, "vr_small.npz"))
+    w = V.make_weights_51(256, 8, 16, seed=3)
+    m = V.predict_mask_51(w, 256, z["mask51_in"])
+    assert np.abs(m - z["mask51_ref"]).max() <= 5e-6
+    p51 = V.single_band_param(n_fft=256, hl=64, bins=128, pre_filter_start=120, pre_filter_stop=127)
+    p51["band"][1]["convert_channels"] = "mid_side_c"
+    cfg = V.VRConfig(param=p51, window_size=160, aggression=5, primary_stem="Vocals", offset=64, is_51=True, nout=8, nout_lstm=16)
+    wave = M.synth_music(int(z["n_samples"]), seed=int(z["wave_seed"]))
+    assert np.abs(V.loading_mix(wave, cfg) - z["X_51"]).max() <= 1e-4
+    # filter masks of the 5.1 glue: length and end points (spec_utils.py:398-407)
+    lp, hp = V.lp_filter_mask(100, 40, 60)[:, 0], V.hp_filter_mask(100, 30, 10)[:, 0]
+    assert len(lp) == 100 and lp[38] == 1 and lp[39] == 1 and lp[59] == 0 and lp[60] == 0 and 0 < lp[50] < 1
+    assert len(hp) == 100 and hp[10] == 0 and hp[11] == 0 and hp[31] == 1 and 0 < hp[20] < 1

@@ -215,3 +215,100 @@ def test_vr_separator_plugin_end_to_end(vr, tmp_path):
             got = np.frombuffer(wf.readframes(n), dtype="<i2").astype(np.int32)
         want = M.to_pcm16(ref.T.copy(), 0.9, 0.0).astype(np.int32)
         assert np.abs(got - want).max() <= 3
+
+
+# ------------------------------------------------------------------------------------------------ VR 5.1 (CascadedNet + LSTM)
+def test_lstm_and_dilated_conv_kernels(vr):
+    from audio_separator.separator.b200._lib import check, lib
+    from audio_separator.separator.b200.demucs import block_conv_weight, conv2d
+
+    g = torch.Generator().manual_seed(21)
+    T, N, nin, hid = 37, 3, 20, 12
+    lstm = torch.nn.LSTM(input_size=nin, hidden_size=hid, bidirectional=True)
+    x = torch.randn((T, N, nin), generator=g)
+    with torch.no_grad():
+        ref, _ = lstm(x)
+        xp = torch.stack([x.reshape(T * N, nin) @ lstm.weight_ih_l0.t() + lstm.bias_ih_l0 + lstm.bias_hh_l0,
+                          x.reshape(T * N, nin) @ lstm.weight_ih_l0_reverse.t() + lstm.bias_ih_l0_reverse + lstm.bias_hh_l0_reverse])
+        whh = torch.stack([lstm.weight_hh_l0, lstm.weight_hh_l0_reverse])
+    xpd, wd = xp.contiguous().cuda(), whh.contiguous().cuda()
+    out = torch.empty((T, N, 2 * hid), device="cuda")
+    check(lib.b200sep_lstm_bidir_f32(xpd.data_ptr(), wd.data_ptr(), out.data_ptr(), T, N, hid, 0))
+    torch.cuda.synchronize()
+    assert (out.cpu() - ref).abs().max() <= 2e-6
+    # dilation along both axes: tensor-core route (large) and the direct kernel (tiny)
+    for (B, cin, cout, H, W) in ((1, 16, 24, 40, 36), (2, 8, 8, 5, 11)):
+        xc = torch.randn((B, cin, H, W), generator=g)
+        wc = torch.randn((cout, cin, 3, 3), generator=g) / (cin * 9) ** 0.5
+        bc = torch.randn(cout, generator=g)
+        ref = F.relu(F.conv2d(xc.double(), wc.double(), bc.double(), padding=(8, 4), dilation=(8, 4)))
+        got = conv2d(xc.cuda(), dev(block_conv_weight(wc.numpy())), bc.cuda(), cout, (3, 3), p=(8, 4), dw=4, dh=8, act=1).cpu()
+        assert got.shape == ref.shape and (got.double() - ref).abs().max() <= 3e-5 * max(1.0, ref.abs().max())
+
+
+def test_vr51_predict_mask_and_path_vs_reference_golden(vr, gold):
+    w = V.make_weights_51(256, 8, 16, seed=3)
+    net = vr.VRNet51(256, 8, 16, w)
+    m = net.predict_mask(dev(gold["mask51_in"])).cpu().numpy()
+    assert m.shape == gold["mask51_ref"].shape and np.abs(m - gold["mask51_ref"]).max() <= 1e-4, np.abs(m - gold["mask51_ref"]).max()
+    p51 = V.single_band_param(n_fft=256, hl=64, bins=128, pre_filter_start=120, pre_filter_stop=127)
+    p51["band"][1]["convert_channels"] = "mid_side_c"
+    eng = vr.VREngine(net, p51, window_size=160, aggression=5, primary_stem="Vocals", batch_size=3)
+    wave = M.synth_music(int(gold["n_samples"]), seed=int(gold["wave_seed"]))
+    X = eng.loading_mix(dev(wave)).cpu().numpy()
+    assert np.abs(cplx(X) - gold["X_51"]).max() <= 1e-4
+    prim, sec = eng.separate(wave)
+    assert prim.shape == gold["prim_51"].shape
+    assert np.abs(prim - gold["prim_51"]).max() <= 1e-4 and np.abs(sec - gold["sec_51"]).max() <= 1e-4
+    # multi-band analysis / synthesis glue of a 5.1 model (filter masks, stereo_n on the top band)
+    p4 = V.four_band_v2_param()
+    p4["band"][4]["convert_channels"] = "stereo_n"
+    w4 = V.make_weights_51(1344, 8, 16, seed=4)
+    eng4 = vr.VREngine(vr.VRNet51(1344, 8, 16, w4), p4, window_size=160, batch_size=1)
+    wave4 = M.synth_music(int(gold["n_samples4"]), seed=int(gold["wave4_seed"]))
+    X4 = eng4.loading_mix(dev(wave4)).cpu().numpy()
+    assert np.abs(cplx(X4) - gold["X_4band_51"]).max() <= 1e-4 * max(1.0, np.abs(gold["X_4band_51"]).max())
+    w_out = eng4.spec_to_wav(dev(planes(gold["X_4band_51"]))).cpu().numpy()
+    assert w_out.shape == gold["wave_4band_51_standin"].shape and np.abs(w_out - gold["wave_4band_51_standin"]).max() <= 1e-4
+
+
+def test_vr51_full_size_patch_vs_oracle(vr):
+    """A released VR 5.1 geometry: nout 48 / nout_lstm 128 on a 4band_v3 patch (2, 673, 512)."""
+    w = V.make_weights_51(1344, 48, 128, seed=12)
+    x = np.abs(np.random.default_rng(13).standard_normal((1, 2, 673, 512))).astype(np.float32)
+    x /= x.max()
+    ref = V.predict_mask_51(w, 1344, x)
+    got = vr.VRNet51(1344, 48, 128, w).predict_mask(dev(x)).cpu().numpy()
+    assert got.shape == ref.shape == (1, 2, 673, 384)
+    err = np.abs(got - ref)
+    assert err.max() <= 1e-3 and err.mean() <= 2e-4, (err.max(), err.mean())
+
+
+def test_vr51_separator_plugin_end_to_end(vr, tmp_path):
+    import json
+    import wave as wavmod
+
+    from audio_separator.separator import Separator
+
+    w = V.make_weights_51(256, 8, 16, seed=5)
+    np.savez(tmp_path / "tiny-vr51.npz", **w)
+    (tmp_path / "tiny-vr51.json").write_text('{"vr_model_param": "tiny_1band_51", "primary_stem": "Vocals", "nout": 8, "nout_lstm": 16}')
+    p = V.single_band_param(n_fft=256, hl=64, bins=128, pre_filter_start=120, pre_filter_stop=127)
+    (tmp_path / "tiny_1band_51.json").write_text(json.dumps({k: v for k, v in p.items() if not isinstance(v, bool)}))
+    mix = M.synth_music(30000, seed=8)
+    pcm = (mix.T * 32767).astype("<i2")
+    with wavmod.open(str(tmp_path / "song.wav"), "wb") as wf:
+        wf.setnchannels(2); wf.setsampwidth(2); wf.setframerate(44100); wf.writeframes(pcm.tobytes())
+    sep = Separator(model_file_dir=str(tmp_path), output_dir=str(tmp_path / "out"), vr_params={"window_size": 160, "batch_size": 4, "aggression": 5})
+    sep.load_model("tiny-vr51.npz")
+    files = sep.separate(str(tmp_path / "song.wav"))
+    assert files == ["song_(Vocals)_tiny-vr51.wav", "song_(Instrumental)_tiny-vr51.wav"]
+    loaded = pcm.astype(np.float32).T / 32768.0
+    cfg = V.VRConfig(param=p, window_size=160, aggression=5, primary_stem="Vocals", offset=64, is_51=True, nout=8, nout_lstm=16)
+    prim, sec = V.separate_arrays(loaded, cfg, lambda b: V.predict_mask_51(w, 256, b), batch_size=4)
+    for fname, ref in zip(files, (prim, sec)):
+        with wavmod.open(str(tmp_path / "out" / fname)) as wf:
+            n = wf.getnframes()
+            assert n == ref.shape[1]
+            got = np.frombuffer(wf.readframes(n), dtype="<i2").astype(np.int32)
+        assert np.abs(got - M.to_pcm16(ref.T.copy(), 0.9, 0.0).astype(np.int32)).max() <= 3
