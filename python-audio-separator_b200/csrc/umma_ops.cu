@@ -71,6 +71,19 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
+// activation of a whole register group with ONE test of the (kernel-uniform) activation code: inside the unrolled column loops the per-column
+// form cost a uniform branch (and, for GELU, an inlined erf with its own selects) per output
+template <int N>
+__device__ __forceinline__ void act_group(float (&x)[N], int act) {
+  if (act == 1) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) x[j] = fmaxf(x[j], 0.f);
+  } else if (act == 2) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) x[j] = 0.5f * x[j] * (1.f + erff(x[j] * 0.70710678118654752440f));
+  }
+}
+
 __device__ __forceinline__ void split_store2(float v, bf16& hi, bf16& lo) {
   hi = __float2bfloat16_rn(v);
   lo = __float2bfloat16_rn(v - __bfloat162float(hi));
@@ -302,9 +315,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
             const size_t o = (size_t)r * p.n_total + n;
             float x[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              x[j] = apply_act(fmaf(__uint_as_float(v[j]), sc, sh), p.act);
-            }
+            for (int j = 0; j < 16; ++j) x[j] = fmaf(__uint_as_float(v[j]), sc, sh);
+            act_group(x, p.act);
             if (p.res_hi && !(p.dbg & 1)) {
               const bf16* h = reinterpret_cast<const bf16*>(rh[k]);
               const bf16* l = reinterpret_cast<const bf16*>(rl[k]);
@@ -364,14 +376,19 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
               }
               bf16* ph = p.out_hi + o0;
               bf16* pl = p.out_lo + o0;
+              float xa[CW], xb[CW];
 #pragma unroll
               for (int j = 0; j < CW; ++j) {
-                float x0 = fmaf(__uint_as_float(v0[j]), scv[j], shv[j]), x1 = fmaf(__uint_as_float(v1[j]), scv[j], shv[j]);
-                x0 = apply_act(x0, p.act);
-                x1 = apply_act(x1, p.act);
+                xa[j] = fmaf(__uint_as_float(v0[j]), scv[j], shv[j]);
+                xb[j] = fmaf(__uint_as_float(v1[j]), scv[j], shv[j]);
+              }
+              act_group(xa, p.act);
+              act_group(xb, p.act);
+#pragma unroll
+              for (int j = 0; j < CW; ++j) {
                 // bf16 -> fp32 is a 16-bit shift: low half = element 0 (dx = 0), high half = element 1 (dx = 1)
-                x0 *= __uint_as_float(sk_h[j] << 16) + __uint_as_float(sk_l[j] << 16);
-                x1 *= __uint_as_float(sk_h[j] & 0xffff0000u) + __uint_as_float(sk_l[j] & 0xffff0000u);
+                float x0 = xa[j] * (__uint_as_float(sk_h[j] << 16) + __uint_as_float(sk_l[j] << 16));
+                float x1 = xb[j] * (__uint_as_float(sk_h[j] & 0xffff0000u) + __uint_as_float(sk_l[j] & 0xffff0000u));
                 __nv_bfloat162 oh, ol;
                 split_store2(x0, oh.x, ol.x);
                 split_store2(x1, oh.y, ol.y);
@@ -412,11 +429,14 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
           if (row_ok) {
             bf16* ph = p.out_hi + base + (size_t)c0 * plane;
             bf16* pl = p.out_lo + base + (size_t)c0 * plane;
+            float y[CW];
+#pragma unroll
+            for (int j = 0; j < CW; ++j) y[j] = fmaf(x[j], sc[j], sh[j]);
+            act_group(y, p.act);
 #pragma unroll
             for (int j = 0; j < CW; ++j) {
-              const float y = apply_act(fmaf(x[j], sc[j], sh[j]), p.act);
               bf16 h, l;
-              split_store2(y, h, l);
+              split_store2(y[j], h, l);
               *ph = h;
               *pl = l;
               ph += plane;
@@ -446,24 +466,33 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
             sh[4 * j4] = h4.x; sh[4 * j4 + 1] = h4.y; sh[4 * j4 + 2] = h4.z; sh[4 * j4 + 3] = h4.w;
           }
           if (row_ok) {
-            float rv[CW], mv[CW];
+            float y[CW];
 #pragma unroll
-            for (int j = 0; j < CW; ++j) {
-              rv[j] = 0.f;
-              mv[j] = 1.f;
-              const size_t ro = rbase + (size_t)(c0 + j) * plane;
-              if (p.res_hi) rv[j] = __bfloat162float(p.res_hi[ro]) + __bfloat162float(p.res_lo[ro]);
-              if (p.mul_hi) mv[j] = __bfloat162float(p.mul_hi[ro]) + __bfloat162float(p.mul_lo[ro]);
+            for (int j = 0; j < CW; ++j) y[j] = fmaf(__uint_as_float(v[j]), sc[j], sh[j]);
+            act_group(y, p.act);
+            if (p.res_hi) {
+#pragma unroll
+              for (int j = 0; j < CW; ++j) {
+                const size_t ro = rbase + (size_t)(c0 + j) * plane;
+                y[j] += __bfloat162float(p.res_hi[ro]) + __bfloat162float(p.res_lo[ro]);
+              }
             }
+            if (p.mul_hi) {
 #pragma unroll
-            for (int j = 0; j < CW; ++j) {
-              const float y = (apply_act(fmaf(__uint_as_float(v[j]), sc[j], sh[j]), p.act) + rv[j]) * mv[j];
-              const size_t o = base + (size_t)(c0 + j) * plane;
-              if (p.out_f32) {
-                p.out_f32[o] = y;
-              } else {
+              for (int j = 0; j < CW; ++j) {
+                const size_t ro = rbase + (size_t)(c0 + j) * plane;
+                y[j] *= __bfloat162float(p.mul_hi[ro]) + __bfloat162float(p.mul_lo[ro]);
+              }
+            }
+            if (p.out_f32) {
+#pragma unroll
+              for (int j = 0; j < CW; ++j) p.out_f32[base + (size_t)(c0 + j) * plane] = y[j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < CW; ++j) {
+                const size_t o = base + (size_t)(c0 + j) * plane;
                 bf16 h, l;
-                split_store2(y, h, l);
+                split_store2(y[j], h, l);
                 p.out_hi[o] = h;
                 p.out_lo[o] = l;
               }
@@ -539,13 +568,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
             // The activation and the optional residual / multiplier are decided once per group, outside the column loops (no per-column
             // tests, no dummy "+0" / "*1" arithmetic); every load of the group is still issued before the first store.
             float y[CW];
-            if (p.act == 1) {
 #pragma unroll
-              for (int j = 0; j < CW; ++j) y[j] = fmaxf(fmaf(x[j], sc[j], sh[j]), 0.f);
-            } else {
-#pragma unroll
-              for (int j = 0; j < CW; ++j) y[j] = apply_act(fmaf(x[j], sc[j], sh[j]), p.act);
-            }
+            for (int j = 0; j < CW; ++j) y[j] = fmaf(x[j], sc[j], sh[j]);
+            act_group(y, p.act);
             if (p.res_hi) {
 #pragma unroll
               for (int j = 0; j < CW; ++j) {
