@@ -287,6 +287,12 @@ int b200sep_vr_magnitude_pad(const float* spec, float* mag, int bins, int frames
  * mask (2, bins, mask_stride); e = exp_low_* below split_bin, exp_high_* from it on, per channel. */
 int b200sep_vr_apply_mask(const float* mask, int mask_stride, const float* spec, int bins, int frames, int split_bin, float exp_low_left, float exp_high_left,
                           float exp_low_right, float exp_high_right, float* y_spec, float* v_spec, void* stream);
+/* enable_post_process (vr_separator.py:334-335): adjust_aggr in place, the per-frame minimum merge_artifacts thresholds (spec_utils.py:187), and
+ * y_mask += weight[t] * (1 - y_mask) (:213-214); the run detection between the last two is host logic on the frames-long vector */
+int b200sep_vr_mask_pow(float* mask, int mask_stride, int bins, int frames, int split_bin, float exp_low_left, float exp_high_left, float exp_low_right,
+                        float exp_high_right, void* stream);
+int b200sep_vr_frame_min(const float* mask, int mask_stride, int rows, int frames, float* out, void* stream);
+int b200sep_vr_mask_merge(float* mask, const float* frame_weight, int mask_stride, int rows, int frames, void* stream);
 /* scipy.signal.resample_poly's upfirdn (== librosa.resample(res_type="polyphase"), vr_separator.py:280):
  * y[c][k] = sum_i x[c][i] * taps[(k + n_pre_remove)*down - i*up];  taps = the zero-padded FIR scaled by `up` */
 int b200sep_resample_poly_f32(const float* x, const float* taps, int n_taps, int up, int down, int64_t n_pre_remove, int channels, int64_t n_in,

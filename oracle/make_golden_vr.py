@@ -118,6 +118,30 @@ def main():
     check("separate 1-band primary", prim_ref, prim_orc, 2e-5)
     check("separate 1-band secondary", sec_ref, sec_orc, 2e-5)
     out.update(wave_seed=41, n_samples=20000, X_1band=X_ref.astype(np.complex64), prim_1band=prim_ref.astype(np.float32), sec_1band=sec_ref.astype(np.float32))
+    # test-time augmentation (enable_tta): second pass with the padding shifted by roi/2, averaged
+    sep.enable_tta = True
+    yt_ref, vt_ref = sep.inference_vr(X_ref.copy(), "cpu", sep.aggressiveness)
+    sep.enable_tta = False
+    yt_orc, vt_orc = V.inference_vr(X_ref.copy(), cfg1, pred, batch_size=2, enable_tta=True)
+    check("inference_vr enable_tta", yt_ref, yt_orc, 1e-4)
+    out["y_tta"] = yt_ref.astype(np.complex64)
+    # enable_post_process: spec_utils.merge_artifacts on crafted masks (runs at the start, in the middle, close together, at the end, too short)
+    su = ref_shim.ref_module("audio_separator.separator.uvr_lib_v5.spec_utils")
+    crafted = []
+    for runs, n in (([(0, 90), (200, 330), (340, 450), (700, 760)], 900), ([(100, 170), (300, 600)], 600), ([(10, 40)], 300), ([], 200), ([(0, 500)], 500)):
+        mk = (rng.uniform(0.0, 0.15, (2, 9, n))).astype(np.float32)
+        for a_, b_ in runs:
+            mk[:, :, a_:b_] = rng.uniform(0.3, 0.9, (2, 9, b_ - a_)).astype(np.float32)
+        m_ref = su.merge_artifacts(mk.copy(), thres=0.2)
+        check(f"merge_artifacts runs={runs}", m_ref, V.merge_artifacts(mk.copy(), thres=0.2), 0.0)
+        crafted.append((mk, m_ref))
+    out["pp_mask_in"], out["pp_mask_ref"] = crafted[0]
+    sep.enable_post_process, sep.post_process_threshold = True, 0.05
+    yp_ref, vp_ref = sep.inference_vr(X_ref.copy(), "cpu", sep.aggressiveness)
+    sep.enable_post_process = False
+    yp_orc, _ = V.inference_vr(X_ref.copy(), cfg1, pred, batch_size=2, post_process_threshold=0.05)
+    check("inference_vr enable_post_process (threshold 0.05)", yp_ref, yp_orc, 1e-4)
+    out["y_pp"] = yp_ref.astype(np.complex64)
     # non-accompaniment primary stem (aggressiveness flips) and a vocal-ish aggression
     cfg1v = V.VRConfig(param=p1, nn_architecture=arch, window_size=272, aggression=10, primary_stem="Vocals")
     sepv = ref_separator(cfg1v, net, wave)

@@ -389,23 +389,71 @@ def adjust_aggr(mask, is_non_accom_stem, value, split_bin, aggr_correction=None)
     return mask
 
 
-def inference_vr(X_spec: np.ndarray, cfg: VRConfig, predict, batch_size=1):
-    """VRSeparator.inference_vr (vr_separator.py:295-366; enable_tta / enable_post_process off): -> (y_spec, v_spec) complex.
+def merge_artifacts(y_mask, thres=0.01, min_range=64, fade_size=32):
+    """spec_utils.merge_artifacts (:180-223): frames whose smallest mask value exceeds `thres` for more than `min_range` consecutive frames are pushed
+    towards 1 with linear fades at the run ends (enable_post_process).  Any exception inside leaves the mask unchanged, as in the reference."""
+    mask = y_mask
+    try:
+        if min_range < fade_size * 2:
+            raise ValueError("min_range must be >= fade_size * 2")
+        idx = np.where(y_mask.min(axis=(0, 1)) > thres)[0]
+        start_idx = np.insert(idx[np.where(np.diff(idx) != 1)[0] + 1], 0, idx[0])
+        end_idx = np.append(idx[np.where(np.diff(idx) != 1)[0]], idx[-1])
+        artifact_idx = np.where(end_idx - start_idx > min_range)[0]
+        weight = np.zeros_like(y_mask)
+        if len(artifact_idx) > 0:
+            start_idx = start_idx[artifact_idx]
+            end_idx = end_idx[artifact_idx]
+            old_e = None
+            for s, e in zip(start_idx, end_idx):
+                if old_e is not None and s - old_e < fade_size:
+                    s = old_e - fade_size * 2
+                if s != 0:
+                    weight[:, :, s : s + fade_size] = np.linspace(0, 1, fade_size)
+                else:
+                    s -= fade_size
+                if e != y_mask.shape[2]:
+                    weight[:, :, e - fade_size : e] = np.linspace(1, 0, fade_size)
+                else:
+                    e += fade_size
+                weight[:, :, s + fade_size : e - fade_size] = 1
+                old_e = e
+        v_mask = 1 - y_mask
+        y_mask += weight * v_mask
+        mask = y_mask
+    except Exception:  # noqa: BLE001  (the reference prints and carries on)
+        pass
+    return mask
+
+
+def inference_vr(X_spec: np.ndarray, cfg: VRConfig, predict, batch_size=1, enable_tta=False, post_process_threshold=None):
+    """VRSeparator.inference_vr (vr_separator.py:295-366; enable_post_process off): -> (y_spec, v_spec) complex.
     predict: (B, 2, bins+1, window) float32 -> (B, 2, bins+1, window - 2*offset)."""
     X_mag, X_phase = np.abs(X_spec), np.angle(X_spec)
     n_frame = X_mag.shape[2]
     pad_l, pad_r, roi = make_padding(n_frame, cfg.window_size, cfg.offset)
-    X_pad = np.pad(X_mag, ((0, 0), (0, 0), (pad_l, pad_r)), mode="constant")
-    X_pad /= X_pad.max()
-    patches = (X_pad.shape[2] - 2 * cfg.offset) // roi
-    data = np.asarray([X_pad[:, :, i * roi : i * roi + cfg.window_size] for i in range(patches)])
-    masks = []
-    for i in range(0, patches, batch_size):
-        pred = predict(data[i : i + batch_size])
-        masks.append(np.concatenate(list(pred), axis=2))
-    mask = np.concatenate(masks, axis=2)[:, :, :n_frame]
+
+    def execute(pl, pr):  # _execute (:296-327)
+        X_pad = np.pad(X_mag, ((0, 0), (0, 0), (pl, pr)), mode="constant")
+        X_pad /= X_pad.max()
+        patches = (X_pad.shape[2] - 2 * cfg.offset) // roi
+        data = np.asarray([X_pad[:, :, i * roi : i * roi + cfg.window_size] for i in range(patches)])
+        masks = []
+        for i in range(0, patches, batch_size):
+            pred = predict(data[i : i + batch_size])
+            masks.append(np.concatenate(list(pred), axis=2))
+        return np.concatenate(masks, axis=2)
+
+    mask = execute(pad_l, pad_r)
+    if enable_tta:  # test-time augmentation: a second pass shifted by half a region of interest, averaged (:351-359)
+        mask_tta = execute(pad_l + roi // 2, pad_r + roi // 2)[:, :, roi // 2 :]
+        mask = (mask[:, :, :n_frame] + mask_tta[:, :, :n_frame]) * 0.5
+    else:
+        mask = mask[:, :, :n_frame]
     value = float(int(cfg.aggression) / 100)
     mask = adjust_aggr(mask, cfg.primary_stem in NON_ACCOM_STEMS, value, cfg.param["band"][1]["crop_stop"], cfg.param.get("aggr_correction"))
+    if post_process_threshold is not None:  # enable_post_process (:334-335)
+        mask = merge_artifacts(mask, thres=post_process_threshold)
     y = mask * X_mag * np.exp(1.0j * X_phase)
     v = (1 - mask) * X_mag * np.exp(1.0j * X_phase)
     return y, v

@@ -5,7 +5,7 @@ VRSeparator.loading_mix / inference_vr / spec_to_wav (architectures/vr_separator
 band resampling, the patch loop, the mask post-processing and the band synthesis all on the GPU.
 This file is the graph builder: device buffers + launch order.  All arithmetic is behind the C ABI (include/b200sep.h).
 
-VR 5.1 models (nets_new.CascadedNet, LSTM branch) run through VRNet51.  Not covered (raises): enable_tta / enable_post_process / high_end_process, `reverse` model
+VR 5.1 models (nets_new.CascadedNet, LSTM branch) run through VRNet51.  enable_tta and enable_post_process are supported.  Not covered (raises): high_end_process, `reverse` model
 parameters, analysis bands resampled with anything but res_type "polyphase".  The band UP-sampling of the synthesis side uses the
 same Kaiser polyphase design (the reference calls libsamplerate "sinc_fastest" there; see DESIGN.md: parity unpinned for that step).
 """
@@ -80,6 +80,40 @@ def lp_filter_mask(n_bins, start, stop):
 def hp_filter_mask(n_bins, start, stop):
     """get_hp_filter_mask (spec_utils.py:404-407): zeros up to `stop`, a linear ramp 0 -> 1 up to `start`, ones."""
     return np.concatenate([np.zeros(stop + 1), np.linspace(0, 1, 1 + start - stop), np.ones(n_bins - start - 2)])
+
+
+def merge_weights(frame_min: np.ndarray, thres: float, min_range=64, fade_size=32):
+    """The per-frame weight merge_artifacts builds (spec_utils.py:180-212): runs of more than `min_range` consecutive frames whose smallest mask value
+    exceeds `thres` get weight 1 with `fade_size`-frame linear ramps (none at the very start / end of the track; a run that starts closer than one
+    fade after the previous one is merged into it).  Returns None where the reference's code raises and leaves the mask untouched (no such frame)."""
+    if min_range < fade_size * 2:
+        return None
+    n = len(frame_min)
+    hot = np.flatnonzero(frame_min > thres)
+    if hot.size == 0:
+        return None
+    breaks = np.flatnonzero(np.diff(hot) != 1)
+    starts, ends = np.concatenate([[hot[0]], hot[breaks + 1]]), np.concatenate([hot[breaks], [hot[-1]]])
+    w = np.zeros(n, np.float32)
+    prev_end = None
+    up, down = np.linspace(0, 1, fade_size).astype(np.float32), np.linspace(1, 0, fade_size).astype(np.float32)
+    for s, e in zip(starts, ends):
+        if e - s <= min_range:
+            continue
+        s, e = int(s), int(e)
+        if prev_end is not None and s - prev_end < fade_size:
+            s = prev_end - fade_size * 2
+        if s != 0:
+            w[s : s + fade_size] = up[: max(0, min(fade_size, n - s))] if s >= 0 else w[s : s + fade_size]
+        else:
+            s -= fade_size
+        if e != n:
+            w[e - fade_size : e] = down
+        else:
+            e += fade_size
+        w[s + fade_size : e - fade_size] = 1
+        prev_end = e
+    return w
 
 
 def capacity(nn_architecture: int):
@@ -484,14 +518,10 @@ class VREngine:
             a[1] += corr["right"]
         return 1 + a[0] / 3, 1 + a[0], 1 + a[1] / 3, 1 + a[1]
 
-    def inference(self, spec: torch.Tensor):
-        """VRSeparator.inference_vr (vr_separator.py:295-366): planes (4, bins+1, frames) -> (y planes, v planes)."""
+    def _execute(self, spec, pad_l, pad_r, roi):
+        """_execute of inference_vr (vr_separator.py:296-327): zero-pad the magnitudes, normalise by the maximum, run every patch -> mask (2, bins, patches*roi)."""
         nb, n_frame = spec.shape[1], spec.shape[2]
         off = self.net.offset
-        roi = self.window_size - 2 * off
-        if roi == 0:
-            roi = self.window_size
-        pad_l, pad_r = off, roi - (n_frame % roi) + off  # make_padding (spec_utils.py:85-96)
         n_pad = pad_l + n_frame + pad_r
         mag = torch.zeros((2, nb, n_pad), dtype=torch.float32, device=self.device)
         check(lib.b200sep_vr_magnitude_pad(_ptr(spec), _ptr(mag), nb, n_frame, n_pad, pad_l, _stream()), "vr_magnitude_pad")
@@ -511,9 +541,42 @@ class VREngine:
             copy_view(src, batch)
             pred = self.net.predict_mask(batch)  # (b, 2, nb, roi)
             copy_view(pred, m4[:, :, i : i + b].permute(2, 0, 1, 3))
+        return mask
+
+    def _post_process(self, mask, n_frame, thres):
+        """merge_artifacts (spec_utils.py:180-223) on the aggressiveness-adjusted mask (2, bins, stride): the min over (channel, bin) per frame is reduced
+        on the device, the run detection works on that frames-long vector on the host, the merge runs on the device."""
+        nb, stride = mask.shape[1], mask.shape[2]
+        fm = _new((n_frame,), mask)
+        check(lib.b200sep_vr_frame_min(_ptr(mask), stride, 2 * nb, n_frame, _ptr(fm), _stream()), "vr_frame_min")
+        w = merge_weights(fm.cpu().numpy(), float(thres))
+        if w is not None:
+            wd = torch.from_numpy(w).to(self.device)
+            check(lib.b200sep_vr_mask_merge(_ptr(mask), _ptr(wd), stride, 2 * nb, n_frame, _stream()), "vr_mask_merge")
+
+    def inference(self, spec: torch.Tensor, enable_tta=False, post_process_threshold=None):
+        """VRSeparator.inference_vr (vr_separator.py:295-366): planes (4, bins+1, frames) -> (y planes, v planes)."""
+        nb, n_frame = spec.shape[1], spec.shape[2]
+        off = self.net.offset
+        roi = self.window_size - 2 * off
+        if roi == 0:
+            roi = self.window_size
+        pad_l, pad_r = off, roi - (n_frame % roi) + off  # make_padding (spec_utils.py:85-96)
+        mask = self._execute(spec, pad_l, pad_r, roi)
+        if enable_tta:  # second pass shifted by half a region of interest; (mask + mask_tta[roi/2:]) / 2 on the first n_frame columns (:351-359)
+            m2 = self._execute(spec, pad_l + roi // 2, pad_r + roi // 2, roi)
+            avg = _new((2, nb, n_frame), mask)
+            a_c, b_c = _new((2, nb, n_frame), mask), _new((2, nb, n_frame), mask)
+            copy_view(mask[None, :, :, :n_frame], a_c[None])
+            copy_view(m2[None, :, :, roi // 2 : roi // 2 + n_frame], b_c[None])
+            mask = ew(a_c, b_c, avg, 0.5, 0.5)
         y, v = _new(spec.shape, spec), _new(spec.shape, spec)
         e = self._exponents()
-        check(lib.b200sep_vr_apply_mask(_ptr(mask), patches * roi, _ptr(spec), nb, n_frame, self.p["band"][1]["crop_stop"], e[0], e[1], e[2], e[3], _ptr(y), _ptr(v),
+        if post_process_threshold is not None:  # enable_post_process: adjust_aggr first, then merge_artifacts, then the products (vr_separator.py:329-343)
+            check(lib.b200sep_vr_mask_pow(_ptr(mask), mask.shape[2], nb, n_frame, self.p["band"][1]["crop_stop"], e[0], e[1], e[2], e[3], _stream()), "vr_mask_pow")
+            self._post_process(mask, n_frame, post_process_threshold)
+            e = (1.0, 1.0, 1.0, 1.0)
+        check(lib.b200sep_vr_apply_mask(_ptr(mask), mask.shape[2], _ptr(spec), nb, n_frame, self.p["band"][1]["crop_stop"], e[0], e[1], e[2], e[3], _ptr(y), _ptr(v),
                                         _stream()), "vr_apply_mask")
         return y, v
 
@@ -573,9 +636,9 @@ class VREngine:
                 wave = self._resample(w_d, bp["sr"], p["band"][d + 1]["sr"])
         return wave
 
-    def separate(self, wave: np.ndarray):
+    def separate(self, wave: np.ndarray, enable_tta=False, post_process_threshold=None):
         """(2, N) host -> primary (2, M), secondary (2, M) host float32, M = hop_top * (frames - 1)."""
         wd = torch.from_numpy(np.ascontiguousarray(wave, dtype=np.float32)).to(self.device)
         spec = self.loading_mix(wd)
-        y, v = self.inference(spec)
+        y, v = self.inference(spec, enable_tta, post_process_threshold)
         return self.spec_to_wav(y).cpu().numpy(), self.spec_to_wav(v).cpu().numpy()

@@ -133,6 +133,36 @@ __global__ void vr_mask_kernel(const float* __restrict__ mask, int mask_stride, 
   }
 }
 
+// adjust_aggr alone (spec_utils.py:472-492), in place on the mask (2, bins, stride): needed when merge_artifacts runs between it and the products
+__global__ void vr_mask_pow_kernel(float* __restrict__ mask, int stride, int bins, int frames, int split_bin, float e_lo0, float e_hi0, float e_lo1, float e_hi1, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int t = (int)(i % frames);
+    const int64_t cb = i / frames;
+    const int c = (int)(cb / bins), bin = (int)(cb % bins);
+    const float e = (c == 0) ? (bin < split_bin ? e_lo0 : e_hi0) : (bin < split_bin ? e_lo1 : e_hi1);
+    if (e != 1.f) mask[cb * stride + t] = powf(mask[cb * stride + t], e);
+  }
+}
+
+// y_mask.min(axis=(0, 1)) of merge_artifacts (spec_utils.py:187): smallest mask value of every frame
+__global__ void vr_frame_min_kernel(const float* __restrict__ mask, int stride, int rows, int frames, float* __restrict__ out) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < frames; t += gridDim.x * blockDim.x) {
+    float m = INFINITY;
+    for (int r = 0; r < rows; ++r) m = fminf(m, __ldg(&mask[(int64_t)r * stride + t]));
+    out[t] = m;
+  }
+}
+
+// y_mask += weight * (1 - y_mask) with a per-frame weight (merge_artifacts, spec_utils.py:213-214)
+__global__ void vr_mask_merge_kernel(float* __restrict__ mask, const float* __restrict__ w, int stride, int frames, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int t = (int)(i % frames);
+    const int64_t r = i / frames;
+    const float m = mask[r * stride + t];
+    mask[r * stride + t] = m + __ldg(&w[t]) * (1.f - m);
+  }
+}
+
 // scipy.signal.resample_poly / upfirdn: y[k] = sum_i x[i] * h[(k + n_pre_remove) * down - i * up], h = the zero-padded, up-scaled
 // Kaiser FIR the host builds (see vr.py).  x (C, n_in) -> y (C, n_out); double accumulation keeps the 1e-7 agreement with scipy.
 __global__ void resample_poly_kernel(const float* __restrict__ x, const float* __restrict__ h, int n_taps, int up, int down, int64_t n_pre_remove, int64_t n_in,
@@ -275,6 +305,30 @@ extern "C" int b200sep_lstm_bidir_f32(const float* x_proj, const float* w_hh, fl
     attr = smem;
   }
   lstm_bidir_kernel<<<dim3(N, 2), 4 * hid, smem, (cudaStream_t)stream>>>(x_proj, w_hh, out, T, N, hid);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
+extern "C" int b200sep_vr_mask_pow(float* mask, int mask_stride, int bins, int frames, int split_bin, float exp_low_left, float exp_high_left, float exp_low_right,
+                                   float exp_high_right, void* stream) {
+  B2_CHECK_ARG(mask && bins >= 1 && frames >= 1 && mask_stride >= frames && split_bin >= 0, "vr_mask_pow: bad argument");
+  const int64_t n = (int64_t)2 * bins * frames;
+  vr_mask_pow_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(mask, mask_stride, bins, frames, split_bin, exp_low_left, exp_high_left, exp_low_right, exp_high_right, n);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
+extern "C" int b200sep_vr_frame_min(const float* mask, int mask_stride, int rows, int frames, float* out, void* stream) {
+  B2_CHECK_ARG(mask && out && rows >= 1 && frames >= 1 && mask_stride >= frames, "vr_frame_min: bad argument");
+  vr_frame_min_kernel<<<cdiv(frames, 128), 128, 0, (cudaStream_t)stream>>>(mask, mask_stride, rows, frames, out);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
+extern "C" int b200sep_vr_mask_merge(float* mask, const float* frame_weight, int mask_stride, int rows, int frames, void* stream) {
+  B2_CHECK_ARG(mask && frame_weight && rows >= 1 && frames >= 1 && mask_stride >= frames, "vr_mask_merge: bad argument");
+  const int64_t n = (int64_t)rows * frames;
+  vr_mask_merge_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(mask, frame_weight, mask_stride, frames, n);
   B2_LAUNCHED();
   return B200SEP_OK;
 }

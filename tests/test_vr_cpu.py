@@ -81,3 +81,30 @@ def test_vr51_oracle_matches_reference_golden(golden_dir):
     lp, hp = V.lp_filter_mask(100, 40, 60)[:, 0], V.hp_filter_mask(100, 30, 10)[:, 0]
     assert len(lp) == 100 and lp[38] == 1 and lp[39] == 1 and lp[59] == 0 and lp[60] == 0 and 0 < lp[50] < 1
     assert len(hp) == 100 and hp[10] == 0 and hp[11] == 0 and hp[31] == 1 and 0 < hp[20] < 1
+
+
+def test_post_process_run_logic_matches_the_oracle(lib_built, golden_dir):
+    """merge_artifacts: the oracle is pinned against the reference function (oracle/make_golden_vr.py); the product's host-side run detection
+    must give the same masks on random run layouts (runs at the start / end, runs closer than one fade, runs that are too short, no run at all)."""
+    from audio_separator.separator.b200 import vr
+
+    z = np.load(os.path.join(golden_dir, "vr_small.npz"))
+    assert np.array_equal(V.merge_artifacts(z["pp_mask_in"].copy(), thres=0.2), z["pp_mask_ref"])
+    rng = np.random.default_rng(0)
+    for _ in range(120):
+        n = int(rng.integers(100, 1200))
+        mk = rng.uniform(0, 0.15, (2, 5, n)).astype(np.float32)
+        pos = 0
+        while pos < n - 5:
+            pos += int(rng.integers(1, 150))
+            if rng.random() < 0.15:
+                pos = 0
+            L = int(rng.integers(5, 300))
+            mk[:, :, pos : pos + L] = 0.7
+            pos += L
+        if rng.random() < 0.2:
+            mk[:, :, -int(rng.integers(70, 200)) :] = 0.8
+        ref = V.merge_artifacts(mk.copy(), thres=0.2)
+        w = vr.merge_weights(mk.min(axis=(0, 1)), 0.2)
+        got = mk.copy() if w is None else mk + w[None, None, :] * (1 - mk)
+        assert np.array_equal(got, ref)

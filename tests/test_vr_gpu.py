@@ -131,6 +131,15 @@ def test_single_band_path_vs_reference_golden(vr, gold):
     prim, sec = eng.separate(wave)
     assert prim.shape == gold["prim_1band"].shape  # hop * (frames - 1) samples: not the input length
     assert np.abs(prim - gold["prim_1band"]).max() <= 1e-4 and np.abs(sec - gold["sec_1band"]).max() <= 1e-4
+    # test-time augmentation: two passes, the second shifted by roi/2
+    yt, vt = eng.inference(dev(planes(gold["X_1band"])), enable_tta=True)
+    assert np.abs(cplx(yt.cpu().numpy()) - gold["y_tta"]).max() <= 2e-4 * np.abs(gold["y_tta"]).max()
+    # enable_post_process: merge_artifacts between adjust_aggr and the products; and the crafted-mask case of the golden file
+    yp, _ = eng.inference(dev(planes(gold["X_1band"])), post_process_threshold=0.05)
+    assert np.abs(cplx(yp.cpu().numpy()) - gold["y_pp"]).max() <= 2e-4 * np.abs(gold["y_pp"]).max()
+    mk = dev(gold["pp_mask_in"])
+    eng._post_process(mk, mk.shape[2], 0.2)
+    assert np.abs(mk.cpu().numpy() - gold["pp_mask_ref"]).max() <= 1e-6
     # vocal primary stem with aggression 10: exponents flip to 1 - aggr
     eng_v, _, _ = _engine_1band(vr, aggression=10, primary_stem="Vocals", batch_size=2)
     y, v = eng_v.inference(dev(planes(gold["X_1band"])))
