@@ -293,6 +293,11 @@ int b200sep_vr_mask_pow(float* mask, int mask_stride, int bins, int frames, int 
                         float exp_high_right, void* stream);
 int b200sep_vr_frame_min(const float* mask, int mask_stride, int rows, int frames, float* out, void* stream);
 int b200sep_vr_mask_merge(float* mask, const float* frame_weight, int mask_stride, int rows, int frames, void* stream);
+/* high_end_process (vr_separator.py:368-372; spec_utils.mirroring :458-463 + cmb_spectrogram_to_wave :354-356): bins [max_bin-h, max_bin) of the top band's
+ * un-cropped spectrogram (4, band_bins, frames) <- the kept input high end (4, high_rows, high_frames) limited in magnitude by the flipped combined-spectrogram
+ * bins [pre_filter_start-10-h, pre_filter_start-10) */
+int b200sep_vr_mirror_high_end(const float* spec_m, int bins, const float* high_end, int high_rows, int high_frames, float* band_spec, int band_bins, int frames,
+                               int h, int max_bin, int pre_filter_start, void* stream);
 /* scipy.signal.resample_poly's upfirdn (== librosa.resample(res_type="polyphase"), vr_separator.py:280):
  * y[c][k] = sum_i x[c][i] * taps[(k + n_pre_remove)*down - i*up];  taps = the zero-padded FIR scaled by `up` */
 int b200sep_resample_poly_f32(const float* x, const float* taps, int n_taps, int up, int down, int64_t n_pre_remove, int channels, int64_t n_in,

@@ -165,6 +165,18 @@ def main():
     prim4_ref = sep4.spec_to_wav(y4)
     prim4_orc = V.cmb_spectrogram_to_wave(y4o, p4)
     check("cmb_spectrogram_to_wave 4band (glue; up-sampler = stand-in on both sides)", prim4_ref, prim4_orc, 5e-5)
+    # high_end_process: the top band's bins above its crop are kept at load time and mirrored back in at synthesis time (vr_separator.py:287-289, :368-372)
+    sep4.high_end_process = True
+    X4h = sep4.loading_mix()
+    hh, he = V.high_end_of(wave4, cfg4)
+    assert sep4.input_high_end_h == hh
+    check("loading_mix input_high_end", sep4.input_high_end, he[:, :, : sep4.input_high_end.shape[2]], 1e-4)
+    prim4h_ref = sep4.spec_to_wav(y4)
+    he_m = V.mirroring(y4o, he[:, :, : y4o.shape[2]], p4)
+    prim4h_orc = V.cmb_spectrogram_to_wave(y4o, p4, extra_bins_h=hh, extra_bins=he_m)
+    check("spec_to_wav high_end_process (mirroring)", prim4h_ref, prim4h_orc, 5e-5)
+    sep4.high_end_process, sep4.input_high_end, sep4.input_high_end_h = False, None, None
+    out.update(y_4band=np.asarray(y4o).astype(np.complex64), prim_4band_high_end_standin=prim4h_ref.astype(np.float32))
     out.update(wave4_seed=43, n_samples4=60000, X_4band=X4_ref.astype(np.complex64), prim_4band_standin=prim4_ref.astype(np.float32))
     # ---- VR 5.1: CascadedNet (LSTM branch) + the is_v51_model glue (filter masks, convert_channels)
     nets_new = ref_shim.ref_module("audio_separator.separator.uvr_lib_v5.vr_network.nets_new")

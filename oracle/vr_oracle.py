@@ -479,8 +479,26 @@ def spectrogram_to_wave(spec, hop, param, is_51=False, band=None):  # spec_utils
     return np.stack([l, r])
 
 
-def cmb_spectrogram_to_wave(spec_m: np.ndarray, p: dict, up=upsample, is_51=False) -> np.ndarray:
-    """spec_utils.py:341-395 (no high-end bins).  `up` is the band up-sampler (see the module docstring)."""
+def high_end_of(wave: np.ndarray, cfg: "VRConfig"):
+    """The slice loading_mix keeps when high_end_process is on (vr_separator.py:287-289): the top band's own STFT bins above its crop."""
+    p = cfg.param
+    n = cfg.bands
+    bp = p["band"][n]
+    h = (bp["n_fft"] // 2 - bp["crop_stop"]) + (p["pre_filter_stop"] - p["pre_filter_start"])
+    spec = wave_to_spectrogram(np.asarray(wave, dtype=np.float32), bp["hl"], bp["n_fft"], p, cfg.is_51, n)
+    return h, spec[:, bp["n_fft"] // 2 - h : bp["n_fft"] // 2, :]
+
+
+def mirroring(spec_m, input_high_end, p):
+    """spec_utils.mirroring("mirroring", ...) (:458-463): the magnitudes just below the pre-filter, flipped, with the input's phases, where they are smaller than the input."""
+    pfs = p["pre_filter_start"]
+    mirror = np.flip(np.abs(spec_m[:, pfs - 10 - input_high_end.shape[1] : pfs - 10, :]), 1)
+    mirror = mirror * np.exp(1.0j * np.angle(input_high_end))
+    return np.where(np.abs(input_high_end) <= np.abs(mirror), input_high_end, mirror)
+
+
+def cmb_spectrogram_to_wave(spec_m: np.ndarray, p: dict, up=upsample, is_51=False, extra_bins_h=None, extra_bins=None) -> np.ndarray:
+    """spec_utils.py:341-395.  `up` is the band up-sampler (see the module docstring)."""
     def hp(s_, a, b_):
         return s_ * hp_filter_mask(s_.shape[1], a, b_) if is_51 else fft_hp_filter(s_, a, b_)
 
@@ -497,6 +515,9 @@ def cmb_spectrogram_to_wave(spec_m: np.ndarray, p: dict, up=upsample, is_51=Fals
         s[:, bp["crop_start"] : bp["crop_stop"], :] = spec_m[:, off : off + h, :]
         off += h
         if d == n:
+            if extra_bins_h:  # high_end_process (spec_utils.py:354-356)
+                max_bin = bp["n_fft"] // 2
+                s[:, max_bin - extra_bins_h : max_bin, :] = extra_bins[:, :extra_bins_h, :]
             if bp["hpf_start"] > 0:
                 s = hp(s, bp["hpf_start"], bp["hpf_stop"] - 1)
             w_d = spectrogram_to_wave(s, bp["hl"], p, is_51, d)

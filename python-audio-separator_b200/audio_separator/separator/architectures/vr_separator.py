@@ -33,9 +33,6 @@ class VRSeparator(CommonSeparator):
         self.high_end_process = arch_config.get("high_end_process", False)
         self.aggression_setting = int(arch_config.get("aggression", 5))
         self.aggression = float(self.aggression_setting / 100)
-        for flag in ("high_end_process",):
-            if getattr(self, flag):
-                raise NotImplementedError(f"{flag} is not part of the accelerated VR path")
         if not torch.cuda.is_available():
             raise RuntimeError("VRSeparator (B200 build) needs a CUDA device: there is no CPU path in this package")
         self.torch_device = torch.device("cuda", torch.cuda.current_device())
@@ -67,7 +64,8 @@ class VRSeparator(CommonSeparator):
         self.audio_file_base = os.path.splitext(os.path.basename(audio_file_path))[0]
         wave = self.prepare_mix(audio_file_path)  # librosa.load(mono=False, sr=44100) of a 44.1 kHz file (vr_separator.py:271)
         primary, secondary = self.engine.separate(np.asarray(wave, dtype=np.float32), enable_tta=bool(self.enable_tta),
-                                                    post_process_threshold=self.post_process_threshold if self.enable_post_process else None)
+                                                    post_process_threshold=self.post_process_threshold if self.enable_post_process else None,
+                                                    high_end_process=bool(self.high_end_process))
         self.primary_source, self.secondary_source = primary.T, secondary.T
         output_files = []
         if self.output_single_stem and self.output_single_stem.lower() not in (self.primary_stem_name.lower(), self.secondary_stem_name.lower()):

@@ -85,6 +85,7 @@ _SIGS = {
     "b200sep_vr_mask_pow": (i32, [vp, i32, i32, i32, i32, f32, f32, f32, f32, vp]),
     "b200sep_vr_frame_min": (i32, [vp, i32, i32, i32, vp, vp]),
     "b200sep_vr_mask_merge": (i32, [vp, vp, i32, i32, i32, vp]),
+    "b200sep_vr_mirror_high_end": (i32, [vp, i32, vp, i32, i32, vp, i32, i32, i32, i32, i32, vp]),
     "b200sep_resample_poly_f32": (i32, [vp, vp, i32, i32, i32, i64, i32, i64, i64, vp, vp]),
     "b200sep_rmsnorm_f32": (i32, [vp, vp, vp, i64, i32, i64, i64, vp]),
     "b200sep_rope_split_heads_f32": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),

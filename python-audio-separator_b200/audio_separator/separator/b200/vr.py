@@ -5,7 +5,7 @@ VRSeparator.loading_mix / inference_vr / spec_to_wav (architectures/vr_separator
 band resampling, the patch loop, the mask post-processing and the band synthesis all on the GPU.
 This file is the graph builder: device buffers + launch order.  All arithmetic is behind the C ABI (include/b200sep.h).
 
-VR 5.1 models (nets_new.CascadedNet, LSTM branch) run through VRNet51.  enable_tta and enable_post_process are supported.  Not covered (raises): high_end_process, `reverse` model
+VR 5.1 models (nets_new.CascadedNet, LSTM branch) run through VRNet51.  enable_tta, enable_post_process and high_end_process are supported.  Not covered (raises): `reverse` model
 parameters, analysis bands resampled with anything but res_type "polyphase".  The band UP-sampling of the synthesis side uses the
 same Kaiser polyphase design (the reference calls libsamplerate "sinc_fastest" there; see DESIGN.md: parity unpinned for that step).
 """
@@ -473,7 +473,7 @@ class VREngine:
             spec = mixed
         return spec
 
-    def loading_mix(self, wave: torch.Tensor) -> torch.Tensor:
+    def loading_mix(self, wave: torch.Tensor, keep_high_end=False) -> torch.Tensor:
         """VRSeparator.loading_mix + combine_spectrograms: (2, N) at the top band's rate -> planes (4, bins + 1, frames)."""
         p, n = self.p, self.n_bands
         if p["band"][n]["sr"] != p["sr"]:
@@ -489,6 +489,11 @@ class VREngine:
                     raise NotImplementedError(f"band {d} is resampled with res_type={bp.get('res_type')}: only polyphase is covered")
                 waves[d] = self._resample(waves[d + 1], up_sr, bp["sr"])
             specs[d] = self._wave_to_spec(waves[d], d)
+        if keep_high_end:  # high_end_process (vr_separator.py:287-289): the top band's bins above its crop, as loaded
+            bp = p["band"][n]
+            self.high_end_h = (bp["n_fft"] // 2 - bp["crop_stop"]) + (p["pre_filter_stop"] - p["pre_filter_start"])
+            mb = bp["n_fft"] // 2
+            self.high_end = specs[n][:, mb - self.high_end_h : mb, :].contiguous()
         l = min(s.shape[2] for s in specs.values())
         out = torch.zeros((4, p["bins"] + 1, l), dtype=torch.float32, device=self.device)
         off = 0
@@ -611,8 +616,9 @@ class VREngine:
             return w2
         return wave
 
-    def spec_to_wav(self, spec_m: torch.Tensor) -> torch.Tensor:
-        """cmb_spectrogram_to_wave (spec_utils.py:341-395): planes (4, bins+1, frames) -> (2, hop_top*(frames-1))."""
+    def spec_to_wav(self, spec_m: torch.Tensor, high_end=False) -> torch.Tensor:
+        """cmb_spectrogram_to_wave (spec_utils.py:341-395): planes (4, bins+1, frames) -> (2, hop_top*(frames-1)).  high_end: mirror the kept input high end
+        into the top band (VRSeparator.spec_to_wav with high_end_process, vr_separator.py:368-372)."""
         p, n = self.p, self.n_bands
         frames = spec_m.shape[2]
         off = 0
@@ -624,6 +630,10 @@ class VREngine:
             h = bp["crop_stop"] - bp["crop_start"]
             copy_view(spec_m[None, :, off : off + h], s[None, :, bp["crop_start"] : bp["crop_stop"]])
             off += h
+            if d == n and high_end:
+                he = self.high_end
+                check(lib.b200sep_vr_mirror_high_end(_ptr(spec_m), spec_m.shape[1], _ptr(he), he.shape[1], he.shape[2], _ptr(s), nb, frames, self.high_end_h, bp["n_fft"] // 2,
+                                                     p["pre_filter_start"], _stream()), "vr_mirror_high_end")
             filtered = (d == n and bp.get("hpf_start", -1) > 0) or d < n
             if filtered:
                 check(lib.b200sep_bin_gain_f32(_ptr(s), _ptr(self.syn_gain[d]), 4, nb, frames, _stream()), "bin_gain_f32")
@@ -636,9 +646,9 @@ class VREngine:
                 wave = self._resample(w_d, bp["sr"], p["band"][d + 1]["sr"])
         return wave
 
-    def separate(self, wave: np.ndarray, enable_tta=False, post_process_threshold=None):
+    def separate(self, wave: np.ndarray, enable_tta=False, post_process_threshold=None, high_end_process=False):
         """(2, N) host -> primary (2, M), secondary (2, M) host float32, M = hop_top * (frames - 1)."""
         wd = torch.from_numpy(np.ascontiguousarray(wave, dtype=np.float32)).to(self.device)
-        spec = self.loading_mix(wd)
+        spec = self.loading_mix(wd, keep_high_end=high_end_process)
         y, v = self.inference(spec, enable_tta, post_process_threshold)
-        return self.spec_to_wav(y).cpu().numpy(), self.spec_to_wav(v).cpu().numpy()
+        return self.spec_to_wav(y, high_end_process).cpu().numpy(), self.spec_to_wav(v, high_end_process).cpu().numpy()

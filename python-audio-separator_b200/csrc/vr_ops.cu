@@ -163,6 +163,31 @@ __global__ void vr_mask_merge_kernel(float* __restrict__ mask, const float* __re
   }
 }
 
+// spec_utils.mirroring("mirroring") (:458-463) written straight into the top band's un-cropped spectrogram: row i of the kept high end (bins
+// max_bin-h .. max_bin-1 of the band) takes the magnitude of combined-spectrogram bin (pre_filter_start - 11 - i) with the input's phase, where that is smaller
+__global__ void vr_mirror_kernel(const float* __restrict__ spec_m, int bins, const float* __restrict__ high, int high_rows, int high_frames, float* __restrict__ band,
+                                 int band_bins, int frames, int h, int max_bin, int pre_filter_start, int64_t n) {
+  const int64_t plane_m = (int64_t)bins * frames, plane_h = (int64_t)high_rows * high_frames, plane_b = (int64_t)band_bins * frames;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int t = (int)(idx % frames);
+    const int i = (int)((idx / frames) % h);
+    const int c = (int)(idx / ((int64_t)frames * h));
+    const int bm = pre_filter_start - 11 - i;
+    const float mr = __ldg(&spec_m[(2 * c) * plane_m + (int64_t)bm * frames + t]), mi = __ldg(&spec_m[(2 * c + 1) * plane_m + (int64_t)bm * frames + t]);
+    const float hr = __ldg(&high[(2 * c) * plane_h + (int64_t)i * high_frames + t]), hi = __ldg(&high[(2 * c + 1) * plane_h + (int64_t)i * high_frames + t]);
+    const float mag = hypotf(mr, mi), a = hypotf(hr, hi);
+    float outr = hr, outi = hi;
+    if (!(a <= mag)) {  // |input| > |mirror|: keep the input's phase, take the mirrored magnitude
+      const float sc = mag / a;
+      outr = hr * sc;
+      outi = hi * sc;
+    }
+    const int64_t o = (int64_t)(max_bin - h + i) * frames + t;
+    band[(2 * c) * plane_b + o] = outr;
+    band[(2 * c + 1) * plane_b + o] = outi;
+  }
+}
+
 // scipy.signal.resample_poly / upfirdn: y[k] = sum_i x[i] * h[(k + n_pre_remove) * down - i * up], h = the zero-padded, up-scaled
 // Kaiser FIR the host builds (see vr.py).  x (C, n_in) -> y (C, n_out); double accumulation keeps the 1e-7 agreement with scipy.
 __global__ void resample_poly_kernel(const float* __restrict__ x, const float* __restrict__ h, int n_taps, int up, int down, int64_t n_pre_remove, int64_t n_in,
@@ -329,6 +354,18 @@ extern "C" int b200sep_vr_mask_merge(float* mask, const float* frame_weight, int
   B2_CHECK_ARG(mask && frame_weight && rows >= 1 && frames >= 1 && mask_stride >= frames, "vr_mask_merge: bad argument");
   const int64_t n = (int64_t)rows * frames;
   vr_mask_merge_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(mask, frame_weight, mask_stride, frames, n);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
+extern "C" int b200sep_vr_mirror_high_end(const float* spec_m, int bins, const float* high_end, int high_rows, int high_frames, float* band_spec, int band_bins, int frames,
+                                          int h, int max_bin, int pre_filter_start, void* stream) {
+  B2_CHECK_ARG(spec_m && high_end && band_spec && bins >= 1 && frames >= 1 && h >= 1 && h <= high_rows && frames <= high_frames && max_bin <= band_bins && max_bin - h >= 0,
+               "vr_mirror_high_end: bad argument");
+  B2_CHECK_ARG(pre_filter_start - 10 - h >= 0 && pre_filter_start - 11 < bins, "vr_mirror_high_end: the mirrored bins [%d, %d) fall outside the combined spectrogram",
+               pre_filter_start - 10 - h, pre_filter_start - 10);
+  const int64_t n = (int64_t)2 * h * frames;
+  vr_mirror_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(spec_m, bins, high_end, high_rows, high_frames, band_spec, band_bins, frames, h, max_bin, pre_filter_start, n);
   B2_LAUNCHED();
   return B200SEP_OK;
 }

@@ -156,6 +156,10 @@ def test_four_band_path_vs_reference_golden_and_oracle(vr, gold):
     assert X.shape[1:] == ref.shape[1:] and np.abs(cplx(X) - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
     y, v = eng.inference(dev(planes(ref)))
     prim = eng.spec_to_wav(y).cpu().numpy()
+    # high_end_process: the input's bins above the top band's crop are mirrored back in at synthesis time
+    eng.loading_mix(dev(wave), keep_high_end=True)
+    prim_h = eng.spec_to_wav(dev(planes(gold["y_4band"])), high_end=True).cpu().numpy()
+    assert np.abs(prim_h - gold["prim_4band_high_end_standin"]).max() <= 1e-4
     # reference glue + the Kaiser polyphase stand-in for the libsamplerate up-sampling (parity unpinned for that step)
     assert prim.shape == gold["prim_4band_standin"].shape == (2, 480 * (ref.shape[2] - 1))
     assert np.abs(prim - gold["prim_4band_standin"]).max() <= 1e-4
