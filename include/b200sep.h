@@ -336,6 +336,15 @@ int b200sep_overlap_add_starts(const float* chunks, const int64_t* starts, const
 int b200sep_lstm_bidir_f32(const float* x_proj, const float* w_hh, float* out, int T, int N, int hid, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Ensembling of several models' stems (audio_separator/separator/ensembler.py:10-156, spec_utils.ensembling :583-608).
+ * ensemble_f32: x (n_models, n) -> out (n); algo 0 weighted mean (weights: device float[n_models]), 1 median, 2 / 3 the value of smallest / largest
+ * magnitude (first on ties): avg_wave, median_wave, min_wave, max_wave, and avg_fft / median_fft applied to spectrogram planes.
+ * ensemble_spec_abs: planes (n_models, 4, plane_elems) -> (4, plane_elems), per complex entry the model with the smallest / largest modulus
+ * (last_wins 0: min_fft / max_fft; 1: uvr_min_spec / uvr_max_spec).  n_models <= 16. */
+int b200sep_ensemble_f32(const float* x, int n_models, int64_t n, const float* weights, int algo, float* out, void* stream);
+int b200sep_ensemble_spec_abs(const float* planes, int n_models, int64_t plane_elems, int take_max, int last_wins, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Self-tests of the tensor-core ("bf16x3 pair") operators in isolation: fp32 device tensors in, the operator runs
  * exactly as inside the network (split into bf16 hi/lo planes -> tcgen05 kernel -> join), fp32 out.  Synchronous.
  *   gemm   : out[M][N] = act((a[M][K] @ w[N][K]^T) * scale[c] + shift[c]) (+ res),  c = (row / rows_per_channel) % channels

@@ -245,8 +245,9 @@ def stft(y: np.ndarray, n_fft: int, hop: int) -> np.ndarray:
     return np.fft.rfft(frames.astype(np.float32), axis=0).astype(np.complex64)
 
 
-def istft(spec: np.ndarray, hop: int) -> np.ndarray:
-    """librosa.istft(spec, hop_length=) defaults: n_fft from the bin count, hann, center=True, length=None -> hop*(frames-1) samples."""
+def istft(spec: np.ndarray, hop: int, length=None) -> np.ndarray:
+    """librosa.istft(spec, hop_length=, length=) defaults: n_fft from the bin count, hann, center=True; length=None -> hop*(frames-1) samples,
+    otherwise the overlap-add buffer is read from n_fft/2 for `length` samples (zero-padded past its end)."""
     n_fft = 2 * (spec.shape[0] - 1)
     n_frames = spec.shape[1]
     win = hann_periodic(n_fft)
@@ -259,6 +260,9 @@ def istft(spec: np.ndarray, hop: int) -> np.ndarray:
         wss[t * hop : t * hop + n_fft] += win * win
     nz = wss > np.finfo(np.float32).tiny
     y[nz] /= wss[nz]
+    if length is not None:
+        out = y[n_fft // 2 : n_fft // 2 + length]
+        return np.pad(out, (0, length - len(out))) if len(out) < length else out
     return y[n_fft // 2 : total - n_fft // 2]
 
 
