@@ -520,8 +520,33 @@ extern "C" int b200sep_groupnorm1_f32(const float* x, const float* gamma, const 
   return B200SEP_OK;
 }
 
+// permutations that keep the innermost dimension in place (the "b t f d <-> b f t d" swaps around the Roformer transformers) move whole
+// float4s: same index arithmetic on d3/4 "elements" of 16 bytes
+__global__ void permute4_vec_kernel(const float4* __restrict__ x, float4* __restrict__ y, int d0, int d1, int d2, int d3q, int p0, int p1, int p2, int64_t n) {
+  const int din[3] = {d0, d1, d2};
+  const int perm[3] = {p0, p1, p2};
+  const int64_t sin_[3] = {(int64_t)d1 * d2 * d3q, (int64_t)d2 * d3q, d3q};
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = o / d3q, src = o - r * d3q;
+    for (int k = 2; k >= 0; --k) {
+      const int dk = din[perm[k]];
+      src += (r % dk) * sin_[perm[k]];
+      r /= dk;
+    }
+    y[o] = x[src];
+  }
+}
+
 extern "C" int b200sep_permute4_f32(const float* x, float* y, int d0, int d1, int d2, int d3, int p0, int p1, int p2, int p3, void* stream) {
   B2_CHECK_ARG(x && y && d0 >= 1 && d1 >= 1 && d2 >= 1 && d3 >= 1, "permute4_f32: bad argument");
+  if (p3 == 3 && d3 % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 && p0 >= 0 && p0 < 3 && p1 >= 0 && p1 < 3 && p2 >= 0 && p2 < 3 &&
+      ((1 << p0) | (1 << p1) | (1 << p2)) == 7) {
+    const int64_t nq = (int64_t)d0 * d1 * d2 * (d3 / 4);
+    permute4_vec_kernel<<<(int)std::min<int64_t>(cdiv(nq, 256), kNumSMs * 16), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), d0,
+                                                                                                                 d1, d2, d3 / 4, p0, p1, p2, nq);
+    B2_LAUNCHED();
+    return B200SEP_OK;
+  }
   const int seen = (1 << p0) | (1 << p1) | (1 << p2) | (1 << p3);
   B2_CHECK_ARG(p0 >= 0 && p0 < 4 && p1 >= 0 && p1 < 4 && p2 >= 0 && p2 < 4 && p3 >= 0 && p3 < 4 && seen == 15, "permute4_f32: not a permutation");
   const int64_t n = (int64_t)d0 * d1 * d2 * d3;

@@ -161,8 +161,27 @@ extern "C" int b200sep_rope_split_heads_f32(const float* qkv, const float* freqs
   return B200SEP_OK;
 }
 
+// float4 variant (dh % 4 == 0): one thread per four consecutive d
+__global__ void gate_merge_vec_kernel(const float4* __restrict__ o, const float* __restrict__ gates, float4* __restrict__ y, int n, int H, int dhq, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int d = (int)(i % dhq);
+    const int h = (int)((i / dhq) % H);
+    const int64_t bn = i / ((int64_t)dhq * H);
+    const int64_t b = bn / n, pos = bn - b * n;
+    const float g = 1.f / (1.f + expf(-__ldg(&gates[bn * H + h])));
+    const float4 v = o[((b * H + h) * n + pos) * (int64_t)dhq + d];
+    y[i] = make_float4(v.x * g, v.y * g, v.z * g, v.w * g);
+  }
+}
+
 extern "C" int b200sep_gate_merge_heads_f32(const float* o, const float* gates, float* y, int B, int n, int H, int dh, void* stream) {
   B2_CHECK_ARG(o && gates && y && B >= 1 && n >= 1 && H >= 1 && dh >= 1, "gate_merge_heads_f32: bad argument");
+  if (dh % 4 == 0 && ((reinterpret_cast<uintptr_t>(o) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+    const int64_t tq = (int64_t)B * n * H * (dh / 4);
+    gate_merge_vec_kernel<<<rf_grid(tq), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(o), gates, reinterpret_cast<float4*>(y), n, H, dh / 4, tq);
+    B2_LAUNCHED();
+    return B200SEP_OK;
+  }
   const int64_t total = (int64_t)B * n * H * dh;
   gate_merge_kernel<<<rf_grid(total), 256, 0, (cudaStream_t)stream>>>(o, gates, y, n, H, dh, total);
   B2_LAUNCHED();
