@@ -65,11 +65,6 @@ struct UmmaParams {
   int out_c_total, out_c_off;  // conv modes: the output occupies channels [out_c_off, out_c_off + Cout) of a (B, out_c_total, T', F') tensor
 };
 
-__device__ __forceinline__ float apply_act(float x, int act) {
-  if (act == 1) return fmaxf(x, 0.f);
-  if (act == 2) return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));  // nn.GELU() default (exact erf form)
-  return x;
-}
 
 // activation of a whole register group with ONE test of the (kernel-uniform) activation code: inside the unrolled column loops the per-column
 // form cost a uniform branch (and, for GELU, an inlined erf with its own selects) per output
