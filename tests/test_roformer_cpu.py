@@ -63,3 +63,25 @@ def test_melband_oracle_and_band_layout(golden_dir, lib_built):
         mask, idx, nfpb, nbpf = b
         assert mask[0, 0] and mask[-1, -1] and nbpf.min() >= 1 and nfpb.sum() * 2 == len(idx)
         assert (np.diff(np.where(mask[5])[0]) == 1).all()  # a band covers a contiguous run of bins
+
+
+def test_roformer_config_parsing(lib_built):
+    """The YAML `model` section -> graph configuration (roformer_loader.py:120-195): defaults, tuple conversion, and loud failures for what is not covered."""
+    import pytest
+
+    from audio_separator.separator.b200 import roformer as rf
+
+    c = rf.BSRoformerConfig.from_model_section({"dim": 384, "depth": 6, "stereo": True, "num_stems": 1, "time_transformer_depth": 1, "freq_transformer_depth": 1,
+                                                "freqs_per_bands": list(rf.DEFAULT_FREQS_PER_BANDS), "dim_head": 64, "heads": 8, "stft_hop_length": 441, "mask_estimator_depth": 2,
+                                                "attn_dropout": 0.1, "flash_attn": True, "multi_stft_hop_size": 147})  # training-only keys are ignored
+    assert (c.dim, c.depth, c.stft_hop_length, c.mask_estimator_depth) == (384, 6, 441, 2) and isinstance(c.freqs_per_bands, tuple) and len(c.band_dims) == 62
+    assert sum(c.band_dims) == 1025 * 4
+    with pytest.raises(ValueError):
+        rf.BSRoformerConfig.from_model_section({"dim": 64, "depth": 1, "freqs_per_bands": [2, 2, 4]})  # does not add up to n_fft/2 + 1
+    for bad in ({"linear_transformer_depth": 1}, {"sage_attention": True}, {"stft_normalized": True}, {"stft_win_length": 1024}, {"stft_window_fn": "torch.hamming_window"}):
+        with pytest.raises(NotImplementedError):
+            rf.BSRoformerConfig.from_model_section(dict({"dim": 64, "depth": 1}, **bad))
+    m = rf.MelBandRoformerConfig.from_model_section({"dim": 384, "depth": 6, "stereo": True, "num_bands": 60, "stft_hop_length": 441, "mask_estimator_depth": 2, "sample_rate": 44100})
+    assert len(m.band_dims) == 60 and sum(m.band_dims) == 2 * 3958 and m.freqs_per_bands[0] == 7
+    with pytest.raises(NotImplementedError):
+        rf.MelBandRoformerConfig.from_model_section({"dim": 64, "depth": 1, "num_bands": 8, "match_input_audio_length": True})
