@@ -101,6 +101,12 @@ int b200sep_demix_overlap_add_range(const float* chunks, int first_chunk, int n_
                                     int64_t total_len, int64_t trim, int64_t n_out, int64_t q_begin, int64_t q_end, int use_window,
                                     float out_scale, const float* mix, float compensate, int interleave, float* primary,
                                     float* secondary, void* stream);
+/* Same with the outputs and the mix given as SLICES: primary / secondary hold the rows [out_base, ...) of the interleaved (n_out, 2) stems and
+ * mix is (2, mix_ld) holding the samples [mix_base, mix_base + mix_ld) -- a rank of the sharded end-to-end path only ever holds its own part. */
+int b200sep_demix_overlap_add_range_ex(const float* chunks, int first_chunk, int n_local_chunks, int n_chunks, int chunk_len, int64_t step,
+                                       int64_t total_len, int64_t trim, int64_t n_out, int64_t q_begin, int64_t q_end, int use_window,
+                                       float out_scale, const float* mix, int64_t mix_ld, int64_t mix_base, float compensate, int interleave,
+                                       float* primary, float* secondary, int64_t out_base, void* stream);
 
 /* max |x| over n floats -> *result (device float).  (np.abs(mix).max(), mdx_separator.py:155; spec_utils.py:110) */
 int b200sep_absmax(const float* x, int64_t n, float* result, void* stream);
@@ -199,6 +205,12 @@ int b200sep_tfcnet_forward(b200sep_tfcnet* net, const float* spec_in, float* spe
  */
 int b200sep_rect_overlap_add(const float* chunks, int n_chunks, int channels, int chunk_len, int64_t hop, int64_t front, int64_t n_out,
                              float divisor, float* out, void* stream);
+/* Time-sharded form (MDXC row): `chunks` holds the global chunks [first_chunk, first_chunk + n_local) only and
+ * the samples [q_begin, q_end) of the (channels, n_out) output are written to out[c * out_ld + q - out_base] (a rank's own slice);
+ * every chunk covering that range must be local. */
+int b200sep_rect_overlap_add_range(const float* chunks, int first_chunk, int n_local, int n_chunks, int channels, int chunk_len, int64_t hop,
+                                   int64_t front, int64_t n_out, int64_t q_begin, int64_t q_end, float divisor, float* out, int64_t out_ld,
+                                   int64_t out_base, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Generalised STFT framing (HTDemucs._spec / _ispec, uvr_lib_v5/demucs/htdemucs.py:383-413 + spec.py:11-38): see stft.cu.
@@ -265,6 +277,11 @@ int b200sep_meanstd_f32(const float* x, int64_t n, float* out2, void* stream);
  * -- q0/scale/accumulate fold in the shift average (apply.py:197-214), chan_scale (nullable) the bag weights (apply.py:169-195). */
 int b200sep_triangle_overlap_add(const float* segs, int n_segs, int channels, int seg_len, int64_t stride, int64_t length, int64_t q0, int64_t n_out,
                                  float scale, const float* chan_scale, int accumulate, float* out, void* stream);
+/* Time-sharded form (Demucs row): `segs` holds the global segments [first_seg, first_seg + n_local) only; the n_out
+ * samples go to out[c * out_ld + out_off + n] (a slice of full-length rows); every segment covering [q0, q0 + n_out) must be local. */
+int b200sep_triangle_overlap_add_range(const float* segs, int first_seg, int n_local, int n_segs, int channels, int seg_len, int64_t stride,
+                                       int64_t length, int64_t q0, int64_t n_out, float scale, const float* chan_scale, int accumulate, float* out,
+                                       int64_t out_ld, int64_t out_off, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Operators of the VR path (uvr_lib_v5/vr_network/{nets,layers}.py, architectures/vr_separator.py, uvr_lib_v5/spec_utils.py).

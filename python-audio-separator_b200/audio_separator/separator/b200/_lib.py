@@ -41,6 +41,7 @@ _SIGS = {
     "b200sep_stft_inverse": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp]),
     "b200sep_demix_overlap_add": (i32, [vp, i32, i32, i64, i64, i64, i64, i32, f32, vp, f32, i32, vp, vp, vp]),
     "b200sep_demix_overlap_add_range": (i32, [vp, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i32, f32, vp, f32, i32, vp, vp, vp]),
+    "b200sep_demix_overlap_add_range_ex": (i32, [vp, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i32, f32, vp, i64, i64, f32, i32, vp, vp, i64, vp]),
     "b200sep_absmax": (i32, [vp, i64, vp, vp]),
     "b200sep_normalize": (i32, [vp, i64, vp, f32, f32, vp, vp]),
     "b200sep_to_pcm16": (i32, [vp, i64, vp, vp]),
@@ -58,6 +59,7 @@ _SIGS = {
     "b200sep_tfcnet_device_bytes": (i64, [vp]),
     "b200sep_tfcnet_forward": (i32, [vp, vp, vp, i32, vp]),
     "b200sep_rect_overlap_add": (i32, [vp, i32, i32, i32, i64, i64, i64, f32, vp, vp]),
+    "b200sep_rect_overlap_add_range": (i32, [vp, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, f32, vp, i64, i64, vp]),
     "b200sep_stft_forward_ex": (i32, [vp, vp, i64, i64, i64, i32, i32, i32, i32, f32, i32, i32, i32, i32, vp, vp]),
     "b200sep_stft_inverse_ex": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp, vp, vp]),
     "b200sep_conv2d_f32": (i32, [vp, vp, vp, vp, vp] + [i32] * 23 + [vp, vp]),
@@ -75,6 +77,7 @@ _SIGS = {
     "b200sep_ew_f32": (i32, [vp, vp, vp, i64, f32, f32, i32, vp]),
     "b200sep_meanstd_f32": (i32, [vp, i64, vp, vp]),
     "b200sep_triangle_overlap_add": (i32, [vp, i32, i32, i32, i64, i64, i64, i64, f32, vp, i32, vp, vp]),
+    "b200sep_triangle_overlap_add_range": (i32, [vp, i32, i32, i32, i32, i32, i64, i64, i64, i64, f32, vp, i32, vp, i64, i64, vp]),
     "b200sep_dwconv3x3_f32": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "b200sep_upsample2x_bilinear_f32": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "b200sep_mean_h_f32": (i32, [vp, vp, i32, i32, i32, vp]),

@@ -493,10 +493,17 @@ class HTDemucsNet:
 
 # --------------------------------------------------------------------------------------------------------- apply_model / demix
 class DemucsEngine:
-    """apply_model(shifts, split=True, overlap) over a bag of HTDemucs models + DemucsSeparator.demix_demucs, device resident."""
+    """apply_model(shifts, split=True, overlap) over a bag of HTDemucs models + DemucsSeparator.demix_demucs, device resident.
 
-    def __init__(self, nets, bag_weights=None, overlap=0.25, batch_size=4):
+    With `dist` (torch.distributed, backend nccl, one process per GPU) the segments of every (model, shift) pass are time-sharded
+    (Demucs row, option A): rank r finalises the output samples [N*r/W, N*(r+1)/W) of EVERY pass, computes the
+    segments that start in that range and receives from its left neighbour the one or two segments that reach into it (b200/sharded.py).
+    Per output sample the passes accumulate in the single-GPU order, so the sharded result is the single-GPU result."""
+
+    def __init__(self, nets, bag_weights=None, overlap=0.25, batch_size=4, dist=None, group=None):
         _require_cuda()
+        from .sharded import ShardRunner
+
         self.nets = list(nets)
         cfg = self.nets[0].cfg
         self.cfg = cfg
@@ -508,42 +515,64 @@ class DemucsEngine:
         self.overlap = float(overlap)
         self.batch_size = int(batch_size)
         self.device = self.nets[0].device
+        self.runner = ShardRunner(dist, group)
+        self.rank, self.world = self.runner.rank, self.runner.world
+
+    def out_range(self, N):
+        """Output samples [q0, q1) this rank finalises (everything on a single GPU)."""
+        return N * self.rank // self.world, N * (self.rank + 1) // self.world
 
     def _apply_split(self, net, tensor, offset, length, out, q0, n_out, scale, chan_scale, accumulate):
         """apply_model's split branch on TensorChunk(tensor, offset, length) (apply.py:215-250); the weighted result's samples
-        [q0, q0 + n_out) are scaled and written / accumulated into out (S*2, n_out)."""
+        [q0, q0 + n_out) -- this rank's part [r0, r1) of them -- are scaled and written / accumulated into out (S*2, r1 - r0)."""
+        from .sharded import plan_range_shards
+
         cfg = self.cfg
         seg = cfg.seg_len
         S = len(cfg.sources)
         stride = int((1 - self.overlap) * seg)
         total = tensor.shape[-1]
         offs = list(range(0, length, stride))
-        ext = torch.zeros((2, total + 2 * seg), dtype=torch.float32, device=tensor.device)  # TensorChunk.padded zero-fills outside the tensor (apply.py:97-113)
-        ext[:, seg : seg + total].copy_(tensor)
-        segs = torch.zeros((len(offs), S * 2, seg), dtype=torch.float32, device=tensor.device)
-        for i0 in range(0, len(offs), self.batch_size):
-            group = offs[i0 : i0 + self.batch_size]
-            batch = _new((len(group), 2, seg), tensor)
+        sh = plan_range_shards(n_out, self.world, len(offs), stride, seg, q0)[self.rank]
+        assert tuple(out.shape) == (S * 2, sh.q1 - sh.q0), (out.shape, sh)
+        # TensorChunk.padded zero-fills outside the tensor (apply.py:97-113): only the part this rank's segments read is materialised
+        lo = offset + sh.c0 * stride - seg
+        hi = offset + (sh.c1 - 1) * stride + 2 * seg if sh.n_own else lo + 1
+        ext = torch.zeros((2, hi - lo), dtype=torch.float32, device=tensor.device)
+        a, b = max(lo, 0), min(hi, total)
+        if b > a:
+            ext[:, a - lo : b - lo].copy_(tensor[:, a:b])
+        local = torch.empty((sh.halo + sh.n_own, S * 2, seg), dtype=torch.float32, device=tensor.device)
+
+        def compute(buf, slot0, unit0, n):
+            batch = _new((n, 2, seg), tensor)
             clens = []
-            for j, off in enumerate(group):
+            for j in range(n):
+                off = offs[unit0 + j]
                 clen = min(length - off, seg)
                 start = offset + off - (seg - clen) // 2
-                batch[j].copy_(ext[:, seg + start : seg + start + seg])
+                batch[j].copy_(ext[:, start - lo : start - lo + seg])
                 clens.append(clen)
             y = net.forward(batch)  # (n, S, 2, seg)
             for j, clen in enumerate(clens):  # center_trim to the chunk's valid length (apply.py:258), stored from sample 0
                 d = (seg - clen) // 2
-                segs[i0 + j, :, :clen].copy_(y[j].reshape(S * 2, seg)[:, d : d + clen])
-        check(lib.b200sep_triangle_overlap_add(_ptr(segs), len(offs), S * 2, seg, stride, length, q0, n_out, scale, _ptr(chan_scale) if chan_scale is not None else None,
-                                               int(accumulate), _ptr(out), _stream()), "triangle_overlap_add")
+                buf[slot0 + j, :, :clen].copy_(y[j].reshape(S * 2, seg)[:, d : d + clen])
+
+        self.runner.wait_all(self.runner.run_units(sh, local, compute, self.batch_size))
+        if sh.q1 > sh.q0:
+            check(lib.b200sep_triangle_overlap_add_range(_ptr(local), sh.c0 - sh.halo, sh.halo + sh.n_own, len(offs), S * 2, seg, stride, length, q0 + sh.q0, sh.q1 - sh.q0,
+                                                         scale, _ptr(chan_scale) if chan_scale is not None else None, int(accumulate), _ptr(out), sh.q1 - sh.q0, 0,
+                                                         _stream()), "triangle_overlap_add_range")
 
     def apply_model(self, mix: torch.Tensor, shift_offsets, net_index=0, out=None, chan_scale=None, accumulate=False):
-        """mix (2, N) cuda -> (S*2, N).  shift_offsets: the `random.randint(0, max_shift)` draws of apply.py:207 (empty = shifts 0)."""
+        """mix (2, N) cuda -> (S*2, q1 - q0): this rank's output range (the whole (S*2, N) on a single GPU).
+        shift_offsets: the `random.randint(0, max_shift)` draws of apply.py:207 (empty = shifts 0)."""
         net = self.nets[net_index]
         S = len(self.cfg.sources)
         N = mix.shape[-1]
+        r0, r1 = self.out_range(N)
         if out is None:
-            out = _new((S * 2, N), mix)
+            out = _new((S * 2, r1 - r0), mix)
         if not shift_offsets:
             self._apply_split(net, mix, 0, N, out, 0, N, 1.0, chan_scale, accumulate)
             return out
@@ -554,11 +583,10 @@ class DemucsEngine:
             self._apply_split(net, pm, o, N + ms - o, out, ms - o, N, 1.0 / len(shift_offsets), chan_scale, accumulate or i > 0)
         return out
 
-    def demix(self, mix: np.ndarray, shift_offsets) -> np.ndarray:
-        """DemucsSeparator.demix_demucs (demucs_separator.py:162-195): mix (2, N) host -> sources (S, 2, N) host, sources 0/1 swapped.
-        shift_offsets: one list of shift draws per model of the bag."""
+    def demix_device(self, mix_d: torch.Tensor, shift_offsets) -> torch.Tensor:
+        """DemucsSeparator.demix_demucs (demucs_separator.py:162-195) on a (2, N) CUDA mix -> this rank's (S, 2, q1 - q0) slice of the sources
+        (sources 0/1 swapped like the reference; the whole (S, 2, N) on a single GPU).  shift_offsets: one list of shift draws per model of the bag."""
         S = len(self.cfg.sources)
-        mix_d = torch.from_numpy(np.ascontiguousarray(mix, dtype=np.float32)).to(self.device)
         N = mix_d.shape[1]
         ref = ew(mix_d[0], mix_d[1], _new((N,), mix_d), 0.5, 0.5)
         stats = _new((2,), mix_d)
@@ -566,11 +594,23 @@ class DemucsEngine:
         mean, std = (float(v) for v in stats.cpu())
         mn = ew(mix_d, None, _new(mix_d.shape, mix_d), 1.0 / std, -mean / std)
         tot = np.sum(np.asarray(self.bag_weights, np.float64), axis=0)
-        out = _new((S * 2, N), mix_d)
+        r0, r1 = self.out_range(N)
+        out = _new((S * 2, r1 - r0), mix_d)
         for mi in range(len(self.nets)):
             cs = torch.tensor(np.repeat(np.asarray(self.bag_weights[mi]) / tot, 2).astype(np.float32), device=self.device)
             self.apply_model(mn, list(shift_offsets[mi]), mi, out, cs, accumulate=mi > 0)
         ew(out, None, out, std, mean)
-        src = out.view(S, 2, N).cpu().numpy()
-        src[[0, 1]] = src[[1, 0]]
-        return src
+        src = out.view(S, 2, r1 - r0)
+        return torch.cat([src[1:2], src[0:1], src[2:]], dim=0) if S >= 2 else src
+
+    def gather(self, part: torch.Tensor, N: int):
+        """Rank 0: the full (S, 2, N) sources from every rank's demix_device slice (None elsewhere); identity on a single GPU."""
+        if self.world == 1:
+            return part
+        return self.runner.gather_cols(part, [(N * r // self.world, N * (r + 1) // self.world) for r in range(self.world)], N)
+
+    def demix(self, mix: np.ndarray, shift_offsets) -> np.ndarray:
+        """Host arrays in and out: mix (2, N) -> sources (S, 2, N) (rank 0; None on the other ranks of a sharded run)."""
+        mix_d = torch.from_numpy(np.ascontiguousarray(mix, dtype=np.float32)).to(self.device)
+        full = self.gather(self.demix_device(mix_d, shift_offsets), mix_d.shape[1])
+        return None if full is None else full.cpu().numpy()

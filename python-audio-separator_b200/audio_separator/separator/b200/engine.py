@@ -338,16 +338,24 @@ class TfcNet:
 
 class MdxcEngine:
     """Device-resident MDXCSeparator.demix, non-Roformer branch (mdxc_separator.py:345-404): unfold -> batches ->
-    STFT -> TFC_TDF_net -> iSTFT -> rectangular overlap-add / overlap."""
+    STFT -> TFC_TDF_net -> iSTFT -> rectangular overlap-add / overlap.
 
-    def __init__(self, net: TfcNet, n_fft, hop_length, dim_f, dim_t, overlap):
+    With `dist` (torch.distributed, nccl, one process per GPU) the chunk grid is time-sharded (MDXC row): rank r finalises the
+    output samples [N*r/W, N*(r+1)/W), computes the chunks that start there and receives from its left neighbour the chunks that reach into its range
+    (`overlap - 1` of them: 228 480 samples of halo at the MDX23C sizes), b200/sharded.py."""
+
+    def __init__(self, net: TfcNet, n_fft, hop_length, dim_f, dim_t, overlap, dist=None, group=None):
         _require_cuda()
+        from .sharded import ShardRunner
+
         self.net, self.n_fft, self.hop, self.dim_f, self.dim_t, self.overlap = net, int(n_fft), int(hop_length), int(dim_f), int(dim_t), int(overlap)
         self.chunk_size = self.hop * (self.dim_t - 1)  # :361
         self.hop_size = self.chunk_size // self.overlap  # :364
         self.plan = StftPlan(self.n_fft, self.hop)
         self.batch = net.max_batch
         self.device = torch.device("cuda", torch.cuda.current_device())
+        self.runner = ShardRunner(dist, group)
+        self.rank, self.world = self.runner.rank, self.runner.world
 
     def grid(self, n_samples):
         chunk, hop = self.chunk_size, self.hop_size
@@ -369,23 +377,47 @@ class MdxcEngine:
             out[b0 : b0 + nb] = w.reshape(nb, S, 2, T)
         return out
 
+    def out_range(self, N):
+        return N * self.rank // self.world, N * (self.rank + 1) // self.world
+
     def demix_device(self, mix_dev: torch.Tensor) -> torch.Tensor:
-        """mix (2,N) float32 CUDA -> (S, 2, N)."""
+        """mix (2,N) float32 CUDA -> (S, 2, q1 - q0): this rank's output range (the whole (S, 2, N) on a single GPU)."""
+        from .sharded import plan_range_shards
+
         mix_dev = mix_dev.contiguous()
         N = mix_dev.shape[1]
         Lp, front, pad, n_chunks = self.grid(N)
         T, hop, S = self.chunk_size, self.hop_size, self.net.num_targets
-        padded = torch.zeros((2, Lp), dtype=torch.float32, device=self.device)  # :371
-        padded[:, front : front + N] = mix_dev
-        chunks = torch.empty((n_chunks, S * 2, T), dtype=torch.float32, device=self.device)
-        for b0 in range(0, n_chunks, self.batch):
-            nb = min(self.batch, n_chunks - b0)
+        sh = plan_range_shards(N, self.world, n_chunks, hop, T, front)[self.rank]
+        # this rank's part of the padded mixture (:371): positions [c0*hop, (c1-1)*hop + chunk)
+        p0 = sh.c0 * hop
+        p1 = (sh.c1 - 1) * hop + T if sh.n_own else p0 + 1
+        padded = torch.zeros((2, p1 - p0), dtype=torch.float32, device=self.device)
+        a, b = max(p0, front), min(p1, front + N)
+        if b > a:
+            padded[:, a - p0 : b - p0] = mix_dev[:, a - front : b - front]
+        Ls = padded.shape[1]
+        local = torch.empty((sh.halo + sh.n_own, S * 2, T), dtype=torch.float32, device=self.device)
+
+        def compute(buf, slot0, unit0, nb):
             spec = torch.empty((nb, 4, self.dim_t, self.dim_f), dtype=torch.float32, device=self.device)
+            off = unit0 * hop - p0
             # chunks are read straight out of the padded mixture (mix.unfold(1, chunk, hop), :374)
-            check(lib.b200sep_stft_forward(self.plan.handle, padded.data_ptr() + b0 * hop * 4, hop, Lp, Lp - b0 * hop, nb, T, self.dim_f, 0, LAYOUT_CTF, _ptr(spec), _stream()), "stft_forward")
+            check(lib.b200sep_stft_forward(self.plan.handle, padded.data_ptr() + off * 4, hop, Ls, Ls - off, nb, T, self.dim_f, 0, LAYOUT_CTF, _ptr(spec), _stream()), "stft_forward")
             y = self.net.forward_spec(spec)
             w = self.plan.inverse(y.reshape(nb * S, 4, self.dim_t, self.dim_f), LAYOUT_CTF)  # (nb*S, 2, T)
-            chunks[b0 : b0 + nb] = w.reshape(nb, S * 2, T)
-        out = torch.empty((S * 2, N), dtype=torch.float32, device=self.device)
-        check(lib.b200sep_rect_overlap_add(_ptr(chunks), n_chunks, S * 2, T, hop, front, N, float(self.overlap), _ptr(out), _stream()), "rect_overlap_add")  # :395-402
-        return out.reshape(S, 2, N)
+            buf[slot0 : slot0 + nb] = w.reshape(nb, S * 2, T)
+
+        self.runner.wait_all(self.runner.run_units(sh, local, compute, self.batch))
+        n_q = sh.q1 - sh.q0
+        out = torch.empty((S * 2, n_q), dtype=torch.float32, device=self.device)
+        if n_q:
+            check(lib.b200sep_rect_overlap_add_range(_ptr(local), sh.c0 - sh.halo, sh.halo + sh.n_own, n_chunks, S * 2, T, hop, front, N, sh.q0, sh.q1, float(self.overlap),
+                                                     _ptr(out), n_q, sh.q0, _stream()), "rect_overlap_add_range")  # :395-402
+        return out.reshape(S, 2, n_q)
+
+    def gather(self, part: torch.Tensor, N: int):
+        """Rank 0: the full (S, 2, N) stems from every rank's demix_device slice (None elsewhere); identity on a single GPU."""
+        if self.world == 1:
+            return part
+        return self.runner.gather_cols(part, [(N * r // self.world, N * (r + 1) // self.world) for r in range(self.world)], N)

@@ -468,8 +468,8 @@ __global__ void __launch_bounds__(1024) meanstd_kernel(const float* __restrict__
 // segments i start at o_i = i * stride, have `seg_len` samples except the last (clipped at `length`); triangle weight of `seg_len`.
 // Output sample n of channel c is position q = q0 + n of the overlap-added signal, times scale * chan_scale[c]; `accumulate` adds to out
 // (the shift-trick average, apply.py:197-214, and the per-source bag weights, apply.py:169-195, folded into the same pass).
-__global__ void tri_ola_kernel(const float* __restrict__ segs, int n_segs, int channels, int seg_len, int64_t stride, int64_t length, int64_t q0, int64_t n_out,
-                               float scale, const float* __restrict__ chan_scale, int accumulate, float* __restrict__ out) {
+__global__ void tri_ola_kernel(const float* __restrict__ segs, int first_seg, int n_segs, int channels, int seg_len, int64_t stride, int64_t length, int64_t q0,
+                               int64_t n_out, float scale, const float* __restrict__ chan_scale, int accumulate, float* __restrict__ out, int64_t out_ld, int64_t out_off) {
   const int c = blockIdx.y;
   const float wmax = (float)(seg_len - seg_len / 2 > seg_len / 2 ? seg_len - seg_len / 2 : seg_len / 2);
   const float sc = scale * (chan_scale ? __ldg(&chan_scale[c]) : 1.f);
@@ -482,10 +482,10 @@ __global__ void tri_ola_kernel(const float* __restrict__ segs, int n_segs, int c
     for (int64_t i = i_lo; i <= i_hi; ++i) {
       const int64_t n = q - i * stride;  // position inside segment i (its valid part is always long enough: clipped only at `length`)
       const float w = ((n < seg_len / 2) ? (float)(n + 1) : (float)(seg_len - n)) / wmax;  // cat(arange(1, s/2+1), arange(s - s/2, 0, -1)) / max
-      acc += w * __ldg(&segs[((int64_t)i * channels + c) * seg_len + n]);
+      acc += w * __ldg(&segs[((int64_t)(i - first_seg) * channels + c) * seg_len + n]);  // segs[0] is global segment `first_seg`
       sw += w;
     }
-    const int64_t o = (int64_t)c * n_out + n_o;
+    const int64_t o = (int64_t)c * out_ld + out_off + n_o;
     const float v = sc * (acc / sw);
     out[o] = accumulate ? out[o] + v : v;
   }
@@ -621,16 +621,32 @@ extern "C" int b200sep_meanstd_f32(const float* x, int64_t n, float* out2, void*
   return B200SEP_OK;
 }
 
-extern "C" int b200sep_triangle_overlap_add(const float* segs, int n_segs, int channels, int seg_len, int64_t stride, int64_t length, int64_t q0, int64_t n_out,
-                                            float scale, const float* chan_scale, int accumulate, float* out, void* stream) {
+extern "C" int b200sep_triangle_overlap_add_range(const float* segs, int first_seg, int n_local, int n_segs, int channels, int seg_len, int64_t stride, int64_t length,
+                                                  int64_t q0, int64_t n_out, float scale, const float* chan_scale, int accumulate, float* out, int64_t out_ld,
+                                                  int64_t out_off, void* stream) {
   B2_CHECK_ARG(segs && out && n_segs >= 1 && channels >= 1 && seg_len >= 2 && stride >= 1 && length >= 1, "triangle_overlap_add: bad argument");
-  B2_CHECK_ARG(q0 >= 0 && n_out >= 1 && q0 + n_out <= length, "triangle_overlap_add: output range [%lld, %lld) outside the signal of %lld samples",
+  B2_CHECK_ARG(q0 >= 0 && n_out >= 0 && q0 + n_out <= length, "triangle_overlap_add: output range [%lld, %lld) outside the signal of %lld samples",
                (long long)q0, (long long)(q0 + n_out), (long long)length);
   B2_CHECK_ARG((int64_t)(n_segs - 1) * stride < length, "triangle_overlap_add: more segments than the signal holds");
+  B2_CHECK_ARG(out_off >= 0 && out_off + n_out <= out_ld, "triangle_overlap_add: output slice [%lld, %lld) outside rows of %lld", (long long)out_off,
+               (long long)(out_off + n_out), (long long)out_ld);
+  if (n_out == 0) return B200SEP_OK;
+  // every segment that covers [q0, q0 + n_out) must be present in the local buffer
+  const int64_t need_lo = (q0 - seg_len + 1 <= 0) ? 0 : (q0 - seg_len + stride) / stride;
+  const int64_t need_hi = std::min<int64_t>((q0 + n_out - 1) / stride, n_segs - 1);
+  B2_CHECK_ARG(need_lo >= first_seg && need_hi < (int64_t)first_seg + n_local, "triangle_overlap_add: outputs [%lld,%lld) need segments [%lld,%lld] but the buffer holds [%d,%d)",
+               (long long)q0, (long long)(q0 + n_out), (long long)need_lo, (long long)need_hi, first_seg, first_seg + n_local);
   dim3 grid((unsigned)std::min<int64_t>(cdiv(n_out, 256), kNumSMs * 8), channels);
-  tri_ola_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(segs, n_segs, channels, seg_len, stride, length, q0, n_out, scale, chan_scale, accumulate, out);
+  tri_ola_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(segs, first_seg, n_segs, channels, seg_len, stride, length, q0, n_out, scale, chan_scale, accumulate, out, out_ld,
+                                                         out_off);
   B2_LAUNCHED();
   return B200SEP_OK;
+}
+
+extern "C" int b200sep_triangle_overlap_add(const float* segs, int n_segs, int channels, int seg_len, int64_t stride, int64_t length, int64_t q0, int64_t n_out,
+                                            float scale, const float* chan_scale, int accumulate, float* out, void* stream) {
+  B2_CHECK_ARG(n_out >= 1, "triangle_overlap_add: empty output");
+  return b200sep_triangle_overlap_add_range(segs, 0, n_segs, n_segs, channels, seg_len, stride, length, q0, n_out, scale, chan_scale, accumulate, out, n_out, 0, stream);
 }
 
 extern "C" int b200sep_gemm_kn_f32(const float* A, const float* B_kn, float* C, int M, int N, int K, int lda, int ldb, int ldc, int batch, int64_t strideA, int64_t strideB,

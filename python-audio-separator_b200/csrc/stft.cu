@@ -270,8 +270,8 @@ __global__ void istft_ola_kernel(const float* __restrict__ fr, const float* __re
 // demix accumulate/divide/trim as a gather over covering chunks (mdx_separator.py:348-401)
 __global__ void demix_ola_kernel(const float* __restrict__ chunks, int first_chunk, int n_chunks, int chunk_len, int64_t step, int64_t total_len,
                                  int64_t trim, int64_t n_out, int64_t q_begin, int64_t q_end, int use_window, float out_scale,
-                                 const float* __restrict__ mix, float compensate, int interleave, float* __restrict__ primary,
-                                 float* __restrict__ secondary) {
+                                 const float* __restrict__ mix, int64_t mix_ld, int64_t mix_base, float compensate, int interleave,
+                                 float* __restrict__ primary, float* __restrict__ secondary, int64_t out_base, int64_t out_ld) {
   for (int64_t q = q_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < q_end; q += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p = q + trim;
     int64_t i_hi = p / step;
@@ -300,26 +300,26 @@ __global__ void demix_ola_kernel(const float* __restrict__ chunks, int first_chu
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       const float v = __fmul_rn(res[c] / div, out_scale);
-      const int64_t o = interleave ? (q * 2 + c) : ((int64_t)c * n_out + q);
+      const int64_t o = interleave ? ((q - out_base) * 2 + c) : ((int64_t)c * out_ld + (q - out_base));
       primary[o] = v;
-      if (mix != nullptr) secondary[o] = __fadd_rn(__fmul_rn(-v, compensate), __ldg(&mix[(int64_t)c * n_out + q]));
+      if (mix != nullptr) secondary[o] = __fadd_rn(__fmul_rn(-v, compensate), __ldg(&mix[(int64_t)c * mix_ld + (q - mix_base)]));
     }
   }
 }
 
 // MDX23C accumulation (mdxc_separator.py:395-402): rectangular overlap-add of full-length chunks placed every `hop`,
 // slice [front, front + n_out), divide by the constant `overlap`.  chunks: (n_chunks, C, chunk); out: (C, n_out).
-__global__ void rect_ola_kernel(const float* __restrict__ chunks, int n_chunks, int C, int chunk_len, int64_t hop, int64_t front, int64_t n_out,
-                                float divisor, float* __restrict__ out) {
+__global__ void rect_ola_kernel(const float* __restrict__ chunks, int first_chunk, int n_chunks, int C, int chunk_len, int64_t hop, int64_t front, int64_t n_out,
+                                int64_t q_begin, int64_t q_end, float divisor, float* __restrict__ out, int64_t out_ld, int64_t out_base) {
   const int c = blockIdx.y;
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_out; q += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t q = q_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < q_end; q += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p = q + front;
     int64_t i_hi = p / hop;
     if (i_hi > n_chunks - 1) i_hi = n_chunks - 1;
     int64_t i_lo = (p - chunk_len + 1 <= 0) ? 0 : (p - chunk_len + hop) / hop;
     float acc = 0.f;
-    for (int64_t i = i_lo; i <= i_hi; ++i) acc += __ldg(&chunks[((int64_t)i * C + c) * chunk_len + (p - i * hop)]);
-    out[(int64_t)c * n_out + q] = acc / divisor;
+    for (int64_t i = i_lo; i <= i_hi; ++i) acc += __ldg(&chunks[((int64_t)(i - first_chunk) * C + c) * chunk_len + (p - i * hop)]);  // chunks[0] is global chunk `first_chunk`
+    out[(int64_t)c * out_ld + (q - out_base)] = acc / divisor;
   }
 }
 
@@ -495,14 +495,17 @@ extern "C" int b200sep_stft_inverse_ex(const b200sep_stft_plan* plan, const floa
   return B200SEP_OK;
 }
 
-extern "C" int b200sep_demix_overlap_add_range(const float* chunks, int first_chunk, int n_local_chunks, int n_chunks, int chunk_len, int64_t step,
-                                               int64_t total_len, int64_t trim, int64_t n_out, int64_t q_begin, int64_t q_end, int use_window,
-                                               float out_scale, const float* mix, float compensate, int interleave, float* primary,
-                                               float* secondary, void* stream) {
+extern "C" int b200sep_demix_overlap_add_range_ex(const float* chunks, int first_chunk, int n_local_chunks, int n_chunks, int chunk_len, int64_t step,
+                                                  int64_t total_len, int64_t trim, int64_t n_out, int64_t q_begin, int64_t q_end, int use_window,
+                                                  float out_scale, const float* mix, int64_t mix_ld, int64_t mix_base, float compensate, int interleave,
+                                                  float* primary, float* secondary, int64_t out_base, void* stream) {
   B2_CHECK_ARG(chunks && primary, "demix_overlap_add_range: NULL argument");
   B2_CHECK_ARG(mix == nullptr || secondary != nullptr, "demix_overlap_add_range: mix given without a secondary buffer");
   B2_CHECK_ARG(n_chunks >= 1 && chunk_len >= 1 && step >= 1 && total_len >= 1 && trim >= 0 && n_out >= 0, "demix_overlap_add_range: bad sizes");
   B2_CHECK_ARG(trim + n_out <= total_len && 0 <= q_begin && q_begin <= q_end && q_end <= n_out, "demix_overlap_add_range: bad output range");
+  B2_CHECK_ARG(out_base >= 0 && out_base <= q_begin && (mix == nullptr || (mix_base >= 0 && mix_base <= q_begin && q_end - mix_base <= mix_ld)),
+               "demix_overlap_add_range: output / mix slices do not cover [%lld, %lld)", (long long)q_begin, (long long)q_end);
+  B2_CHECK_ARG(interleave || out_base == 0, "demix_overlap_add_range: planar output slices are not supported");
   if (q_end == q_begin) return B200SEP_OK;
   // every chunk that covers [q_begin, q_end) must be present in the local buffer
   const int64_t p0 = q_begin + trim, p1 = q_end - 1 + trim;
@@ -513,9 +516,17 @@ extern "C" int b200sep_demix_overlap_add_range(const float* chunks, int first_ch
                (long long)need_lo, (long long)need_hi, first_chunk, first_chunk + n_local_chunks);
   const int blocks = (int)std::min<int64_t>(cdiv(q_end - q_begin, 256), kNumSMs * 16);
   demix_ola_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(chunks, first_chunk, n_chunks, chunk_len, step, total_len, trim, n_out, q_begin, q_end, use_window,
-                                                             out_scale, mix, compensate, interleave, primary, secondary);
+                                                             out_scale, mix, mix_ld, mix_base, compensate, interleave, primary, secondary, out_base, n_out);
   B2_LAUNCHED();
   return B200SEP_OK;
+}
+
+extern "C" int b200sep_demix_overlap_add_range(const float* chunks, int first_chunk, int n_local_chunks, int n_chunks, int chunk_len, int64_t step,
+                                               int64_t total_len, int64_t trim, int64_t n_out, int64_t q_begin, int64_t q_end, int use_window,
+                                               float out_scale, const float* mix, float compensate, int interleave, float* primary,
+                                               float* secondary, void* stream) {
+  return b200sep_demix_overlap_add_range_ex(chunks, first_chunk, n_local_chunks, n_chunks, chunk_len, step, total_len, trim, n_out, q_begin, q_end, use_window, out_scale,
+                                            mix, n_out, 0, compensate, interleave, primary, secondary, 0, stream);
 }
 
 extern "C" int b200sep_demix_overlap_add(const float* chunks, int n_chunks, int chunk_len, int64_t step, int64_t total_len, int64_t trim,
@@ -528,21 +539,33 @@ extern "C" int b200sep_demix_overlap_add(const float* chunks, int n_chunks, int 
   if (n_out == 0) return B200SEP_OK;
   const int blocks = (int)std::min<int64_t>(cdiv(n_out, 256), kNumSMs * 16);
   demix_ola_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(chunks, 0, n_chunks, chunk_len, step, total_len, trim, n_out, 0, n_out, use_window, out_scale,
-                                                             mix, compensate, interleave, primary, secondary);
+                                                             mix, n_out, 0, compensate, interleave, primary, secondary, 0, n_out);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
+extern "C" int b200sep_rect_overlap_add_range(const float* chunks, int first_chunk, int n_local, int n_chunks, int channels, int chunk_len, int64_t hop, int64_t front,
+                                              int64_t n_out, int64_t q_begin, int64_t q_end, float divisor, float* out, int64_t out_ld, int64_t out_base, void* stream) {
+  B2_CHECK_ARG(chunks && out && n_chunks >= 1 && channels >= 1 && chunk_len >= 1 && hop >= 1 && front >= 0 && n_out >= 0 && divisor != 0.f,
+               "rect_overlap_add: bad argument");
+  B2_CHECK_ARG(front + n_out <= (int64_t)(n_chunks - 1) * hop + chunk_len, "rect_overlap_add: output range exceeds the chunk grid");
+  B2_CHECK_ARG(0 <= q_begin && q_begin <= q_end && q_end <= n_out, "rect_overlap_add: bad output range");
+  B2_CHECK_ARG(out_base >= 0 && out_base <= q_begin && q_end - out_base <= out_ld, "rect_overlap_add: output slice does not cover [%lld, %lld)", (long long)q_begin, (long long)q_end);
+  if (q_end == q_begin) return B200SEP_OK;
+  const int64_t p0 = q_begin + front, p1 = q_end - 1 + front;
+  const int64_t need_lo = (p0 - chunk_len + 1 <= 0) ? 0 : (p0 - chunk_len + hop) / hop;
+  const int64_t need_hi = std::min<int64_t>(p1 / hop, n_chunks - 1);
+  B2_CHECK_ARG(need_lo >= first_chunk && need_hi < (int64_t)first_chunk + n_local, "rect_overlap_add: outputs [%lld,%lld) need chunks [%lld,%lld] but the buffer holds [%d,%d)",
+               (long long)q_begin, (long long)q_end, (long long)need_lo, (long long)need_hi, first_chunk, first_chunk + n_local);
+  dim3 grid((unsigned)std::min<int64_t>(cdiv(q_end - q_begin, 256), kNumSMs * 8), channels);
+  rect_ola_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(chunks, first_chunk, n_chunks, channels, chunk_len, hop, front, n_out, q_begin, q_end, divisor, out, out_ld, out_base);
   B2_LAUNCHED();
   return B200SEP_OK;
 }
 
 extern "C" int b200sep_rect_overlap_add(const float* chunks, int n_chunks, int channels, int chunk_len, int64_t hop, int64_t front, int64_t n_out,
                                         float divisor, float* out, void* stream) {
-  B2_CHECK_ARG(chunks && out && n_chunks >= 1 && channels >= 1 && chunk_len >= 1 && hop >= 1 && front >= 0 && n_out >= 0 && divisor != 0.f,
-               "rect_overlap_add: bad argument");
-  B2_CHECK_ARG(front + n_out <= (int64_t)(n_chunks - 1) * hop + chunk_len, "rect_overlap_add: output range exceeds the chunk grid");
-  if (n_out == 0) return B200SEP_OK;
-  dim3 grid((unsigned)std::min<int64_t>(cdiv(n_out, 256), kNumSMs * 8), channels);
-  rect_ola_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(chunks, n_chunks, channels, chunk_len, hop, front, n_out, divisor, out);
-  B2_LAUNCHED();
-  return B200SEP_OK;
+  return b200sep_rect_overlap_add_range(chunks, 0, n_chunks, n_chunks, channels, chunk_len, hop, front, n_out, 0, n_out, divisor, out, n_out, 0, stream);
 }
 
 extern "C" int b200sep_absmax(const float* x, int64_t n, float* result, void* stream) {
