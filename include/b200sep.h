@@ -271,6 +271,15 @@ int b200sep_gemm_kn_f32(const float* A, const float* B_kn, float* C, int M, int 
 int b200sep_ew_f32(const float* a, const float* b, float* out, int64_t n, float alpha, float beta, int op, void* stream);
 /* out2[0] = mean, out2[1] = unbiased std over n elements (htdemucs.py:501-510) */
 int b200sep_meanstd_f32(const float* x, int64_t n, float* out2, void* stream);
+/* One fused DConv residual layer (uvr_lib_v5/demucs/demucs.py:85-168, `layers[d]` of DConv.forward):
+ *   y = x + ls * GLU(GroupNorm(1,2C)(Conv1d(hid->2C,1)(GELU(GroupNorm(1,hid)(Conv1d(C->hid,3,dilation)(x))))))
+ * on (B, C, Fr, L) with one GroupNorm sample per (b, fr) row (hdemucs.py:141-146).  w0 (hid, C, 3), w3 (2C, hid); y may alias x.
+ * u_in (nullable): the (B, hid, Fr, L) output of the first convolution computed by the caller (w0 is then unused).
+ * work: b200sep_dconv_work_floats(...) floats, 16-byte aligned.  See csrc/dconv_fused.cu for the three-pass scheme. */
+int64_t b200sep_dconv_work_floats(int B, int C, int Fr, int64_t L, int hid);
+int b200sep_dconv_f32(const float* x, float* y, const float* w0, const float* b0, const float* g1, const float* be1, const float* w3, const float* b3,
+                      const float* g4, const float* be4, const float* ls, int B, int C, int Fr, int64_t L, int hid, int dilation, const float* u_in,
+                      float* work, void* stream);
 /* apply_model's split branch (demucs/apply.py:215-250): triangle-weighted overlap-add of segments (n_segs, channels, seg_len;
  * each already centre-trimmed to its valid length, stored from sample 0) at stride `stride` over a signal of `length` samples,
  * normalised by the summed weights.  out (channels, n_out): out[c][n] (+)= scale * chan_scale[c] * signal[c][q0 + n]

@@ -38,6 +38,7 @@ class MDXSeparator(CommonSeparator):
             raise RuntimeError("MDXSeparator (B200 build) needs a CUDA device: there is no onnxruntime / CPU path in this package")
         self.torch_device = torch.device("cuda", torch.cuda.current_device())
         self.n_bins = self.trim = self.chunk_size = self.gen_size = 0
+        self._host_bufs = {}
         self.stft = None
         self.engine = None
         self.load_model()
@@ -86,19 +87,42 @@ class MDXSeparator(CommonSeparator):
         mix_dev = torch.as_tensor(np.ascontiguousarray(mix, dtype=np.float32)).to(self.torch_device)
         return self.engine.demix_device(mix_dev, is_match_mix=is_match_mix).cpu().numpy()
 
+    def _pinned(self, name, shape):
+        """Page-locked staging buffers, kept between files of the same length (one cudaHostAlloc per size, not per file)."""
+        buf = self._host_bufs.get(name)
+        if buf is None or tuple(buf.shape) != tuple(shape):
+            buf = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+            self._host_bufs[name] = buf
+        return buf
+
+    def separate_host(self, mix):
+        """The array-level body of separate() (mdx_separator.py:152-182) on HOST buffers: mix (2, N) float32 ndarray as prepare_mix returns it ->
+        (primary (N, 2), secondary (N, 2)) float32 ndarrays (views of pinned buffers owned by the plugin, valid until the next call).
+        One upload, the whole chunk loop on the device, one download per stem."""
+        self.initialize_model_settings()
+        mix = np.ascontiguousarray(mix, dtype=np.float32)
+        N = mix.shape[1]
+        stage = self._pinned("mix", (2, N))
+        stage.numpy()[...] = mix
+        mix_dev = stage.to(self.torch_device, non_blocking=True)
+        primary_dev, secondary_dev = self.engine.separate_device(mix_dev, self.normalization_threshold, self.amplification_threshold)
+        out_p, out_s = self._pinned("primary", (N, 2)), self._pinned("secondary", (N, 2))
+        out_p.copy_(primary_dev, non_blocking=True)
+        out_s.copy_(secondary_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out_p.numpy(), out_s.numpy()
+
     def separate(self, audio_file_path, custom_output_names=None):
         self.audio_file_path = audio_file_path
         self.audio_file_base = os.path.splitext(os.path.basename(audio_file_path))[0]
-        self.initialize_model_settings()
         mix = self.prepare_mix(self.audio_file_path)
-        mix_dev = torch.as_tensor(np.ascontiguousarray(mix, dtype=np.float32)).to(self.torch_device)
-        primary_dev, secondary_dev = self.engine.separate_device(mix_dev, self.normalization_threshold, self.amplification_threshold)
         if self.invert_using_spec:
             raise NotImplementedError("invert_using_spec=True (spec_utils.invert_stem) is not part of the accelerated path yet")
+        primary, secondary = self.separate_host(mix)
         if not isinstance(self.primary_source, np.ndarray):
-            self.primary_source = primary_dev.cpu().numpy()
+            self.primary_source = np.array(primary)
         if not isinstance(self.secondary_source, np.ndarray):
-            self.secondary_source = secondary_dev.cpu().numpy()
+            self.secondary_source = np.array(secondary)
 
         output_files = []
         for is_secondary in (True, False):  # secondary stem file first, then primary (:185-197)

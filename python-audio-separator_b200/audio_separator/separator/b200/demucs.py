@@ -21,6 +21,7 @@ from ._lib import LAYOUT_CFT, check, lib
 from .engine import StftPlan, _ptr, _require_cuda, _stream
 
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+_DCONV_FUSED_HID = (4, 6, 8, 12, 16, 24, 32, 48)  # hidden widths b200sep_dconv_f32 is instantiated for
 
 
 @dataclass
@@ -237,6 +238,8 @@ class HTDemucsNet:
         st = {k: np.asarray(v, dtype=np.float32) for k, v in state.items()}
         self._check_structure(st)
         for name, a in st.items():
+            if ".dconv.layers." in name and name.endswith((".0.weight", ".3.weight")):  # the fused DConv kernel takes the plain (out, in[, k]) matrices
+                self.W[name + ":raw"] = torch.from_numpy(np.ascontiguousarray(a.reshape(a.shape[0], -1) if name.endswith(".3.weight") else a)).to(self.device)
             if name.endswith("conv_tr.weight"):
                 a = block_convtr_weight(a.reshape(a.shape[0], a.shape[1], cfg.kernel_size), cfg.stride)
             elif name.endswith(".weight") and a.ndim >= 3 and "crosstransformer" not in name:
@@ -288,10 +291,21 @@ class HTDemucsNet:
         C_ = x.shape[1]
         if f"{prefix}.dconv.layers.0.0.weight" not in W:  # dconv_mode without DConv on this side (hdemucs.py:83-84, :268-269)
             return x
+        B, _, Fr, L = x.shape
         for d in range(self.cfg.dconv_depth):
             p = f"{prefix}.dconv.layers.{d}"
             dil = 2**d
             hid = W[f"{p}.0.bias"].numel()
+            if hid in _DCONV_FUSED_HID and C_ * 2 * (-(-hid // 4) * 4 + 4) * 4 <= 200 * 1024:
+                # one fused residual layer (csrc/dconv_fused.cu); the C -> hid convolution of the widest layers stays on the tensor cores
+                u_in = None
+                if 3 * C_ * (-(-hid // 4) * 4) * 4 > 200 * 1024:
+                    u_in = conv2d(x, W[f"{p}.0.weight"], W[f"{p}.0.bias"], hid, (1, 3), p=(0, dil), dw=dil)
+                work = _new((lib.b200sep_dconv_work_floats(B, C_, Fr, L, hid),), x)
+                check(lib.b200sep_dconv_f32(_ptr(x), _ptr(x), _ptr(W[f"{p}.0.weight:raw"]), _ptr(W[f"{p}.0.bias"]), _ptr(W[f"{p}.1.weight"]), _ptr(W[f"{p}.1.bias"]),
+                                            _ptr(W[f"{p}.3.weight:raw"]), _ptr(W[f"{p}.3.bias"]), _ptr(W[f"{p}.4.weight"]), _ptr(W[f"{p}.4.bias"]), _ptr(W[f"{p}.6.scale"]),
+                                            B, C_, Fr, L, hid, dil, _ptr(u_in) if u_in is not None else None, _ptr(work), _stream()), "dconv_f32")
+                continue
             h = conv2d(x, W[f"{p}.0.weight"], W[f"{p}.0.bias"], hid, (1, 3), p=(0, dil), dw=dil)
             groupnorm1(h, W[f"{p}.1.weight"], W[f"{p}.1.bias"], ACT_GELU)
             h = conv2d(h, W[f"{p}.3.weight"], W[f"{p}.3.bias"], 2 * C_, (1, 1))

@@ -268,8 +268,8 @@ class ShardedMdxEngine(MdxEngine):
             lo, hi = min(lo, a - self.trim), max(hi, b - self.trim)
         n_part, n_q = max(hi - lo, 0), sh.q1 - sh.q0
         part = torch.zeros((2, max(n_part, 1)), dtype=torch.float32, device=self.device)
-        if n_part:
-            part[:, :n_part].copy_(mix_host[:, lo:hi], non_blocking=True)
+        for c in range(2 if n_part else 0):  # contiguous row slices: true async copies out of the pinned buffer
+            part[c, :n_part].copy_(mix_host[c, lo:hi], non_blocking=True)
         peak = torch.zeros(1, dtype=torch.float32, device=self.device)
         if n_q > 0:  # peak over the DISJOINT partition [q0, q1)
             own = part[:, sh.q0 - lo : sh.q1 - lo].contiguous()

@@ -22,6 +22,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
+#include <tuple>
 #include <vector>
 
 #include "common.cuh"
@@ -35,11 +38,14 @@ constexpr int kEpiParts = 2;  // epilogue warps per TMEM lane quadrant: the epil
 constexpr int kUmmaThreads = 64 + 128 * kEpiParts;  // warp 0 TMA, warp 1 MMA, then 4 * kEpiParts epilogue warps
 constexpr int kMaxChannels = 1024;  // per-channel scale/shift staged in shared memory (conv modes)
 constexpr int kTileM = 128;
-constexpr int kConvStride = 120;  // output pixels per conv tile (multiple of 8: TMA box starts must be 16-byte aligned)
+constexpr int kConvStride = 112;  // output pixels per 3x3 tile: TMEM rows 8..119 of the 128 loaded pixels [f0 - 8, f0 + 120), so that loads AND stores start 16-byte aligned
 
 struct UmmaParams {
   int mode;  // 0 GEMM, 1 CONV3x3, 2 UP (ConvTranspose2d k2 s2), 3 DOWN (Conv2d k2 s2), 4 PW (Conv2d 1x1)
   int f_stride, t_mul, t_off;  // implicit-GEMM addressing: tile f0 = blockIdx.x*f_stride, input row = t*t_mul + r + t_off
+  int f_off;                   // first input pixel of a tile = f0 + f_off (CONV3x3: -8, so that the 112 outputs of a tile start 16-byte aligned)
+  int n_sbuf;                  // CONV3x3: output staging buffers per epilogue half (2 when shared memory allows)
+  int cluster;                 // conv modes: CTAs per cluster walking tiles of the same weight tile in lockstep; each loads 1/cluster of every B stage and multicasts it
   int n_tile, n_total, tmem_cols;
   int num_iters, ksteps, stages;
   int dbg;  // development switches from env B200SEP_DBG (0 in production): see launch()
@@ -105,6 +111,110 @@ __device__ __forceinline__ TileCoord decode_tile(const UmmaParams& p, int tile) 
   return c;
 }
 
+// ===== TMA producer (one thread): fills the shared-memory ring, continuous across the tiles of this CTA =====
+__device__ __forceinline__ void umma_producer_loop(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUtensorMap& tmB_hi, const CUtensorMap& tmB_lo,
+                                                   const UmmaParams& p, uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar) {
+  int s = 0;
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    const TileCoord tc = decode_tile(p, tile);
+    const int n0 = tc.n_idx * p.n_tile;
+    for (int i = 0; i < p.num_iters; ++i) {
+      ptx::mbar_wait(&empty_bar[s], phase ^ 1, 100 + i);
+      uint8_t* st = smem + (size_t)s * p.stage_bytes;
+      uint8_t* a_hi = st;
+      uint8_t* a_lo = st + p.a_bytes;
+      uint8_t* b_hi = st + 2 * p.a_bytes;
+      uint8_t* b_lo = b_hi + p.b_bytes;
+      ptx::mbar_arrive_expect_tx(&full_bar[s], ((p.dbg & 8) ? 0 : 2 * p.a_bytes) + ((p.dbg & 16) ? 0 : 2 * p.b_bytes));
+      if (p.mode == 0) {
+        const int k0 = i * 64;
+        if (!(p.dbg & 8)) {
+          ptx::tma_load_2d(a_hi, &tmA_hi, &full_bar[s], k0, tc.m0);
+          ptx::tma_load_2d(a_lo, &tmA_lo, &full_bar[s], k0, tc.m0);
+        }
+        if (!(p.dbg & 16)) {
+          ptx::tma_load_2d(b_hi, &tmB_hi, &full_bar[s], k0, n0);
+          ptx::tma_load_2d(b_lo, &tmB_lo, &full_bar[s], k0, n0);
+        }
+      } else {
+        const int r = i / p.n_chunks, chunk = i - r * p.n_chunks;
+        const int cf = tc.f0 + p.f_off, ct = tc.t * p.t_mul + r + p.t_off, cc = tc.b * p.Cin + chunk * p.kc;
+        const uint32_t box = (uint32_t)p.kc * 128u;
+        if (!(p.dbg & 8)) {
+          ptx::tma_load_3d(a_hi, &tmA_hi, &full_bar[s], cf, ct, cc);
+          ptx::tma_load_3d(a_hi + box, &tmA_hi, &full_bar[s], cf + 64, ct, cc);
+          ptx::tma_load_3d(a_lo, &tmA_lo, &full_bar[s], cf, ct, cc);
+          ptx::tma_load_3d(a_lo + box, &tmA_lo, &full_bar[s], cf + 64, ct, cc);
+        }
+        const size_t woff = ((size_t)tc.n_idx * p.num_iters + i) * (size_t)(p.b_bytes / 2);
+        if (p.cluster > 1) {
+          // the CTAs of a cluster are at the same (weight tile, iteration): this one fetches its 1/cluster share of the stage for all of them
+          const uint32_t slice = p.b_bytes / (uint32_t)p.cluster, off = ptx::cluster_ctarank() * slice;
+          const uint16_t mask = (uint16_t)((1u << p.cluster) - 1u);
+          ptx::bulk_load_1d_multicast(b_hi + off, p.wb_hi + woff + off / 2, slice, &full_bar[s], mask);
+          ptx::bulk_load_1d_multicast(b_lo + off, p.wb_lo + woff + off / 2, slice, &full_bar[s], mask);
+        } else if (!(p.dbg & 16)) {
+          ptx::bulk_load_1d(b_hi, p.wb_hi + woff, p.b_bytes, &full_bar[s]);
+          ptx::bulk_load_1d(b_lo, p.wb_lo + woff, p.b_bytes, &full_bar[s]);
+        }
+      }
+      if (++s == p.stages) {
+        s = 0;
+        phase ^= 1;
+      }
+    }
+  }
+}
+
+// ===== MMA issuer (one thread): three bf16 UMMAs per k-step into one of two TMEM accumulators =====
+__device__ __forceinline__ void umma_mma_loop(const UmmaParams& p, uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar, uint64_t* tmem_full_bar,
+                                              uint64_t* tmem_empty_bar, uint32_t tmem_base, uint32_t acc_stride) {
+  const uint32_t idesc = ptx::instr_desc_bf16(kTileM, p.n_tile, p.mode != 0 ? 1 : 0, 0);
+  int s = 0, acc = 0;
+  uint32_t phase = 0, acc_phase = 0;
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, 400 + acc);  // epilogue has drained this accumulator
+    ptx::tc_fence_after();
+    const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_stride;
+    for (int i = 0; i < p.num_iters; ++i) {
+      ptx::mbar_wait(&full_bar[s], phase, 200 + i);
+      ptx::tc_fence_after();
+      const uint32_t st = ptx::smem_u32(smem + (size_t)s * p.stage_bytes);
+      const uint32_t a_hi = st, a_lo = st + p.a_bytes, b_hi = st + 2 * p.a_bytes, b_lo = b_hi + p.b_bytes;
+      for (int j = 0; j < ((p.dbg & 4) ? 0 : p.ksteps); ++j) {
+        uint64_t dah, dal, dbh, dbl;
+        if (p.mode == 0) {
+          dah = ptx::smem_desc(a_hi + j * 32, 16, 1024, ptx::kLayoutSW128);
+          dal = ptx::smem_desc(a_lo + j * 32, 16, 1024, ptx::kLayoutSW128);
+          dbh = ptx::smem_desc(b_hi + j * 32, 16, 1024, ptx::kLayoutSW128);
+          dbl = ptx::smem_desc(b_lo + j * 32, 16, 1024, ptx::kLayoutSW128);
+        } else {
+          const uint32_t lbo = (uint32_t)p.kc * 128u;  // next 64 pixels (second TMA box)
+          dah = ptx::smem_desc(a_hi + j * 2048, lbo, 1024, ptx::kLayoutSW128);
+          dal = ptx::smem_desc(a_lo + j * 2048, lbo, 1024, ptx::kLayoutSW128);
+          const uint32_t bstep = (uint32_t)p.n_tile * 32u;  // one [n_tile][16] block of 8x8 core matrices
+          dbh = ptx::smem_desc(b_hi + j * bstep, 128, 256, ptx::kLayoutNone);
+          dbl = ptx::smem_desc(b_lo + j * bstep, 128, 256, ptx::kLayoutNone);
+        }
+        ptx::umma_bf16(d_tmem, dah, dbh, idesc, (i | j) != 0 ? 1u : 0u);
+        ptx::umma_bf16(d_tmem, dah, dbl, idesc, 1u);
+        ptx::umma_bf16(d_tmem, dal, dbh, idesc, 1u);
+      }
+      // frees the smem stage once these MMAs have read it -- in every CTA of the cluster when the stage was filled by multicast
+      if (p.cluster > 1) ptx::umma_commit_multicast(&empty_bar[s], (uint16_t)((1u << p.cluster) - 1u));
+      else ptx::umma_commit(&empty_bar[s]);
+      if (++s == p.stages) {
+        s = 0;
+        phase ^= 1;
+      }
+    }
+    ptx::umma_commit(&tmem_full_bar[acc]);
+    acc ^= 1;
+    if (acc == 0) acc_phase ^= 1;
+  }
+}
+
 // Persistent kernel: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ...  Three pipelines run
 // concurrently: TMA producer -> smem ring (full/empty mbarriers, continuous across tiles), MMA issuer -> one of two TMEM
 // accumulators (tmem_full/tmem_empty), epilogue warps draining the other accumulator.
@@ -122,14 +232,13 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   float* sc_s = reinterpret_cast<float*>(tmem_slot + 4);  // conv modes: folded BatchNorm scale / shift per output channel
   float* sh_s = sc_s + kMaxChannels;
-  float* edge_base = sh_s + kMaxChannels;  // CONV3x3: [2 acc][2][4 quadrants][n_c] rows exchanged between epilogue warps
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], p.cluster > 1 ? p.cluster : 1);
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
@@ -152,104 +261,15 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (p.cluster > 1) ptx::cluster_sync();  // every CTA's barriers exist before a peer multicasts into them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t acc_stride = (uint32_t)p.tmem_cols / 2;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      int s = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(p, tile);
-        const int n0 = tc.n_idx * p.n_tile;
-        for (int i = 0; i < p.num_iters; ++i) {
-          ptx::mbar_wait(&empty_bar[s], phase ^ 1, 100 + i);
-          uint8_t* st = smem + (size_t)s * p.stage_bytes;
-          uint8_t* a_hi = st;
-          uint8_t* a_lo = st + p.a_bytes;
-          uint8_t* b_hi = st + 2 * p.a_bytes;
-          uint8_t* b_lo = b_hi + p.b_bytes;
-          ptx::mbar_arrive_expect_tx(&full_bar[s], ((p.dbg & 8) ? 0 : 2 * p.a_bytes) + ((p.dbg & 16) ? 0 : 2 * p.b_bytes));
-          if (p.mode == 0) {
-            const int k0 = i * 64;
-            if (!(p.dbg & 8)) {
-              ptx::tma_load_2d(a_hi, &tmA_hi, &full_bar[s], k0, tc.m0);
-              ptx::tma_load_2d(a_lo, &tmA_lo, &full_bar[s], k0, tc.m0);
-            }
-            if (!(p.dbg & 16)) {
-              ptx::tma_load_2d(b_hi, &tmB_hi, &full_bar[s], k0, n0);
-              ptx::tma_load_2d(b_lo, &tmB_lo, &full_bar[s], k0, n0);
-            }
-          } else {
-            const int r = i / p.n_chunks, chunk = i - r * p.n_chunks;
-            const int cf = tc.f0, ct = tc.t * p.t_mul + r + p.t_off, cc = tc.b * p.Cin + chunk * p.kc;
-            const uint32_t box = (uint32_t)p.kc * 128u;
-            if (!(p.dbg & 8)) {
-              ptx::tma_load_3d(a_hi, &tmA_hi, &full_bar[s], cf, ct, cc);
-              ptx::tma_load_3d(a_hi + box, &tmA_hi, &full_bar[s], cf + 64, ct, cc);
-              ptx::tma_load_3d(a_lo, &tmA_lo, &full_bar[s], cf, ct, cc);
-              ptx::tma_load_3d(a_lo + box, &tmA_lo, &full_bar[s], cf + 64, ct, cc);
-            }
-            const size_t woff = ((size_t)tc.n_idx * p.num_iters + i) * (size_t)(p.b_bytes / 2);
-            if (!(p.dbg & 16)) {
-              ptx::bulk_load_1d(b_hi, p.wb_hi + woff, p.b_bytes, &full_bar[s]);
-              ptx::bulk_load_1d(b_lo, p.wb_lo + woff, p.b_bytes, &full_bar[s]);
-            }
-          }
-          if (++s == p.stages) {
-            s = 0;
-            phase ^= 1;
-          }
-        }
-      }
-    }
+    if (lane == 0) umma_producer_loop(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p, smem, full_bar, empty_bar);
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      const uint32_t idesc = ptx::instr_desc_bf16(kTileM, p.n_tile, p.mode != 0 ? 1 : 0, 0);
-      int s = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, 400 + acc);  // epilogue has drained this accumulator
-        ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_stride;
-        for (int i = 0; i < p.num_iters; ++i) {
-          ptx::mbar_wait(&full_bar[s], phase, 200 + i);
-          ptx::tc_fence_after();
-          const uint32_t st = ptx::smem_u32(smem + (size_t)s * p.stage_bytes);
-          const uint32_t a_hi = st, a_lo = st + p.a_bytes, b_hi = st + 2 * p.a_bytes, b_lo = b_hi + p.b_bytes;
-          for (int j = 0; j < ((p.dbg & 4) ? 0 : p.ksteps); ++j) {
-            uint64_t dah, dal, dbh, dbl;
-            if (p.mode == 0) {
-              dah = ptx::smem_desc(a_hi + j * 32, 16, 1024, ptx::kLayoutSW128);
-              dal = ptx::smem_desc(a_lo + j * 32, 16, 1024, ptx::kLayoutSW128);
-              dbh = ptx::smem_desc(b_hi + j * 32, 16, 1024, ptx::kLayoutSW128);
-              dbl = ptx::smem_desc(b_lo + j * 32, 16, 1024, ptx::kLayoutSW128);
-            } else {
-              const uint32_t lbo = (uint32_t)p.kc * 128u;  // next 64 pixels (second TMA box)
-              dah = ptx::smem_desc(a_hi + j * 2048, lbo, 1024, ptx::kLayoutSW128);
-              dal = ptx::smem_desc(a_lo + j * 2048, lbo, 1024, ptx::kLayoutSW128);
-              const uint32_t bstep = (uint32_t)p.n_tile * 32u;  // one [n_tile][16] block of 8x8 core matrices
-              dbh = ptx::smem_desc(b_hi + j * bstep, 128, 256, ptx::kLayoutNone);
-              dbl = ptx::smem_desc(b_lo + j * bstep, 128, 256, ptx::kLayoutNone);
-            }
-            ptx::umma_bf16(d_tmem, dah, dbh, idesc, (i | j) != 0 ? 1u : 0u);
-            ptx::umma_bf16(d_tmem, dah, dbl, idesc, 1u);
-            ptx::umma_bf16(d_tmem, dal, dbh, idesc, 1u);
-          }
-          ptx::umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
-          if (++s == p.stages) {
-            s = 0;
-            phase ^= 1;
-          }
-        }
-        ptx::umma_commit(&tmem_full_bar[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-      }
-    }
+    if (lane == 0) umma_mma_loop(p, smem, full_bar, empty_bar, tmem_full_bar, tmem_empty_bar, tmem_base, acc_stride);
   } else {
     // ===== epilogue: TMEM -> registers -> BN/ReLU(/+res, *skip) -> split into bf16 hi/lo -> global =====
     // Eight warps: warp w may only touch TMEM lanes 32*(w%4)..+31, so two warps share each lane quadrant and split
@@ -494,106 +514,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
             }
           }
         }
-      } else {
-        // 3x3: P_dx[m][co] sits in column dx*n_c + co of TMEM lane m.  out[f0+j] = P_0[j-1] + P_1[j] + P_2[j+1].
-        constexpr int CW = 8;
-        const int nc = p.n_c;
-        float* edge = edge_base + acc * 8 * nc;
-        float* edge0 = edge + q * nc;        // this warp's row 32q+31 of P_0 (needed by lane 0 of quadrant q+1)
-        float* edge2 = edge + (4 + q) * nc;  // this warp's row 32q    of P_2 (needed by lane 31 of quadrant q-1)
-        for (int ch = ch_begin; ch < ch_end; ++ch) {
-          const int c0 = ch * CW;
-          uint32_t v0[CW], v2[CW];
-          ptx::tmem_ld8(trow + (uint32_t)c0, v0);
-          ptx::tmem_ld8(trow + (uint32_t)(2 * nc + c0), v2);
-          ptx::tmem_ld_wait();
-          if (lane == 31) {
-#pragma unroll
-            for (int j = 0; j < CW; ++j) edge0[c0 + j] = __uint_as_float(v0[j]);
-          }
-          if (lane == 0) {
-#pragma unroll
-            for (int j = 0; j < CW; ++j) edge2[c0 + j] = __uint_as_float(v2[j]);
-          }
-        }
-        // the four warps that own this column half exchange their boundary rows (named barrier 1 or 2, 128 threads)
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
-        const float* left = edge + (q - 1) * nc;       // valid for q > 0
-        const float* right = edge + (4 + q + 1) * nc;  // valid for q < 3
-        const int f = f0 + m;
-        const int j_lo = (f0 == 0) ? 0 : 1;
-        const bool row_ok = (m >= j_lo) && (m < kConvStride + 1) && (f < p.F);
-        const size_t plane = (size_t)p.T * p.F;
-        const size_t base = ((size_t)b * p.out_c_total + p.out_c_off + n0) * plane + (size_t)t * p.F + f;
-        const size_t rbase = ((size_t)b * p.Cout + n0) * plane + (size_t)t * p.F + f;  // residual / multiplier: (B, Cout, T, F)
-        for (int ch = ch_begin; ch < ch_end; ++ch) {
-          const int c0 = ch * CW;
-          uint32_t v0[CW], v1[CW], v2[CW];
-          ptx::tmem_ld8(trow + (uint32_t)c0, v0);
-          ptx::tmem_ld8(trow + (uint32_t)(nc + c0), v1);
-          ptx::tmem_ld8(trow + (uint32_t)(2 * nc + c0), v2);
-          ptx::tmem_ld_wait();
-          float x[CW];
-#pragma unroll
-          for (int j = 0; j < CW; ++j) {
-            const float a = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[j]), 1);    // P_0 of row m-1
-            const float c = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[j]), 1);  // P_2 of row m+1
-            x[j] = __uint_as_float(v1[j]) + ((lane == 0) ? 0.f : a) + ((lane == 31) ? 0.f : c);
-          }
-          // rows at a warp edge take their neighbour from the exchange buffer (one divergent region per group);
-          // m == 0 with f0 == 0 is the left zero padding, m == 0 otherwise and m == 127 are never output rows
-          if (lane == 0 && q > 0) {
-#pragma unroll
-            for (int j = 0; j < CW; ++j) x[j] += left[c0 + j];
-          }
-          if (lane == 31 && q < 3) {
-#pragma unroll
-            for (int j = 0; j < CW; ++j) x[j] += right[c0 + j];
-          }
-          // per-channel affine: read the coefficients before the first global store (vector LDS, no per-column stall)
-          float sc[CW], sh[CW];
-#pragma unroll
-          for (int j4 = 0; j4 < CW / 4; ++j4) {
-            const float4 s4 = *reinterpret_cast<const float4*>(&sc_s[n0 + c0 + 4 * j4]);
-            const float4 h4 = *reinterpret_cast<const float4*>(&sh_s[n0 + c0 + 4 * j4]);
-            sc[4 * j4] = s4.x; sc[4 * j4 + 1] = s4.y; sc[4 * j4 + 2] = s4.z; sc[4 * j4 + 3] = s4.w;
-            sh[4 * j4] = h4.x; sh[4 * j4 + 1] = h4.y; sh[4 * j4 + 2] = h4.z; sh[4 * j4 + 3] = h4.w;
-          }
-          if (row_ok) {
-            // The activation and the optional residual / multiplier are decided once per group, outside the column loops (no per-column
-            // tests, no dummy "+0" / "*1" arithmetic); every load of the group is still issued before the first store.
-            float y[CW];
-#pragma unroll
-            for (int j = 0; j < CW; ++j) y[j] = fmaf(x[j], sc[j], sh[j]);
-            act_group(y, p.act);
-            if (p.res_hi) {
-#pragma unroll
-              for (int j = 0; j < CW; ++j) {
-                const size_t ro = rbase + (size_t)(c0 + j) * plane;
-                y[j] += __bfloat162float(p.res_hi[ro]) + __bfloat162float(p.res_lo[ro]);
-              }
-            }
-            if (p.mul_hi) {
-#pragma unroll
-              for (int j = 0; j < CW; ++j) {
-                const size_t ro = rbase + (size_t)(c0 + j) * plane;
-                y[j] *= __bfloat162float(p.mul_hi[ro]) + __bfloat162float(p.mul_lo[ro]);
-              }
-            }
-            bf16* ph = p.out_hi + base + (size_t)c0 * plane;
-            bf16* pl = p.out_lo + base + (size_t)c0 * plane;
-#pragma unroll
-            for (int j = 0; j < CW; ++j) {
-              bf16 h, l;
-              split_store2(y[j], h, l);
-              *ph = h;  // 32 lanes -> 32 consecutive pixels: one 64-byte segment per plane
-              *pl = l;
-              ph += plane;
-              pl += plane;
-            }
-          }
-        }
-      }
+      }  // (CONV3x3 has its own kernel, umma_conv3_kernel)
       // this warp is done reading the accumulator: hand it back to the MMA issuer
       ptx::tc_fence_before();
       __syncwarp();
@@ -604,6 +525,183 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (p.cluster > 1) ptx::cluster_sync();  // no CTA leaves while a peer may still signal its barriers
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// CONV3x3 kernel.  Same producer / MMA pipelines as umma_pair_kernel; the epilogue is specialised (NC = output channels per CTA):
+//   * a tile loads the 128 pixels [f0 - 8, f0 + 120) (TMA zero-fills the left / right padding) and produces the 112 outputs
+//     [f0, f0 + 112) = TMEM rows 8..119, so both the loads and the STORES start 16-byte aligned (TMA faults on any other
+//     innermost coordinate, measured: tests/dev/tma_probe2.cu);
+//   * each of the 8 epilogue warps pulls ALL its accumulator columns (3 * NC/2) into registers with one tcgen05.wait::ld and
+//     hands the accumulator back to the MMA issuer at once -- the arithmetic below overlaps the next tiles' MMAs;
+//   * out[j] = P_0[j-1] + P_1[j] + P_2[j+1] by warp shuffles, the three warp-boundary rows through a 128-thread exchange
+//     (no second pass over TMEM), folded BatchNorm + activation (+ residual, * multiplier), bf16 hi/lo split;
+//   * the tile is staged in shared memory as [channel][pixel] bf16 planes and written with two cp.async.bulk.tensor stores per half
+//     (UTMASTG): no per-thread global stores, no 64-bit address arithmetic, full 224-byte rows per channel.
+template <int NC>
+__global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                                                                     const __grid_constant__ CUtensorMap tmO_hi, const __grid_constant__ CUtensorMap tmO_lo,
+                                                                     const UmmaParams p) {
+  constexpr int H = NC / 2;                 // channels per epilogue warp
+  constexpr int kPlane = H * kConvStride;   // bf16 elements of one staged plane [H][112]
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  bf16* stage_out = reinterpret_cast<bf16*>(smem + (size_t)p.stages * p.stage_bytes);  // [n_sbuf][2 halves][hi, lo][H][112]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stage_out) + (size_t)p.n_sbuf * 4 * kPlane * sizeof(bf16));
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full_bar = empty_bar + p.stages;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* sc_s = reinterpret_cast<float*>(tmem_slot + 4);
+  float* sh_s = sc_s + kMaxChannels;
+  float* edge_base = sh_s + kMaxChannels;  // [2 halves][P_0 row 31 | P_2 row 0][4 quadrants][H]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], p.cluster > 1 ? p.cluster : 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full_bar[a], 1);
+      ptx::mbar_init(&tmem_empty_bar[a], 4 * kEpiParts);
+    }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tensormap(&tmA_hi);
+    ptx::prefetch_tensormap(&tmA_lo);
+    ptx::prefetch_tensormap(&tmO_hi);
+    ptx::prefetch_tensormap(&tmO_lo);
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
+    sc_s[i] = p.scale ? __ldg(&p.scale[i]) : 1.f;
+    sh_s[i] = p.shift ? __ldg(&p.shift[i]) : 0.f;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (p.cluster > 1) ptx::cluster_sync();  // every CTA's barriers exist before a peer multicasts into them
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc_stride = (uint32_t)p.tmem_cols / 2;
+
+  if (warp == 0) {
+    if (lane == 0) umma_producer_loop(tmA_hi, tmA_lo, tmA_hi, tmA_lo, p, smem, full_bar, empty_bar);
+  } else if (warp == 1) {
+    if (lane == 0) umma_mma_loop(p, smem, full_bar, empty_bar, tmem_full_bar, tmem_empty_bar, tmem_base, acc_stride);
+  } else {
+    const int q = warp & 3;           // TMEM lane quadrant
+    const int half = (warp - 2) >> 2;  // which NC/2 channels
+    const int m = q * 32 + lane;
+    const bool issuer = (q == 0) && (lane == 0);  // the thread of this half that owns the bulk store groups
+    const bool out_row = (m >= 8) && (m < 8 + kConvStride);
+    float* edge0 = edge_base + half * 8 * H;  // [q][H]: P_0 of row 32q+31
+    float* edge2 = edge0 + 4 * H;             // [q][H]: P_2 of row 32q
+    const int bar_a = 1 + 2 * half, bar_b = 2 + 2 * half;
+    int acc = 0, it = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const TileCoord tc = decode_tile(p, tile);
+      const int n0 = tc.n_idx * NC + half * H;  // first output channel of this warp
+      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase, 300 + acc);
+      ptx::tc_fence_after();
+      const uint32_t trow = tmem_base + (uint32_t)acc * acc_stride + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * H);
+      uint32_t v0[H], v1[H], v2[H];
+      ptx::tmem_ld_n<H>(trow, v0);
+      ptx::tmem_ld_n<H>(trow + NC, v1);
+      ptx::tmem_ld_n<H>(trow + 2 * NC, v2);
+      ptx::tmem_ld_wait();
+      // the accumulator now lives in registers: hand it back to the MMA issuer
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+      // boundary rows for the neighbouring quadrants
+      if (lane == 31) {
+#pragma unroll
+        for (int j = 0; j < H; j += 4) *reinterpret_cast<uint4*>(&edge0[q * H + j]) = make_uint4(v0[j], v0[j + 1], v0[j + 2], v0[j + 3]);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < H; j += 4) *reinterpret_cast<uint4*>(&edge2[q * H + j]) = make_uint4(v2[j], v2[j + 1], v2[j + 2], v2[j + 3]);
+      }
+      // the staging buffer of this tile must have been read out by the store issued n_sbuf tiles ago
+      if (issuer) {
+        if (p.n_sbuf == 2) ptx::bulk_wait_read<1>();
+        else ptx::bulk_wait_read<0>();
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_a) : "memory");
+      float x[H];
+#pragma unroll
+      for (int j = 0; j < H; ++j) {
+        const float a = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[j]), 1);    // P_0 of row m-1
+        const float c = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[j]), 1);  // P_2 of row m+1
+        x[j] = __uint_as_float(v1[j]) + ((lane == 0) ? 0.f : a) + ((lane == 31) ? 0.f : c);
+      }
+      if (lane == 0 && q > 0) {
+#pragma unroll
+        for (int j = 0; j < H; j += 4) {
+          const float4 e = *reinterpret_cast<const float4*>(&edge0[(q - 1) * H + j]);
+          x[j] += e.x; x[j + 1] += e.y; x[j + 2] += e.z; x[j + 3] += e.w;
+        }
+      }
+      if (lane == 31 && q < 3) {
+#pragma unroll
+        for (int j = 0; j < H; j += 4) {
+          const float4 e = *reinterpret_cast<const float4*>(&edge2[(q + 1) * H + j]);
+          x[j] += e.x; x[j + 1] += e.y; x[j + 2] += e.z; x[j + 3] += e.w;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < H; j += 4) {
+        const float4 s4 = *reinterpret_cast<const float4*>(&sc_s[n0 + j]);
+        const float4 h4 = *reinterpret_cast<const float4*>(&sh_s[n0 + j]);
+        x[j] = fmaf(x[j], s4.x, h4.x); x[j + 1] = fmaf(x[j + 1], s4.y, h4.y); x[j + 2] = fmaf(x[j + 2], s4.z, h4.z); x[j + 3] = fmaf(x[j + 3], s4.w, h4.w);
+      }
+      act_group(x, p.act);
+      const int f = tc.f0 + m - 8;
+      if ((p.res_hi || p.mul_hi) && out_row && f < p.F) {
+        const size_t plane = (size_t)p.T * p.F;
+        const size_t rbase = ((size_t)tc.b * p.Cout + n0) * plane + (size_t)tc.t * p.F + f;  // residual / multiplier: (B, Cout, T, F)
+        if (p.res_hi) {
+#pragma unroll
+          for (int j = 0; j < H; ++j) x[j] += __bfloat162float(p.res_hi[rbase + (size_t)j * plane]) + __bfloat162float(p.res_lo[rbase + (size_t)j * plane]);
+        }
+        if (p.mul_hi) {
+#pragma unroll
+          for (int j = 0; j < H; ++j) x[j] *= __bfloat162float(p.mul_hi[rbase + (size_t)j * plane]) + __bfloat162float(p.mul_lo[rbase + (size_t)j * plane]);
+        }
+      }
+      bf16* s_hi = stage_out + (size_t)(((p.n_sbuf == 2) ? (it & 1) : 0) * 2 + half) * 2 * kPlane;
+      bf16* s_lo = s_hi + kPlane;
+      if (out_row) {
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+          bf16 h, l;
+          split_store2(x[j], h, l);
+          s_hi[j * kConvStride + (m - 8)] = h;
+          s_lo[j * kConvStride + (m - 8)] = l;
+        }
+      }
+      ptx::fence_proxy_async();
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_b) : "memory");
+      if (issuer) {
+        const int cc = tc.b * p.out_c_total + p.out_c_off + n0;
+        ptx::tma_store_3d(&tmO_hi, s_hi, tc.f0, tc.t, cc);
+        ptx::tma_store_3d(&tmO_lo, s_lo, tc.f0, tc.t, cc);
+        ptx::bulk_commit();
+      }
+    }
+    if (issuer) ptx::bulk_wait_all();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (p.cluster > 1) ptx::cluster_sync();  // no CTA leaves while a peer may still signal its barriers
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
@@ -627,7 +725,8 @@ static PFN_encodeTiled get_encode() {
 }
 
 // bf16 tensor map, SWIZZLE_128B, zero OOB fill.  dims/box innermost first; strides in BYTES for dims 1..rank-1.
-static int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+static int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -642,7 +741,7 @@ static int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t
     if (i > 0) gs[i - 1] = strides_bytes[i - 1];
   }
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (CUresult %d) rank=%d dims=[%llu,%llu,%llu] box=[%u,%u,%u]", (int)r, rank, (unsigned long long)dims[0],
               (unsigned long long)(rank > 1 ? dims[1] : 0), (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0);
@@ -665,6 +764,61 @@ static int num_sms() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kNumSMs;
   }
   return n;
+}
+
+// Cluster size for the weight multicast (conv modes): the CTAs of a cluster must sit on the same weight tile at every step of their tile walk, which
+// holds when tile ids, the grid and the number of tiles per weight tile are all multiples of the cluster size.  B200SEP_CLUSTER overrides (1 = off).
+static int choose_cluster(const UmmaParams& p) {
+  static int want = -1;
+  if (want < 0) {
+    const char* e = getenv("B200SEP_CLUSTER");
+    want = e ? atoi(e) : 4;
+    if (want != 1 && want != 2 && want != 4 && want != 8) want = 4;
+  }
+  if (p.mode == 0) return 1;
+  for (int cs = want; cs > 1; cs >>= 1)
+    if (p.num_tiles % cs == 0 && (p.n_ftiles * p.t_tiles) % cs == 0 && p.b_bytes % (16u * cs) == 0) return cs;
+  return 1;
+}
+
+// Persistent launch: one CTA per SM, as clusters of `cs` when the weight operand is multicast (the grid is then the number of co-resident clusters x cs).
+template <class Kernel, class... Args>
+static int launch_persistent(Kernel kernel, int cs, int num_tiles, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(kUmmaThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int grid = std::min(num_tiles, num_sms());
+  if (cs > 1) {
+    static std::map<std::tuple<const void*, int, size_t>, int> cache;
+    static std::mutex mu;
+    int nclusters = 0;
+    {
+      std::lock_guard<std::mutex> lock(mu);
+      const auto key = std::make_tuple((const void*)kernel, cs, smem);
+      auto it = cache.find(key);
+      if (it == cache.end()) {
+        cfg.gridDim = dim3((unsigned)(num_sms() / cs * cs));
+        B2_CUDA(cudaOccupancyMaxActiveClusters(&nclusters, kernel, &cfg));
+        cache[key] = nclusters;
+      } else {
+        nclusters = it->second;
+      }
+    }
+    B2_CHECK_ARG(nclusters >= 1, "umma: no cluster of %d CTAs with %zu bytes of shared memory can be resident", cs, smem);
+    grid = std::min(num_tiles, nclusters * cs) / cs * cs;
+  }
+  cfg.gridDim = dim3((unsigned)grid);
+  B2_CUDA(cudaLaunchKernelEx(&cfg, kernel, args...));
+  count_launch();
+  return B200SEP_OK;
 }
 
 // `tiles` is the logical tile grid: GEMM (n tiles, m tiles, 1); conv modes (f tiles, output rows, batch * channel tiles).
@@ -694,10 +848,8 @@ static int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtens
     B2_CUDA(cudaFuncSetAttribute(umma_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const int grid = std::min(p.num_tiles, num_sms());
-  umma_pair_kernel<<<grid, kUmmaThreads, smem, st>>>(a_hi, a_lo, b_hi, b_lo, p);
-  B2_LAUNCHED();
-  return B200SEP_OK;
+  p.cluster = choose_cluster(p);
+  return launch_persistent(umma_pair_kernel, p.cluster, p.num_tiles, smem, st, a_hi, a_lo, b_hi, b_lo, p);
 }
 
 bool umma_gemm_supported(int M, int N, int K) { return M >= 1 && N % 16 == 0 && K % 8 == 0 && N >= 16 && K >= 16; }
@@ -792,9 +944,46 @@ int umma_conv_run(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_lo, 
   return umma_conv_run_ex(pl, wb_hi, wb_lo, B, Cout, n_c, e, st);
 }
 
+// TMA store maps of a conv3x3 output: the (F, T, B * C_total) bf16 planes with a [112 px][1 row][NC/2 channels] box, no swizzle.  Encoding a map costs a few
+// microseconds on the host and the same activation buffers are written forward after forward, so the maps are cached by (plane address, geometry).
+struct StoreMapKey {
+  const void* base; int F, T, C, box_c;
+  bool operator<(const StoreMapKey& o) const { return std::tie(base, F, T, C, box_c) < std::tie(o.base, o.F, o.T, o.C, o.box_c); }
+};
+static int store_map(const void* base, int F, int T, int C, int box_c, CUtensorMap* out) {
+  static std::map<StoreMapKey, CUtensorMap> cache;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  const StoreMapKey key{base, F, T, C, box_c};
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    CUtensorMap m;
+    const uint64_t d[3] = {(uint64_t)F, (uint64_t)T, (uint64_t)C};
+    const uint64_t st[2] = {(uint64_t)F * 2, (uint64_t)T * F * 2};
+    const uint32_t bx[3] = {(uint32_t)kConvStride, 1, (uint32_t)box_c};
+    int rc = make_map(&m, base, 3, d, st, bx, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+    if (cache.size() > 4096) cache.clear();
+    it = cache.emplace(key, m).first;
+  }
+  *out = it->second;
+  return B200SEP_OK;
+}
+
+template <int NC>
+static int launch_conv3(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& o_hi, const CUtensorMap& o_lo, UmmaParams& p, size_t smem, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2_CUDA(cudaFuncSetAttribute(umma_conv3_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  p.cluster = choose_cluster(p);
+  return launch_persistent(umma_conv3_kernel<NC>, p.cluster, p.num_tiles, smem, st, a_hi, a_lo, o_hi, o_lo, p);
+}
+
 int umma_conv_run_ex(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_lo, int B, int Cout, int n_c, const UmmaEpilogue& e, cudaStream_t st) {
   UmmaParams p{};
-  p.mode = 1; p.f_stride = kConvStride; p.t_mul = 1; p.t_off = -1;
+  p.mode = 1; p.f_stride = kConvStride; p.f_off = -8; p.t_mul = 1; p.t_off = -1;
   p.n_c = n_c; p.n_tile = 3 * n_c; p.n_total = Cout;
   p.kc = pl.kc; p.n_chunks = pl.Cin / pl.kc;
   p.num_iters = 3 * p.n_chunks; p.ksteps = pl.kc / 16;
@@ -802,8 +991,40 @@ int umma_conv_run_ex(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_l
   p.T = pl.T; p.F = pl.F; p.Cin = pl.Cin; p.Cout = Cout; p.n_tiles = Cout / n_c;
   p.wb_hi = (const bf16*)wb_hi; p.wb_lo = (const bf16*)wb_lo;
   fill_epilogue(p, e, Cout);
-  dim3 grid(pl.F <= 1 ? 1 : cdiv(pl.F - 1, kConvStride), pl.T, B * p.n_tiles);
-  return launch(pl.a_hi, pl.a_lo, pl.a_hi, pl.a_lo, p, grid, st);
+  B2_CHECK_ARG(Cout <= kMaxChannels, "umma_conv: more than %d output channels", kMaxChannels);
+  B2_CHECK_ARG(e.out_f32 == nullptr, "umma_conv: 3x3 convolutions write pair tensors only");
+  p.stage_bytes = ((2 * p.a_bytes + 2 * p.b_bytes + 1023) / 1024) * 1024;
+  p.tmem_cols = 2 * pow2_cols(p.n_tile);
+  B2_CHECK_ARG(p.tmem_cols <= 512, "umma_conv: n_c=%d needs more than 512 TMEM columns", n_c);
+  p.n_ftiles = cdiv(pl.F, kConvStride);
+  p.t_tiles = pl.T;
+  p.num_tiles = p.n_ftiles * pl.T * B * p.n_tiles;
+  const size_t stage_plane = (size_t)(n_c / 2) * kConvStride * 2;  // bytes of one staged [n_c/2][112] bf16 plane
+  const size_t fixed = 1024 /*alignment slack*/ + 64 * sizeof(uint64_t) + 64 + 2 * kMaxChannels * sizeof(float) + (size_t)16 * (n_c / 2) * sizeof(float);
+  const size_t budget = 227 * 1024 - fixed;
+  p.n_sbuf = 2;
+  int stages = (int)((budget - 2 * 4 * stage_plane) / p.stage_bytes);
+  if (stages < 3) {  // deep layers with 80 KB stages: one staging buffer leaves room for the ring
+    p.n_sbuf = 1;
+    stages = (int)((budget - 4 * stage_plane) / p.stage_bytes);
+  }
+  if (stages > 8) stages = 8;
+  B2_CHECK_ARG(stages >= 2, "umma_conv: a pipeline stage of %u bytes does not fit twice in shared memory", p.stage_bytes);
+  p.stages = stages;
+  const size_t smem = (size_t)stages * p.stage_bytes + (size_t)p.n_sbuf * 4 * stage_plane + fixed;
+  CUtensorMap o_hi, o_lo;
+  int rc = store_map(p.out_hi, pl.F, pl.T, B * p.out_c_total, n_c / 2, &o_hi);
+  if (!rc) rc = store_map(p.out_lo, pl.F, pl.T, B * p.out_c_total, n_c / 2, &o_lo);
+  if (rc) return rc;
+  switch (n_c) {
+    case 16: return launch_conv3<16>(pl.a_hi, pl.a_lo, o_hi, o_lo, p, smem, st);
+    case 32: return launch_conv3<32>(pl.a_hi, pl.a_lo, o_hi, o_lo, p, smem, st);
+    case 48: return launch_conv3<48>(pl.a_hi, pl.a_lo, o_hi, o_lo, p, smem, st);
+    case 64: return launch_conv3<64>(pl.a_hi, pl.a_lo, o_hi, o_lo, p, smem, st);
+    case 80: return launch_conv3<80>(pl.a_hi, pl.a_lo, o_hi, o_lo, p, smem, st);
+  }
+  set_error("umma_conv: n_c=%d has no kernel instance", n_c);
+  return B200SEP_ERR_ARG;
 }
 
 static int pick_nc(int Cout, int mult, int limit) {  // largest n_c | Cout with mult*n_c <= limit and mult*n_c % 16 == 0

@@ -145,6 +145,40 @@ def test_gemm_f32_and_attention_pattern(dm):
     assert (dm.linear(x2.cuda(), w2.cuda(), None).cpu() - x2 @ w2.t()).abs().max() <= 2e-5
 
 
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("B,C,Fr,L,hid,dil,u_in", [(2, 48, 5, 336, 6, 1, False), (1, 96, 3, 130, 12, 2, False), (2, 48, 1, 5000, 6, 2, False), (1, 192, 2, 336, 24, 1, False),
+                                                  (1, 384, 2, 200, 48, 2, True), (1, 32, 1, 2500, 4, 1, False), (1, 64, 2, 77, 8, 2, False)])
+def test_fused_dconv_layer_vs_torch(dm, B, C, Fr, L, hid, dil, u_in):
+    """b200sep_dconv_f32 (csrc/dconv_fused.cu) against the operator-by-operator definition of one DConv residual layer (demucs.py:124-168), fp64 on the CPU."""
+    from audio_separator.separator.b200._lib import check, lib
+
+    g = torch.Generator().manual_seed(B * 7 + C + Fr + L + hid)
+    x = torch.randn(B, C, Fr, L, generator=g)
+    w0 = torch.randn(hid, C, 3, generator=g) / (3 * C) ** 0.5
+    b0 = torch.randn(hid, generator=g) * 0.1
+    g1, be1 = torch.rand(hid, generator=g) + 0.5, torch.randn(hid, generator=g) * 0.1
+    w3 = torch.randn(2 * C, hid, generator=g) / hid**0.5
+    b3 = torch.randn(2 * C, generator=g) * 0.1
+    g4, be4 = torch.rand(2 * C, generator=g) + 0.5, torch.randn(2 * C, generator=g) * 0.1
+    ls = torch.rand(C, generator=g) * 0.5
+    xs = x.double().permute(0, 2, 1, 3).reshape(B * Fr, C, L)  # one sample per (b, fr) row
+    u = F.conv1d(xs, w0.double(), b0.double(), padding=dil, dilation=dil)
+    h = F.gelu(F.group_norm(u, 1, g1.double(), be1.double(), eps=1e-5))
+    z = F.group_norm(F.conv1d(h, w3.double()[:, :, None], b3.double()), 1, g4.double(), be4.double(), eps=1e-5)
+    ref = (xs + ls.double()[None, :, None] * F.glu(z, dim=1)).reshape(B, Fr, C, L).permute(0, 2, 1, 3)
+    d = [t.cuda().contiguous() for t in (x, w0, b0, g1, be1, w3, b3, g4, be4, ls)]
+    y = torch.full_like(d[0], float("nan"))
+    uin = u.float().reshape(B, Fr, hid, L).permute(0, 2, 1, 3).contiguous().cuda() if u_in else None
+    work = torch.empty(lib.b200sep_dconv_work_floats(B, C, Fr, L, hid), device="cuda")
+    check(lib.b200sep_dconv_f32(d[0].data_ptr(), y.data_ptr(), *[t.data_ptr() for t in d[1:]], B, C, Fr, L, hid, dil, uin.data_ptr() if u_in else None, work.data_ptr(), None), "dconv_f32")
+    torch.cuda.synchronize()
+    assert torch.isfinite(y).all()
+    assert (y.cpu().double() - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+    # in place (y aliases x), as HTDemucsNet uses it
+    check(lib.b200sep_dconv_f32(d[0].data_ptr(), d[0].data_ptr(), *[t.data_ptr() for t in d[1:]], B, C, Fr, L, hid, dil, uin.data_ptr() if u_in else None, work.data_ptr(), None), "dconv_f32")
+    assert torch.equal(d[0], y)
+
+
 def test_meanstd_and_stats_ops(dm):
     from audio_separator.separator.b200._lib import check, lib
 
