@@ -275,8 +275,9 @@ def chunk_starts(n_samples: int, cfg: MDXConfig, is_match_mix=False):
     return L, step, list(range(0, L, step))
 
 
-def demix(mix: np.ndarray, cfg: MDXConfig, model_run, is_match_mix=False) -> np.ndarray:
-    """MDXSeparator.demix (mdx_separator.py:293-412): mix (2,N) float32 -> (2,N) float32."""
+def demix(mix: np.ndarray, cfg: MDXConfig, model_run, is_match_mix=False, only_chunks=None) -> np.ndarray:
+    """MDXSeparator.demix (mdx_separator.py:293-412): mix (2,N) float32 -> (2,N) float32.
+    only_chunks (bench.py's bounded CPU sample): process just these indices of the chunk grid (the result is then only meaningful where they cover)."""
     mix = np.asarray(mix, dtype=np.float32)
     N = mix.shape[-1]
     chunk = cfg.chunk_size
@@ -286,7 +287,9 @@ def demix(mix: np.ndarray, cfg: MDXConfig, model_run, is_match_mix=False) -> np.
     mixture[:, cfg.trim : cfg.trim + N] = mix  # mdx_separator.py:329
     result = np.zeros((1, 2, L), dtype=np.float32)
     divider = np.zeros((1, 2, L), dtype=np.float32)
-    for start in starts:
+    for ci, start in enumerate(starts):
+        if only_chunks is not None and ci not in only_chunks:
+            continue
         end = min(start + chunk, L)
         actual = end - start
         part = np.zeros((1, 2, chunk), dtype=np.float32)  # right zero-pad short last chunk, :363-366

@@ -27,6 +27,7 @@ class MDXSeparator(CommonSeparator):
         self.hop_length = arch_config.get("hop_length")
         self.enable_denoise = arch_config.get("enable_denoise")
         self.precision = int(arch_config.get("b200_precision", 1))  # 0 = fp32 SIMT, 1 = bf16x3 split tensor-core path
+        self.sharded = bool(arch_config.get("b200_sharded", False))  # one process per GPU (torch.distributed, nccl): time-shard every track over the ranks
 
         self.compensate = self.model_data["compensate"]
         self.dim_f = self.model_data["mdx_dim_f_set"]
@@ -63,7 +64,10 @@ class MDXSeparator(CommonSeparator):
         flat = mdx_weights.flatten_state(state, **hp)
         max_batch = max(1, int(self.batch_size))
         self.net = MdxNet(flat, dim_t=self.segment_size, max_batch=max_batch, precision=self.precision, **hp)
-        self.engine = MdxEngine(self.net, self.n_fft, self.hop_length, self.dim_f, self.segment_size, self.overlap, self.compensate, bool(self.enable_denoise), max_batch)
+        engine_cls = MdxEngine
+        if self.sharded:
+            from ..b200.sharded import ShardedMdxEngine as engine_cls
+        self.engine = engine_cls(self.net, self.n_fft, self.hop_length, self.dim_f, self.segment_size, self.overlap, self.compensate, bool(self.enable_denoise), max_batch)
         self.model_run = lambda spek: self.net.forward(torch.as_tensor(spek, dtype=torch.float32, device=self.torch_device))
 
     def initialize_model_settings(self):
@@ -100,17 +104,25 @@ class MDXSeparator(CommonSeparator):
         (primary (N, 2), secondary (N, 2)) float32 ndarrays (views of pinned buffers owned by the plugin, valid until the next call).
         One upload, the whole chunk loop on the device, one download per stem."""
         self.initialize_model_settings()
-        mix = np.ascontiguousarray(mix, dtype=np.float32)
-        N = mix.shape[1]
-        stage = self._pinned("mix", (2, N))
-        stage.numpy()[...] = mix
-        mix_dev = stage.to(self.torch_device, non_blocking=True)
+        # a page-locked tensor is uploaded by DMA as it is; a plain ndarray goes through the driver's staged copy (no extra host pass here either way)
+        src = mix if isinstance(mix, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(mix, dtype=np.float32))
+        N = src.shape[1]
+        mix_dev = src.to(self.torch_device, non_blocking=True)
         primary_dev, secondary_dev = self.engine.separate_device(mix_dev, self.normalization_threshold, self.amplification_threshold)
         out_p, out_s = self._pinned("primary", (N, 2)), self._pinned("secondary", (N, 2))
         out_p.copy_(primary_dev, non_blocking=True)
         out_s.copy_(secondary_dev, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return out_p.numpy(), out_s.numpy()
+
+    def separate_host_shared(self, mix_shared, out_primary, out_secondary):
+        """separate_host for the sharded plugin (one process per GPU): the arguments are page-locked host tensors MAPPED BY EVERY RANK -- mix (2, N),
+        stems (N, 2).  Each rank uploads the samples its chunks read and downloads the slice of both stems it finalised (b200/sharded.py), so the
+        host<->device traffic of one track is spread over all PCIe links.  Returns this rank's (h2d, d2h) bytes."""
+        if not self.sharded:
+            raise RuntimeError("separate_host_shared needs arch_config['b200_sharded'] and an initialised torch.distributed process group")
+        self.initialize_model_settings()
+        return self.engine.separate_host(mix_shared, out_primary, out_secondary, self.normalization_threshold, self.amplification_threshold)
 
     def separate(self, audio_file_path, custom_output_names=None):
         self.audio_file_path = audio_file_path

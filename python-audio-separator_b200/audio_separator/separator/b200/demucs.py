@@ -623,6 +623,20 @@ class DemucsEngine:
             return part
         return self.runner.gather_cols(part, [(N * r // self.world, N * (r + 1) // self.world) for r in range(self.world)], N)
 
+    def demix_host(self, mix_host: torch.Tensor, out_host: torch.Tensor, shift_offsets):
+        """End-to-end entry point on page-locked host tensors: mix_host (2, N) -> out_host (S, 2, N).  Sharded runs map the SAME two buffers in every rank:
+        each rank uploads the mix over its own PCIe link and downloads only the (S, 2, q1 - q0) slice it finalised -- no gather.  Returns this rank's (h2d, d2h) bytes."""
+        mix_d = mix_host.to(self.device, non_blocking=True)
+        N = mix_d.shape[1]
+        part = self.demix_device(mix_d, shift_offsets)
+        r0, r1 = self.out_range(N)
+        S = part.shape[0]
+        for s_ in range(S if r1 > r0 else 0):
+            for c in range(2):
+                out_host[s_, c, r0:r1].copy_(part[s_, c], non_blocking=True)  # contiguous row slices: true async copies
+        torch.cuda.current_stream().synchronize()
+        return int(mix_host.numel() * 4), int(part.numel() * 4)
+
     def demix(self, mix: np.ndarray, shift_offsets) -> np.ndarray:
         """Host arrays in and out: mix (2, N) -> sources (S, 2, N) (rank 0; None on the other ranks of a sharded run)."""
         mix_d = torch.from_numpy(np.ascontiguousarray(mix, dtype=np.float32)).to(self.device)

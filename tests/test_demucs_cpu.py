@@ -20,9 +20,10 @@ def test_oracle_matches_reference_golden(golden_dir):
     w = D.make_weights(cfg, seed=int(z["weights_seed"]))
     mix = M.synth_music(3 * cfg.seg_len, seed=int(z["mix_seed"]))
     y = D.forward(w, cfg, mix[None, :, : cfg.seg_len])
-    assert np.abs(y - z["forward_ref"]).max() <= 2e-5
+    # torch-CPU reductions are partitioned by thread count: seen up to ~2e-5 between an idle and a loaded host, so the gate is 5e-5 (1e-4 on audio is the contract)
+    assert np.abs(y - z["forward_ref"]).max() <= 5e-5
     ys = D.forward(w, cfg, mix[None, :, : cfg.seg_len - 1234])
-    assert ys.shape == z["forward_short_ref"].shape and np.abs(ys - z["forward_short_ref"]).max() <= 2e-5
+    assert ys.shape == z["forward_short_ref"].shape and np.abs(ys - z["forward_short_ref"]).max() <= 5e-5
     N = int(z["n_apply"])
     src = D.demix_demucs([lambda c: D.forward(w, cfg, c)], [[1.0] * 4], cfg, mix[:, :N], [[int(v) for v in z["shift_offsets"]]], 0.25)
     assert src.shape == (4, 2, N) and np.abs(src - z["demix_ref"]).max() <= 5e-5

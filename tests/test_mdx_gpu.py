@@ -251,6 +251,33 @@ def test_full_size_grid_against_oracle(eng):
     assert np.abs(got_half - 0.5 * got).max() < 1e-6  # linearity
 
 
+@pytest.mark.timeout(900)
+def test_baseline_config1_full_size_net_three_chunks_vs_oracle(eng):
+    """BASELINE configs[0]: 10 s of 44.1 kHz stereo through the WHOLE path at the Inst_HQ_3 sizes -- 3 overlapping chunks, the full-size ConvTDFNet
+    (16.7 M parameters), STFT / iSTFT 6144, Hann overlap-add, peak normalisation, secondary = mix - compensate * primary -- MdxEngine.separate_device
+    against oracle.separate_arrays (the reference's algorithm on the CPU), both arithmetic paths of the library.  Gate: 1e-4 max-abs per sample."""
+    from audio_separator.separator.b200 import mdx_weights
+
+    cfg = O.MDXConfig()
+    N = 441_000
+    assert eng.MdxEngine(None, cfg.n_fft, cfg.hop_length, cfg.dim_f, cfg.segment_size, cfg.overlap).grid(N)[2] == 3
+    w = O.make_convtdfnet_weights(cfg, seed=21, out_gain=0.05)
+    mix = O.synth_music(N, seed=1234)
+    torch.set_num_threads(min(32, os.cpu_count() or 8))
+    ref_p, ref_s = O.separate_arrays(mix, cfg, lambda s: O.convtdfnet_forward(w, cfg, s))
+    assert ref_p.shape == (N, 2) and float(np.abs(ref_p).max()) > 1e-3
+    hp = mdx_weights.infer_hparams_from_state(w)
+    flat = mdx_weights.flatten_state(w, **hp)
+    for precision, batch in ((1, 2), (0, 1)):
+        net = eng.MdxNet(flat, dim_t=cfg.dim_t, max_batch=batch, precision=precision, **hp)
+        e = eng.MdxEngine(net, cfg.n_fft, cfg.hop_length, cfg.dim_f, cfg.segment_size, cfg.overlap, cfg.compensate, batch_size=batch)
+        p, s = e.separate_device(dev(mix))
+        ep, es = maxabs(p.cpu().numpy(), ref_p), maxabs(s.cpu().numpy(), ref_s)
+        print(f"config 1, precision {precision}: max|gpu - oracle| primary {ep:.2e} secondary {es:.2e}")
+        assert ep <= 1e-4 and es <= 1e-4, (precision, ep, es)
+        del e, net
+
+
 def test_mdx_separator_plugin_end_to_end(eng, tmp_path):
     """Separator(...).load_model(); separate(wav) -> two WAVs, secondary first, names as the reference builds them."""
     import wave
