@@ -271,6 +271,9 @@ int b200sep_gemm_kn_f32(const float* A, const float* B_kn, float* C, int M, int 
 int b200sep_ew_f32(const float* a, const float* b, float* out, int64_t n, float alpha, float beta, int op, void* stream);
 /* out2[0] = mean, out2[1] = unbiased std over n elements (htdemucs.py:501-510) */
 int b200sep_meanstd_f32(const float* x, int64_t n, float* out2, void* stream);
+/* the same for `batch` samples x + z * x_stride in two launches: out[z * out_stride + {0, 1}]; work: b200sep_meanstd_work_floats(batch) floats, 16-byte aligned */
+int64_t b200sep_meanstd_work_floats(int batch);
+int b200sep_meanstd_batch_f32(const float* x, int64_t n, int batch, int64_t x_stride, float* out, int out_stride, float* work, void* stream);
 /* One fused DConv residual layer (uvr_lib_v5/demucs/demucs.py:85-168, `layers[d]` of DConv.forward):
  *   y = x + ls * GLU(GroupNorm(1,2C)(Conv1d(hid->2C,1)(GELU(GroupNorm(1,hid)(Conv1d(C->hid,3,dilation)(x))))))
  * on (B, C, Fr, L) with one GroupNorm sample per (b, fr) row (hdemucs.py:141-146).  w0 (hid, C, 3), w3 (2C, hid); y may alias x.

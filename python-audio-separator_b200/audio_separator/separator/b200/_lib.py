@@ -76,6 +76,8 @@ _SIGS = {
     "b200sep_softmax_rows_f32": (i32, [vp, i64, i32, i64, vp]),
     "b200sep_ew_f32": (i32, [vp, vp, vp, i64, f32, f32, i32, vp]),
     "b200sep_meanstd_f32": (i32, [vp, i64, vp, vp]),
+    "b200sep_meanstd_work_floats": (i64, [i32]),
+    "b200sep_meanstd_batch_f32": (i32, [vp, i64, i32, i64, vp, i32, vp, vp]),
     "b200sep_dconv_work_floats": (i64, [i32, i32, i32, i64, i32]),
     "b200sep_dconv_f32": (i32, [vp] * 11 + [i32, i32, i32, i64, i32, i32, vp, vp, vp]),
     "b200sep_triangle_overlap_add": (i32, [vp, i32, i32, i32, i64, i64, i64, i64, f32, vp, i32, vp, vp]),

@@ -172,8 +172,9 @@ def conv_transpose(x, wb, bias, cout, axis, stride, trim, out_len, act=ACT_NONE)
     else:
         y = _new((B, cout, H, out_len), x)
         k, p, hw = (1, 2), (0, 1), (H, W + 1)
+    pk = _packed_conv(wb, cin, 2, stride * cout)
     check(lib.b200sep_conv2d_f32(_ptr(x), _ptr(wb), _ptr(bias), None, _ptr(y), B, cin, H, W, stride * cout, hw[0], hw[1], k[0], k[1], 1, 1, p[0], p[1], 1, 1, act, 0,
-                                 axis, stride, trim, out_len, 0, 0, None, _stream()), "conv2d_f32(transposed)")
+                                 axis, stride, trim, out_len, 0, 0, _ptr(pk) if pk is not None else None, _stream()), "conv2d_f32(transposed)")
     return y
 
 
@@ -459,9 +460,10 @@ class HTDemucsNet:
         x = _new(spec.shape, mp)
         xt = _new((B, 2, 1, T_len), mp)
         fs = 4
+        mswork = _new((lib.b200sep_meanstd_work_floats(B),), mp)
+        check(lib.b200sep_meanstd_batch_f32(_ptr(spec), spec[0].numel(), B, spec[0].numel(), _ptr(stats), 4, _ptr(mswork), _stream()), "meanstd_batch_f32")
+        check(lib.b200sep_meanstd_batch_f32(_ptr(mp), mp[0].numel(), B, mp[0].numel(), stats.data_ptr() + 2 * fs, 4, _ptr(mswork), _stream()), "meanstd_batch_f32")
         for b in range(B):
-            check(lib.b200sep_meanstd_f32(_ptr(spec[b]), spec[b].numel(), stats.data_ptr() + (4 * b) * fs, _stream()), "meanstd_f32")
-            check(lib.b200sep_meanstd_f32(_ptr(mp[b]), mp[b].numel(), stats.data_ptr() + (4 * b + 2) * fs, _stream()), "meanstd_f32")
             check(lib.b200sep_ew_f32(_ptr(spec[b]), stats.data_ptr() + (4 * b) * fs, _ptr(x[b]), spec[b].numel(), 1.0, 0.0, 2, _stream()), "ew_f32")
             check(lib.b200sep_ew_f32(_ptr(mp[b]), stats.data_ptr() + (4 * b + 2) * fs, _ptr(xt[b]), mp[b].numel(), 1.0, 0.0, 2, _stream()), "ew_f32")
         saved, saved_t, lengths_t = [], [], []

@@ -433,12 +433,15 @@ __global__ void ew_kernel(const float* __restrict__ a, const float* __restrict__
   }
 }
 
-// sum and sum of squares (double accumulation) -> out[0] = mean, out[1] = unbiased std  (x.mean(), x.std() of htdemucs.py:501-510)
-__global__ void __launch_bounds__(1024) meanstd_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
-  __shared__ double rs[32], rq[32];
+// sum and sum of squares (double accumulation) -> out[0] = mean, out[1] = unbiased std  (x.mean(), x.std() of htdemucs.py:501-510).
+// Two deterministic passes: kMsBlocks CTAs per sample leave (sum, sum of squares) partials, one CTA per sample adds them in a fixed order.
+constexpr int kMsBlocks = 128;
+__global__ void __launch_bounds__(256) meanstd_partial_kernel(const float* __restrict__ x, int64_t n, int64_t x_stride, double2* __restrict__ part) {
+  __shared__ double rs[8], rq[8];
+  const float* xs = x + (int64_t)blockIdx.y * x_stride;
   double s = 0.0, q = 0.0;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const double v = x[i];
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)kMsBlocks * 256) {
+    const double v = xs[i];
     s += v;
     q += v * v;
   }
@@ -453,14 +456,29 @@ __global__ void __launch_bounds__(1024) meanstd_kernel(const float* __restrict__
   __syncthreads();
   if (threadIdx.x == 0) {
     double S = 0.0, Q = 0.0;
-    for (int w = 0; w < (blockDim.x >> 5); ++w) {
+    for (int w = 0; w < 8; ++w) {
       S += rs[w];
       Q += rq[w];
     }
-    const double mean = S / (double)n;
-    const double var = (Q - S * mean) / (double)(n - 1);
-    out[0] = (float)mean;
-    out[1] = (float)sqrt(var > 0.0 ? var : 0.0);
+    part[(int64_t)blockIdx.y * kMsBlocks + blockIdx.x] = make_double2(S, Q);
+  }
+}
+__global__ void meanstd_final_kernel(const double2* __restrict__ part, int64_t n, float* __restrict__ out, int out_stride) {
+  const double2* ps = part + (int64_t)blockIdx.x * kMsBlocks;
+  double s = 0.0, q = 0.0;
+  for (int i = threadIdx.x; i < kMsBlocks; i += 32) {
+    s += ps[i].x;
+    q += ps[i].y;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (threadIdx.x == 0) {
+    const double mean = s / (double)n;
+    const double var = (q - s * mean) / (double)(n - 1);
+    out[(int64_t)blockIdx.x * out_stride] = (float)mean;
+    out[(int64_t)blockIdx.x * out_stride + 1] = (float)sqrt(var > 0.0 ? var : 0.0);
   }
 }
 
@@ -614,11 +632,28 @@ extern "C" int b200sep_ew_f32(const float* a, const float* b, float* out, int64_
   return B200SEP_OK;
 }
 
-extern "C" int b200sep_meanstd_f32(const float* x, int64_t n, float* out2, void* stream) {
-  B2_CHECK_ARG(x && out2 && n >= 2, "meanstd_f32: need at least 2 elements");
-  meanstd_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, n, out2);
+extern "C" int64_t b200sep_meanstd_work_floats(int batch) { return batch >= 1 ? (int64_t)batch * kMsBlocks * 4 : 0; }
+
+extern "C" int b200sep_meanstd_batch_f32(const float* x, int64_t n, int batch, int64_t x_stride, float* out, int out_stride, float* work, void* stream) {
+  B2_CHECK_ARG(x && out && work && n >= 2 && batch >= 1 && batch <= 65535 && out_stride >= 2, "meanstd_batch_f32: need at least 2 elements per sample");
+  B2_CHECK_ARG((reinterpret_cast<uintptr_t>(work) & 15) == 0, "meanstd_batch_f32: work must be 16-byte aligned");
+  meanstd_partial_kernel<<<dim3(kMsBlocks, batch), 256, 0, (cudaStream_t)stream>>>(x, n, x_stride, reinterpret_cast<double2*>(work));
+  B2_LAUNCHED();
+  meanstd_final_kernel<<<batch, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double2*>(work), n, out, out_stride);
   B2_LAUNCHED();
   return B200SEP_OK;
+}
+
+// single-sample form: the partials live in a per-device scratch buffer owned by the library (allocated on first use; calls on different streams
+// of one device must not overlap -- the engines issue everything on one stream)
+extern "C" int b200sep_meanstd_f32(const float* x, int64_t n, float* out2, void* stream) {
+  B2_CHECK_ARG(x && out2 && n >= 2, "meanstd_f32: need at least 2 elements");
+  static float* scratch[64] = {nullptr};
+  int dev = 0;
+  B2_CUDA(cudaGetDevice(&dev));
+  B2_CHECK_ARG(dev >= 0 && dev < 64, "meanstd_f32: device index %d", dev);
+  if (!scratch[dev]) B2_CUDA(cudaMalloc(&scratch[dev], kMsBlocks * 4 * sizeof(float)));
+  return b200sep_meanstd_batch_f32(x, n, 1, 0, out2, 2, scratch[dev], stream);
 }
 
 extern "C" int b200sep_triangle_overlap_add_range(const float* segs, int first_seg, int n_local, int n_segs, int channels, int seg_len, int64_t stride, int64_t length,

@@ -59,6 +59,9 @@ struct TcParams {
   const float* bias_m;
   float alpha;
   int act, add_before_act;
+  // transposed-convolution scatter (mode 1 only; same contract as conv_gen.cu): GEMM column n = r * up_cout + co, output index along the strided axis =
+  // q * up + r - trim (kept when 0 <= index < out_len); up_axis 1 = H, 2 = W; bias_n has up_cout entries; up_cout % 16 == 0
+  int up_axis, up, trim, out_len, up_cout, Ho;
   // B operand pre-split into the kernel's shared-memory image (tc_pack_*): per (n-tile, k-block) one [hi plane | lo plane] block that a
   // single cp.async.bulk drops into the stage -- static weights cost the producer warps nothing
   const uint8_t* b_packed;
@@ -363,6 +366,39 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f32_kernel(const TcParams p) {
         ptx::tmem_ld16(trow + (uint32_t)c0, v);
         ptx::tmem_ld_wait();
         if (!row_ok) continue;
+        if (p.up_axis) {
+          // ConvTranspose as a 2-tap convolution over the coarse index: this 16-column group is one phase r and 16 consecutive real channels
+          const int nb = n0 + c0;
+          const int r = nb / p.up_cout, co0 = nb - r * p.up_cout;
+          const int hq = m / p.Wo, wq = m - hq * p.Wo;
+          const int pos = ((p.up_axis == 1) ? hq : wq) * p.up + r - p.trim;
+          if (pos < 0 || pos >= p.out_len) continue;
+          const int64_t cs = (p.up_axis == 1) ? (int64_t)p.out_len * p.Wo : (int64_t)p.Ho * p.out_len;
+          float* o = p.out + (int64_t)z * p.o_sz + (int64_t)co0 * cs + ((p.up_axis == 1) ? (int64_t)pos * p.Wo + wq : (int64_t)hq * p.out_len + pos);
+          float x[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]);
+          if (p.bias_n) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias_n + co0) + j4);  // co0 is a multiple of 16
+              x[4 * j4] += bv.x; x[4 * j4 + 1] += bv.y; x[4 * j4 + 2] += bv.z; x[4 * j4 + 3] += bv.w;
+            }
+          }
+          switch (p.act) {
+            case 0: break;
+            case 1:
+#pragma unroll
+              for (int j = 0; j < 16; ++j) x[j] = fmaxf(x[j], 0.f);
+              break;
+            default:
+#pragma unroll
+              for (int j = 0; j < 16; ++j) x[j] = tc_act(x[j], p.act);
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[(int64_t)j * cs] = x[j];
+          continue;
+        }
         // Everything that does not depend on the column is decided OUTSIDE the 16-column loops (the first version re-tested bias / residual /
         // activation per column: ~25 instructions per output, 48 k warp-instructions per tile, which made K = 64 attention GEMMs epilogue-bound).
         float x[16];
@@ -566,7 +602,7 @@ bool tc_conv_usable(int Cin, int Cout, int KH, int KW, int Ho, int Wo, int B) {
 
 int tc_conv2d_f32(const float* x, const float* w_blocked, const float* bias, const float* add, float* y, int B, int Cin, int H, int W, int Cout, int CoutPad, int Ho,
                   int Wo, int KH, int KW, int SH, int SW, int PH, int PW, int DH, int DW, int act, int add_before_act, int out_c_total, int out_c_off, const void* w_packed,
-                  cudaStream_t st) {
+                  cudaStream_t st, int up_axis, int up, int trim, int out_len) {
   TcParams p{};
   p.mode = 1;
   p.b_packed = (const uint8_t*)w_packed;
@@ -580,6 +616,11 @@ int tc_conv2d_f32(const float* x, const float* w_blocked, const float* bias, con
   p.out = y + (int64_t)(out_c_total ? out_c_off : 0) * P; p.o_sz = ct * P; p.o_sm = 1; p.o_sn = P;
   p.res = add; p.r_sz = (int64_t)Cout * P; p.r_sm = 1; p.r_sn = P;
   p.res_scale = nullptr; p.bias_n = bias; p.bias_m = nullptr; p.alpha = 1.f; p.act = act; p.add_before_act = add_before_act;
+  if (up_axis) {
+    B2_CHECK_ARG(up >= 1 && Cout % up == 0 && (Cout / up) % 16 == 0 && add == nullptr && out_c_total == 0, "tc_conv2d_f32: transposed mode needs Cout/up a multiple of 16 and no residual");
+    p.up_axis = up_axis; p.up = up; p.trim = trim; p.out_len = out_len; p.up_cout = Cout / up; p.Ho = Ho;
+    p.o_sz = (int64_t)(Cout / up) * (up_axis == 1 ? (int64_t)out_len * Wo : (int64_t)Ho * out_len);
+  }
   return tc_launch(p, st);
 }
 

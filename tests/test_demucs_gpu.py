@@ -98,6 +98,28 @@ def test_conv_transpose_f32(dm, axis):
     assert (got.double() - ref).abs().max() <= 2e-5 * max(1.0, ref.abs().max())
 
 
+@pytest.mark.parametrize("axis", [1, 2])
+def test_conv_transpose_f32_tensor_core_route(dm, axis):
+    """Same operator at shapes the tcgen05 kernel takes (real output channels a multiple of 16, >= 512 coarse pixels): the scatter epilogue of tc_f32.cu."""
+    g = torch.Generator().manual_seed(5)
+    cin, cout = 96, 48
+    if axis == 1:
+        x = torch.randn((2, cin, 8, 90), generator=g)
+        w = torch.randn((cin, cout, 8, 1), generator=g) / cin**0.5
+        b = torch.randn(cout, generator=g)
+        ref = F.gelu(F.conv_transpose2d(x.double(), w.double(), b.double(), stride=(4, 1))[..., 2:-2, :])
+        got = dm.conv_transpose(x.cuda(), dev(dm.block_convtr_weight(w.numpy().reshape(cin, cout, 8), 4)), b.cuda(), cout, 1, 4, 2, 32, dm.ACT_GELU).cpu()
+    else:
+        x = torch.randn((2, cin, 1, 700), generator=g)
+        w = torch.randn((cin, cout, 8), generator=g) / cin**0.5
+        b = torch.randn(cout, generator=g)
+        length = 2797
+        ref = F.conv_transpose1d(x[:, :, 0].double(), w.double(), b.double(), stride=4)[..., 2 : 2 + length][:, :, None]
+        got = dm.conv_transpose(x.cuda(), dev(dm.block_convtr_weight(w.numpy(), 4)), b.cuda(), cout, 2, 4, 2, length).cpu()
+    assert got.shape == ref.shape and torch.isfinite(got).all()
+    assert (got.double() - ref).abs().max() <= 5e-5 * max(1.0, ref.abs().max())
+
+
 def test_groupnorm_glu_layernorm_softmax_permute(dm):
     g = torch.Generator().manual_seed(4)
     x = torch.randn((2, 6, 5, 77), generator=g) * 3 + 1
