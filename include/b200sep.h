@@ -115,6 +115,9 @@ int b200sep_absmax(const float* x, int64_t n, float* result, void* stream);
 int b200sep_normalize(const float* x, int64_t n, const float* absmax, float max_peak, float min_peak, float* y, void* stream);
 /* (x*32767) truncated toward zero to int16 (common_separator.py:331); x is (n,) float32 */
 int b200sep_to_pcm16(const float* x, int64_t n, int16_t* y, void* stream);
+/* The same at the input file's bit depth (common_separator.py:322-383): n samples -> n * bits/8 little-endian bytes.  via_int16 = 1: the default (pydub) writer,
+ * int16 quantisation widened by shifting; 0: the libsndfile writer, lrint(x * (2^(bits-1) - 1)). */
+int b200sep_to_pcm_bytes(const float* x, int64_t n, int bits, int via_int16, uint8_t* y, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * ConvTDFNet (the graph inside UVR-MDX-NET-*.onnx; topology: uvr_lib_v5/mdxnet.py:30-120, modules.py:1-74).

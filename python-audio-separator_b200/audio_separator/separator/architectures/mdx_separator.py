@@ -14,7 +14,7 @@ import torch
 
 from ..b200 import mdx_weights, onnx_reader
 from ..b200.engine import MdxEngine, MdxNet
-from ..common_separator import CommonSeparator
+from ..common_separator import CommonSeparator, DeviceStem
 from ..uvr_lib_v5.stft import STFT
 
 
@@ -130,11 +130,14 @@ class MDXSeparator(CommonSeparator):
         mix = self.prepare_mix(self.audio_file_path)
         if self.invert_using_spec:
             raise NotImplementedError("invert_using_spec=True (spec_utils.invert_stem) is not part of the accelerated path yet")
-        primary, secondary = self.separate_host(mix)
+        # device-resident output pipeline: the float stems stay in HBM; write_audio pulls bits/8 bytes per sample (normalise, quantise and pack are kernels)
+        self.initialize_model_settings()
+        mix_dev = torch.from_numpy(np.ascontiguousarray(mix, dtype=np.float32)).to(self.torch_device)
+        primary_dev, secondary_dev = self.engine.separate_device(mix_dev, self.normalization_threshold, self.amplification_threshold)
         if not isinstance(self.primary_source, np.ndarray):
-            self.primary_source = np.array(primary)
+            self.primary_source = DeviceStem(primary_dev)
         if not isinstance(self.secondary_source, np.ndarray):
-            self.secondary_source = np.array(secondary)
+            self.secondary_source = DeviceStem(secondary_dev)
 
         output_files = []
         for is_secondary in (True, False):  # secondary stem file first, then primary (:185-197)
@@ -143,7 +146,8 @@ class MDXSeparator(CommonSeparator):
                 continue
             path = self.get_stem_output_path(name, custom_output_names)
             self.logger.info(f"Saving {name} stem to {path}...")
-            self.final_process(path, self.secondary_source if is_secondary else self.primary_source, name)
+            src = self.secondary_source if is_secondary else self.primary_source
+            self.final_process(path, src.tensor if isinstance(src, DeviceStem) else src, name)
             if is_secondary:
                 self.secondary_stem_output_path = path
             else:

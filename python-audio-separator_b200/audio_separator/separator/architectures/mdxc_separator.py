@@ -32,7 +32,8 @@ class MDXCSeparator(CommonSeparator):
         if not torch.cuda.is_available():
             raise RuntimeError("MDXCSeparator (B200 build) needs a CUDA device: there is no CPU path in this package")
         self.torch_device = torch.device("cuda", torch.cuda.current_device())
-        self.is_primary_stem_main_target = bool(self.model_data_cfgdict["training"].get("target_instrument")) if self.is_roformer else False  # :69
+        self.is_primary_stem_main_target = bool(self.model_data_cfgdict["training"].get("target_instrument"))  # :69, both model families
+        self._engines = {}  # dim_t -> engine: the chunk length is fixed per engine, and separate() switches it for clips shorter than 10 s (:137-143)
         self.load_model()
 
     def load_model(self):
@@ -50,12 +51,25 @@ class MDXCSeparator(CommonSeparator):
         else:
             sd = torch.load(path, map_location="cpu", weights_only=True)
             state = {k: v.float().numpy() for k, v in (sd.get("state_dict", sd)).items()}
-        dim_t = self.segment_size if self.override_model_segment_size else cfg["inference"]["dim_t"]  # :355-360
-        targets = 1 if training.get("target_instrument") else len(training["instruments"])
-        self.net = TfcNet(state, audio["dim_f"], dim_t, model["num_subbands"], audio.get("num_channels", 2), model["num_scales"], model["num_blocks_per_scale"],
-                          model["num_channels"], model["growth"], model["bottleneck_factor"], targets, max_batch=max(1, int(self.batch_size)))
-        self.engine = MdxcEngine(self.net, audio["n_fft"], audio["hop_length"], audio["dim_f"], dim_t, self.overlap)
-        self.model_run = self.engine.model_run
+        self._state = state
+        self._select_engine()
+
+    def _select_engine(self):
+        """The engine for the current `override_model_segment_size` (dim_t = segment_size or the model's inference.dim_t, :281-286 / :355-360); built once per dim_t."""
+        cfg = self.model_data_cfgdict
+        audio, model, training = cfg["audio"], cfg["model"], cfg["training"]
+        dim_t = int(self.segment_size if self.override_model_segment_size else cfg["inference"]["dim_t"])
+        if dim_t not in self._engines:
+            if self.is_roformer:
+                eng = RoformerEngine(self.net, dim_t, self.overlap, audio.get("sample_rate", 44100), len(training["instruments"]), max(1, int(self.batch_size)))
+                self._engines[dim_t] = (self.net, eng, self.net.forward)
+            else:
+                targets = 1 if training.get("target_instrument") else len(training["instruments"])
+                net = TfcNet(self._state, audio["dim_f"], dim_t, model["num_subbands"], audio.get("num_channels", 2), model["num_scales"], model["num_blocks_per_scale"],
+                             model["num_channels"], model["growth"], model["bottleneck_factor"], targets, max_batch=max(1, int(self.batch_size)))
+                eng = MdxcEngine(net, audio["n_fft"], audio["hop_length"], audio["dim_f"], dim_t, self.overlap)
+                self._engines[dim_t] = (net, eng, eng.model_run)
+        self.net, self.engine, self.model_run = self._engines[dim_t]
 
     def _load_roformer(self, cfg):
         """RoformerLoader.load_model (roformer/roformer_loader.py:82-195): BSRoformer(**model section) + load_state_dict."""
@@ -74,9 +88,7 @@ class MDXCSeparator(CommonSeparator):
             sd = torch.load(path, map_location="cpu", weights_only=True)
             state = {k: v.float().numpy() for k, v in (sd.get("state_dict", sd)).items()}
         self.net = BSRoformerNet(rcfg, state, device=self.torch_device)
-        dim_t = self.segment_size if self.override_model_segment_size else cfg["inference"]["dim_t"]  # :281-286
-        self.engine = RoformerEngine(self.net, dim_t, self.overlap, cfg["audio"].get("sample_rate", 44100), len(training["instruments"]), max(1, int(self.batch_size)))
-        self.model_run = self.net.forward
+        self._select_engine()
 
     def _demix_roformer(self, mix):
         """Roformer branch of demix + the stem dictionary (mdxc_separator.py:272-343, :406-468)."""
@@ -94,16 +106,25 @@ class MDXCSeparator(CommonSeparator):
         """(2, N) ndarray -> {instrument: (2, N) ndarray} (mdxc_separator.py:406-434) or the single target's array."""
         if self.is_roformer:
             return self._demix_roformer(mix)
-        out = self.engine.demix_device(torch.as_tensor(np.ascontiguousarray(mix, dtype=np.float32)).to(self.torch_device)).cpu().numpy()
+        orig = np.ascontiguousarray(mix, dtype=np.float32)
+        out = self.engine.demix_device(torch.as_tensor(orig).to(self.torch_device)).cpu().numpy()
         training = self.model_data_cfgdict["training"]
         if self.net.num_targets > 1:
             return {k: v for k, v in zip(training["instruments"], out)}
-        return out[0]
+        primary = out[0]
+        if self.is_primary_stem_main_target:  # single-target models also return the residual as the secondary stem (:452-461)
+            return {self.primary_stem_name: primary, self.secondary_stem_name: orig - primary}
+        return primary
 
     def separate(self, audio_file_path, custom_output_names=None):
         self.audio_file_path = audio_file_path
         self.audio_file_base = os.path.splitext(os.path.basename(audio_file_path))[0]
         mix = self.prepare_mix(self.audio_file_path)
+        if mix.shape[1] / self.sample_rate < 10.0 and not self.override_model_segment_size:  # :137-143 (the switch is sticky in the reference too)
+            self.override_model_segment_size = True
+            self.logger.warning(f"Audio duration ({mix.shape[1] / self.sample_rate:.2f}s) is less than 10 seconds.")
+            self.logger.warning("Automatically enabling override_model_segment_size for better processing of short audio.")
+            self._select_engine()
         mix = normalize(wave=np.array(mix, dtype=np.float32), max_peak=self.normalization_threshold, min_peak=self.amplification_threshold)  # :149
         source = self.demix(mix)
         output_files = []
@@ -127,12 +148,10 @@ class MDXCSeparator(CommonSeparator):
                 self.final_process(path, src, name)
                 output_files.append(path)
             return output_files
-        self.primary_source = normalize(wave=source, max_peak=self.normalization_threshold, min_peak=self.amplification_threshold).T  # :160-182
-        self.secondary_source = mix.T - source.T
-        for name, src in ((self.secondary_stem_name, self.secondary_source), (self.primary_stem_name, self.primary_source)):
-            if self.output_single_stem and self.output_single_stem.lower() != name.lower():
-                continue
-            path = self.get_stem_output_path(name, custom_output_names)
-            self.final_process(path, src, name)
+        # a bare array = a single-source model without a target instrument: only the primary stem is written, as it is (:216-226)
+        if not self.output_single_stem or self.output_single_stem.lower() == self.primary_stem_name.lower():
+            self.primary_source = source.T
+            path = self.get_stem_output_path(self.primary_stem_name, custom_output_names)
+            self.final_process(path, self.primary_source, self.primary_stem_name)
             output_files.append(path)
         return output_files

@@ -27,6 +27,24 @@ def normalize(wave, max_peak=1.0, min_peak=None):
     return wave
 
 
+class DeviceStem:
+    """A float stem that lives in HBM.  `primary_source` / `secondary_source` of a plugin hold these after separate(); np.asarray(stem) downloads it
+    (once) for code that expects the reference's host arrays, while write_audio consumes the tensor directly."""
+
+    def __init__(self, tensor):
+        self.tensor = tensor
+        self._host = None
+
+    @property
+    def shape(self):
+        return tuple(self.tensor.shape)
+
+    def __array__(self, dtype=None, copy=None):
+        if self._host is None:
+            self._host = self.tensor.detach().cpu().numpy()
+        return self._host if dtype is None else self._host.astype(dtype, copy=False)
+
+
 class CommonSeparator:
     VOCAL_STEM, INST_STEM, OTHER_STEM, BASS_STEM, DRUM_STEM = "Vocals", "Instrumental", "Other", "Bass", "Drums"
     GUITAR_STEM, PIANO_STEM, PRIMARY_STEM, SECONDARY_STEM, NO_STEM = "Guitar", "Piano", "Primary Stem", "Secondary Stem", "No "
@@ -121,6 +139,10 @@ class CommonSeparator:
         self.write_audio(stem_path, source)
         return {stem_name: source}
 
+    def _output_bits(self):
+        """Output sample width follows the input file (common_separator.py:322-324); 16 bits when unknown."""
+        return self.input_bit_depth if self.input_bit_depth in (16, 24, 32) else 16
+
     def pcm16_interleaved(self, stem_source):
         """normalise -> near-silence check -> (x*32767).astype(int16) (truncation) -> interleave (common_separator.py:310-339)."""
         s = normalize(np.array(stem_source, dtype=np.float32, copy=True), self.normalization_threshold, self.amplification_threshold)
@@ -129,25 +151,81 @@ class CommonSeparator:
             return None
         return np.ascontiguousarray((s * 32767).astype(np.int16)).reshape(-1)
 
+    def pcm_bytes(self, stem_source):
+        """(N, 2) float stem -> (bits, interleaved little-endian PCM bytes) at the input's bit depth, or None for a near-silent stem.
+        A CUDA tensor never leaves the device as floats: peak, normalisation, quantisation and byte packing are kernels (b200sep_absmax / _normalize /
+        _to_pcm_bytes), the host receives bits/8 bytes per sample.  A host array takes the numpy path of the reference."""
+        bits = self._output_bits()
+        via16 = not self.use_soundfile  # write_audio_pydub quantises to int16 first; write_audio_soundfile converts the floats (:322-336 / :391-451)
+        if isinstance(stem_source, torch.Tensor) and stem_source.is_cuda:
+            from .b200._lib import check, lib
+
+            x = stem_source.contiguous()
+            n = x.numel()
+            st = torch.cuda.current_stream().cuda_stream
+            peak = torch.empty(1, dtype=torch.float32, device=x.device)
+            check(lib.b200sep_absmax(x.data_ptr(), n, peak.data_ptr(), st), "absmax")
+            norm = torch.empty_like(x)
+            min_peak = -1.0 if self.amplification_threshold is None else float(self.amplification_threshold)
+            check(lib.b200sep_normalize(x.data_ptr(), n, peak.data_ptr(), float(self.normalization_threshold), min_peak, norm.data_ptr(), st), "normalize")
+            out = torch.empty(n * bits // 8, dtype=torch.uint8, device=x.device)
+            check(lib.b200sep_to_pcm_bytes(norm.data_ptr(), n, bits, int(via16), out.data_ptr(), st), "to_pcm_bytes")
+            pk = float(peak.item())
+            scale = self.normalization_threshold / pk if pk > self.normalization_threshold else (min_peak / pk if (min_peak >= 0 and 0 < pk < min_peak) else 1.0)
+            if pk * scale < 1e-6:
+                self.logger.warning("Warning: stem_source array is near-silent or empty.")
+                return None
+            return bits, out.cpu().numpy().tobytes()
+        if isinstance(stem_source, np.ndarray) and stem_source.dtype == np.int16:
+            q = stem_source.reshape(-1).astype(np.int64)
+            via16 = True
+        else:
+            s = normalize(np.array(stem_source, dtype=np.float32, copy=True), self.normalization_threshold, self.amplification_threshold)
+            if np.max(np.abs(s)) < 1e-6:
+                self.logger.warning("Warning: stem_source array is near-silent or empty.")
+                return None
+            s = np.ascontiguousarray(s).reshape(-1)
+            if via16:
+                q = (s * 32767).astype(np.int16).astype(np.int64)
+            elif bits == 32:
+                q = np.clip(np.rint(s.astype(np.float64) * 2147483648.0), -2147483648.0, 2147483647.0).astype(np.int64)
+            else:
+                q = np.rint(s * np.float32((1 << (bits - 1)) - 1)).astype(np.int64)
+        if via16:
+            q = q << (bits - 16)
+        if bits == 16:
+            return bits, q.astype("<i2").tobytes()
+        if bits == 32:
+            return bits, q.astype("<i4").tobytes()
+        b4 = q.astype("<i4").view(np.uint8).reshape(-1, 4)
+        return bits, np.ascontiguousarray(b4[:, :3]).tobytes()
+
     def write_audio(self, stem_path, stem_source):
-        pcm = stem_source if isinstance(stem_source, np.ndarray) and stem_source.dtype == np.int16 else self.pcm16_interleaved(stem_source)
-        if pcm is None:
+        packed = self.pcm_bytes(stem_source)
+        if packed is None:
             return
+        bits, data = packed
         if self.output_dir:
             os.makedirs(self.output_dir, exist_ok=True)
             stem_path = os.path.join(self.output_dir, stem_path)
         if stem_path.lower().endswith(".wav"):
             with _wave.open(stem_path, "wb") as wf:
                 wf.setnchannels(2)
-                wf.setsampwidth(2)
+                wf.setsampwidth(bits // 8)
                 wf.setframerate(int(self.sample_rate))
-                wf.writeframes(np.ascontiguousarray(pcm.reshape(-1)).tobytes())
+                wf.writeframes(data)
             return
         try:
             import soundfile as sf
         except ImportError as e:
             raise RuntimeError(f"writing {stem_path}: only WAV output is available without soundfile/pydub") from e
-        sf.write(stem_path, pcm.reshape(-1, 2), self.sample_rate)
+        dt = {16: "<i2", 32: "<i4"}.get(bits)
+        if dt is None:  # 24-bit: hand libsndfile int32 with the sample in the top three bytes
+            a = np.frombuffer(data, dtype=np.uint8).reshape(-1, 3)
+            pcm = (np.concatenate([np.zeros((a.shape[0], 1), np.uint8), a], axis=1).view("<i4")).reshape(-1, 2)
+        else:
+            pcm = np.frombuffer(data, dtype=dt).reshape(-1, 2)
+        sf.write(stem_path, pcm, self.sample_rate, subtype=f"PCM_{bits}")
 
     def clear_gpu_cache(self):
         gc.collect()

@@ -346,6 +346,27 @@ __global__ void pcm16_kernel(const float* __restrict__ x, int64_t n, int16_t* __
   }
 }
 
+// PCM bytes (little endian) at the input file's bit depth (common_separator.py:322-383).  via_int16 = the pydub writer: samples are quantised to int16
+// first ((x * 32767).astype(int16)) and ffmpeg widens them (s16 -> s32 = << 16; pcm_s24le keeps the top three bytes).  Otherwise the libsndfile
+// writer: lrint(x * (2^(bits-1) - 1)) (PCM_32 scales by 2^31 and saturates).
+__global__ void pcm_bytes_kernel(const float* __restrict__ x, int64_t n, int bits, int via_int16, uint8_t* __restrict__ y) {
+  const int width = bits >> 3;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int v;
+    if (via_int16) {
+      v = (int)(int16_t)(int)__fmul_rn(x[i], 32767.f);
+      v = (int)((unsigned)v << (bits - 16));
+    } else if (bits == 32) {
+      const double d = rint((double)x[i] * 2147483648.0);
+      v = d >= 2147483647.0 ? 2147483647 : (d <= -2147483648.0 ? (int)0x80000000 : (int)d);
+    } else {
+      v = (int)rintf(__fmul_rn(x[i], (float)((1 << (bits - 1)) - 1)));
+    }
+    uint8_t* o = y + i * width;
+    for (int b = 0; b < width; ++b) o[b] = (uint8_t)((unsigned)v >> (8 * b));
+  }
+}
+
 static int factor_fft(int n, FftStages* st) {
   st->n = n;
   st->n_stages = 0;
@@ -583,6 +604,15 @@ extern "C" int b200sep_normalize(const float* x, int64_t n, const float* absmax,
   if (n == 0) return B200SEP_OK;
   const int blocks = (int)std::min<int64_t>(cdiv(n, 1024), kNumSMs * 8);
   normalize_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n, absmax, max_peak, min_peak, y);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
+extern "C" int b200sep_to_pcm_bytes(const float* x, int64_t n, int bits, int via_int16, uint8_t* y, void* stream) {
+  B2_CHECK_ARG(x && y && n >= 0 && (bits == 16 || bits == 24 || bits == 32), "to_pcm_bytes: bits must be 16, 24 or 32");
+  if (n == 0) return B200SEP_OK;
+  const int blocks = (int)std::min<int64_t>(cdiv(n, 1024), kNumSMs * 8);
+  pcm_bytes_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n, bits, via_int16, y);
   B2_LAUNCHED();
   return B200SEP_OK;
 }

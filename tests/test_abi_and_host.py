@@ -125,6 +125,37 @@ def test_common_separator_contract(tmp_path, lib_built):
         cs.write_audio("z.wav", np.zeros((10, 2), np.float32)) or cs.prepare_mix(_silent(tmp_path))
 
 
+def test_write_audio_follows_the_input_bit_depth(tmp_path, lib_built):
+    """common_separator.py:322-383: the output keeps the input file's sample width.  The default (pydub) writer quantises to int16 and lets ffmpeg widen
+    the samples (a shift); the libsndfile writer converts the floats (lrint(x * (2^(bits-1) - 1)))."""
+    x = (O.synth_music(3000, seed=2) * 0.6).T.copy()
+    p16 = O.to_pcm16(x, 0.9, 0.0).astype(np.int64)
+    xn = O.normalize(x.copy(), 0.9, 0.0)
+    for bits in (16, 24, 32):
+        for use_sf in (False, True):
+            cs = _common(tmp_path, use_soundfile=use_sf)
+            cs.input_bit_depth = bits
+            cs.write_audio("b.wav", x)
+            with wave.open(str(tmp_path / "b.wav")) as wf:
+                assert (wf.getnchannels(), wf.getsampwidth(), wf.getnframes()) == (2, bits // 8, 3000)
+                raw = np.frombuffer(wf.readframes(3000), dtype=np.uint8).reshape(-1, bits // 8).astype(np.int64)
+            val = sum(raw[:, b] << (8 * b) for b in range(bits // 8))
+            val = np.where(val >= 1 << (bits - 1), val - (1 << bits), val)
+            if not use_sf:
+                want = p16 << (bits - 16)
+            elif bits == 32:
+                want = np.clip(np.rint(xn.reshape(-1).astype(np.float64) * 2147483648.0), -(2**31), 2**31 - 1).astype(np.int64)
+            else:
+                want = np.rint(xn.reshape(-1) * np.float32((1 << (bits - 1)) - 1)).astype(np.int64)
+            assert np.array_equal(val, want), (bits, use_sf)
+    cs = _common(tmp_path)
+    with wave.open(str(tmp_path / "in24.wav"), "wb") as wf:  # a 24-bit input sets the depth the stems are written with
+        wf.setnchannels(2); wf.setsampwidth(3); wf.setframerate(44100)
+        wf.writeframes(bytes([1, 2, 3] * 200))
+    cs.prepare_mix(str(tmp_path / "in24.wav"))
+    assert cs.input_bit_depth == 24 and cs._output_bits() == 24
+
+
 def _silent(tmp_path):
     p = str(tmp_path / "silent.wav")
     with wave.open(p, "wb") as wf:

@@ -278,6 +278,31 @@ def test_baseline_config1_full_size_net_three_chunks_vs_oracle(eng):
         del e, net
 
 
+def test_device_output_pipeline_matches_host_writer(eng, tmp_path):
+    """CommonSeparator.pcm_bytes on a CUDA stem (absmax / normalize / to_pcm_bytes kernels, bytes downloaded) == the numpy path on the same stem, every bit depth and both writers."""
+    import logging
+
+    from audio_separator.separator.common_separator import CommonSeparator, DeviceStem
+
+    x = (O.synth_music(50_001, seed=4) * 1.3).T.copy()  # peak above the 0.9 threshold: the normalisation is active
+    for bits in (16, 24, 32):
+        for use_sf in (False, True):
+            cs = CommonSeparator(dict(logger=logging.getLogger("t"), model_name="m", model_path="/x/m.onnx", model_data={"primary_stem": "Vocals"}, output_dir=str(tmp_path),
+                                      output_format="WAV", normalization_threshold=0.9, amplification_threshold=0.0, sample_rate=44100, use_soundfile=use_sf))
+            cs.input_bit_depth = bits
+            host = cs.pcm_bytes(x)
+            devb = cs.pcm_bytes(dev(x))
+            assert host[0] == devb[0] == bits and len(devb[1]) == x.size * bits // 8
+            a, b = np.frombuffer(host[1], np.uint8).astype(np.int32), np.frombuffer(devb[1], np.uint8).astype(np.int32)
+            if use_sf and bits > 16:  # x * scale is rounded once on the device and once in numpy: identical inputs, identical fp32 products
+                assert np.array_equal(a, b)
+            else:
+                assert np.array_equal(a, b), (bits, use_sf)
+    assert cs.pcm_bytes(dev(np.zeros((100, 2), np.float32))) is None  # near-silent stems are skipped like the reference does
+    st = DeviceStem(dev(x))
+    assert np.array_equal(np.asarray(st), x) and st.shape == x.shape
+
+
 def test_mdx_separator_plugin_end_to_end(eng, tmp_path):
     """Separator(...).load_model(); separate(wav) -> two WAVs, secondary first, names as the reference builds them."""
     import wave

@@ -88,9 +88,12 @@ def test_mdxc_plugin_end_to_end(setup, tmp_path):
     pcm = (mix.T * 32767).astype("<i2")
     with wave.open(str(tmp_path / "song.wav"), "wb") as wf:
         wf.setnchannels(2); wf.setsampwidth(2); wf.setframerate(44100); wf.writeframes(pcm.tobytes())
-    sep = Separator(model_file_dir=str(tmp_path), output_dir=str(tmp_path / "out"), mdxc_params={"overlap": cfg.overlap, "batch_size": 2})
+    sep = Separator(model_file_dir=str(tmp_path), output_dir=str(tmp_path / "out"), mdxc_params={"overlap": cfg.overlap, "batch_size": 2, "segment_size": cfg.dim_t})
     sep.load_model("tiny-mdx23c.npz")
+    assert not sep.model_instance.override_model_segment_size
     files = sep.separate(str(tmp_path / "song.wav"))
+    # a clip shorter than 10 s switches the plugin to dim_t = segment_size, like the reference (mdxc_separator.py:137-143); here both are 16
+    assert sep.model_instance.override_model_segment_size and sep.model_instance.engine.dim_t == cfg.dim_t
     assert files == ["song_(Instrumental)_tiny-mdx23c.wav", "song_(Vocals)_tiny-mdx23c.wav"]  # two-stem dict: the secondary file first (mdxc_separator.py:186-214)
     loaded = M.normalize(pcm.astype(np.float32).T / 32768.0, 0.9, 0.0)
     ref = X.demix(loaded, cfg, lambda x: X.net_forward(w, cfg, x))  # rows in training.instruments order: Vocals, Instrumental

@@ -182,7 +182,7 @@ def test_mdxc_plugin_roformer_end_to_end(rf, tmp_path):
     pcm = (mix.T * 32767).astype("<i2")
     with wavmod.open(str(tmp_path / "song.wav"), "wb") as wf:
         wf.setnchannels(2); wf.setsampwidth(2); wf.setframerate(44100); wf.writeframes(pcm.tobytes())
-    sep = Separator(model_file_dir=str(tmp_path), output_dir=str(tmp_path / "out"), mdxc_params={"batch_size": 4})
+    sep = Separator(model_file_dir=str(tmp_path), output_dir=str(tmp_path / "out"), mdxc_params={"batch_size": 4, "segment_size": 65})  # < 10 s: dim_t = segment_size (:137-143)
     sep.load_model("tiny_bs_roformer.npz")
     files = sep.separate(str(tmp_path / "song.wav"))
     assert files == ["song_(Instrumental)_tiny_bs_roformer.wav", "song_(Vocals)_tiny_bs_roformer.wav"]  # secondary (residual) first, then the target
