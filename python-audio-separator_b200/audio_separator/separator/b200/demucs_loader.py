@@ -29,12 +29,25 @@ class _Placeholder:
     """Stands in for a class the package pickled by reference (e.g. demucs.htdemucs.HTDemucs)."""
 
 
+# Globals a Demucs package legitimately pickles: tensor rebuild helpers / storages, plain containers, Fraction, numpy scalars and omegaconf containers (the
+# training config some packages carry).  EVERYTHING else -- first of all the model class itself -- becomes an inert placeholder instead of being imported:
+# a crafted .th cannot name an arbitrary callable (the reference's plain torch.load would execute it).
+_ALLOWED_MODULES = ("torch._utils", "torch.storage", "torch._tensor", "torch.serialization", "collections", "fractions", "numpy", "numpy.core.multiarray", "numpy._core.multiarray",
+                    "numpy.core.numeric", "numpy._core.numeric", "omegaconf.dictconfig", "omegaconf.listconfig", "omegaconf.base", "omegaconf.nodes", "builtins")
+_ALLOWED_BUILTINS = {"set", "frozenset", "dict", "list", "tuple", "int", "float", "bool", "str", "bytes", "bytearray", "complex", "slice", "range", "object"}
+
+
 class _TolerantUnpickler(pickle.Unpickler):
     def find_class(self, module, name):
-        try:
-            return super().find_class(module, name)
-        except (ImportError, AttributeError):
-            return type(name, (_Placeholder,), {"__module__": module})
+        allowed = module in _ALLOWED_MODULES or (module == "torch" and (name.endswith("Storage") or name in ("Size", "device", "dtype", "Tensor") or name.startswith(("float", "int", "uint", "bfloat", "bool", "half", "double", "long", "short", "complex"))))
+        if module == "builtins" and name not in _ALLOWED_BUILTINS:
+            allowed = False
+        if allowed:
+            try:
+                return super().find_class(module, name)
+            except (ImportError, AttributeError):
+                pass
+        return type(name, (_Placeholder,), {"__module__": module})
 
 
 _pickle_shim = types.ModuleType("b200sep_tolerant_pickle")

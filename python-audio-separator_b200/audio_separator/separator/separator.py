@@ -116,8 +116,12 @@ class Separator:
             raise ValueError("Initialization failed or model not loaded. Please load a model before attempting to separate.")
         paths = [audio_file_path] if isinstance(audio_file_path, str) else list(audio_file_path)
         outputs = []
+        audio_ext = (".wav", ".flac", ".mp3", ".ogg", ".opus", ".m4a", ".aiff", ".ac3")  # separator.py:972
         for path in paths:
-            files = [os.path.join(path, f) for f in sorted(os.listdir(path))] if os.path.isdir(path) else [path]
+            if os.path.isdir(path):  # recursive, audio files only (separator.py:966-979)
+                files = [os.path.join(root, f) for root, _, names in os.walk(path) for f in names if f.endswith(audio_ext)]
+            else:
+                files = [path]
             for f in files:
                 try:
                     outputs.extend(self._separate_file(f, custom_output_names))

@@ -129,7 +129,14 @@ __device__ __forceinline__ void umma_producer_loop(const CUtensorMap& tmA_hi, co
       ptx::mbar_arrive_expect_tx(&full_bar[s], ((p.dbg & 8) ? 0 : 2 * p.a_bytes) + ((p.dbg & 16) ? 0 : 2 * p.b_bytes));
       if (p.mode == 0) {
         const int k0 = i * 64;
-        if (!(p.dbg & 8)) {
+        if (p.cluster > 1) {
+          // the CTAs of a cluster sit on the same 128 activation rows (consecutive weight tiles): this one fetches 128/cluster rows for all of them
+          // (tmA_* are then the maps with a [64 k][128/cluster rows] box; rows are 128 bytes, so a slice is whole 1024-byte swizzle atoms)
+          const uint32_t rows = 128u / (uint32_t)p.cluster, r0 = ptx::cluster_ctarank() * rows;
+          const uint16_t mask = (uint16_t)((1u << p.cluster) - 1u);
+          ptx::tma_load_2d_multicast(a_hi + r0 * 128u, &tmA_hi, &full_bar[s], k0, tc.m0 + (int)r0, mask);
+          ptx::tma_load_2d_multicast(a_lo + r0 * 128u, &tmA_lo, &full_bar[s], k0, tc.m0 + (int)r0, mask);
+        } else if (!(p.dbg & 8)) {
           ptx::tma_load_2d(a_hi, &tmA_hi, &full_bar[s], k0, tc.m0);
           ptx::tma_load_2d(a_lo, &tmA_lo, &full_bar[s], k0, tc.m0);
         }
@@ -766,17 +773,23 @@ static int num_sms() {
   return n;
 }
 
-// Cluster size for the weight multicast (conv modes): the CTAs of a cluster must sit on the same weight tile at every step of their tile walk, which
-// holds when tile ids, the grid and the number of tiles per weight tile are all multiples of the cluster size.  B200SEP_CLUSTER overrides (1 = off).
+// Cluster size for the operand multicast.  Conv modes: the CTAs of a cluster must sit on the same weight tile at every step of their tile walk, which holds
+// when tile ids, the grid and the number of tiles per weight tile are all multiples of the cluster size; GEMM: `cs` consecutive tiles share their activation rows
+// when cs divides the tiles along N.  Measured on B200 (profiles/README.md, round 2): the conv kernels gain nothing from it (they are not L2-bound), so it is
+// off by default there; B200SEP_CLUSTER / B200SEP_CLUSTER_GEMM (1, 2, 4, 8) select it for A/B runs.
+static int env_cluster(const char* name, int dflt) {
+  const char* e = getenv(name);
+  const int v = e ? atoi(e) : dflt;
+  return (v == 1 || v == 2 || v == 4 || v == 8) ? v : dflt;
+}
 static int choose_cluster(const UmmaParams& p) {
-  static int want = -1;
-  if (want < 0) {
-    const char* e = getenv("B200SEP_CLUSTER");
-    want = e ? atoi(e) : 4;
-    if (want != 1 && want != 2 && want != 4 && want != 8) want = 4;
+  static const int want_conv = env_cluster("B200SEP_CLUSTER", 1), want_gemm = env_cluster("B200SEP_CLUSTER_GEMM", 1);
+  if (p.mode == 0) {
+    for (int cs = std::min(want_gemm, 4); cs > 1; cs >>= 1)
+      if (p.n_tiles % cs == 0) return cs;
+    return 1;
   }
-  if (p.mode == 0) return 1;
-  for (int cs = want; cs > 1; cs >>= 1)
+  for (int cs = want_conv; cs > 1; cs >>= 1)
     if (p.num_tiles % cs == 0 && (p.n_ftiles * p.t_tiles) % cs == 0 && p.b_bytes % (16u * cs) == 0) return cs;
   return 1;
 }
@@ -823,7 +836,7 @@ static int launch_persistent(Kernel kernel, int cs, int num_tiles, size_t smem, 
 
 // `tiles` is the logical tile grid: GEMM (n tiles, m tiles, 1); conv modes (f tiles, output rows, batch * channel tiles).
 static int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo, UmmaParams& p, dim3 tiles,
-                  cudaStream_t st) {
+                  cudaStream_t st, const CUtensorMap* a_slices = nullptr /* GEMM: {hi, lo} with 64-row boxes, {hi, lo} with 32-row boxes */) {
   {
     const char* e = getenv("B200SEP_DBG");  // development only: selectively disable parts of the kernel (results become wrong)
     p.dbg = e ? atoi(e) : 0;
@@ -849,6 +862,11 @@ static int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtens
     attr_set = true;
   }
   p.cluster = choose_cluster(p);
+  if (p.mode == 0 && p.cluster > 1) {
+    B2_CHECK_ARG(a_slices != nullptr, "umma: GEMM multicast needs the sliced activation maps");
+    const CUtensorMap* sl = a_slices + (p.cluster == 4 ? 2 : 0);
+    return launch_persistent(umma_pair_kernel, p.cluster, p.num_tiles, smem, st, sl[0], sl[1], b_hi, b_lo, p);
+  }
   return launch_persistent(umma_pair_kernel, p.cluster, p.num_tiles, smem, st, a_hi, a_lo, b_hi, b_lo, p);
 }
 
@@ -861,6 +879,10 @@ int umma_gemm_plan_create(UmmaGemmPlan* pl, const void* a_hi, const void* a_lo, 
     for (n_tile = 128; n_tile >= 16; n_tile -= 16)
       if (N % n_tile == 0) break;
   }
+  // prefer a tile width whose tile count along N is a multiple of 4 (then of 2): those tiles run as one cluster and share the activation rows by multicast
+  auto share = [&](int nt) { const int t = N / nt; return t % 4 == 0 ? 4 : (t % 2 == 0 ? 2 : 1); };
+  for (int cand : {96, 64})
+    if (N % cand == 0 && N >= cand && share(cand) > share(n_tile)) n_tile = cand;
   pl->n_tile = n_tile;
   const uint64_t da[2] = {(uint64_t)K, (uint64_t)M}, sa[1] = {(uint64_t)K * 2};
   const uint32_t ba[2] = {64, 128};
@@ -868,6 +890,11 @@ int umma_gemm_plan_create(UmmaGemmPlan* pl, const void* a_hi, const void* a_lo, 
   const uint32_t bb[2] = {64, (uint32_t)n_tile};
   int rc = make_map(&pl->a_hi, a_hi, 2, da, sa, ba);
   if (!rc) rc = make_map(&pl->a_lo, a_lo, 2, da, sa, ba);
+  const uint32_t ba2[2] = {64, 64}, ba4[2] = {64, 32};
+  if (!rc) rc = make_map(&pl->a_slices[0], a_hi, 2, da, sa, ba2);
+  if (!rc) rc = make_map(&pl->a_slices[1], a_lo, 2, da, sa, ba2);
+  if (!rc) rc = make_map(&pl->a_slices[2], a_hi, 2, da, sa, ba4);
+  if (!rc) rc = make_map(&pl->a_slices[3], a_lo, 2, da, sa, ba4);
   if (!rc) rc = make_map(&pl->b_hi, w_hi, 2, db, sa, bb);
   if (!rc) rc = make_map(&pl->b_lo, w_lo, 2, db, sa, bb);
   return rc;
@@ -902,7 +929,7 @@ int umma_gemm_run_ex(const UmmaGemmPlan& pl, int rows_per_channel, int channels,
   p.out_hi = (bf16*)out_hi; p.out_lo = (bf16*)out_lo; p.res_hi = (const bf16*)res_hi; p.res_lo = (const bf16*)res_lo;
   B2_CHECK_ARG(pl.n_tile <= 128, "umma_gemm: n_tile=%d exceeds the epilogue's 8 column groups", pl.n_tile);
   dim3 grid(pl.N / pl.n_tile, cdiv(M_active, kTileM));
-  return launch(pl.a_hi, pl.a_lo, pl.b_hi, pl.b_lo, p, grid, st);
+  return launch(pl.a_hi, pl.a_lo, pl.b_hi, pl.b_lo, p, grid, st, pl.a_slices);
 }
 
 bool umma_conv_supported(int Cin, int Cout, int F, int kh, int kw) {
