@@ -391,6 +391,16 @@ int b200sep_selftest_umma_conv3x3(const float* x, const float* w_host, float* ou
 int b200sep_selftest_umma_updown(const float* x, const float* w_host, const float* skip, float* out, int B, int Cin, int Cout, int T, int F,
                                  const float* scale, const float* shift, int relu, int up, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * CUDA-graph capture of a launch list issued through this ABI (csrc/api.cu): bracket any sequence of operator calls on `stream`, replay it with
+ * one launch.  The buffers must keep their addresses; run the sequence once before capturing.
+ */
+typedef struct b200sep_graph b200sep_graph;
+int b200sep_capture_begin(void* stream);
+int b200sep_capture_end(void* stream, b200sep_graph** out);
+int b200sep_graph_launch(b200sep_graph* graph, void* stream);
+void b200sep_graph_destroy(b200sep_graph* graph);
+
 #ifdef __cplusplus
 }
 #endif

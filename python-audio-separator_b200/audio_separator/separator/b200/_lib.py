@@ -109,6 +109,10 @@ _SIGS = {
     "b200sep_selftest_umma_gemm": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, vp]),
     "b200sep_selftest_umma_conv3x3": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, vp]),
     "b200sep_selftest_umma_updown": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp]),
+    "b200sep_capture_begin": (i32, [vp]),
+    "b200sep_capture_end": (i32, [vp, vp]),
+    "b200sep_graph_launch": (i32, [vp, vp]),
+    "b200sep_graph_destroy": (None, [vp]),
     "b200sep_mdx_run_model_work_floats": (i64, [vp, i32, i32, i32]),
     "b200sep_mdx_run_model": (i32, [vp, vp, vp, i64, i64, i64, i32, i32, i32, i32, vp, vp, vp]),
 }

@@ -260,6 +260,9 @@ class HTDemucsNet:
         self.freq_emb_t = torch.from_numpy(np.ascontiguousarray((np.float32(cfg.freq_emb) * emb).T)).to(self.device)
         self._pe_cache = {}
         self._emb_cache = {}
+        from .graphs import GraphedForward
+
+        self.graphed = GraphedForward(self.forward)
 
     def _check_structure(self, st):
         cfg = self.cfg
@@ -569,7 +572,7 @@ class DemucsEngine:
                 start = offset + off - (seg - clen) // 2
                 batch[j].copy_(ext[:, start - lo : start - lo + seg])
                 clens.append(clen)
-            y = net.forward(batch)  # (n, S, 2, seg)
+            y = net.graphed(batch)  # (n, S, 2, seg): the launch list of the forward, replayed as one CUDA graph per batch size
             for j, clen in enumerate(clens):  # center_trim to the chunk's valid length (apply.py:258), stored from sample 0
                 d = (seg - clen) // 2
                 buf[slot0 + j, :, :clen].copy_(y[j].reshape(S * 2, seg)[:, d : d + clen])

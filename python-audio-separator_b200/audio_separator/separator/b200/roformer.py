@@ -312,6 +312,9 @@ class RoformerEngine:
         m = np.arange(self.chunk_size, dtype=np.float64)
         ham = 0.54 - 0.46 * np.cos(2.0 * np.pi * m / (self.chunk_size - 1)) if self.chunk_size > 1 else np.ones(1)  # scipy.signal.windows.hamming (symmetric)
         self.window = torch.from_numpy(ham.astype(np.float32)).to(self.device)
+        from .graphs import GraphedForward
+
+        self.graphed = GraphedForward(self.net.forward)
 
     def demix_device(self, mix: torch.Tensor) -> torch.Tensor:
         """mix (2, N) cuda -> (n_out, 2, N): n_out = num_stems rows for multi-stem models, 1 row for single-target models."""
@@ -327,7 +330,7 @@ class RoformerEngine:
             batch = _new((len(group), 2, C), mix)
             for j, s in enumerate(group):
                 batch[j].copy_(mix[:, s : s + C])
-            y = self.net.forward(batch)  # (g, 2, L') or (g, S, 2, L')
+            y = self.graphed(batch)  # (g, 2, L') or (g, S, 2, L'): CUDA-graph replay of the forward's launch list
             Lp = y.shape[-1]
             if Lp != C:  # safe_len = min(length, x.shape[-1], window) (:252): hop does not divide the chunk -> zero weight beyond the model output
                 raise NotImplementedError("chunk sizes that are not a multiple of the STFT hop are not covered")

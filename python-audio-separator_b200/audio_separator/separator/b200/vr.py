@@ -424,6 +424,9 @@ class VREngine:
             else:
                 g = hp_f(nb, bp["hpf_start"], bp["hpf_stop"] - 1) * lp_f(nb, bp["lpf_start"], bp["lpf_stop"])
             self.syn_gain[d] = torch.from_numpy(g.astype(np.float32)).to(self.device)
+        from .graphs import GraphedForward
+
+        self.graphed = GraphedForward(self.net.predict_mask)
 
     # ---- resampling
     def _resample(self, x: torch.Tensor, orig_sr: int, target_sr: int) -> torch.Tensor:
@@ -544,7 +547,7 @@ class VREngine:
             batch = _new((b, 2, nb, self.window_size), mag)
             src = torch.as_strided(mag, (b, 2, nb, self.window_size), (roi, nb * n_pad, n_pad, 1), storage_offset=i * roi)
             copy_view(src, batch)
-            pred = self.net.predict_mask(batch)  # (b, 2, nb, roi)
+            pred = self.graphed(batch)  # (b, 2, nb, roi): CascadedASPPNet.predict_mask, its launch list replayed as one CUDA graph per batch size
             copy_view(pred, m4[:, :, i : i + b].permute(2, 0, 1, 3))
         return mask
 

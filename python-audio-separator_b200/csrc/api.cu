@@ -76,3 +76,47 @@ extern "C" int b200sep_mdx_run_model(const b200sep_stft_plan* plan, b200sep_mdxn
   }
   return b200sep_stft_inverse(plan, pred, batch, frames, dim_f, B200SEP_LAYOUT_CTF, wave_out, fr, stream);
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// CUDA-graph capture of a launch list issued through this ABI.  Every operator launches on the caller's stream and none synchronises, so a host
+// (C, C++ or the ctypes layer) can bracket any sequence of calls -- e.g. the several hundred launches of one HTDemucs forward -- and replay it with one
+// cudaGraphLaunch.  Buffers must keep their addresses between capture and replay; run the sequence once before capturing (first calls allocate
+// scratch memory, set kernel attributes and encode tensor maps, which stream capture does not allow).
+struct b200sep_graph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+};
+
+extern "C" int b200sep_capture_begin(void* stream) {
+  B2_CUDA(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal));
+  return B200SEP_OK;
+}
+
+extern "C" int b200sep_capture_end(void* stream, b200sep_graph** out) {
+  B2_CHECK_ARG(out, "capture_end: NULL argument");
+  b200sep_graph* g = new b200sep_graph();
+  cudaError_t e = cudaStreamEndCapture((cudaStream_t)stream, &g->graph);
+  if (e == cudaSuccess) e = cudaGraphInstantiate(&g->exec, g->graph, 0);
+  if (e != cudaSuccess) {
+    set_error("capture_end: %s", cudaGetErrorString(e));
+    if (g->graph) cudaGraphDestroy(g->graph);
+    delete g;
+    return B200SEP_ERR_CUDA;
+  }
+  *out = g;
+  return B200SEP_OK;
+}
+
+extern "C" int b200sep_graph_launch(b200sep_graph* g, void* stream) {
+  B2_CHECK_ARG(g && g->exec, "graph_launch: NULL graph");
+  B2_CUDA(cudaGraphLaunch(g->exec, (cudaStream_t)stream));
+  count_launch();
+  return B200SEP_OK;
+}
+
+extern "C" void b200sep_graph_destroy(b200sep_graph* g) {
+  if (!g) return;
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->graph) cudaGraphDestroy(g->graph);
+  delete g;
+}
