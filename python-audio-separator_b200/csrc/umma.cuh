@@ -153,6 +153,9 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
                : "r"(taddr)
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, "
@@ -163,18 +166,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
       : "r"(taddr)
       : "memory");
 }
-// N consecutive columns (N a multiple of 8) as the widest pieces available; no wait
+// N consecutive columns (N a multiple of 4) as the widest pieces available; no wait
 template <int N>
 __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t* v) {
-  static_assert(N % 8 == 0 && N >= 8, "tmem_ld_n: multiples of 8 columns");
+  static_assert(N % 4 == 0 && N >= 4, "tmem_ld_n: multiples of 4 columns");
   if constexpr (N >= 32) {
     tmem_ld32(taddr, v);
     if constexpr (N > 32) tmem_ld_n<N - 32>(taddr + 32, v + 32);
   } else if constexpr (N >= 16) {
     tmem_ld16(taddr, v);
     if constexpr (N > 16) tmem_ld_n<N - 16>(taddr + 16, v + 16);
-  } else {
+  } else if constexpr (N >= 8) {
     tmem_ld8(taddr, v);
+    if constexpr (N > 8) tmem_ld_n<N - 8>(taddr + 8, v + 8);
+  } else {
+    tmem_ld4(taddr, v);
   }
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }

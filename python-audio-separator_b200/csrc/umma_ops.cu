@@ -38,6 +38,8 @@ constexpr int kEpiParts = 2;  // epilogue warps per TMEM lane quadrant: the epil
 constexpr int kUmmaThreads = 64 + 128 * kEpiParts;  // warp 0 TMA, warp 1 MMA, then 4 * kEpiParts epilogue warps
 constexpr int kMaxChannels = 1024;  // per-channel scale/shift staged in shared memory (conv modes)
 constexpr int kTileM = 128;
+constexpr int kConv3Parts = 4;  // CONV3x3 kernel: epilogue warps per TMEM lane quadrant (16 warps: the epilogue is latency-bound at 2 warps per scheduler, 7.1 cycles per issued instruction)
+constexpr int kConv3Threads = 64 + 128 * kConv3Parts;
 constexpr int kConvStride = 112;  // output pixels per 3x3 tile: TMEM rows 8..119 of the 128 loaded pixels [f0 - 8, f0 + 120), so that loads AND stores start 16-byte aligned
 
 struct UmmaParams {
@@ -551,22 +553,22 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
 //   * the tile is staged in shared memory as [channel][pixel] bf16 planes and written with two cp.async.bulk.tensor stores per half
 //     (UTMASTG): no per-thread global stores, no 64-bit address arithmetic, full 224-byte rows per channel.
 template <int NC>
-__global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+__global__ void __launch_bounds__(kConv3Threads, 1) umma_conv3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                                                                      const __grid_constant__ CUtensorMap tmO_hi, const __grid_constant__ CUtensorMap tmO_lo,
                                                                      const UmmaParams p) {
-  constexpr int H = NC / 2;                 // channels per epilogue warp
+  constexpr int H = NC / kConv3Parts;       // channels per epilogue warp
   constexpr int kPlane = H * kConvStride;   // bf16 elements of one staged plane [H][112]
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  bf16* stage_out = reinterpret_cast<bf16*>(smem + (size_t)p.stages * p.stage_bytes);  // [n_sbuf][2 halves][hi, lo][H][112]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stage_out) + (size_t)p.n_sbuf * 4 * kPlane * sizeof(bf16));
+  bf16* stage_out = reinterpret_cast<bf16*>(smem + (size_t)p.stages * p.stage_bytes);  // [n_sbuf][kConv3Parts column parts][hi, lo][H][112]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stage_out) + (size_t)p.n_sbuf * 2 * kConv3Parts * kPlane * sizeof(bf16));
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full_bar = empty_bar + p.stages;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   float* sc_s = reinterpret_cast<float*>(tmem_slot + 4);
   float* sh_s = sc_s + kMaxChannels;
-  float* edge_base = sh_s + kMaxChannels;  // [2 halves][P_0 row 31 | P_2 row 0][4 quadrants][H]
+  float* edge_base = sh_s + kMaxChannels;  // [kConv3Parts][P_0 row 31 | P_2 row 0][4 quadrants][H]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -576,7 +578,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv3_kernel(const __gri
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
-      ptx::mbar_init(&tmem_empty_bar[a], 4 * kEpiParts);
+      ptx::mbar_init(&tmem_empty_bar[a], 4 * kConv3Parts);
     }
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tmA_hi);
@@ -602,7 +604,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv3_kernel(const __gri
     if (lane == 0) umma_mma_loop(p, smem, full_bar, empty_bar, tmem_full_bar, tmem_empty_bar, tmem_base, acc_stride);
   } else {
     const int q = warp & 3;           // TMEM lane quadrant
-    const int half = (warp - 2) >> 2;  // which NC/2 channels
+    const int half = (warp - 2) >> 2;  // which NC/kConv3Parts channels
     const int m = q * 32 + lane;
     const bool issuer = (q == 0) && (lane == 0);  // the thread of this half that owns the bulk store groups
     const bool out_row = (m >= 8) && (m < 8 + kConvStride);
@@ -684,7 +686,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_conv3_kernel(const __gri
           for (int j = 0; j < H; ++j) x[j] *= __bfloat162float(p.mul_hi[rbase + (size_t)j * plane]) + __bfloat162float(p.mul_lo[rbase + (size_t)j * plane]);
         }
       }
-      bf16* s_hi = stage_out + (size_t)(((p.n_sbuf == 2) ? (it & 1) : 0) * 2 + half) * 2 * kPlane;
+      bf16* s_hi = stage_out + (size_t)(((p.n_sbuf == 2) ? (it & 1) : 0) * kConv3Parts + half) * 2 * kPlane;
       bf16* s_lo = s_hi + kPlane;
       if (out_row) {
 #pragma unroll
@@ -796,9 +798,9 @@ static int choose_cluster(const UmmaParams& p) {
 
 // Persistent launch: one CTA per SM, as clusters of `cs` when the weight operand is multicast (the grid is then the number of co-resident clusters x cs).
 template <class Kernel, class... Args>
-static int launch_persistent(Kernel kernel, int cs, int num_tiles, size_t smem, cudaStream_t st, Args... args) {
+static int launch_persistent(Kernel kernel, int threads, int cs, int num_tiles, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg{};
-  cfg.blockDim = dim3(kUmmaThreads);
+  cfg.blockDim = dim3((unsigned)threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -865,9 +867,9 @@ static int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtens
   if (p.mode == 0 && p.cluster > 1) {
     B2_CHECK_ARG(a_slices != nullptr, "umma: GEMM multicast needs the sliced activation maps");
     const CUtensorMap* sl = a_slices + (p.cluster == 4 ? 2 : 0);
-    return launch_persistent(umma_pair_kernel, p.cluster, p.num_tiles, smem, st, sl[0], sl[1], b_hi, b_lo, p);
+    return launch_persistent(umma_pair_kernel, kUmmaThreads, p.cluster, p.num_tiles, smem, st, sl[0], sl[1], b_hi, b_lo, p);
   }
-  return launch_persistent(umma_pair_kernel, p.cluster, p.num_tiles, smem, st, a_hi, a_lo, b_hi, b_lo, p);
+  return launch_persistent(umma_pair_kernel, kUmmaThreads, p.cluster, p.num_tiles, smem, st, a_hi, a_lo, b_hi, b_lo, p);
 }
 
 bool umma_gemm_supported(int M, int N, int K) { return M >= 1 && N % 16 == 0 && K % 8 == 0 && N >= 16 && K >= 16; }
@@ -1005,7 +1007,7 @@ static int launch_conv3(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const 
     attr_set = true;
   }
   p.cluster = choose_cluster(p);
-  return launch_persistent(umma_conv3_kernel<NC>, p.cluster, p.num_tiles, smem, st, a_hi, a_lo, o_hi, o_lo, p);
+  return launch_persistent(umma_conv3_kernel<NC>, kConv3Threads, p.cluster, p.num_tiles, smem, st, a_hi, a_lo, o_hi, o_lo, p);
 }
 
 int umma_conv_run_ex(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_lo, int B, int Cout, int n_c, const UmmaEpilogue& e, cudaStream_t st) {
@@ -1026,22 +1028,24 @@ int umma_conv_run_ex(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_l
   p.n_ftiles = cdiv(pl.F, kConvStride);
   p.t_tiles = pl.T;
   p.num_tiles = p.n_ftiles * pl.T * B * p.n_tiles;
-  const size_t stage_plane = (size_t)(n_c / 2) * kConvStride * 2;  // bytes of one staged [n_c/2][112] bf16 plane
-  const size_t fixed = 1024 /*alignment slack*/ + 64 * sizeof(uint64_t) + 64 + 2 * kMaxChannels * sizeof(float) + (size_t)16 * (n_c / 2) * sizeof(float);
+  B2_CHECK_ARG(n_c % (4 * kConv3Parts) == 0, "umma_conv: n_c=%d is not a multiple of %d", n_c, 4 * kConv3Parts);
+  const size_t stage_plane = (size_t)(n_c / kConv3Parts) * kConvStride * 2;  // bytes of one staged [n_c/parts][112] bf16 plane
+  const size_t fixed = 1024 /*alignment slack*/ + 64 * sizeof(uint64_t) + 64 + 2 * kMaxChannels * sizeof(float) + (size_t)8 * n_c * sizeof(float);
   const size_t budget = 227 * 1024 - fixed;
   p.n_sbuf = 2;
-  int stages = (int)((budget - 2 * 4 * stage_plane) / p.stage_bytes);
+  const size_t sbuf_bytes = 2 * kConv3Parts * stage_plane;  // hi + lo plane per column part
+  int stages = (int)((budget - 2 * sbuf_bytes) / p.stage_bytes);
   if (stages < 3) {  // deep layers with 80 KB stages: one staging buffer leaves room for the ring
     p.n_sbuf = 1;
-    stages = (int)((budget - 4 * stage_plane) / p.stage_bytes);
+    stages = (int)((budget - sbuf_bytes) / p.stage_bytes);
   }
   if (stages > 8) stages = 8;
   B2_CHECK_ARG(stages >= 2, "umma_conv: a pipeline stage of %u bytes does not fit twice in shared memory", p.stage_bytes);
   p.stages = stages;
-  const size_t smem = (size_t)stages * p.stage_bytes + (size_t)p.n_sbuf * 4 * stage_plane + fixed;
+  const size_t smem = (size_t)stages * p.stage_bytes + (size_t)p.n_sbuf * sbuf_bytes + fixed;
   CUtensorMap o_hi, o_lo;
-  int rc = store_map(p.out_hi, pl.F, pl.T, B * p.out_c_total, n_c / 2, &o_hi);
-  if (!rc) rc = store_map(p.out_lo, pl.F, pl.T, B * p.out_c_total, n_c / 2, &o_lo);
+  int rc = store_map(p.out_hi, pl.F, pl.T, B * p.out_c_total, n_c / kConv3Parts, &o_hi);
+  if (!rc) rc = store_map(p.out_lo, pl.F, pl.T, B * p.out_c_total, n_c / kConv3Parts, &o_lo);
   if (rc) return rc;
   switch (n_c) {
     case 16: return launch_conv3<16>(pl.a_hi, pl.a_lo, o_hi, o_lo, p, smem, st);

@@ -108,3 +108,18 @@ def test_post_process_run_logic_matches_the_oracle(lib_built, golden_dir):
         w = vr.merge_weights(mk.min(axis=(0, 1)), 0.2)
         got = mk.copy() if w is None else mk + w[None, None, :] * (1 - mk)
         assert np.array_equal(got, ref)
+
+
+def test_band_upsampler_against_libsamplerate_when_present():
+    """the multi-band synthesis up-samples with librosa.resample(res_type="sinc_fastest") = libsamplerate, which is in neither the
+    reference tree nor this image, so oracle and product share a Kaiser polyphase stand-in and that ONE step is "parity unpinned".  Wherever the
+    `samplerate` wheel exists (a box with the reference installed) this test pins it: the stand-in must stay within the audio gate of libsamplerate
+    on band-limited material, and it fails loudly if it does not -- telling the maintainer the stand-in has to be replaced by the exact table."""
+    samplerate = pytest.importorskip("samplerate")
+    y = M.synth_music(7350 * 4, seed=3)[:, ::6].astype(np.float32)  # 4 s at 7350 Hz, the lowest 4band_v2 band rate
+    for sr_in, sr_out in ((7350, 14700), (14700, 44100)):
+        ref = np.stack([samplerate.resample(ch, sr_out / sr_in, "sinc_fastest") for ch in y])
+        got = V.upsample(y, sr_in, sr_out)
+        n = min(ref.shape[1], got.shape[1])
+        core = slice(64, n - 64)  # the two resamplers treat the edges differently
+        assert np.abs(got[:, core] - ref[:, core]).max() <= 1e-4
