@@ -38,7 +38,7 @@ constexpr int kEpiParts = 2;  // epilogue warps per TMEM lane quadrant: the epil
 constexpr int kUmmaThreads = 64 + 128 * kEpiParts;  // warp 0 TMA, warp 1 MMA, then 4 * kEpiParts epilogue warps
 constexpr int kMaxChannels = 1024;  // per-channel scale/shift staged in shared memory (conv modes)
 constexpr int kTileM = 128;
-constexpr int kConv3Parts = 4;  // CONV3x3 kernel: epilogue warps per TMEM lane quadrant (16 warps: the epilogue is latency-bound at 2 warps per scheduler, 7.1 cycles per issued instruction)
+constexpr int kConv3Parts = 2;  // CONV3x3 kernel: epilogue warps per TMEM lane quadrant.  Measured with 4 (16 epilogue warps, 88 registers): 530 us vs 477 us per scale-0 launch under ncu -- the epilogue is not what paces the kernel (profiles/README.md, round 2)
 constexpr int kConv3Threads = 64 + 128 * kConv3Parts;
 constexpr int kConvStride = 112;  // output pixels per 3x3 tile: TMEM rows 8..119 of the 128 loaded pixels [f0 - 8, f0 + 120), so that loads AND stores start 16-byte aligned
 
