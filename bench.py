@@ -353,7 +353,7 @@ class DemucsWorkload:
         torch = ctx.torch
         self.ctx, self.D, self.dm = ctx, D, dm
         self.ocfg = D.HTConfig()
-        self.nets = [dm.HTDemucsNet(dm.HTDemucsConfig(), D.make_weights(self.ocfg, seed=11 + i)) for i in range(4)]
+        self.nets = [dm.HTDemucsNet(dm.HTDemucsConfig(), D.make_weights(self.ocfg, seed=11 + i), device=torch.device("cuda", ctx.local)) for i in range(4)]
         self.bag = [[1.0 if s == m else 0.0 for s in range(4)] for m in range(4)]  # htdemucs_ft.yaml: one fine-tuned model per source
         self.eng = dm.DemucsEngine(self.nets, bag_weights=self.bag, overlap=0.25, batch_size=self.batch, dist=ctx.dist)
         rng = random.Random(0)
@@ -537,7 +537,7 @@ class VrWorkload:
         torch = ctx.torch
         self.ctx = ctx
         arch = 537238
-        self.eng = vr.VREngine(vr.VRNet(arch, 1344, V.make_weights(arch, seed=9)), V.four_band_v2_param(), window_size=512, aggression=10, batch_size=4)
+        self.eng = vr.VREngine(vr.VRNet(arch, 1344, V.make_weights(arch, seed=9), device=torch.device("cuda", ctx.local)), V.four_band_v2_param(), window_size=512, aggression=10, batch_size=4)
         self.mine = list(range(ctx.rank, self.tracks, ctx.world))  # vr_separator.py has no cross-file state: tracks are independent units
         base = O.normalize(music(self.N, 1234), 0.9, 0.0)
         # distinct tracks from one synthesised pattern: rotate it by a track-dependent offset (cheap, deterministic)
@@ -709,13 +709,28 @@ def main():
     line = measure(WORKLOADS[args.workload](args), ctx, args, args.steps, warmup, with_cpu=not args.no_cpu_baseline)
     if args.workload == "mdx" and args.also in WORKLOADS and args.also != "mdx":
         import gc
+        import signal
 
+        printed = []
+
+        def emit(extra):
+            if line is not None and not printed:
+                printed.append(1)
+                line["also"] = {args.also: extra}
+                print(json.dumps(line), flush=True)
+
+        # the headline line is already measured: a failure of the second workload (here or on a peer rank -- torchrun then SIGTERMs this one) must not lose it
+        signal.signal(signal.SIGTERM, lambda *_: (emit({"error": "terminated: a peer rank failed during this workload"}), os._exit(0)))
         gc.collect()
         ctx.torch.cuda.empty_cache()
-        extra = measure(WORKLOADS[args.also](args), ctx, args, min(args.steps, 2), 3, with_cpu=not args.no_cpu_baseline)
-        if line is not None:
-            line["also"] = {args.also: extra}
-    if line is not None:
+        try:
+            extra = measure(WORKLOADS[args.also](args), ctx, args, min(args.steps, 2), 3, with_cpu=not args.no_cpu_baseline)
+        except Exception as e:  # noqa: BLE001
+            extra = {"error": f"{type(e).__name__}: {e}"[:500]}
+            emit(extra)
+            os._exit(0 if ctx.rank == 0 else 1)
+        emit(extra)
+    elif line is not None:
         print(json.dumps(line), flush=True)
     if ctx.dist is not None:
         ctx.dist.destroy_process_group()

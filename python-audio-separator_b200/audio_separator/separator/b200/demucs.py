@@ -228,11 +228,11 @@ def _gemm_raw(a_ptr, b_ptr, c_ptr, M, N, K, lda, ldb, ldc, batch, sA, sB, sC, al
 class HTDemucsNet:
     """Device-resident HTDemucs weights (re-blocked for the conv kernel) + the launch sequence of one forward."""
 
-    def __init__(self, cfg: HTDemucsConfig, state: dict, device="cuda:0"):
+    def __init__(self, cfg: HTDemucsConfig, state: dict, device=None):
         _require_cuda()
         cfg.validate()
         self.cfg = cfg
-        self.device = torch.device(device)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())  # one process per GPU: the rank's own device
         self.S = len(cfg.sources)
         self.stft = StftPlan(cfg.nfft, cfg.hop)
         self.W = {}

@@ -167,10 +167,10 @@ class BSRoformerNet:
     """BS-Roformer (cfg: BSRoformerConfig) or Mel-Band Roformer (cfg: MelBandRoformerConfig): the graphs differ only in the band layout (disjoint
     slices vs gathered, overlapping mel bands whose masks are averaged), the per-transformer output norm and the mask MLP depth."""
 
-    def __init__(self, cfg, state: dict, device="cuda:0"):
+    def __init__(self, cfg, state: dict, device=None):
         _require_cuda()
         self.cfg = cfg
-        self.device = torch.device(device)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())  # one process per GPU: the rank's own device
         if not cfg.stereo:
             raise NotImplementedError("mono BS-Roformer checkpoints are not covered (the STFT kernels process stereo pairs)")
         self.stft = StftPlan(cfg.stft_n_fft, cfg.stft_hop_length)

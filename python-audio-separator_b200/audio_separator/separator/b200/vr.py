@@ -130,14 +130,14 @@ def capacity(nn_architecture: int):
 class VRNet:
     """CascadedASPPNet in eval mode: BatchNorm folded into the preceding (bias-free) convolution, Dropout = identity."""
 
-    def __init__(self, nn_architecture: int, n_fft_bins: int, state: dict, device="cuda:0"):
+    def __init__(self, nn_architecture: int, n_fft_bins: int, state: dict, device=None):
         _require_cuda()
         self.arch = int(nn_architecture)
         self.c1, self.cb, self.c2, self.c3 = capacity(self.arch)
         self.n_enc = 5 if self.arch == 129605 else 4
         self.n_extra = 1 if self.arch == 129605 else (2 if self.arch in (537238, 537227, 33966) else 0)
         self.max_bin, self.output_bin, self.offset = n_fft_bins // 2, n_fft_bins // 2 + 1, 128
-        self.device = torch.device(device)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())  # one process per GPU: the rank's own device
         st = {k: np.asarray(v) for k, v in state.items()}
         self.W = {}
         self._fold_all(st)
@@ -259,12 +259,12 @@ class VRNet51(VRNet):
     """CascadedNet of VR 5.1 (vr_network/nets_new.py:52-160, layers_new.py): five band nets with stride-2 encoders, an ASPP of dilated 3x3 convolutions
     (dilations (4,2), (8,4), (12,6)) and a bidirectional-LSTM branch over the time axis in front of the last decoder; eval mode (BatchNorm folded)."""
 
-    def __init__(self, n_fft_bins: int, nout: int, nout_lstm: int, state: dict, nn_arch_size: int = 56817, device="cuda:0"):
+    def __init__(self, n_fft_bins: int, nout: int, nout_lstm: int, state: dict, nn_arch_size: int = 56817, device=None):
         _require_cuda()
         self.arch = int(nn_arch_size)
         self.nout = 64 if self.arch == 218409 else int(nout)
         self.max_bin, self.output_bin, self.offset = n_fft_bins // 2, n_fft_bins // 2 + 1, 64
-        self.device = torch.device(device)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())  # one process per GPU: the rank's own device
         st = {k: np.asarray(v) for k, v in state.items()}
         self.W = {}
         self._fold_all(st)

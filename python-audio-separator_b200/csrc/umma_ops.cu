@@ -47,6 +47,8 @@ struct UmmaParams {
   int f_stride, t_mul, t_off;  // implicit-GEMM addressing: tile f0 = blockIdx.x*f_stride, input row = t*t_mul + r + t_off
   int f_off;                   // first input pixel of a tile = f0 + f_off (CONV3x3: -8, so that the 112 outputs of a tile start 16-byte aligned)
   int n_sbuf;                  // CONV3x3: output staging buffers per epilogue half (2 when shared memory allows)
+  int b_resident;              // CONV3x3 with one weight tile that fits (Cin = Cout = 48: 83 KB): the whole B operand is loaded ONCE per CTA and the ring carries only A
+  uint32_t b_res_off;          //   byte offset of the resident image [num_iters][hi | lo] from the start of dynamic shared memory (after alignment)
   int cluster;                 // conv modes: CTAs per cluster walking tiles of the same weight tile in lockstep; each loads 1/cluster of every B stage and multicasts it
   int n_tile, n_total, tmem_cols;
   int num_iters, ksteps, stages;
@@ -115,9 +117,17 @@ __device__ __forceinline__ TileCoord decode_tile(const UmmaParams& p, int tile) 
 
 // ===== TMA producer (one thread): fills the shared-memory ring, continuous across the tiles of this CTA =====
 __device__ __forceinline__ void umma_producer_loop(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUtensorMap& tmB_hi, const CUtensorMap& tmB_lo,
-                                                   const UmmaParams& p, uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar) {
+                                                   const UmmaParams& p, uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar, uint64_t* wres_bar = nullptr) {
   int s = 0;
   uint32_t phase = 0;
+  if (p.b_resident) {  // the layer's whole weight operand, once: [iteration][hi | lo] blocks of b_bytes
+    ptx::mbar_arrive_expect_tx(wres_bar, 2u * p.b_bytes * (uint32_t)p.num_iters);
+    for (int i = 0; i < p.num_iters; ++i) {
+      uint8_t* dst = smem + p.b_res_off + (size_t)i * 2 * p.b_bytes;
+      ptx::bulk_load_1d(dst, p.wb_hi + (size_t)i * (p.b_bytes / 2), p.b_bytes, wres_bar);
+      ptx::bulk_load_1d(dst + p.b_bytes, p.wb_lo + (size_t)i * (p.b_bytes / 2), p.b_bytes, wres_bar);
+    }
+  }
   for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
     const TileCoord tc = decode_tile(p, tile);
     const int n0 = tc.n_idx * p.n_tile;
@@ -128,7 +138,7 @@ __device__ __forceinline__ void umma_producer_loop(const CUtensorMap& tmA_hi, co
       uint8_t* a_lo = st + p.a_bytes;
       uint8_t* b_hi = st + 2 * p.a_bytes;
       uint8_t* b_lo = b_hi + p.b_bytes;
-      ptx::mbar_arrive_expect_tx(&full_bar[s], ((p.dbg & 8) ? 0 : 2 * p.a_bytes) + ((p.dbg & 16) ? 0 : 2 * p.b_bytes));
+      ptx::mbar_arrive_expect_tx(&full_bar[s], ((p.dbg & 8) ? 0 : 2 * p.a_bytes) + (((p.dbg & 16) || p.b_resident) ? 0 : 2 * p.b_bytes));
       if (p.mode == 0) {
         const int k0 = i * 64;
         if (p.cluster > 1) {
@@ -157,7 +167,9 @@ __device__ __forceinline__ void umma_producer_loop(const CUtensorMap& tmA_hi, co
           ptx::tma_load_3d(a_lo + box, &tmA_lo, &full_bar[s], cf + 64, ct, cc);
         }
         const size_t woff = ((size_t)tc.n_idx * p.num_iters + i) * (size_t)(p.b_bytes / 2);
-        if (p.cluster > 1) {
+        if (p.b_resident) {
+          // nothing to fetch: the weights are resident
+        } else if (p.cluster > 1) {
           // the CTAs of a cluster are at the same (weight tile, iteration): this one fetches its 1/cluster share of the stage for all of them
           const uint32_t slice = p.b_bytes / (uint32_t)p.cluster, off = ptx::cluster_ctarank() * slice;
           const uint16_t mask = (uint16_t)((1u << p.cluster) - 1u);
@@ -178,8 +190,9 @@ __device__ __forceinline__ void umma_producer_loop(const CUtensorMap& tmA_hi, co
 
 // ===== MMA issuer (one thread): three bf16 UMMAs per k-step into one of two TMEM accumulators =====
 __device__ __forceinline__ void umma_mma_loop(const UmmaParams& p, uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar, uint64_t* tmem_full_bar,
-                                              uint64_t* tmem_empty_bar, uint32_t tmem_base, uint32_t acc_stride) {
+                                              uint64_t* tmem_empty_bar, uint32_t tmem_base, uint32_t acc_stride, uint64_t* wres_bar = nullptr) {
   const uint32_t idesc = ptx::instr_desc_bf16(kTileM, p.n_tile, p.mode != 0 ? 1 : 0, 0);
+  if (p.b_resident) ptx::mbar_wait(wres_bar, 0, 500);  // the resident weight image has landed
   int s = 0, acc = 0;
   uint32_t phase = 0, acc_phase = 0;
   for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -190,7 +203,8 @@ __device__ __forceinline__ void umma_mma_loop(const UmmaParams& p, uint8_t* smem
       ptx::mbar_wait(&full_bar[s], phase, 200 + i);
       ptx::tc_fence_after();
       const uint32_t st = ptx::smem_u32(smem + (size_t)s * p.stage_bytes);
-      const uint32_t a_hi = st, a_lo = st + p.a_bytes, b_hi = st + 2 * p.a_bytes, b_lo = b_hi + p.b_bytes;
+      const uint32_t a_hi = st, a_lo = st + p.a_bytes;
+      const uint32_t b_hi = p.b_resident ? ptx::smem_u32(smem + p.b_res_off + (size_t)i * 2 * p.b_bytes) : st + 2 * p.a_bytes, b_lo = b_hi + p.b_bytes;
       for (int j = 0; j < ((p.dbg & 4) ? 0 : p.ksteps); ++j) {
         uint64_t dah, dal, dbh, dbl;
         if (p.mode == 0) {
@@ -560,12 +574,14 @@ __global__ void __launch_bounds__(kConv3Threads, 1) umma_conv3_kernel(const __gr
   constexpr int kPlane = H * kConvStride;   // bf16 elements of one staged plane [H][112]
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  bf16* stage_out = reinterpret_cast<bf16*>(smem + (size_t)p.stages * p.stage_bytes);  // [n_sbuf][kConv3Parts column parts][hi, lo][H][112]
+  // [ring: stages x stage_bytes][resident weights, when b_resident][output staging][barriers, BN coefficients, edge rows]
+  bf16* stage_out = reinterpret_cast<bf16*>(smem + (size_t)p.stages * p.stage_bytes + (p.b_resident ? (size_t)2 * p.b_bytes * p.num_iters : 0));  // [n_sbuf][parts][hi, lo][H][112]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stage_out) + (size_t)p.n_sbuf * 2 * kConv3Parts * kPlane * sizeof(bf16));
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full_bar = empty_bar + p.stages;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* wres_bar = tmem_empty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wres_bar + 1);
   float* sc_s = reinterpret_cast<float*>(tmem_slot + 4);
   float* sh_s = sc_s + kMaxChannels;
   float* edge_base = sh_s + kMaxChannels;  // [kConv3Parts][P_0 row 31 | P_2 row 0][4 quadrants][H]
@@ -580,6 +596,7 @@ __global__ void __launch_bounds__(kConv3Threads, 1) umma_conv3_kernel(const __gr
       ptx::mbar_init(&tmem_full_bar[a], 1);
       ptx::mbar_init(&tmem_empty_bar[a], 4 * kConv3Parts);
     }
+    ptx::mbar_init(wres_bar, 1);
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tmA_hi);
     ptx::prefetch_tensormap(&tmA_lo);
@@ -599,9 +616,9 @@ __global__ void __launch_bounds__(kConv3Threads, 1) umma_conv3_kernel(const __gr
   const uint32_t acc_stride = (uint32_t)p.tmem_cols / 2;
 
   if (warp == 0) {
-    if (lane == 0) umma_producer_loop(tmA_hi, tmA_lo, tmA_hi, tmA_lo, p, smem, full_bar, empty_bar);
+    if (lane == 0) umma_producer_loop(tmA_hi, tmA_lo, tmA_hi, tmA_lo, p, smem, full_bar, empty_bar, wres_bar);
   } else if (warp == 1) {
-    if (lane == 0) umma_mma_loop(p, smem, full_bar, empty_bar, tmem_full_bar, tmem_empty_bar, tmem_base, acc_stride);
+    if (lane == 0) umma_mma_loop(p, smem, full_bar, empty_bar, tmem_full_bar, tmem_empty_bar, tmem_base, acc_stride, wres_bar);
   } else {
     const int q = warp & 3;           // TMEM lane quadrant
     const int half = (warp - 2) >> 2;  // which NC/kConv3Parts channels
@@ -943,7 +960,6 @@ int umma_conv_choose(int Cin, int Cout, int* kc, int* n_c) {
   int k = 64;
   while (k > 16 && Cin % k != 0) k -= 16;
   if (Cin % 48 == 0) k = 48;
-  *kc = k;
   int nc = 16;
   const int cand[5] = {48, 80, 64, 32, 16};
   for (int i = 0; i < 5; ++i)
@@ -951,6 +967,20 @@ int umma_conv_choose(int Cin, int Cout, int* kc, int* n_c) {
       nc = cand[i];
       break;
     }
+  // the ring needs at least two stages next to the output staging tile of the TMA-store epilogue: shrink the channel step of wide tiles
+  // (n_c = 80 with 64 channels per stage is a 92 KB stage: MDX23C's 640-channel scale)
+  auto fits = [&](int kk) {
+    const size_t stage = ((size_t)2 * kk * 256 + (size_t)2 * (kk / 16) * (3 * nc) * 32 + 1023) / 1024 * 1024;
+    const size_t staging = (size_t)2 * kConv3Parts * (nc / kConv3Parts) * kConvStride * 2;
+    return 2 * stage + staging + 16 * 1024 <= 227 * 1024;
+  };
+  while (!fits(k) && k > 16) {
+    int kk = k - 16;
+    while (kk > 16 && Cin % kk != 0) kk -= 16;
+    if (Cin % kk != 0) break;
+    k = kk;
+  }
+  *kc = k;
   *n_c = nc;
   return 0;
 }
@@ -1022,7 +1052,12 @@ int umma_conv_run_ex(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_l
   fill_epilogue(p, e, Cout);
   B2_CHECK_ARG(Cout <= kMaxChannels, "umma_conv: more than %d output channels", kMaxChannels);
   B2_CHECK_ARG(e.out_f32 == nullptr, "umma_conv: 3x3 convolutions write pair tensors only");
-  p.stage_bytes = ((2 * p.a_bytes + 2 * p.b_bytes + 1023) / 1024) * 1024;
+  // one weight tile whose whole B operand fits next to the ring (Cin = Cout = 48: 83 KB): keep it resident; the shared-memory data pipe is the kernel's
+  // limiter (TC operand fetch + TMA fill + epilogue stores, profiles/README.md round 2) and the per-tile weight refill was 30 % of the TMA fill
+  const size_t b_all = (size_t)2 * p.b_bytes * p.num_iters;
+  static const bool allow_res = !(getenv("B200SEP_WRES") && atoi(getenv("B200SEP_WRES")) == 0);
+  p.b_resident = (allow_res && p.n_tiles == 1 && b_all <= 96 * 1024) ? 1 : 0;
+  p.stage_bytes = ((2 * p.a_bytes + (p.b_resident ? 0 : 2 * p.b_bytes) + 1023) / 1024) * 1024;
   p.tmem_cols = 2 * pow2_cols(p.n_tile);
   B2_CHECK_ARG(p.tmem_cols <= 512, "umma_conv: n_c=%d needs more than 512 TMEM columns", n_c);
   p.n_ftiles = cdiv(pl.F, kConvStride);
@@ -1030,7 +1065,8 @@ int umma_conv_run_ex(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_l
   p.num_tiles = p.n_ftiles * pl.T * B * p.n_tiles;
   B2_CHECK_ARG(n_c % (4 * kConv3Parts) == 0, "umma_conv: n_c=%d is not a multiple of %d", n_c, 4 * kConv3Parts);
   const size_t stage_plane = (size_t)(n_c / kConv3Parts) * kConvStride * 2;  // bytes of one staged [n_c/parts][112] bf16 plane
-  const size_t fixed = 1024 /*alignment slack*/ + 64 * sizeof(uint64_t) + 64 + 2 * kMaxChannels * sizeof(float) + (size_t)8 * n_c * sizeof(float);
+  const size_t fixed = 1024 /*alignment slack*/ + 64 * sizeof(uint64_t) + 64 + 2 * kMaxChannels * sizeof(float) + (size_t)8 * n_c * sizeof(float) +
+                       (p.b_resident ? b_all : 0);
   const size_t budget = 227 * 1024 - fixed;
   p.n_sbuf = 2;
   const size_t sbuf_bytes = 2 * kConv3Parts * stage_plane;  // hi + lo plane per column part
@@ -1042,6 +1078,7 @@ int umma_conv_run_ex(const UmmaConvPlan& pl, const void* wb_hi, const void* wb_l
   if (stages > 8) stages = 8;
   B2_CHECK_ARG(stages >= 2, "umma_conv: a pipeline stage of %u bytes does not fit twice in shared memory", p.stage_bytes);
   p.stages = stages;
+  p.b_res_off = (uint32_t)((size_t)stages * p.stage_bytes);
   const size_t smem = (size_t)stages * p.stage_bytes + (size_t)p.n_sbuf * sbuf_bytes + fixed;
   CUtensorMap o_hi, o_lo;
   int rc = store_map(p.out_hi, pl.F, pl.T, B * p.out_c_total, n_c / kConv3Parts, &o_hi);

@@ -44,7 +44,7 @@ def test_umma_gemm_vs_torch(lib, M, N, K, rpc, ch, res):
 
 
 @pytest.mark.timeout(120)
-@pytest.mark.parametrize("B,Cin,Cout,T,Fq", [(1, 16, 16, 4, 128), (2, 48, 48, 8, 256), (1, 96, 96, 6, 192), (1, 32, 64, 5, 96), (2, 144, 144, 4, 64), (1, 288, 288, 8, 96), (1, 48, 48, 16, 3072)])
+@pytest.mark.parametrize("B,Cin,Cout,T,Fq", [(1, 16, 16, 4, 128), (2, 48, 48, 8, 256), (1, 96, 96, 6, 192), (1, 32, 64, 5, 96), (2, 144, 144, 4, 64), (1, 288, 288, 8, 96), (1, 48, 48, 16, 3072), (1, 640, 640, 3, 64), (1, 256, 256, 4, 128), (1, 768, 768, 2, 32)])  # the last three: MDX23C widths (n_c 80 / 64 / 48, smaller channel steps)
 def test_umma_conv3x3_vs_torch(lib, B, Cin, Cout, T, Fq):
     g = torch.Generator(device="cuda").manual_seed(B * 1000 + Cin + Cout + T + Fq)
     x = torch.randn(B, Cin, T, Fq, device="cuda", generator=g)
