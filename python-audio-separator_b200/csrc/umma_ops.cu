@@ -581,7 +581,7 @@ __global__ void __launch_bounds__(kConv3Threads, 1) umma_conv3_kernel(const __gr
   uint64_t* tmem_full_bar = empty_bar + p.stages;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
   uint64_t* wres_bar = tmem_empty_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wres_bar + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wres_bar + 2);  // (+2: keeps everything behind it 16-byte aligned -- sc_s / sh_s / the edge rows are read as float4)
   float* sc_s = reinterpret_cast<float*>(tmem_slot + 4);
   float* sh_s = sc_s + kMaxChannels;
   float* edge_base = sh_s + kMaxChannels;  // [kConv3Parts][P_0 row 31 | P_2 row 0][4 quadrants][H]
