@@ -45,6 +45,10 @@ def main():
         ref = ens.Ensembler(logging.getLogger("ref"), algo).ensemble([w.copy() for w in mono])
         check(f"Ensembler {algo} (mono)", ref, E.ensemble([w.copy() for w in mono], algo), 1e-6)
         out[f"{algo}_mono"] = np.asarray(ref, dtype=np.float32)
+    # ensemble_wav (spec_utils.ensemble_wav): the reference's own function on the same waveforms
+    for tag, wl in (("4", waves), ("3", waves[:3])):
+        ref = ens.Ensembler(logging.getLogger("ref"), "ensemble_wav").ensemble([w.copy() for w in wl])
+        out[f"ensemble_wav_{tag}"] = np.asarray(ref, dtype=np.float32)
     np.savez_compressed(os.path.join(GOLD, "ensemble_small.npz"), **out)
     print("wrote tests/golden/ensemble_small.npz; oracle pinned: OK")
 

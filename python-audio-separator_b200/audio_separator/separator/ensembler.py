@@ -1,6 +1,6 @@
 """B200 mirror of the reference's Ensembler (audio_separator/separator/ensembler.py): same constructor `(logger, algorithm, weights)` and
 `ensemble(waveforms) -> ndarray`, the reductions over the model axis (and the 2048 / 1024 STFTs of the *_fft and uvr_* algorithms) run on the GPU.
-`ensemble_wav` (spec_utils.ensemble_wav splits a (channels, length) array along the CHANNEL axis into 240 parts, most of them empty) is not covered."""
+`ensemble_wav` (spec_utils.ensemble_wav: a per-channel pick of the quietest model) is a handful of host comparisons and mirrors the numpy semantics."""
 import numpy as np
 import torch
 
@@ -42,6 +42,24 @@ class Ensembler:
         check(lib.b200sep_stft_inverse_ex(self._plan.handle, _ptr(planes), 1, frames, 1025, LAYOUT_CFT, length, 1024, 0, 1.0, _ptr(wave), _ptr(work), _stream()), "stft_inverse_ex")
         return wave
 
+    @staticmethod
+    def _ensemble_wav(waveforms, split_size=240):
+        """spec_utils.ensemble_wav (spec_utils.py:1245-1266): every waveform is np.array_split into 240 parts ALONG ITS FIRST AXIS -- for the (channels, length)
+        arrays the Separator passes that is the channel axis, so parts 0..channels-1 are one channel row each and the rest are empty -- and for every part the
+        waveform with the lowest mean |x| is taken.  A few comparisons per file: host arithmetic, same numpy semantics (an empty part's mean is nan and
+        argmin then picks the first waveform)."""
+        parts = [np.array_split(np.asarray(w), split_size) for w in waveforms]
+        out = []
+        with np.errstate(invalid="ignore", divide="ignore"):
+            import warnings
+
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", RuntimeWarning)
+                for k in range(split_size):
+                    means = [np.abs(p[k]).mean() for p in parts]
+                    out.append(parts[int(np.argmin(means))][k])
+        return np.concatenate(out)
+
     def ensemble(self, waveforms):
         """waveforms: list of (channels, length) arrays -> (channels, length) (ensembler.py:18-92)"""
         if not waveforms:
@@ -51,7 +69,10 @@ class Ensembler:
         if self.algorithm not in ALGORITHMS:
             raise ValueError(f"Unknown ensemble algorithm: {self.algorithm}")
         if self.algorithm == "ensemble_wav":
-            raise NotImplementedError("ensemble_wav is not part of the accelerated ensembler")
+            if any(w.shape[0] != waveforms[0].shape[0] for w in waveforms):
+                raise ValueError("All waveforms must have the same number of channels for ensembling.")
+            n = max(w.shape[1] for w in waveforms)  # zero-padded to the longest first (ensembler.py:27-29)
+            return self._ensemble_wav([np.pad(w, ((0, 0), (0, n - w.shape[1]))) if w.shape[1] < n else w for w in waveforms])
         if not torch.cuda.is_available():
             raise RuntimeError("Ensembler (B200 build) needs a CUDA device: there is no CPU path in this package")
         num_channels = waveforms[0].shape[0]

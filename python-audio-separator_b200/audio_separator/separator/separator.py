@@ -7,8 +7,12 @@ import importlib
 import json
 import logging
 import os
+import re
+import shutil
+import tempfile
 import time
 
+import numpy as np
 import torch
 
 # UVR model_data_new.json entries for the BASELINE models (looked up by MD5 at runtime in the reference, separator.py:786-824)
@@ -16,6 +20,16 @@ KNOWN_MODEL_DATA = {
     "UVR-MDX-NET-Inst_HQ_3.onnx": {"compensate": 1.022, "mdx_dim_f_set": 3072, "mdx_dim_t_set": 8, "mdx_n_fft_scale_set": 6144, "primary_stem": "Instrumental"},
     "UVR-MDX-NET-Inst_HQ_5.onnx": {"compensate": 1.010, "mdx_dim_f_set": 2560, "mdx_dim_t_set": 8, "mdx_n_fft_scale_set": 5120, "primary_stem": "Instrumental"},
 }
+
+
+# canonical stem names of the ensemble grouping (separator.py:29-49)
+STEM_NAME_MAP = {
+    "vocals": "Vocals", "instrumental": "Instrumental", "inst": "Instrumental", "karaoke": "Instrumental", "other": "Other", "no_vocals": "Instrumental",
+    "drums": "Drums", "bass": "Bass", "guitar": "Guitar", "piano": "Piano", "synthesizer": "Synthesizer", "strings": "Strings", "woodwinds": "Woodwinds",
+    "brass": "Brass", "wind inst": "Wind Inst", "lead vocals": "Lead Vocals", "backing vocals": "Backing Vocals", "primary stem": "Primary Stem",
+    "secondary stem": "Secondary Stem",
+}
+_SLUG_PREFIXES = ("mel_band_roformer_", "melband_roformer_", "bs_roformer_", "model_bs_roformer_", "UVR-MDX-NET-", "UVR_MDXNET_")
 
 
 class Separator:
@@ -45,8 +59,13 @@ class Separator:
         if self.sample_rate <= 0 or self.sample_rate > 12800000:
             raise ValueError(f"The sample rate setting is {self.sample_rate} but it must be a non-zero whole number.")
         self.use_soundfile, self.use_autocast = use_soundfile, use_autocast
-        if ensemble_algorithm or ensemble_preset or chunk_duration:
-            raise NotImplementedError("ensembles / file-level chunking are outside the B200 hot-path scope")
+        if ensemble_preset or chunk_duration:
+            raise NotImplementedError("ensemble presets (ensemble_presets.json) / file-level chunking are outside the B200 hot-path scope; pass the model list and algorithm explicitly")
+        self.ensemble_algorithm = ensemble_algorithm or "avg_wave"  # separator.py:237-238
+        self.ensemble_weights = ensemble_weights
+        self.ensemble_preset = None
+        self.model_filename = None
+        self.model_filenames = []
         self.arch_specific_params = {
             "MDX": {"hop_length": 1024, "segment_size": 256, "overlap": 0.25, "batch_size": 1, "enable_denoise": False, **(mdx_params or {})},
             "VR": {"batch_size": 1, "window_size": 512, "aggression": 5, "enable_tta": False, "enable_post_process": False, "post_process_threshold": 0.2, "high_end_process": False, **(vr_params or {})}, "Demucs": {"segment_size": "Default", "shifts": 2, "overlap": 0.25, "segments_enabled": True, **(demucs_params or {})}, "MDXC": {"segment_size": 256, "override_model_segment_size": False, "batch_size": 1, "overlap": 8, "pitch_shift": 0, **(mdxc_params or {})},
@@ -85,8 +104,15 @@ class Separator:
         raise ValueError(f"no model parameters for {name}: put a {os.path.basename(side)} (UVR model_data entry) next to the model file")
 
     def load_model(self, model_filename="UVR-MDX-NET-Inst_HQ_3.onnx"):
-        if isinstance(model_filename, (list, tuple)):
-            raise NotImplementedError("multi-model ensembles are outside the B200 hot-path scope")
+        if isinstance(model_filename, (list, tuple)):  # several models = an ensemble: they are loaded one after the other inside separate() (separator.py:839-845)
+            if len(model_filename) > 1:
+                self.model_filename = list(model_filename)
+                self.model_filenames = list(model_filename)
+                self.logger.info(f"Multiple models specified for ensembling: {self.model_filenames}")
+                return
+            model_filename = model_filename[0]
+        self.model_filename = model_filename
+        self.model_filenames = [model_filename]
         t0 = time.perf_counter()
         model_path = model_filename if os.path.isabs(model_filename) else os.path.join(self.model_file_dir, model_filename)
         if not os.path.isfile(model_path):
@@ -112,6 +138,8 @@ class Separator:
         self.logger.info(f"Loading model completed in {time.perf_counter() - t0:.2f}s")
 
     def separate(self, audio_file_path, custom_output_names=None):
+        if isinstance(self.model_filename, list) and len(self.model_filename) > 1:
+            return self._separate_ensemble(audio_file_path, custom_output_names)
         if self.model_instance is None:
             raise ValueError("Initialization failed or model not loaded. Please load a model before attempting to separate.")
         paths = [audio_file_path] if isinstance(audio_file_path, str) else list(audio_file_path)
@@ -128,6 +156,72 @@ class Separator:
                 except Exception as e:  # per-file errors are logged, not raised (separator.py:978-987)
                     self.logger.error(f"Failed to process file {f}: {e}")
         return outputs
+
+    def _separate_ensemble(self, audio_file_path, custom_output_names=None):
+        """Several models on the same file, their stems grouped by canonical stem name and reduced by the Ensembler (separator.py:1242-1412).
+        Every model runs on the GPU through its plugin, the intermediate stems go through a temporary directory exactly as in the reference (the file round trip
+        quantises them to the input bit depth there too), and the reductions over the model axis run on the GPU (audio_separator/separator/ensembler.py)."""
+        from .ensembler import Ensembler
+
+        paths = [audio_file_path] if isinstance(audio_file_path, str) else list(audio_file_path)
+        models, output_files = list(self.model_filenames), []
+        for path in paths:
+            temp_dir = tempfile.mkdtemp(prefix="audio-separator-ensemble-")
+            original_output_dir = self.output_dir
+            try:
+                stems_by_type = {}
+                for model_filename in models:
+                    self.logger.info(f"Processing with model: {model_filename}")
+                    self.load_model(model_filename)
+                    self.output_dir = temp_dir
+                    self.model_instance.output_dir = temp_dir
+                    try:
+                        model_stems = self._separate_file(path, None)  # default "base_(Stem)_model.ext" names: the stem type is parsed from them
+                    finally:
+                        self.output_dir = original_output_dir
+                    names = []
+                    for stem_path in model_stems:
+                        m = re.search(r"_\(([^)]+)\)", os.path.basename(stem_path))
+                        names.append(m.group(1) if m else "Unknown")
+                    has_vocal = any("vocal" in n.lower() for n in names)
+                    for stem_path, raw in zip(model_stems, names):
+                        low = raw.lower()
+                        if "vocal" in low and "lead" not in low and "backing" not in low:
+                            stem = "Vocals"
+                        elif low == "other" and len(names) == 2 and has_vocal:
+                            stem = "Instrumental"  # the non-vocal stem of a two-stem model
+                        else:
+                            stem = STEM_NAME_MAP.get(low, raw.title())
+                        stems_by_type.setdefault(stem, []).append(stem_path if os.path.isabs(stem_path) else os.path.join(temp_dir, stem_path))
+                ensembler = Ensembler(self.logger, self.ensemble_algorithm, self.ensemble_weights)
+                base_name = os.path.splitext(os.path.basename(path))[0]
+                writer = self.model_instance
+                for stem_name, stem_paths in stems_by_type.items():
+                    self.logger.info(f"Ensembling {len(stem_paths)} stems for type: {stem_name}")
+                    waves = [writer.prepare_mix(sp) for sp in stem_paths]  # (2, N) float32, the reader the plugins use
+                    ens = ensembler.ensemble(waves)
+                    if custom_output_names and stem_name in custom_output_names:
+                        out_name = custom_output_names[stem_name]
+                    else:
+                        slugs = []
+                        for mf in models:
+                            name = os.path.splitext(os.path.basename(mf))[0]
+                            for prefix in _SLUG_PREFIXES:
+                                if name.startswith(prefix):
+                                    name = name[len(prefix):]
+                                    break
+                            slugs.append(name[:12])
+                        out_name = f"{base_name}_({stem_name})_custom_ensemble_{'_'.join(slugs)}"
+                    out_path = f"{out_name}.{self.output_format.lower()}"
+                    writer.audio_file_path = path
+                    writer.output_dir = self.output_dir
+                    writer.write_audio(out_path, np.ascontiguousarray(np.asarray(ens).T))
+                    output_files.append(os.path.join(self.output_dir, out_path))
+            finally:
+                self.model_filename, self.model_filenames = list(models), list(models)
+                self.model_instance = None
+                shutil.rmtree(temp_dir, ignore_errors=True)
+        return output_files
 
     def _separate_file(self, audio_file_path, custom_output_names=None):
         t0 = time.perf_counter()

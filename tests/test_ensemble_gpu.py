@@ -52,3 +52,46 @@ def test_ensembler_edges(lib_built):
     a = Ensembler(log, "avg_wave", [1.0, -1.0]).ensemble([w[0].copy(), w[2].copy()])
     b = Ensembler(log, "avg_wave", [3.0]).ensemble([w[0].copy(), w[2].copy()])
     assert np.abs(a - (w[0] + w[2]) / 2).max() <= 1e-6 and np.abs(b - a).max() <= 1e-7
+
+
+def test_separator_multi_model_ensemble_end_to_end(tmp_path):
+    """Separator.load_model([a, b]) + separate(): both models run through their plugin, stems are grouped by canonical name and reduced by the Ensembler
+    (separator.py:1242-1412).  Expected files = the same reduction applied to what the two single-model runs write."""
+    import json
+    import wave as wavmod
+
+    import mdx_oracle as O
+    from audio_separator.separator import Separator
+    from audio_separator.separator.ensembler import Ensembler
+
+    cfg = O.MDXConfig(n_fft=1536, hop_length=256, dim_f=768, dim_t=32, segment_size=32, g=8)
+    md = {"compensate": cfg.compensate, "mdx_dim_f_set": cfg.dim_f, "mdx_dim_t_set": 5, "mdx_n_fft_scale_set": cfg.n_fft, "primary_stem": "Vocals"}
+    for name, seed in (("UVR-MDX-NET-tinyA", 7), ("UVR-MDX-NET-tinyB", 8)):
+        np.savez(tmp_path / f"{name}.npz", **O.make_convtdfnet_weights(cfg, seed=seed, out_gain=0.05))
+        (tmp_path / f"{name}.json").write_text(json.dumps(md))
+    mix = O.synth_music(30000, seed=3)
+    with wavmod.open(str(tmp_path / "song.wav"), "wb") as wf:
+        wf.setnchannels(2); wf.setsampwidth(2); wf.setframerate(44100); wf.writeframes((mix.T * 32767).astype("<i2").tobytes())
+    params = {"segment_size": cfg.segment_size, "hop_length": cfg.hop_length, "overlap": cfg.overlap, "batch_size": 2}
+
+    def read(path):
+        with wavmod.open(str(path)) as wf:
+            return (np.frombuffer(wf.readframes(wf.getnframes()), dtype="<i2").astype(np.float32) / 32768.0).reshape(-1, 2).T
+
+    singles = {}
+    for name in ("UVR-MDX-NET-tinyA", "UVR-MDX-NET-tinyB"):
+        sep = Separator(model_file_dir=str(tmp_path), output_dir=str(tmp_path / name), mdx_params=params)
+        sep.load_model(f"{name}.npz")
+        singles[name] = {f.split("_(")[1].split(")")[0]: read(tmp_path / name / f) for f in sep.separate(str(tmp_path / "song.wav"))}
+    for algo, weights in (("avg_wave", [2.0, 1.0]), ("max_fft", None)):
+        out_dir = tmp_path / f"ens_{algo}"
+        sep = Separator(model_file_dir=str(tmp_path), output_dir=str(out_dir), mdx_params=params, ensemble_algorithm=algo, ensemble_weights=weights)
+        sep.load_model(["UVR-MDX-NET-tinyA.npz", "UVR-MDX-NET-tinyB.npz"])
+        files = sep.separate(str(tmp_path / "song.wav"))
+        assert sorted(os.path.basename(f) for f in files) == ["song_(Instrumental)_custom_ensemble_tinyA_tinyB.wav", "song_(Vocals)_custom_ensemble_tinyA_tinyB.wav"]
+        for f in files:
+            stem = os.path.basename(f).split("_(")[1].split(")")[0]
+            want = Ensembler(None, algo, weights).ensemble([singles["UVR-MDX-NET-tinyA"][stem], singles["UVR-MDX-NET-tinyB"][stem]])
+            want_pcm = O.to_pcm16(np.ascontiguousarray(np.asarray(want).T), 0.9, 0.0).astype(np.int32)
+            got_pcm = (read(f).T.reshape(-1) * 32768.0).astype(np.int32)
+            assert got_pcm.shape == want_pcm.shape and np.abs(got_pcm - want_pcm).max() <= 1
