@@ -55,6 +55,7 @@ __device__ __forceinline__ float2 block_sum2(float a, float b, float* red) {
 struct GnGeom {
   int C, Fr, channel_last;
   uint32_t L, n, chunk;
+  int groups;  // > 1: nn.GroupNorm(groups, C_total) on channel-first data: sample = b * groups + g owns C consecutive channels, affine index g * C + c
 };
 __device__ __forceinline__ int64_t gn_index(const GnGeom& g, int sample, uint32_t i) {
   if (g.channel_last || g.Fr == 1) return (int64_t)sample * g.n + i;
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
   const float mean = stat[0], rstd = stat[1];
   const uint32_t lo = blockIdx.x * g.chunk, hi = min(g.n, lo + g.chunk);
   for (uint32_t i = lo + threadIdx.x; i < hi; i += 256) {
-    const int c = g.channel_last ? (int)(i % (uint32_t)g.C) : (int)(i / g.L);
+    const int c = (g.channel_last ? (int)(i % (uint32_t)g.C) : (int)(i / g.L)) + (sample % g.groups) * g.C;
     const int64_t o = gn_index(g, sample, i);
     y[o] = f32_act((x[o] - mean) * rstd * __ldg(&gamma[c]) + __ldg(&beta[c]), act);
   }
@@ -528,7 +529,32 @@ extern "C" int b200sep_groupnorm1_f32(const float* x, const float* gamma, const 
   const int samples = B * Fr;
   const int nblk = gn_blocks_per_sample(samples, (int64_t)C * L);
   GnGeom g;
-  g.C = C; g.Fr = Fr; g.channel_last = channel_last; g.L = (uint32_t)L; g.n = (uint32_t)((int64_t)C * L);
+  g.C = C; g.Fr = Fr; g.channel_last = channel_last; g.L = (uint32_t)L; g.n = (uint32_t)((int64_t)C * L); g.groups = 1;
+  g.chunk = (uint32_t)cdiv((int64_t)g.n, nblk);
+  dim3 grid(nblk, samples);
+  gn_partial_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, g, reinterpret_cast<double2*>(work));
+  B2_LAUNCHED();
+  gn_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, y, g, reinterpret_cast<const double2*>(work), act);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
+// nn.GroupNorm(groups, C) on a contiguous channel-first (B, C, X) tensor (hdemucs.py:87-88 norm_fn with norm_groups = 4): group (b, g) is the
+// contiguous block of (C / groups) * X elements, i.e. one "sample" of the kernels above; gamma / beta are indexed by the absolute channel.
+extern "C" int64_t b200sep_groupnorm_work_floats(int B, int C, int groups, int64_t X) {
+  if (B < 1 || C < 1 || groups < 1 || X < 1 || C % groups) return 0;
+  return (int64_t)B * groups * (gn_blocks_per_sample(B * groups, (int64_t)(C / groups) * X) + 1) * 4;
+}
+
+extern "C" int b200sep_groupnorm_f32(const float* x, const float* gamma, const float* beta, float* y, int B, int C, int groups, int64_t X, int act, float* work,
+                                     void* stream) {
+  B2_CHECK_ARG(x && gamma && beta && y && work && B >= 1 && C >= 1 && groups >= 1 && X >= 1 && C % groups == 0, "groupnorm_f32: bad argument");
+  const int Cg = C / groups, samples = B * groups;
+  B2_CHECK_ARG((int64_t)Cg * X < (1ll << 31) && samples <= 65535, "groupnorm_f32: group of %lld elements / %d groups too large", (long long)Cg * X, samples);
+  B2_CHECK_ARG((reinterpret_cast<uintptr_t>(work) & 15) == 0, "groupnorm_f32: work must be 16-byte aligned");
+  const int nblk = gn_blocks_per_sample(samples, (int64_t)Cg * X);
+  GnGeom g;
+  g.C = Cg; g.Fr = 1; g.channel_last = 0; g.L = (uint32_t)X; g.n = (uint32_t)((int64_t)Cg * X); g.groups = groups;
   g.chunk = (uint32_t)cdiv((int64_t)g.n, nblk);
   dim3 grid(nblk, samples);
   gn_partial_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, g, reinterpret_cast<double2*>(work));
