@@ -368,6 +368,28 @@ int b200sep_overlap_add_starts(const float* chunks, const int64_t* starts, const
 int b200sep_lstm_bidir_f32(const float* x_proj, const float* w_hh, float* out, int T, int N, int hid, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Hybrid Demucs v3 (uvr_lib_v5/demucs/hdemucs.py, demucs.py): the operators its DConv branches add to the HTDemucs set.
+ * groupnorm_f32: nn.GroupNorm(groups, C) (hdemucs.py:87-88, norm_groups = 4) on contiguous channel-first x (B, C, X), affine, optional activation.
+ * lstm_bidir_wide_f32: the recurrence of one bidirectional nn.LSTM layer for ANY hidden size (BLSTM of DConv, demucs.py:26-30: hid = 192 / 384 in
+ *   the released models).  Same x_proj (2, T, N, 4*hid) / out (T, N, 2*hid) as lstm_bidir_f32; the recurrent matrix is passed TRANSPOSED,
+ *   w_hh_t (2, hid, 4*hid).  A thread-block cluster splits the hidden units and exchanges h_t through distributed shared memory.
+ * lstm_frames_gather_f32 / _scatter_f32: BLSTM.forward's framing (demucs.py:38-45 unfold into frames of `width` every `stride`; :52-64 the
+ *   trimmed concatenation back + the skip connection): x (B, C, T) -> frames (width, B*n_frames, C);  frames -> y (B, C, T) = skip + kept parts.
+ *   n_frames = 1, width = T is the unframed case (a pure permute).
+ * local_state_attn_f32: LocalState.forward (demucs.py:197-231, nfreqs = 0) between the 1x1 projections: query / key / content (B, C, T),
+ *   decay (B, heads*ndecay, T) = the query_decay convolution BEFORE the sigmoid -> out (B, C, T) = attention-weighted content
+ *   (decay penalty, -100 on the diagonal, softmax over the key axis).  C / heads in {1,2,3,4,6,8,12,16,24,32,48,64,96}.
+ * add_rowvec_f32: x (B, R, L) += v (R) broadcast over B and L: the frequency embedding after the first encoder (hdemucs.py:708-713), R = C * Fr. */
+int b200sep_add_rowvec_f32(float* x, const float* v, int B, int R, int64_t L, void* stream);
+int64_t b200sep_groupnorm_work_floats(int B, int C, int groups, int64_t X);
+int b200sep_groupnorm_f32(const float* x, const float* gamma, const float* beta, float* y, int B, int C, int groups, int64_t X, int act, float* work, void* stream);
+int b200sep_lstm_bidir_wide_f32(const float* x_proj, const float* w_hh_t, float* out, int T, int N, int hid, void* stream);
+int b200sep_lstm_frames_gather_f32(const float* x, float* frames, int B, int C, int T, int n_frames, int width, int stride, void* stream);
+int b200sep_lstm_frames_scatter_f32(const float* frames, const float* skip, float* y, int B, int C, int T, int n_frames, int width, int stride, void* stream);
+int b200sep_local_state_attn_f32(const float* query, const float* key, const float* content, const float* decay, float* out, int B, int C, int T, int heads,
+                                 int ndecay, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Ensembling of several models' stems (audio_separator/separator/ensembler.py:10-156, spec_utils.ensembling :583-608).
  * ensemble_f32: x (n_models, n) -> out (n); algo 0 weighted mean (weights: device float[n_models]), 1 median, 2 / 3 the value of smallest / largest
  * magnitude (first on ties): avg_wave, median_wave, min_wave, max_wave, and avg_fft / median_fft applied to spectrogram planes.

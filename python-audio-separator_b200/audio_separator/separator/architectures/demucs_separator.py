@@ -1,10 +1,10 @@
-"""B200 Demucs architecture plugin (HTDemucs v4 models and bags: htdemucs, htdemucs_ft, ...).
+"""B200 Demucs architecture plugin (HTDemucs v4 models and bags: htdemucs, htdemucs_ft, ...; Hybrid Demucs v3: hdemucs_mmi, mdx_extra, ...).
 
 Plugin contract of the reference's DemucsSeparator (audio_separator/separator/architectures/demucs_separator.py:26-195):
 ctor `(common_config, arch_config)` with arch keys segment_size / shifts / overlap / segments_enabled,
 `separate(path, custom_output_names)`, `demix_demucs(mix) -> (S, 2, N)` with sources 0 and 1 swapped.
 Every forward, the shift trick, the segment overlap-add and the bag average run on the GPU (b200.demucs.DemucsEngine).
-Demucs v1-v3 (Demucs, HDemucs) packages are not part of this path.
+Time-domain Demucs v1 / v2 packages are not part of this path.
 """
 import os
 import random
@@ -15,6 +15,7 @@ import torch
 
 from ..b200.demucs import DemucsEngine, HTDemucsNet
 from ..b200.demucs_loader import load_demucs
+from ..b200.hdemucs import HDemucsConfig, HDemucsNet
 from ..common_separator import CommonSeparator
 
 DEMUCS_2_SOURCE_MAPPER = {CommonSeparator.INST_STEM: 0, CommonSeparator.VOCAL_STEM: 1}
@@ -50,7 +51,7 @@ class DemucsSeparator(CommonSeparator):
                     cfg.segment = Fraction(int(self.segment_size))  # demucs_segments: sub.segment = int(segment)
                 except (TypeError, ValueError):
                     pass
-            nets.append(HTDemucsNet(cfg, state, device=self.torch_device))
+            nets.append((HDemucsNet if isinstance(cfg, HDemucsConfig) else HTDemucsNet)(cfg, state, device=self.torch_device))
         self.engine = DemucsEngine(nets, bag_weights=weights, overlap=self.overlap, batch_size=self.batch_size)
 
     def demix_demucs(self, mix):

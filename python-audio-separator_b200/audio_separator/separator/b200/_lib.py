@@ -65,6 +65,13 @@ _SIGS = {
     "b200sep_stft_inverse_ex": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp, vp, vp]),
     "b200sep_conv2d_f32": (i32, [vp, vp, vp, vp, vp] + [i32] * 23 + [vp, vp]),
     "b200sep_lstm_bidir_f32": (i32, [vp, vp, vp, i32, i32, i32, vp]),
+    "b200sep_add_rowvec_f32": (i32, [vp, vp, i32, i32, i64, vp]),
+    "b200sep_groupnorm_work_floats": (i64, [i32, i32, i32, i64]),
+    "b200sep_groupnorm_f32": (i32, [vp, vp, vp, vp, i32, i32, i32, i64, i32, vp, vp]),
+    "b200sep_lstm_bidir_wide_f32": (i32, [vp, vp, vp, i32, i32, i32, vp]),
+    "b200sep_lstm_frames_gather_f32": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "b200sep_lstm_frames_scatter_f32": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "b200sep_local_state_attn_f32": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "b200sep_tc_packed_floats": (i64, [i32, i32]),
     "b200sep_tc_pack_linear_weights": (i32, [vp, i32, i32, i32, vp, vp]),
     "b200sep_tc_pack_conv_weights": (i32, [vp, i32, i32, i32, vp, vp]),

@@ -563,19 +563,25 @@ class DemucsEngine:
             ext[:, a - lo : b - lo].copy_(tensor[:, a:b])
         local = torch.empty((sh.halo + sh.n_own, S * 2, seg), dtype=torch.float32, device=tensor.device)
 
+        pads = getattr(cfg, "pads_to_segment", True)  # HTDemucs: chunk.padded(valid_length = training segment); HDemucs: every chunk at its own length (apply.py:252-257)
+
         def compute(buf, slot0, unit0, n):
-            batch = _new((n, 2, seg), tensor)
-            clens = []
-            for j in range(n):
-                off = offs[unit0 + j]
-                clen = min(length - off, seg)
-                start = offset + off - (seg - clen) // 2
-                batch[j].copy_(ext[:, start - lo : start - lo + seg])
-                clens.append(clen)
-            y = net.graphed(batch)  # (n, S, 2, seg): the launch list of the forward, replayed as one CUDA graph per batch size
-            for j, clen in enumerate(clens):  # center_trim to the chunk's valid length (apply.py:258), stored from sample 0
-                d = (seg - clen) // 2
-                buf[slot0 + j, :, :clen].copy_(y[j].reshape(S * 2, seg)[:, d : d + clen])
+            clens = [min(length - offs[unit0 + j], seg) for j in range(n)]
+            j0 = 0
+            while j0 < n:  # units of one input length form one forward (only the last segment of a pass is shorter)
+                j1 = j0 + 1
+                while pads and j1 < n or (not pads and j1 < n and clens[j1] == clens[j0]):
+                    j1 += 1
+                width = seg if pads else clens[j0]
+                batch = _new((j1 - j0, 2, width), tensor)
+                for j in range(j0, j1):
+                    start = offset + offs[unit0 + j] - ((seg - clens[j]) // 2 if pads else 0)
+                    batch[j - j0].copy_(ext[:, start - lo : start - lo + width])
+                y = net.graphed(batch)  # (n, S, 2, width): the launch list of the forward (HTDemucs: replayed as one CUDA graph per batch size)
+                for j in range(j0, j1):  # center_trim to the chunk's valid length (apply.py:258), stored from sample 0
+                    d = (seg - clens[j]) // 2 if pads else 0
+                    buf[slot0 + j, :, : clens[j]].copy_(y[j - j0].reshape(S * 2, width)[:, d : d + clens[j]])
+                j0 = j1
 
         self.runner.wait_all(self.runner.run_units(sh, local, compute, self.batch_size))
         if sh.q1 > sh.q0:

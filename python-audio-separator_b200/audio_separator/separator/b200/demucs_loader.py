@@ -16,6 +16,7 @@ import torch
 import yaml
 
 from .demucs import HTDemucsConfig
+from .hdemucs import HDemucsConfig
 
 # constructor arguments that must keep the value the B200 graph was built for (htdemucs.py:36-98)
 _REQUIRED = dict(cac=True, wiener_iters=0, end_iters=0, wiener_residual=False, rewrite=True, multi_freqs=None, context_enc=0, t_emb="sin", t_norm_in=True,
@@ -23,6 +24,12 @@ _REQUIRED = dict(cac=True, wiener_iters=0, end_iters=0, wiener_residual=False, r
                  t_sparse_self_attn=False, t_sparse_cross_attn=False, t_cross_first=False, channels_time=None, use_train_segment=True)
 _MAPPED = ("sources", "audio_channels", "channels", "growth", "nfft", "depth", "kernel_size", "stride", "context", "dconv_depth", "dconv_comp", "bottom_channels",
            "t_layers", "t_heads", "t_hidden_scale", "freq_emb", "emb_scale", "samplerate", "segment")
+
+
+# HDemucs (v3) constructor arguments (hdemucs.py:360-400): values the B200 graph is built for, and the ones that map onto HDemucsConfig
+_HD_REQUIRED = dict(cac=True, wiener_iters=0, end_iters=0, wiener_residual=False, rewrite=True, hybrid=True, channels_time=None)
+_HD_MAPPED = ("sources", "audio_channels", "channels", "growth", "nfft", "depth", "hybrid_old", "freq_emb", "emb_scale", "kernel_size", "time_stride", "stride", "context",
+              "context_enc", "norm_starts", "norm_groups", "dconv_mode", "dconv_depth", "dconv_comp", "dconv_attn", "dconv_lstm", "samplerate", "segment")
 
 
 class _Placeholder:
@@ -60,14 +67,28 @@ def load_package(path: str) -> dict:
     return torch.load(path, map_location="cpu", pickle_module=_pickle_shim, weights_only=False)
 
 
-def config_from_package(package: dict) -> HTDemucsConfig:
+def _hdemucs_config(kwargs: dict) -> HDemucsConfig:
+    for k, v in _HD_REQUIRED.items():
+        if k in kwargs and kwargs[k] != v:
+            raise NotImplementedError(f"HDemucs option {k}={kwargs[k]!r} is outside the supported structure (needs {v!r})")
+    if kwargs.get("multi_freqs"):
+        raise NotImplementedError("HDemucs multi_freqs (MultiWrap band splitting) is not supported")
+    fields = {k: kwargs[k] for k in _HD_MAPPED if k in kwargs}
+    if "sources" in fields:
+        fields["sources"] = tuple(fields["sources"])
+    return HDemucsConfig(**fields)
+
+
+def config_from_package(package: dict):
     klass = package["klass"]
     name = getattr(klass, "__name__", str(klass))
-    if name != "HTDemucs":
-        raise NotImplementedError(f"model class {name}: the B200 Demucs path covers HTDemucs (v4) packages only")
+    if name not in ("HTDemucs", "HDemucs"):
+        raise NotImplementedError(f"model class {name}: the B200 Demucs path covers HTDemucs (v4) and HDemucs (v3 hybrid) packages; Demucs v1 / v2 time-domain models are not built")
     kwargs = dict(package.get("kwargs", {}))
     if package.get("args"):
         raise ValueError("positional constructor arguments in a Demucs package are not supported")
+    if name == "HDemucs":
+        return _hdemucs_config(kwargs)
     for k, v in _REQUIRED.items():
         if k in kwargs and kwargs[k] != v:
             raise NotImplementedError(f"HTDemucs option {k}={kwargs[k]!r} is outside the supported structure (needs {v!r})")

@@ -207,6 +207,11 @@ __global__ void __launch_bounds__(256) local_state_attn_kernel(const float* __re
   }
 }
 
+// x[b][r][l] += v[r]: the frequency embedding added after the first encoder (hdemucs.py:708-713), r = channel * Fr + fr
+__global__ void add_rowvec_kernel(float* __restrict__ x, const float* __restrict__ v, int R, int L, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) x[i] += __ldg(&v[(i / L) % R]);
+}
+
 template <int CH>
 int launch_local_state(const float* q, const float* k, const float* content, const float* decay, float* out, int B, int C, int T, int heads, int nd, cudaStream_t st) {
   dim3 grid(cdiv(T, 8), heads, B);
@@ -221,6 +226,14 @@ static inline int ew_grid(int64_t n) { return (int)std::min<int64_t>(cdiv(n, 256
 }  // namespace b200sep
 
 using namespace b200sep;
+
+extern "C" int b200sep_add_rowvec_f32(float* x, const float* v, int B, int R, int64_t L, void* stream) {
+  B2_CHECK_ARG(x && v && B >= 1 && R >= 1 && L >= 1 && L <= 0x7fffffff, "add_rowvec_f32: bad argument");
+  const int64_t total = (int64_t)B * R * L;
+  add_rowvec_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(x, v, R, (int)L, total);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
 
 extern "C" int b200sep_lstm_frames_gather_f32(const float* x, float* frames, int B, int C, int T, int n_frames, int width, int stride, void* stream) {
   B2_CHECK_ARG(x && frames && B >= 1 && C >= 1 && T >= 1 && n_frames >= 1 && width >= 1 && stride >= 1, "lstm_frames_gather_f32: bad argument");

@@ -71,9 +71,9 @@ def test_package_and_bag_loader(lib_built, tmp_path):
     c2 = L.config_from_package(L.load_package(str(tmp_path / "defaults.th")))
     assert (c2.bottom_channels, c2.segment, c2.channels, c2.sources) == (0, Fraction(10), 48, ("a", "b"))
     # anything outside the supported structure fails loudly instead of producing different audio
-    _fake_package(str(tmp_path / "v3.th"), {}, state, klass_name="HDemucs")
+    _fake_package(str(tmp_path / "v2.th"), {}, state, klass_name="Demucs")
     with pytest.raises(NotImplementedError):
-        L.config_from_package(L.load_package(str(tmp_path / "v3.th")))
+        L.config_from_package(L.load_package(str(tmp_path / "v2.th")))
     _fake_package(str(tmp_path / "sparse.th"), dict(cfg.kwargs(), t_sparse_self_attn=True), state)
     with pytest.raises(NotImplementedError):
         L.config_from_package(L.load_package(str(tmp_path / "sparse.th")))
@@ -98,3 +98,57 @@ def test_host_side_weight_blocking_and_embeddings(lib_built):
     assert np.abs(D.sin_embedding_1d(87, 32) - dm.sin_embedding_1d(87, 32, 10000.0)).max() <= 1e-6
     with pytest.raises(ValueError):
         dm.HTDemucsConfig(kernel_size=4).validate()
+
+
+# ----------------------------------------------------------------------------------------------------------------- Hybrid Demucs v3
+HD_SMALL = dict(channels=8, nfft=256, depth=4, norm_starts=2, dconv_lstm=2, dconv_attn=2, segment=0.5)
+
+
+def test_hdemucs_oracle_matches_reference_golden(golden_dir):
+    import hdemucs_oracle as H
+
+    z = np.load(os.path.join(golden_dir, "hdemucs_small.npz"))
+    cfg = H.HDConfig(**HD_SMALL)
+    w = H.make_weights(cfg, seed=int(z["weights_seed"]))
+    mix = M.synth_music(3 * cfg.seg_len, seed=int(z["mix_seed"]))
+    L = int(z["seg_len"])
+    assert np.abs(H.forward(w, cfg, mix[None, :, :L]) - z["forward_ref"]).max() <= 5e-5
+    yl = H.forward(w, cfg, mix[None, :, : int(z["long_len"])])  # ragged length, BLSTM input framed into overlapping 200-step windows
+    assert yl.shape == z["forward_long_ref"].shape and np.abs(yl - z["forward_long_ref"]).max() <= 5e-5
+    yo = H.forward(w, H.HDConfig(**dict(HD_SMALL, hybrid_old=True)), mix[None, :, :L])
+    assert np.abs(yo - z["forward_old_ref"]).max() <= 5e-5
+    N = int(z["n_apply"])
+    m2 = torch.from_numpy(mix[:, :N])
+    mn = ((m2 - m2.mean(0).mean()) / m2.mean(0).std()).numpy()
+    a = H.apply_model(lambda c: H.forward(w, cfg, c), cfg, mn[None], [int(v) for v in z["shift_offsets"]], 0.25)
+    assert np.abs(a - z["apply_ref"]).max() <= 1e-4 * np.abs(z["apply_ref"]).max()
+
+
+def test_hdemucs_layer_plan_and_package_loader(lib_built, tmp_path):
+    """The layer geometry of the released hybrid models (depth 6, nfft 4096) and HDemucs packages through the loader."""
+    import hdemucs_oracle as H
+    from audio_separator.separator.b200 import demucs_loader as L
+    from audio_separator.separator.b200 import hdemucs as hd
+
+    plan = hd.layer_plan(hd.HDemucsConfig())
+    assert plan == H.layer_plan(H.HDConfig())  # the product's restatement of the constructor agrees with the oracle's (pinned: its state_dict layout loads into the reference)
+    e = [p["enc"] for p in plan]
+    assert [(l["chin"], l["chout"], l["k"], l["s"], l["freq"], l["pad"], l["norm"], l["lstm"]) for l in e] == [
+        (4, 48, 8, 4, True, 2, False, False), (48, 96, 8, 4, True, 2, False, False), (96, 192, 8, 4, True, 2, False, False), (192, 384, 8, 4, True, 2, False, False),
+        (384, 768, 8, 4, True, 0, True, True), (768, 1536, 4, 2, False, 1, True, True)]
+    assert [p["tenc"]["empty"] for p in plan[:5]] == [False, False, False, False, True] and plan[5]["tenc"] is None
+    assert plan[0]["dec"]["chout"] == 16 and plan[0]["tdec"]["chout"] == 8 and plan[0]["dec"]["last"]
+    cfg = H.HDConfig(**HD_SMALL)
+    w = H.make_weights(cfg, seed=2)
+    state = {k: torch.from_numpy(v) for k, v in w.items()}
+    _fake_package(str(tmp_path / "hd.th"), dict(cfg.kwargs(), cac=True, hybrid=True, wiener_iters=0, multi_freqs=[], rescale=0.1, dconv_init=1e-3), state, klass_name="HDemucs")
+    models, wts, seg = L.load_demucs(str(tmp_path / "hd.th"))
+    c, st = models[0]
+    assert isinstance(c, hd.HDemucsConfig) and (c.channels, c.nfft, c.depth, c.norm_starts, c.dconv_lstm, c.segment, c.pads_to_segment) == (8, 256, 4, 2, 2, 0.5, False)
+    assert c.seg_len == 22050 and set(st) == set(w)
+    for bad in (dict(multi_freqs=[0.5]), dict(cac=False), dict(hybrid=False), dict(wiener_iters=2)):
+        _fake_package(str(tmp_path / "bad.th"), dict(cfg.kwargs(), **bad), state, klass_name="HDemucs")
+        with pytest.raises(NotImplementedError):
+            L.config_from_package(L.load_package(str(tmp_path / "bad.th")))
+    with pytest.raises(ValueError):
+        hd.HDemucsConfig(kernel_size=6).validate()

@@ -1,0 +1,218 @@
+"""GPU parity of the Hybrid Demucs v3 path: the new operators (grouped GroupNorm, cluster LSTM recurrence, BLSTM framing, LocalState attention)
+against torch-CPU definitions / the oracle's restatements, HDemucsNet.forward and apply_model (through DemucsEngine) against golden vectors
+produced by the UNMODIFIED reference (oracle/make_golden_hdemucs.py), and a full-size (48 channels, depth 6, nfft 4096) forward against the
+oracle.  Audio tolerance: 1e-4 max-abs relative to the signal peak (BASELINE gate)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import hdemucs_oracle as H
+import mdx_oracle as M
+
+pytestmark = pytest.mark.gpu
+
+SMALL = dict(channels=8, nfft=256, depth=4, norm_starts=2, dconv_lstm=2, dconv_attn=2, segment=0.5)
+
+
+def dev(x):
+    return torch.as_tensor(np.ascontiguousarray(x)).cuda()
+
+
+@pytest.fixture(scope="module")
+def hd(lib_built):
+    assert torch.cuda.is_available()
+    from audio_separator.separator.b200 import hdemucs
+
+    return hdemucs
+
+
+@pytest.fixture(scope="module")
+def small(hd, golden_dir):
+    z = np.load(os.path.join(golden_dir, "hdemucs_small.npz"))
+    ocfg = H.HDConfig(**SMALL)
+    w = H.make_weights(ocfg, seed=int(z["weights_seed"]))
+    net = hd.HDemucsNet(hd.HDemucsConfig(**SMALL), w)
+    mix = M.synth_music(3 * ocfg.seg_len, seed=int(z["mix_seed"]))
+    return z, ocfg, w, net, mix
+
+
+# ------------------------------------------------------------------------------------------------ operators
+@pytest.mark.parametrize("shape,groups", [((2, 32, 1, 87), 4), ((3, 24, 8, 50), 4), ((1, 64, 1, 3000), 1), ((2, 12, 5, 7), 3)])
+def test_groupnorm_groups(hd, shape, groups):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(shape, generator=g) * 2 + 0.7
+    gamma, beta = torch.rand(shape[1], generator=g) + 0.5, torch.randn(shape[1], generator=g)
+    ref = F.gelu(F.group_norm(x.double(), groups, gamma.double(), beta.double(), 1e-5))
+    got = hd.groupnorm(x.cuda(), groups, gamma.cuda(), beta.cuda(), hd.ACT_GELU).cpu()
+    assert (got.double() - ref).abs().max() <= 2e-5
+
+
+@pytest.mark.parametrize("hid,T,N", [(192, 40, 11), (384, 17, 9), (64, 23, 3), (104, 9, 20)])
+def test_lstm_bidir_wide_vs_torch(hd, hid, T, N):
+    from audio_separator.separator.b200._lib import check, lib
+    from audio_separator.separator.b200.engine import _ptr, _stream
+
+    torch.manual_seed(hid)
+    lstm = torch.nn.LSTM(input_size=hid, hidden_size=hid, bidirectional=True)
+    x = torch.randn(T, N, hid)
+    with torch.no_grad():
+        ref = lstm(x)[0]
+        xp = torch.stack([x @ lstm.weight_ih_l0.t() + lstm.bias_ih_l0 + lstm.bias_hh_l0, x @ lstm.weight_ih_l0_reverse.t() + lstm.bias_ih_l0_reverse + lstm.bias_hh_l0_reverse])
+        whh_t = torch.stack([lstm.weight_hh_l0.t().contiguous(), lstm.weight_hh_l0_reverse.t().contiguous()])
+    xp_d, w_d = xp.contiguous().cuda(), whh_t.contiguous().cuda()
+    out = torch.empty((T, N, 2 * hid), device="cuda")
+    check(lib.b200sep_lstm_bidir_wide_f32(_ptr(xp_d), _ptr(w_d), _ptr(out), T, N, hid, _stream()), "lstm_bidir_wide_f32")
+    torch.cuda.synchronize()
+    assert (out.cpu() - ref).abs().max() <= 2e-5
+
+
+@pytest.mark.parametrize("T", [87, 200, 201, 555])
+def test_blstm_block_vs_oracle(hd, small, T):
+    """BLSTM.forward (framing at T > 200, two layers, linear, skip) of one DConv branch of the small model against the oracle's restatement."""
+    _, ocfg, w, net, _ = small
+    p = "encoder.2.dconv.layers.0.3"
+    hid = w[f"{p}.linear.bias"].shape[0]
+    g = torch.Generator().manual_seed(T)
+    x = torch.randn((2, hid, T), generator=g)
+    Wt = {k: torch.from_numpy(v) for k, v in w.items()}
+    with torch.no_grad():
+        ref = H.blstm(x, Wt, p, ocfg)
+    got = net._blstm(x.cuda().view(2, hid, 1, T).contiguous(), p).cpu().view(2, hid, T)
+    assert (got - ref).abs().max() <= 3e-5 * max(1.0, ref.abs().max())
+
+
+@pytest.mark.parametrize("C,T,B", [(192, 300, 2), (384, 131, 1), (8, 87, 2), (64, 65, 1)])
+def test_local_state_attention_vs_oracle(hd, C, T, B):
+    from audio_separator.separator.b200._lib import check, lib
+    from audio_separator.separator.b200.engine import _ptr, _stream
+
+    g = torch.Generator().manual_seed(C + T)
+    heads, nd = 4, 4
+    q, k, ct = (torch.randn((B, C, T), generator=g) for _ in range(3))
+    dq = torch.randn((B, heads * nd, T), generator=g) - 2.0
+    # the oracle's local_state with identity projections: weights that make query / key / content / decay the given tensors is not possible for all four at
+    # once, so restate the attention core directly (demucs.py:206-229) in float64
+    idx = torch.arange(T, dtype=torch.float64)
+    delta = idx[:, None] - idx[None, :]
+    qq, kk, cc = (t.double().view(B, heads, -1, T) for t in (q, k, ct))
+    dots = torch.einsum("bhct,bhcs->bhts", kk, qq) / kk.shape[2] ** 0.5
+    decays = torch.arange(1, nd + 1, dtype=torch.float64)
+    dqq = torch.sigmoid(dq.double().view(B, heads, -1, T)) / 2
+    dots = dots + torch.einsum("fts,bhfs->bhts", -decays.view(-1, 1, 1) * delta.abs() / nd**0.5, dqq)
+    dots.masked_fill_(torch.eye(T, dtype=torch.bool), -100)
+    ref = torch.einsum("bhts,bhct->bhcs", torch.softmax(dots, dim=2), cc).reshape(B, C, T)
+    out = torch.empty((B, C, T), device="cuda")
+    check(lib.b200sep_local_state_attn_f32(_ptr(q.cuda()), _ptr(k.cuda()), _ptr(ct.cuda()), _ptr(dq.cuda()), _ptr(out), B, C, T, heads, nd, _stream()), "local_state_attn_f32")
+    torch.cuda.synchronize()
+    assert (out.cpu().double() - ref).abs().max() <= 2e-5 * max(1.0, ref.abs().max())
+
+
+def test_local_state_block_vs_oracle(hd, small):
+    _, ocfg, w, net, _ = small
+    p = "encoder.3.dconv.layers.1.4"
+    hid = w[f"{p}.proj.bias"].shape[0]
+    x = torch.randn((2, hid, 130), generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        ref = H.local_state(x, {k: torch.from_numpy(v) for k, v in w.items()}, p, ocfg)
+    got = net._local_state(x.cuda().view(2, hid, 1, 130).contiguous(), p).cpu().view(2, hid, 130)
+    assert (got - ref).abs().max() <= 3e-5 * max(1.0, ref.abs().max())
+
+
+# ------------------------------------------------------------------------------------------------ the network
+def _check_forward(net, ocfg, w, seg, ref, tol=1e-4):
+    got = net.forward(dev(seg)).cpu().numpy()
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    err = float(np.abs(got - ref).max())
+    assert err <= tol * max(1.0, float(np.abs(ref).max())), (err, float(np.abs(ref).max()))
+
+
+def test_forward_vs_reference_golden(small):
+    z, ocfg, w, net, mix = small
+    L = int(z["seg_len"])
+    _check_forward(net, ocfg, w, mix[None, :, :L], z["forward_ref"])
+
+
+def test_forward_ragged_length_framed_blstm_vs_reference_golden(small):
+    z, ocfg, w, net, mix = small
+    _check_forward(net, ocfg, w, mix[None, :, : int(z["long_len"])], z["forward_long_ref"])
+
+
+def test_forward_batch2_vs_reference_golden(small):
+    z, ocfg, w, net, mix = small
+    L = int(z["seg_len"])
+    _check_forward(net, ocfg, w, np.stack([mix[:, :L], mix[:, L : 2 * L]]), z["forward_b2_ref"])
+
+
+def test_forward_hybrid_old_vs_reference_golden(hd, small):
+    z, ocfg, w, _, mix = small
+    net = hd.HDemucsNet(hd.HDemucsConfig(**dict(SMALL, hybrid_old=True)), w)
+    _check_forward(net, ocfg, w, mix[None, :, : int(z["seg_len"])], z["forward_old_ref"])
+
+
+def test_encoder_layers_vs_oracle_taps(small):
+    """Every encoder / decoder output of the small model against the oracle's intermediate tensors (localises a failure of the forward tests)."""
+    z, ocfg, w, net, mix = small
+    seg = mix[None, :, : int(z["long_len"])]
+    taps = {}
+    H.forward(w, ocfg, seg, taps=taps)
+    got = {}
+    orig_enc, orig_dec = net._enc_layer, net._dec_layer
+
+    def enc(x, prefix, L, inject=None):
+        y = orig_enc(x, prefix, L, inject)
+        got[prefix] = y
+        return y
+
+    def dec(x, skip, length, prefix, L):
+        zz, y = orig_dec(x, skip, length, prefix, L)
+        got[prefix] = zz
+        return zz, y
+
+    net._enc_layer, net._dec_layer = enc, dec
+    try:
+        net.forward(dev(seg))
+    finally:
+        net._enc_layer, net._dec_layer = orig_enc, orig_dec
+    torch.cuda.synchronize()
+    names = {"encoder": "enc", "tencoder": "tenc", "decoder": "dec", "tdecoder": "tdec"}
+    report = []
+    for prefix, t in got.items():
+        kind, idx = prefix.split(".")
+        ref = taps[f"{names[kind]}{idx}"]
+        a = t.cpu().numpy().reshape(ref.shape) if t.numel() == ref.size else None
+        assert a is not None, (prefix, tuple(t.shape), ref.shape)
+        report.append((prefix, float(np.abs(a - ref).max()), float(np.abs(ref).max())))
+    bad = [r for r in report if r[1] > 1e-4 * max(1.0, r[2])]
+    assert not bad, report
+
+
+def test_apply_model_vs_reference_golden(hd, small):
+    """apply_model(split=True) for a model without valid_length: full segments batched, the last one at its own length (apply.py:215-260)."""
+    from audio_separator.separator.b200.demucs import DemucsEngine
+
+    z, ocfg, w, net, mix = small
+    N = int(z["n_apply"])
+    m2 = mix[:, :N]
+    ref_ = torch.from_numpy(m2).mean(0)
+    mn = ((torch.from_numpy(m2) - ref_.mean()) / ref_.std()).numpy()
+    eng = DemucsEngine([net], overlap=0.25, batch_size=2)
+    got0 = eng.apply_model(dev(mn), []).cpu().numpy().reshape(1, 4, 2, N)
+    assert np.abs(got0 - z["apply0_ref"]).max() <= 1e-4 * max(1.0, np.abs(z["apply0_ref"]).max())
+    got1 = eng.apply_model(dev(mn), [int(v) for v in z["shift_offsets"]]).cpu().numpy().reshape(1, 4, 2, N)
+    assert np.abs(got1 - z["apply_ref"]).max() <= 1e-4 * max(1.0, np.abs(z["apply_ref"]).max())
+
+
+def test_full_size_forward_vs_oracle(hd):
+    """The released geometry (48 channels, depth 6, nfft 4096: BLSTM hidden 192 / 384 on the cluster kernel, LocalState with 48 / 96 channels per head) on
+    a 5-second input (216 frames: the BLSTMs frame their input) against the oracle."""
+    ocfg = H.HDConfig()
+    w = H.make_weights(ocfg, seed=21)
+    mix = M.synth_music(220500, seed=77)[None]
+    ref = H.forward(w, ocfg, mix)
+    net = hd.HDemucsNet(hd.HDemucsConfig(), w)
+    got = net.forward(dev(mix)).cpu().numpy()
+    err = float(np.abs(got - ref).max())
+    assert err <= 1e-4 * max(1.0, float(np.abs(ref).max())), (err, float(np.abs(ref).max()))
