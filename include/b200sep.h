@@ -264,6 +264,14 @@ int b200sep_gemm_f32(const float* A, const float* Bw, float* C, int M, int N, in
 int64_t b200sep_tc_packed_floats(int N, int K);
 int b200sep_tc_pack_linear_weights(const float* W, int N, int K, int ldw, float* packed, void* stream);
 int b200sep_tc_pack_conv_weights(const float* w_blocked, int Cin, int taps, int Cout, float* packed, void* stream);
+/* Fused attention, head dimension 64: out[b, m, h*64 + d] = sum_n softmax_n(alpha <q[b, m, h], k[b, n, h]>) v[b, n, h*64 + d] with the scores kept on chip
+ * (one tcgen05 kernel: Q K^T into TMEM, running softmax in registers, P V from shared memory).  q (B, Lq, .) / k (B, Lk, .) / out (B, Lq, .): batch and row
+ * strides in floats, head h at columns [h*64, h*64 + 64);  v_is_kn = 0: vt = V TRANSPOSED, vt[b * vt_batch_stride + (h*64 + d) * vt_row_stride + n] (keys
+ * contiguous);  v_is_kn = 1: plain V, vt[b * vt_batch_stride + n * vt_row_stride + h*64 + d].
+ * Replaces gemm_f32 (scores) + softmax_rows_f32 + gemm_f32 (P V) of nn.MultiheadAttention (transformer.py:196-409). */
+int b200sep_attention_f32(const float* q, const float* k, const float* vt, float* out, int B, int H, int Lq, int Lk, int head_dim, int64_t q_batch_stride,
+                          int64_t q_row_stride, int64_t k_batch_stride, int64_t k_row_stride, int64_t vt_batch_stride, int64_t vt_row_stride,
+                          int64_t out_batch_stride, int64_t out_row_stride, float alpha, int v_is_kn, void* stream);
 /* in-place softmax over the first n columns of each row (row stride ld >= n; padding columns are left untouched) */
 int b200sep_softmax_rows_f32(float* x, int64_t rows, int n, int64_t ld, void* stream);
 /* batched C[z] = alpha * A[z] (M,K; lda) @ B[z] (K,N; ldb): the P @ V product of attention without a transposed copy of V */

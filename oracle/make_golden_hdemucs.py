@@ -78,8 +78,56 @@ def main():
     offs = [random.randint(0, int(0.5 * cfg.samplerate))]
     print("  shift offsets:", offs)
     check("apply_model shifts=1 split", a_ref, H.apply_model(fn, cfg, mn.numpy()[None], offs, 0.25), 5e-5 * max(1.0, np.abs(a_ref).max()))
+    # segments_enabled=False: apply_model(split=False) -- one forward over the whole (shifted) track (apply.py:251-260)
+    random.seed(4)
+    state = random.getstate()
+    with torch.no_grad():
+        ns_ref = apply.apply_model(model, mn[None], shifts=1, split=False, device="cpu").numpy()
+    random.setstate(state)
+    ns_offs = [random.randint(0, int(0.5 * cfg.samplerate))]
+
+    def whole(fn_, c_, mixn, offs_, valid_of):  # restated: pad by max_shift, TensorChunk(offset, length + max_shift - offset), centred zero-padding to valid_length, center_trim
+        import demucs_oracle as D
+
+        ms = int(0.5 * c_.samplerate)
+        Nn = mixn.shape[-1]
+        pm = D.padded(mixn, 0, Nn, Nn + 2 * ms)
+        out = 0
+        for o in offs_:
+            ln = Nn + ms - o
+            y = D.center_trim(fn_(D.padded(pm, o, ln, valid_of(ln))), ln)
+            out = out + y[..., ms - o :]
+        return out / len(offs_)
+
+    check("apply_model shifts=1 split=False (HDemucs: no valid_length)", ns_ref, whole(fn, cfg, mn.numpy()[None], ns_offs, lambda ln: ln), 5e-5 * max(1.0, np.abs(ns_ref).max()))
+    # the same for HTDemucs on a clip shorter than its training segment (valid_length = the training segment; longer inputs raise, htdemucs.py:469-481)
+    import demucs_oracle as D
+    from make_golden_demucs import SMALL as HT_SMALL, ref_model as ht_ref_model
+
+    hcfg = D.HTConfig(**HT_SMALL)
+    hw = D.make_weights(hcfg, seed=5)
+    hmodel = ht_ref_model(hcfg, hw)
+    hN = hcfg.seg_len - 1000  # shifts = 0: the small model's training segment (0.5 s) is no longer than max_shift, so a shifted chunk never fits
+    hm = torch.from_numpy(mix[:, :hN])
+    hmn = (hm - hm.mean(0).mean()) / hm.mean(0).std()
+    hoffs = []
+    with torch.no_grad():
+        hns_ref = apply.apply_model(hmodel, hmn[None], shifts=0, split=False, device="cpu").numpy()
+
+    def whole0(fn_, mixn, valid):
+        return D.center_trim(fn_(D.padded(mixn, 0, mixn.shape[-1], valid)), mixn.shape[-1])
+
+    check("apply_model shifts=0 split=False (HTDemucs, padded to the training segment)", hns_ref,
+          whole0(lambda c: D.forward(hw, hcfg, c), hmn.numpy()[None], hcfg.seg_len), 5e-5 * max(1.0, np.abs(hns_ref).max()))
+    try:
+        with torch.no_grad():
+            apply.apply_model(hmodel, torch.zeros(1, 2, hcfg.seg_len + 10), shifts=0, split=False, device="cpu")
+        raise AssertionError("the reference accepted an input longer than the training segment")
+    except ValueError as e:
+        print("  reference refuses long inputs without segments:", e)
     np.savez_compressed(
-        os.path.join(GOLD, "hdemucs_small.npz"), weights_seed=9, mix_seed=41, seg_len=L, n_apply=N, shift_offsets=np.array(offs), long_len=long.shape[-1],
+        os.path.join(GOLD, "hdemucs_small.npz"), nosplit_ref=ns_ref.astype(np.float32), nosplit_offsets=np.array(ns_offs), ht_nosplit_ref=hns_ref.astype(np.float32),
+        ht_nosplit_offsets=np.array(hoffs), ht_nosplit_n=hN, weights_seed=9, mix_seed=41, seg_len=L, n_apply=N, shift_offsets=np.array(offs), long_len=long.shape[-1],
         forward_ref=y_ref.astype(np.float32), forward_long_ref=yl_ref.astype(np.float32), forward_old_ref=yo_ref.astype(np.float32), forward_b2_ref=y2_ref.astype(np.float32),
         apply_ref=a_ref.astype(np.float32), apply0_ref=b_ref.astype(np.float32),
     )

@@ -31,8 +31,6 @@ class DemucsSeparator(CommonSeparator):
         self.overlap = arch_config.get("overlap", 0.25)
         self.segments_enabled = arch_config.get("segments_enabled", True)
         self.batch_size = int(arch_config.get("batch_size", 4))  # segments per forward (B200 addition; results do not depend on it)
-        if not self.segments_enabled:
-            raise NotImplementedError("segments_enabled=False (one forward over the whole track) is outside the accelerated path")
         if not torch.cuda.is_available():
             raise RuntimeError("DemucsSeparator (B200 build) needs a CUDA device: there is no CPU path in this package")
         self.torch_device = torch.device("cuda", torch.cuda.current_device())
@@ -52,7 +50,8 @@ class DemucsSeparator(CommonSeparator):
                 except (TypeError, ValueError):
                     pass
             nets.append((HDemucsNet if isinstance(cfg, HDemucsConfig) else HTDemucsNet)(cfg, state, device=self.torch_device))
-        self.engine = DemucsEngine(nets, bag_weights=weights, overlap=self.overlap, batch_size=self.batch_size)
+        # segments_enabled=False: apply_model(split=False), one forward over the whole track (HTDemucs raises beyond its training segment, like the reference)
+        self.engine = DemucsEngine(nets, bag_weights=weights, overlap=self.overlap, batch_size=self.batch_size, split=bool(self.segments_enabled))
 
     def demix_demucs(self, mix):
         """(2, N) -> (S, 2, N) (demucs_separator.py:162-195).  The shift offsets are drawn exactly where apply_model draws them

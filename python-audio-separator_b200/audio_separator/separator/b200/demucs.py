@@ -11,6 +11,7 @@ operator launches; every arithmetic step is a kernel behind the C ABI (include/b
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from fractions import Fraction
 
@@ -21,6 +22,7 @@ from ._lib import LAYOUT_CFT, check, lib
 from .engine import StftPlan, _ptr, _require_cuda, _stream
 
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+_FUSED_ATTENTION = os.environ.get("B200SEP_FUSED_ATTN", "1") != "0"  # 0: the unfused scores / softmax / P V launches (A/B measurements)
 _DCONV_FUSED_HID = (4, 6, 8, 12, 16, 24, 32, 48)  # hidden widths b200sep_dconv_f32 is instantiated for
 
 
@@ -361,6 +363,11 @@ class HTDemucsNet:
         wv, bv = W[f"{p}.v_weight"], W[f"{p}.v_bias"]
         _gemm_raw(_ptr(wv), _ptr(kv_in), _ptr(vt), D, Lk, D, D, D, Lk, B, 0, Lk * D, D * Lk, bias_m=_ptr(bv))
         o = _new((B, Lq, D), q_in)
+        if hd == 64 and _FUSED_ATTENTION:  # one kernel, the (H, Lq, Lk) scores stay on chip
+            check(lib.b200sep_attention_f32(_ptr(q), _ptr(k), _ptr(vt), _ptr(o), B, H, Lq, Lk, hd, Lq * D, D, Lk * D, D, D * Lk, Lk, Lq * D, D, 1.0 / math.sqrt(hd),
+                                            0, _stream()), "attention_f32")
+            y = linear(o.view(B * Lq, D), W[f"{p}.out_proj.weight"], W[f"{p}.out_proj.bias"], res=res.view(B * Lq, D), res_scale=res_scale)
+            return y.view(B, Lq, D)
         sc = _new((H, Lq, Lk), q_in)
         fs = 4  # bytes per float
         for b in range(B):
@@ -519,7 +526,7 @@ class DemucsEngine:
     segments that start in that range and receives from its left neighbour the one or two segments that reach into it (b200/sharded.py).
     Per output sample the passes accumulate in the single-GPU order, so the sharded result is the single-GPU result."""
 
-    def __init__(self, nets, bag_weights=None, overlap=0.25, batch_size=4, dist=None, group=None):
+    def __init__(self, nets, bag_weights=None, overlap=0.25, batch_size=4, dist=None, group=None, split=True):
         _require_cuda()
         from .sharded import ShardRunner
 
@@ -536,6 +543,9 @@ class DemucsEngine:
         self.device = self.nets[0].device
         self.runner = ShardRunner(dist, group)
         self.rank, self.world = self.runner.rank, self.runner.world
+        self.split = bool(split)  # apply_model(split=...): False = segments_enabled False, ONE forward over the whole (shifted) track (apply.py:251-260)
+        if not self.split and self.world > 1:
+            raise ValueError("split=False is one forward over the whole track: nothing to shard across ranks")
 
     def out_range(self, N):
         """Output samples [q0, q1) this rank finalises (everything on a single GPU)."""
@@ -589,6 +599,28 @@ class DemucsEngine:
                                                          scale, _ptr(chan_scale) if chan_scale is not None else None, int(accumulate), _ptr(out), sh.q1 - sh.q0, 0,
                                                          _stream()), "triangle_overlap_add_range")
 
+    def _apply_whole(self, net, tensor, offset, length, out, q0, n_out, scale, chan_scale, accumulate):
+        """apply_model's leaf (apply.py:251-260) on TensorChunk(tensor, offset, length): the chunk zero-padded (centred) to model.valid_length(length) -- the training
+        segment for HTDemucs, which REFUSES anything longer (htdemucs.py:469-481); the length itself for models without valid_length -- one forward, center_trim."""
+        cfg = self.cfg
+        S = len(cfg.sources)
+        seg = cfg.seg_len
+        valid = seg if getattr(cfg, "pads_to_segment", True) else length
+        if valid < length:
+            raise ValueError(f"Given length {length} is longer than training length {valid}")
+        delta = valid - length
+        start = offset - delta // 2
+        batch = torch.zeros((1, 2, valid), dtype=torch.float32, device=tensor.device)
+        a, b = max(start, 0), min(start + valid, tensor.shape[-1])
+        if b > a:
+            batch[0, :, a - start : b - start].copy_(tensor[:, a:b])
+        y = net.forward(batch).reshape(S * 2, valid)
+        d = delta // 2  # center_trim (utils.py:53-70): delta // 2 off the left
+        cs = chan_scale.cpu().tolist() if chan_scale is not None else [1.0] * (S * 2)
+        for c in range(S * 2):
+            src = y[c, d + q0 : d + q0 + n_out]
+            ew(src, out[c] if accumulate else None, out[c], scale * cs[c], 1.0 if accumulate else 0.0)
+
     def apply_model(self, mix: torch.Tensor, shift_offsets, net_index=0, out=None, chan_scale=None, accumulate=False):
         """mix (2, N) cuda -> (S*2, q1 - q0): this rank's output range (the whole (S*2, N) on a single GPU).
         shift_offsets: the `random.randint(0, max_shift)` draws of apply.py:207 (empty = shifts 0)."""
@@ -598,14 +630,15 @@ class DemucsEngine:
         r0, r1 = self.out_range(N)
         if out is None:
             out = _new((S * 2, r1 - r0), mix)
+        one = self._apply_split if self.split else self._apply_whole
         if not shift_offsets:
-            self._apply_split(net, mix, 0, N, out, 0, N, 1.0, chan_scale, accumulate)
+            one(net, mix, 0, N, out, 0, N, 1.0, chan_scale, accumulate)
             return out
         ms = int(0.5 * self.cfg.samplerate)
         pm = torch.zeros((2, N + 2 * ms), dtype=torch.float32, device=mix.device)
         pm[:, ms : ms + N].copy_(mix)
         for i, o in enumerate(shift_offsets):
-            self._apply_split(net, pm, o, N + ms - o, out, ms - o, N, 1.0 / len(shift_offsets), chan_scale, accumulate or i > 0)
+            one(net, pm, o, N + ms - o, out, ms - o, N, 1.0 / len(shift_offsets), chan_scale, accumulate or i > 0)
         return out
 
     def demix_device(self, mix_d: torch.Tensor, shift_offsets) -> torch.Tensor:

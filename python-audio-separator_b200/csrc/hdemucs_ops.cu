@@ -48,30 +48,35 @@ __global__ void lstm_frames_scatter_kernel(const float* __restrict__ fr, const f
 
 // ----------------------------------------------------------------------------------------------------------------------------------
 // Bidirectional LSTM recurrence for any hidden size.  One cluster of CL CTAs per (group of NS sequences, direction); CTA r owns the hidden
-// units [r * UH, (r + 1) * UH) and the 4 * UH gate columns that feed them (thread = one gate column, NS accumulators).  Its slice of W_hh^T
-// stays in shared memory when it fits, otherwise it is streamed from L2 every step.  h_t is written into every CTA's shared memory
-// (double-buffered), one cluster barrier per step.
+// units [r * UH, (r + 1) * UH) and the GL = 4 * UH gate columns that feed them.  Thread = (gate column, k-split kq of KS): NS accumulators over
+// its quarter of the hidden dimension -- KS > 1 keeps KS times more weight loads in flight when the CTA's slice of W_hh^T does not fit shared
+// memory and is streamed from L2 every step (the loop is latency-bound).  h_t is written into every CTA's shared memory (double-buffered),
+// one cluster barrier per step.
 template <int NS>
-__global__ void lstm_bidir_cluster_kernel(const float* __restrict__ xp, const float* __restrict__ whh_t, float* __restrict__ out, int T, int N, int hid, int w_in_smem) {
+__global__ void lstm_bidir_cluster_kernel(const float* __restrict__ xp, const float* __restrict__ whh_t, float* __restrict__ out, int T, int N, int hid, int w_in_smem,
+                                          int KS) {
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = (int)cluster.num_blocks();
   const int r = (int)cluster.block_rank();
   const int UH = hid / CL, GL = 4 * UH, G = 4 * hid;
+  const int nthreads = GL * KS;
   const int tid = threadIdx.x;
-  const int gate = tid / UH, ul = tid - gate * UH;
+  const int col = tid % GL, kq = tid / GL;
+  const int gate = col / UH, ul = col - gate * UH;
   const int j = gate * hid + r * UH + ul;  // this thread's column of the (T, N, 4 * hid) gate pre-activations
+  const int kspan = hid / KS, k_lo = kq * kspan, k_hi = k_lo + kspan;
   const int grp = blockIdx.x / CL, dir = blockIdx.y;
   const int n0 = grp * NS;
   extern __shared__ __align__(16) float lsm[];
-  float* hs = lsm;                 // [2][hid][NS]
-  float* gs = hs + 2 * hid * NS;   // [NS][GL]
-  float* cs = gs + NS * GL;        // [NS][UH]
-  float* ws = cs + NS * UH;        // [hid][GL] when w_in_smem
+  float* hs = lsm;                     // [2][hid][NS]
+  float* gs = hs + 2 * hid * NS;       // [KS][NS][GL]
+  float* cs = gs + KS * NS * GL;       // [NS][UH]
+  float* ws = cs + NS * UH;            // [hid][GL] when w_in_smem
   const float* w = whh_t + (int64_t)dir * hid * G;
   if (w_in_smem)
-    for (int k = 0; k < hid; ++k) ws[k * GL + tid] = __ldg(&w[(int64_t)k * G + j]);
-  for (int i = tid; i < 2 * hid * NS; i += GL) hs[i] = 0.f;
-  for (int i = tid; i < NS * UH; i += GL) cs[i] = 0.f;
+    for (int k = k_lo; k < k_hi; ++k) ws[k * GL + col] = __ldg(&w[(int64_t)k * G + j]);
+  for (int i = tid; i < 2 * hid * NS; i += nthreads) hs[i] = 0.f;
+  for (int i = tid; i < NS * UH; i += nthreads) cs[i] = 0.f;
   cluster.sync();  // every CTA's h buffers are zero before the first remote write can land
   const float* xpd = xp + (int64_t)dir * T * N * G;
   int cur = 0;
@@ -79,12 +84,12 @@ __global__ void lstm_bidir_cluster_kernel(const float* __restrict__ xp, const fl
     const int t = dir ? T - 1 - s : s;
     float acc[NS];
 #pragma unroll
-    for (int n = 0; n < NS; ++n) acc[n] = (n0 + n < N) ? __ldg(&xpd[((int64_t)t * N + n0 + n) * G + j]) : 0.f;
+    for (int n = 0; n < NS; ++n) acc[n] = (kq == 0 && n0 + n < N) ? __ldg(&xpd[((int64_t)t * N + n0 + n) * G + j]) : 0.f;
     const float* hc = hs + cur * hid * NS;
     if (w_in_smem) {
 #pragma unroll 4
-      for (int k = 0; k < hid; ++k) {
-        const float wv = ws[k * GL + tid];
+      for (int k = k_lo; k < k_hi; ++k) {
+        const float wv = ws[k * GL + col];
 #pragma unroll
         for (int n = 0; n < NS; n += 4) {
           const float4 hv = *reinterpret_cast<const float4*>(&hc[k * NS + n]);
@@ -95,8 +100,8 @@ __global__ void lstm_bidir_cluster_kernel(const float* __restrict__ xp, const fl
         }
       }
     } else {
-#pragma unroll 8
-      for (int k = 0; k < hid; ++k) {
+#pragma unroll 16
+      for (int k = k_lo; k < k_hi; ++k) {
         const float wv = __ldg(&w[(int64_t)k * G + j]);
 #pragma unroll
         for (int n = 0; n < NS; n += 4) {
@@ -109,13 +114,20 @@ __global__ void lstm_bidir_cluster_kernel(const float* __restrict__ xp, const fl
       }
     }
 #pragma unroll
-    for (int n = 0; n < NS; ++n) gs[n * GL + tid] = acc[n];
+    for (int n = 0; n < NS; ++n) gs[(kq * NS + n) * GL + col] = acc[n];
     __syncthreads();
     float* hn = hs + (cur ^ 1) * hid * NS;
-    for (int i = tid; i < NS * UH; i += GL) {
+    for (int i = tid; i < NS * UH; i += nthreads) {
       const int n = i / UH, u = i - n * UH;
-      const float* g4 = gs + n * GL + u;
-      const float ig = sigmoidf_(g4[0]), fg = sigmoidf_(g4[UH]), gg = tanhf(g4[2 * UH]), og = sigmoidf_(g4[3 * UH]);
+      float g4[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int q = 0; q < KS; ++q) {
+        const float* gp = gs + (q * NS + n) * GL + u;
+        g4[0] += gp[0];
+        g4[1] += gp[UH];
+        g4[2] += gp[2 * UH];
+        g4[3] += gp[3 * UH];
+      }
+      const float ig = sigmoidf_(g4[0]), fg = sigmoidf_(g4[1]), gg = tanhf(g4[2]), og = sigmoidf_(g4[3]);
       const float c = fg * cs[i] + ig * gg;
       cs[i] = c;
       const float h = og * tanhf(c);
@@ -264,10 +276,17 @@ extern "C" int b200sep_lstm_bidir_wide_f32(const float* x_proj, const float* w_h
     }
   const int UH = hid / CL, GL = 4 * UH;
   B2_CHECK_ARG(GL <= 1024, "lstm_bidir_wide_f32: hidden size %d needs %d threads per CTA", hid, GL);
-  size_t smem = ((size_t)2 * hid * NS + (size_t)NS * GL + (size_t)NS * UH) * sizeof(float);
   const size_t wbytes = (size_t)hid * GL * sizeof(float);
-  const int w_in_smem = smem + wbytes <= 200 * 1024;
-  if (w_in_smem) smem += wbytes;
+  const size_t base1 = ((size_t)2 * hid * NS + (size_t)NS * GL + (size_t)NS * UH) * sizeof(float);
+  const int w_in_smem = base1 + wbytes <= 200 * 1024;
+  int KS = 1;  // k-splits per gate column: streamed weights want many loads in flight
+  if (!w_in_smem)
+    for (int c : {4, 2})
+      if (hid % c == 0 && GL * c <= 1024) {
+        KS = c;
+        break;
+      }
+  size_t smem = ((size_t)2 * hid * NS + (size_t)KS * NS * GL + (size_t)NS * UH) * sizeof(float) + (w_in_smem ? wbytes : 0);
   static size_t attr = 0;
   if (smem > attr) {
     B2_CUDA(cudaFuncSetAttribute(lstm_bidir_cluster_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -275,7 +294,7 @@ extern "C" int b200sep_lstm_bidir_wide_f32(const float* x_proj, const float* w_h
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(cdiv(N, NS) * CL), 2);
-  cfg.blockDim = dim3((unsigned)GL);
+  cfg.blockDim = dim3((unsigned)(GL * KS));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = (cudaStream_t)stream;
   cudaLaunchAttribute at[1];
@@ -285,7 +304,7 @@ extern "C" int b200sep_lstm_bidir_wide_f32(const float* x_proj, const float* w_h
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  B2_CUDA(cudaLaunchKernelEx(&cfg, lstm_bidir_cluster_kernel<NS>, x_proj, w_hh_t, out, T, N, hid, w_in_smem));
+  B2_CUDA(cudaLaunchKernelEx(&cfg, lstm_bidir_cluster_kernel<NS>, x_proj, w_hh_t, out, T, N, hid, w_in_smem, KS));
   count_launch();
   return B200SEP_OK;
 }

@@ -137,7 +137,7 @@ __device__ __forceinline__ void fill_kmajor(uint8_t* hi, uint8_t* lo, const floa
 // row-major ("N-major") source: element (r, k) at src[r + k*ks]; lanes walk consecutive rows so the loads coalesce
 __device__ __forceinline__ void fill_nmajor(uint8_t* hi, uint8_t* lo, const float* __restrict__ src, int64_t ks, int rows_tile, int row0, int rows_total, int k0, int K,
                                             int pt) {
-  const int sh = (rows_tile == 256) ? 8 : 7;  // tiles are 128 or 256 rows
+  const int sh = (rows_tile == 256) ? 8 : (rows_tile == 128) ? 7 : 6;  // tiles are 64, 128 or 256 rows
   const int items = rows_tile * 8;
   for (int base = pt; base < items; base += kG * kProdThreads) {
     float v[kG][8];
@@ -535,6 +535,294 @@ int tc_launch(TcParams& p, cudaStream_t st) {
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// ===================================================================================================================================
+// Fused attention for head dimension 64:  O = softmax(alpha * Q K^T) V  per (batch, head), fp32 in / out, every product as bf16 hi/lo x3 on
+// tcgen05 with fp32 accumulation in TMEM -- the score matrix never reaches HBM (the unfused form wrote, re-read, normalised and re-read
+// B*H*Lq*Lk floats: 0.9 GB per HTDemucs frequency layer at batch 4).
+//
+//   one CTA per (128-query tile, batch*head);  key tiles of 128:
+//   warp 0       : MMA issuer: S_j = Q K_j^T (128 x 128, K = 64) into one of two TMEM score buffers, then R_{j-1} = P_{j-1} V_{j-1}
+//                  (128 x 64, K = 128) into one of two TMEM output-tile buffers -- S_{j+1} is in flight while the softmax of tile j runs
+//   warps 1..8   : producers: Q once, then K_j (keys x 64) and V^T_j (64 x keys) fp32 -> bf16 hi/lo -> SWIZZLE_128B shared memory (2 stages)
+//   warps 9..12  : softmax, one thread per query row: row maximum, exp, running sum, P_j split into bf16 hi/lo and written as the A operand
+//                  of the second product; the 64 output accumulators of the row live in registers and are rescaled when the maximum moves
+//                  (R_j is folded in one tile late, so the fold never waits for the tensor core)
+constexpr int kAttProdWarps = 8, kAttSoftWarps = 4;
+constexpr int kAttThreads = 32 * (1 + kAttProdWarps + kAttSoftWarps);  // 416
+constexpr int kAttQ = 128, kAttKeys = 128, kAttD = 64;
+constexpr uint32_t kAttQBytes = kAttQ * 128;            // one plane of Q: 128 rows x 64 bf16
+constexpr uint32_t kAttPBlk = kAttQ * 128;              // one plane of one 64-key block of P
+constexpr uint32_t kAttKBytes = kAttKeys * 128;         // one plane of K_j
+constexpr uint32_t kAttVBlk = kAttD * 128;              // one plane of one 64-key block of V^T_j
+constexpr uint32_t kAttStage = 2 * kAttKBytes + 4 * kAttVBlk;  // 64 KB
+constexpr uint32_t kAttOffP = 2 * kAttQBytes, kAttOffStage = kAttOffP + 4 * kAttPBlk;
+constexpr uint32_t kAttSmem = kAttOffStage + 2 * kAttStage;  // 224 KB
+
+struct AttParams {
+  const float* q;   // q[b * q_bs + m * q_rs + h * 64 + d]
+  const float* k;   // k[b * k_bs + n * k_rs + h * 64 + d]
+  const float* vt;  // vt[b * vt_bs + (h * 64 + d) * vt_rs + n]   (V transposed: keys contiguous)
+  float* out;       // out[b * o_bs + m * o_rs + h * 64 + d]
+  int64_t q_bs, q_rs, k_bs, k_rs, vt_bs, vt_rs, o_bs, o_rs;
+  int H, Lq, Lk;
+  float alpha;
+  int q_vec, k_vec, v_vec, o_vec;
+  int v_kn;  // 1: V given untransposed, v[b * vt_bs + n * vt_rs + h * 64 + d] (the producers gather it d-major)
+};
+
+__global__ void __launch_bounds__(kAttThreads, 1) tc_attention_kernel(const AttParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kAttSmem);
+  uint64_t* q_full = bars;            // [1]
+  uint64_t* kv_full = bars + 1;       // [2]
+  uint64_t* kv_empty = bars + 3;      // [2]
+  uint64_t* s_full = bars + 5;        // [2]
+  uint64_t* s_empty = bars + 7;       // [2]
+  uint64_t* p_full = bars + 9;        // [1]
+  uint64_t* p_empty = bars + 10;      // [1]
+  uint64_t* o_full = bars + 11;       // [2]
+  uint64_t* o_empty = bars + 13;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(q_full, kAttProdWarps);
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&kv_full[a], kAttProdWarps);
+      ptx::mbar_init(&kv_empty[a], 1);
+      ptx::mbar_init(&s_full[a], 1);
+      ptx::mbar_init(&s_empty[a], kAttSoftWarps);
+      ptx::mbar_init(&o_full[a], 1);
+      ptx::mbar_init(&o_empty[a], kAttSoftWarps);
+    }
+    ptx::mbar_init(p_full, kAttSoftWarps);
+    ptx::mbar_init(p_empty, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) ptx::tmem_alloc(tmem_slot, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;  // columns [0, 256): two score buffers; [256, 384): two output-tile buffers
+
+  const int z = blockIdx.y, b = z / p.H, h = z - b * p.H;
+  const int m0 = blockIdx.x * kAttQ;
+  const int nk = (p.Lk + kAttKeys - 1) / kAttKeys;
+  uint8_t* q_hi = smem;
+  uint8_t* q_lo = smem + kAttQBytes;
+  uint8_t* p_hi = smem + kAttOffP;                 // [2 key blocks][128 rows x 128 B]
+  uint8_t* p_lo = smem + kAttOffP + 2 * kAttPBlk;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc_s = ptx::instr_desc_bf16(kAttQ, kAttKeys, 0, 0), idesc_o = ptx::instr_desc_bf16(kAttQ, kAttD, 0, 0);
+      const uint32_t qh = ptx::smem_u32(q_hi), ql = ptx::smem_u32(q_lo), ph_ = ptx::smem_u32(p_hi), pl_ = ptx::smem_u32(p_lo);
+      ptx::mbar_wait(q_full, 0, 500);
+      for (int j = 0; j <= nk; ++j) {
+        if (j < nk) {  // S_j = Q K_j^T
+          const int st = j & 1;
+          const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+          ptx::mbar_wait(&kv_full[st], ph, 510 + st);
+          ptx::mbar_wait(&s_empty[st], ph ^ 1u, 520 + st);
+          ptx::tc_fence_after();
+          const uint32_t d = tmem_base + (uint32_t)st * kAttKeys;
+          const uint32_t kh = ptx::smem_u32(smem + kAttOffStage + (size_t)st * kAttStage), kl = kh + kAttKBytes;
+#pragma unroll
+          for (int jj = 0; jj < kAttD / 16; ++jj) {
+            const uint64_t dqh = ptx::smem_desc(qh + jj * 32, 16, 1024, ptx::kLayoutSW128), dql = ptx::smem_desc(ql + jj * 32, 16, 1024, ptx::kLayoutSW128);
+            const uint64_t dkh = ptx::smem_desc(kh + jj * 32, 16, 1024, ptx::kLayoutSW128), dkl = ptx::smem_desc(kl + jj * 32, 16, 1024, ptx::kLayoutSW128);
+            ptx::umma_bf16(d, dqh, dkh, idesc_s, jj != 0 ? 1u : 0u);
+            ptx::umma_bf16(d, dqh, dkl, idesc_s, 1u);
+            ptx::umma_bf16(d, dql, dkh, idesc_s, 1u);
+          }
+          ptx::umma_commit(&s_full[st]);
+        }
+        if (j > 0) {  // R_{j-1} = P_{j-1} V_{j-1}
+          const int jp = j - 1, st = jp & 1;
+          const uint32_t ph = (uint32_t)(jp >> 1) & 1u;
+          ptx::mbar_wait(p_full, (uint32_t)jp & 1u, 530);
+          ptx::mbar_wait(&o_empty[st], ph ^ 1u, 540 + st);
+          ptx::tc_fence_after();
+          const uint32_t d = tmem_base + 2 * kAttKeys + (uint32_t)st * kAttD;
+          const uint32_t vh = ptx::smem_u32(smem + kAttOffStage + (size_t)st * kAttStage) + 2 * kAttKBytes, vl = vh + 2 * kAttVBlk;
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const uint64_t dph = ptx::smem_desc(ph_ + kb * kAttPBlk + jj * 32, 16, 1024, ptx::kLayoutSW128);
+              const uint64_t dpl = ptx::smem_desc(pl_ + kb * kAttPBlk + jj * 32, 16, 1024, ptx::kLayoutSW128);
+              const uint64_t dvh = ptx::smem_desc(vh + kb * kAttVBlk + jj * 32, 16, 1024, ptx::kLayoutSW128);
+              const uint64_t dvl = ptx::smem_desc(vl + kb * kAttVBlk + jj * 32, 16, 1024, ptx::kLayoutSW128);
+              ptx::umma_bf16(d, dph, dvh, idesc_o, (kb | jj) != 0 ? 1u : 0u);
+              ptx::umma_bf16(d, dph, dvl, idesc_o, 1u);
+              ptx::umma_bf16(d, dpl, dvh, idesc_o, 1u);
+            }
+          }
+          ptx::umma_commit(&o_full[st]);
+          ptx::umma_commit(&kv_empty[st]);
+          ptx::umma_commit(p_empty);
+        }
+      }
+    }
+  } else if (warp <= kAttProdWarps) {
+    // ===== producers =====
+    const int pt = threadIdx.x - 32;
+    const float* qb = p.q + (int64_t)b * p.q_bs + (int64_t)h * kAttD;
+    const float* kb_ = p.k + (int64_t)b * p.k_bs + (int64_t)h * kAttD;
+    const float* vb = p.vt + (int64_t)b * p.vt_bs + (p.v_kn ? (int64_t)h * kAttD : (int64_t)h * kAttD * p.vt_rs);
+    fill_kmajor(q_hi, q_lo, qb, p.q_rs, kAttQ, m0, p.Lq, 0, kAttD, p.q_vec, pt);
+    ptx::fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(q_full);
+    for (int j = 0; j < nk; ++j) {
+      const int st = j & 1;
+      const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+      ptx::mbar_wait(&kv_empty[st], ph ^ 1u, 550 + st);
+      uint8_t* sb = smem + kAttOffStage + (size_t)st * kAttStage;
+      fill_kmajor(sb, sb + kAttKBytes, kb_, p.k_rs, kAttKeys, j * kAttKeys, p.Lk, 0, kAttD, p.k_vec, pt);
+      uint8_t* vh = sb + 2 * kAttKBytes;
+      uint8_t* vl = vh + 2 * kAttVBlk;
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) {
+        if (p.v_kn) fill_nmajor(vh + kb * kAttVBlk, vl + kb * kAttVBlk, vb, p.vt_rs, kAttD, 0, kAttD, j * kAttKeys + kb * 64, p.Lk, pt);
+        else fill_kmajor(vh + kb * kAttVBlk, vl + kb * kAttVBlk, vb, p.vt_rs, kAttD, 0, kAttD, j * kAttKeys + kb * 64, p.Lk, p.v_vec, pt);
+      }
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&kv_full[st]);
+    }
+  } else {
+    // ===== softmax: thread = query row (TMEM lane quadrant = warp % 4) =====
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const int m = m0 + row;
+    const uint32_t tlane = tmem_base + ((uint32_t)(qd * 32) << 16);
+    float mrun = -INFINITY, l = 0.f, corr_prev = 1.f;
+    float O[kAttD];
+#pragma unroll
+    for (int e = 0; e < kAttD; ++e) O[e] = 0.f;
+    for (int j = 0; j <= nk; ++j) {
+      float corr = 1.f;
+      if (j < nk) {
+        const int st = j & 1;
+        const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+        ptx::mbar_wait(&s_full[st], ph, 560 + st);
+        ptx::tc_fence_after();
+        const uint32_t ts = tlane + (uint32_t)st * kAttKeys;
+        const int nvalid = min(kAttKeys, p.Lk - j * kAttKeys);
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          ptx::tmem_ld32(ts + c * 32, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (c * 32 + e < nvalid) mx = fmaxf(mx, __uint_as_float(v[e]));
+        }
+        const float mnew = fmaxf(mrun, mx * p.alpha);
+        corr = expf(mrun - mnew);  // first tile: exp(-inf) = 0
+        mrun = mnew;
+        ptx::mbar_wait(p_empty, ((uint32_t)j & 1u) ^ 1u, 570);  // P_{j-1} consumed by the tensor core
+        float lsum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          ptx::tmem_ld32(ts + c * 32, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            float pv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int col = c * 32 + ch * 8 + e;
+              pv[e] = col < nvalid ? expf(fmaf(__uint_as_float(v[ch * 8 + e]), p.alpha, -mnew)) : 0.f;
+              lsum += pv[e];
+            }
+            const int chunk = c * 4 + ch;  // 16 chunks of 8 keys; chunks 0..7 = key block 0
+            store_chunk(p_hi + (chunk >> 3) * kAttPBlk, p_lo + (chunk >> 3) * kAttPBlk, row, chunk & 7, pv);
+          }
+        }
+        l = l * corr + lsum;
+        ptx::tc_fence_before();
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::mbar_arrive(&s_empty[st]);
+          ptx::mbar_arrive(p_full);
+        }
+      }
+      if (j > 0) {  // fold R_{j-1} (relative to the maximum after tile j-1) into the accumulators (relative to the maximum after tile j-2)
+        const int jp = j - 1, st = jp & 1;
+        const uint32_t ph = (uint32_t)(jp >> 1) & 1u;
+        ptx::mbar_wait(&o_full[st], ph, 580 + st);
+        ptx::tc_fence_after();
+        const uint32_t to = tlane + 2 * kAttKeys + (uint32_t)st * kAttD;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          ptx::tmem_ld32(to + c * 32, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) O[c * 32 + e] = fmaf(O[c * 32 + e], corr_prev, __uint_as_float(v[e]));
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&o_empty[st]);
+      }
+      corr_prev = corr;
+    }
+    if (m < p.Lq) {
+      const float inv = 1.f / l;
+      float* o = p.out + (int64_t)b * p.o_bs + (int64_t)m * p.o_rs + (int64_t)h * kAttD;
+      if (p.o_vec) {
+#pragma unroll
+        for (int e = 0; e < kAttD; e += 4) *reinterpret_cast<float4*>(o + e) = make_float4(O[e] * inv, O[e + 1] * inv, O[e + 2] * inv, O[e + 3] * inv);
+      } else {
+#pragma unroll
+        for (int e = 0; e < kAttD; ++e) o[e] = O[e] * inv;
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+bool tc_attention_usable(int hd, int Lq, int Lk) { return tc_enabled() && hd == kAttD && Lq >= 1 && Lk >= 1; }
+
+int tc_attention_f32(const float* q, const float* k, const float* vt, float* out, int B, int H, int Lq, int Lk, int64_t q_bs, int64_t q_rs, int64_t k_bs, int64_t k_rs,
+                     int64_t vt_bs, int64_t vt_rs, int64_t o_bs, int64_t o_rs, float alpha, int v_kn, cudaStream_t st) {
+  AttParams p{};
+  p.v_kn = v_kn;
+  p.q = q; p.k = k; p.vt = vt; p.out = out;
+  p.q_bs = q_bs; p.q_rs = q_rs; p.k_bs = k_bs; p.k_rs = k_rs; p.vt_bs = vt_bs; p.vt_rs = vt_rs; p.o_bs = o_bs; p.o_rs = o_rs;
+  p.H = H; p.Lq = Lq; p.Lk = Lk; p.alpha = alpha;
+  p.q_vec = (q_rs % 4 == 0) && (q_bs % 4 == 0) && aligned16(q);
+  p.k_vec = (k_rs % 4 == 0) && (k_bs % 4 == 0) && aligned16(k);
+  p.v_vec = (vt_rs % 4 == 0) && (vt_bs % 4 == 0) && aligned16(vt);
+  p.o_vec = (o_rs % 4 == 0) && (o_bs % 4 == 0) && aligned16(out);
+  const size_t smem = (size_t)kAttSmem + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2_CUDA(cudaFuncSetAttribute(tc_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  B2_CHECK_ARG((int64_t)B * H <= 65535, "attention_f32: batch * heads too large");
+  dim3 grid((unsigned)cdiv(Lq, kAttQ), (unsigned)(B * H));
+  tc_attention_kernel<<<grid, kAttThreads, smem, st>>>(p);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
+namespace {
 }  // namespace
 
 bool tc_enabled() {
@@ -625,3 +913,16 @@ int tc_conv2d_f32(const float* x, const float* w_blocked, const float* bias, con
 }
 
 }  // namespace b200sep
+
+// softmax(alpha Q K^T) V per (batch, head) for head dimension 64 without materialising the scores (nn.MultiheadAttention of the HTDemucs
+// cross-transformer, transformer.py:196-409; Attend of the Roformers).  Layouts in the header.
+extern "C" int b200sep_attention_f32(const float* q, const float* k, const float* vt, float* out, int B, int H, int Lq, int Lk, int head_dim, int64_t q_batch_stride,
+                                     int64_t q_row_stride, int64_t k_batch_stride, int64_t k_row_stride, int64_t vt_batch_stride, int64_t vt_row_stride,
+                                     int64_t out_batch_stride, int64_t out_row_stride, float alpha, int v_is_kn, void* stream) {
+  using namespace b200sep;
+  B2_CHECK_ARG(q && k && vt && out && B >= 1 && H >= 1 && Lq >= 1 && Lk >= 1 && alpha > 0.f, "attention_f32: bad argument");
+  B2_CHECK_ARG(head_dim == 64, "attention_f32: head dimension %d is not supported (64 only)", head_dim);
+  B2_CHECK_ARG(v_is_kn ? vt_row_stride >= 64 : vt_row_stride >= Lk, "attention_f32: V row stride %lld too short", (long long)vt_row_stride);
+  return tc_attention_f32(q, k, vt, out, B, H, Lq, Lk, q_batch_stride, q_row_stride, k_batch_stride, k_row_stride, vt_batch_stride, vt_row_stride, out_batch_stride,
+                          out_row_stride, alpha, v_is_kn, (cudaStream_t)stream);
+}

@@ -105,7 +105,8 @@ def test_local_state_attention_vs_oracle(hd, C, T, B):
     dots.masked_fill_(torch.eye(T, dtype=torch.bool), -100)
     ref = torch.einsum("bhts,bhct->bhcs", torch.softmax(dots, dim=2), cc).reshape(B, C, T)
     out = torch.empty((B, C, T), device="cuda")
-    check(lib.b200sep_local_state_attn_f32(_ptr(q.cuda()), _ptr(k.cuda()), _ptr(ct.cuda()), _ptr(dq.cuda()), _ptr(out), B, C, T, heads, nd, _stream()), "local_state_attn_f32")
+    qd, kd, cd, dd = q.cuda(), k.cuda(), ct.cuda(), dq.cuda()  # held in variables: a temporary would be freed (and its memory reused) before the launch
+    check(lib.b200sep_local_state_attn_f32(_ptr(qd), _ptr(kd), _ptr(cd), _ptr(dd), _ptr(out), B, C, T, heads, nd, _stream()), "local_state_attn_f32")
     torch.cuda.synchronize()
     assert (out.cpu().double() - ref).abs().max() <= 2e-5 * max(1.0, ref.abs().max())
 
@@ -163,12 +164,12 @@ def test_encoder_layers_vs_oracle_taps(small):
 
     def enc(x, prefix, L, inject=None):
         y = orig_enc(x, prefix, L, inject)
-        got[prefix] = y
+        got[prefix] = y.clone() if prefix != "encoder.0" else y  # encoder.0: the frequency embedding is added in place afterwards, as in the oracle's tap
         return y
 
     def dec(x, skip, length, prefix, L):
         zz, y = orig_dec(x, skip, length, prefix, L)
-        got[prefix] = zz
+        got[prefix] = zz.clone()  # the last decoder output is de-normalised in place by forward()
         return zz, y
 
     net._enc_layer, net._dec_layer = enc, dec
@@ -216,3 +217,36 @@ def test_full_size_forward_vs_oracle(hd):
     got = net.forward(dev(mix)).cpu().numpy()
     err = float(np.abs(got - ref).max())
     assert err <= 1e-4 * max(1.0, float(np.abs(ref).max())), (err, float(np.abs(ref).max()))
+
+
+def test_apply_model_without_segments_vs_reference_golden(hd, small):
+    """segments_enabled=False = apply_model(split=False): one forward over the whole shifted track (HDemucs has no valid_length)."""
+    from audio_separator.separator.b200.demucs import DemucsEngine
+
+    z, ocfg, w, net, mix = small
+    N = int(z["n_apply"])
+    m2 = torch.from_numpy(mix[:, :N])
+    mn = ((m2 - m2.mean(0).mean()) / m2.mean(0).std()).numpy()
+    eng = DemucsEngine([net], overlap=0.25, split=False)
+    got = eng.apply_model(dev(mn), [int(v) for v in z["nosplit_offsets"]]).cpu().numpy().reshape(1, 4, 2, N)
+    assert np.abs(got - z["nosplit_ref"]).max() <= 1e-4 * max(1.0, np.abs(z["nosplit_ref"]).max())
+
+
+def test_htdemucs_without_segments_vs_reference_golden(lib_built, golden_dir, small):
+    """HTDemucs with segments_enabled=False: the clip is zero-padded (centred) to the training segment; anything longer raises like the reference (htdemucs.py:469-481)."""
+    from fractions import Fraction
+
+    import demucs_oracle as D
+    from audio_separator.separator.b200 import demucs as dm
+
+    z, _, _, _, mix = small
+    SM = dict(channels=8, bottom_channels=32, t_layers=3, t_heads=4, segment=Fraction(1, 2))
+    net = dm.HTDemucsNet(dm.HTDemucsConfig(**SM), D.make_weights(D.HTConfig(**SM), seed=5))
+    N = int(z["ht_nosplit_n"])
+    m2 = torch.from_numpy(mix[:, :N])
+    mn = ((m2 - m2.mean(0).mean()) / m2.mean(0).std()).numpy()
+    eng = dm.DemucsEngine([net], split=False)
+    got = eng.apply_model(dev(mn), []).cpu().numpy().reshape(1, 4, 2, N)
+    assert np.abs(got - z["ht_nosplit_ref"]).max() <= 1e-4 * max(1.0, np.abs(z["ht_nosplit_ref"]).max())
+    with pytest.raises(ValueError, match="longer than training length"):
+        eng.apply_model(dev(np.zeros((2, net.cfg.seg_len + 10), np.float32)), [])

@@ -99,3 +99,34 @@ def test_tc_conv2d_slice_and_add(dm):
     assert (o[:, :10] == 7).all() and (o[:, 43:] == 7).all()
     got = dm.conv2d(x.cuda(), wb, b.cuda(), 33, (3, 3), p=(1, 1), act=dm.ACT_RELU, add=add.cuda(), add_before_act=False).cpu()
     assert rel_err(got, F.relu(ref) + add.double()) <= 3e-5
+
+
+# ------------------------------------------------------------------------------------------------ fused attention (head dimension 64)
+@pytest.mark.parametrize(
+    "B,H,Lq,Lk,v_kn",
+    [(2, 3, 200, 1344, 0), (1, 2, 130, 130, 1), (1, 8, 2688, 2688, 0), (2, 2, 1344, 2688, 0), (3, 1, 1101, 1101, 1), (1, 1, 5, 7, 0), (1, 2, 128, 256, 1)],
+)
+def test_fused_attention_vs_fp64(lib_built, B, H, Lq, Lk, v_kn):
+    """b200sep_attention_f32 (scores in TMEM, running softmax, P V from shared memory) against softmax(q k^T / 8) v in float64; ragged query / key tiles,
+    both V layouts (transposed with keys contiguous: HTDemucs; plain (keys, d): Roformer)."""
+    from audio_separator.separator.b200._lib import check, lib
+    from audio_separator.separator.b200.engine import _ptr, _stream
+
+    g = torch.Generator().manual_seed(B * 1000 + Lq + Lk)
+    D = H * 64
+    q = torch.randn((B, Lq, D), generator=g) * 1.5
+    k = torch.randn((B, Lk, D), generator=g) * 1.5
+    v = torch.randn((B, Lk, D), generator=g)
+    qh, kh, vh = (t.double().view(B, -1, H, 64).transpose(1, 2) for t in (q, k, v))
+    ref = (torch.softmax(qh @ kh.transpose(-1, -2) / 8.0, dim=-1) @ vh).transpose(1, 2).reshape(B, Lq, D)
+    qd, kd = q.cuda(), k.cuda()
+    out = torch.full((B, Lq, D), float("nan"), device="cuda")
+    if v_kn:
+        vd = v.cuda()
+        check(lib.b200sep_attention_f32(_ptr(qd), _ptr(kd), _ptr(vd), _ptr(out), B, H, Lq, Lk, 64, Lq * D, D, Lk * D, D, Lk * D, D, Lq * D, D, 0.125, 1, _stream()), "attention_f32")
+    else:
+        vd = v.transpose(1, 2).contiguous().cuda()  # (B, D, Lk)
+        check(lib.b200sep_attention_f32(_ptr(qd), _ptr(kd), _ptr(vd), _ptr(out), B, H, Lq, Lk, 64, Lq * D, D, Lk * D, D, D * Lk, Lk, Lq * D, D, 0.125, 0, _stream()), "attention_f32")
+    torch.cuda.synchronize()
+    err = (out.cpu().double() - ref).abs().max().item()
+    assert err <= 3e-5 * max(1.0, ref.abs().max().item()), err
