@@ -25,6 +25,7 @@ void count_launch(int n = 1);
     cudaError_t e__ = (call);                                                                      \
     if (e__ != cudaSuccess) {                                                                      \
       ::b200sep::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      (void)cudaGetLastError(); /* a failed launch API call also latches the error: do not let the NEXT launch check report it */ \
       return B200SEP_ERR_CUDA;                                                                     \
     }                                                                                              \
   } while (0)

@@ -53,7 +53,7 @@ __global__ void lstm_frames_scatter_kernel(const float* __restrict__ fr, const f
 // memory and is streamed from L2 every step (the loop is latency-bound).  h_t is written into every CTA's shared memory (double-buffered),
 // one cluster barrier per step.
 template <int NS>
-__global__ void lstm_bidir_cluster_kernel(const float* __restrict__ xp, const float* __restrict__ whh_t, float* __restrict__ out, int T, int N, int hid, int w_in_smem,
+__global__ void __launch_bounds__(768) lstm_bidir_cluster_kernel(const float* __restrict__ xp, const float* __restrict__ whh_t, float* __restrict__ out, int T, int N, int hid, int w_in_smem,
                                           int KS) {
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = (int)cluster.num_blocks();
@@ -275,14 +275,14 @@ extern "C" int b200sep_lstm_bidir_wide_f32(const float* x_proj, const float* w_h
       break;
     }
   const int UH = hid / CL, GL = 4 * UH;
-  B2_CHECK_ARG(GL <= 1024, "lstm_bidir_wide_f32: hidden size %d needs %d threads per CTA", hid, GL);
+  B2_CHECK_ARG(GL <= 768, "lstm_bidir_wide_f32: hidden size %d needs %d threads per CTA", hid, GL);
   const size_t wbytes = (size_t)hid * GL * sizeof(float);
   const size_t base1 = ((size_t)2 * hid * NS + (size_t)NS * GL + (size_t)NS * UH) * sizeof(float);
   const int w_in_smem = base1 + wbytes <= 200 * 1024;
   int KS = 1;  // k-splits per gate column: streamed weights want many loads in flight
   if (!w_in_smem)
     for (int c : {4, 2})
-      if (hid % c == 0 && GL * c <= 1024) {
+      if (hid % c == 0 && GL * c <= 768) {
         KS = c;
         break;
       }

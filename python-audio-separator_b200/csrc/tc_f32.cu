@@ -570,6 +570,12 @@ struct AttParams {
   int v_kn;  // 1: V given untransposed, v[b * vt_bs + n * vt_rs + h * 64 + d] (the producers gather it d-major)
 };
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __global__ void __launch_bounds__(kAttThreads, 1) tc_attention_kernel(const AttParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -699,6 +705,9 @@ __global__ void __launch_bounds__(kAttThreads, 1) tc_attention_kernel(const AttP
     const int row = qd * 32 + lane;
     const int m = m0 + row;
     const uint32_t tlane = tmem_base + ((uint32_t)(qd * 32) << 16);
+    // base-2 domain: p = 2^(s * a2 - m2) with a2 = alpha * log2(e): one FFMA + one MUFU.EX2 per score (expf() costs ~10 instructions, and this warp is
+    // the only softmax warp of its scheduler: its instruction count is the kernel's critical path)
+    const float a2 = p.alpha * 1.4426950408889634f;
     float mrun = -INFINITY, l = 0.f, corr_prev = 1.f;
     float O[kAttD];
 #pragma unroll
@@ -712,18 +721,24 @@ __global__ void __launch_bounds__(kAttThreads, 1) tc_attention_kernel(const AttP
         ptx::tc_fence_after();
         const uint32_t ts = tlane + (uint32_t)st * kAttKeys;
         const int nvalid = min(kAttKeys, p.Lk - j * kAttKeys);
+        const bool full = nvalid == kAttKeys;  // warp-uniform
         float mx = -INFINITY;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t v[32];
           ptx::tmem_ld32(ts + c * 32, v);
           ptx::tmem_ld_wait();
+          if (full) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (c * 32 + e < nvalid) mx = fmaxf(mx, __uint_as_float(v[e]));
+            for (int e = 0; e < 32; e += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[e]), __uint_as_float(v[e + 1])));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (c * 32 + e < nvalid) mx = fmaxf(mx, __uint_as_float(v[e]));
+          }
         }
-        const float mnew = fmaxf(mrun, mx * p.alpha);
-        corr = expf(mrun - mnew);  // first tile: exp(-inf) = 0
+        const float mnew = fmaxf(mrun, mx * a2);
+        corr = ex2_approx(mrun - mnew);  // first tile: 2^(-inf) = 0
         mrun = mnew;
         ptx::mbar_wait(p_empty, ((uint32_t)j & 1u) ^ 1u, 570);  // P_{j-1} consumed by the tensor core
         float lsum = 0.f;
@@ -737,8 +752,8 @@ __global__ void __launch_bounds__(kAttThreads, 1) tc_attention_kernel(const AttP
             float pv[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              const int col = c * 32 + ch * 8 + e;
-              pv[e] = col < nvalid ? expf(fmaf(__uint_as_float(v[ch * 8 + e]), p.alpha, -mnew)) : 0.f;
+              const float x = ex2_approx(fmaf(__uint_as_float(v[ch * 8 + e]), a2, -mnew));
+              pv[e] = (full || c * 32 + ch * 8 + e < nvalid) ? x : 0.f;
               lsum += pv[e];
             }
             const int chunk = c * 4 + ch;  // 16 chunks of 8 keys; chunks 0..7 = key block 0
