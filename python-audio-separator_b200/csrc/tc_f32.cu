@@ -102,14 +102,15 @@ __device__ __forceinline__ void store_chunk(uint8_t* plane_hi, uint8_t* plane_lo
 constexpr int kG = 4;
 
 // K-major source: rows x 64 k, element (r, k) at src[r*rs + k].  pt = producer thread index (0..255).
+template <int NT = kProdThreads>
 __device__ __forceinline__ void fill_kmajor(uint8_t* hi, uint8_t* lo, const float* __restrict__ src, int64_t rs, int rows_tile, int row0, int rows_total, int k0,
                                             int K, int vec, int pt) {
   const int items = rows_tile * 8;
-  for (int base = pt; base < items; base += kG * kProdThreads) {
+  for (int base = pt; base < items; base += kG * NT) {
     float v[kG][8];
 #pragma unroll
     for (int g = 0; g < kG; ++g) {
-      const int id = base + g * kProdThreads;
+      const int id = base + g * NT;
       const int r = id >> 3, c = id & 7;
       const int k = k0 + c * 8;
 #pragma unroll
@@ -128,22 +129,23 @@ __device__ __forceinline__ void fill_kmajor(uint8_t* hi, uint8_t* lo, const floa
     }
 #pragma unroll
     for (int g = 0; g < kG; ++g) {
-      const int id = base + g * kProdThreads;
+      const int id = base + g * NT;
       if (id < items) store_chunk(hi, lo, id >> 3, id & 7, v[g]);
     }
   }
 }
 
 // row-major ("N-major") source: element (r, k) at src[r + k*ks]; lanes walk consecutive rows so the loads coalesce
+template <int NT = kProdThreads>
 __device__ __forceinline__ void fill_nmajor(uint8_t* hi, uint8_t* lo, const float* __restrict__ src, int64_t ks, int rows_tile, int row0, int rows_total, int k0, int K,
                                             int pt) {
   const int sh = (rows_tile == 256) ? 8 : (rows_tile == 128) ? 7 : 6;  // tiles are 64, 128 or 256 rows
   const int items = rows_tile * 8;
-  for (int base = pt; base < items; base += kG * kProdThreads) {
+  for (int base = pt; base < items; base += kG * NT) {
     float v[kG][8];
 #pragma unroll
     for (int g = 0; g < kG; ++g) {
-      const int id = base + g * kProdThreads;
+      const int id = base + g * NT;
       const int r = id & (rows_tile - 1), c = id >> sh;
       const int k = k0 + c * 8;
 #pragma unroll
@@ -157,7 +159,7 @@ __device__ __forceinline__ void fill_nmajor(uint8_t* hi, uint8_t* lo, const floa
     }
 #pragma unroll
     for (int g = 0; g < kG; ++g) {
-      const int id = base + g * kProdThreads;
+      const int id = base + g * NT;
       if (id < items) store_chunk(hi, lo, id & (rows_tile - 1), id >> sh, v[g]);
     }
   }
@@ -543,7 +545,8 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 //   one CTA per (128-query tile, batch*head);  key tiles of 128:
 //   warp 0       : MMA issuer: S_j = Q K_j^T (128 x 128, K = 64) into one of two TMEM score buffers, then R_{j-1} = P_{j-1} V_{j-1}
 //                  (128 x 64, K = 128) into one of two TMEM output-tile buffers -- S_{j+1} is in flight while the softmax of tile j runs
-//   warps 1..8   : producers: Q once, then K_j (keys x 64) and V^T_j (64 x keys) fp32 -> bf16 hi/lo -> SWIZZLE_128B shared memory (2 stages)
+//   warps 1..4   : K producers: Q once, then K_j (keys x 64) fp32 -> bf16 hi/lo -> SWIZZLE_128B shared memory (2 slots, freed when S_j completes)
+//   warps 5..8   : V producers: V^T_j (64 x keys), 2 slots freed when R_j completes
 //   warps 9..12  : softmax, one thread per query row: row maximum, exp, running sum, P_j split into bf16 hi/lo and written as the A operand
 //                  of the second product; the 64 output accumulators of the row live in registers and are rescaled when the maximum moves
 //                  (R_j is folded in one tile late, so the fold never waits for the tensor core)
@@ -581,22 +584,26 @@ __global__ void __launch_bounds__(kAttThreads, 1) tc_attention_kernel(const AttP
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kAttSmem);
   uint64_t* q_full = bars;            // [1]
-  uint64_t* kv_full = bars + 1;       // [2]
-  uint64_t* kv_empty = bars + 3;      // [2]
-  uint64_t* s_full = bars + 5;        // [2]
-  uint64_t* s_empty = bars + 7;       // [2]
-  uint64_t* p_full = bars + 9;        // [1]
-  uint64_t* p_empty = bars + 10;      // [1]
-  uint64_t* o_full = bars + 11;       // [2]
-  uint64_t* o_empty = bars + 13;      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* k_full = bars + 1;        // [2]  K_j converted            (K producer warps -> MMA)
+  uint64_t* k_empty = bars + 3;       // [2]  S_j done: K slot free     (MMA commit -> K producers)
+  uint64_t* v_full = bars + 5;        // [2]
+  uint64_t* v_empty = bars + 7;       // [2]  R_j done: V slot free
+  uint64_t* s_full = bars + 9;        // [2]
+  uint64_t* s_empty = bars + 11;      // [2]
+  uint64_t* p_full = bars + 13;       // [1]
+  uint64_t* p_empty = bars + 14;      // [1]
+  uint64_t* o_full = bars + 15;       // [2]
+  uint64_t* o_empty = bars + 17;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    ptx::mbar_init(q_full, kAttProdWarps);
+    ptx::mbar_init(q_full, kAttProdWarps / 2);
     for (int a = 0; a < 2; ++a) {
-      ptx::mbar_init(&kv_full[a], kAttProdWarps);
-      ptx::mbar_init(&kv_empty[a], 1);
+      ptx::mbar_init(&k_full[a], kAttProdWarps / 2);
+      ptx::mbar_init(&k_empty[a], 1);
+      ptx::mbar_init(&v_full[a], kAttProdWarps / 2);
+      ptx::mbar_init(&v_empty[a], 1);
       ptx::mbar_init(&s_full[a], 1);
       ptx::mbar_init(&s_empty[a], kAttSoftWarps);
       ptx::mbar_init(&o_full[a], 1);
@@ -626,78 +633,107 @@ __global__ void __launch_bounds__(kAttThreads, 1) tc_attention_kernel(const AttP
       const uint32_t idesc_s = ptx::instr_desc_bf16(kAttQ, kAttKeys, 0, 0), idesc_o = ptx::instr_desc_bf16(kAttQ, kAttD, 0, 0);
       const uint32_t qh = ptx::smem_u32(q_hi), ql = ptx::smem_u32(q_lo), ph_ = ptx::smem_u32(p_hi), pl_ = ptx::smem_u32(p_lo);
       ptx::mbar_wait(q_full, 0, 500);
-      for (int j = 0; j <= nk; ++j) {
-        if (j < nk) {  // S_j = Q K_j^T
-          const int st = j & 1;
-          const uint32_t ph = (uint32_t)(j >> 1) & 1u;
-          ptx::mbar_wait(&kv_full[st], ph, 510 + st);
-          ptx::mbar_wait(&s_empty[st], ph ^ 1u, 520 + st);
-          ptx::tc_fence_after();
-          const uint32_t d = tmem_base + (uint32_t)st * kAttKeys;
-          const uint32_t kh = ptx::smem_u32(smem + kAttOffStage + (size_t)st * kAttStage), kl = kh + kAttKBytes;
+      // Two instruction streams, issued in whatever order their inputs arrive: S_js = Q K_js^T needs K_js and a free score buffer, R_jo = P_jo V_jo needs
+      // P_jo, V_jo and a free output-tile buffer.  (A fixed S, R, S, R order made R_{j-1} wait for the K_j conversion and serialised the pipeline.)
+      int js = 0, jo = 0;
+      uint32_t idle = 0;
+      while (jo < nk) {
+        bool did = false;
+        if (js < nk) {
+          const int st = js & 1;
+          const uint32_t ph = (uint32_t)(js >> 1) & 1u;
+          if (ptx::mbar_try_wait(&k_full[st], ph) && ptx::mbar_try_wait(&s_empty[st], ph ^ 1u)) {
+            ptx::tc_fence_after();
+            const uint32_t d = tmem_base + (uint32_t)st * kAttKeys;
+            const uint32_t kh = ptx::smem_u32(smem + kAttOffStage + (size_t)st * kAttStage), kl = kh + kAttKBytes;
 #pragma unroll
-          for (int jj = 0; jj < kAttD / 16; ++jj) {
-            const uint64_t dqh = ptx::smem_desc(qh + jj * 32, 16, 1024, ptx::kLayoutSW128), dql = ptx::smem_desc(ql + jj * 32, 16, 1024, ptx::kLayoutSW128);
-            const uint64_t dkh = ptx::smem_desc(kh + jj * 32, 16, 1024, ptx::kLayoutSW128), dkl = ptx::smem_desc(kl + jj * 32, 16, 1024, ptx::kLayoutSW128);
-            ptx::umma_bf16(d, dqh, dkh, idesc_s, jj != 0 ? 1u : 0u);
-            ptx::umma_bf16(d, dqh, dkl, idesc_s, 1u);
-            ptx::umma_bf16(d, dql, dkh, idesc_s, 1u);
-          }
-          ptx::umma_commit(&s_full[st]);
-        }
-        if (j > 0) {  // R_{j-1} = P_{j-1} V_{j-1}
-          const int jp = j - 1, st = jp & 1;
-          const uint32_t ph = (uint32_t)(jp >> 1) & 1u;
-          ptx::mbar_wait(p_full, (uint32_t)jp & 1u, 530);
-          ptx::mbar_wait(&o_empty[st], ph ^ 1u, 540 + st);
-          ptx::tc_fence_after();
-          const uint32_t d = tmem_base + 2 * kAttKeys + (uint32_t)st * kAttD;
-          const uint32_t vh = ptx::smem_u32(smem + kAttOffStage + (size_t)st * kAttStage) + 2 * kAttKBytes, vl = vh + 2 * kAttVBlk;
-#pragma unroll
-          for (int kb = 0; kb < 2; ++kb) {
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const uint64_t dph = ptx::smem_desc(ph_ + kb * kAttPBlk + jj * 32, 16, 1024, ptx::kLayoutSW128);
-              const uint64_t dpl = ptx::smem_desc(pl_ + kb * kAttPBlk + jj * 32, 16, 1024, ptx::kLayoutSW128);
-              const uint64_t dvh = ptx::smem_desc(vh + kb * kAttVBlk + jj * 32, 16, 1024, ptx::kLayoutSW128);
-              const uint64_t dvl = ptx::smem_desc(vl + kb * kAttVBlk + jj * 32, 16, 1024, ptx::kLayoutSW128);
-              ptx::umma_bf16(d, dph, dvh, idesc_o, (kb | jj) != 0 ? 1u : 0u);
-              ptx::umma_bf16(d, dph, dvl, idesc_o, 1u);
-              ptx::umma_bf16(d, dpl, dvh, idesc_o, 1u);
+            for (int jj = 0; jj < kAttD / 16; ++jj) {
+              const uint64_t dqh = ptx::smem_desc(qh + jj * 32, 16, 1024, ptx::kLayoutSW128), dql = ptx::smem_desc(ql + jj * 32, 16, 1024, ptx::kLayoutSW128);
+              const uint64_t dkh = ptx::smem_desc(kh + jj * 32, 16, 1024, ptx::kLayoutSW128), dkl = ptx::smem_desc(kl + jj * 32, 16, 1024, ptx::kLayoutSW128);
+              ptx::umma_bf16(d, dqh, dkh, idesc_s, jj != 0 ? 1u : 0u);
+              ptx::umma_bf16(d, dqh, dkl, idesc_s, 1u);
+              ptx::umma_bf16(d, dql, dkh, idesc_s, 1u);
             }
+            ptx::umma_commit(&s_full[st]);
+            ptx::umma_commit(&k_empty[st]);
+            ++js;
+            did = true;
           }
-          ptx::umma_commit(&o_full[st]);
-          ptx::umma_commit(&kv_empty[st]);
-          ptx::umma_commit(p_empty);
+        }
+        if (jo < js) {
+          const int st = jo & 1;
+          const uint32_t ph = (uint32_t)(jo >> 1) & 1u;
+          if (ptx::mbar_try_wait(p_full, (uint32_t)jo & 1u) && ptx::mbar_try_wait(&v_full[st], ph) && ptx::mbar_try_wait(&o_empty[st], ph ^ 1u)) {
+            ptx::tc_fence_after();
+            const uint32_t d = tmem_base + 2 * kAttKeys + (uint32_t)st * kAttD;
+            const uint32_t vh = ptx::smem_u32(smem + kAttOffStage + (size_t)st * kAttStage) + 2 * kAttKBytes, vl = vh + 2 * kAttVBlk;
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const uint64_t dph = ptx::smem_desc(ph_ + kb * kAttPBlk + jj * 32, 16, 1024, ptx::kLayoutSW128);
+                const uint64_t dpl = ptx::smem_desc(pl_ + kb * kAttPBlk + jj * 32, 16, 1024, ptx::kLayoutSW128);
+                const uint64_t dvh = ptx::smem_desc(vh + kb * kAttVBlk + jj * 32, 16, 1024, ptx::kLayoutSW128);
+                const uint64_t dvl = ptx::smem_desc(vl + kb * kAttVBlk + jj * 32, 16, 1024, ptx::kLayoutSW128);
+                ptx::umma_bf16(d, dph, dvh, idesc_o, (kb | jj) != 0 ? 1u : 0u);
+                ptx::umma_bf16(d, dph, dvl, idesc_o, 1u);
+                ptx::umma_bf16(d, dpl, dvh, idesc_o, 1u);
+              }
+            }
+            ptx::umma_commit(&o_full[st]);
+            ptx::umma_commit(&v_empty[st]);
+            ptx::umma_commit(p_empty);
+            ++jo;
+            did = true;
+          }
+        }
+        if (did) {
+          idle = 0;
+        } else if (++idle > (1u << 24)) {
+          printf("b200sep: attention MMA issuer stalled block=(%d,%d) js=%d jo=%d\n", blockIdx.x, blockIdx.y, js, jo);
+          __trap();
         }
       }
     }
-  } else if (warp <= kAttProdWarps) {
-    // ===== producers =====
+  } else if (warp <= kAttProdWarps / 2) {
+    // ===== K producers (warps 1..4): Q once, then K_j into the K half of stage j % 2 as soon as S_{j-2} has consumed it =====
+    constexpr int NT = 32 * (kAttProdWarps / 2);
     const int pt = threadIdx.x - 32;
     const float* qb = p.q + (int64_t)b * p.q_bs + (int64_t)h * kAttD;
     const float* kb_ = p.k + (int64_t)b * p.k_bs + (int64_t)h * kAttD;
-    const float* vb = p.vt + (int64_t)b * p.vt_bs + (p.v_kn ? (int64_t)h * kAttD : (int64_t)h * kAttD * p.vt_rs);
-    fill_kmajor(q_hi, q_lo, qb, p.q_rs, kAttQ, m0, p.Lq, 0, kAttD, p.q_vec, pt);
+    fill_kmajor<NT>(q_hi, q_lo, qb, p.q_rs, kAttQ, m0, p.Lq, 0, kAttD, p.q_vec, pt);
     ptx::fence_proxy_async();
     __syncwarp();
     if (lane == 0) ptx::mbar_arrive(q_full);
     for (int j = 0; j < nk; ++j) {
       const int st = j & 1;
       const uint32_t ph = (uint32_t)(j >> 1) & 1u;
-      ptx::mbar_wait(&kv_empty[st], ph ^ 1u, 550 + st);
+      ptx::mbar_wait(&k_empty[st], ph ^ 1u, 550 + st);
       uint8_t* sb = smem + kAttOffStage + (size_t)st * kAttStage;
-      fill_kmajor(sb, sb + kAttKBytes, kb_, p.k_rs, kAttKeys, j * kAttKeys, p.Lk, 0, kAttD, p.k_vec, pt);
-      uint8_t* vh = sb + 2 * kAttKBytes;
+      fill_kmajor<NT>(sb, sb + kAttKBytes, kb_, p.k_rs, kAttKeys, j * kAttKeys, p.Lk, 0, kAttD, p.k_vec, pt);
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&k_full[st]);
+    }
+  } else if (warp <= kAttProdWarps) {
+    // ===== V producers (warps 5..8): V^T_j (64 x 128 keys as two 64-key blocks) into the V half of stage j % 2 once R_{j-2} has consumed it =====
+    constexpr int NT = 32 * (kAttProdWarps / 2);
+    const int pt = threadIdx.x - 32 - NT;
+    const float* vb = p.vt + (int64_t)b * p.vt_bs + (p.v_kn ? (int64_t)h * kAttD : (int64_t)h * kAttD * p.vt_rs);
+    for (int j = 0; j < nk; ++j) {
+      const int st = j & 1;
+      const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+      ptx::mbar_wait(&v_empty[st], ph ^ 1u, 555 + st);
+      uint8_t* vh = smem + kAttOffStage + (size_t)st * kAttStage + 2 * kAttKBytes;
       uint8_t* vl = vh + 2 * kAttVBlk;
 #pragma unroll
       for (int kb = 0; kb < 2; ++kb) {
-        if (p.v_kn) fill_nmajor(vh + kb * kAttVBlk, vl + kb * kAttVBlk, vb, p.vt_rs, kAttD, 0, kAttD, j * kAttKeys + kb * 64, p.Lk, pt);
-        else fill_kmajor(vh + kb * kAttVBlk, vl + kb * kAttVBlk, vb, p.vt_rs, kAttD, 0, kAttD, j * kAttKeys + kb * 64, p.Lk, p.v_vec, pt);
+        if (p.v_kn) fill_nmajor<NT>(vh + kb * kAttVBlk, vl + kb * kAttVBlk, vb, p.vt_rs, kAttD, 0, kAttD, j * kAttKeys + kb * 64, p.Lk, pt);
+        else fill_kmajor<NT>(vh + kb * kAttVBlk, vl + kb * kAttVBlk, vb, p.vt_rs, kAttD, 0, kAttD, j * kAttKeys + kb * 64, p.Lk, p.v_vec, pt);
       }
       ptx::fence_proxy_async();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&kv_full[st]);
+      if (lane == 0) ptx::mbar_arrive(&v_full[st]);
     }
   } else {
     // ===== softmax: thread = query row (TMEM lane quadrant = warp % 4) =====
