@@ -44,7 +44,9 @@ struct GenGeom {
   static constexpr int COLS_PAD = ((COLS + 3) / 4) * 4 + 4;
   static constexpr int TAPS = KH * KW;
   static constexpr int XV = 3 * SW + (KW - 1) * DW + 1;
-  static constexpr int SMEM_FLOATS = GCI * ROWS * COLS_PAD + GCI * TAPS * GTCO;
+  static constexpr int OPERAND_FLOATS = GCI * ROWS * COLS_PAD + GCI * TAPS * GTCO;
+  static constexpr int STAGE_FLOATS = GTH * GTCO * (GTW + 1);  // output staging of the W-transposed mode
+  static constexpr int SMEM_FLOATS = OPERAND_FLOATS > STAGE_FLOATS ? OPERAND_FLOATS : STAGE_FLOATS;
 };
 
 template <int KH, int KW, int SH, int SW, int DW>
@@ -86,6 +88,7 @@ __global__ void __launch_bounds__(GNT) conv_gen_kernel(ConvGenParams p) {
     __syncthreads();
 #pragma unroll 2
     for (int ci = 0; ci < GCI; ++ci) {
+      if (ci0 + ci >= p.Cin) break;  // the 2-channel waveform convolution of the first time encoder: no arithmetic on the zero-filled channels
 #pragma unroll
       for (int kh = 0; kh < KH; ++kh) {
         const float* row = &in_s[(ci * G::ROWS + ty * SH + kh) * G::COLS_PAD + 4 * SW * tx];
@@ -105,6 +108,35 @@ __global__ void __launch_bounds__(GNT) conv_gen_kernel(ConvGenParams p) {
       }
     }
     __syncthreads();
+  }
+  if (p.up_axis == 2) {
+    // Transposed convolution along W: thread (wq, column r * CoutReal + c) owns output sample wq * up + r - trim, i.e. a warp's stores would be `up` floats
+    // apart.  Stage the tile in shared memory and write whole rows: for every real channel the block holds the 128 * up CONSECUTIVE samples of each row.
+    float* out_s = gsm;  // [GTH][GTCO][GTW + 1]   (the main loop ended with a barrier: the operand tiles are dead)
+#pragma unroll
+    for (int j = 0; j < 12; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) out_s[(ty * GTCO + tc * 12 + j) * (GTW + 1) + 4 * tx + i] = acc[i][j];
+    __syncthreads();
+    const int span = GTW * p.up;
+    for (int idx = tid; idx < GTH * p.CoutReal * span; idx += GNT) {
+      const int wl = idx % span;
+      const int c_real = (idx / span) % p.CoutReal;
+      const int hy = idx / (span * p.CoutReal);
+      const int wq_l = wl / p.up, r_up = wl - wq_l * p.up;
+      const int col = r_up * p.CoutReal + c_real - co0;
+      const int h = h0 + hy, wq = w0 + wq_l;
+      if (col < 0 || col >= GTCO || co0 + col >= p.Cout || h >= p.Ho || wq >= p.Wo) continue;
+      const int wo = wq * p.up + r_up - p.trim;
+      if (wo < 0 || wo >= p.out_len) continue;
+      const int64_t o = (((int64_t)b * p.CoutReal + c_real) * p.Ho + h) * p.out_len + wo;
+      float v = out_s[(hy * GTCO + col) * (GTW + 1) + wq_l] + (p.bias ? __ldg(&p.bias[c_real]) : 0.f);
+      if (p.add && p.add_before_act) v += __ldg(&p.add[o]);
+      v = gen_act(v, p.act);
+      if (p.add && !p.add_before_act) v += __ldg(&p.add[o]);
+      p.y[o] = v;
+    }
+    return;
   }
   const int h = h0 + ty;
   if (h >= p.Ho) return;
@@ -175,10 +207,11 @@ __global__ void conv_direct_kernel(ConvGenParams p, int KH, int KW, int SH, int 
 template <int KH, int KW, int SH, int SW, int DW>
 static int launch_gen(const ConvGenParams& p, cudaStream_t st) {
   using G = GenGeom<KH, KW, SH, SW, DW>;
-  const int smem = G::SMEM_FLOATS * (int)sizeof(float);
+  // the W-transposed mode stages its output tile in shared memory; everything else only needs the operand tiles (keeps the occupancy of the small geometries)
+  const int smem = (p.up_axis == 2 ? G::SMEM_FLOATS : G::OPERAND_FLOATS) * (int)sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    B2_CUDA(cudaFuncSetAttribute(conv_gen_kernel<KH, KW, SH, SW, DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    B2_CUDA(cudaFuncSetAttribute(conv_gen_kernel<KH, KW, SH, SW, DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_FLOATS * (int)sizeof(float)));
     attr_set = true;
   }
   dim3 grid(cdiv(p.Wo, GTW), cdiv(p.Ho, GTH), p.B * (p.CoutPad / GTCO));
