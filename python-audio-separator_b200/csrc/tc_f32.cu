@@ -542,17 +542,14 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 // tcgen05 with fp32 accumulation in TMEM -- the score matrix never reaches HBM (the unfused form wrote, re-read, normalised and re-read
 // B*H*Lq*Lk floats: 0.9 GB per HTDemucs frequency layer at batch 4).
 //
-//   one CTA per (128-query tile, batch*head);  key tiles of 128;  TWO sweeps over the keys:
-//     sweep 1:  S_j = Q K_j^T only -> the softmax warps take the row maxima (one TMEM round trip and 128 max operations per tile)
-//     sweep 2:  S_j again, P_j = 2^(a2 S_j - m_row) with the FINAL row maximum, O += P_j V_j accumulated by the tensor core in TMEM
-//   Recomputing Q K^T (tensor-core time, which this kernel has to spare) removes everything that made the one-sweep form latency-bound on its four
-//   softmax warps: no running maximum, no rescaling of the output accumulators, no accumulators in registers (so a tile's scores are fetched with two
-//   TMEM round trips instead of ten) -- measured 9 k cycles per tile before.
-//   warp 0       : MMA issuer: polls two instruction streams (score tiles, P V tiles) and issues whichever has its operands
-//   warps 1..4   : K producers: Q once, then K_j (keys x 64) fp32 -> bf16 hi/lo -> SWIZZLE_128B shared memory, twice over the keys (2 slots, freed when S completes)
-//   warps 5..8   : V producers: V^T_j (64 x keys) during sweep 2 (2 slots, freed when P_j V_j completes)
-//   warps 9..12  : softmax, one thread per query row (TMEM lane = row): maxima in sweep 1; in sweep 2 exponentials (one FFMA + one MUFU.EX2 per score), row
-//                  sums, P_j split into bf16 hi/lo and written as the K-major A operand of the second product
+//   one CTA per (128-query tile, batch*head);  key tiles of 128:
+//   warp 0       : MMA issuer: S_j = Q K_j^T (128 x 128, K = 64) into one of two TMEM score buffers, then R_{j-1} = P_{j-1} V_{j-1}
+//                  (128 x 64, K = 128) into one of two TMEM output-tile buffers -- S_{j+1} is in flight while the softmax of tile j runs
+//   warps 1..4   : K producers: Q once, then K_j (keys x 64) fp32 -> bf16 hi/lo -> SWIZZLE_128B shared memory (2 slots, freed when S_j completes)
+//   warps 5..8   : V producers: V^T_j (64 x keys), 2 slots freed when R_j completes
+//   warps 9..12  : softmax, one thread per query row: row maximum, exp, running sum, P_j split into bf16 hi/lo and written as the A operand
+//                  of the second product; the 64 output accumulators of the row live in registers and are rescaled when the maximum moves
+//                  (R_j is folded in one tile late, so the fold never waits for the tensor core)
 constexpr int kAttProdWarps = 8, kAttSoftWarps = 4;
 constexpr int kAttThreads = 32 * (1 + kAttProdWarps + kAttSoftWarps);  // 416
 constexpr int kAttQ = 128, kAttKeys = 128, kAttD = 64;
@@ -560,7 +557,7 @@ constexpr uint32_t kAttQBytes = kAttQ * 128;            // one plane of Q: 128 r
 constexpr uint32_t kAttPBlk = kAttQ * 128;              // one plane of one 64-key block of P
 constexpr uint32_t kAttKBytes = kAttKeys * 128;         // one plane of K_j
 constexpr uint32_t kAttVBlk = kAttD * 128;              // one plane of one 64-key block of V^T_j
-constexpr uint32_t kAttStage = 2 * kAttKBytes + 4 * kAttVBlk;  // 64 KB: K slot + V slot
+constexpr uint32_t kAttStage = 2 * kAttKBytes + 4 * kAttVBlk;  // 64 KB
 constexpr uint32_t kAttOffP = 2 * kAttQBytes, kAttOffStage = kAttOffP + 4 * kAttPBlk;
 constexpr uint32_t kAttSmem = kAttOffStage + 2 * kAttStage;  // 224 KB
 
@@ -587,16 +584,17 @@ __global__ void __launch_bounds__(kAttThreads, 1) tc_attention_kernel(const AttP
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kAttSmem);
   uint64_t* q_full = bars;            // [1]
-  uint64_t* k_full = bars + 1;        // [2]  K tile converted          (K producer warps -> MMA)
-  uint64_t* k_empty = bars + 3;       // [2]  score tile done: K slot free
+  uint64_t* k_full = bars + 1;        // [2]  K_j converted            (K producer warps -> MMA)
+  uint64_t* k_empty = bars + 3;       // [2]  S_j done: K slot free     (MMA commit -> K producers)
   uint64_t* v_full = bars + 5;        // [2]
-  uint64_t* v_empty = bars + 7;       // [2]  P_j V_j done: V slot free
+  uint64_t* v_empty = bars + 7;       // [2]  R_j done: V slot free
   uint64_t* s_full = bars + 9;        // [2]
   uint64_t* s_empty = bars + 11;      // [2]
   uint64_t* p_full = bars + 13;       // [1]
   uint64_t* p_empty = bars + 14;      // [1]
-  uint64_t* o_full = bars + 15;       // [1]  the last P V product has completed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* o_full = bars + 15;       // [2]
+  uint64_t* o_empty = bars + 17;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -608,22 +606,22 @@ __global__ void __launch_bounds__(kAttThreads, 1) tc_attention_kernel(const AttP
       ptx::mbar_init(&v_empty[a], 1);
       ptx::mbar_init(&s_full[a], 1);
       ptx::mbar_init(&s_empty[a], kAttSoftWarps);
+      ptx::mbar_init(&o_full[a], 1);
+      ptx::mbar_init(&o_empty[a], kAttSoftWarps);
     }
     ptx::mbar_init(p_full, kAttSoftWarps);
     ptx::mbar_init(p_empty, 1);
-    ptx::mbar_init(o_full, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 0) ptx::tmem_alloc(tmem_slot, 512);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;  // columns [0, 256): two score buffers; [256, 320): the output accumulator
+  const uint32_t tmem_base = *tmem_slot;  // columns [0, 256): two score buffers; [256, 384): two output-tile buffers
 
   const int z = blockIdx.y, b = z / p.H, h = z - b * p.H;
   const int m0 = blockIdx.x * kAttQ;
   const int nk = (p.Lk + kAttKeys - 1) / kAttKeys;
-  const int nt = 2 * nk;  // score tiles: t < nk sweep 1, t >= nk sweep 2 (key tile t % nk)
   uint8_t* q_hi = smem;
   uint8_t* q_lo = smem + kAttQBytes;
   uint8_t* p_hi = smem + kAttOffP;                 // [2 key blocks][128 rows x 128 B]
@@ -635,13 +633,15 @@ __global__ void __launch_bounds__(kAttThreads, 1) tc_attention_kernel(const AttP
       const uint32_t idesc_s = ptx::instr_desc_bf16(kAttQ, kAttKeys, 0, 0), idesc_o = ptx::instr_desc_bf16(kAttQ, kAttD, 0, 0);
       const uint32_t qh = ptx::smem_u32(q_hi), ql = ptx::smem_u32(q_lo), ph_ = ptx::smem_u32(p_hi), pl_ = ptx::smem_u32(p_lo);
       ptx::mbar_wait(q_full, 0, 500);
-      int ts = 0, jo = 0;  // next score tile, next P V tile
+      // Two instruction streams, issued in whatever order their inputs arrive: S_js = Q K_js^T needs K_js and a free score buffer, R_jo = P_jo V_jo needs
+      // P_jo, V_jo and a free output-tile buffer.  (A fixed S, R, S, R order made R_{j-1} wait for the K_j conversion and serialised the pipeline.)
+      int js = 0, jo = 0;
       uint32_t idle = 0;
       while (jo < nk) {
         bool did = false;
-        if (ts < nt) {
-          const int st = ts & 1;
-          const uint32_t ph = (uint32_t)(ts >> 1) & 1u;
+        if (js < nk) {
+          const int st = js & 1;
+          const uint32_t ph = (uint32_t)(js >> 1) & 1u;
           if (ptx::mbar_try_wait(&k_full[st], ph) && ptx::mbar_try_wait(&s_empty[st], ph ^ 1u)) {
             ptx::tc_fence_after();
             const uint32_t d = tmem_base + (uint32_t)st * kAttKeys;
@@ -656,16 +656,16 @@ __global__ void __launch_bounds__(kAttThreads, 1) tc_attention_kernel(const AttP
             }
             ptx::umma_commit(&s_full[st]);
             ptx::umma_commit(&k_empty[st]);
-            ++ts;
+            ++js;
             did = true;
           }
         }
-        if (nk + jo < ts) {  // the scores of sweep-2 tile jo have been issued: P_jo will come
+        if (jo < js) {
           const int st = jo & 1;
           const uint32_t ph = (uint32_t)(jo >> 1) & 1u;
-          if (ptx::mbar_try_wait(p_full, (uint32_t)jo & 1u) && ptx::mbar_try_wait(&v_full[st], ph)) {
+          if (ptx::mbar_try_wait(p_full, (uint32_t)jo & 1u) && ptx::mbar_try_wait(&v_full[st], ph) && ptx::mbar_try_wait(&o_empty[st], ph ^ 1u)) {
             ptx::tc_fence_after();
-            const uint32_t d = tmem_base + 2 * kAttKeys;
+            const uint32_t d = tmem_base + 2 * kAttKeys + (uint32_t)st * kAttD;
             const uint32_t vh = ptx::smem_u32(smem + kAttOffStage + (size_t)st * kAttStage) + 2 * kAttKBytes, vl = vh + 2 * kAttVBlk;
 #pragma unroll
             for (int kb = 0; kb < 2; ++kb) {
@@ -675,14 +675,14 @@ __global__ void __launch_bounds__(kAttThreads, 1) tc_attention_kernel(const AttP
                 const uint64_t dpl = ptx::smem_desc(pl_ + kb * kAttPBlk + jj * 32, 16, 1024, ptx::kLayoutSW128);
                 const uint64_t dvh = ptx::smem_desc(vh + kb * kAttVBlk + jj * 32, 16, 1024, ptx::kLayoutSW128);
                 const uint64_t dvl = ptx::smem_desc(vl + kb * kAttVBlk + jj * 32, 16, 1024, ptx::kLayoutSW128);
-                ptx::umma_bf16(d, dph, dvh, idesc_o, (jo | kb | jj) != 0 ? 1u : 0u);
+                ptx::umma_bf16(d, dph, dvh, idesc_o, (kb | jj) != 0 ? 1u : 0u);
                 ptx::umma_bf16(d, dph, dvl, idesc_o, 1u);
                 ptx::umma_bf16(d, dpl, dvh, idesc_o, 1u);
               }
             }
+            ptx::umma_commit(&o_full[st]);
             ptx::umma_commit(&v_empty[st]);
             ptx::umma_commit(p_empty);
-            if (jo == nk - 1) ptx::umma_commit(o_full);
             ++jo;
             did = true;
           }
@@ -690,13 +690,13 @@ __global__ void __launch_bounds__(kAttThreads, 1) tc_attention_kernel(const AttP
         if (did) {
           idle = 0;
         } else if (++idle > (1u << 24)) {
-          printf("b200sep: attention MMA issuer stalled block=(%d,%d) ts=%d jo=%d\n", blockIdx.x, blockIdx.y, ts, jo);
+          printf("b200sep: attention MMA issuer stalled block=(%d,%d) js=%d jo=%d\n", blockIdx.x, blockIdx.y, js, jo);
           __trap();
         }
       }
     }
   } else if (warp <= kAttProdWarps / 2) {
-    // ===== K producers (warps 1..4): Q once, then the key tiles twice =====
+    // ===== K producers (warps 1..4): Q once, then K_j into the K half of stage j % 2 as soon as S_{j-2} has consumed it =====
     constexpr int NT = 32 * (kAttProdWarps / 2);
     const int pt = threadIdx.x - 32;
     const float* qb = p.q + (int64_t)b * p.q_bs + (int64_t)h * kAttD;
@@ -705,9 +705,9 @@ __global__ void __launch_bounds__(kAttThreads, 1) tc_attention_kernel(const AttP
     ptx::fence_proxy_async();
     __syncwarp();
     if (lane == 0) ptx::mbar_arrive(q_full);
-    for (int t = 0; t < nt; ++t) {
-      const int st = t & 1, j = t >= nk ? t - nk : t;
-      const uint32_t ph = (uint32_t)(t >> 1) & 1u;
+    for (int j = 0; j < nk; ++j) {
+      const int st = j & 1;
+      const uint32_t ph = (uint32_t)(j >> 1) & 1u;
       ptx::mbar_wait(&k_empty[st], ph ^ 1u, 550 + st);
       uint8_t* sb = smem + kAttOffStage + (size_t)st * kAttStage;
       fill_kmajor<NT>(sb, sb + kAttKBytes, kb_, p.k_rs, kAttKeys, j * kAttKeys, p.Lk, 0, kAttD, p.k_vec, pt);
@@ -716,7 +716,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) tc_attention_kernel(const AttP
       if (lane == 0) ptx::mbar_arrive(&k_full[st]);
     }
   } else if (warp <= kAttProdWarps) {
-    // ===== V producers (warps 5..8): V^T_j (64 x 128 keys as two 64-key blocks) into the V slot j % 2 once P_{j-2} V_{j-2} has consumed it =====
+    // ===== V producers (warps 5..8): V^T_j (64 x 128 keys as two 64-key blocks) into the V half of stage j % 2 once R_{j-2} has consumed it =====
     constexpr int NT = 32 * (kAttProdWarps / 2);
     const int pt = threadIdx.x - 32 - NT;
     const float* vb = p.vt + (int64_t)b * p.vt_bs + (p.v_kn ? (int64_t)h * kAttD : (int64_t)h * kAttD * p.vt_rs);
@@ -741,94 +741,99 @@ __global__ void __launch_bounds__(kAttThreads, 1) tc_attention_kernel(const AttP
     const int row = qd * 32 + lane;
     const int m = m0 + row;
     const uint32_t tlane = tmem_base + ((uint32_t)(qd * 32) << 16);
-    // base-2 domain: p = 2^(s * a2 - m2) with a2 = alpha * log2(e): one FFMA + one MUFU.EX2 per score
+    // base-2 domain: p = 2^(s * a2 - m2) with a2 = alpha * log2(e): one FFMA + one MUFU.EX2 per score (expf() costs ~10 instructions, and this warp is
+    // the only softmax warp of its scheduler: its instruction count is the kernel's critical path)
     const float a2 = p.alpha * 1.4426950408889634f;
-    // ---- sweep 1: row maxima
-    float mx = -INFINITY;
-    for (int t = 0; t < nk; ++t) {
-      const int st = t & 1;
-      const uint32_t ph = (uint32_t)(t >> 1) & 1u;
-      ptx::mbar_wait(&s_full[st], ph, 560 + st);
-      ptx::tc_fence_after();
-      const uint32_t ts = tlane + (uint32_t)st * kAttKeys;
-      const int nvalid = min(kAttKeys, p.Lk - t * kAttKeys);
+    float mrun = -INFINITY, l = 0.f, corr_prev = 1.f;
+    float O[kAttD];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[64];
-        ptx::tmem_ld32(ts + c * 64, v);
-        ptx::tmem_ld32(ts + c * 64 + 32, v + 32);
-        ptx::tmem_ld_wait();
-        if (nvalid == kAttKeys) {  // warp-uniform
+    for (int e = 0; e < kAttD; ++e) O[e] = 0.f;
+    for (int j = 0; j <= nk; ++j) {
+      float corr = 1.f;
+      if (j < nk) {
+        const int st = j & 1;
+        const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+        ptx::mbar_wait(&s_full[st], ph, 560 + st);
+        ptx::tc_fence_after();
+        const uint32_t ts = tlane + (uint32_t)st * kAttKeys;
+        const int nvalid = min(kAttKeys, p.Lk - j * kAttKeys);
+        const bool full = nvalid == kAttKeys;  // warp-uniform
+        float mx = -INFINITY;
 #pragma unroll
-          for (int e = 0; e < 64; e += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[e]), __uint_as_float(v[e + 1])));
-        } else {
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          ptx::tmem_ld32(ts + c * 32, v);
+          ptx::tmem_ld_wait();
+          if (full) {
 #pragma unroll
-          for (int e = 0; e < 64; ++e)
-            if (c * 64 + e < nvalid) mx = fmaxf(mx, __uint_as_float(v[e]));
-        }
-      }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&s_empty[st]);
-    }
-    const float m2 = mx * a2;  // alpha > 0: the maximum of the scaled scores
-    // ---- sweep 2: P_j = 2^(a2 S_j - m2), row sums; the tensor core accumulates P_j V_j
-    float l = 0.f;
-    for (int j = 0; j < nk; ++j) {
-      const int t = nk + j, st = t & 1;
-      const uint32_t ph = (uint32_t)(t >> 1) & 1u;
-      ptx::mbar_wait(&s_full[st], ph, 570 + st);
-      ptx::tc_fence_after();
-      const uint32_t ts = tlane + (uint32_t)st * kAttKeys;
-      const int nvalid = min(kAttKeys, p.Lk - j * kAttKeys);
-      const bool full = nvalid == kAttKeys;
-      ptx::mbar_wait(p_empty, ((uint32_t)j & 1u) ^ 1u, 580);  // P_{j-1} consumed by the tensor core
+            for (int e = 0; e < 32; e += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[e]), __uint_as_float(v[e + 1])));
+          } else {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[64];
-        ptx::tmem_ld32(ts + c * 64, v);
-        ptx::tmem_ld32(ts + c * 64 + 32, v + 32);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          float pv[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float x = ex2_approx(fmaf(__uint_as_float(v[ch * 8 + e]), a2, -m2));
-            pv[e] = (full || c * 64 + ch * 8 + e < nvalid) ? x : 0.f;
-            l += pv[e];
+            for (int e = 0; e < 32; ++e)
+              if (c * 32 + e < nvalid) mx = fmaxf(mx, __uint_as_float(v[e]));
           }
-          store_chunk(p_hi + c * kAttPBlk, p_lo + c * kAttPBlk, row, ch, pv);  // key block c, 16-byte chunk ch
+        }
+        const float mnew = fmaxf(mrun, mx * a2);
+        corr = ex2_approx(mrun - mnew);  // first tile: 2^(-inf) = 0
+        mrun = mnew;
+        ptx::mbar_wait(p_empty, ((uint32_t)j & 1u) ^ 1u, 570);  // P_{j-1} consumed by the tensor core
+        float lsum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          ptx::tmem_ld32(ts + c * 32, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            float pv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float x = ex2_approx(fmaf(__uint_as_float(v[ch * 8 + e]), a2, -mnew));
+              pv[e] = (full || c * 32 + ch * 8 + e < nvalid) ? x : 0.f;
+              lsum += pv[e];
+            }
+            const int chunk = c * 4 + ch;  // 16 chunks of 8 keys; chunks 0..7 = key block 0
+            store_chunk(p_hi + (chunk >> 3) * kAttPBlk, p_lo + (chunk >> 3) * kAttPBlk, row, chunk & 7, pv);
+          }
+        }
+        l = l * corr + lsum;
+        ptx::tc_fence_before();
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::mbar_arrive(&s_empty[st]);
+          ptx::mbar_arrive(p_full);
         }
       }
-      ptx::tc_fence_before();
-      ptx::fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) {
-        ptx::mbar_arrive(&s_empty[st]);
-        ptx::mbar_arrive(p_full);
+      if (j > 0) {  // fold R_{j-1} (relative to the maximum after tile j-1) into the accumulators (relative to the maximum after tile j-2)
+        const int jp = j - 1, st = jp & 1;
+        const uint32_t ph = (uint32_t)(jp >> 1) & 1u;
+        ptx::mbar_wait(&o_full[st], ph, 580 + st);
+        ptx::tc_fence_after();
+        const uint32_t to = tlane + 2 * kAttKeys + (uint32_t)st * kAttD;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          ptx::tmem_ld32(to + c * 32, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) O[c * 32 + e] = fmaf(O[c * 32 + e], corr_prev, __uint_as_float(v[e]));
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&o_empty[st]);
       }
+      corr_prev = corr;
     }
-    // ---- epilogue: O / l
-    ptx::mbar_wait(o_full, 0, 590);
-    ptx::tc_fence_after();
-    const float inv = 1.f / l;
-    float* o = p.out + (int64_t)b * p.o_bs + (int64_t)m * p.o_rs + (int64_t)h * kAttD;
+    if (m < p.Lq) {
+      const float inv = 1.f / l;
+      float* o = p.out + (int64_t)b * p.o_bs + (int64_t)m * p.o_rs + (int64_t)h * kAttD;
+      if (p.o_vec) {
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
-      ptx::tmem_ld32(tlane + 2 * kAttKeys + c * 32, v);
-      ptx::tmem_ld_wait();
-      if (m < p.Lq) {
-        if (p.o_vec) {
+        for (int e = 0; e < kAttD; e += 4) *reinterpret_cast<float4*>(o + e) = make_float4(O[e] * inv, O[e + 1] * inv, O[e + 2] * inv, O[e + 3] * inv);
+      } else {
 #pragma unroll
-          for (int e = 0; e < 32; e += 4)
-            *reinterpret_cast<float4*>(o + c * 32 + e) = make_float4(__uint_as_float(v[e]) * inv, __uint_as_float(v[e + 1]) * inv, __uint_as_float(v[e + 2]) * inv,
-                                                                      __uint_as_float(v[e + 3]) * inv);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) o[c * 32 + e] = __uint_as_float(v[e]) * inv;
-        }
+        for (int e = 0; e < kAttD; ++e) o[e] = O[e] * inv;
       }
     }
   }
