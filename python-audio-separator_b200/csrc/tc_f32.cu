@@ -689,7 +689,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) tc_attention_kernel(const AttP
         }
         if (did) {
           idle = 0;
-        } else if (++idle > (1u << 24)) {
+        } else if (__nanosleep(40), ++idle > (1u << 22)) {
           printf("b200sep: attention MMA issuer stalled block=(%d,%d) js=%d jo=%d\n", blockIdx.x, blockIdx.y, js, jo);
           __trap();
         }
@@ -708,7 +708,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) tc_attention_kernel(const AttP
     for (int j = 0; j < nk; ++j) {
       const int st = j & 1;
       const uint32_t ph = (uint32_t)(j >> 1) & 1u;
-      ptx::mbar_wait(&k_empty[st], ph ^ 1u, 550 + st);
+      ptx::mbar_wait_backoff(&k_empty[st], ph ^ 1u, 200, 550 + st);
       uint8_t* sb = smem + kAttOffStage + (size_t)st * kAttStage;
       fill_kmajor<NT>(sb, sb + kAttKBytes, kb_, p.k_rs, kAttKeys, j * kAttKeys, p.Lk, 0, kAttD, p.k_vec, pt);
       ptx::fence_proxy_async();
@@ -723,7 +723,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) tc_attention_kernel(const AttP
     for (int j = 0; j < nk; ++j) {
       const int st = j & 1;
       const uint32_t ph = (uint32_t)(j >> 1) & 1u;
-      ptx::mbar_wait(&v_empty[st], ph ^ 1u, 555 + st);
+      ptx::mbar_wait_backoff(&v_empty[st], ph ^ 1u, 200, 555 + st);
       uint8_t* vh = smem + kAttOffStage + (size_t)st * kAttStage + 2 * kAttKBytes;
       uint8_t* vl = vh + 2 * kAttVBlk;
 #pragma unroll
@@ -753,13 +753,13 @@ __global__ void __launch_bounds__(kAttThreads, 1) tc_attention_kernel(const AttP
       if (j < nk) {
         const int st = j & 1;
         const uint32_t ph = (uint32_t)(j >> 1) & 1u;
-        ptx::mbar_wait(&s_full[st], ph, 560 + st);
+        ptx::mbar_wait_backoff(&s_full[st], ph, 20, 560 + st);
         ptx::tc_fence_after();
         const uint32_t ts = tlane + (uint32_t)st * kAttKeys;
         const int nvalid = min(kAttKeys, p.Lk - j * kAttKeys);
         const bool full = nvalid == kAttKeys;  // warp-uniform
         float mx = -INFINITY;
-#pragma unroll
+#pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t v[32];
           ptx::tmem_ld32(ts + c * 32, v);
@@ -776,9 +776,9 @@ __global__ void __launch_bounds__(kAttThreads, 1) tc_attention_kernel(const AttP
         const float mnew = fmaxf(mrun, mx * a2);
         corr = ex2_approx(mrun - mnew);  // first tile: 2^(-inf) = 0
         mrun = mnew;
-        ptx::mbar_wait(p_empty, ((uint32_t)j & 1u) ^ 1u, 570);  // P_{j-1} consumed by the tensor core
+        ptx::mbar_wait_backoff(p_empty, ((uint32_t)j & 1u) ^ 1u, 20, 570);  // P_{j-1} consumed by the tensor core
         float lsum = 0.f;
-#pragma unroll
+#pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t v[32];
           ptx::tmem_ld32(ts + c * 32, v);
@@ -808,7 +808,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) tc_attention_kernel(const AttP
       if (j > 0) {  // fold R_{j-1} (relative to the maximum after tile j-1) into the accumulators (relative to the maximum after tile j-2)
         const int jp = j - 1, st = jp & 1;
         const uint32_t ph = (uint32_t)(jp >> 1) & 1u;
-        ptx::mbar_wait(&o_full[st], ph, 580 + st);
+        ptx::mbar_wait_backoff(&o_full[st], ph, 20, 580 + st);
         ptx::tc_fence_after();
         const uint32_t to = tlane + 2 * kAttKeys + (uint32_t)st * kAttD;
 #pragma unroll
