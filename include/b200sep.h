@@ -271,7 +271,11 @@ int b200sep_tc_pack_conv_weights(const float* w_blocked, int Cin, int taps, int 
  * Replaces gemm_f32 (scores) + softmax_rows_f32 + gemm_f32 (P V) of nn.MultiheadAttention (transformer.py:196-409). */
 int b200sep_attention_f32(const float* q, const float* k, const float* vt, float* out, int B, int H, int Lq, int Lk, int head_dim, int64_t q_batch_stride,
                           int64_t q_row_stride, int64_t k_batch_stride, int64_t k_row_stride, int64_t vt_batch_stride, int64_t vt_row_stride,
-                          int64_t out_batch_stride, int64_t out_row_stride, float alpha, int v_is_kn, void* stream);
+                          int64_t out_batch_stride, int64_t out_row_stride, float alpha, int v_is_kn, float* work, void* stream);
+/* work (nullable): b200sep_attention_work_floats(...) floats of 16-byte aligned device scratch.  With it Q / K / V are split into bf16 hi / lo tile images ONCE
+ * (a small pre-pass) and the attention kernel fetches them with bulk copies; without it every CTA converts the tiles it reads (slower: each K / V tile is read
+ * by all query tiles of its (batch, head)). */
+int64_t b200sep_attention_work_floats(int B, int H, int Lq, int Lk);
 /* in-place softmax over the first n columns of each row (row stride ld >= n; padding columns are left untouched) */
 int b200sep_softmax_rows_f32(float* x, int64_t rows, int n, int64_t ld, void* stream);
 /* batched C[z] = alpha * A[z] (M,K; lda) @ B[z] (K,N; ldb): the P @ V product of attention without a transposed copy of V */

@@ -82,7 +82,8 @@ _SIGS = {
     "b200sep_layernorm_f32": (i32, [vp, vp, vp, vp, i64, i32, vp]),
     "b200sep_gemm_f32": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i64, i64, i64, f32, vp, vp, i32, vp, vp, vp, vp]),
     "b200sep_softmax_rows_f32": (i32, [vp, i64, i32, i64, vp]),
-    "b200sep_attention_f32": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, f32, i32, vp]),
+    "b200sep_attention_f32": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, f32, i32, vp, vp]),
+    "b200sep_attention_work_floats": (i64, [i32, i32, i32, i32]),
     "b200sep_ew_f32": (i32, [vp, vp, vp, i64, f32, f32, i32, vp]),
     "b200sep_meanstd_f32": (i32, [vp, i64, vp, vp]),
     "b200sep_meanstd_work_floats": (i64, [i32]),

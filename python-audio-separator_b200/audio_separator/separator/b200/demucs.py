@@ -364,8 +364,9 @@ class HTDemucsNet:
         _gemm_raw(_ptr(wv), _ptr(kv_in), _ptr(vt), D, Lk, D, D, D, Lk, B, 0, Lk * D, D * Lk, bias_m=_ptr(bv))
         o = _new((B, Lq, D), q_in)
         if hd == 64 and _FUSED_ATTENTION:  # one kernel, the (H, Lq, Lk) scores stay on chip
+            work = _new((lib.b200sep_attention_work_floats(B, H, Lq, Lk),), q_in)  # bf16 hi / lo tile images of Q, K, V^T (split once, not once per consumer)
             check(lib.b200sep_attention_f32(_ptr(q), _ptr(k), _ptr(vt), _ptr(o), B, H, Lq, Lk, hd, Lq * D, D, Lk * D, D, D * Lk, Lk, Lq * D, D, 1.0 / math.sqrt(hd),
-                                            0, _stream()), "attention_f32")
+                                            0, _ptr(work), _stream()), "attention_f32")
             y = linear(o.view(B * Lq, D), W[f"{p}.out_proj.weight"], W[f"{p}.out_proj.bias"], res=res.view(B * Lq, D), res_scale=res_scale)
             return y.view(B, Lq, D)
         sc = _new((H, Lq, Lk), q_in)

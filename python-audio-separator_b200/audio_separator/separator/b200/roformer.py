@@ -216,8 +216,9 @@ class BSRoformerNet:
             check(lib.b200sep_rope_split_heads_f32(_ptr(qkv), _ptr(W[f"{a}.rotary_embed.freqs"]), _ptr(q), _ptr(k), _ptr(v), Bq, n, H, dh, _stream()), "rope_split_heads_f32")
             o = _new((Bq, H, n, dh), x)
             if dh == 64 and _FUSED_ATTENTION:  # scores stay on chip (b200sep_attention_f32): every (batch, head) pair is one batch entry of the kernel, V untransposed
-                check(lib.b200sep_attention_f32(_ptr(q), _ptr(k), _ptr(v), _ptr(o), Bq * H, 1, n, n, dh, n * dh, dh, n * dh, dh, n * dh, dh, n * dh, dh, dh**-0.5, 1, _stream()),
-                      "attention_f32")
+                work = _new((lib.b200sep_attention_work_floats(Bq * H, 1, n, n),), x)
+                check(lib.b200sep_attention_f32(_ptr(q), _ptr(k), _ptr(v), _ptr(o), Bq * H, 1, n, n, dh, n * dh, dh, n * dh, dh, n * dh, dh, n * dh, dh, dh**-0.5, 1,
+                                                _ptr(work), _stream()), "attention_f32")
             else:
                 sc = _new((Bq * H, n, ldv), x)  # padding columns n..ldv-1 are never read: the P@V GEMM runs K = n over rows of stride ldv
                 check(lib.b200sep_gemm_f32(_ptr(q), _ptr(k), _ptr(sc), n, n, dh, dh, dh, ldv, Bq * H, n * dh, n * dh, n * ldv, dh**-0.5, None, None, 0, None, None, None,

@@ -571,6 +571,12 @@ struct AttParams {
   float alpha;
   int q_vec, k_vec, v_vec, o_vec;
   int v_kn;  // 1: V given untransposed, v[b * vt_bs + n * vt_rs + h * 64 + d] (the producers gather it d-major)
+  // PACKED variant: Q / K / V^T already split into bf16 hi / lo and laid out as the kernel's shared-memory tiles by att_pack_kernel, 32 KB per tile:
+  //   qimg[(z * mq_tiles + mt)] = [hi 128 x 128 B | lo],  kimg[(z * nk + j)] = [hi | lo],  vimg[(z * nk + j)] = [hi kb0 | hi kb1 | lo kb0 | lo kb1] (64 rows x 128 B each)
+  const uint8_t* qimg;
+  const uint8_t* kimg;
+  const uint8_t* vimg;
+  int mq_tiles;
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -579,7 +585,50 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(kAttThreads, 1) tc_attention_kernel(const AttParams p) {
+constexpr int kAttThreadsPacked = 32 * (2 + kAttSoftWarps);  // MMA issuer warp, loader warp, 4 softmax warps
+
+// one 16-byte chunk (8 values) of a tile image per thread; see AttParams for the image layouts
+__global__ void att_pack_kernel(const AttParams p, uint8_t* __restrict__ qimg, uint8_t* __restrict__ kimg, uint8_t* __restrict__ vimg, int nk, int64_t nq_chunks,
+                                int64_t nk_chunks) {
+  const int64_t total = nq_chunks + 2 * nk_chunks;
+  for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (int64_t)gridDim.x * blockDim.x) {
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (id < nq_chunks + nk_chunks) {  // Q or K: rows = tokens, 8 consecutive head-dimension values
+      const bool is_q = id < nq_chunks;
+      const int64_t cid = is_q ? id : id - nq_chunks;
+      const int c = (int)(cid & 7), r = (int)((cid >> 3) & 127);
+      const int64_t img = cid >> 10;
+      const int tiles = is_q ? p.mq_tiles : nk;
+      const int z = (int)(img / tiles), t = (int)(img - (int64_t)z * tiles);
+      const int b = z / p.H, h = z - b * p.H;
+      const int row = t * 128 + r;
+      if (row < (is_q ? p.Lq : p.Lk)) {
+        const float* src = is_q ? p.q + (int64_t)b * p.q_bs + (int64_t)row * p.q_rs : p.k + (int64_t)b * p.k_bs + (int64_t)row * p.k_rs;
+        src += h * kAttD + c * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = __ldg(src + e);
+      }
+      uint8_t* base = (is_q ? qimg : kimg) + img * 32768;
+      store_chunk(base, base + 16384, r, c, v);
+    } else {  // V^T: rows = head dimension, 8 consecutive keys
+      const int64_t cid = id - nq_chunks - nk_chunks;
+      const int c = (int)(cid & 7), r = (int)((cid >> 3) & 63), kb = (int)((cid >> 9) & 1);
+      const int64_t img = cid >> 10;
+      const int z = (int)(img / nk), j = (int)(img - (int64_t)z * nk);
+      const int b = z / p.H, h = z - b * p.H;
+      const int n0 = j * kAttKeys + kb * 64 + c * 8;
+      const float* vb = p.vt + (int64_t)b * p.vt_bs;
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (n0 + e < p.Lk) v[e] = p.v_kn ? __ldg(vb + (int64_t)(n0 + e) * p.vt_rs + h * kAttD + r) : __ldg(vb + (int64_t)(h * kAttD + r) * p.vt_rs + n0 + e);
+      uint8_t* base = vimg + img * 32768 + kb * kAttVBlk;
+      store_chunk(base, base + 2 * kAttVBlk, r, c, v);
+    }
+  }
+}
+
+template <bool PACKED>
+__global__ void __launch_bounds__(PACKED ? kAttThreadsPacked : kAttThreads, 1) tc_attention_kernel(const AttParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kAttSmem);
@@ -598,11 +647,12 @@ __global__ void __launch_bounds__(kAttThreads, 1) tc_attention_kernel(const AttP
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    ptx::mbar_init(q_full, kAttProdWarps / 2);
+    constexpr uint32_t kFillArrivals = PACKED ? 1 : kAttProdWarps / 2;  // PACKED: the loader thread's arrive.expect_tx (the bulk copy completes the bytes)
+    ptx::mbar_init(q_full, kFillArrivals);
     for (int a = 0; a < 2; ++a) {
-      ptx::mbar_init(&k_full[a], kAttProdWarps / 2);
+      ptx::mbar_init(&k_full[a], kFillArrivals);
       ptx::mbar_init(&k_empty[a], 1);
-      ptx::mbar_init(&v_full[a], kAttProdWarps / 2);
+      ptx::mbar_init(&v_full[a], kFillArrivals);
       ptx::mbar_init(&v_empty[a], 1);
       ptx::mbar_init(&s_full[a], 1);
       ptx::mbar_init(&s_empty[a], kAttSoftWarps);
@@ -695,7 +745,43 @@ __global__ void __launch_bounds__(kAttThreads, 1) tc_attention_kernel(const AttP
         }
       }
     }
-  } else if (warp <= kAttProdWarps / 2) {
+  } else if (PACKED && warp == 1) {
+    // ===== loader (PACKED): one thread, bulk copies of the pre-split 32 KB tile images; K and V streams polled independently =====
+    if (lane == 0) {
+      const int64_t zq = (int64_t)z * p.mq_tiles + blockIdx.x, zk = (int64_t)z * nk;
+      ptx::mbar_arrive_expect_tx(q_full, 32768);
+      ptx::bulk_load_1d(q_hi, p.qimg + zq * 32768, 32768, q_full);
+      int jk = 0, jv = 0;
+      uint32_t idle = 0;
+      while (jk < nk || jv < nk) {
+        bool did = false;
+        if (jk < nk) {
+          const int st = jk & 1;
+          if (ptx::mbar_try_wait(&k_empty[st], ((uint32_t)(jk >> 1) & 1u) ^ 1u)) {
+            ptx::mbar_arrive_expect_tx(&k_full[st], 32768);
+            ptx::bulk_load_1d(smem + kAttOffStage + (size_t)st * kAttStage, p.kimg + (zk + jk) * 32768, 32768, &k_full[st]);
+            ++jk;
+            did = true;
+          }
+        }
+        if (jv < nk) {
+          const int st = jv & 1;
+          if (ptx::mbar_try_wait(&v_empty[st], ((uint32_t)(jv >> 1) & 1u) ^ 1u)) {
+            ptx::mbar_arrive_expect_tx(&v_full[st], 32768);
+            ptx::bulk_load_1d(smem + kAttOffStage + (size_t)st * kAttStage + 2 * kAttKBytes, p.vimg + (zk + jv) * 32768, 32768, &v_full[st]);
+            ++jv;
+            did = true;
+          }
+        }
+        if (did) {
+          idle = 0;
+        } else if (__nanosleep(100), ++idle > (1u << 22)) {
+          printf("b200sep: attention loader stalled block=(%d,%d) jk=%d jv=%d\n", blockIdx.x, blockIdx.y, jk, jv);
+          __trap();
+        }
+      }
+    }
+  } else if (!PACKED && warp <= kAttProdWarps / 2) {
     // ===== K producers (warps 1..4): Q once, then K_j into the K half of stage j % 2 as soon as S_{j-2} has consumed it =====
     constexpr int NT = 32 * (kAttProdWarps / 2);
     const int pt = threadIdx.x - 32;
@@ -715,7 +801,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) tc_attention_kernel(const AttP
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&k_full[st]);
     }
-  } else if (warp <= kAttProdWarps) {
+  } else if (!PACKED && warp <= kAttProdWarps) {
     // ===== V producers (warps 5..8): V^T_j (64 x 128 keys as two 64-key blocks) into the V half of stage j % 2 once R_{j-2} has consumed it =====
     constexpr int NT = 32 * (kAttProdWarps / 2);
     const int pt = threadIdx.x - 32 - NT;
@@ -849,8 +935,13 @@ __global__ void __launch_bounds__(kAttThreads, 1) tc_attention_kernel(const AttP
 
 bool tc_attention_usable(int hd, int Lq, int Lk) { return tc_enabled() && hd == kAttD && Lq >= 1 && Lk >= 1; }
 
+// bytes of scratch for the pre-split Q / K / V^T tile images (one 32 KB image per 128-row tile and (batch, head))
+int64_t tc_attention_work_bytes(int B, int H, int Lq, int Lk) {
+  return (int64_t)B * H * ((int64_t)cdiv(Lq, kAttQ) + 2 * (int64_t)cdiv(Lk, kAttKeys)) * 32768;
+}
+
 int tc_attention_f32(const float* q, const float* k, const float* vt, float* out, int B, int H, int Lq, int Lk, int64_t q_bs, int64_t q_rs, int64_t k_bs, int64_t k_rs,
-                     int64_t vt_bs, int64_t vt_rs, int64_t o_bs, int64_t o_rs, float alpha, int v_kn, cudaStream_t st) {
+                     int64_t vt_bs, int64_t vt_rs, int64_t o_bs, int64_t o_rs, float alpha, int v_kn, void* work, cudaStream_t st) {
   AttParams p{};
   p.v_kn = v_kn;
   p.q = q; p.k = k; p.vt = vt; p.out = out;
@@ -861,14 +952,36 @@ int tc_attention_f32(const float* q, const float* k, const float* vt, float* out
   p.v_vec = (vt_rs % 4 == 0) && (vt_bs % 4 == 0) && aligned16(vt);
   p.o_vec = (o_rs % 4 == 0) && (o_bs % 4 == 0) && aligned16(out);
   const size_t smem = (size_t)kAttSmem + 1024 + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B2_CUDA(cudaFuncSetAttribute(tc_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
   B2_CHECK_ARG((int64_t)B * H <= 65535, "attention_f32: batch * heads too large");
   dim3 grid((unsigned)cdiv(Lq, kAttQ), (unsigned)(B * H));
-  tc_attention_kernel<<<grid, kAttThreads, smem, st>>>(p);
+  if (work) {
+    // Every K / V tile is consumed by all query tiles of its (batch, head): split it into bf16 hi / lo ONCE here, not once per consumer inside the attention
+    // kernel (ncu: the in-kernel producers were 40 % of its instructions and took the schedulers from the softmax warps).
+    B2_CHECK_ARG(aligned16(work), "attention_f32: work must be 16-byte aligned");
+    static bool attr_packed = false;
+    if (!attr_packed) {
+      B2_CUDA(cudaFuncSetAttribute(tc_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_packed = true;
+    }
+    const int nk = cdiv(Lk, kAttKeys);
+    p.mq_tiles = cdiv(Lq, kAttQ);
+    uint8_t* qimg = (uint8_t*)work;
+    uint8_t* kimg = qimg + (int64_t)B * H * p.mq_tiles * 32768;
+    uint8_t* vimg = kimg + (int64_t)B * H * nk * 32768;
+    p.qimg = qimg; p.kimg = kimg; p.vimg = vimg;
+    const int64_t nq_chunks = (int64_t)B * H * p.mq_tiles * 1024, nk_chunks = (int64_t)B * H * nk * 1024;
+    att_pack_kernel<<<(int)std::min<int64_t>(cdiv(nq_chunks + 2 * nk_chunks, 256), kNumSMs * 32), 256, 0, st>>>(p, qimg, kimg, vimg, nk, nq_chunks, nk_chunks);
+    B2_LAUNCHED();
+    tc_attention_kernel<true><<<grid, kAttThreadsPacked, smem, st>>>(p);
+    B2_LAUNCHED();
+    return B200SEP_OK;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2_CUDA(cudaFuncSetAttribute(tc_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  tc_attention_kernel<false><<<grid, kAttThreads, smem, st>>>(p);
   B2_LAUNCHED();
   return B200SEP_OK;
 }
@@ -969,11 +1082,16 @@ int tc_conv2d_f32(const float* x, const float* w_blocked, const float* bias, con
 // cross-transformer, transformer.py:196-409; Attend of the Roformers).  Layouts in the header.
 extern "C" int b200sep_attention_f32(const float* q, const float* k, const float* vt, float* out, int B, int H, int Lq, int Lk, int head_dim, int64_t q_batch_stride,
                                      int64_t q_row_stride, int64_t k_batch_stride, int64_t k_row_stride, int64_t vt_batch_stride, int64_t vt_row_stride,
-                                     int64_t out_batch_stride, int64_t out_row_stride, float alpha, int v_is_kn, void* stream) {
+                                     int64_t out_batch_stride, int64_t out_row_stride, float alpha, int v_is_kn, float* work, void* stream) {
   using namespace b200sep;
   B2_CHECK_ARG(q && k && vt && out && B >= 1 && H >= 1 && Lq >= 1 && Lk >= 1 && alpha > 0.f, "attention_f32: bad argument");
   B2_CHECK_ARG(head_dim == 64, "attention_f32: head dimension %d is not supported (64 only)", head_dim);
   B2_CHECK_ARG(v_is_kn ? vt_row_stride >= 64 : vt_row_stride >= Lk, "attention_f32: V row stride %lld too short", (long long)vt_row_stride);
   return tc_attention_f32(q, k, vt, out, B, H, Lq, Lk, q_batch_stride, q_row_stride, k_batch_stride, k_row_stride, vt_batch_stride, vt_row_stride, out_batch_stride,
-                          out_row_stride, alpha, v_is_kn, (cudaStream_t)stream);
+                          out_row_stride, alpha, v_is_kn, work, (cudaStream_t)stream);
+}
+
+extern "C" int64_t b200sep_attention_work_floats(int B, int H, int Lq, int Lk) {
+  if (B < 1 || H < 1 || Lq < 1 || Lk < 1) return 0;
+  return b200sep::tc_attention_work_bytes(B, H, Lq, Lk) / 4;
 }

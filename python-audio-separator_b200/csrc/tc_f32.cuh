@@ -17,7 +17,8 @@ int tc_conv2d_f32(const float* x, const float* w_blocked, const float* bias, con
 // fused attention, head dimension 64: out = softmax(alpha q k^T) v with vt = v transposed (keys contiguous); strides in floats (see tc_f32.cu)
 bool tc_attention_usable(int hd, int Lq, int Lk);
 int tc_attention_f32(const float* q, const float* k, const float* vt, float* out, int B, int H, int Lq, int Lk, int64_t q_bs, int64_t q_rs, int64_t k_bs, int64_t k_rs,
-                     int64_t vt_bs, int64_t vt_rs, int64_t o_bs, int64_t o_rs, float alpha, int v_kn, cudaStream_t st);
+                     int64_t vt_bs, int64_t vt_rs, int64_t o_bs, int64_t o_rs, float alpha, int v_kn, void* work, cudaStream_t st);
+int64_t tc_attention_work_bytes(int B, int H, int Lq, int Lk);
 // static B operands (weights) pre-split into the kernel's shared-memory image; K = the kernel's K (convolution: ceil8(Cin) * taps)
 int64_t tc_packed_bytes(int N, int K);
 int tc_pack_linear(const float* W, int N, int K, int ldw, void* packed, cudaStream_t st);

@@ -102,11 +102,12 @@ def test_tc_conv2d_slice_and_add(dm):
 
 
 # ------------------------------------------------------------------------------------------------ fused attention (head dimension 64)
+@pytest.mark.parametrize("packed", [1, 0])
 @pytest.mark.parametrize(
     "B,H,Lq,Lk,v_kn",
     [(2, 3, 200, 1344, 0), (1, 2, 130, 130, 1), (1, 8, 2688, 2688, 0), (2, 2, 1344, 2688, 0), (3, 1, 1101, 1101, 1), (1, 1, 5, 7, 0), (1, 2, 128, 256, 1)],
 )
-def test_fused_attention_vs_fp64(lib_built, B, H, Lq, Lk, v_kn):
+def test_fused_attention_vs_fp64(lib_built, B, H, Lq, Lk, v_kn, packed):
     """b200sep_attention_f32 (scores in TMEM, running softmax, P V from shared memory) against softmax(q k^T / 8) v in float64; ragged query / key tiles,
     both V layouts (transposed with keys contiguous: HTDemucs; plain (keys, d): Roformer)."""
     from audio_separator.separator.b200._lib import check, lib
@@ -121,12 +122,15 @@ def test_fused_attention_vs_fp64(lib_built, B, H, Lq, Lk, v_kn):
     ref = (torch.softmax(qh @ kh.transpose(-1, -2) / 8.0, dim=-1) @ vh).transpose(1, 2).reshape(B, Lq, D)
     qd, kd = q.cuda(), k.cuda()
     out = torch.full((B, Lq, D), float("nan"), device="cuda")
+    # packed: Q / K / V^T pre-split into tile images in `work` and fetched by bulk copies; otherwise every CTA converts the tiles it reads
+    work = torch.empty((lib.b200sep_attention_work_floats(B, H, Lq, Lk),), device="cuda") if packed else None
+    wp = _ptr(work) if packed else None
     if v_kn:
         vd = v.cuda()
-        check(lib.b200sep_attention_f32(_ptr(qd), _ptr(kd), _ptr(vd), _ptr(out), B, H, Lq, Lk, 64, Lq * D, D, Lk * D, D, Lk * D, D, Lq * D, D, 0.125, 1, _stream()), "attention_f32")
+        check(lib.b200sep_attention_f32(_ptr(qd), _ptr(kd), _ptr(vd), _ptr(out), B, H, Lq, Lk, 64, Lq * D, D, Lk * D, D, Lk * D, D, Lq * D, D, 0.125, 1, wp, _stream()), "attention_f32")
     else:
         vd = v.transpose(1, 2).contiguous().cuda()  # (B, D, Lk)
-        check(lib.b200sep_attention_f32(_ptr(qd), _ptr(kd), _ptr(vd), _ptr(out), B, H, Lq, Lk, 64, Lq * D, D, Lk * D, D, D * Lk, Lk, Lq * D, D, 0.125, 0, _stream()), "attention_f32")
+        check(lib.b200sep_attention_f32(_ptr(qd), _ptr(kd), _ptr(vd), _ptr(out), B, H, Lq, Lk, 64, Lq * D, D, Lk * D, D, D * Lk, Lk, Lq * D, D, 0.125, 0, wp, _stream()), "attention_f32")
     torch.cuda.synchronize()
     err = (out.cpu().double() - ref).abs().max().item()
     assert err <= 3e-5 * max(1.0, ref.abs().max().item()), err
