@@ -693,7 +693,7 @@ def main():
     ap.add_argument("--also", default="htdemucs_ft", help="second workload measured by the default (mdx) run and reported under \"also\" (none = skip)")
     ap.add_argument("--minutes", type=float, default=None, help="track length (default: the BASELINE config's)")
     ap.add_argument("--batch", type=int, default=None, help="MDX chunks per network forward (default 4; with N > 1 all the chunks of a rank, up to 12)")
-    ap.add_argument("--demucs-batch", type=int, default=8, help="HTDemucs segments per forward")
+    ap.add_argument("--demucs-batch", type=int, default=13, help="HTDemucs segments per forward")
     ap.add_argument("--tracks", type=int, default=32, help="VR workload: tracks in the batch")
     ap.add_argument("--precision", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
