@@ -13,6 +13,8 @@
 // with a tiny finalise kernel after K1 and K2 turning the partial sums (double) into (mean, rstd) per sample.
 // All arithmetic is fp32 FMA (no tensor cores: 2*hid*2C flops per position against 4*(2C + C/4) bytes is below the ridge even for
 // fp32 SIMT); thread = P positions, the small weight matrices sit in shared memory and are read as broadcast float4.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -322,6 +324,193 @@ int dconv_launch(DconvParams p, bool have_u, cudaStream_t st) {
   return B200SEP_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Single-pass form for rows that fit in shared memory (the frequency branch: one GroupNorm sample = one (b, fr) row of C x L values, 64 KB at C = 48,
+// L = 336): the row is read ONCE, both GroupNorm reductions happen inside the CTA, and the result is written once -- instead of three passes over x, the
+// hidden tensor through HBM and two partial-sum round trips.  Persistent CTAs walk the rows; the weights are staged once per CTA.
+constexpr int kRowMaxThreads = 512;
+
+__device__ __forceinline__ void row_sum2(double& s, double& q, double* sm) {
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();  // sm may still be read from the previous reduction
+  if ((threadIdx.x & 31) == 0) {
+    sm[2 * w] = s;
+    sm[2 * w + 1] = q;
+  }
+  __syncthreads();
+  s = 0.0;
+  q = 0.0;
+  for (int i = 0; i < nw; ++i) {
+    s += sm[2 * i];
+    q += sm[2 * i + 1];
+  }
+}
+
+template <int HID>
+__global__ void __launch_bounds__(kRowMaxThreads) dconv_row_kernel(const DconvParams p) {
+  constexpr int HP = (HID + 3) / 4 * 4;
+  extern __shared__ __align__(16) float smem_dc[];
+  const int C = p.C, L = p.L;
+  float* xs = smem_dc;                        // [C][L]
+  float* us = xs + (size_t)C * L;             // [HP][L]: u, then h = GELU(GN(u)) in place
+  float* w0s = us + (size_t)HP * L;           // [C][3][HP]
+  float* w3s = w0s + (size_t)C * 3 * HP;      // [C][2][HP]: rows c (value) and C + c (gate) of w3
+  float* cst = w3s + (size_t)C * 2 * HP;      // [C][8]: b3[c], b3[C+c], g4[c], be4[c], g4[C+c], be4[C+c], ls[c], -
+  float* k1s = cst + (size_t)C * 8;           // [HP][4]: b0, g1, be1, -
+  __shared__ double red[2 * kRowMaxThreads / 32];
+  const int NT = blockDim.x;
+  for (int i = threadIdx.x; i < HP * C * 3; i += NT) {
+    const int k = i / (C * 3), r = i - k * (C * 3);  // w0 is (HID, C, 3): r = c*3 + t
+    w0s[r * HP + k] = k < HID ? __ldg(&p.w0[i]) : 0.f;
+  }
+  for (int i = threadIdx.x; i < 2 * C * HP; i += NT) {
+    const int row = i / HP, k = i - row * HP;  // w3 is (2C, HID)
+    const int c = row < C ? row : row - C, half = row < C ? 0 : 1;
+    w3s[(c * 2 + half) * HP + k] = k < HID ? __ldg(&p.w3[row * HID + k]) : 0.f;
+  }
+  for (int c = threadIdx.x; c < C; c += NT) {
+    float* o = cst + c * 8;
+    o[0] = __ldg(&p.b3[c]); o[1] = __ldg(&p.b3[C + c]);
+    o[2] = __ldg(&p.g4[c]); o[3] = __ldg(&p.be4[c]); o[4] = __ldg(&p.g4[C + c]); o[5] = __ldg(&p.be4[C + c]);
+    o[6] = __ldg(&p.ls[c]); o[7] = 0.f;
+  }
+  for (int k = threadIdx.x; k < HP; k += NT) {
+    k1s[k * 4] = k < HID ? __ldg(&p.b0[k]) : 0.f;
+    k1s[k * 4 + 1] = k < HID ? __ldg(&p.g1[k]) : 0.f;
+    k1s[k * 4 + 2] = k < HID ? __ldg(&p.be1[k]) : 0.f;
+    k1s[k * 4 + 3] = 0.f;
+  }
+  const int samples = p.B * p.Fr;
+  const int64_t cs = (int64_t)p.Fr * L;
+  for (int sample = blockIdx.x; sample < samples; sample += gridDim.x) {
+    const int b = sample / p.Fr, fr = sample - b * p.Fr;
+    const float* xr = p.x + ((int64_t)b * C * p.Fr + fr) * L;
+    float* yr = p.y + ((int64_t)b * C * p.Fr + fr) * L;
+    __syncthreads();  // the previous row's xs / us are dead (and the staged weights are visible)
+    for (int i = threadIdx.x; i < C * L; i += NT) {
+      const int c = i / L, l = i - c * L;
+      xs[i] = __ldg(&xr[(int64_t)c * cs + l]);
+    }
+    __syncthreads();
+    // ---- u = conv3(x) + b0 and its statistics
+    double s = 0.0, q = 0.0;
+    for (int l = threadIdx.x; l < L; l += NT) {
+      float acc[HP];
+#pragma unroll
+      for (int k = 0; k < HP; ++k) acc[k] = k1s[k * 4];
+      for (int c = 0; c < C; ++c) {
+        const float* xc = xs + (size_t)c * L;
+        const float* wc = w0s + c * 3 * HP;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          const int ll = l + (t - 1) * p.dil;
+          const float xv = (ll >= 0 && ll < L) ? xc[ll] : 0.f;
+#pragma unroll
+          for (int k4 = 0; k4 < HP; k4 += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(&wc[t * HP + k4]);
+            acc[k4] = fmaf(w.x, xv, acc[k4]);
+            acc[k4 + 1] = fmaf(w.y, xv, acc[k4 + 1]);
+            acc[k4 + 2] = fmaf(w.z, xv, acc[k4 + 2]);
+            acc[k4 + 3] = fmaf(w.w, xv, acc[k4 + 3]);
+          }
+        }
+      }
+      float fs = 0.f, fq = 0.f;
+#pragma unroll
+      for (int k = 0; k < HID; ++k) {
+        us[(size_t)k * L + l] = acc[k];
+        fs += acc[k];
+        fq = fmaf(acc[k], acc[k], fq);
+      }
+      s += fs;
+      q += fq;
+    }
+    row_sum2(s, q, red);
+    const double nu = (double)HID * L;
+    const double mu_d = s / nu;
+    double var_u = q / nu - mu_d * mu_d;
+    if (var_u < 0.0) var_u = 0.0;
+    const float mu = (float)mu_d, ru = (float)(1.0 / sqrt(var_u + 1e-5));
+    // ---- h = GELU(GN(u)) kept in registers per position; z = W3 h + b3: statistics first, then the output
+    double sz = 0.0, qz = 0.0;
+    for (int l = threadIdx.x; l < L; l += NT) {
+      float h[HP];
+#pragma unroll
+      for (int k = 0; k < HP; ++k) h[k] = k < HID ? gelu_erf(fmaf((us[(size_t)k * L + l] - mu) * ru, k1s[k * 4 + 1], k1s[k * 4 + 2])) : 0.f;
+#pragma unroll
+      for (int k = 0; k < HID; ++k) us[(size_t)k * L + l] = h[k];  // only this thread touches column l
+      float fs = 0.f, fq = 0.f;
+      for (int c = 0; c < C; ++c) {
+        const float* wc = w3s + c * 2 * HP;
+        float a = cst[c * 8], g = cst[c * 8 + 1];
+#pragma unroll
+        for (int k = 0; k < HP; k += 4) {
+          const float4 wa = *reinterpret_cast<const float4*>(&wc[k]);
+          const float4 wg = *reinterpret_cast<const float4*>(&wc[HP + k]);
+          a = fmaf(wa.x, h[k], a); a = fmaf(wa.y, h[k + 1], a); a = fmaf(wa.z, h[k + 2], a); a = fmaf(wa.w, h[k + 3], a);
+          g = fmaf(wg.x, h[k], g); g = fmaf(wg.y, h[k + 1], g); g = fmaf(wg.z, h[k + 2], g); g = fmaf(wg.w, h[k + 3], g);
+        }
+        fs += a + g;
+        fq = fmaf(a, a, fmaf(g, g, fq));
+      }
+      sz += fs;
+      qz += fq;
+    }
+    row_sum2(sz, qz, red);
+    const double nz = 2.0 * C * L;
+    const double mz_d = sz / nz;
+    double var_z = qz / nz - mz_d * mz_d;
+    if (var_z < 0.0) var_z = 0.0;
+    const float mz = (float)mz_d, rz = (float)(1.0 / sqrt(var_z + 1e-5));
+    for (int l = threadIdx.x; l < L; l += NT) {
+      float h[HP];
+#pragma unroll
+      for (int k = 0; k < HP; ++k) h[k] = k < HID ? us[(size_t)k * L + l] : 0.f;
+      for (int c = 0; c < C; ++c) {
+        const float* wc = w3s + c * 2 * HP;
+        const float4 k0 = *reinterpret_cast<const float4*>(&cst[c * 8]);
+        const float4 k1 = *reinterpret_cast<const float4*>(&cst[c * 8 + 4]);
+        float a = k0.x, g = k0.y;
+#pragma unroll
+        for (int k = 0; k < HP; k += 4) {
+          const float4 wa = *reinterpret_cast<const float4*>(&wc[k]);
+          const float4 wg = *reinterpret_cast<const float4*>(&wc[HP + k]);
+          a = fmaf(wa.x, h[k], a); a = fmaf(wa.y, h[k + 1], a); a = fmaf(wa.z, h[k + 2], a); a = fmaf(wa.w, h[k + 3], a);
+          g = fmaf(wg.x, h[k], g); g = fmaf(wg.y, h[k + 1], g); g = fmaf(wg.z, h[k + 2], g); g = fmaf(wg.w, h[k + 3], g);
+        }
+        const float an = fmaf((a - mz) * rz, k0.z, k0.w);
+        const float gn = fmaf((g - mz) * rz, k1.x, k1.y);
+        yr[(int64_t)c * cs + l] = xs[(size_t)c * L + l] + k1.z * (an / (1.f + expf(-gn)));
+      }
+    }
+  }
+}
+
+template <int HID>
+size_t dconv_row_smem(int C, int L) {
+  constexpr int HP = (HID + 3) / 4 * 4;
+  return ((size_t)C * L + (size_t)HP * L + (size_t)C * 3 * HP + (size_t)C * 2 * HP + (size_t)C * 8 + (size_t)HP * 4) * sizeof(float);
+}
+
+template <int HID>
+int dconv_row_launch(const DconvParams& p, cudaStream_t st) {
+  const size_t smem = dconv_row_smem<HID>(p.C, p.L);
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2_CUDA(cudaFuncSetAttribute(dconv_row_kernel<HID>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set = true;
+  }
+  const int threads = std::min(kRowMaxThreads, std::max(128, (p.L + 31) / 32 * 32));
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / smem));
+  dconv_row_kernel<HID><<<std::min(p.B * p.Fr, kNumSMs * per_sm), threads, smem, st>>>(p);
+  B2_LAUNCHED();
+  return B200SEP_OK;
+}
+
 int dconv_positions_per_thread(int L) { return L >= 2048 ? 2 : 1; }
 
 }  // namespace
@@ -358,6 +547,22 @@ extern "C" int b200sep_dconv_f32(const float* x, float* y, const float* w0, cons
   p.B = B; p.C = C; p.Fr = Fr; p.L = (int)L; p.dil = dilation;
   cudaStream_t st = (cudaStream_t)stream;
   const bool have_u = u_in != nullptr;
+  // rows that fit in shared memory (the frequency branch) take the single-pass kernel; B200SEP_DCONV_ROW=0 keeps the three-pass form for A/B runs
+  static const bool row_on = [] {
+    const char* e = getenv("B200SEP_DCONV_ROW");
+    return !(e && e[0] == '0');
+  }();
+  if (row_on && !have_u && Fr > 1 && L <= 4096) {
+#define B2_DCONV_ROW_CASE(h) \
+  if (hid == h && dconv_row_smem<h>(C, (int)L) <= 216 * 1024) return dconv_row_launch<h>(p, st);
+    B2_DCONV_ROW_CASE(6)
+    B2_DCONV_ROW_CASE(12)
+    B2_DCONV_ROW_CASE(24)
+    B2_DCONV_ROW_CASE(4)
+    B2_DCONV_ROW_CASE(8)
+    B2_DCONV_ROW_CASE(16)
+#undef B2_DCONV_ROW_CASE
+  }
 #define B2_DCONV_CASE(h)                                                   \
   if (hid == h) return P == 2 ? dconv_launch<h, 2>(p, have_u, st) : dconv_launch<h, 1>(p, have_u, st);
   B2_DCONV_CASE(6)
