@@ -5,3 +5,4 @@ timeout 600 python -m pytest tests/test_demucs_gpu.py -q > $O/c18_demucs_tests.t
 B200SEP_DCONV_ROW=0 timeout 300 python tests/dev/demucs_probe.py 4 2>&1 | head -1
 PROFILE=1 timeout 300 python tests/dev/demucs_probe.py 4 > $O/c18_htdemucs_profile_b4.txt 2>&1; head -1 $O/c18_htdemucs_profile_b4.txt; grep -E "dconv_row|dconv_k|tc_attention|tc_f32_kernel" $O/c18_htdemucs_profile_b4.txt | cut -c1-70,150-230
 timeout 300 python tests/dev/demucs_probe.py 13 2>&1 | head -1
+timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -5
