@@ -70,8 +70,9 @@ __global__ void __launch_bounds__(768) lstm_bidir_cluster_kernel(const float* __
   extern __shared__ __align__(16) float lsm[];
   float* hs = lsm;                     // [2][hid][NS]
   float* gs = hs + 2 * hid * NS;       // [KS][NS][GL]
-  float* cs = gs + KS * NS * GL;       // [NS][UH]
-  float* ws = cs + NS * UH;            // [hid][GL] when w_in_smem
+  float* cs = gs + KS * NS * GL;       // [UH][NS] cell states
+  float* hl = cs + NS * UH;            // [UH][NS] this step's h slice before it is broadcast
+  float* ws = hl + NS * UH;            // [hid][GL] when w_in_smem
   const float* w = whh_t + (int64_t)dir * hid * G;
   if (w_in_smem)
     for (int k = k_lo; k < k_hi; ++k) ws[k * GL + col] = __ldg(&w[(int64_t)k * G + j]);
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(768) lstm_bidir_cluster_kernel(const float* __
     __syncthreads();
     float* hn = hs + (cur ^ 1) * hid * NS;
     for (int i = tid; i < NS * UH; i += nthreads) {
-      const int n = i / UH, u = i - n * UH;
+      const int u = i / NS, n = i - u * NS;  // n fastest: hl[u][n] below is written as contiguous rows
       float g4[4] = {0.f, 0.f, 0.f, 0.f};
       for (int q = 0; q < KS; ++q) {
         const float* gp = gs + (q * NS + n) * GL + u;
@@ -132,7 +133,14 @@ __global__ void __launch_bounds__(768) lstm_bidir_cluster_kernel(const float* __
       cs[i] = c;
       const float h = og * tanhf(c);
       if (n0 + n < N) out[((int64_t)t * N + n0 + n) * (2 * hid) + dir * hid + r * UH + u] = h;
-      for (int q = 0; q < CL; ++q) cluster.map_shared_rank(hn, q)[(r * UH + u) * NS + n] = h;
+      hl[i] = h;  // [UH][NS]: this CTA's slice of h_t
+    }
+    __syncthreads();
+    // broadcast the slice into every CTA's next-step buffer as 16-byte distributed-shared-memory stores (one per thread at 768 threads), not 4-byte ones
+    for (int i = tid; i < CL * UH * (NS / 4); i += nthreads) {
+      const int q = i / (UH * (NS / 4)), w4 = i - q * (UH * (NS / 4));
+      const float4 v = *reinterpret_cast<const float4*>(&hl[w4 * 4]);
+      *reinterpret_cast<float4*>(&cluster.map_shared_rank(hn, q)[r * UH * NS + w4 * 4]) = v;
     }
     cluster.sync();  // h_t visible everywhere; gs / the other h buffer are free again
     cur ^= 1;
@@ -277,7 +285,7 @@ extern "C" int b200sep_lstm_bidir_wide_f32(const float* x_proj, const float* w_h
   const int UH = hid / CL, GL = 4 * UH;
   B2_CHECK_ARG(GL <= 768, "lstm_bidir_wide_f32: hidden size %d needs %d threads per CTA", hid, GL);
   const size_t wbytes = (size_t)hid * GL * sizeof(float);
-  const size_t base1 = ((size_t)2 * hid * NS + (size_t)NS * GL + (size_t)NS * UH) * sizeof(float);
+  const size_t base1 = ((size_t)2 * hid * NS + (size_t)NS * GL + (size_t)2 * NS * UH) * sizeof(float);
   const int w_in_smem = base1 + wbytes <= 200 * 1024;
   int KS = 1;  // k-splits per gate column: streamed weights want many loads in flight
   if (!w_in_smem)
@@ -286,7 +294,7 @@ extern "C" int b200sep_lstm_bidir_wide_f32(const float* x_proj, const float* w_h
         KS = c;
         break;
       }
-  size_t smem = ((size_t)2 * hid * NS + (size_t)KS * NS * GL + (size_t)NS * UH) * sizeof(float) + (w_in_smem ? wbytes : 0);
+  size_t smem = ((size_t)2 * hid * NS + (size_t)KS * NS * GL + (size_t)2 * NS * UH) * sizeof(float) + (w_in_smem ? wbytes : 0);
   static size_t attr = 0;
   if (smem > attr) {
     B2_CUDA(cudaFuncSetAttribute(lstm_bidir_cluster_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
