@@ -1,6 +1,8 @@
 #!/bin/bash
 # round-2 GPU call 17: checkpoint of the final build: full GPU suite, default bench (mdx + htdemucs_ft), reference arm, launch list, mdx23c and vr bench lines
 O=gpurun_out/r02; mkdir -p $O
+PROFILE=1 timeout 300 python tests/dev/demucs_probe.py 4 > $O/r02_htdemucs_profile_b4_final.txt 2>&1; head -1 $O/r02_htdemucs_profile_b4_final.txt; grep -E "dconv_row|tc_attention|tc_f32_kernel" $O/r02_htdemucs_profile_b4_final.txt | cut -c1-70,150-230
+PROFILE=1 timeout 300 python tests/dev/hdemucs_probe.py 4 40 > $O/r02_hdemucs_probe_b4_final.txt 2>&1; head -1 $O/r02_hdemucs_probe_b4_final.txt; grep -E "lstm_bidir" $O/r02_hdemucs_probe_b4_final.txt | cut -c1-70,150-230
 timeout 1500 python -m pytest tests -m gpu -q > $O/r02_gpu_tests.txt 2>&1; tail -4 $O/r02_gpu_tests.txt | cut -c1-300
 timeout 900 python bench.py > $O/r02_bench_n1.json 2> $O/r02_bench_n1.err; tail -2 $O/r02_bench_n1.err
 python - <<'PY'
