@@ -391,9 +391,9 @@ __global__ void __launch_bounds__(kRowMaxThreads) dconv_row_kernel(const DconvPa
     const float* xr = p.x + ((int64_t)b * C * p.Fr + fr) * L;
     float* yr = p.y + ((int64_t)b * C * p.Fr + fr) * L;
     __syncthreads();  // the previous row's xs / us are dead (and the staged weights are visible)
-    for (int l = threadIdx.x; l < L; l += NT) {
-#pragma unroll 8
-      for (int c = 0; c < C; ++c) xs[(size_t)c * L + l] = __ldg(&xr[(int64_t)c * cs + l]);  // 8 independent loads in flight per thread
+    for (int i = threadIdx.x; i < C * L; i += NT) {
+      const int c = i / L, l = i - c * L;
+      xs[i] = __ldg(&xr[(int64_t)c * cs + l]);
     }
     __syncthreads();
     // ---- u = conv3(x) + b0 and its statistics
@@ -444,32 +444,18 @@ __global__ void __launch_bounds__(kRowMaxThreads) dconv_row_kernel(const DconvPa
 #pragma unroll
       for (int k = 0; k < HID; ++k) us[(size_t)k * L + l] = h[k];  // only this thread touches column l
       float fs = 0.f, fq = 0.f;
-      for (int c0 = 0; c0 < C; c0 += 4) {  // 4 channels = 8 independent FMA chains (one value + one gate each): the dependent chain of one channel is 2 HP long
-        float a[4], g[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int c = min(c0 + i, C - 1);
-          a[i] = cst[c * 8];
-          g[i] = cst[c * 8 + 1];
-        }
+      for (int c = 0; c < C; ++c) {
+        const float* wc = w3s + c * 2 * HP;
+        float a = cst[c * 8], g = cst[c * 8 + 1];
 #pragma unroll
         for (int k = 0; k < HP; k += 4) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float* wc = w3s + min(c0 + i, C - 1) * 2 * HP;
-            const float4 wa = *reinterpret_cast<const float4*>(&wc[k]);
-            const float4 wg = *reinterpret_cast<const float4*>(&wc[HP + k]);
-            a[i] = fmaf(wa.x, h[k], a[i]); a[i] = fmaf(wa.y, h[k + 1], a[i]); a[i] = fmaf(wa.z, h[k + 2], a[i]); a[i] = fmaf(wa.w, h[k + 3], a[i]);
-            g[i] = fmaf(wg.x, h[k], g[i]); g[i] = fmaf(wg.y, h[k + 1], g[i]); g[i] = fmaf(wg.z, h[k + 2], g[i]); g[i] = fmaf(wg.w, h[k + 3], g[i]);
-          }
+          const float4 wa = *reinterpret_cast<const float4*>(&wc[k]);
+          const float4 wg = *reinterpret_cast<const float4*>(&wc[HP + k]);
+          a = fmaf(wa.x, h[k], a); a = fmaf(wa.y, h[k + 1], a); a = fmaf(wa.z, h[k + 2], a); a = fmaf(wa.w, h[k + 3], a);
+          g = fmaf(wg.x, h[k], g); g = fmaf(wg.y, h[k + 1], g); g = fmaf(wg.z, h[k + 2], g); g = fmaf(wg.w, h[k + 3], g);
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (c0 + i < C) {
-            fs += a[i] + g[i];
-            fq = fmaf(a[i], a[i], fmaf(g[i], g[i], fq));
-          }
-        }
+        fs += a + g;
+        fq = fmaf(a, a, fmaf(g, g, fq));
       }
       sz += fs;
       qz += fq;
@@ -484,36 +470,21 @@ __global__ void __launch_bounds__(kRowMaxThreads) dconv_row_kernel(const DconvPa
       float h[HP];
 #pragma unroll
       for (int k = 0; k < HP; ++k) h[k] = k < HID ? us[(size_t)k * L + l] : 0.f;
-      for (int c0 = 0; c0 < C; c0 += 4) {
-        float a[4], g[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int c = min(c0 + i, C - 1);
-          a[i] = cst[c * 8];
-          g[i] = cst[c * 8 + 1];
-        }
+      for (int c = 0; c < C; ++c) {
+        const float* wc = w3s + c * 2 * HP;
+        const float4 k0 = *reinterpret_cast<const float4*>(&cst[c * 8]);
+        const float4 k1 = *reinterpret_cast<const float4*>(&cst[c * 8 + 4]);
+        float a = k0.x, g = k0.y;
 #pragma unroll
         for (int k = 0; k < HP; k += 4) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float* wc = w3s + min(c0 + i, C - 1) * 2 * HP;
-            const float4 wa = *reinterpret_cast<const float4*>(&wc[k]);
-            const float4 wg = *reinterpret_cast<const float4*>(&wc[HP + k]);
-            a[i] = fmaf(wa.x, h[k], a[i]); a[i] = fmaf(wa.y, h[k + 1], a[i]); a[i] = fmaf(wa.z, h[k + 2], a[i]); a[i] = fmaf(wa.w, h[k + 3], a[i]);
-            g[i] = fmaf(wg.x, h[k], g[i]); g[i] = fmaf(wg.y, h[k + 1], g[i]); g[i] = fmaf(wg.z, h[k + 2], g[i]); g[i] = fmaf(wg.w, h[k + 3], g[i]);
-          }
+          const float4 wa = *reinterpret_cast<const float4*>(&wc[k]);
+          const float4 wg = *reinterpret_cast<const float4*>(&wc[HP + k]);
+          a = fmaf(wa.x, h[k], a); a = fmaf(wa.y, h[k + 1], a); a = fmaf(wa.z, h[k + 2], a); a = fmaf(wa.w, h[k + 3], a);
+          g = fmaf(wg.x, h[k], g); g = fmaf(wg.y, h[k + 1], g); g = fmaf(wg.z, h[k + 2], g); g = fmaf(wg.w, h[k + 3], g);
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int c = c0 + i;
-          if (c < C) {
-            const float4 k0 = *reinterpret_cast<const float4*>(&cst[c * 8]);
-            const float4 k1 = *reinterpret_cast<const float4*>(&cst[c * 8 + 4]);
-            const float an = fmaf((a[i] - mz) * rz, k0.z, k0.w);
-            const float gn = fmaf((g[i] - mz) * rz, k1.x, k1.y);
-            yr[(int64_t)c * cs + l] = xs[(size_t)c * L + l] + k1.z * (an / (1.f + expf(-gn)));
-          }
-        }
+        const float an = fmaf((a - mz) * rz, k0.z, k0.w);
+        const float gn = fmaf((g - mz) * rz, k1.x, k1.y);
+        yr[(int64_t)c * cs + l] = xs[(size_t)c * L + l] + k1.z * (an / (1.f + expf(-gn)));
       }
     }
   }
