@@ -726,7 +726,10 @@ def main():
         try:
             extra = measure(WORKLOADS[args.also](args), ctx, args, min(args.steps, 2), 3, with_cpu=not args.no_cpu_baseline)
         except Exception as e:  # noqa: BLE001
-            extra = {"error": f"{type(e).__name__}: {e}"[:500]}
+            import traceback
+
+            extra = {"error": f"{type(e).__name__}: {e}"[:500], "where": [ln.strip()[:160] for ln in traceback.format_exc().splitlines() if ln.strip().startswith("File")][-6:]}
+            traceback.print_exc()
             emit(extra)
             os._exit(0 if ctx.rank == 0 else 1)
         emit(extra)

@@ -65,6 +65,7 @@ struct TcParams {
   // B operand pre-split into the kernel's shared-memory image (tc_pack_*): per (n-tile, k-block) one [hi plane | lo plane] block that a
   // single cp.async.bulk drops into the stage -- static weights cost the producer warps nothing
   const uint8_t* b_packed;
+  int sleep_ns;  // > 0: waiting producer / epilogue warps sleep between polls (B200SEP_WAIT_SLEEP_NS)
 };
 
 __device__ __forceinline__ float tc_act(float v, int act) {
@@ -284,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f32_kernel(const TcParams p) {
         wi0 = wo * p.SW - p.PW;
       }
       for (int i = 0; i < p.num_iters; ++i) {
-        ptx::mbar_wait(&empty_bar[s], phase ^ 1, 100 + i);
+        ptx::mbar_wait_opt(&empty_bar[s], phase ^ 1, p.sleep_ns, 100 + i);
         uint8_t* st = smem + (size_t)s * p.stage_bytes;
         uint8_t* a_hi = st;
         uint8_t* a_lo = st + p.a_bytes;
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f32_kernel(const TcParams p) {
       const float bm = (row_ok && p.bias_m) ? __ldg(&p.bias_m[m]) : 0.f;
       float* orow = p.out + (int64_t)z * p.o_sz + (int64_t)m * p.o_sm;
       const float* rrow = p.res ? p.res + (int64_t)z * p.r_sz + (int64_t)m * p.r_sm : nullptr;
-      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase, 300 + acc);
+      ptx::mbar_wait_opt(&tmem_full_bar[acc], acc_phase, p.sleep_ns, 300 + acc);
       ptx::tc_fence_after();
       const uint32_t trow = tmem_base + (uint32_t)acc * acc_stride + ((uint32_t)(q * 32) << 16);
       for (int ch = ch_begin; ch < ch_end; ++ch) {
@@ -510,7 +511,16 @@ __global__ void tc_pack_kernel(const float* __restrict__ src, int conv, int64_t 
   }
 }
 
+int wait_sleep_ns() {
+  static const int ns = [] {
+    const char* e = getenv("B200SEP_WAIT_SLEEP_NS");
+    return e ? atoi(e) : 0;
+  }();
+  return ns;
+}
+
 int tc_launch(TcParams& p, cudaStream_t st) {
+  p.sleep_ns = wait_sleep_ns();
   p.n_tile = pick_n_tile(p.N);
   p.stages = (p.n_tile == 256) ? 2 : 3;
   p.tmem_cols = 2 * p.n_tile;

@@ -60,6 +60,12 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
   }
 }
 
+// ns == 0: the plain bounded wait; otherwise the sleeping one
+__device__ __forceinline__ void mbar_wait_opt(uint64_t* bar, uint32_t parity, int ns, int tag = 0) {
+  if (ns > 0) mbar_wait_backoff(bar, parity, (unsigned)ns, tag);
+  else mbar_wait(bar, parity, tag);
+}
+
 // ---- TMA ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -53,6 +53,7 @@ struct UmmaParams {
   int n_tile, n_total, tmem_cols;
   int num_iters, ksteps, stages;
   int dbg;  // development switches from env B200SEP_DBG (0 in production): see launch()
+  int sleep_ns;  // > 0: waiting producer / epilogue warps sleep between polls (B200SEP_WAIT_SLEEP_NS)
   int num_tiles, n_ftiles, t_tiles;  // persistent tile walk (n_tiles below = tiles along N / output channels)
   uint32_t a_bytes, b_bytes, stage_bytes;
   // CONV
@@ -132,7 +133,7 @@ __device__ __forceinline__ void umma_producer_loop(const CUtensorMap& tmA_hi, co
     const TileCoord tc = decode_tile(p, tile);
     const int n0 = tc.n_idx * p.n_tile;
     for (int i = 0; i < p.num_iters; ++i) {
-      ptx::mbar_wait(&empty_bar[s], phase ^ 1, 100 + i);
+      ptx::mbar_wait_opt(&empty_bar[s], phase ^ 1, p.sleep_ns, 100 + i);
       uint8_t* st = smem + (size_t)s * p.stage_bytes;
       uint8_t* a_hi = st;
       uint8_t* a_lo = st + p.a_bytes;
@@ -327,7 +328,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_pair_kernel(const __grid
           }
         }
       }
-      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase, 300 + acc);
+      ptx::mbar_wait_opt(&tmem_full_bar[acc], acc_phase, p.sleep_ns, 300 + acc);
       ptx::tc_fence_after();
       const uint32_t trow = tmem_base + (uint32_t)acc * acc_stride + ((uint32_t)(q * 32) << 16);
       if (p.dbg & 32) {
@@ -633,7 +634,7 @@ __global__ void __launch_bounds__(kConv3Threads, 1) umma_conv3_kernel(const __gr
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const TileCoord tc = decode_tile(p, tile);
       const int n0 = tc.n_idx * NC + half * H;  // first output channel of this warp
-      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase, 300 + acc);
+      ptx::mbar_wait_opt(&tmem_full_bar[acc], acc_phase, p.sleep_ns, 300 + acc);
       ptx::tc_fence_after();
       const uint32_t trow = tmem_base + (uint32_t)acc * acc_stride + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * H);
       uint32_t v0[H], v1[H], v2[H];
@@ -801,6 +802,14 @@ static int env_cluster(const char* name, int dflt) {
   const int v = e ? atoi(e) : dflt;
   return (v == 1 || v == 2 || v == 4 || v == 8) ? v : dflt;
 }
+static int umma_wait_sleep_ns() {
+  static const int ns = [] {
+    const char* e = getenv("B200SEP_WAIT_SLEEP_NS");
+    return e ? atoi(e) : 0;
+  }();
+  return ns;
+}
+
 static int choose_cluster(const UmmaParams& p) {
   static const int want_conv = env_cluster("B200SEP_CLUSTER", 1), want_gemm = env_cluster("B200SEP_CLUSTER_GEMM", 1);
   if (p.mode == 0) {
@@ -859,6 +868,7 @@ static int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtens
   {
     const char* e = getenv("B200SEP_DBG");  // development only: selectively disable parts of the kernel (results become wrong)
     p.dbg = e ? atoi(e) : 0;
+    p.sleep_ns = umma_wait_sleep_ns();
   }
   p.stage_bytes = ((2 * p.a_bytes + 2 * p.b_bytes + 1023) / 1024) * 1024;
   p.tmem_cols = 2 * pow2_cols(p.n_tile);  // two accumulators: the epilogue of tile i overlaps the MMAs of tile i+1
@@ -1037,6 +1047,7 @@ static int launch_conv3(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const 
     attr_set = true;
   }
   p.cluster = choose_cluster(p);
+  p.sleep_ns = umma_wait_sleep_ns();
   return launch_persistent(umma_conv3_kernel<NC>, kConv3Threads, p.cluster, p.num_tiles, smem, st, a_hi, a_lo, o_hi, o_lo, p);
 }
 
