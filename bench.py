@@ -145,6 +145,11 @@ class Ctx:
         self.barrier()
         arr = np.memmap(path, dtype=np.float32, mode="r+", shape=tuple(shape))
         t = torch.from_numpy(arr)
+        # The mapping stays alive (and registered) until the process exits: a workload's buffers that were unmapped while still page-locked leave a stale
+        # registration behind, and the next workload's mmap of the same size lands on the same addresses -> cudaHostRegister fails (seen at N = 2: the second
+        # workload of the default run died here).
+        self._shared = getattr(self, "_shared", [])
+        self._shared.append((arr, t))
         rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), n * 4, 0)
         assert int(rc) == 0, f"cudaHostRegister failed ({rc})"
         self.barrier()

@@ -124,10 +124,11 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
   }
 }
 
-static int gn_blocks_per_sample(int samples, int64_t n) {
-  int64_t nblk = std::max<int64_t>(1, (4 * kNumSMs + samples - 1) / samples);
-  nblk = std::min<int64_t>(nblk, std::max<int64_t>(1, n / 2048));
-  return (int)std::min<int64_t>(nblk, 1024);
+// CTAs per sample: a function of the sample size ONLY.  (It used to shrink with the number of samples in the launch; the partition of the partial sums then
+// depended on the batch size of a forward, and a time-sharded run -- whose ranks batch their segments differently -- differed from the single-GPU run in the
+// last bits: 4e-6 after de-normalisation in tests/test_sharded_gpu.py.)
+static int gn_blocks_per_sample(int /*samples*/, int64_t n) {
+  return (int)std::min<int64_t>(std::max<int64_t>(1, n / 65536), 1024);
 }
 
 // out[perm(i)] = in[i] for a 4-D tensor: out dims = in dims permuted by (p0,p1,p2,p3) ("b c fr t -> b t fr c" etc., transformer.py:532,555)
