@@ -519,6 +519,22 @@ class HTDemucsNet:
 
 
 # --------------------------------------------------------------------------------------------------------- apply_model / demix
+def group_units(clens, seg, pads):
+    """Consecutive units (segments of one apply_model pass) that can share a forward: -> [(j0, j1, input width)].  A model that pads every chunk to its training
+    segment (HTDemucs.valid_length, htdemucs.py:469-481) takes all of them at width `seg`; a model without valid_length (HDemucs) runs every chunk at its own
+    length (apply.py:252-257), so only runs of equal length batch -- in practice all full segments, then the shorter last one."""
+    if pads:
+        return [(0, len(clens), seg)] if clens else []
+    groups, j0 = [], 0
+    while j0 < len(clens):
+        j1 = j0 + 1
+        while j1 < len(clens) and clens[j1] == clens[j0]:
+            j1 += 1
+        groups.append((j0, j1, clens[j0]))
+        j0 = j1
+    return groups
+
+
 class DemucsEngine:
     """apply_model(shifts, split=True, overlap) over a bag of HTDemucs models + DemucsSeparator.demix_demucs, device resident.
 
@@ -578,12 +594,7 @@ class DemucsEngine:
 
         def compute(buf, slot0, unit0, n):
             clens = [min(length - offs[unit0 + j], seg) for j in range(n)]
-            j0 = 0
-            while j0 < n:  # units of one input length form one forward (only the last segment of a pass is shorter)
-                j1 = j0 + 1
-                while pads and j1 < n or (not pads and j1 < n and clens[j1] == clens[j0]):
-                    j1 += 1
-                width = seg if pads else clens[j0]
+            for j0, j1, width in group_units(clens, seg, pads):  # units of one input length form one forward (only the last segment of a pass is shorter)
                 batch = _new((j1 - j0, 2, width), tensor)
                 for j in range(j0, j1):
                     start = offset + offs[unit0 + j] - ((seg - clens[j]) // 2 if pads else 0)
@@ -592,7 +603,6 @@ class DemucsEngine:
                 for j in range(j0, j1):  # center_trim to the chunk's valid length (apply.py:258), stored from sample 0
                     d = (seg - clens[j]) // 2 if pads else 0
                     buf[slot0 + j, :, : clens[j]].copy_(y[j - j0].reshape(S * 2, width)[:, d : d + clens[j]])
-                j0 = j1
 
         self.runner.wait_all(self.runner.run_units(sh, local, compute, self.batch_size))
         if sh.q1 > sh.q0:

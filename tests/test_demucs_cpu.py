@@ -152,3 +152,14 @@ def test_hdemucs_layer_plan_and_package_loader(lib_built, tmp_path):
             L.config_from_package(L.load_package(str(tmp_path / "bad.th")))
     with pytest.raises(ValueError):
         hd.HDemucsConfig(kernel_size=6).validate()
+
+
+def test_group_units_for_models_with_and_without_valid_length(lib_built):
+    """Which segments of an apply_model pass share a forward: everything at the training segment for HTDemucs, runs of equal length for HDemucs."""
+    from audio_separator.separator.b200.demucs import group_units
+
+    assert group_units([100, 100, 100, 37], 100, True) == [(0, 4, 100)]
+    assert group_units([100, 100, 100, 37], 100, False) == [(0, 3, 100), (3, 4, 37)]
+    assert group_units([37], 100, False) == [(0, 1, 37)] and group_units([37], 100, True) == [(0, 1, 100)]
+    assert group_units([], 100, True) == [] and group_units([], 100, False) == []
+    assert group_units([100, 60, 60, 100], 100, False) == [(0, 1, 100), (1, 3, 60), (3, 4, 100)]
