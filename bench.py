@@ -197,7 +197,7 @@ class MdxWorkload:
         a = self.args
         return {"workload": f"UVR-MDX-NET-Inst_HQ_3 topology (ConvTDFNet g=48, dim_f=3072, n_fft=6144), {self.minutes:g}-min 44.1 kHz stereo synthetic, segment_size=256, overlap=0.25, 68 chunks/step"
                 if self.minutes == 5.0 else f"UVR-MDX-NET-Inst_HQ_3 topology, {self.minutes:g}-min 44.1 kHz stereo synthetic, segment_size=256, overlap=0.25",
-                "batch": a.batch, "precision": a.precision, "l2": "inputs larger than L2 (106 MB track, 0.6-4.8 GB activations per forward)",
+                "batch": a.batch, "precision": a.precision, "l2": f"inputs larger than L2 (106 MB track, {0.15 * a.batch:.1f}-{1.2 * a.batch:.1f} GB activations per forward)",
                 "parallelism": f"time-sharded chunks x{a.gpus}" if a.gpus > 1 else "single GPU"}
 
     def setup(self, ctx):
@@ -697,7 +697,7 @@ def main():
     ap.add_argument("--workload", default="mdx", choices=sorted(WORKLOADS))
     ap.add_argument("--also", default="htdemucs_ft", help="second workload measured by the default (mdx) run and reported under \"also\" (none = skip)")
     ap.add_argument("--minutes", type=float, default=None, help="track length (default: the BASELINE config's)")
-    ap.add_argument("--batch", type=int, default=None, help="MDX chunks per network forward (default 4; with N > 1 all the chunks of a rank, up to 12)")
+    ap.add_argument("--batch", type=int, default=None, help="MDX chunks per network forward (default 8; with N > 1 all the chunks of a rank, up to 12)")
     ap.add_argument("--demucs-batch", type=int, default=13, help="HTDemucs segments per forward")
     ap.add_argument("--tracks", type=int, default=32, help="VR workload: tracks in the batch")
     ap.add_argument("--precision", type=int, default=1)
@@ -705,7 +705,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     if args.batch is None:
-        args.batch = 4 if args.gpus == 1 else min(12, -(-68 // args.gpus))
+        args.batch = 8 if args.gpus == 1 else min(12, -(-68 // args.gpus))  # 8 chunks per forward measured 2 % faster than 4 on one box (1242 vs 1215)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))  # synthetic weights + programme material generators, and the cpu legs
     if args.impl == "reference":
         return run_reference(args)
